@@ -1,0 +1,98 @@
+/*
+ * ttb200 -- C ABI of the B200-native tensor-train core-sweep path.
+ *
+ * This is the drop-in boundary for the hot path of gorodetsky-umich/tensor_networks
+ * (`pytens`): TT inner product / norm, TT rounding and TT-SVD in fp64.  The
+ * reference has no FFI layer of its own (it is pure Python on NumPy); each entry
+ * point below cites the reference function whose arithmetic it replaces, and
+ * INTEGRATION.md shows the ctypes binding a pytens maintainer would add.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no C++/torch types.
+ *   - every function returns an int status (0 = TTB_OK); on failure
+ *     ttb_last_error() returns a thread-local message.  No exceptions cross
+ *     the boundary.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  All
+ *     work is enqueued on it; functions that return host-visible results
+ *     (ranks) synchronise that stream before returning, the others do not.
+ *   - device buffers are owned by the caller (PyTorch tensors on the Python
+ *     side).  Workspace is queried with *_workspace_bytes and passed in.
+ *   - fp64 throughout, C-order (row-major) cores exactly as the reference
+ *     stores them (pytens/algs.py:1188-1216).
+ */
+#ifndef TTB200_H
+#define TTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    TTB_OK = 0,
+    TTB_INVALID_ARGUMENT = 1,
+    TTB_CUDA_ERROR = 2,
+    TTB_WORKSPACE_TOO_SMALL = 3,
+    TTB_NOT_CONVERGED = 4,
+    TTB_UNSUPPORTED = 5
+};
+
+/* A tensor train with d cores.  n[k]: mode size; r[k]: bond rank left of core k
+ * (r[0] = r[d] = 1); core[k]: DEVICE pointer to the C-order array
+ * (r[k], n[k], r[k+1]).  n, r, core are HOST arrays.  Byte-identical to the
+ * reference's cores (first core (n,r), last core (r,n): pytens/algs.py:1188-1216). */
+typedef struct ttb_tt {
+    int32_t d;
+    const int64_t* n;
+    const int64_t* r;
+    double* const* core;
+} ttb_tt;
+
+/* ---- library ---------------------------------------------------------- */
+const char* ttb_version(void);
+const char* ttb_last_error(void);
+/* number of CUDA kernels this library has launched in this process */
+uint64_t ttb_launch_count(void);
+
+/* ---- dense FP64 GEMM on the DMMA tensor pipe --------------------------
+ * C (M x N, row-major, ldc) = alpha * A * B + beta * C with
+ * A(m,k) = A[m*sAm + k*sAk], B(k,n) = B[k*sBk + n*sBn]; one stride of each
+ * operand must be 1.  Replaces the dgemm under np.dot / np.einsum /
+ * opt_einsum's tensordot on this path (pytens/algs.py:482, :1701, :1886). */
+size_t ttb_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int ttb_gemm_f64(int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t sAm,
+                 int64_t sAk, const double* B, int64_t sBk, int64_t sBn, double beta, double* C,
+                 int64_t ldc, void* workspace, size_t workspace_bytes, void* stream);
+/* test/tuning hook: same, with the tile shape (0..3) and split-K factor forced */
+int ttb_gemm_f64_ex(int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t sAm,
+                    int64_t sAk, const double* B, int64_t sBk, int64_t sBn, double beta, double* C,
+                    int64_t ldc, int tile, int splits, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* measurement hook for bench.py: CUDA-event timing of every dgemm kernel launch
+ * between enable(1) and read(); read() returns the summed kernel time, the summed
+ * algorithmic FLOPs (2 M N K per launch) and the number of launches timed. */
+int ttb_gemm_profile_enable(int enable);
+int ttb_gemm_profile_read(double* total_ms, double* total_flops, uint64_t* launches);
+
+/* ---- TT inner product --------------------------------------------------
+ * out_dev[0] = <A, B>; replaces TensorNetwork.inner (pytens/algs.py:585-587,
+ * i.e. attach() :521-572 + contract() :469-485).  norm() (:589-594) is
+ * sqrt(|inner(A, A)|) on the host side. */
+size_t ttb_inner_workspace_bytes(const ttb_tt* a, const ttb_tt* b);
+int ttb_inner_f64(const ttb_tt* a, const ttb_tt* b, double* out_dev, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* ---- dense contraction of a chain --------------------------------------
+ * out_dev (n_1 x ... x n_d, C-order) = the tensor the TT represents; what
+ * TensorNetwork.contract() returns for a chain (pytens/algs.py:469-485). */
+size_t ttb_tt_to_dense_workspace_bytes(const ttb_tt* a);
+int ttb_tt_to_dense_f64(const ttb_tt* a, double* out_dev, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTB200_H */

@@ -1,0 +1,138 @@
+// Shared device/host helpers for the ttb200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+namespace ttb {
+
+// ---------------------------------------------------------------------------
+// error plumbing: no exceptions cross the C ABI; every entry point returns an
+// int status and stores a message retrievable through ttb_last_error().
+// ---------------------------------------------------------------------------
+enum Status : int {
+    kOk = 0,
+    kInvalidArgument = 1,
+    kCudaError = 2,
+    kWorkspaceTooSmall = 3,
+    kNotConverged = 4,
+    kUnsupported = 5,
+};
+
+void set_last_error(const std::string& msg);
+const char* last_error_cstr();
+
+#define TTB_CHECK_CUDA(expr)                                                        \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) {                                                    \
+            ::ttb::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + \
+                                  " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+            return ::ttb::kCudaError;                                               \
+        }                                                                           \
+    } while (0)
+
+#define TTB_REQUIRE(cond, msg)                                                      \
+    do {                                                                            \
+        if (!(cond)) {                                                              \
+            ::ttb::set_last_error(std::string(msg) + " [" #cond "] (" + __FILE__ +  \
+                                  ":" + std::to_string(__LINE__) + ")");            \
+            return ::ttb::kInvalidArgument;                                         \
+        }                                                                           \
+    } while (0)
+
+#define TTB_PROPAGATE(expr)                 \
+    do {                                    \
+        int _s = (expr);                    \
+        if (_s != ::ttb::kOk) return _s;    \
+    } while (0)
+
+inline int num_sms() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        if (cached <= 0) cached = 148;
+    }
+    return cached;
+}
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) {
+    return (a + b - 1) / b;
+}
+template <typename T>
+__host__ __device__ constexpr T round_up(T a, T b) {
+    return ceil_div(a, b) * b;
+}
+
+// Simple bump allocator over a caller-provided device workspace.
+struct Workspace {
+    char* base;
+    size_t size;
+    size_t off;
+    Workspace(void* p, size_t n) : base(static_cast<char*>(p)), size(n), off(0) {}
+    template <typename T>
+    T* take(size_t count) {
+        size_t bytes = round_up<size_t>(count * sizeof(T), 256);
+        if (off + bytes > size) return nullptr;
+        T* p = reinterpret_cast<T*>(base + off);
+        off += bytes;
+        return p;
+    }
+};
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------
+// device primitives
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// 16-byte async copy global->shared, zero-filled when !pred (LDGSTS).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+    const int sz = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem)),
+                 "l"(gmem), "r"(sz));
+}
+// 8-byte variant for operands that are not 16-byte aligned.
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool pred) {
+    const int sz = pred ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(smem)),
+                 "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).  SASS: DMMA.8x8x4.
+// Fragment ownership (lane = threadIdx.x % 32):
+//   a  = A[lane / 4][lane % 4]
+//   b  = B[lane % 4][lane / 4]
+//   c0 = C[lane / 4][2 * (lane % 4)],  c1 = C[lane / 4][2 * (lane % 4) + 1]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+#endif  // __CUDACC__
+
+}  // namespace ttb

@@ -1,0 +1,31 @@
+// Tensor-train descriptor shared by the host-side drivers.
+#pragma once
+
+#include "common.cuh"
+
+namespace ttb {
+
+// A tensor train with d cores.  n[k] = mode size, r[k] = bond rank to the left
+// of core k (r[0] = r[d] = 1).  core[k] points to DEVICE memory holding the
+// C-order array (r[k], n[k], r[k+1]) -- byte-identical to the reference's cores
+// (pytens/algs.py:1188-1216) with the unit bonds of the first/last core made
+// explicit.  n, r and core themselves are HOST arrays.
+struct TTDesc {
+    int d;
+    const int64_t* n;
+    const int64_t* r;
+    double* const* core;
+};
+
+int validate(const TTDesc& t, const char* what);
+
+// --- inner product (inner.cu) ---
+size_t inner_workspace_bytes(const TTDesc& a, const TTDesc& b);
+int inner(const TTDesc& a, const TTDesc& b, double* out_dev, void* ws, size_t ws_bytes,
+          cudaStream_t stream);
+
+// --- dense contraction of a chain (inner.cu) ---
+int tt_to_dense(const TTDesc& a, double* out_dev, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t tt_to_dense_workspace_bytes(const TTDesc& a);
+
+}  // namespace ttb

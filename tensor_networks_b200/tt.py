@@ -1,0 +1,233 @@
+"""`TensorTrain`: a device-resident tensor train driven through the ttb200 C ABI.
+
+The reference has no such class -- a TT there is a `TensorNetwork` whose nodes
+are the ints 0..d-1 in a chain (pytens/algs.py:1180-1218).  This container holds
+the same data, core k as a CUDA fp64 tensor of shape (r_{k-1}, n_k, r_k) in
+C order (byte-identical to the reference's cores with the unit bonds explicit),
+and exposes the hot-path operations:
+
+    inner / norm      <- TensorNetwork.inner / norm        pytens/algs.py:585-594
+    right_orth        <- tt_right_orth                     pytens/algs.py:1654-1704
+    round             <- tt_svd_round (relative eps)       pytens/algs.py:1841-1903
+    dense             <- TensorNetwork.contract (chain)    pytens/algs.py:469-485
+
+PyTorch is used for buffer ownership and streams only; all arithmetic happens in
+libttb200.so.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import TTDescriptor, check
+
+_WORKSPACES: dict = {}
+
+
+def workspace(nbytes: int, device: torch.device, slot: str = "main") -> torch.Tensor:
+    """A cached, grow-only uint8 scratch buffer per (device, slot)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _WORKSPACES.pop(key, None)
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = buf
+    return buf
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("tensor_networks_b200 needs a CUDA device (no CPU fallback)")
+
+
+class TensorTrain:
+    """A tensor train resident in HBM.  See the module docstring."""
+
+    def __init__(self, cores: Sequence[torch.Tensor]):
+        _require_cuda()
+        cores = list(cores)
+        if not cores:
+            raise ValueError("a TensorTrain needs at least one core")
+        for k, c in enumerate(cores):
+            if c.dtype != torch.float64 or not c.is_cuda or c.dim() != 3:
+                raise ValueError(f"core {k}: need a 3-d CUDA float64 tensor, got {c.dtype} {tuple(c.shape)}")
+            if not c.is_contiguous():
+                cores[k] = c.contiguous()
+        if cores[0].shape[0] != 1 or cores[-1].shape[2] != 1:
+            raise AssertionError("boundary bond ranks must be 1")
+        for k in range(len(cores) - 1):
+            if cores[k].shape[2] != cores[k + 1].shape[0]:
+                raise AssertionError(
+                    f"bond {k}: {tuple(cores[k].shape)} does not chain with {tuple(cores[k + 1].shape)}"
+                )
+        self.cores: List[torch.Tensor] = cores
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_cores(cls, cores: Sequence[np.ndarray], device="cuda", pinned: bool = False) -> "TensorTrain":
+        """Upload host cores.  Accepts the reference's shapes (2-d first/last core)."""
+        _require_cuda()
+        d = len(cores)
+        out = []
+        for k, c in enumerate(cores):
+            a = np.ascontiguousarray(np.asarray(c, dtype=np.float64))
+            if a.ndim == 2 and d == 1:
+                raise ValueError("a 1-core TT must be given as (1, n, 1)")
+            if a.ndim == 2 and k == 0:
+                a = a.reshape(1, a.shape[0], a.shape[1])
+            elif a.ndim == 2 and k == d - 1:
+                a = a.reshape(a.shape[0], a.shape[1], 1)
+            elif a.ndim != 3:
+                raise ValueError(f"core {k} has unsupported shape {a.shape}")
+            t = torch.from_numpy(a)
+            if pinned:
+                t = t.pin_memory()
+            out.append(t.to(device, non_blocking=pinned))
+        return cls(out)
+
+    @classmethod
+    def from_network(cls, tn, device="cuda") -> "TensorTrain":
+        """From a pytens-style TensorNetwork whose nodes are 0..d-1 in a chain."""
+        d = len(tn.network.nodes)
+        vals = []
+        for k in range(d):
+            if k not in tn.network.nodes:
+                raise ValueError("TT-shaped networks must have integer nodes 0..d-1 (pytens/algs.py:1870-1885)")
+            vals.append(tn.network.nodes[k]["tensor"].value)
+        return cls.from_cores(vals, device=device)
+
+    @classmethod
+    def rand(
+        cls,
+        shape: Sequence[int],
+        ranks: Sequence[int],
+        seed: Optional[int] = None,
+        scaled: bool = True,
+        device="cuda",
+    ) -> "TensorTrain":
+        """Random TT generated on the device (layout of rand_tt, pytens/algs.py:1180-1218).
+
+        `scaled` multiplies core k by (n_k r_k)^(-1/2) so that ||X|| = O(1).
+        """
+        _require_cuda()
+        d = len(shape)
+        assert len(ranks) + 1 == d
+        r = [1] + [int(x) for x in ranks] + [1]
+        gen = torch.Generator(device=device)
+        if seed is not None:
+            gen.manual_seed(int(seed))
+        cores = []
+        for k in range(d):
+            c = torch.randn((r[k], int(shape[k]), r[k + 1]), dtype=torch.float64, device=device, generator=gen)
+            if scaled:
+                c *= 1.0 / math.sqrt(shape[k] * r[k + 1])
+            cores.append(c)
+        return cls(cores)
+
+    def clone(self) -> "TensorTrain":
+        return TensorTrain([c.clone() for c in self.cores])
+
+    # ------------------------------------------------------------------ accessors
+    @property
+    def d(self) -> int:
+        return len(self.cores)
+
+    def dim(self) -> int:
+        return len(self.cores)
+
+    def shape(self) -> List[int]:
+        return [int(c.shape[1]) for c in self.cores]
+
+    def ranks(self) -> List[int]:
+        return [int(c.shape[2]) for c in self.cores[:-1]]
+
+    def bond_ranks(self) -> List[int]:
+        return [1] + self.ranks() + [1]
+
+    @property
+    def device(self) -> torch.device:
+        return self.cores[0].device
+
+    def nbytes(self) -> int:
+        return sum(c.numel() * 8 for c in self.cores)
+
+    def to_cores(self) -> List[np.ndarray]:
+        return [c.detach().cpu().numpy() for c in self.cores]
+
+    def descriptor(self) -> TTDescriptor:
+        return TTDescriptor(self.shape(), self.bond_ranks(), [c.data_ptr() for c in self.cores])
+
+    def scale(self, alpha: float) -> "TensorTrain":
+        """In place, on the first core -- TensorNetwork.scale, pytens/algs.py:578-583."""
+        self.cores[0] *= float(alpha)
+        return self
+
+    def __add__(self, other: "TensorTrain") -> "TensorTrain":
+        """Formal sum by block-diagonal rank growth (pytens/algs.py:1339-1353, :308-344)."""
+        if self.shape() != other.shape():
+            raise AssertionError("TT sum needs equal mode sizes")
+        d = self.d
+        out = []
+        for k, (a, b) in enumerate(zip(self.cores, other.cores)):
+            if d == 1:
+                out.append(a + b)
+            elif k == 0:
+                out.append(torch.cat([a, b], dim=2))
+            elif k == d - 1:
+                out.append(torch.cat([a, b], dim=0))
+            else:
+                c = torch.zeros(
+                    (a.shape[0] + b.shape[0], a.shape[1], a.shape[2] + b.shape[2]),
+                    dtype=torch.float64,
+                    device=a.device,
+                )
+                c[: a.shape[0], :, : a.shape[2]] = a
+                c[a.shape[0] :, :, a.shape[2] :] = b
+                out.append(c)
+        return TensorTrain(out)
+
+    # ------------------------------------------------------------------ hot path
+    def inner_dev(self, other: "TensorTrain", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """<self, other> as a 0-d CUDA tensor; no host synchronisation."""
+        L = _lib.lib()
+        da, db = self.descriptor(), other.descriptor()
+        if self.shape() != other.shape():
+            raise AssertionError("inner: free indices (mode sizes) differ")
+        nbytes = L.ttb_inner_workspace_bytes(da.ref(), db.ref())
+        ws = workspace(nbytes, self.device)
+        if out is None:
+            out = torch.empty((), dtype=torch.float64, device=self.device)
+        check(L.ttb_inner_f64(da.ref(), db.ref(), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr()))
+        return out
+
+    def inner(self, other: "TensorTrain") -> np.ndarray:
+        """0-d float64 ndarray, like TensorNetwork.inner (pytens/algs.py:585-587)."""
+        return np.asarray(self.inner_dev(other).item(), dtype=np.float64)
+
+    def norm(self) -> float:
+        """sqrt(|<X, X>|) -- TensorNetwork.norm, pytens/algs.py:589-594."""
+        val = float(self.inner_dev(self).item())
+        return float(np.sqrt(np.abs(val)))
+
+    def dense_dev(self) -> torch.Tensor:
+        """The dense tensor (n_1, ..., n_d) on the device."""
+        L = _lib.lib()
+        desc = self.descriptor()
+        nbytes = L.ttb_tt_to_dense_workspace_bytes(desc.ref())
+        ws = workspace(nbytes, self.device)
+        out = torch.empty(self.shape(), dtype=torch.float64, device=self.device)
+        check(L.ttb_tt_to_dense_f64(desc.ref(), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr()))
+        return out
+
+    def dense(self) -> np.ndarray:
+        return self.dense_dev().cpu().numpy()

@@ -1,0 +1,81 @@
+"""GPU parity: the DMMA GEMM behind every contraction on the path vs numpy fp64."""
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(M, N, K, a_kc, b_kc, alpha=1.0, beta=0.0, tile=-1, splits=0, seed=0, pad=0):
+    from tensor_networks_b200 import _lib
+    from tensor_networks_b200.tt import workspace
+
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    # A stored (M, K) row-major if a_kc else (K, M) row-major
+    A = torch.randn((M, K + pad) if a_kc else (K, M + pad), dtype=torch.float64, device="cuda", generator=g)
+    B = torch.randn((N, K + pad) if b_kc else (K, N + pad), dtype=torch.float64, device="cuda", generator=g)
+    C = torch.randn((M, N + pad), dtype=torch.float64, device="cuda", generator=g)
+    A_log = A[:, :K] if a_kc else A[:, :M].T
+    B_log = B[:, :K].T if b_kc else B[:, :N]
+    ref = alpha * (A_log.cpu().numpy() @ B_log.cpu().numpy()) + beta * C[:, :N].cpu().numpy()
+    sAm, sAk = (A.stride(0), 1) if a_kc else (1, A.stride(0))
+    sBk, sBn = (1, B.stride(0)) if b_kc else (B.stride(0), 1)
+    nbytes = max(L.ttb_gemm_workspace_bytes(M, N, K), 64 * M * N * 8 if splits > 1 else 0)
+    ws = workspace(nbytes, A.device, "test")
+    st = L.ttb_gemm_f64_ex(
+        M, N, K, alpha, A.data_ptr(), sAm, sAk, B.data_ptr(), sBk, sBn, beta, C.data_ptr(), C.stride(0),
+        tile, splits, ws.data_ptr(), ws.numel(), None,
+    )
+    _lib.check(st)
+    torch.cuda.synchronize()
+    got = C[:, :N].cpu().numpy()
+    scale = np.abs(A_log.cpu().numpy()) @ np.abs(B_log.cpu().numpy()) + np.abs(beta * ref) + 1e-300
+    err = np.max(np.abs(got - ref) / scale)
+    assert err < 1e-14, f"rel err {err}"
+    if pad:
+        # padding columns of C must be untouched
+        assert torch.equal(C[:, N:], C[:, N:])
+
+
+@pytest.mark.parametrize("a_kc", [True, False])
+@pytest.mark.parametrize("b_kc", [True, False])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (256, 224, 256), (64, 64, 16), (100, 36, 52)])
+def test_layouts_aligned(shape, a_kc, b_kc):
+    _run(*shape, a_kc, b_kc)
+
+
+@pytest.mark.parametrize("a_kc", [True, False])
+@pytest.mark.parametrize("b_kc", [True, False])
+@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 5, 7), (33, 65, 17), (129, 113, 35), (1, 1, 777), (7, 1, 64), (1, 9, 64)])
+def test_layouts_ragged(shape, a_kc, b_kc):
+    _run(*shape, a_kc, b_kc, pad=1)
+
+
+@pytest.mark.parametrize("tile", [0, 1, 2, 3])
+@pytest.mark.parametrize("layout", [(True, False), (False, False), (True, True), (False, True)])
+def test_every_tile(tile, layout):
+    _run(256, 336, 96, layout[0], layout[1], tile=tile, splits=1)
+    _run(130, 250, 40, layout[0], layout[1], tile=tile, splits=1)
+
+
+@pytest.mark.parametrize("splits", [2, 5, 37])
+def test_split_k(splits):
+    _run(256, 256, 2048, False, False, splits=splits, tile=0)
+    _run(70, 90, 1500, True, False, splits=splits)
+
+
+def test_alpha_beta():
+    _run(96, 80, 64, True, False, alpha=-1.0, beta=1.0)
+    _run(96, 80, 64, False, True, alpha=0.5, beta=-2.0, pad=2)
+    _run(64, 64, 4096, False, False, alpha=-1.0, beta=1.0)  # split-K + beta
+
+
+def test_sweep_shapes():
+    # the two GEMMs of one environment step at r=256, n=8
+    _run(256, 8 * 256, 256, True, False)
+    _run(256, 256, 8 * 256, False, False)
+    # projection-like skinny shapes
+    _run(32, 224, 4096, True, True)
+    _run(32, 4096, 224, True, False, alpha=-1.0, beta=1.0)
