@@ -92,6 +92,43 @@ size_t ttb_tt_to_dense_workspace_bytes(const ttb_tt* a);
 int ttb_tt_to_dense_f64(const ttb_tt* a, double* out_dev, void* workspace, size_t workspace_bytes,
                         void* stream);
 
+/* ---- TT rounding ---------------------------------------------------------
+ * In-place rounding of the cores of `t` with relative accuracy eps: RQ pass +
+ * left-to-right delta-truncated SVD sweep, delta = eps / sqrt(d-1) * ||X||_F.
+ * Replaces tt_svd_round (pytens/algs.py:1841-1903), which calls tt_right_orth
+ * (:1654-1704) and delta_svd (pytens/utils.py:19-100).  On return core k holds
+ * the C-order array (ranks_out[k], n[k], ranks_out[k+1]) at the start of its
+ * buffer.  max_rank <= 0: unlimited (the reference has no max_rank; when given,
+ * rank = min(rank_eps, max_rank)).  ranks_out: HOST array of d+1 entries.
+ * delta_out (HOST, may be NULL): the absolute delta used.  stats_out (HOST, may
+ * be NULL): {number of SVDs, total Jacobi sweeps, SVDs that hit the sweep cap}.
+ * Synchronises the stream. */
+size_t ttb_round_workspace_bytes(const ttb_tt* t);
+int ttb_round_f64(const ttb_tt* t, double eps, int32_t max_rank, int64_t* ranks_out, double* delta_out,
+                  int32_t* stats_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* One RQ step on core `node` (1 <= node <= d-1): its horizontal unfolding gets
+ * orthonormal rows and R^T is pushed into core node-1.  Replaces tt_right_orth
+ * (pytens/algs.py:1654-1704) including its conventions: an interior core with
+ * n*r_right < r_left keeps its rank and is zero-padded (:1679-1685); the last core
+ * shrinks to min(r, n) (:1695-1697).  new_rank_out (HOST): bond rank left of `node`
+ * after the step. */
+size_t ttb_right_orth_workspace_bytes(const ttb_tt* t, int32_t node);
+int ttb_right_orth_f64(const ttb_tt* t, int32_t node, int64_t* new_rank_out, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* delta-truncated SVD of a dense row-major matrix (m x n) on the device.
+ * Replaces delta_svd (pytens/utils.py:19-100): rank chosen by the tail-energy rule
+ * (drop trailing sigma while their cumulative energy <= delta^2, keep >= 1);
+ * with_normalizing scales delta by ||data||_F first.  Outputs (device):
+ * u (m x rank, compact), s (rank), svt = diag(s) V^T (rank x n, compact);
+ * v of the reference is svt with row i divided by s[i].  info_out (HOST, 4
+ * doubles): rank, delta used, remaining_delta, sum sigma^2.  Synchronises. */
+size_t ttb_delta_svd_workspace_bytes(int64_t m, int64_t n);
+int ttb_delta_svd_f64(const double* data, int64_t m, int64_t n, double delta, int32_t with_normalizing,
+                      int32_t max_rank, double* u_out, double* s_out, double* svt_out, double* info_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,24 @@ def _declare(lib):
     lib.ttb_inner_f64.restype = c_int
     lib.ttb_inner_f64.argtypes = [P(ttb_tt), P(ttb_tt), c_void_p, c_void_p, c_size_t, c_void_p]
 
+    lib.ttb_round_workspace_bytes.restype = c_size_t
+    lib.ttb_round_workspace_bytes.argtypes = [P(ttb_tt)]
+    lib.ttb_round_f64.restype = c_int
+    lib.ttb_round_f64.argtypes = [
+        P(ttb_tt), c_double, c_int32, P(c_int64), P(c_double), P(c_int32), c_void_p, c_size_t, c_void_p,
+    ]
+    lib.ttb_right_orth_workspace_bytes.restype = c_size_t
+    lib.ttb_right_orth_workspace_bytes.argtypes = [P(ttb_tt), c_int32]
+    lib.ttb_right_orth_f64.restype = c_int
+    lib.ttb_right_orth_f64.argtypes = [P(ttb_tt), c_int32, P(c_int64), c_void_p, c_size_t, c_void_p]
+    lib.ttb_delta_svd_workspace_bytes.restype = c_size_t
+    lib.ttb_delta_svd_workspace_bytes.argtypes = [c_int64, c_int64]
+    lib.ttb_delta_svd_f64.restype = c_int
+    lib.ttb_delta_svd_f64.argtypes = [
+        c_void_p, c_int64, c_int64, c_double, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+        P(c_double), c_void_p, c_size_t, c_void_p,
+    ]
+
     lib.ttb_tt_to_dense_workspace_bytes.restype = c_size_t
     lib.ttb_tt_to_dense_workspace_bytes.argtypes = [P(ttb_tt)]
     lib.ttb_tt_to_dense_f64.restype = c_int

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "tt.cuh"
+#include "round.cuh"
 
 namespace {
 inline ttb::TTDesc to_desc(const ttb_tt* t) {
@@ -83,6 +84,74 @@ int ttb_tt_to_dense_f64(const ttb_tt* a, double* out_dev, void* workspace, size_
         return TTB_INVALID_ARGUMENT;
     }
     return ttb::tt_to_dense(to_desc(a), out_dev, workspace, workspace_bytes, as_stream(stream));
+}
+
+size_t ttb_round_workspace_bytes(const ttb_tt* t) {
+    if (!t) return 0;
+    return ttb::round_workspace_bytes(to_desc(t));
+}
+
+int ttb_round_f64(const ttb_tt* t, double eps, int32_t max_rank, int64_t* ranks_out, double* delta_out,
+                  int32_t* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!t) {
+        ttb::set_last_error("ttb_round_f64: null descriptor");
+        return TTB_INVALID_ARGUMENT;
+    }
+    ttb::RoundStats st;
+    const int rc = ttb::round_tt(to_desc(t), eps, max_rank, ranks_out, delta_out, &st, workspace,
+                                 workspace_bytes, as_stream(stream));
+    if (stats_out) {
+        stats_out[0] = st.svds;
+        stats_out[1] = st.jacobi_sweeps;
+        stats_out[2] = st.not_converged;
+    }
+    return rc;
+}
+
+size_t ttb_right_orth_workspace_bytes(const ttb_tt* t, int32_t node) {
+    if (!t || node < 1 || node >= t->d) return 0;
+    return ttb::right_orth_workspace_bytes(t->r[node - 1] * t->n[node - 1], t->r[node],
+                                           t->n[node] * t->r[node + 1]);
+}
+
+int ttb_right_orth_f64(const ttb_tt* t, int32_t node, int64_t* new_rank_out, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    if (!t) {
+        ttb::set_last_error("ttb_right_orth_f64: null descriptor");
+        return TTB_INVALID_ARGUMENT;
+    }
+    const ttb::TTDesc d = to_desc(t);
+    int st = ttb::validate(d, "right_orth");
+    if (st != TTB_OK) return st;
+    if (node < 1 || node >= d.d) {
+        ttb::set_last_error("ttb_right_orth_f64: node must be in 1..d-1");
+        return TTB_INVALID_ARGUMENT;
+    }
+    const bool last = (node == d.d - 1);
+    return ttb::right_orth_step(d.core[node], d.r[node], d.n[node] * d.r[node + 1], d.core[node - 1],
+                                d.r[node - 1] * d.n[node - 1], /*shrink=*/last, new_rank_out, workspace,
+                                workspace_bytes, as_stream(stream));
+}
+
+size_t ttb_delta_svd_workspace_bytes(int64_t m, int64_t n) {
+    if (m <= 0 || n <= 0) return 0;
+    return ttb::trunc_svd_workspace_bytes(m, n);
+}
+
+int ttb_delta_svd_f64(const double* data, int64_t m, int64_t n, double delta, int32_t with_normalizing,
+                      int32_t max_rank, double* u_out, double* s_out, double* svt_out, double* info_out,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    ttb::TruncSvdInfo info{};
+    const double abs_tol = with_normalizing ? 0.0 : 1e-4 * delta;
+    const int rc = ttb::trunc_svd(data, m, n, delta, with_normalizing != 0, max_rank, abs_tol, u_out, svt_out,
+                                  s_out, &info, workspace, workspace_bytes, as_stream(stream));
+    if (rc == TTB_OK && info_out) {
+        info_out[0] = double(info.rank);
+        info_out[1] = info.delta_abs;
+        info_out[2] = info.remaining_delta;
+        info_out[3] = info.fro2;
+    }
+    return rc;
 }
 
 }  // extern "C"

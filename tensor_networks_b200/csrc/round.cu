@@ -1,0 +1,299 @@
+// TT rounding on the device: RQ right-orthogonalisation pass followed by the
+// left-to-right delta-truncated SVD sweep.
+//
+// Follows tt_svd_round / tt_right_orth / delta_svd of the reference
+// (pytens/algs.py:1841-1903, :1654-1704, pytens/utils.py:19-100):
+//   * RQ pass, cores d-1 .. 1: the horizontal unfolding (r_{k-1} x n_k r_k) is
+//     orthonormalised row-wise in place (orth_rows: TSQR Householder panels +
+//     BCGS2) and R^T is pushed into core k-1 with a DMMA GEMM.
+//   * forward pass, cores 0 .. d-2: truncated SVD of the vertical unfolding
+//     (rho_{k-1} n_k x r_k): tall matrices go through orth_rows on the transposed
+//     copy, the small R factor (or a wide unfolding itself) is diagonalised by the
+//     block Jacobi kernel, the rank is chosen on the device by the reference's
+//     tail-energy rule with delta = eps / sqrt(d-1) * ||X||_F taken from the first
+//     core, and the carry diag(s) V^T is contracted into the next core.
+// The only host synchronisations are the convergence word of each Jacobi sweep
+// and the rank of each core (it sizes the next launch).
+#include "round.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "gemm.cuh"
+#include "qr.cuh"
+#include "svd.cuh"
+
+namespace ttb {
+
+namespace {
+
+__global__ void transpose_kernel(const double* __restrict__ in, int64_t rows, int64_t cols, int64_t ldi,
+                                 double* __restrict__ out, int64_t ldo) {
+    __shared__ double tile[32][33];
+    const int64_t c0 = int64_t(blockIdx.x) * 32, r0 = int64_t(blockIdx.y) * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int64_t r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < cols) ? in[r * ldi + c] : 0.0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int64_t c = c0 + i, r = r0 + threadIdx.x;
+        if (c < cols && r < rows) out[c * ldo + r] = tile[threadIdx.x][i];
+    }
+}
+
+int transpose(const double* in, int64_t rows, int64_t cols, int64_t ldi, double* out, int64_t ldo,
+              cudaStream_t stream) {
+    dim3 grid(unsigned(ceil_div<int64_t>(cols, 32)), unsigned(ceil_div<int64_t>(rows, 32)));
+    TTB_REQUIRE(grid.y < 65536, "transpose: too many rows");
+    transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(in, rows, cols, ldi, out, ldo);
+    ++g_launch_count;
+    TTB_CHECK_CUDA(cudaGetLastError());
+    return kOk;
+}
+
+struct HostWords {
+    unsigned long long* conv = nullptr;  // pinned
+    double* info = nullptr;              // pinned, 4 doubles
+};
+int host_words(HostWords* hw) {
+    static HostWords g;
+    if (!g.conv) {
+        void* p = nullptr;
+        TTB_CHECK_CUDA(cudaHostAlloc(&p, 64, cudaHostAllocDefault));
+        g.conv = static_cast<unsigned long long*>(p);
+        g.info = reinterpret_cast<double*>(static_cast<char*>(p) + 16);
+    }
+    *hw = g;
+    return kOk;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// truncated SVD of a contiguous row-major matrix
+// ---------------------------------------------------------------------------
+size_t trunc_svd_workspace_bytes(int64_t m, int64_t c) {
+    const int64_t p = std::min(m, c);
+    size_t b = 0;
+    b += round_up<size_t>(size_t(m) * c * 8, 256);                  // Mt / X
+    b += 4 * round_up<size_t>(size_t(p) * std::max(p, c) * 8, 256); // R, J, Jsel, (spare)
+    b += 4 * round_up<size_t>(size_t(p) * 8, 256) + 1024;           // perm, sigma, nrm2, info/conv
+    b += (m > c) ? orth_rows_workspace_bytes(c, m) : 0;
+    b += round_up<size_t>(gemm_workspace_bytes(m, p, c), 256);
+    return b + 4096;
+}
+
+int trunc_svd(const double* M, int64_t m, int64_t c, double delta, bool with_normalizing, int max_rank,
+              double jacobi_abs_tol, double* U_out, double* SVt_out, double* sigma_out,
+              TruncSvdInfo* res, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    TTB_REQUIRE(M && U_out && SVt_out && res, "trunc_svd: null pointer");
+    TTB_REQUIRE(m >= 1 && c >= 1, "trunc_svd: empty matrix");
+    TTB_REQUIRE(std::min(m, c) <= 8192, "trunc_svd: min(m, n) > 8192 unsupported");
+    const size_t need = trunc_svd_workspace_bytes(m, c);
+    if (ws == nullptr || ws_bytes < need) {
+        set_last_error("trunc_svd: workspace too small, need " + std::to_string(need) + " bytes");
+        return kWorkspaceTooSmall;
+    }
+    HostWords hw;
+    TTB_PROPAGATE(host_words(&hw));
+    const bool tall = m > c;
+    const int p = int(std::min(m, c));  // number of singular values
+    const int q = int(c);               // length of the rows handed to Jacobi
+
+    Workspace W(ws, ws_bytes);
+    double* big = W.take<double>(size_t(m) * c);
+    double* Rm = W.take<double>(size_t(p) * std::max<int64_t>(p, c));
+    double* J = W.take<double>(size_t(p) * std::max<int64_t>(p, c));
+    double* Jsel = W.take<double>(size_t(p) * std::max<int64_t>(p, c));
+    int* perm = W.take<int>(size_t(p) * 2);
+    double* sigma = W.take<double>(p);
+    double* nrm2 = W.take<double>(p);
+    double* info = W.take<double>(8);
+    unsigned long long* conv = W.take<unsigned long long>(8);
+    TTB_REQUIRE(big && Rm && J && Jsel && perm && sigma && nrm2 && info && conv, "trunc_svd: carve failed");
+    const size_t rest = ws_bytes - W.off;
+    void* sub = W.base + W.off;
+
+    double* X;  // rows to rotate (p x q)
+    if (tall) {
+        // M^T (c x m): rows orthonormalised in place, R (c x c) holds M^T = Q^T R  =>  M = Q_col R
+        TTB_PROPAGATE(transpose(M, m, c, c, big, m, stream));
+        TTB_PROPAGATE(orth_rows(big, c, m, m, Rm, c, sub, rest, stream));
+        X = Rm;
+    } else {
+        TTB_CHECK_CUDA(cudaMemcpyAsync(big, M, size_t(m) * c * 8, cudaMemcpyDeviceToDevice, stream));
+        X = big;
+    }
+    int sweeps = 0;
+    const int jst = jacobi_rows(X, p, q, q, J, jacobi_abs_tol, 40, &sweeps, conv, hw.conv, stream);
+    if (jst != kOk && jst != kNotConverged) return jst;
+    TTB_PROPAGATE(svd_select(X, p, q, q, delta, with_normalizing ? 1 : 0, max_rank, perm, sigma, info, nrm2,
+                             stream));
+    TTB_CHECK_CUDA(cudaMemcpyAsync(hw.info, info, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
+    const int rho = int(hw.info[0]);
+    res->rank = rho;
+    res->delta_abs = hw.info[1];
+    res->remaining_delta = hw.info[2];
+    res->fro2 = hw.info[3];
+    res->sweeps = sweeps;
+    res->converged = (jst == kOk);
+    TTB_REQUIRE(rho >= 1 && rho <= p, "trunc_svd: bad rank from selection kernel");
+
+    // carry = diag(s) V^T = selected rotated rows
+    TTB_PROPAGATE(gather_rows(X, q, perm, rho, q, SVt_out, q, false, stream));
+    if (sigma_out)
+        TTB_CHECK_CUDA(cudaMemcpyAsync(sigma_out, sigma, size_t(rho) * 8, cudaMemcpyDeviceToDevice, stream));
+    if (tall) {
+        // U (m x rho) = Q_col (m x c) . Jsel^T (c x rho);  Q_col(i, k) = big[k * m + i]
+        TTB_PROPAGATE(gather_rows(J, p, perm, rho, p, Jsel, p, false, stream));
+        GemmArgs g;
+        g.M = m; g.N = rho; g.K = c;
+        g.A = big; g.sAm = 1; g.sAk = m;
+        g.B = Jsel; g.sBk = 1; g.sBn = p;
+        g.C = U_out; g.ldc = rho;
+        const size_t gneed = gemm_workspace_bytes(m, rho, c);
+        TTB_PROPAGATE(gemm(g, gneed <= rest ? sub : nullptr, gneed <= rest ? rest : 0, stream));
+    } else {
+        // U (m x rho) = J^T[:, sel]  -> U[i][s] = J[perm[s]][i]
+        TTB_PROPAGATE(gather_rows(J, p, perm, rho, p, U_out, rho, true, stream));
+    }
+    return kOk;
+}
+
+// ---------------------------------------------------------------------------
+// one RQ step (tt_right_orth, pytens/algs.py:1654-1704)
+// ---------------------------------------------------------------------------
+size_t right_orth_workspace_bytes(int64_t r_prev_n_prev, int64_t c, int64_t m) {
+    size_t b = 0;
+    b += round_up<size_t>(size_t(c) * c * 8, 256);               // R
+    b += round_up<size_t>(size_t(r_prev_n_prev) * c * 8, 256);   // pushed core k-1
+    b += orth_rows_workspace_bytes(c, m);
+    b += round_up<size_t>(gemm_workspace_bytes(r_prev_n_prev, c, c), 256);
+    return b + 2048;
+}
+
+// core_k: (c x m) row-major, orthonormalised in place.  core_prev: (P x c) row-major,
+// replaced by core_prev . R^T[:, :c_new] stored compactly as (P x c_new).
+// shrink: c_new = min(c, m) (rounding sweep / last core); otherwise c_new = c with the
+// reference's zero padding.
+int right_orth_step(double* core_k, int64_t c, int64_t m, double* core_prev, int64_t P, bool shrink,
+                    int64_t* c_new_out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    const size_t need = right_orth_workspace_bytes(P, c, m);
+    if (ws == nullptr || ws_bytes < need) {
+        set_last_error("right_orth: workspace too small, need " + std::to_string(need) + " bytes");
+        return kWorkspaceTooSmall;
+    }
+    Workspace W(ws, ws_bytes);
+    double* R = W.take<double>(size_t(c) * c);
+    double* pushed = W.take<double>(size_t(P) * c);
+    TTB_REQUIRE(R && pushed, "right_orth: carve failed");
+    const size_t rest = ws_bytes - W.off;
+    void* sub = W.base + W.off;
+
+    TTB_PROPAGATE(orth_rows(core_k, c, m, m, R, c, sub, rest, stream));
+    const int64_t c_new = shrink ? std::min(c, m) : c;
+    GemmArgs g;  // pushed (P x c_new) = core_prev (P x c) . R^T[:, :c_new] ; B(k, n) = R[n][k]
+    g.M = P; g.N = c_new; g.K = c;
+    g.A = core_prev; g.sAm = c; g.sAk = 1;
+    g.B = R; g.sBk = 1; g.sBn = c;
+    g.C = pushed; g.ldc = c_new;
+    TTB_PROPAGATE(gemm(g, sub, rest, stream));
+    TTB_CHECK_CUDA(cudaMemcpyAsync(core_prev, pushed, size_t(P) * c_new * 8, cudaMemcpyDeviceToDevice, stream));
+    if (c_new_out) *c_new_out = c_new;
+    return kOk;
+}
+
+// ---------------------------------------------------------------------------
+// full rounding
+// ---------------------------------------------------------------------------
+size_t round_workspace_bytes(const TTDesc& t) {
+    size_t sub = 0, carry_elems = 1, core_elems = 1;
+    for (int k = 0; k < t.d; ++k) {
+        const int64_t rl = t.r[k], n = t.n[k], rr = t.r[k + 1];
+        core_elems = std::max<size_t>(core_elems, size_t(rl) * n * rr);
+        if (k >= 1) sub = std::max(sub, right_orth_workspace_bytes(t.r[k - 1] * t.n[k - 1], rl, n * rr));
+        if (k < t.d - 1) {
+            sub = std::max(sub, trunc_svd_workspace_bytes(rl * n, rr));
+            carry_elems = std::max<size_t>(carry_elems, size_t(rr) * rr);
+            sub = std::max(sub, round_up<size_t>(gemm_workspace_bytes(rr, t.n[k + 1] * t.r[k + 2], rr), 256));
+        }
+    }
+    return round_up<size_t>(core_elems * 8, 256) + round_up<size_t>(carry_elems * 8, 256) + sub + 4096;
+}
+
+int round_tt(const TTDesc& t, double eps, int max_rank, int64_t* ranks_out, double* delta_out,
+             RoundStats* stats, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    TTB_PROPAGATE(validate(t, "round"));
+    TTB_REQUIRE(ranks_out != nullptr, "round: ranks_out is null");
+    TTB_REQUIRE(eps >= 0.0, "round: eps must be non-negative");
+    const int d = t.d;
+    std::vector<int64_t> r(t.r, t.r + d + 1);
+    if (stats) *stats = RoundStats{};
+    if (d == 1) {
+        ranks_out[0] = ranks_out[1] = 1;
+        if (delta_out) *delta_out = 0.0;
+        return kOk;
+    }
+    const size_t need = round_workspace_bytes(t);
+    if (ws == nullptr || ws_bytes < need) {
+        set_last_error("round: workspace too small, need " + std::to_string(need) + " bytes");
+        return kWorkspaceTooSmall;
+    }
+    Workspace W(ws, ws_bytes);
+    size_t core_elems = 1, carry_elems = 1;
+    for (int k = 0; k < d; ++k) {
+        core_elems = std::max<size_t>(core_elems, size_t(t.r[k]) * t.n[k] * t.r[k + 1]);
+        if (k < d - 1) carry_elems = std::max<size_t>(carry_elems, size_t(t.r[k + 1]) * t.r[k + 1]);
+    }
+    double* tmp = W.take<double>(core_elems);
+    double* SVt = W.take<double>(carry_elems);
+    TTB_REQUIRE(tmp && SVt, "round: carve failed");
+    const size_t rest = ws_bytes - W.off;
+    void* sub = W.base + W.off;
+
+    // ---- RQ pass (pytens/algs.py:1864-1867) ----
+    for (int k = d - 1; k >= 1; --k) {
+        int64_t c_new = r[k];
+        TTB_PROPAGATE(right_orth_step(t.core[k], r[k], t.n[k] * r[k + 1], t.core[k - 1], r[k - 1] * t.n[k - 1],
+                                      /*shrink=*/true, &c_new, sub, rest, stream));
+        r[k] = c_new;
+    }
+
+    // ---- forward truncation sweep (pytens/algs.py:1869-1901) ----
+    double delta_abs = 0.0;
+    for (int k = 0; k < d - 1; ++k) {
+        const int64_t m = r[k] * t.n[k], c = r[k + 1];
+        TruncSvdInfo info{};
+        const bool first = (k == 0);
+        const double dl = first ? eps / std::sqrt(double(d - 1)) : delta_abs;
+        const double abs_tol = first ? 0.0 : 1e-4 * delta_abs;
+        // M = core_k (m x c); U overwrites core_k compactly as (m x rho)
+        TTB_PROPAGATE(trunc_svd(t.core[k], m, c, dl, first, max_rank, abs_tol, t.core[k], SVt, nullptr, &info,
+                                sub, rest, stream));
+        if (first) delta_abs = info.delta_abs;
+        const int64_t rho = info.rank;
+        if (stats) {
+            stats->jacobi_sweeps += info.sweeps;
+            stats->svds += 1;
+            if (!info.converged) stats->not_converged += 1;
+        }
+        // next core: (rho x c) . (c x n r'') -> tmp, then back in place (compact)
+        const int64_t ncols = t.n[k + 1] * r[k + 2];
+        GemmArgs g;
+        g.M = rho; g.N = ncols; g.K = c;
+        g.A = SVt; g.sAm = c; g.sAk = 1;
+        g.B = t.core[k + 1]; g.sBk = ncols; g.sBn = 1;
+        g.C = tmp; g.ldc = ncols;
+        TTB_PROPAGATE(gemm(g, sub, rest, stream));
+        TTB_CHECK_CUDA(cudaMemcpyAsync(t.core[k + 1], tmp, size_t(rho) * ncols * 8, cudaMemcpyDeviceToDevice, stream));
+        r[k + 1] = rho;
+    }
+    for (int k = 0; k <= d; ++k) ranks_out[k] = r[k];
+    if (delta_out) *delta_out = delta_abs;
+    return kOk;
+}
+
+}  // namespace ttb

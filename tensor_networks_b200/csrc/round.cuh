@@ -1,0 +1,44 @@
+// TT rounding drivers; see round.cu.
+#pragma once
+
+#include "common.cuh"
+#include "tt.cuh"
+
+namespace ttb {
+
+struct TruncSvdInfo {
+    int rank;
+    double delta_abs;        // absolute delta used (after optional normalisation)
+    double remaining_delta;  // sqrt(delta^2 - discarded energy), pytens/utils.py:85
+    double fro2;             // sum of sigma^2
+    int sweeps;
+    bool converged;
+};
+
+struct RoundStats {
+    int svds = 0;
+    int jacobi_sweeps = 0;
+    int not_converged = 0;
+};
+
+// delta-truncated SVD of M (m x c, row-major contiguous), the device form of
+// delta_svd (pytens/utils.py:19-100).  U_out (m x rank, ld = rank) and
+// SVt_out = diag(s) V^T (rank x c, ld = c) are written compactly; U_out may alias M.
+// Synchronises the stream (the rank sizes the outputs).
+size_t trunc_svd_workspace_bytes(int64_t m, int64_t c);
+int trunc_svd(const double* M, int64_t m, int64_t c, double delta, bool with_normalizing, int max_rank,
+              double jacobi_abs_tol, double* U_out, double* SVt_out, double* sigma_out,
+              TruncSvdInfo* res, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+// One RQ step (tt_right_orth, pytens/algs.py:1654-1704).
+size_t right_orth_workspace_bytes(int64_t r_prev_n_prev, int64_t c, int64_t m);
+int right_orth_step(double* core_k, int64_t c, int64_t m, double* core_prev, int64_t P, bool shrink,
+                    int64_t* c_new_out, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+// tt_svd_round (pytens/algs.py:1841-1903) in place on the cores of `t`;
+// ranks_out: host array of d+1 bond ranks after rounding.
+size_t round_workspace_bytes(const TTDesc& t);
+int round_tt(const TTDesc& t, double eps, int max_rank, int64_t* ranks_out, double* delta_out,
+             RoundStats* stats, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+}  // namespace ttb

@@ -1,0 +1,459 @@
+// On-device SVD for the truncation step: one-sided block Jacobi on the ROWS of a
+// small matrix (the R factor of the tall-skinny QR, or a wide unfolding itself),
+// followed by the reference's tail-energy rank selection.
+//
+// Replaces np.linalg.svd inside delta_svd (pytens/utils.py:56-68, LAPACK gesdd)
+// and the truncation scan (pytens/utils.py:70-85).  There is no CPU fallback.
+//
+// X (p x q).  Rows are rotated in pairs until mutually orthogonal:
+//        Xrot = J X,   J orthogonal (p x p, accumulated product of rotations)
+// so X = J^T Xrot with Xrot = diag(sigma) V^T up to row order:  U = J^T,
+// sigma_i = ||Xrot[i, :]||, and diag(sigma) V^T -- exactly the carry
+// np.dot(np.diag(s), v) the rounding sweep needs (pytens/algs.py:1878) -- is Xrot
+// itself.  J is orthogonal to machine precision by construction, so the
+// truncated basis stays orthonormal regardless of how small the dropped sigma are.
+//
+// Block scheme: rows are grouped in nb blocks of b; a round-robin tournament
+// gives nb-1 rounds of nb/2 disjoint block pairs per sweep, one CTA per pair.
+// A CTA stages its 2b rows of [X | J] in shared memory, forms the 2b x 2b Gram
+// matrix with DMMA, runs cyclic two-sided Jacobi sweeps on that small matrix
+// (same rotations as one-sided Jacobi on the rows, touching 2b x 2b instead of
+// 2b x (q+p) data), and applies the accumulated rotation to the staged rows with
+// DMMA.  Convergence: largest |g_ij| / sqrt(g_ii g_jj) seen in a sweep.
+#include "svd.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+#include "gemm.cuh"
+
+namespace ttb {
+
+namespace {
+
+constexpr int JB_NT = 512;
+constexpr int JB_NWARP = JB_NT / 32;
+constexpr int JB_MAXR = 32;           // rows per CTA (2b)
+constexpr int JB_GP = JB_MAXR + 1;    // pitch of the small matrices
+
+struct JacobiParams {
+    double* X;
+    int64_t ldx;
+    double* J;  // p x p, ld = p
+    int p, q;
+    int b;        // block size (rows per block); CTA handles 2b rows
+    int nb;       // number of blocks (even)
+    int round;    // tournament round 0..nb-2
+    int qx;       // column offset of the J part in the staged tile (round_up(q, 8))
+    int ncol;     // staged columns (round_up(qx + p, 8))
+    int pitch;    // ncol + 4
+    int inner_sweeps;
+    double tol;       // relative threshold
+    double abs_tol2;  // skip rotation when g_ij^2 <= abs_tol2 * max(g_ii, g_jj)
+    unsigned long long* conv;  // max relative off-diagonal (double bits, non-negative)
+};
+
+__device__ __forceinline__ void rr_pair(int n, int round, int k, int& a, int& b) {
+    // circle method on n (even) players; k = 0..n/2-1
+    if (k == 0) {
+        a = n - 1;
+        b = round;
+    } else {
+        a = (round + k) % (n - 1);
+        b = (round - k + (n - 1)) % (n - 1);
+    }
+    if (a > b) {
+        const int t = a;
+        a = b;
+        b = t;
+    }
+}
+
+__global__ void __launch_bounds__(JB_NT, 1) jacobi_block_kernel(const JacobiParams p) {
+    extern __shared__ __align__(16) double sm[];
+    double* T = sm;  // [R2][pitch]
+    const int R2 = 2 * p.b;
+    double* G = T + size_t(R2) * p.pitch;   // [R2][JB_GP]
+    double* W = G + JB_MAXR * JB_GP;        // [R2][JB_GP]
+    __shared__ double rot_c[JB_MAXR / 2], rot_s[JB_MAXR / 2];
+    __shared__ int rot_i[JB_MAXR / 2], rot_j[JB_MAXR / 2];
+    __shared__ double blk_max;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int bi, bj;
+    rr_pair(p.nb, p.round, blockIdx.x, bi, bj);
+    auto grow = [&](int a) -> int {  // global row of staged row a (may be >= p: padding)
+        return (a < p.b) ? bi * p.b + a : bj * p.b + (a - p.b);
+    };
+
+    // ---- stage rows ----
+    for (int a = warp; a < R2; a += JB_NWARP) {
+        const int gr = grow(a);
+        double* t = T + size_t(a) * p.pitch;
+        const bool live = gr < p.p;
+        const double* xr = p.X + int64_t(gr) * p.ldx;
+        const double* jr = p.J + int64_t(gr) * p.p;
+        for (int k = lane; k < p.qx; k += 32) t[k] = (live && k < p.q) ? xr[k] : 0.0;
+        for (int k = lane; k < p.ncol - p.qx; k += 32) t[p.qx + k] = (live && k < p.p) ? jr[k] : 0.0;
+    }
+    for (int idx = tid; idx < JB_MAXR * JB_GP; idx += JB_NT) {
+        G[idx] = 0.0;
+        W[idx] = 0.0;
+    }
+    if (tid == 0) blk_max = 0.0;
+    __syncthreads();
+    if (tid < R2) W[tid * JB_GP + tid] = 1.0;
+
+    // ---- Gram matrix G = Xs Xs^T over the first q columns (DMMA, split over warps) ----
+    {
+        const int mt = R2 / 8;
+        const int ntiles = mt * mt;
+        const int nslices = max(1, JB_NWARP / ntiles);
+        const int kq = (p.q + 3) & ~3;
+        const int ksteps = kq / 4;
+        for (int job = warp; job < ntiles * nslices; job += JB_NWARP) {
+            const int tile = job % ntiles, slice = job / ntiles;
+            const int a0 = (tile / mt) * 8, b0 = (tile % mt) * 8;
+            if (b0 < a0) continue;  // symmetric: upper tiles only
+            const int ks0 = int((int64_t(ksteps) * slice) / nslices);
+            const int ks1 = int((int64_t(ksteps) * (slice + 1)) / nslices);
+            double c0 = 0.0, c1 = 0.0;
+            const double* ra = T + size_t(a0 + (lane >> 2)) * p.pitch + (lane & 3);
+            const double* rb = T + size_t(b0 + (lane >> 2)) * p.pitch + (lane & 3);
+            for (int ks = ks0; ks < ks1; ++ks) dmma884(c0, c1, ra[ks * 4], rb[ks * 4]);
+            const int r = a0 + (lane >> 2), c = b0 + 2 * (lane & 3);
+            atomicAdd(&G[r * JB_GP + c], c0);
+            atomicAdd(&G[r * JB_GP + c + 1], c1);
+        }
+    }
+    __syncthreads();
+    // mirror the strictly-lower part
+    for (int idx = tid; idx < R2 * R2; idx += JB_NT) {
+        const int r = idx / R2, c = idx % R2;
+        if ((r / 8) > (c / 8)) G[r * JB_GP + c] = G[c * JB_GP + r];
+    }
+    __syncthreads();
+
+    // ---- cyclic two-sided Jacobi sweeps on G, accumulating W (rows) ----
+    const int npairs = R2 / 2;
+    bool any_rot = false;
+    for (int sw = 0; sw < p.inner_sweeps; ++sw) {
+        for (int rd = 0; rd < R2 - 1; ++rd) {
+            if (tid < npairs) {
+                int i, j;
+                rr_pair(R2, rd, tid, i, j);
+                const double a = G[i * JB_GP + i], b = G[j * JB_GP + j], c = G[i * JB_GP + j];
+                double cs = 1.0, sn = 0.0;
+                if (a > 0.0 && b > 0.0 && c != 0.0) {
+                    const double rel = fabs(c) / sqrt(a * b);
+                    const bool small_abs = c * c <= p.abs_tol2 * fmax(a, b);
+                    if (sw == 0 && !small_abs) {
+                        // non-negative doubles order like their bit patterns
+                        atomicMax(reinterpret_cast<unsigned long long*>(&blk_max),
+                                  static_cast<unsigned long long>(__double_as_longlong(rel)));
+                    }
+                    if (rel > p.tol && !small_abs) {
+                        const double zeta = (b - a) / (2.0 * c);
+                        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                        cs = 1.0 / sqrt(1.0 + t * t);
+                        sn = cs * t;
+                    }
+                }
+                rot_i[tid] = i;
+                rot_j[tid] = j;
+                rot_c[tid] = cs;
+                rot_s[tid] = sn;
+            }
+            __syncthreads();
+            // row rotations of G and W: rows (i, j) <- (cs*ri - sn*rj, sn*ri + cs*rj)
+            for (int idx = tid; idx < npairs * R2 * 2; idx += JB_NT) {
+                const int pr = idx / (2 * R2);
+                const int rem = idx % (2 * R2);
+                const double sn = rot_s[pr];
+                if (sn == 0.0) continue;
+                const double cs = rot_c[pr];
+                double* Mx = (rem < R2) ? G : W;
+                const int col = rem % R2;
+                const int i = rot_i[pr], j = rot_j[pr];
+                const double vi = Mx[i * JB_GP + col], vj = Mx[j * JB_GP + col];
+                Mx[i * JB_GP + col] = cs * vi - sn * vj;
+                Mx[j * JB_GP + col] = sn * vi + cs * vj;
+            }
+            __syncthreads();
+            // column rotations of G
+            for (int idx = tid; idx < npairs * R2; idx += JB_NT) {
+                const int pr = idx / R2, row = idx % R2;
+                const double sn = rot_s[pr];
+                if (sn == 0.0) continue;
+                const double cs = rot_c[pr];
+                const int i = rot_i[pr], j = rot_j[pr];
+                const double vi = G[row * JB_GP + i], vj = G[row * JB_GP + j];
+                G[row * JB_GP + i] = cs * vi - sn * vj;
+                G[row * JB_GP + j] = sn * vi + cs * vj;
+            }
+            __syncthreads();
+        }
+    }
+    // did anything rotate?  (W != I)
+    {
+        bool mine = false;
+        for (int idx = tid; idx < R2 * R2; idx += JB_NT) {
+            const int r = idx / R2, c = idx % R2;
+            if (r != c && W[r * JB_GP + c] != 0.0) mine = true;
+        }
+        any_rot = __syncthreads_or(mine);
+    }
+    if (tid == 0 && blk_max > 0.0)
+        atomicMax(p.conv, static_cast<unsigned long long>(__double_as_longlong(blk_max)));
+    if (!any_rot) return;
+
+    // ---- apply: T <- W T  (DMMA; each warp owns slabs of 32 columns, in place) ----
+    {
+        const int mt = R2 / 8;
+        const int nslab = (p.ncol + 31) / 32;
+        for (int slab = warp; slab < nslab; slab += JB_NWARP) {
+            const int n0 = slab * 32;
+            const int nt = min(4, (p.ncol - n0) / 8);
+            double acc[JB_MAXR / 8][4][2];
+#pragma unroll
+            for (int i = 0; i < JB_MAXR / 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int ks = 0; ks < R2 / 4; ++ks) {
+                double a[JB_MAXR / 8], bf[4];
+#pragma unroll
+                for (int i = 0; i < JB_MAXR / 8; ++i)
+                    a[i] = (i < mt) ? W[(8 * i + (lane >> 2)) * JB_GP + ks * 4 + (lane & 3)] : 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    bf[j] = (j < nt) ? T[size_t(ks * 4 + (lane & 3)) * p.pitch + n0 + 8 * j + (lane >> 2)] : 0.0;
+#pragma unroll
+                for (int i = 0; i < JB_MAXR / 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (i < mt && j < nt) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < JB_MAXR / 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (i < mt && j < nt) {
+                        double* dst = T + size_t(8 * i + (lane >> 2)) * p.pitch + n0 + 8 * j + 2 * (lane & 3);
+                        dst[0] = acc[i][j][0];
+                        dst[1] = acc[i][j][1];
+                    }
+        }
+    }
+    __syncthreads();
+
+    // ---- write back ----
+    for (int a = warp; a < R2; a += JB_NWARP) {
+        const int gr = grow(a);
+        if (gr >= p.p) continue;
+        const double* t = T + size_t(a) * p.pitch;
+        double* xr = p.X + int64_t(gr) * p.ldx;
+        double* jr = p.J + int64_t(gr) * p.p;
+        for (int k = lane; k < p.q; k += 32) xr[k] = t[k];
+        for (int k = lane; k < p.p; k += 32) jr[k] = t[p.qx + k];
+    }
+}
+
+__global__ void set_identity_kernel(double* J, int p) {
+    const int64_t total = int64_t(p) * p;
+    for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += int64_t(gridDim.x) * blockDim.x)
+        J[idx] = (idx / p == idx % p) ? 1.0 : 0.0;
+}
+
+// ---- rank selection: the reference's tail-energy rule (pytens/utils.py:70-85) ----
+// info[0] = rank, info[1] = delta (absolute) used, info[2] = remaining_delta,
+// info[3] = sum sigma^2.  perm = row order by descending norm, sigma = sorted values.
+constexpr int SEL_NT = 1024;
+__global__ void __launch_bounds__(SEL_NT) svd_select_kernel(const double* __restrict__ X, int64_t ldx,
+                                                            int p, int q, double delta,
+                                                            int with_normalizing, int max_rank,
+                                                            int* __restrict__ perm,
+                                                            double* __restrict__ sigma,
+                                                            double* __restrict__ info,
+                                                            double* __restrict__ nrm2) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int r = warp; r < p; r += SEL_NT / 32) {
+        const double* x = X + int64_t(r) * ldx;
+        double s = 0.0;
+        for (int k = lane; k < q; k += 32) s = fma(x[k], x[k], s);
+        s = warp_sum(s);
+        if (lane == 0) nrm2[r] = s;
+    }
+    __threadfence_block();
+    __syncthreads();
+    // rank by counting (stable): position = #rows with larger norm, ties by index
+    for (int r = tid; r < p; r += SEL_NT) {
+        const double v = nrm2[r];
+        int pos = 0;
+        for (int o = 0; o < p; ++o) {
+            const double w = nrm2[o];
+            pos += (w > v) || (w == v && o < r);
+        }
+        perm[pos] = r;
+        sigma[pos] = sqrt(v);
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (tid == 0) {
+        // sum of squares in the reference's order (np.sum(s**2) over descending s)
+        double fro2 = 0.0;
+        for (int i = 0; i < p; ++i) fro2 += sigma[i] * sigma[i];
+        double d = delta;
+        if (with_normalizing) d = delta * sqrt(fro2);
+        const double d2 = d * d;
+        double cum = 0.0, used = 0.0;
+        int ndrop = 0;
+        for (int i = p - 1; i >= 0; --i) {  // np.cumsum over the reversed s*s (utils.py:74-82)
+            cum += sigma[i] * sigma[i];
+            if (cum <= d2) {
+                ++ndrop;
+                used = cum;
+            } else {
+                break;
+            }
+        }
+        int rank = p - ndrop;
+        if (rank < 1) rank = 1;
+        if (max_rank > 0 && rank > max_rank) rank = max_rank;
+        info[0] = double(rank);
+        info[1] = d;
+        info[2] = sqrt(fmax(d2 - used, 0.0));
+        info[3] = fro2;
+    }
+}
+
+// dst (rho x cols) rows = src[perm[i]] ; optionally transposed destination (cols x rho)
+__global__ void gather_rows_kernel(const double* __restrict__ src, int64_t lds, const int* __restrict__ perm,
+                                   int rho, int cols, double* __restrict__ dst, int64_t ldd,
+                                   int transpose) {
+    const int64_t total = int64_t(rho) * cols;
+    for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += int64_t(gridDim.x) * blockDim.x) {
+        const int i = int(idx / cols), k = int(idx % cols);
+        const double v = src[int64_t(perm[i]) * lds + k];
+        if (transpose)
+            dst[int64_t(k) * ldd + i] = v;
+        else
+            dst[int64_t(i) * ldd + k] = v;
+    }
+}
+
+int pick_block(int p, int q, int* ncol_out, int* qx_out, size_t* smem_out) {
+    const int qx = round_up(q, 8);
+    const int ncol = round_up(qx + p, 8);
+    const int pitch = ncol + 4;
+    int dev = 0, maxsm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (maxsm <= 0) maxsm = 227 * 1024;
+    for (int R2 = JB_MAXR; R2 >= 8; R2 /= 2) {
+        const size_t bytes = (size_t(R2) * pitch + 2 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
+        if (bytes + 2048 <= size_t(maxsm)) {
+            *ncol_out = ncol;
+            *qx_out = qx;
+            *smem_out = bytes;
+            return R2 / 2;
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+size_t jacobi_workspace_bytes(int p) { return round_up<size_t>(size_t(p) * p * 8, 256) + 1024; }
+
+int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol, int max_sweeps,
+                int* sweeps_out, unsigned long long* conv_dev, unsigned long long* conv_host_pinned,
+                cudaStream_t stream) {
+    TTB_REQUIRE(X && J && conv_dev && conv_host_pinned, "jacobi_rows: null pointer");
+    TTB_REQUIRE(p >= 1 && q >= 1 && ldx >= q, "jacobi_rows: bad extents");
+    {
+        const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(int64_t(p) * p, 256), 1024));
+        set_identity_kernel<<<blocks, 256, 0, stream>>>(J, p);
+        ++g_launch_count;
+        TTB_CHECK_CUDA(cudaGetLastError());
+    }
+    if (sweeps_out) *sweeps_out = 0;
+    if (p == 1) return kOk;
+
+    JacobiParams jp{};
+    size_t smem = 0;
+    const int b_fit = pick_block(p, q, &jp.ncol, &jp.qx, &smem);
+    if (b_fit == 0) {
+        set_last_error("jacobi_rows: matrix too wide for the shared-memory block Jacobi (p + q = " +
+                       std::to_string(p + q) + ")");
+        return kUnsupported;
+    }
+    // rows per block: multiple of 4 (DMMA tiles of 8 rows per pair), no larger than needed
+    int b = b_fit;
+    while (b > 4 && 2 * (b / 2) >= p && (b / 2) % 4 == 0) b /= 2;
+    int nb = ceil_div(p, b);
+    if (nb < 2) nb = 2;
+    if (nb & 1) ++nb;
+    jp.X = X;
+    jp.ldx = ldx;
+    jp.J = J;
+    jp.p = p;
+    jp.q = q;
+    jp.b = b;
+    jp.nb = nb;
+    jp.pitch = jp.ncol + 4;
+    jp.inner_sweeps = (nb == 2) ? 3 : 2;
+    jp.tol = 1e-15 * std::sqrt(double(std::max(q, 16)));
+    jp.abs_tol2 = abs_tol * abs_tol;
+    jp.conv = conv_dev;
+    smem = (size_t(2 * b) * jp.pitch + 2 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
+    static size_t configured = 0;
+    if (smem > configured) {
+        TTB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured = smem;
+    }
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+        TTB_CHECK_CUDA(cudaMemsetAsync(conv_dev, 0, sizeof(unsigned long long), stream));
+        for (int rd = 0; rd < nb - 1; ++rd) {
+            jp.round = rd;
+            jacobi_block_kernel<<<nb / 2, JB_NT, smem, stream>>>(jp);
+            ++g_launch_count;
+        }
+        TTB_CHECK_CUDA(cudaGetLastError());
+        TTB_CHECK_CUDA(cudaMemcpyAsync(conv_host_pinned, conv_dev, sizeof(unsigned long long),
+                                       cudaMemcpyDeviceToHost, stream));
+        TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
+        double mx;
+        static_assert(sizeof(double) == sizeof(unsigned long long), "");
+        memcpy(&mx, conv_host_pinned, sizeof(double));
+        if (sweeps_out) *sweeps_out = sweep + 1;
+        if (mx <= jp.tol) return kOk;
+    }
+    set_last_error("jacobi_rows: not converged after " + std::to_string(max_sweeps) + " sweeps");
+    return kNotConverged;
+}
+
+int svd_select(const double* X, int p, int q, int64_t ldx, double delta, int with_normalizing,
+               int max_rank, int* perm_dev, double* sigma_dev, double* info_dev, double* nrm2_dev,
+               cudaStream_t stream) {
+    TTB_REQUIRE(p <= 16384, "svd_select: too many singular values");
+    svd_select_kernel<<<1, SEL_NT, 0, stream>>>(X, ldx, p, q, delta, with_normalizing, max_rank, perm_dev,
+                                                sigma_dev, info_dev, nrm2_dev);
+    ++g_launch_count;
+    TTB_CHECK_CUDA(cudaGetLastError());
+    return kOk;
+}
+
+int gather_rows(const double* src, int64_t lds, const int* perm_dev, int rho, int cols, double* dst,
+                int64_t ldd, bool transpose, cudaStream_t stream) {
+    if (rho <= 0 || cols <= 0) return kOk;
+    const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(int64_t(rho) * cols, 256), 4096));
+    gather_rows_kernel<<<blocks, 256, 0, stream>>>(src, lds, perm_dev, rho, cols, dst, ldd, transpose ? 1 : 0);
+    ++g_launch_count;
+    TTB_CHECK_CUDA(cudaGetLastError());
+    return kOk;
+}
+
+}  // namespace ttb

@@ -1,0 +1,30 @@
+// On-device Jacobi SVD + tail-energy rank selection; see svd.cu.
+#pragma once
+
+#include "common.cuh"
+
+namespace ttb {
+
+// Rotate the rows of X (p x q, row-major, ld = ldx) until mutually orthogonal:
+// X <- J X_in with J (p x p, row-major, ld = p) orthogonal, initialised here.
+// abs_tol: rotations with |g_ij| <= abs_tol * sqrt(max(g_ii, g_jj)) are skipped
+// (0 = purely relative criterion).  conv_dev / conv_host_pinned: one 8-byte
+// device word and one pinned host word used for the per-sweep convergence read.
+// Synchronises `stream` once per sweep.
+int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol, int max_sweeps,
+                int* sweeps_out, unsigned long long* conv_dev, unsigned long long* conv_host_pinned,
+                cudaStream_t stream);
+
+// Row norms of X -> singular values (descending) with their row permutation, and
+// the reference's truncation rule (pytens/utils.py:70-85):
+//   info[0] = rank, info[1] = absolute delta used, info[2] = remaining_delta, info[3] = sum sigma^2.
+// max_rank <= 0: unlimited.  nrm2_dev: scratch of p doubles.
+int svd_select(const double* X, int p, int q, int64_t ldx, double delta, int with_normalizing,
+               int max_rank, int* perm_dev, double* sigma_dev, double* info_dev, double* nrm2_dev,
+               cudaStream_t stream);
+
+// dst[i, :] = src[perm[i], :] for i < rho (or the transpose of that when `transpose`).
+int gather_rows(const double* src, int64_t lds, const int* perm_dev, int rho, int cols, double* dst,
+                int64_t ldd, bool transpose, cudaStream_t stream);
+
+}  // namespace ttb

@@ -219,6 +219,72 @@ class TensorTrain:
         val = float(self.inner_dev(self).item())
         return float(np.sqrt(np.abs(val)))
 
+    def right_orth(self, node: int) -> "TensorTrain":
+        """One RQ step on core `node`, in place -- tt_right_orth, pytens/algs.py:1654-1704.
+
+        Core `node` gets orthonormal rows (horizontal unfolding) and R^T is pushed into
+        core node-1.  Interior cores keep their rank (zero-padded when n*r_right < r_left),
+        the last core shrinks to min(r, n), exactly like the reference.
+        """
+        import ctypes
+
+        L = _lib.lib()
+        if not 1 <= node <= self.d - 1:
+            raise ValueError("right_orth: node must be in 1..d-1")
+        desc = self.descriptor()
+        nbytes = L.ttb_right_orth_workspace_bytes(desc.ref(), node)
+        ws = workspace(nbytes, self.device)
+        new_rank = ctypes.c_int64(0)
+        check(L.ttb_right_orth_f64(desc.ref(), node, ctypes.byref(new_rank), ws.data_ptr(), ws.numel(), _stream_ptr()))
+        c_new = int(new_rank.value)
+        ck, cp = self.cores[node], self.cores[node - 1]
+        if c_new != ck.shape[0]:
+            self.cores[node] = ck.reshape(-1)[: c_new * ck.shape[1] * ck.shape[2]].view(c_new, ck.shape[1], ck.shape[2])
+            self.cores[node - 1] = cp.reshape(-1)[: cp.shape[0] * cp.shape[1] * c_new].view(cp.shape[0], cp.shape[1], c_new)
+        return self
+
+    def round(self, eps: float, max_rank: Optional[int] = None) -> "TensorTrain":
+        """Round in place with relative accuracy eps -- tt_svd_round, pytens/algs.py:1841-1903.
+
+        RQ pass then left-to-right delta-truncated SVD sweep with
+        delta = eps / sqrt(d-1) * ||X||_F.  `max_rank` (not in the reference) caps every
+        bond: rank = min(rank_eps, max_rank).  Returns self; `self.last_round` holds
+        {"delta", "svds", "jacobi_sweeps", "not_converged"}.
+        """
+        import ctypes
+
+        L = _lib.lib()
+        d = self.d
+        desc = self.descriptor()
+        nbytes = L.ttb_round_workspace_bytes(desc.ref())
+        ws = workspace(nbytes, self.device)
+        ranks = (ctypes.c_int64 * (d + 1))()
+        delta = ctypes.c_double(0.0)
+        stats = (ctypes.c_int32 * 3)()
+        check(
+            L.ttb_round_f64(
+                desc.ref(), float(eps), int(max_rank) if max_rank else 0, ranks, ctypes.byref(delta), stats,
+                ws.data_ptr(), ws.numel(), _stream_ptr(),
+            )
+        )
+        new = []
+        for k, c in enumerate(self.cores):
+            rl, n, rr = int(ranks[k]), int(c.shape[1]), int(ranks[k + 1])
+            new.append(c.reshape(-1)[: rl * n * rr].view(rl, n, rr))
+        self.cores = new
+        self.last_round = {
+            "delta": float(delta.value),
+            "svds": int(stats[0]),
+            "jacobi_sweeps": int(stats[1]),
+            "not_converged": int(stats[2]),
+        }
+        return self
+
+    def compact(self) -> "TensorTrain":
+        """Re-own the cores (drop the slack left in the buffers by an in-place rounding)."""
+        self.cores = [c.clone() for c in self.cores]
+        return self
+
     def dense_dev(self) -> torch.Tensor:
         """The dense tensor (n_1, ..., n_d) on the device."""
         L = _lib.lib()
