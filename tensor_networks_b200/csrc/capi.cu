@@ -142,7 +142,7 @@ int ttb_delta_svd_f64(const double* data, int64_t m, int64_t n, double delta, in
                       int32_t max_rank, double* u_out, double* s_out, double* svt_out, double* info_out,
                       void* workspace, size_t workspace_bytes, void* stream) {
     ttb::TruncSvdInfo info{};
-    const double abs_tol = with_normalizing ? 0.0 : 1e-4 * delta;
+    const double abs_tol = 0.0;  // full-accuracy SVD for the stand-alone entry point
     const int rc = ttb::trunc_svd(data, m, n, delta, with_normalizing != 0, max_rank, abs_tol, u_out, svt_out,
                                   s_out, &info, workspace, workspace_bytes, as_stream(stream));
     if (rc == TTB_OK && info_out) {

@@ -263,17 +263,22 @@ int round_tt(const TTDesc& t, double eps, int max_rank, int64_t* ranks_out, doub
     }
 
     // ---- forward truncation sweep (pytens/algs.py:1869-1901) ----
-    double delta_abs = 0.0;
+    double delta_abs = 0.0, fro = 0.0;
     for (int k = 0; k < d - 1; ++k) {
         const int64_t m = r[k] * t.n[k], c = r[k + 1];
         TruncSvdInfo info{};
         const bool first = (k == 0);
         const double dl = first ? eps / std::sqrt(double(d - 1)) : delta_abs;
-        const double abs_tol = first ? 0.0 : 1e-4 * delta_abs;
+        // rotations that cannot move more than ~1e-14 ||X|| of energy are skipped (rows at
+        // rounding-noise level); far below the 1e-10 parity gate on the reconstruction error
+        const double abs_tol = first ? 0.0 : 1e-14 * fro;
         // M = core_k (m x c); U overwrites core_k compactly as (m x rho)
         TTB_PROPAGATE(trunc_svd(t.core[k], m, c, dl, first, max_rank, abs_tol, t.core[k], SVt, nullptr, &info,
                                 sub, rest, stream));
-        if (first) delta_abs = info.delta_abs;
+        if (first) {
+            delta_abs = info.delta_abs;
+            fro = std::sqrt(info.fro2);
+        }
         const int64_t rho = info.rank;
         if (stats) {
             stats->jacobi_sweeps += info.sweeps;
