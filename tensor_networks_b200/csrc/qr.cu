@@ -49,18 +49,40 @@ struct LeafGeom {
 // One Householder step j on the tile As[c][i] (c < ww vectors, i < hh elements):
 // annihilates As[j][j+1..], leaves beta on the diagonal, normalised v below it,
 // and applies the reflection to vectors j+1..ww-1.  Must be called by all threads.
-__device__ __forceinline__ void house_step(double* As, int ww, int hh, int j, double* sdot,
-                                           double* arow, double* tau_s) {
+__device__ __forceinline__ void house_step(double* __restrict__ As, int ww, int hh, int j,
+                                           double* __restrict__ sdot, double* __restrict__ arow,
+                                           double* __restrict__ tau_s) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* xj = As + j * QR_PITCH;
-    for (int c = j + warp; c < ww; c += QR_NWARP) {
-        const double* xc = As + c * QR_PITCH;
-        double s = 0.0;
-        for (int i = j + lane; i < hh; i += 32) s = fma(xj[i], xc[i], s);
-        s = warp_sum(s);
+    {
+        // each warp owns vectors c = j + warp + 8 t (t < 4); partial dots first, then the
+        // four shuffle reductions interleaved so their latencies overlap
+        constexpr int NC = QR_W / QR_NWARP;
+        double s[NC];
+#pragma unroll
+        for (int t = 0; t < NC; ++t) s[t] = 0.0;
+        for (int i = j + lane; i < hh; i += 32) {
+            const double x = xj[i];
+#pragma unroll
+            for (int t = 0; t < NC; ++t) {
+                const int c = j + warp + QR_NWARP * t;
+                if (c < ww) s[t] = fma(x, As[c * QR_PITCH + i], s[t]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int t = 0; t < NC; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], o);
+        }
         if (lane == 0) {
-            sdot[c] = s;
-            arow[c] = xc[j];
+#pragma unroll
+            for (int t = 0; t < NC; ++t) {
+                const int c = j + warp + QR_NWARP * t;
+                if (c < ww) {
+                    sdot[c] = s[t];
+                    arow[c] = As[c * QR_PITCH + j];
+                }
+            }
         }
     }
     __syncthreads();
@@ -77,9 +99,19 @@ __device__ __forceinline__ void house_step(double* As, int ww, int hh, int j, do
     const int t = tid;
     if (t >= j && t < hh) {
         const double ut = (t == j) ? (alpha - beta) : xj[t];
-        for (int c = j + 1; c < ww; ++c) {
-            const double f = (sdot[c] - beta * arow[c]) * inv;
-            As[c * QR_PITCH + t] = fma(-ut, f, As[c * QR_PITCH + t]);
+        const double uti = -ut * inv;
+        // batches of 8 vectors: all loads first, then the stores (no load waits on a store)
+        for (int c0 = j + 1; c0 < ww; c0 += 8) {
+            double f[8], v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = min(c0 + u, ww - 1);
+                f[u] = sdot[c] - beta * arow[c];
+                v[u] = As[c * QR_PITCH + t];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (c0 + u < ww) As[(c0 + u) * QR_PITCH + t] = fma(uti, f[u], v[u]);
         }
         if (t == j) {
             As[j * QR_PITCH + j] = beta;
@@ -92,27 +124,55 @@ __device__ __forceinline__ void house_step(double* As, int ww, int hh, int j, do
 }
 
 // Apply H_j = I - tau v v^T (v from As[j][j..], v_j = 1) to the ww vectors of Bs.
-__device__ __forceinline__ void house_apply(const double* As, double* Bs, int ww, int hh, int j,
-                                            double tau, double* sdot) {
+__device__ __forceinline__ void house_apply(const double* __restrict__ As, double* __restrict__ Bs,
+                                            int ww, int hh, int j, double tau,
+                                            double* __restrict__ sdot) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tau == 0.0) return;  // uniform
     const double* vj = As + j * QR_PITCH;
-    for (int c = warp; c < ww; c += QR_NWARP) {
-        const double* bc = Bs + c * QR_PITCH;
-        double s = 0.0;
+    {
+        constexpr int NC = QR_W / QR_NWARP;
+        double s[NC];
+#pragma unroll
+        for (int t = 0; t < NC; ++t) s[t] = 0.0;
         for (int i = j + lane; i < hh; i += 32) {
             const double v = (i == j) ? 1.0 : vj[i];
-            s = fma(v, bc[i], s);
+#pragma unroll
+            for (int t = 0; t < NC; ++t) {
+                const int c = warp + QR_NWARP * t;
+                if (c < ww) s[t] = fma(v, Bs[c * QR_PITCH + i], s[t]);
+            }
         }
-        s = warp_sum(s);
-        if (lane == 0) sdot[c] = s;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int t = 0; t < NC; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int t = 0; t < NC; ++t) {
+                const int c = warp + QR_NWARP * t;
+                if (c < ww) sdot[c] = s[t];
+            }
+        }
     }
     __syncthreads();
     const int t = tid;
     if (t >= j && t < hh) {
         const double vt = (t == j) ? 1.0 : vj[t];
-        const double tv = tau * vt;
-        for (int c = 0; c < ww; ++c) Bs[c * QR_PITCH + t] = fma(-tv, sdot[c], Bs[c * QR_PITCH + t]);
+        const double tv = -tau * vt;
+        for (int c0 = 0; c0 < ww; c0 += 8) {
+            double f[8], v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = min(c0 + u, ww - 1);
+                f[u] = sdot[c];
+                v[u] = Bs[c * QR_PITCH + t];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (c0 + u < ww) Bs[(c0 + u) * QR_PITCH + t] = fma(tv, f[u], v[u]);
+        }
     }
     __syncthreads();
 }
@@ -340,9 +400,12 @@ __global__ void zero_rows_kernel(double* X, int64_t rows, int64_t cols, int64_t 
         X[(idx / cols) * ld + (idx % cols)] = 0.0;
 }
 
+// gemm_ws is a recommendation (split-K partials); gemm() degrades gracefully with less,
+// so only `required()` is enforced.
 struct OrthLayout {
     size_t c1, c2, r1, r2, tsqr, gemm_ws;
-    size_t total() const { return (c1 + c2 + r1 + r2 + tsqr) * 8 + round_up<size_t>(gemm_ws, 256) + 6 * 256; }
+    size_t required() const { return (c1 + c2 + r1 + r2 + tsqr) * 8 + 6 * 256; }
+    size_t total() const { return required() + round_up<size_t>(gemm_ws, 256); }
 };
 
 OrthLayout orth_layout(int64_t c, int64_t m) {
@@ -350,7 +413,8 @@ OrthLayout orth_layout(int64_t c, int64_t m) {
     L.c1 = L.c2 = size_t(QR_W) * size_t(std::max<int64_t>(c, 1));
     L.r1 = L.r2 = QR_W * QR_W;
     L.tsqr = tsqr_scratch_doubles(m);
-    L.gemm_ws = std::max(gemm_workspace_bytes(QR_W, c, m), gemm_workspace_bytes(c, c, m));
+    L.gemm_ws = std::min<size_t>(std::max(gemm_workspace_bytes(QR_W, c, m), gemm_workspace_bytes(c, c, m)),
+                                 size_t(64) << 20);
     return L;
 }
 
@@ -366,8 +430,8 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
     TTB_REQUIRE(M && R, "orth_rows: null pointer");
     TTB_REQUIRE(c >= 1 && m >= 1 && ldm >= m && ldr >= c, "orth_rows: bad extents");
     const OrthLayout L = orth_layout(c, m);
-    if (ws == nullptr || ws_bytes < L.total()) {
-        set_last_error("orth_rows: workspace too small, need " + std::to_string(L.total()) + " bytes");
+    if (ws == nullptr || ws_bytes < L.required()) {
+        set_last_error("orth_rows: workspace too small, need " + std::to_string(L.required()) + " bytes");
         return kWorkspaceTooSmall;
     }
     Workspace W(ws, ws_bytes);
@@ -376,8 +440,9 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
     double* R1 = W.take<double>(L.r1);
     double* R2 = W.take<double>(L.r2);
     double* tsq = W.take<double>(L.tsqr);
-    void* gws = L.gemm_ws ? W.take<char>(L.gemm_ws) : nullptr;
     TTB_REQUIRE(C1 && C2 && R1 && R2 && tsq, "orth_rows: workspace carve failed");
+    void* gws = W.base + W.off;
+    const size_t gws_bytes = ws_bytes - W.off;
 
     TTB_CHECK_CUDA(cudaMemsetAsync(R, 0, size_t(c - 1) * ldr * 8 + size_t(c) * 8, stream));
     const int64_t kmax = std::min(c, m);  // at most m orthonormal vectors of length m
@@ -395,14 +460,14 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                 g.A = P; g.sAm = ldm; g.sAk = 1;
                 g.B = M; g.sBk = 1; g.sBn = ldm;
                 g.C = Cb; g.ldc = j0;
-                TTB_PROPAGATE(gemm(g, gws, L.gemm_ws, stream));
+                TTB_PROPAGATE(gemm(g, gws, gws_bytes, stream));
                 GemmArgs u;  // P -= C . Qp
                 u.M = w; u.N = m; u.K = j0;
                 u.A = Cb; u.sAm = j0; u.sAk = 1;
                 u.B = M; u.sBk = ldm; u.sBn = 1;
                 u.C = P; u.ldc = ldm;
                 u.alpha = -1.0; u.beta = 1.0;
-                TTB_PROPAGATE(gemm(u, gws, L.gemm_ws, stream));
+                TTB_PROPAGATE(gemm(u, gws, gws_bytes, stream));
             }
             TTB_PROPAGATE(tsqr_panel(P, w, m, ldm, Rb, w, tsq, stream));
         }
@@ -421,7 +486,7 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
         g.A = M; g.sAm = ldm; g.sAk = 1;
         g.B = M + kmax * ldm; g.sBk = 1; g.sBn = ldm;
         g.C = R + kmax; g.ldc = ldr;
-        TTB_PROPAGATE(gemm(g, gws, L.gemm_ws, stream));
+        TTB_PROPAGATE(gemm(g, gws, gws_bytes, stream));
         const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(extra * m, 256), 2048));
         zero_rows_kernel<<<blocks, 256, 0, stream>>>(M + kmax * ldm, extra, m, ldm);
         ++g_launch_count;

@@ -74,16 +74,20 @@ int host_words(HostWords* hw) {
 // ---------------------------------------------------------------------------
 // truncated SVD of a contiguous row-major matrix
 // ---------------------------------------------------------------------------
-size_t trunc_svd_workspace_bytes(int64_t m, int64_t c) {
+namespace {
+constexpr size_t kGemmWsCap = size_t(64) << 20;  // recommended split-K scratch, never required
+size_t trunc_svd_required(int64_t m, int64_t c) {
     const int64_t p = std::min(m, c);
     size_t b = 0;
     b += round_up<size_t>(size_t(m) * c * 8, 256);                  // Mt / X
     b += 4 * round_up<size_t>(size_t(p) * std::max(p, c) * 8, 256); // R, J, Jsel, (spare)
     b += 4 * round_up<size_t>(size_t(p) * 8, 256) + 1024;           // perm, sigma, nrm2, info/conv
     b += (m > c) ? orth_rows_workspace_bytes(c, m) : 0;
-    b += round_up<size_t>(gemm_workspace_bytes(m, p, c), 256);
     return b + 4096;
 }
+}  // namespace
+
+size_t trunc_svd_workspace_bytes(int64_t m, int64_t c) { return trunc_svd_required(m, c) + kGemmWsCap; }
 
 int trunc_svd(const double* M, int64_t m, int64_t c, double delta, bool with_normalizing, int max_rank,
               double jacobi_abs_tol, double* U_out, double* SVt_out, double* sigma_out,
@@ -91,7 +95,7 @@ int trunc_svd(const double* M, int64_t m, int64_t c, double delta, bool with_nor
     TTB_REQUIRE(M && U_out && SVt_out && res, "trunc_svd: null pointer");
     TTB_REQUIRE(m >= 1 && c >= 1, "trunc_svd: empty matrix");
     TTB_REQUIRE(std::min(m, c) <= 8192, "trunc_svd: min(m, n) > 8192 unsupported");
-    const size_t need = trunc_svd_workspace_bytes(m, c);
+    const size_t need = trunc_svd_required(m, c);
     if (ws == nullptr || ws_bytes < need) {
         set_last_error("trunc_svd: workspace too small, need " + std::to_string(need) + " bytes");
         return kWorkspaceTooSmall;
@@ -154,8 +158,7 @@ int trunc_svd(const double* M, int64_t m, int64_t c, double delta, bool with_nor
         g.A = big; g.sAm = 1; g.sAk = m;
         g.B = Jsel; g.sBk = 1; g.sBn = p;
         g.C = U_out; g.ldc = rho;
-        const size_t gneed = gemm_workspace_bytes(m, rho, c);
-        TTB_PROPAGATE(gemm(g, gneed <= rest ? sub : nullptr, gneed <= rest ? rest : 0, stream));
+        TTB_PROPAGATE(gemm(g, sub, rest, stream));
     } else {
         // U (m x rho) = J^T[:, sel]  -> U[i][s] = J[perm[s]][i]
         TTB_PROPAGATE(gather_rows(J, p, perm, rho, p, U_out, rho, true, stream));
@@ -166,13 +169,18 @@ int trunc_svd(const double* M, int64_t m, int64_t c, double delta, bool with_nor
 // ---------------------------------------------------------------------------
 // one RQ step (tt_right_orth, pytens/algs.py:1654-1704)
 // ---------------------------------------------------------------------------
-size_t right_orth_workspace_bytes(int64_t r_prev_n_prev, int64_t c, int64_t m) {
+namespace {
+size_t right_orth_required(int64_t r_prev_n_prev, int64_t c, int64_t m) {
     size_t b = 0;
     b += round_up<size_t>(size_t(c) * c * 8, 256);               // R
     b += round_up<size_t>(size_t(r_prev_n_prev) * c * 8, 256);   // pushed core k-1
     b += orth_rows_workspace_bytes(c, m);
-    b += round_up<size_t>(gemm_workspace_bytes(r_prev_n_prev, c, c), 256);
     return b + 2048;
+}
+}  // namespace
+
+size_t right_orth_workspace_bytes(int64_t r_prev_n_prev, int64_t c, int64_t m) {
+    return right_orth_required(r_prev_n_prev, c, m) + kGemmWsCap;
 }
 
 // core_k: (c x m) row-major, orthonormalised in place.  core_prev: (P x c) row-major,
@@ -181,7 +189,7 @@ size_t right_orth_workspace_bytes(int64_t r_prev_n_prev, int64_t c, int64_t m) {
 // reference's zero padding.
 int right_orth_step(double* core_k, int64_t c, int64_t m, double* core_prev, int64_t P, bool shrink,
                     int64_t* c_new_out, void* ws, size_t ws_bytes, cudaStream_t stream) {
-    const size_t need = right_orth_workspace_bytes(P, c, m);
+    const size_t need = right_orth_required(P, c, m);
     if (ws == nullptr || ws_bytes < need) {
         set_last_error("right_orth: workspace too small, need " + std::to_string(need) + " bytes");
         return kWorkspaceTooSmall;
@@ -218,7 +226,6 @@ size_t round_workspace_bytes(const TTDesc& t) {
         if (k < t.d - 1) {
             sub = std::max(sub, trunc_svd_workspace_bytes(rl * n, rr));
             carry_elems = std::max<size_t>(carry_elems, size_t(rr) * rr);
-            sub = std::max(sub, round_up<size_t>(gemm_workspace_bytes(rr, t.n[k + 1] * t.r[k + 2], rr), 256));
         }
     }
     return round_up<size_t>(core_elems * 8, 256) + round_up<size_t>(carry_elems * 8, 256) + sub + 4096;
