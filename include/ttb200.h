@@ -129,6 +129,20 @@ int ttb_delta_svd_f64(const double* data, int64_t m, int64_t n, double delta, in
                       int32_t max_rank, double* u_out, double* s_out, double* svt_out, double* info_out,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- TT-SVD of a dense tensor ---------------------------------------------
+ * dense: device, C-order (shape[0] x ... x shape[d-1]), not modified.  Sequential
+ * reshape-and-truncate with delta = eps / sqrt(d-1) * ||X||_F; replaces the
+ * composition TensorNetwork.svd + merge (pytens/algs.py:633-702, :735-761) over
+ * Tensor.svd (:238-274) and delta_svd (pytens/utils.py:19-100, delta formula :53).
+ * Cores are written back to back into `arena` (device, arena_doubles capacity):
+ * core k = C-order (ranks_out[k], shape[k], ranks_out[k+1]) at element offset
+ * sum_{j<k} ranks_out[j]*shape[j]*ranks_out[j+1].  ranks_out: HOST, d+1 entries.
+ * Synchronises the stream. */
+size_t ttb_ttsvd_workspace_bytes(int32_t d, const int64_t* shape);
+int ttb_ttsvd_f64(const double* dense, int32_t d, const int64_t* shape, double eps, int32_t max_rank,
+                  double* arena, size_t arena_doubles, int64_t* ranks_out, double* delta_out,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,6 +96,14 @@ def _declare(lib):
         P(c_double), c_void_p, c_size_t, c_void_p,
     ]
 
+    lib.ttb_ttsvd_workspace_bytes.restype = c_size_t
+    lib.ttb_ttsvd_workspace_bytes.argtypes = [c_int32, P(c_int64)]
+    lib.ttb_ttsvd_f64.restype = c_int
+    lib.ttb_ttsvd_f64.argtypes = [
+        c_void_p, c_int32, P(c_int64), c_double, c_int32, c_void_p, c_size_t, P(c_int64), P(c_double),
+        c_void_p, c_size_t, c_void_p,
+    ]
+
     lib.ttb_tt_to_dense_workspace_bytes.restype = c_size_t
     lib.ttb_tt_to_dense_workspace_bytes.argtypes = [P(ttb_tt)]
     lib.ttb_tt_to_dense_f64.restype = c_int

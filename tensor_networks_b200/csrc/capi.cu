@@ -5,6 +5,7 @@
 #include "gemm.cuh"
 #include "tt.cuh"
 #include "round.cuh"
+#include "ttsvd.cuh"
 
 namespace {
 inline ttb::TTDesc to_desc(const ttb_tt* t) {
@@ -135,7 +136,7 @@ int ttb_right_orth_f64(const ttb_tt* t, int32_t node, int64_t* new_rank_out, voi
 
 size_t ttb_delta_svd_workspace_bytes(int64_t m, int64_t n) {
     if (m <= 0 || n <= 0) return 0;
-    return ttb::trunc_svd_workspace_bytes(m, n);
+    return ttb::trunc_svd_workspace_bytes(m, n, false);
 }
 
 int ttb_delta_svd_f64(const double* data, int64_t m, int64_t n, double delta, int32_t with_normalizing,
@@ -143,7 +144,8 @@ int ttb_delta_svd_f64(const double* data, int64_t m, int64_t n, double delta, in
                       void* workspace, size_t workspace_bytes, void* stream) {
     ttb::TruncSvdInfo info{};
     const double abs_tol = 0.0;  // full-accuracy SVD for the stand-alone entry point
-    const int rc = ttb::trunc_svd(data, m, n, delta, with_normalizing != 0, max_rank, abs_tol, u_out, svt_out,
+    const int rc = ttb::trunc_svd(const_cast<double*>(data), m, n, delta, with_normalizing != 0, max_rank, abs_tol,
+                                  /*inplace=*/false, u_out, svt_out,
                                   s_out, &info, workspace, workspace_bytes, as_stream(stream));
     if (rc == TTB_OK && info_out) {
         info_out[0] = double(info.rank);
@@ -152,6 +154,15 @@ int ttb_delta_svd_f64(const double* data, int64_t m, int64_t n, double delta, in
         info_out[3] = info.fro2;
     }
     return rc;
+}
+
+size_t ttb_ttsvd_workspace_bytes(int32_t d, const int64_t* shape) { return ttb::ttsvd_workspace_bytes(d, shape); }
+
+int ttb_ttsvd_f64(const double* dense, int32_t d, const int64_t* shape, double eps, int32_t max_rank,
+                  double* arena, size_t arena_doubles, int64_t* ranks_out, double* delta_out,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+    return ttb::ttsvd(dense, d, shape, eps, max_rank, arena, arena_doubles, ranks_out, delta_out, workspace,
+                      workspace_bytes, as_stream(stream));
 }
 
 }  // extern "C"

@@ -76,59 +76,83 @@ int host_words(HostWords* hw) {
 // ---------------------------------------------------------------------------
 namespace {
 constexpr size_t kGemmWsCap = size_t(64) << 20;  // recommended split-K scratch, never required
-size_t trunc_svd_required(int64_t m, int64_t c) {
+
+enum SvdPath { kPathTall, kPathWideLQ, kPathWideDirect };
+SvdPath svd_path(int64_t m, int64_t c) {
+    if (m > c) return kPathTall;
+    // very wide: LQ first so that Jacobi only sees the m x m factor (the mirror image of the
+    // reference's tall-skinny QR-first branch, pytens/utils.py:56-60)
+    if (c >= 2 * m && c > 64) return kPathWideLQ;
+    return kPathWideDirect;
+}
+
+size_t trunc_svd_required(int64_t m, int64_t c, bool inplace) {
     const int64_t p = std::min(m, c);
+    const SvdPath path = svd_path(m, c);
     size_t b = 0;
-    b += round_up<size_t>(size_t(m) * c * 8, 256);                  // Mt / X
-    b += 4 * round_up<size_t>(size_t(p) * std::max(p, c) * 8, 256); // R, J, Jsel, (spare)
-    b += 4 * round_up<size_t>(size_t(p) * 8, 256) + 1024;           // perm, sigma, nrm2, info/conv
-    b += (m > c) ? orth_rows_workspace_bytes(c, m) : 0;
+    if (path == kPathTall || !inplace) b += round_up<size_t>(size_t(m) * c * 8, 256);  // M^T / copy of M
+    b += 4 * round_up<size_t>(size_t(p) * std::max(p, path == kPathWideLQ ? p : c) * 8, 256);  // R, J, Jsel, L
+    b += 4 * round_up<size_t>(size_t(p) * 8, 256) + 1024;  // perm, sigma, nrm2, info/conv
+    if (path == kPathTall) b += orth_rows_workspace_bytes(c, m);
+    if (path == kPathWideLQ) b += orth_rows_workspace_bytes(m, c);
     return b + 4096;
 }
 }  // namespace
 
-size_t trunc_svd_workspace_bytes(int64_t m, int64_t c) { return trunc_svd_required(m, c) + kGemmWsCap; }
+size_t trunc_svd_workspace_bytes(int64_t m, int64_t c, bool inplace) {
+    return trunc_svd_required(m, c, inplace) + kGemmWsCap;
+}
 
-int trunc_svd(const double* M, int64_t m, int64_t c, double delta, bool with_normalizing, int max_rank,
-              double jacobi_abs_tol, double* U_out, double* SVt_out, double* sigma_out,
+int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizing, int max_rank,
+              double jacobi_abs_tol, bool inplace, double* U_out, double* SVt_out, double* sigma_out,
               TruncSvdInfo* res, void* ws, size_t ws_bytes, cudaStream_t stream) {
     TTB_REQUIRE(M && U_out && SVt_out && res, "trunc_svd: null pointer");
     TTB_REQUIRE(m >= 1 && c >= 1, "trunc_svd: empty matrix");
     TTB_REQUIRE(std::min(m, c) <= 8192, "trunc_svd: min(m, n) > 8192 unsupported");
-    const size_t need = trunc_svd_required(m, c);
+    const size_t need = trunc_svd_required(m, c, inplace);
     if (ws == nullptr || ws_bytes < need) {
         set_last_error("trunc_svd: workspace too small, need " + std::to_string(need) + " bytes");
         return kWorkspaceTooSmall;
     }
     HostWords hw;
     TTB_PROPAGATE(host_words(&hw));
-    const bool tall = m > c;
-    const int p = int(std::min(m, c));  // number of singular values
-    const int q = int(c);               // length of the rows handed to Jacobi
+    const SvdPath path = svd_path(m, c);
+    const int p = int(std::min(m, c));                      // number of singular values
+    const int q = (path == kPathWideLQ) ? p : int(c);       // length of the rows handed to Jacobi
+    const size_t small = size_t(p) * size_t(std::max<int64_t>(p, q));
 
     Workspace W(ws, ws_bytes);
-    double* big = W.take<double>(size_t(m) * c);
-    double* Rm = W.take<double>(size_t(p) * std::max<int64_t>(p, c));
-    double* J = W.take<double>(size_t(p) * std::max<int64_t>(p, c));
-    double* Jsel = W.take<double>(size_t(p) * std::max<int64_t>(p, c));
+    double* big = (path == kPathTall || !inplace) ? W.take<double>(size_t(m) * c) : M;
+    double* Rm = W.take<double>(small);
+    double* J = W.take<double>(small);
+    double* Jsel = W.take<double>(small);
+    double* Lm = W.take<double>(small);
     int* perm = W.take<int>(size_t(p) * 2);
     double* sigma = W.take<double>(p);
     double* nrm2 = W.take<double>(p);
     double* info = W.take<double>(8);
     unsigned long long* conv = W.take<unsigned long long>(8);
-    TTB_REQUIRE(big && Rm && J && Jsel && perm && sigma && nrm2 && info && conv, "trunc_svd: carve failed");
+    TTB_REQUIRE(big && Rm && J && Jsel && Lm && perm && sigma && nrm2 && info && conv, "trunc_svd: carve failed");
     const size_t rest = ws_bytes - W.off;
     void* sub = W.base + W.off;
 
     double* X;  // rows to rotate (p x q)
-    if (tall) {
+    if (path == kPathTall) {
         // M^T (c x m): rows orthonormalised in place, R (c x c) holds M^T = Q^T R  =>  M = Q_col R
         TTB_PROPAGATE(transpose(M, m, c, c, big, m, stream));
         TTB_PROPAGATE(orth_rows(big, c, m, m, Rm, c, sub, rest, stream));
         X = Rm;
     } else {
-        TTB_CHECK_CUDA(cudaMemcpyAsync(big, M, size_t(m) * c * 8, cudaMemcpyDeviceToDevice, stream));
-        X = big;
+        if (big != M)
+            TTB_CHECK_CUDA(cudaMemcpyAsync(big, M, size_t(m) * c * 8, cudaMemcpyDeviceToDevice, stream));
+        if (path == kPathWideLQ) {
+            // rows of M orthonormalised in place: M^T = Q^T R  =>  M = L Q with L = R^T (m x m)
+            TTB_PROPAGATE(orth_rows(big, m, c, c, Rm, m, sub, rest, stream));
+            TTB_PROPAGATE(transpose(Rm, m, m, m, Lm, m, stream));
+            X = Lm;
+        } else {
+            X = big;
+        }
     }
     int sweeps = 0;
     const int jst = jacobi_rows(X, p, q, q, J, jacobi_abs_tol, 40, &sweeps, conv, hw.conv, stream);
@@ -145,12 +169,12 @@ int trunc_svd(const double* M, int64_t m, int64_t c, double delta, bool with_nor
     res->sweeps = sweeps;
     res->converged = (jst == kOk);
     TTB_REQUIRE(rho >= 1 && rho <= p, "trunc_svd: bad rank from selection kernel");
-
-    // carry = diag(s) V^T = selected rotated rows
-    TTB_PROPAGATE(gather_rows(X, q, perm, rho, q, SVt_out, q, false, stream));
     if (sigma_out)
         TTB_CHECK_CUDA(cudaMemcpyAsync(sigma_out, sigma, size_t(rho) * 8, cudaMemcpyDeviceToDevice, stream));
-    if (tall) {
+
+    if (path == kPathTall) {
+        // carry = diag(s) V^T = selected rotated rows of R
+        TTB_PROPAGATE(gather_rows(X, q, perm, rho, q, SVt_out, q, false, stream));
         // U (m x rho) = Q_col (m x c) . Jsel^T (c x rho);  Q_col(i, k) = big[k * m + i]
         TTB_PROPAGATE(gather_rows(J, p, perm, rho, p, Jsel, p, false, stream));
         GemmArgs g;
@@ -159,7 +183,18 @@ int trunc_svd(const double* M, int64_t m, int64_t c, double delta, bool with_nor
         g.B = Jsel; g.sBk = 1; g.sBn = p;
         g.C = U_out; g.ldc = rho;
         TTB_PROPAGATE(gemm(g, sub, rest, stream));
+    } else if (path == kPathWideLQ) {
+        // L = J^T Xrot  =>  M = J^T Xrot Q:  U = J^T[:, sel],  carry = Xrot[sel] (rho x m) . Q (m x c)
+        TTB_PROPAGATE(gather_rows(J, p, perm, rho, p, U_out, rho, true, stream));
+        TTB_PROPAGATE(gather_rows(X, q, perm, rho, q, Jsel, q, false, stream));
+        GemmArgs g;
+        g.M = rho; g.N = c; g.K = m;
+        g.A = Jsel; g.sAm = m; g.sAk = 1;
+        g.B = big; g.sBk = c; g.sBn = 1;
+        g.C = SVt_out; g.ldc = c;
+        TTB_PROPAGATE(gemm(g, sub, rest, stream));
     } else {
+        TTB_PROPAGATE(gather_rows(X, q, perm, rho, q, SVt_out, q, false, stream));
         // U (m x rho) = J^T[:, sel]  -> U[i][s] = J[perm[s]][i]
         TTB_PROPAGATE(gather_rows(J, p, perm, rho, p, U_out, rho, true, stream));
     }
@@ -224,7 +259,7 @@ size_t round_workspace_bytes(const TTDesc& t) {
         core_elems = std::max<size_t>(core_elems, size_t(rl) * n * rr);
         if (k >= 1) sub = std::max(sub, right_orth_workspace_bytes(t.r[k - 1] * t.n[k - 1], rl, n * rr));
         if (k < t.d - 1) {
-            sub = std::max(sub, trunc_svd_workspace_bytes(rl * n, rr));
+            sub = std::max(sub, trunc_svd_workspace_bytes(rl * n, rr, false));
             carry_elems = std::max<size_t>(carry_elems, size_t(rr) * rr);
         }
     }
@@ -280,7 +315,7 @@ int round_tt(const TTDesc& t, double eps, int max_rank, int64_t* ranks_out, doub
         // rounding-noise level); far below the 1e-10 parity gate on the reconstruction error
         const double abs_tol = first ? 0.0 : 1e-14 * fro;
         // M = core_k (m x c); U overwrites core_k compactly as (m x rho)
-        TTB_PROPAGATE(trunc_svd(t.core[k], m, c, dl, first, max_rank, abs_tol, t.core[k], SVt, nullptr, &info,
+        TTB_PROPAGATE(trunc_svd(t.core[k], m, c, dl, first, max_rank, abs_tol, false, t.core[k], SVt, nullptr, &info,
                                 sub, rest, stream));
         if (first) {
             delta_abs = info.delta_abs;

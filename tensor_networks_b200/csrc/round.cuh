@@ -25,9 +25,11 @@ struct RoundStats {
 // delta_svd (pytens/utils.py:19-100).  U_out (m x rank, ld = rank) and
 // SVt_out = diag(s) V^T (rank x c, ld = c) are written compactly; U_out may alias M.
 // Synchronises the stream (the rank sizes the outputs).
-size_t trunc_svd_workspace_bytes(int64_t m, int64_t c);
-int trunc_svd(const double* M, int64_t m, int64_t c, double delta, bool with_normalizing, int max_rank,
-              double jacobi_abs_tol, double* U_out, double* SVt_out, double* sigma_out,
+// inplace: M may be destroyed (saves the m x c scratch copy on the wide paths); then
+// SVt_out must not alias M.
+size_t trunc_svd_workspace_bytes(int64_t m, int64_t c, bool inplace);
+int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizing, int max_rank,
+              double jacobi_abs_tol, bool inplace, double* U_out, double* SVt_out, double* sigma_out,
               TruncSvdInfo* res, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 // One RQ step (tt_right_orth, pytens/algs.py:1654-1704).

@@ -1,0 +1,89 @@
+"""GPU parity for TT-SVD of dense tensors (equal ranks, reconstruction error within 1e-10)."""
+
+import numpy as np
+import pytest
+
+from conftest import golden_files
+from oracle import tt_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+ERR_TOL = 1e-10
+
+
+def _left_orth_defect(tt):
+    worst = 0.0
+    for c in tt.cores[:-1]:
+        m = c.reshape(-1, c.shape[2])
+        g = (m.T @ m).cpu().numpy()
+        worst = max(worst, np.abs(g - np.eye(g.shape[0])).max())
+    return worst
+
+
+@pytest.mark.parametrize("path", golden_files("ttsvd"))
+def test_ttsvd_golden(path):
+    from tensor_networks_b200 import TensorTrain
+
+    z = np.load(path)
+    dense = z["dense"]
+    tt = TensorTrain.from_dense(dense, float(z["eps"]))
+    assert tt.ranks() == list(z["ranks_out"]), (tt.ranks(), list(z["ranks_out"]))
+    assert abs(tt.last_ttsvd["delta"] - float(z["delta"])) <= 1e-12 * float(z["delta"])
+    err = np.linalg.norm(tt.dense() - dense) / np.linalg.norm(dense)
+    assert abs(err - float(z["rel_err"])) <= ERR_TOL
+    assert _left_orth_defect(tt) < 1e-12
+
+
+@pytest.mark.parametrize(
+    "shape,ranks,eps,noise",
+    [
+        ([16, 16, 16, 16], [8, 20, 8], 1e-10, 0.0),
+        ([4, 30, 5, 12, 6], [4, 9, 11, 5], 1e-8, 1e-12),
+        ([2] * 14, [2, 4, 6, 8, 8, 8, 8, 8, 8, 6, 4, 3, 2], 1e-9, 0.0),  # long very-wide unfoldings
+        ([300, 7, 9], [5, 6], 1e-6, 1e-9),  # tall first unfolding
+        ([5, 2000], [3], 1e-10, 0.0),  # d = 2
+        ([12, 12, 12], [12, 12], 1e-3, 1e-2),  # genuine truncation of a noisy tensor
+    ],
+)
+def test_ttsvd_vs_oracle(shape, ranks, eps, noise):
+    from tensor_networks_b200 import TensorTrain
+
+    rng = np.random.default_rng(77)
+    x = orc.rand_tt(shape, ranks, rng)
+    dense = orc.to_dense(x)
+    if noise:
+        dense = dense + noise * np.linalg.norm(dense) / np.sqrt(dense.size) * rng.standard_normal(dense.shape)
+    ref, delta = orc.tt_svd(dense, eps)
+    tt = TensorTrain.from_dense(dense, eps)
+    assert tt.ranks() == orc.ranks_of(ref), (tt.ranks(), orc.ranks_of(ref))
+    err = np.linalg.norm(tt.dense() - dense) / np.linalg.norm(dense)
+    err_ref = np.linalg.norm(orc.to_dense(ref) - dense) / np.linalg.norm(dense)
+    assert abs(err - err_ref) <= ERR_TOL, (err, err_ref)
+    assert err <= eps * (1 + 1e-9) + 1e-13
+    assert _left_orth_defect(tt) < 1e-12
+
+
+def test_ttsvd_one_core_and_max_rank():
+    from tensor_networks_b200 import TensorTrain
+
+    v = np.arange(7.0)
+    tt = TensorTrain.from_dense(v, 1e-10)
+    assert tt.ranks() == [] and np.allclose(tt.dense(), v)
+    rng = np.random.default_rng(3)
+    dense = rng.standard_normal((6, 7, 8))
+    tt = TensorTrain.from_dense(dense, 1e-14, max_rank=3)
+    assert tt.ranks() == [3, 3]
+
+
+def test_ttsvd_medium_16_5():
+    """16^5 (8 MB) slice of BASELINE cfg4: TT ranks [16, 64, 64, 16] recovered at eps = 1e-10."""
+    from tensor_networks_b200 import TensorTrain
+
+    x = TensorTrain.rand([16] * 5, [16, 64, 64, 16], seed=3001)
+    dense = x.dense_dev()
+    tt = TensorTrain.from_dense(dense, 1e-10)
+    assert tt.ranks() == [16, 64, 64, 16]
+    back = tt.dense_dev()
+    err = float((back - dense).norm() / dense.norm())
+    assert err < 1e-10
+    assert _left_orth_defect(tt) < 1e-12
