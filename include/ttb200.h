@@ -50,6 +50,21 @@ typedef struct ttb_tt {
     double* const* core;
 } ttb_tt;
 
+/* `batch` tensor trains of identical shape, stored core-major: core[k] is a DEVICE
+ * pointer to the C-order array (batch, r[k], n[k], r[k+1]); item i of the batch is
+ * the contiguous slab i of every core array, so sharding a batch over GPUs is a
+ * slice of dimension 0.  n, r, core are HOST arrays.  (The reference has no batch
+ * API; batches arise from its callers looping over inner / tt_svd_round:
+ * pytens/algs.py:2752-2757, pytens/search/partition.py:139-141,
+ * pytens/cross/cross.py:403-404.) */
+typedef struct ttb_tt_batch {
+    int32_t d;
+    int64_t batch;
+    const int64_t* n;
+    const int64_t* r;
+    double* const* core;
+} ttb_tt_batch;
+
 /* ---- library ---------------------------------------------------------- */
 const char* ttb_version(void);
 const char* ttb_last_error(void);
@@ -84,6 +99,13 @@ int ttb_gemm_profile_read(double* total_ms, double* total_flops, uint64_t* launc
 size_t ttb_inner_workspace_bytes(const ttb_tt* a, const ttb_tt* b);
 int ttb_inner_f64(const ttb_tt* a, const ttb_tt* b, double* out_dev, void* workspace,
                   size_t workspace_bytes, void* stream);
+
+/* out_dev[i] = <A_i, B_i> for every item of two batches of equal mode sizes:
+ * TensorNetwork.inner (pytens/algs.py:585-587) applied item by item, fused into one
+ * kernel when all bond ranks are <= 32. */
+size_t ttb_inner_batched_workspace_bytes(const ttb_tt_batch* a, const ttb_tt_batch* b);
+int ttb_inner_batched_f64(const ttb_tt_batch* a, const ttb_tt_batch* b, double* out_dev, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* ---- dense contraction of a chain --------------------------------------
  * out_dev (n_1 x ... x n_d, C-order) = the tensor the TT represents; what

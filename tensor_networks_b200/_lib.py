@@ -43,6 +43,16 @@ class ttb_tt(Structure):
     ]
 
 
+class ttb_tt_batch(Structure):
+    _fields_ = [
+        ("d", c_int32),
+        ("batch", c_int64),
+        ("n", POINTER(c_int64)),
+        ("r", POINTER(c_int64)),
+        ("core", POINTER(c_void_p)),
+    ]
+
+
 _lib = None
 
 
@@ -104,6 +114,11 @@ def _declare(lib):
         c_void_p, c_size_t, c_void_p,
     ]
 
+    lib.ttb_inner_batched_workspace_bytes.restype = c_size_t
+    lib.ttb_inner_batched_workspace_bytes.argtypes = [P(ttb_tt_batch), P(ttb_tt_batch)]
+    lib.ttb_inner_batched_f64.restype = c_int
+    lib.ttb_inner_batched_f64.argtypes = [P(ttb_tt_batch), P(ttb_tt_batch), c_void_p, c_void_p, c_size_t, c_void_p]
+
     lib.ttb_tt_to_dense_workspace_bytes.restype = c_size_t
     lib.ttb_tt_to_dense_workspace_bytes.argtypes = [P(ttb_tt)]
     lib.ttb_tt_to_dense_f64.restype = c_int
@@ -142,6 +157,27 @@ class TTDescriptor:
         self._c = (c_void_p * d)(*[int(p) for p in core_ptrs])
         self.struct = ttb_tt(
             d,
+            ctypes.cast(self._n, POINTER(c_int64)),
+            ctypes.cast(self._r, POINTER(c_int64)),
+            ctypes.cast(self._c, POINTER(c_void_p)),
+        )
+
+    def ref(self):
+        return ctypes.byref(self.struct)
+
+
+class TTBatchDescriptor:
+    """Owns the host arrays behind a `ttb_tt_batch` for the duration of a call."""
+
+    def __init__(self, batch, shape, ranks, core_ptrs):
+        d = len(shape)
+        assert len(ranks) == d + 1 and len(core_ptrs) == d
+        self._n = (c_int64 * d)(*[int(x) for x in shape])
+        self._r = (c_int64 * (d + 1))(*[int(x) for x in ranks])
+        self._c = (c_void_p * d)(*[int(p) for p in core_ptrs])
+        self.struct = ttb_tt_batch(
+            d,
+            int(batch),
             ctypes.cast(self._n, POINTER(c_int64)),
             ctypes.cast(self._r, POINTER(c_int64)),
             ctypes.cast(self._c, POINTER(c_void_p)),

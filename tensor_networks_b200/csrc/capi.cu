@@ -5,12 +5,22 @@
 #include "gemm.cuh"
 #include "tt.cuh"
 #include "round.cuh"
+#include "batched.cuh"
 #include "ttsvd.cuh"
 
 namespace {
 inline ttb::TTDesc to_desc(const ttb_tt* t) {
     ttb::TTDesc d;
     d.d = t->d;
+    d.n = t->n;
+    d.r = t->r;
+    d.core = t->core;
+    return d;
+}
+inline ttb::TTBatchDesc to_bdesc(const ttb_tt_batch* t) {
+    ttb::TTBatchDesc d;
+    d.d = t->d;
+    d.batch = t->batch;
     d.n = t->n;
     d.r = t->r;
     d.core = t->core;
@@ -71,6 +81,20 @@ int ttb_inner_f64(const ttb_tt* a, const ttb_tt* b, double* out_dev, void* works
         return TTB_INVALID_ARGUMENT;
     }
     return ttb::inner(to_desc(a), to_desc(b), out_dev, workspace, workspace_bytes, as_stream(stream));
+}
+
+size_t ttb_inner_batched_workspace_bytes(const ttb_tt_batch* a, const ttb_tt_batch* b) {
+    if (!a || !b) return 0;
+    return ttb::inner_batched_workspace_bytes(to_bdesc(a), to_bdesc(b));
+}
+
+int ttb_inner_batched_f64(const ttb_tt_batch* a, const ttb_tt_batch* b, double* out_dev, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    if (!a || !b) {
+        ttb::set_last_error("ttb_inner_batched_f64: null descriptor");
+        return TTB_INVALID_ARGUMENT;
+    }
+    return ttb::inner_batched(to_bdesc(a), to_bdesc(b), out_dev, workspace, workspace_bytes, as_stream(stream));
 }
 
 size_t ttb_tt_to_dense_workspace_bytes(const ttb_tt* a) {

@@ -1,0 +1,67 @@
+"""CPU tests of the multi-GPU host logic: world_size-2 gloo, oracle as the local compute."""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_range_partitions():
+    from tensor_networks_b200.sharding import shard_range
+
+    for batch in (0, 1, 7, 8, 8192, 8191):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(batch, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == batch
+            for (l0, h0), (l1, h1) in zip(spans, spans[1:]):
+                assert h0 == l1
+            sizes = [h - l for l, h in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(8, 2, 2)
+
+
+def _worker(rank, world, port, batch, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import tt_oracle as orc
+    from tensor_networks_b200.sharding import all_gather_items, shard_range
+
+    rng = np.random.default_rng(1234)  # same stream on every rank -> same global batch
+    shape, ra, rb = [3, 4, 2, 3], [2, 3, 2], [3, 2, 2]
+    items = [(orc.rand_tt(shape, ra, rng), orc.rand_tt(shape, rb, rng)) for _ in range(batch)]
+    lo, hi = shard_range(batch, rank, world)
+    local = torch.tensor([float(orc.inner(a, b)) for a, b in items[lo:hi]], dtype=torch.float64)
+    full = all_gather_items(local, batch)
+    ref = torch.tensor([float(orc.inner(a, b)) for a, b in items], dtype=torch.float64)
+    ok_scalar = bool(torch.equal(full, ref))
+    # rank tables (int64, 2-d) gather the same way
+    ranks_local = torch.arange(lo, hi, dtype=torch.int64)[:, None] * torch.ones(1, 5, dtype=torch.int64)
+    ranks_full = all_gather_items(ranks_local, batch)
+    ok_ranks = bool(torch.equal(ranks_full[:, 0], torch.arange(batch, dtype=torch.int64)))
+    q.put((rank, ok_scalar and ok_ranks))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [7, 8])
+def test_all_gather_items_gloo_world2(batch):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + batch
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, batch, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(results) == [(0, True), (1, True)]
