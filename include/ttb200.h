@@ -151,6 +151,16 @@ int ttb_delta_svd_f64(const double* data, int64_t m, int64_t n, double delta, in
                       int32_t max_rank, double* u_out, double* s_out, double* svt_out, double* info_out,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* tt_svd_round (pytens/algs.py:1841-1903) on every item of a batch, in place: item
+ * i's core k is rewritten compactly as (ranks[i][k], n[k], ranks[i][k+1]) at the
+ * start of its slab.  ranks_out_dev: DEVICE (batch, d+1) int64 -- no host
+ * synchronisation.  status_out_dev: DEVICE (batch) int32, SVDs that hit the Jacobi
+ * sweep cap (may be NULL).  One fused kernel (one CTA per train, everything in
+ * shared memory) when bond ranks <= 32 and n*r <= 256. */
+size_t ttb_round_batched_workspace_bytes(const ttb_tt_batch* t);
+int ttb_round_batched_f64(const ttb_tt_batch* t, double eps, int32_t max_rank, int64_t* ranks_out_dev,
+                          int32_t* status_out_dev, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- TT-SVD of a dense tensor ---------------------------------------------
  * dense: device, C-order (shape[0] x ... x shape[d-1]), not modified.  Sequential
  * reshape-and-truncate with delta = eps / sqrt(d-1) * ||X||_F; replaces the

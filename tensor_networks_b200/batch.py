@@ -161,3 +161,24 @@ class TensorTrainBatch:
     def norm(self) -> torch.Tensor:
         """(B,) CUDA tensor of sqrt(|<X_i, X_i>|) -- TensorNetwork.norm, pytens/algs.py:589-594."""
         return self.inner(self).abs().sqrt()
+
+    def round(self, eps: float, max_rank: Optional[int] = None) -> "TensorTrainBatch":
+        """Round every item in place with relative accuracy eps -- tt_svd_round per item
+        (pytens/algs.py:1841-1903).  No host synchronisation: the per-item bond ranks land in
+        `self.item_ranks` ((B, d+1) int64 CUDA tensor) and `self.round_status` ((B,) int32)."""
+        if self.item_ranks is not None:
+            raise RuntimeError("batch already rounded; rebuild it before rounding again")
+        L = _lib.lib()
+        desc = self.descriptor()
+        ws = workspace(L.ttb_round_batched_workspace_bytes(desc.ref()), self.device)
+        ranks = torch.empty((self.batch, self.d + 1), dtype=torch.int64, device=self.device)
+        status = torch.zeros(self.batch, dtype=torch.int32, device=self.device)
+        check(
+            L.ttb_round_batched_f64(
+                desc.ref(), float(eps), int(max_rank) if max_rank else 0, ranks.data_ptr(), status.data_ptr(),
+                ws.data_ptr(), ws.numel(), _stream_ptr(),
+            )
+        )
+        self.item_ranks = ranks
+        self.round_status = status
+        return self

@@ -23,4 +23,13 @@ size_t inner_batched_workspace_bytes(const TTBatchDesc& a, const TTBatchDesc& b)
 int inner_batched(const TTBatchDesc& a, const TTBatchDesc& b, double* out_dev, void* ws, size_t ws_bytes,
                   cudaStream_t stream);
 
+// tt_svd_round (pytens/algs.py:1841-1903) on every item, in place on the batch storage:
+// item i's core k is written compactly as (ranks[i][k], n[k], ranks[i][k+1]) at the start
+// of its slab.  ranks_out_dev: DEVICE (batch, d+1) int64; status_out_dev: DEVICE (batch)
+// int32 count of SVDs that hit the Jacobi sweep cap (may be null).  Shapes with bond
+// ranks <= 32 and n*r <= 256 run in one fused kernel (one CTA per train).
+size_t round_batched_workspace_bytes(const TTBatchDesc& t);
+int round_batched(const TTBatchDesc& t, double eps, int max_rank, int64_t* ranks_out_dev, int* status_out_dev,
+                  void* ws, size_t ws_bytes, cudaStream_t stream);
+
 }  // namespace ttb

@@ -1,0 +1,427 @@
+// Batched TT rounding for small bond ranks: one CTA rounds one tensor train with
+// every intermediate (unfolding tile, Householder reflectors, R factor, Jacobi
+// rotations, carry) in shared memory; the cores are read once per pass from HBM and
+// written back compactly in place.
+//
+// Same algorithm as the large-rank driver in round.cu, i.e. tt_svd_round of the
+// reference (pytens/algs.py:1841-1903): RQ pass with Householder reflections on the
+// horizontal unfoldings (tt_right_orth, :1654-1704), then a left-to-right sweep of
+// Householder QR + one-sided Jacobi SVD of the R factor + tail-energy truncation
+// (delta_svd, pytens/utils.py:19-100) with delta = eps / sqrt(d-1) * ||X||_F taken
+// from the first core.  Requirements: all bond ranks <= 32 and n_k * r <= 256 for
+// both neighbours of every core (the unfolding must fit one 32 x 256 tile); other
+// shapes go through the large-rank path item by item.
+#include "batched.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "gemm.cuh"
+#include "householder.cuh"
+#include "round.cuh"
+
+namespace ttb {
+
+namespace {
+
+using namespace hh;
+
+constexpr int RB_NT = QR_NT;  // 256
+constexpr int RB_SP = 33;     // pitch of the 32 x 32 matrices
+constexpr int kMaxDR = 64;
+
+struct RoundBatchParams {
+    int d;
+    int64_t batch;
+    int n[kMaxDR];
+    int r[kMaxDR + 1];      // storage (input) bond ranks
+    double* core[kMaxDR];   // (batch, r[k], n[k], r[k+1])
+    double eps;
+    int max_rank;
+    int64_t* ranks_out;     // (batch, d+1)
+    int* status_out;        // (batch): Jacobi sweeps that hit the cap
+};
+
+__device__ __forceinline__ void rr_pair_dev(int n, int round, int k, int& a, int& b) {
+    if (k == 0) {
+        a = n - 1;
+        b = round;
+    } else {
+        a = (round + k) % (n - 1);
+        b = (round - k + (n - 1)) % (n - 1);
+    }
+    if (a > b) {
+        const int t = a;
+        a = b;
+        b = t;
+    }
+}
+
+// One-sided Jacobi on the rows of X (p x c, pitch RB_SP) with J (p x p) accumulated.
+// 16 half-warps, one row pair each per round.  Returns the number of sweeps that were
+// needed (> max_sweeps means the cap was hit).
+__device__ int jacobi_rows_smem(double* __restrict__ X, double* __restrict__ J, int p, int c, double tol,
+                                int max_sweeps, unsigned long long* flag) {
+    const int tid = threadIdx.x;
+    const int h = tid >> 4, l = tid & 15;
+    for (int idx = tid; idx < 32 * RB_SP; idx += RB_NT) {
+        const int i = idx / RB_SP, j = idx % RB_SP;
+        J[idx] = (i == j && i < p) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (p < 2) return 0;
+    const int P2 = (p + 1) & ~1;
+    // each half-warp reduces among its own 16 lanes only
+    const unsigned hmask = (h & 1) ? 0xffff0000u : 0x0000ffffu;
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        if (tid == 0) *flag = 0ull;
+        __syncthreads();
+        double worst = 0.0;
+        for (int rd = 0; rd < P2 - 1; ++rd) {
+            int i = 0, j = 0;
+            bool live = false;
+            if (h < P2 / 2) {
+                rr_pair_dev(P2, rd, h, i, j);
+                live = j < p;
+            }
+            if (live) {
+                double* xi = X + i * RB_SP;
+                double* xj = X + j * RB_SP;
+                double a = 0.0, b = 0.0, g = 0.0;
+                for (int k = l; k < c; k += 16) {
+                    const double u = xi[k], v = xj[k];
+                    a = fma(u, u, a);
+                    b = fma(v, v, b);
+                    g = fma(u, v, g);
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {
+                    a += __shfl_xor_sync(hmask, a, o);
+                    b += __shfl_xor_sync(hmask, b, o);
+                    g += __shfl_xor_sync(hmask, g, o);
+                }
+                if (a > 0.0 && b > 0.0 && g != 0.0) {
+                    const double rel = fabs(g) / sqrt(a * b);
+                    worst = fmax(worst, rel);
+                    if (rel > tol) {
+                        const double zeta = (b - a) / (2.0 * g);
+                        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                        const double cs = 1.0 / sqrt(1.0 + t * t);
+                        const double sn = cs * t;
+                        for (int k = l; k < c; k += 16) {
+                            const double u = xi[k], v = xj[k];
+                            xi[k] = cs * u - sn * v;
+                            xj[k] = sn * u + cs * v;
+                        }
+                        double* ji = J + i * RB_SP;
+                        double* jj = J + j * RB_SP;
+                        for (int k = l; k < p; k += 16) {
+                            const double u = ji[k], v = jj[k];
+                            ji[k] = cs * u - sn * v;
+                            jj[k] = sn * u + cs * v;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (worst > 0.0) atomicMax(flag, static_cast<unsigned long long>(__double_as_longlong(worst)));
+        __syncthreads();
+        const double mx = __longlong_as_double(static_cast<long long>(*flag));
+        __syncthreads();
+        if (mx <= tol) return sweep + 1;
+    }
+    return max_sweeps + 1;
+}
+
+__global__ void __launch_bounds__(RB_NT, 1) round_batched_kernel(const __grid_constant__ RoundBatchParams p) {
+    extern __shared__ __align__(16) double sm[];
+    double* As = sm;
+    double* Bs = As + QR_W * QR_PITCH;
+    double* Rm = Bs + QR_W * QR_PITCH;  // R factor / rows handed to Jacobi
+    double* Jm = Rm + 32 * RB_SP;
+    double* Cm = Jm + 32 * RB_SP;       // carry diag(s) V^T
+    __shared__ double sdot[QR_W], arow[QR_W], tau_s[QR_W], nrm2[32], sig[32];
+    __shared__ int perm[32];
+    __shared__ int rq[kMaxDR + 1], rk[kMaxDR + 1];
+    __shared__ unsigned long long flag;
+    __shared__ double sh_delta;
+    __shared__ int sh_rho, sh_bad;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d = p.d;
+
+    for (int64_t item = blockIdx.x; item < p.batch; item += gridDim.x) {
+        for (int k = tid; k <= d; k += RB_NT) {
+            rq[k] = p.r[k];
+            rk[k] = p.r[k];
+        }
+        if (tid == 0) sh_bad = 0;
+        __syncthreads();
+
+        // =========================== RQ pass ===========================
+        for (int k = d - 1; k >= 1; --k) {
+            const int c = p.r[k], nn = p.n[k], ro = p.r[k + 1], rn = rq[k + 1];
+            double* core = p.core[k] + item * (int64_t(c) * nn * ro);
+            const int m = nn * rn;
+            if (k == d - 1) {
+                for (int idx = tid; idx < c * m; idx += RB_NT) As[(idx / m) * QR_PITCH + idx % m] = core[idx];
+            } else {
+                // push of the previous step while loading: new[v][s][j] = sum_i old[v][s][i] R[j][i]
+                for (int t = tid; t < c * nn; t += RB_NT) {
+                    const int v = t / nn, s = t % nn;
+                    const double* src = core + int64_t(t) * ro;
+                    double x[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) x[i] = (i < ro) ? src[i] : 0.0;
+                    for (int j = 0; j < rn; ++j) {
+                        double y = 0.0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) y = fma(x[i], Rm[j * RB_SP + i], y);
+                        As[v * QR_PITCH + s * rn + j] = y;
+                    }
+                }
+            }
+            __syncthreads();
+            const int ww = c, hlen = m;
+            const int nsteps = min(ww, hlen);
+            for (int j = 0; j < nsteps; ++j) house_step(As, ww, hlen, j, sdot, arow, tau_s);
+            // R (nsteps x c): R[j][i] = As[i][j] for j <= i
+            for (int idx = tid; idx < 32 * RB_SP; idx += RB_NT) {
+                const int j = idx / RB_SP, i = idx % RB_SP;
+                Rm[idx] = (j < nsteps && i < c && j <= i) ? As[i * QR_PITCH + j] : 0.0;
+            }
+            for (int idx = tid; idx < ww * QR_H; idx += RB_NT) {
+                const int v = idx / QR_H, i = idx % QR_H;
+                Bs[v * QR_PITCH + i] = (i == v) ? 1.0 : 0.0;
+            }
+            __syncthreads();
+            for (int j = nsteps - 1; j >= 0; --j) house_apply(As, Bs, ww, hlen, j, tau_s[j], sdot);
+            for (int idx = tid; idx < nsteps * m; idx += RB_NT) core[idx] = Bs[(idx / m) * QR_PITCH + idx % m];
+            if (tid == 0) rq[k] = nsteps;
+            __syncthreads();
+        }
+
+        // =========================== forward pass ===========================
+        double delta_abs = 0.0;
+        if (tid == 0) rk[0] = 1;
+        for (int k = 0; k < d - 1; ++k) {
+            const int nn = p.n[k];
+            const int c = rq[k + 1];
+            int mrows;
+            double* core = p.core[k] + item * (int64_t(p.r[k]) * nn * p.r[k + 1]);
+            if (k == 0) {
+                // M[s][j] = sum_i core0[s][i] R[j][i]
+                const int ro = p.r[1];
+                mrows = nn;
+                for (int t = tid; t < nn * c; t += RB_NT) {
+                    const int s = t / c, j = t % c;
+                    const double* src = core + int64_t(s) * ro;
+                    double y = 0.0;
+                    for (int i = 0; i < ro; ++i) y = fma(src[i], Rm[j * RB_SP + i], y);
+                    As[j * QR_PITCH + s] = y;
+                }
+            } else {
+                // M[(q, s)][j] = sum_t carry[q][t] core_k[t][s][j]
+                const int ck = rq[k], rho = rk[k];
+                mrows = rho * nn;
+                for (int t = tid; t < nn * c; t += RB_NT) {
+                    const int s = t / c, j = t % c;
+                    double x[32];
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) x[u] = (u < ck) ? core[(int64_t(u) * nn + s) * c + j] : 0.0;
+                    for (int q = 0; q < rho; ++q) {
+                        double y = 0.0;
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) y = fma(Cm[q * RB_SP + u], x[u], y);
+                        As[j * QR_PITCH + q * nn + s] = y;
+                    }
+                }
+            }
+            __syncthreads();
+            const int ww = c, hlen = mrows;
+            const int psv = min(ww, hlen);  // number of singular values
+            for (int j = 0; j < psv; ++j) house_step(As, ww, hlen, j, sdot, arow, tau_s);
+            // rows handed to Jacobi: X[i][j] = R[i][j] = As[j][i], i <= j
+            for (int idx = tid; idx < 32 * RB_SP; idx += RB_NT) {
+                const int i = idx / RB_SP, j = idx % RB_SP;
+                Rm[idx] = (i < psv && j < c && i <= j) ? As[j * QR_PITCH + i] : 0.0;
+            }
+            for (int idx = tid; idx < ww * QR_H; idx += RB_NT) {
+                const int v = idx / QR_H, i = idx % QR_H;
+                Bs[v * QR_PITCH + i] = (i == v) ? 1.0 : 0.0;
+            }
+            __syncthreads();
+            for (int j = psv - 1; j >= 0; --j) house_apply(As, Bs, ww, hlen, j, tau_s[j], sdot);
+
+            const double tol = 1e-15 * sqrt(double(max(c, 16)));
+            const int sweeps = jacobi_rows_smem(Rm, Jm, psv, c, tol, 40, &flag);
+            if (sweeps > 40 && tid == 0) sh_bad += 1;
+
+            // singular values, order, rank (pytens/utils.py:70-85)
+            for (int i = warp; i < psv; i += RB_NT / 32) {
+                double s = 0.0;
+                for (int j = lane; j < c; j += 32) s = fma(Rm[i * RB_SP + j], Rm[i * RB_SP + j], s);
+                s = warp_sum(s);
+                if (lane == 0) nrm2[i] = s;
+            }
+            __syncthreads();
+            if (tid < psv) {
+                const double v = nrm2[tid];
+                int pos = 0;
+                for (int o = 0; o < psv; ++o) {
+                    const double w = nrm2[o];
+                    pos += (w > v) || (w == v && o < tid);
+                }
+                perm[pos] = tid;
+                sig[pos] = sqrt(v);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double fro2 = 0.0;
+                for (int i = 0; i < psv; ++i) fro2 += sig[i] * sig[i];
+                double dl = (k == 0) ? p.eps / sqrt(double(d - 1)) * sqrt(fro2) : delta_abs;
+                const double d2 = dl * dl;
+                double cum = 0.0;
+                int ndrop = 0;
+                for (int i = psv - 1; i >= 0; --i) {
+                    cum += sig[i] * sig[i];
+                    if (cum <= d2)
+                        ++ndrop;
+                    else
+                        break;
+                }
+                int rho = psv - ndrop;
+                if (rho < 1) rho = 1;
+                if (p.max_rank > 0 && rho > p.max_rank) rho = p.max_rank;
+                sh_rho = rho;
+                sh_delta = dl;
+                rk[k + 1] = rho;
+            }
+            __syncthreads();
+            const int rho_new = sh_rho;
+            delta_abs = sh_delta;
+            // U (mrows x rho_new) = Q (mrows x psv) . J^T[:, sel], written compactly over core k
+            for (int i = tid; i < mrows; i += RB_NT) {
+                double qv[32];
+#pragma unroll
+                for (int t = 0; t < 32; ++t) qv[t] = (t < psv) ? Bs[t * QR_PITCH + i] : 0.0;
+                for (int s = 0; s < rho_new; ++s) {
+                    const double* jr = Jm + perm[s] * RB_SP;
+                    double u = 0.0;
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) u = fma(jr[t], qv[t], u);
+                    core[int64_t(i) * rho_new + s] = u;
+                }
+            }
+            // carry (rho_new x c) = selected rotated rows
+            for (int idx = tid; idx < 32 * RB_SP; idx += RB_NT) {
+                const int s = idx / RB_SP, j = idx % RB_SP;
+                Cm[idx] = (s < rho_new && j < c) ? Rm[perm[s] * RB_SP + j] : 0.0;
+            }
+            __syncthreads();
+        }
+        // last core: (rho x ck) carry times (ck x n) core, compact
+        {
+            const int k = d - 1;
+            const int nn = p.n[k], ck = rq[k], rho = rk[k];
+            double* core = p.core[k] + item * (int64_t(p.r[k]) * nn * p.r[k + 1]);
+            if (d >= 2) {
+                double x[32];
+                const int s = tid;  // one thread per mode index (n <= 256)
+                if (s < nn) {
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) x[u] = (u < ck) ? core[int64_t(u) * nn + s] : 0.0;
+                }
+                __syncthreads();
+                if (s < nn) {
+                    for (int q = 0; q < rho; ++q) {
+                        double y = 0.0;
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) y = fma(Cm[q * RB_SP + u], x[u], y);
+                        core[int64_t(q) * nn + s] = y;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int k = tid; k <= d; k += RB_NT) p.ranks_out[item * (d + 1) + k] = (k == 0 || k == d) ? 1 : rk[k];
+        if (tid == 0 && p.status_out) p.status_out[item] = sh_bad;
+        __syncthreads();
+    }
+}
+
+constexpr size_t kRoundBatchSmem = (2 * size_t(QR_W) * QR_PITCH + 3 * 32 * RB_SP) * sizeof(double);
+
+bool fits_small(const TTBatchDesc& t) {
+    if (t.d > kMaxDR) return false;
+    for (int k = 0; k <= t.d; ++k)
+        if (t.r[k] > 32) return false;
+    for (int k = 0; k < t.d; ++k) {
+        if (t.n[k] * t.r[k + 1] > QR_H || t.r[k] * t.n[k] > QR_H || t.n[k] > QR_H) return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+size_t round_batched_workspace_bytes(const TTBatchDesc& t) {
+    if (t.d < 1) return 0;
+    if (fits_small(t)) return 256;
+    TTDesc one{t.d, t.n, t.r, t.core};
+    return round_workspace_bytes(one);
+}
+
+int round_batched(const TTBatchDesc& t, double eps, int max_rank, int64_t* ranks_out_dev, int* status_out_dev,
+                  void* ws, size_t ws_bytes, cudaStream_t stream) {
+    TTB_PROPAGATE(validate_batch(t, "round_batched"));
+    TTB_REQUIRE(eps >= 0.0, "round_batched: eps must be non-negative");
+    if (t.batch == 0) return kOk;
+    TTB_REQUIRE(ranks_out_dev != nullptr, "round_batched: ranks_out is null");
+
+    if (fits_small(t)) {
+        RoundBatchParams p{};
+        p.d = t.d;
+        p.batch = t.batch;
+        for (int k = 0; k < t.d; ++k) {
+            p.n[k] = int(t.n[k]);
+            p.core[k] = t.core[k];
+        }
+        for (int k = 0; k <= t.d; ++k) p.r[k] = int(t.r[k]);
+        p.eps = eps;
+        p.max_rank = max_rank;
+        p.ranks_out = ranks_out_dev;
+        p.status_out = status_out_dev;
+        static bool configured = false;
+        if (!configured) {
+            TTB_CHECK_CUDA(cudaFuncSetAttribute(round_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                int(kRoundBatchSmem)));
+            configured = true;
+        }
+        const int grid = int(std::min<int64_t>(t.batch, int64_t(num_sms())));
+        round_batched_kernel<<<grid, RB_NT, kRoundBatchSmem, stream>>>(p);
+        ++g_launch_count;
+        TTB_CHECK_CUDA(cudaGetLastError());
+        return kOk;
+    }
+    // larger shapes: the large-rank driver item by item (synchronises per item)
+    std::vector<double*> cores(t.d);
+    std::vector<int64_t> ranks(t.d + 1);
+    for (int64_t i = 0; i < t.batch; ++i) {
+        for (int k = 0; k < t.d; ++k) cores[k] = t.core[k] + i * (t.r[k] * t.n[k] * t.r[k + 1]);
+        TTDesc one{t.d, t.n, t.r, cores.data()};
+        RoundStats st;
+        TTB_PROPAGATE(round_tt(one, eps, max_rank, ranks.data(), nullptr, &st, ws, ws_bytes, stream));
+        TTB_CHECK_CUDA(cudaMemcpyAsync(ranks_out_dev + i * (t.d + 1), ranks.data(), size_t(t.d + 1) * 8,
+                                       cudaMemcpyHostToDevice, stream));
+        if (status_out_dev)
+            TTB_CHECK_CUDA(cudaMemcpyAsync(status_out_dev + i, &st.not_converged, sizeof(int),
+                                           cudaMemcpyHostToDevice, stream));
+        TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
+    }
+    return kOk;
+}
+
+}  // namespace ttb

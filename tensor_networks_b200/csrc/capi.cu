@@ -180,6 +180,21 @@ int ttb_delta_svd_f64(const double* data, int64_t m, int64_t n, double delta, in
     return rc;
 }
 
+size_t ttb_round_batched_workspace_bytes(const ttb_tt_batch* t) {
+    if (!t) return 0;
+    return ttb::round_batched_workspace_bytes(to_bdesc(t));
+}
+
+int ttb_round_batched_f64(const ttb_tt_batch* t, double eps, int32_t max_rank, int64_t* ranks_out_dev,
+                          int32_t* status_out_dev, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!t) {
+        ttb::set_last_error("ttb_round_batched_f64: null descriptor");
+        return TTB_INVALID_ARGUMENT;
+    }
+    return ttb::round_batched(to_bdesc(t), eps, max_rank, ranks_out_dev, status_out_dev, workspace,
+                              workspace_bytes, as_stream(stream));
+}
+
 size_t ttb_ttsvd_workspace_bytes(int32_t d, const int64_t* shape) { return ttb::ttsvd_workspace_bytes(d, shape); }
 
 int ttb_ttsvd_f64(const double* dense, int32_t d, const int64_t* shape, double eps, int32_t max_rank,

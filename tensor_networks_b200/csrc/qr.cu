@@ -29,153 +29,13 @@
 #include <vector>
 
 #include "gemm.cuh"
+#include "householder.cuh"
 
 namespace ttb {
 
 namespace {
 
-constexpr int QR_W = 32;     // max panel width (vectors per panel)
-constexpr int QR_H = 256;    // max leaf length (elements of each vector per leaf)
-constexpr int QR_NT = 256;   // threads per CTA (== QR_H: one thread per row in the update)
-constexpr int QR_PITCH = QR_H + 4;
-constexpr int QR_NWARP = QR_NT / 32;
-
-struct LeafGeom {
-    int64_t base, rem;  // leaf i has base + (i < rem) elements, starting at i*base + min(i, rem)
-    __host__ __device__ int64_t offset(int64_t i) const { return i * base + (i < rem ? i : rem); }
-    __host__ __device__ int len(int64_t i) const { return int(base + (i < rem ? 1 : 0)); }
-};
-
-// One Householder step j on the tile As[c][i] (c < ww vectors, i < hh elements):
-// annihilates As[j][j+1..], leaves beta on the diagonal, normalised v below it,
-// and applies the reflection to vectors j+1..ww-1.  Must be called by all threads.
-__device__ __forceinline__ void house_step(double* __restrict__ As, int ww, int hh, int j,
-                                           double* __restrict__ sdot, double* __restrict__ arow,
-                                           double* __restrict__ tau_s) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double* xj = As + j * QR_PITCH;
-    {
-        // each warp owns vectors c = j + warp + 8 t (t < 4); partial dots first, then the
-        // four shuffle reductions interleaved so their latencies overlap
-        constexpr int NC = QR_W / QR_NWARP;
-        double s[NC];
-#pragma unroll
-        for (int t = 0; t < NC; ++t) s[t] = 0.0;
-        for (int i = j + lane; i < hh; i += 32) {
-            const double x = xj[i];
-#pragma unroll
-            for (int t = 0; t < NC; ++t) {
-                const int c = j + warp + QR_NWARP * t;
-                if (c < ww) s[t] = fma(x, As[c * QR_PITCH + i], s[t]);
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int t = 0; t < NC; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], o);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int t = 0; t < NC; ++t) {
-                const int c = j + warp + QR_NWARP * t;
-                if (c < ww) {
-                    sdot[c] = s[t];
-                    arow[c] = As[c * QR_PITCH + j];
-                }
-            }
-        }
-    }
-    __syncthreads();
-    const double nrm2 = sdot[j];
-    if (!(nrm2 > 1e-300)) {  // zero (or NaN-free denormal) vector: H = I
-        if (tid == 0) tau_s[j] = 0.0;
-        if (tid > j && tid < hh) As[j * QR_PITCH + tid] = 0.0;
-        __syncthreads();
-        return;
-    }
-    const double alpha = arow[j];
-    const double beta = -copysign(sqrt(nrm2), alpha);
-    const double inv = 1.0 / (beta * (beta - alpha));
-    const int t = tid;
-    if (t >= j && t < hh) {
-        const double ut = (t == j) ? (alpha - beta) : xj[t];
-        const double uti = -ut * inv;
-        // batches of 8 vectors: all loads first, then the stores (no load waits on a store)
-        for (int c0 = j + 1; c0 < ww; c0 += 8) {
-            double f[8], v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int c = min(c0 + u, ww - 1);
-                f[u] = sdot[c] - beta * arow[c];
-                v[u] = As[c * QR_PITCH + t];
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (c0 + u < ww) As[(c0 + u) * QR_PITCH + t] = fma(uti, f[u], v[u]);
-        }
-        if (t == j) {
-            As[j * QR_PITCH + j] = beta;
-            tau_s[j] = (beta - alpha) / beta;
-        } else {
-            As[j * QR_PITCH + t] = ut / (alpha - beta);
-        }
-    }
-    __syncthreads();
-}
-
-// Apply H_j = I - tau v v^T (v from As[j][j..], v_j = 1) to the ww vectors of Bs.
-__device__ __forceinline__ void house_apply(const double* __restrict__ As, double* __restrict__ Bs,
-                                            int ww, int hh, int j, double tau,
-                                            double* __restrict__ sdot) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tau == 0.0) return;  // uniform
-    const double* vj = As + j * QR_PITCH;
-    {
-        constexpr int NC = QR_W / QR_NWARP;
-        double s[NC];
-#pragma unroll
-        for (int t = 0; t < NC; ++t) s[t] = 0.0;
-        for (int i = j + lane; i < hh; i += 32) {
-            const double v = (i == j) ? 1.0 : vj[i];
-#pragma unroll
-            for (int t = 0; t < NC; ++t) {
-                const int c = warp + QR_NWARP * t;
-                if (c < ww) s[t] = fma(v, Bs[c * QR_PITCH + i], s[t]);
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int t = 0; t < NC; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], o);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int t = 0; t < NC; ++t) {
-                const int c = warp + QR_NWARP * t;
-                if (c < ww) sdot[c] = s[t];
-            }
-        }
-    }
-    __syncthreads();
-    const int t = tid;
-    if (t >= j && t < hh) {
-        const double vt = (t == j) ? 1.0 : vj[t];
-        const double tv = -tau * vt;
-        for (int c0 = 0; c0 < ww; c0 += 8) {
-            double f[8], v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int c = min(c0 + u, ww - 1);
-                f[u] = sdot[c];
-                v[u] = Bs[c * QR_PITCH + t];
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (c0 + u < ww) Bs[(c0 + u) * QR_PITCH + t] = fma(tv, f[u], v[u]);
-        }
-    }
-    __syncthreads();
-}
+using namespace hh;
 
 struct TsqrLevelParams {
     double* X;        // (ww x mlen) row-space, leading dimension ldx; tile stored back in place

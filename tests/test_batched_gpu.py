@@ -57,3 +57,85 @@ def test_inner_batched_matches_single_path_and_is_deterministic():
     s0, s1 = ta.shard(0, 2), ta.shard(1, 2)
     t0, t1 = tb.shard(0, 2), tb.shard(1, 2)
     assert torch.equal(torch.cat([s0.inner(t0), s1.inner(t1)]), v1)
+
+
+# ----------------------------------------------------------------------------- rounding
+def _round_case(batch, shape, xr, eps, seed, mode="double"):
+    import copy
+
+    from tensor_networks_b200.batch import TensorTrainBatch
+
+    rng = np.random.default_rng(seed)
+    items = []
+    for _ in range(batch):
+        x = orc.rand_tt(shape, xr, rng)
+        if mode == "double":
+            y = orc.tt_add(x, x)
+        else:
+            y = x
+            for j in range(1, 4):
+                z = orc.rand_tt(shape, [2] * (len(shape) - 1), rng)
+                z[0] = z[0] * 10.0 ** (-2 * j)
+                y = orc.tt_add(y, z)
+        items.append(y)
+    tb = TensorTrainBatch.from_numpy(items)
+    tb.round(eps)
+    torch.cuda.synchronize()
+    ranks = tb.item_ranks.cpu().numpy()
+    assert int(tb.round_status.sum().item()) == 0
+    for i, y in enumerate(items):
+        ref, _ = orc.svd_round(copy.deepcopy(y), eps)
+        assert list(ranks[i][1:-1]) == orc.ranks_of(ref), (i, list(ranks[i]), orc.ranks_of(ref))
+        assert ranks[i][0] == 1 and ranks[i][-1] == 1
+        if np.prod(shape) <= 2_000_000:
+            dense = orc.to_dense(y)
+            got = tb.item(i).dense()
+            err = np.linalg.norm(got - dense) / np.linalg.norm(dense)
+            err_ref = np.linalg.norm(orc.to_dense(ref) - dense) / np.linalg.norm(dense)
+            assert abs(err - err_ref) <= 1e-10, (i, err, err_ref)
+    return tb
+
+
+@pytest.mark.parametrize(
+    "batch,shape,xr,eps,mode",
+    [
+        (9, [4] * 6, [3] * 5, 1e-8, "double"),
+        (5, [8, 3, 5, 8, 2], [4, 7, 6, 3], 1e-10, "double"),
+        (6, [6] * 6, [5] * 5, 1e-2, "decay"),  # genuine truncation
+        (3, [7, 5], [4], 1e-8, "double"),  # d = 2
+        (200, [5] * 4, [2] * 3, 1e-6, "double"),  # more items than SMs
+        (2, [3, 2, 2, 3], [4, 7, 5], 1e-8, "double"),  # n*b < r (pad branch of the reference)
+    ],
+)
+def test_round_batched_vs_oracle(batch, shape, xr, eps, mode):
+    _round_case(batch, shape, xr, eps, 77, mode)
+
+
+def test_round_batched_cfg5_items():
+    """Items of BASELINE cfg5: d=20, n=8, X bonds 16 doubled to 32 -> [8, 16, ..., 16, 8]."""
+    from tensor_networks_b200.batch import TensorTrainBatch
+
+    B, d, n, r = 24, 20, 8, 16
+    x = TensorTrainBatch.rand(B, [n] * d, [r] * (d - 1), seed=4000)
+    y = x + x
+    assert y.ranks() == [2 * r] * (d - 1)
+    ny = y.norm()
+    z = y.clone().round(1e-8)
+    ranks = z.item_ranks.cpu().numpy()
+    expect = [1, 8] + [16] * (d - 3) + [8, 1]
+    assert (ranks == np.array(expect)[None, :]).all(), ranks[0]
+    for i in (0, 7, 23):
+        zi, yi = z.item(i), y.item(i)
+        nz = zi.norm()
+        assert abs(nz - float(ny[i])) <= 1e-10 * nz
+        assert abs(float(zi.inner(yi)) / (nz * nz) - 1.0) < 1e-12
+        # against the large-rank single-TT path
+        single = yi.clone().round(1e-8)
+        assert single.ranks() == zi.ranks()
+        for c in zi.cores[:-1]:
+            m = c.reshape(-1, c.shape[2])
+            assert float((m.T @ m - torch.eye(m.shape[1], device=m.device, dtype=m.dtype)).abs().max()) < 1e-12
+
+
+def test_round_batched_large_rank_fallback():
+    _round_case(2, [6] * 4, [20, 24, 18], 1e-8, 5, "double")
