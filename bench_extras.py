@@ -78,9 +78,139 @@ def run_round(d=50, n=64, r=128, eps=1e-8, reps=2, cpu_sample_d=4):
     return res
 
 
+def run_ttsvd(n=16, d=7, ranks=(16, 64, 64, 64, 64, 16), eps=1e-10, reps=1):
+    """configs[3]: TT-SVD of a dense n^d tensor built from a random TT with the given ranks."""
+    x = TensorTrain.rand([n] * d, list(ranks), seed=3001)
+    dense = x.dense_dev()
+    del x
+    L = _lib.lib()
+    tt = TensorTrain.from_dense(dense, eps)  # warm-up
+    out_ranks = tt.ranks()
+    times = []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        l0 = L.ttb_launch_count()
+        t0 = time.perf_counter()
+        tt = TensorTrain.from_dense(dense, eps)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+        launches = int(L.ttb_launch_count() - l0)
+    ms = 1e3 * min(times)
+    flops = orc.ttsvd_flops([n] * d, out_ranks)
+    nbytes = 8 * (dense.numel() + 2 * sum(r * n ** (d - 1 - k) for k, r in enumerate(out_ranks)))
+    back = tt.dense_dev()
+    err = float((back - dense).norm() / dense.norm())
+    return {
+        "workload": f"tt_svd dense {n}^{d} fp64 eps={eps} (BASELINE configs[3])",
+        "ms": ms,
+        "gflops": flops / (ms * 1e-3) / 1e9,
+        "algorithmic_gbs": nbytes / (ms * 1e-3) / 1e9,
+        "flops_model": int(flops),
+        "bytes_model": int(nbytes),
+        "ranks_out": out_ranks,
+        "ranks_expected": list(ranks),
+        "rel_err": err,
+        "launches": launches,
+    }
+
+
+def run_batched(batch=8192, d=20, n=8, r=32, eps=1e-8, steps=5, rank=0, world=1):
+    """configs[4]: `batch` independent TT pairs (inner, bonds r) and TTs (rounding of X (+) X with
+    X bonds r/2), sharded by contiguous blocks across `world` ranks; per-item results are
+    all-gathered (NCCL) inside the timed region.  Timing: CUDA events, max over ranks."""
+    import torch.distributed as dist
+
+    from tensor_networks_b200.batch import TensorTrainBatch
+    from tensor_networks_b200.sharding import all_gather_items, shard_range
+
+    lo, hi = shard_range(batch, rank, world)
+    nloc = hi - lo
+    a = TensorTrainBatch.rand(nloc, [n] * d, [r] * (d - 1), seed=4000 + rank)
+    b = TensorTrainBatch.rand(nloc, [n] * d, [r] * (d - 1), seed=14000 + rank)
+    x = TensorTrainBatch.rand(nloc, [n] * d, [r // 2] * (d - 1), seed=24000 + rank)
+    y = x + x
+    del x
+
+    def sync_max(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- inner ----
+    for _ in range(2):
+        all_gather_items(a.inner(b), batch)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        vals = all_gather_items(a.inner(b), batch)
+    e1.record()
+    barrier()
+    ms_inner = sync_max(e0.elapsed_time(e1) / steps)
+    f_inner = orc.inner_flops([n] * d, [r] * (d - 1), [r] * (d - 1)) * batch
+    by_inner = 2 * orc.tt_bytes([n] * d, [r] * (d - 1)) * batch
+
+    # ---- rounding (in place -> clone outside the timed region) ----
+    z = y.clone().round(eps)
+    ranks0 = z.item_ranks[0].tolist()
+    clones = [y.clone() for _ in range(steps)]
+    barrier()
+    e0.record()
+    for zc in clones:
+        zc.round(eps)
+        ranks = all_gather_items(zc.item_ranks, batch)
+    e1.record()
+    barrier()
+    ms_round = sync_max(e0.elapsed_time(e1) / steps)
+    ok = bool((ranks == ranks[0:1]).all().item())
+    f_round = orc.round_flops([n] * d, [r] * (d - 1), ranks0[1:-1]) * batch
+    by_round = (orc.tt_bytes([n] * d, [r] * (d - 1)) + orc.tt_bytes([n] * d, ranks0[1:-1])) * batch
+    return {
+        "workload": f"batched {batch} TT pairs d={d} n={n} r={r}: inner + rounding eps={eps} (BASELINE configs[4])",
+        "n_gpus": world,
+        "scaling": "strong",
+        "inner": {"ms": ms_inner, "gflops": f_inner / (ms_inner * 1e-3) / 1e9,
+                  "algorithmic_gbs": by_inner / (ms_inner * 1e-3) / 1e9, "pairs_per_s": batch / (ms_inner * 1e-3)},
+        "round": {"ms": ms_round, "gflops": f_round / (ms_round * 1e-3) / 1e9,
+                  "algorithmic_gbs": by_round / (ms_round * 1e-3) / 1e9, "items_per_s": batch / (ms_round * 1e-3),
+                  "ranks_out": [ranks0[1], ranks0[len(ranks0) // 2], ranks0[-2]], "all_items_equal_ranks": ok},
+        "collective": "all_gather of fp64 scalars (inner) and the int64 rank table (rounding)",
+        "checksum_inner": float(vals.abs().sum().item()),
+    }
+
+
+def cpu_batched_sample(d=20, n=8, r=32, eps=1e-8, items=8):
+    """Oracle (reference algorithm) on a few items of configs[4] for the CPU columns."""
+    rng = np.random.default_rng(4000)
+    t_in, t_rd = 0.0, 0.0
+    for _ in range(items):
+        a = orc.rand_tt([n] * d, [r] * (d - 1), rng)
+        b = orc.rand_tt([n] * d, [r] * (d - 1), rng)
+        x = orc.rand_tt([n] * d, [r // 2] * (d - 1), rng)
+        y = orc.tt_add(x, x)
+        t0 = time.perf_counter()
+        orc.inner(a, b)
+        t_in += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        orc.svd_round(y, eps)
+        t_rd += time.perf_counter() - t0
+    return {"kind": "port", "sample": f"{items} items of the batch on the host cores",
+            "inner_pairs_per_s": items / t_in, "round_items_per_s": items / t_rd}
+
+
 def run_all():
     out = {}
     out["round_cfg3"] = run_round()
+    out["ttsvd_cfg4"] = run_ttsvd()
+    out["batched_cfg5"] = run_batched()
+    out["batched_cfg5"]["cpu_baseline"] = cpu_batched_sample()
     return out
 
 
@@ -91,5 +221,9 @@ if __name__ == "__main__":
     small = len(sys.argv) > 1 and sys.argv[1] == "small"
     if small:
         print(json.dumps(run_round(d=10, n=32, r=64, cpu_sample_d=0)))
+    elif len(sys.argv) > 1 and sys.argv[1] == "batched":
+        print(json.dumps(run_batched()))
+    elif len(sys.argv) > 1 and sys.argv[1] == "ttsvd":
+        print(json.dumps(run_ttsvd()))
     else:
         print(json.dumps(run_all()))

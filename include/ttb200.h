@@ -139,6 +139,15 @@ size_t ttb_right_orth_workspace_bytes(const ttb_tt* t, int32_t node);
 int ttb_right_orth_f64(const ttb_tt* t, int32_t node, int64_t* new_rank_out, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Orthonormalise the rows of M (c x m, row-major, ld = m) in place: M_in^T = Q^T R with
+ * Q (rows of M on return) orthonormal and R (c x c, row-major) upper triangular -- the
+ * thin QR of the transposed matrix that tt_right_orth takes (np.linalg.qr(val.T),
+ * pytens/algs.py:1678), without forming the transpose.  Rows >= min(c, m) of Q are
+ * zero (the zero-padding branch :1679-1685). */
+size_t ttb_orth_rows_workspace_bytes(int64_t c, int64_t m);
+int ttb_orth_rows_f64(double* M, int64_t c, int64_t m, double* R, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 /* delta-truncated SVD of a dense row-major matrix (m x n) on the device.
  * Replaces delta_svd (pytens/utils.py:19-100): rank chosen by the tail-energy rule
  * (drop trailing sigma while their cumulative energy <= delta^2, keep >= 1);

@@ -98,6 +98,10 @@ def _declare(lib):
     lib.ttb_right_orth_workspace_bytes.argtypes = [P(ttb_tt), c_int32]
     lib.ttb_right_orth_f64.restype = c_int
     lib.ttb_right_orth_f64.argtypes = [P(ttb_tt), c_int32, P(c_int64), c_void_p, c_size_t, c_void_p]
+    lib.ttb_orth_rows_workspace_bytes.restype = c_size_t
+    lib.ttb_orth_rows_workspace_bytes.argtypes = [c_int64, c_int64]
+    lib.ttb_orth_rows_f64.restype = c_int
+    lib.ttb_orth_rows_f64.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.ttb_delta_svd_workspace_bytes.restype = c_size_t
     lib.ttb_delta_svd_workspace_bytes.argtypes = [c_int64, c_int64]
     lib.ttb_delta_svd_f64.restype = c_int

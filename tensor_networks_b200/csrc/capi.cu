@@ -5,6 +5,7 @@
 #include "gemm.cuh"
 #include "tt.cuh"
 #include "round.cuh"
+#include "qr.cuh"
 #include "batched.cuh"
 #include "ttsvd.cuh"
 
@@ -156,6 +157,13 @@ int ttb_right_orth_f64(const ttb_tt* t, int32_t node, int64_t* new_rank_out, voi
     return ttb::right_orth_step(d.core[node], d.r[node], d.n[node] * d.r[node + 1], d.core[node - 1],
                                 d.r[node - 1] * d.n[node - 1], /*shrink=*/last, new_rank_out, workspace,
                                 workspace_bytes, as_stream(stream));
+}
+
+size_t ttb_orth_rows_workspace_bytes(int64_t c, int64_t m) { return ttb::orth_rows_workspace_bytes(c, m); }
+
+int ttb_orth_rows_f64(double* M, int64_t c, int64_t m, double* R, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+    return ttb::orth_rows(M, c, m, m, R, c, workspace, workspace_bytes, as_stream(stream));
 }
 
 size_t ttb_delta_svd_workspace_bytes(int64_t m, int64_t n) {

@@ -218,39 +218,85 @@ int tsqr_panel(double* P, int ww, int64_t m, int64_t ld, double* R, int64_t ldr,
     return kOk;
 }
 
-// R[0:j0, j0:j0+w] = C1^T + C2^T R1 ;  R[j0:j0+w, j0:j0+w] = R2 R1   (C2/R2 may be null: single pass)
-__global__ void assemble_r_kernel(double* __restrict__ R, int64_t ldr, int64_t j0, int w,
-                                  const double* __restrict__ C1, const double* __restrict__ C2,
-                                  int64_t ldcc, const double* __restrict__ R1,
-                                  const double* __restrict__ R2) {
-    __shared__ double r1[QR_W * QR_W];
-    for (int i = threadIdx.x; i < w * w; i += blockDim.x) r1[i] = R1[i];
+// One BCGS pass of a panel, coefficient bookkeeping.  With P = C Qp + Rp^T Qnew applied on
+// top of the passes already accumulated (vectors = Rb^T Qp + Rd_old^T P):
+//     R[0:j0, panel] += C^T Rd_old          (skipped when C == nullptr, i.e. j0 == 0)
+//     Rd_new = Rp Rd_old  ->  also written to R[j0:j0+w, panel]
+// Rd_old / Rd_new live in scratch (ping-pong) so that no block reads a half-updated factor.
+__global__ void accumulate_r_kernel(double* __restrict__ R, int64_t ldr, int64_t j0, int w,
+                                    const double* __restrict__ C, int64_t ldcc,
+                                    const double* __restrict__ Rp, const double* __restrict__ Rd_old,
+                                    double* __restrict__ Rd_new) {
+    __shared__ double rd[QR_W * QR_W];
+    for (int i = threadIdx.x; i < w * w; i += blockDim.x) rd[i] = Rd_old[i];
     __syncthreads();
     const int64_t total = (j0 + w) * w;
     for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
          idx += int64_t(gridDim.x) * blockDim.x) {
         const int64_t i = idx / w;
         const int t = int(idx % w);
-        double v;
         if (i < j0) {
-            v = C1[t * ldcc + i];
-            if (C2) {
-                double s = 0.0;
-                for (int u = 0; u < w; ++u) s = fma(C2[u * ldcc + i], r1[u * w + t], s);
-                v += s;
-            }
+            double s = 0.0;
+            for (int u = 0; u <= t; ++u) s = fma(C[u * ldcc + i], rd[u * w + t], s);
+            R[i * ldr + j0 + t] += s;
         } else {
             const int s_ = int(i - j0);
-            if (R2) {
-                double s = 0.0;
-                for (int u = s_; u <= t; ++u) s = fma(R2[s_ * w + u], r1[u * w + t], s);
-                v = (s_ <= t) ? s : 0.0;
-            } else {
-                v = r1[s_ * w + t];
-            }
+            double s = 0.0;
+            for (int u = s_; u <= t; ++u) s = fma(Rp[s_ * w + u], rd[u * w + t], s);
+            const double v = (s_ <= t) ? s : 0.0;
+            Rd_new[s_ * w + t] = v;
+            R[i * ldr + j0 + t] = v;
         }
-        R[i * ldr + j0 + t] = v;
     }
+}
+
+__global__ void set_identity_small_kernel(double* Rd, int w) {
+    for (int i = threadIdx.x; i < w * w; i += blockDim.x) Rd[i] = (i / w == i % w) ? 1.0 : 0.0;
+}
+
+// Row norms of the panel and the DGKS reorthogonalisation test: nrm_out[v] = ||P[v, :]||;
+// flag = min over v of nrm_out[v] / nrm_prev[v] (nrm_prev == nullptr: previous norms are 1,
+// the rows are an orthonormal Q from the last pass; a zero previous norm counts as ratio 0).
+// Positive doubles order like their bit patterns, so the min is an integer atomicMin.
+__global__ void __launch_bounds__(256) rownorm_kernel(const double* __restrict__ P, int64_t m, int64_t ld,
+                                                       const double* __restrict__ nrm_prev,
+                                                       double* __restrict__ nrm_out,
+                                                       unsigned long long* __restrict__ flag) {
+    const int v = blockIdx.x;
+    const double* x = P + int64_t(v) * ld;
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < m; i += blockDim.x) s = fma(x[i], x[i], s);
+    __shared__ double red[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        const double nv = sqrt(t);
+        nrm_out[v] = nv;
+        if (flag) {
+            const double prev = nrm_prev ? nrm_prev[v] : 1.0;
+            const double ratio = (prev > 0.0) ? nv / prev : 0.0;
+            atomicMin(flag, static_cast<unsigned long long>(__double_as_longlong(fmax(ratio, 0.0))));
+        }
+    }
+}
+
+// flag = min_v |Rp[v][v]| / nrm_prev[v]: the fraction of vector v that was left after projecting
+// out the previous panels and the earlier vectors of this panel.  nrm_prev == nullptr: the
+// inputs were orthonormal rows (norm 1).  A zero vector counts as ratio 0 (forces a clean-up pass).
+__global__ void dgks_kernel(const double* __restrict__ Rp, int w, const double* __restrict__ nrm_prev,
+                            unsigned long long* __restrict__ flag) {
+    const int v = threadIdx.x;
+    double ratio = 1e300;
+    if (v < w) {
+        const double prev = nrm_prev ? nrm_prev[v] : 1.0;
+        ratio = (prev > 0.0) ? fabs(Rp[v * w + v]) / prev : 0.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ratio = fmin(ratio, __shfl_xor_sync(0xffffffffu, ratio, o));
+    if (v == 0) *flag = static_cast<unsigned long long>(__double_as_longlong(ratio));
 }
 
 __global__ void zero_rows_kernel(double* X, int64_t rows, int64_t cols, int64_t ld) {
@@ -263,19 +309,34 @@ __global__ void zero_rows_kernel(double* X, int64_t rows, int64_t cols, int64_t 
 // gemm_ws is a recommendation (split-K partials); gemm() degrades gracefully with less,
 // so only `required()` is enforced.
 struct OrthLayout {
-    size_t c1, c2, r1, r2, tsqr, gemm_ws;
-    size_t required() const { return (c1 + c2 + r1 + r2 + tsqr) * 8 + 6 * 256; }
+    size_t cbuf, rp, rd, nrm, tsqr, gemm_ws;
+    size_t required() const { return (cbuf + rp + 2 * rd + 2 * nrm + tsqr) * 8 + 10 * 256; }
     size_t total() const { return required() + round_up<size_t>(gemm_ws, 256); }
 };
 
 OrthLayout orth_layout(int64_t c, int64_t m) {
     OrthLayout L;
-    L.c1 = L.c2 = size_t(QR_W) * size_t(std::max<int64_t>(c, 1));
-    L.r1 = L.r2 = QR_W * QR_W;
+    L.cbuf = size_t(QR_W) * size_t(std::max<int64_t>(c, 1));
+    L.rp = L.rd = QR_W * QR_W;
+    L.nrm = 64;
     L.tsqr = tsqr_scratch_doubles(m);
     L.gemm_ws = std::min<size_t>(std::max(gemm_workspace_bytes(QR_W, c, m), gemm_workspace_bytes(c, c, m)),
                                  size_t(64) << 20);
     return L;
+}
+
+struct OrthHost {
+    unsigned long long* flag = nullptr;  // pinned
+};
+int orth_host(OrthHost* h) {
+    static OrthHost g;
+    if (!g.flag) {
+        void* p = nullptr;
+        TTB_CHECK_CUDA(cudaHostAlloc(&p, 64, cudaHostAllocDefault));
+        g.flag = static_cast<unsigned long long*>(p);
+    }
+    *h = g;
+    return kOk;
 }
 
 }  // namespace
@@ -294,26 +355,35 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
         set_last_error("orth_rows: workspace too small, need " + std::to_string(L.required()) + " bytes");
         return kWorkspaceTooSmall;
     }
+    OrthHost host;
+    TTB_PROPAGATE(orth_host(&host));
     Workspace W(ws, ws_bytes);
-    double* C1 = W.take<double>(L.c1);
-    double* C2 = W.take<double>(L.c2);
-    double* R1 = W.take<double>(L.r1);
-    double* R2 = W.take<double>(L.r2);
+    double* Cb = W.take<double>(L.cbuf);
+    double* Rp = W.take<double>(L.rp);
+    double* Rd[2] = {W.take<double>(L.rd), W.take<double>(L.rd)};
+    double* nrm[2] = {W.take<double>(L.nrm), W.take<double>(L.nrm)};
+    unsigned long long* flag = W.take<unsigned long long>(8);
     double* tsq = W.take<double>(L.tsqr);
-    TTB_REQUIRE(C1 && C2 && R1 && R2 && tsq, "orth_rows: workspace carve failed");
+    TTB_REQUIRE(Cb && Rp && Rd[0] && Rd[1] && nrm[0] && nrm[1] && flag && tsq, "orth_rows: workspace carve failed");
     void* gws = W.base + W.off;
     const size_t gws_bytes = ws_bytes - W.off;
 
     TTB_CHECK_CUDA(cudaMemsetAsync(R, 0, size_t(c - 1) * ldr * 8 + size_t(c) * 8, stream));
     const int64_t kmax = std::min(c, m);  // at most m orthonormal vectors of length m
+    constexpr int kMaxPasses = 6;
+    constexpr double kDgks = 0.3;  // reorthogonalise again while a pass removes > 70 % of some vector
 
     for (int64_t j0 = 0; j0 < kmax; j0 += QR_W) {
         const int w = int(std::min<int64_t>(QR_W, kmax - j0));
         double* P = M + j0 * ldm;
-        const int npass = (j0 == 0) ? 1 : 2;
-        for (int pass = 0; pass < npass; ++pass) {
-            double* Cb = pass == 0 ? C1 : C2;
-            double* Rb = pass == 0 ? R1 : R2;
+        set_identity_small_kernel<<<1, 256, 0, stream>>>(Rd[0], w);
+        ++g_launch_count;
+        int cur = 0;
+        if (j0 > 0) {
+            rownorm_kernel<<<w, 256, 0, stream>>>(P, m, ldm, nullptr, nrm[0], nullptr);
+            ++g_launch_count;
+        }
+        for (int pass = 1; pass <= kMaxPasses; ++pass) {
             if (j0 > 0) {
                 GemmArgs g;  // C (w x j0) = P . Qp^T
                 g.M = w; g.N = j0; g.K = m;
@@ -329,14 +399,26 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                 u.alpha = -1.0; u.beta = 1.0;
                 TTB_PROPAGATE(gemm(u, gws, gws_bytes, stream));
             }
-            TTB_PROPAGATE(tsqr_panel(P, w, m, ldm, Rb, w, tsq, stream));
+            TTB_PROPAGATE(tsqr_panel(P, w, m, ldm, Rp, w, tsq, stream));
+            if (j0 > 0) {
+                // DGKS test: how much of each vector survived this pass (projection + panel QR)
+                dgks_kernel<<<1, 32, 0, stream>>>(Rp, w, pass == 1 ? nrm[0] : nullptr, flag);
+                ++g_launch_count;
+            }
+            const int64_t total = (j0 + w) * w;
+            const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(total, 128), 1024));
+            accumulate_r_kernel<<<blocks, 128, 0, stream>>>(R, ldr, j0, w, j0 > 0 ? Cb : nullptr, j0, Rp, Rd[cur],
+                                                            Rd[cur ^ 1]);
+            ++g_launch_count;
+            TTB_CHECK_CUDA(cudaGetLastError());
+            cur ^= 1;
+            if (j0 == 0) break;  // nothing to be orthogonal to: Householder TSQR alone is stable
+            TTB_CHECK_CUDA(cudaMemcpyAsync(host.flag, flag, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+            TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
+            double ratio;
+            memcpy(&ratio, host.flag, sizeof(double));
+            if (ratio >= kDgks) break;
         }
-        const int64_t total = (j0 + w) * w;
-        const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(total, 128), 1024));
-        assemble_r_kernel<<<blocks, 128, 0, stream>>>(R, ldr, j0, w, C1, npass == 2 ? C2 : nullptr, j0,
-                                                      R1, npass == 2 ? R2 : nullptr);
-        ++g_launch_count;
-        TTB_CHECK_CUDA(cudaGetLastError());
     }
     if (c > kmax) {
         // vectors kmax..c-1 lie in span(Q): R[0:kmax, kmax:c] = Q . M[kmax:c, :]^T, rows zeroed

@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "round.cuh"
 
@@ -131,6 +132,9 @@ int ttsvd(const double* dense, int d, const int64_t* shape, double eps, int max_
         TTB_PROPAGATE(trunc_svd(bufA, m, c, delta, false, max_rank, 1e-14 * fro, /*inplace=*/true, arena + off,
                                 bufB, nullptr, &info, sub, rest, stream));
         const int64_t rho = info.rank;
+        if (getenv("TTB_DEBUG"))
+            fprintf(stderr, "[ttsvd] step %d: m=%lld c=%lld rank=%lld sweeps=%d converged=%d fro2=%.6e delta=%.3e\n", k,
+                    (long long)m, (long long)c, (long long)rho, info.sweeps, int(info.converged), info.fro2, delta);
         off += size_t(m) * size_t(rho);
         ranks_out[k + 1] = rho;
         r = rho;

@@ -73,3 +73,18 @@ def delta_svd(data: np.ndarray, delta: float, with_normalizing: bool = False) ->
         info["remaining_delta"],
         info["delta"] if with_normalizing else None,
     )
+
+
+def orth_rows_dev(mat: torch.Tensor):
+    """Orthonormalise the rows of `mat` (c x m CUDA float64) in place; returns (Q, R) with
+    mat_in^T = Q^T R -- the device form of np.linalg.qr(mat.T) in tt_right_orth
+    (pytens/algs.py:1678) without the transposed copy."""
+    _require_cuda()
+    L = _lib.lib()
+    if mat.dim() != 2 or mat.dtype != torch.float64 or not mat.is_cuda or not mat.is_contiguous():
+        raise ValueError("orth_rows_dev needs a contiguous 2-d CUDA float64 tensor")
+    c, m = int(mat.shape[0]), int(mat.shape[1])
+    R = torch.empty((c, c), dtype=torch.float64, device=mat.device)
+    ws = workspace(L.ttb_orth_rows_workspace_bytes(c, m), mat.device)
+    check(L.ttb_orth_rows_f64(mat.data_ptr(), c, m, R.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr()))
+    return mat, R
