@@ -13,8 +13,10 @@ cores is a strict recurrence and does not shard -- DESIGN.md "replicas only"),
 so scaling is weak and there is no data-path collective; timing is CUDA events
 on the launching stream, max over ranks.
 
-One JSON line is printed by rank 0.  Extra workloads (rounding, TT-SVD, batched)
-are reported under "extra" when `--extras` is given.
+One JSON line is printed by rank 0.  The other BASELINE configs are reported under
+"extra": at N = 1 rounding (configs[2]), TT-SVD (configs[3]) and the batched config
+(configs[4]); at N > 1 the batched config sharded by contiguous blocks over the ranks with
+an NCCL all-gather of the per-item results (strong scaling).  `--no-extras` skips them.
 """
 
 from __future__ import annotations
@@ -51,7 +53,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--extras", action="store_true", help="also time rounding / TT-SVD / batched configs")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra workloads (rounding cfg3 / TT-SVD cfg4 / batched cfg5) reported under 'extra'")
     return ap.parse_args()
 
 
@@ -372,12 +375,20 @@ def main():
         res = cpu_inner_sample(a, steps=10, warmup=1, min_seconds=10.0)
         cpu_baseline = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    # ---- extra workloads: N = 1 -> BASELINE configs[2..4]; N > 1 -> the batched config sharded
+    # over the ranks (contiguous blocks, NCCL all-gather of the per-item results)
     extra = None
-    if a.extras and rank == 0 and world == 1:
+    if not a.no_extras:
         try:
             import bench_extras
 
-            extra = bench_extras.run_all()
+            del ta, tb
+            torch.cuda.empty_cache()
+            if world == 1:
+                extra = bench_extras.run_all()
+            else:
+                res = bench_extras.run_batched(rank=rank, world=world, steps=3)
+                extra = {"batched_cfg5": res}
         except Exception as exc:  # extras must never break the contract line
             extra = {"error": repr(exc)}
 
