@@ -95,6 +95,7 @@ using Cfg128x128 = TileCfg<128, 128, 64, 32, 4, 1>;
 using Cfg128x112 = TileCfg<128, 112, 32, 56, 4, 1>;
 using Cfg64x64 = TileCfg<64, 64, 32, 32, 4, 2>;
 using Cfg128x64 = TileCfg<128, 64, 32, 32, 3, 2>;
+using Cfg128x128w16 = TileCfg<128, 128, 32, 32, 4, 1>;
 
 template <class Cfg, bool A_KC, bool B_KC, bool ALIGNED>
 __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) dgemm_kernel(const GemmParams p) {
@@ -126,84 +127,92 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) dgemm_kernel(const GemmPar
     const double* __restrict__ A = p.A + bz * p.bsA;
     const double* __restrict__ B = p.B + bz * p.bsB;
 
-    auto load_tile = [&](int stage, int kt) {
-        const int64_t k0 = kbeg + int64_t(kt) * BK;
+    // ---- per-thread copy descriptors, hoisted out of the k loop ----
+    // Each thread moves the same chunks of every k tile: global pointer (advanced by a constant
+    // stride per tile), shared-memory offset, row predicate and k offset are computed once.
+    constexpr int CHW = ALIGNED ? 2 : 1;  // doubles per cp.async
+    constexpr int A_ROWLEN = (A_KC ? BK : BM) / CHW;   // chunks per smem row of the A stage
+    constexpr int A_ROWS = A_KC ? BM : BK;
+    constexpr int A_CHUNKS = A_ROWS * A_ROWLEN;
+    constexpr int A_ITERS = (A_CHUNKS + NT - 1) / NT;
+    constexpr int A_PITCH = A_KC ? Cfg::SA_KC : Cfg::SA_MC;
+    constexpr int B_ROWLEN = (B_KC ? BK : BN) / CHW;
+    constexpr int B_ROWS = B_KC ? BN : BK;
+    constexpr int B_CHUNKS = B_ROWS * B_ROWLEN;
+    constexpr int B_ITERS = (B_CHUNKS + NT - 1) / NT;
+    constexpr int B_PITCH = B_KC ? Cfg::SB_KC : Cfg::SB_NC;
+
+    const double* a_src[A_ITERS];
+    int a_dst[A_ITERS], a_koff[A_ITERS];
+    bool a_ok[A_ITERS];
+#pragma unroll
+    for (int i = 0; i < A_ITERS; ++i) {
+        const int idx = tid + i * NT;
+        const int r = idx / A_ROWLEN, c = (idx % A_ROWLEN) * CHW;
+        a_dst[i] = r * A_PITCH + c;
+        if constexpr (A_KC) {  // smem row = m, column = k
+            const int64_t gm = m0 + r;
+            a_ok[i] = idx < A_CHUNKS && gm < p.M;
+            a_koff[i] = c;
+            a_src[i] = A + (a_ok[i] ? gm * p.ldA + kbeg + c : 0);
+        } else {  // smem row = k, column = m
+            const int64_t gm = m0 + c;
+            a_ok[i] = idx < A_CHUNKS && gm < p.M;
+            a_koff[i] = r;
+            a_src[i] = A + (a_ok[i] ? (kbeg + r) * p.ldA + gm : 0);
+        }
+    }
+    const int64_t a_step = A_KC ? int64_t(BK) : int64_t(BK) * p.ldA;
+
+    const double* b_src[B_ITERS];
+    int b_dst[B_ITERS], b_koff[B_ITERS];
+    bool b_ok[B_ITERS];
+#pragma unroll
+    for (int i = 0; i < B_ITERS; ++i) {
+        const int idx = tid + i * NT;
+        const int r = idx / B_ROWLEN, c = (idx % B_ROWLEN) * CHW;
+        b_dst[i] = r * B_PITCH + c;
+        if constexpr (B_KC) {  // smem row = n, column = k
+            const int64_t gn = n0 + r;
+            b_ok[i] = idx < B_CHUNKS && gn < p.N;
+            b_koff[i] = c;
+            b_src[i] = B + (b_ok[i] ? gn * p.ldB + kbeg + c : 0);
+        } else {  // smem row = k, column = n
+            const int64_t gn = n0 + c;
+            b_ok[i] = idx < B_CHUNKS && gn < p.N;
+            b_koff[i] = r;
+            b_src[i] = B + (b_ok[i] ? (kbeg + r) * p.ldB + gn : 0);
+        }
+    }
+    const int64_t b_step = B_KC ? int64_t(BK) : int64_t(BK) * p.ldB;
+    const int klen = int(kend > kbeg ? kend - kbeg : 0);
+
+    auto load_a = [&](int stage, int kt) {
         double* as = As + stage * A_STAGE;
+        const int kleft = klen - kt * BK;
+#pragma unroll
+        for (int i = 0; i < A_ITERS; ++i) {
+            if (A_CHUNKS % NT != 0 && i == A_ITERS - 1 && tid + i * NT >= A_CHUNKS) break;
+            const bool pred = a_ok[i] && a_koff[i] < kleft;
+            const double* src = pred ? a_src[i] + int64_t(kt) * a_step : A;
+            if constexpr (ALIGNED)
+                cp_async16(as + a_dst[i], src, pred);
+            else
+                cp_async8(as + a_dst[i], src, pred);
+        }
+    };
+    auto load_b = [&](int stage, int kt) {
         double* bs = Bs + stage * B_STAGE;
-        if constexpr (ALIGNED) {
-            if constexpr (A_KC) {
-                constexpr int CH = BK / 2;
-                for (int idx = tid; idx < BM * CH; idx += NT) {
-                    const int r = idx / CH, c = idx % CH;
-                    const int64_t gm = m0 + r, gk = k0 + 2 * c;
-                    const bool pred = gm < p.M && gk < kend;
-                    const double* src = pred ? A + gm * p.ldA + gk : A;
-                    cp_async16(as + r * Cfg::SA_KC + 2 * c, src, pred);
-                }
-            } else {
-                constexpr int CH = BM / 2;
-                for (int idx = tid; idx < BK * CH; idx += NT) {
-                    const int r = idx / CH, c = idx % CH;
-                    const int64_t gk = k0 + r, gm = m0 + 2 * c;
-                    const bool pred = gk < kend && gm < p.M;
-                    const double* src = pred ? A + gk * p.ldA + gm : A;
-                    cp_async16(as + r * Cfg::SA_MC + 2 * c, src, pred);
-                }
-            }
-            if constexpr (B_KC) {
-                constexpr int CH = BK / 2;
-                for (int idx = tid; idx < BN * CH; idx += NT) {
-                    const int r = idx / CH, c = idx % CH;
-                    const int64_t gn = n0 + r, gk = k0 + 2 * c;
-                    const bool pred = gn < p.N && gk < kend;
-                    const double* src = pred ? B + gn * p.ldB + gk : B;
-                    cp_async16(bs + r * Cfg::SB_KC + 2 * c, src, pred);
-                }
-            } else {
-                constexpr int CH = BN / 2;
-                for (int idx = tid; idx < BK * CH; idx += NT) {
-                    const int r = idx / CH, c = idx % CH;
-                    const int64_t gk = k0 + r, gn = n0 + 2 * c;
-                    const bool pred = gk < kend && gn < p.N;
-                    const double* src = pred ? B + gk * p.ldB + gn : B;
-                    cp_async16(bs + r * Cfg::SB_NC + 2 * c, src, pred);
-                }
-            }
-        } else {
-            if constexpr (A_KC) {
-                for (int idx = tid; idx < BM * BK; idx += NT) {
-                    const int r = idx / BK, c = idx % BK;
-                    const int64_t gm = m0 + r, gk = k0 + c;
-                    const bool pred = gm < p.M && gk < kend;
-                    const double* src = pred ? A + gm * p.ldA + gk : A;
-                    cp_async8(as + r * Cfg::SA_KC + c, src, pred);
-                }
-            } else {
-                for (int idx = tid; idx < BK * BM; idx += NT) {
-                    const int r = idx / BM, c = idx % BM;
-                    const int64_t gk = k0 + r, gm = m0 + c;
-                    const bool pred = gk < kend && gm < p.M;
-                    const double* src = pred ? A + gk * p.ldA + gm : A;
-                    cp_async8(as + r * Cfg::SA_MC + c, src, pred);
-                }
-            }
-            if constexpr (B_KC) {
-                for (int idx = tid; idx < BN * BK; idx += NT) {
-                    const int r = idx / BK, c = idx % BK;
-                    const int64_t gn = n0 + r, gk = k0 + c;
-                    const bool pred = gn < p.N && gk < kend;
-                    const double* src = pred ? B + gn * p.ldB + gk : B;
-                    cp_async8(bs + r * Cfg::SB_KC + c, src, pred);
-                }
-            } else {
-                for (int idx = tid; idx < BK * BN; idx += NT) {
-                    const int r = idx / BN, c = idx % BN;
-                    const int64_t gk = k0 + r, gn = n0 + c;
-                    const bool pred = gk < kend && gn < p.N;
-                    const double* src = pred ? B + gk * p.ldB + gn : B;
-                    cp_async8(bs + r * Cfg::SB_NC + c, src, pred);
-                }
-            }
+        const int kleft = klen - kt * BK;
+#pragma unroll
+        for (int i = 0; i < B_ITERS; ++i) {
+            if (B_CHUNKS % NT != 0 && i == B_ITERS - 1 && tid + i * NT >= B_CHUNKS) break;
+            const bool pred = b_ok[i] && b_koff[i] < kleft;
+            const double* src = pred ? b_src[i] + int64_t(kt) * b_step : B;
+            if constexpr (ALIGNED)
+                cp_async16(bs + b_dst[i], src, pred);
+            else
+                cp_async8(bs + b_dst[i], src, pred);
         }
     };
 
@@ -215,7 +224,10 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) dgemm_kernel(const GemmPar
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < ntk) load_tile(s, s);
+        if (s < ntk) {
+            load_a(s, s);
+            load_b(s, s);
+        }
         cp_async_commit();
     }
 
@@ -223,39 +235,38 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) dgemm_kernel(const GemmPar
     const int fk = lane & 3;     // fragment k
     const int wm0 = warp_m * Cfg::WM;
     const int wn0 = warp_n * Cfg::WN;
+    // fragment base offsets inside a stage
+    const int a_frag = A_KC ? (wm0 + frow) * Cfg::SA_KC + fk : fk * Cfg::SA_MC + wm0 + frow;
+    const int b_frag = B_KC ? (wn0 + frow) * Cfg::SB_KC + fk : fk * Cfg::SB_NC + wn0 + frow;
+    constexpr int A_I = A_KC ? 8 * Cfg::SA_KC : 8;       // step between m fragments
+    constexpr int A_K = A_KC ? 4 : 4 * Cfg::SA_MC;       // step between k4 steps
+    constexpr int B_J = B_KC ? 8 * Cfg::SB_KC : 8;
+    constexpr int B_K = B_KC ? 4 : 4 * Cfg::SB_NC;
 
     for (int kt = 0; kt < ntk; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        {
-            const int nk = kt + STAGES - 1;
-            if (nk < ntk) load_tile(nk % STAGES, nk);
-            cp_async_commit();
-        }
-        const double* as = As + (kt % STAGES) * A_STAGE;
-        const double* bs = Bs + (kt % STAGES) * B_STAGE;
+        const int nk = kt + STAGES - 1;
+        const int nstage = nk % STAGES;
+        const bool more = nk < ntk;
+        const double* as = As + (kt % STAGES) * A_STAGE + a_frag;
+        const double* bs = Bs + (kt % STAGES) * B_STAGE + b_frag;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
             double a[MI], b[NJ];
 #pragma unroll
-            for (int i = 0; i < MI; ++i) {
-                if constexpr (A_KC)
-                    a[i] = as[(wm0 + 8 * i + frow) * Cfg::SA_KC + kk * 4 + fk];
-                else
-                    a[i] = as[(kk * 4 + fk) * Cfg::SA_MC + wm0 + 8 * i + frow];
-            }
+            for (int i = 0; i < MI; ++i) a[i] = as[i * A_I + kk * A_K];
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                if constexpr (B_KC)
-                    b[j] = bs[(wn0 + 8 * j + frow) * Cfg::SB_KC + kk * 4 + fk];
-                else
-                    b[j] = bs[(kk * 4 + fk) * Cfg::SB_NC + wn0 + 8 * j + frow];
-            }
+            for (int j = 0; j < NJ; ++j) b[j] = bs[j * B_J + kk * B_K];
+            // the next tile's copies are issued between the MMA groups so the pipe stays fed
+            if (kk == 0 && more) load_a(nstage, nk);
+            if (kk == 1 && more) load_b(nstage, nk);
 #pragma unroll
             for (int i = 0; i < MI; ++i)
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
+        cp_async_commit();
     }
     cp_async_wait<0>();
 
@@ -337,10 +348,13 @@ struct TileInfo {
     double eff;
 };
 const TileInfo kTileInfo[kNumTiles] = {
-    {128, 128, 1, 1.00},
-    {128, 112, 1, 0.98},
-    {64, 64, 2, 0.70},
-    {128, 64, 2, 0.88},
+    // relative main-loop efficiency measured on B200 (tools/gemm_sweep.py, 4096^3):
+    // 128x64 (2 CTAs/SM) 34.2 TF, 64x64 33.8, 128x128w16 32.8, 128x128 32.6
+    {128, 128, 1, 0.95},
+    {128, 112, 1, 0.96},
+    {64, 64, 2, 0.98},
+    {128, 64, 2, 1.00},
+    {128, 128, 1, 0.955},
 };
 
 template <class Cfg, bool A_KC, bool B_KC, bool ALIGNED>
@@ -379,6 +393,7 @@ int launch_layout(int tile, bool aligned, const GemmParams& p, dim3 grid, cudaSt
         case kTile128x128: return launch_cfg<Cfg128x128, A_KC, B_KC, true>(p, grid, stream);
         case kTile128x112: return launch_cfg<Cfg128x112, A_KC, B_KC, true>(p, grid, stream);
         case kTile128x64: return launch_cfg<Cfg128x64, A_KC, B_KC, true>(p, grid, stream);
+        case kTile128x128w16: return launch_cfg<Cfg128x128w16, A_KC, B_KC, true>(p, grid, stream);
         default: return launch_cfg<Cfg64x64, A_KC, B_KC, true>(p, grid, stream);
     }
 }

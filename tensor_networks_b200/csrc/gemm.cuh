@@ -31,7 +31,14 @@ struct GemmArgs {
     int force_tile = -1;   // -1 = heuristic; otherwise a TileId
 };
 
-enum TileId : int { kTile128x128 = 0, kTile128x112 = 1, kTile64x64 = 2, kTile128x64 = 3, kNumTiles = 4 };
+enum TileId : int {
+    kTile128x128 = 0,
+    kTile128x112 = 1,
+    kTile64x64 = 2,
+    kTile128x64 = 3,
+    kTile128x128w16 = 4,  // 16 warps of 32x32
+    kNumTiles = 5
+};
 
 // Upper bound of the split-K partial-sum workspace gemm() may ask for.
 size_t gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t batch = 1);

@@ -12,7 +12,7 @@ from tensor_networks_b200 import _lib  # noqa: E402
 from tensor_networks_b200.tt import workspace  # noqa: E402
 
 L = _lib.lib()
-TILES = {0: "128x128", 1: "128x112", 2: "64x64", 3: "128x64"}
+TILES = {0: "128x128", 1: "128x112", 2: "64x64", 3: "128x64", 4: "128x128w16"}
 
 
 def time_gemm(M, N, K, a_kc, b_kc, tile, splits, reps=20, nbuf=6):
@@ -59,11 +59,11 @@ def cublas(M, N, K, reps=20):
 
 if __name__ == "__main__":
     cases = [
-        ("gemm1 T=E.B", 256, 8192, 256, True, False, [(0, 1), (1, 1), (2, 1), (3, 1), (0, 2), (-1, 0)]),
+        ("gemm1 T=E.B", 256, 8192, 256, True, False, [(0, 1), (1, 1), (2, 1), (3, 1), (4, 1), (-1, 0)]),
         ("gemm2 E'=A^T.T", 256, 256, 8192, False, False,
-         [(0, 37), (0, 32), (0, 18), (2, 18), (2, 9), (3, 18), (3, 36), (-1, 0)]),
-        ("push core.R^T", 16384, 256, 256, True, True, [(0, 1), (1, 1), (3, 1), (-1, 0)]),
-        ("square 4096", 4096, 4096, 4096, True, False, [(0, 1), (1, 1), (3, 1), (2, 1)]),
+         [(0, 37), (4, 37), (2, 18), (2, 9), (3, 18), (3, 36), (-1, 0)]),
+        ("push core.R^T", 16384, 256, 256, True, True, [(0, 1), (4, 1), (3, 1), (-1, 0)]),
+        ("square 4096", 4096, 4096, 4096, True, False, [(0, 1), (4, 1), (3, 1), (2, 1)]),
         ("proj C=P.Q^T", 32, 224, 16384, True, True, [(2, 16), (2, 64), (-1, 0)]),
         ("proj P-=C.Q", 32, 16384, 224, True, False, [(2, 1), (3, 1), (-1, 0)]),
     ]
