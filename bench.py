@@ -320,7 +320,9 @@ def main():
                 traffic = None
         roofline = {
             "bound": "tensor",
-            "kernel": "dgemm_kernel (FP64 DMMA mma.sync.m8n8k4)",
+            "kernel": ("inner_sweep_kernel (persistent fused sweep: DMMA gemm_tile phases + grid barriers, "
+                       "one launch per sweep)" if int(nl.value) <= psteps else
+                       "dgemm_kernel (FP64 DMMA mma.sync.m8n8k4)"),
             "achieved": achieved,
             "peak": peak,
             "unit": "TFLOP/s",

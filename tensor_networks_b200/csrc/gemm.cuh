@@ -52,6 +52,9 @@ int gemm(const GemmArgs& args, void* ws, size_t ws_bytes, cudaStream_t stream);
 int gemm_profile_enable(int enable);
 int gemm_profile_read(double* total_ms, double* total_flops, unsigned long long* launches);
 
+int profile_begin(cudaStream_t stream);
+void profile_end(int slot, double flops, cudaStream_t stream);
+
 // number of kernels launched by gemm() so far (bench.py's gpu_launches)
 extern unsigned long long g_launch_count;
 

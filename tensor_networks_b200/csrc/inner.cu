@@ -16,6 +16,7 @@
 #include "tt.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace ttb {
@@ -83,9 +84,18 @@ InnerLayout inner_layout(const TTDesc& A, const TTDesc& B) {
 
 }  // namespace
 
+static bool fused_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("TTB_INNER_FUSED");
+        v = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 size_t inner_workspace_bytes(const TTDesc& a, const TTDesc& b) {
     if (a.d != b.d || a.d < 1) return 0;
-    return inner_layout(a, b).total();
+    return std::max(inner_layout(a, b).total(), inner_fused_workspace_bytes(a, b));
 }
 
 int inner(const TTDesc& A, const TTDesc& B, double* out_dev, void* ws, size_t ws_bytes,
@@ -97,6 +107,11 @@ int inner(const TTDesc& A, const TTDesc& B, double* out_dev, void* ws, size_t ws
         TTB_REQUIRE(A.n[k] == B.n[k], "inner: mode sizes differ (free indices must match)");
     TTB_REQUIRE(out_dev != nullptr, "inner: null output");
 
+    if (fused_enabled()) {
+        // one persistent cooperative kernel for the whole sweep when every step is large
+        const int st = inner_fused(A, B, out_dev, ws, ws_bytes, stream);
+        if (st != kUnsupported) return st;
+    }
     const InnerLayout L = inner_layout(A, B);
     if (ws == nullptr || ws_bytes < L.total()) {
         set_last_error("inner: workspace too small, need " + std::to_string(L.total()) + " bytes");

@@ -1,0 +1,312 @@
+// Persistent fused TT inner-product sweep: ONE cooperative launch per <A, B>.
+//
+// The per-GEMM path (inner.cu) spends ~10 us of launch / prologue / epilogue ramp on every
+// ~30 us GEMM and runs a separate split-K reduce kernel per core.  Here 148 resident CTAs
+// (one per SM) walk the cores of the chain themselves; every core is three phases separated
+// by a grid-wide barrier (all CTAs are co-resident: cooperative launch):
+//   1. T   = E . B_k            (or E^T . A_k)   tiles of 128 x 112, DMMA          [gemm_tile]
+//   2. P_s = A_k^T . T | k-slice s               tiles of 128 x 64 x split-K, DMMA  [gemm_tile]
+//   3. E'  = sum_s P_s                            deterministic, all threads
+// The last core (bond ranks 1) is a fused dot product.  Operand tiles are staged with
+// cp.async.cg (L2 only), and values produced by other CTAs are read with ld.global.cg, so no
+// stale L1 line is ever consumed across a barrier.  Same arithmetic and the same summation
+// order as the per-GEMM path whenever the tile/split choices coincide.
+#include <algorithm>
+#include <vector>
+
+#include "gemm.cuh"
+#include "gemm_tile.cuh"
+#include "tt.cuh"
+
+namespace ttb {
+
+namespace {
+
+using namespace gemm_detail;
+
+using CfgT = TileCfg<128, 112, 32, 56, 4, 1>;  // phase 1
+using CfgE = TileCfg<128, 64, 32, 32, 3, 1>;   // phase 2
+static_assert(CfgT::NT == 256 && CfgE::NT == 256, "both phases run with 256 threads");
+constexpr int FS_NT = 256;
+
+constexpr size_t cmax(size_t a, size_t b) { return a > b ? a : b; }
+constexpr size_t kFusedSmem =
+    cmax(cmax(CfgT::smem_bytes<true, false>(), CfgT::smem_bytes<false, false>()), CfgE::smem_bytes<false, false>());
+
+struct SweepStep {
+    const double* A;
+    const double* B;
+    int a, a2, b, b2, n;
+    int eb_order;   // 1: T = E.B_k ; 0: T = E^T.A_k
+    int splits;     // split-K factor of phase 2
+    int kchunk;     // k extent of one split (multiple of BK)
+};
+
+struct SweepParams {
+    const SweepStep* steps;
+    int d;
+    double* E0;
+    double* E1;
+    double* T;
+    double* P;
+    double* out;
+    unsigned* barrier;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++epoch;
+        const unsigned target = epoch * gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+        __threadfence();
+    } else {
+        ++epoch;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams p) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double red[FS_NT / 32];
+    unsigned epoch = 0;
+    int cur = 0;
+    const int tid = threadIdx.x;
+
+    for (int k = 0; k < p.d - 1; ++k) {
+        const SweepStep s = p.steps[k];
+        const double* Ein = cur ? p.E1 : p.E0;
+        double* Eout = cur ? p.E0 : p.E1;
+        const double* A2;
+        const double* B2;
+        int64_t K2;
+        if (k > 0) {
+            // ---------------- phase 1: T ----------------
+            TileJob j;
+            j.alpha = 1.0;
+            j.beta = 0.0;
+            j.plain = false;
+            j.kbeg = 0;
+            j.C = p.T;
+            if (s.eb_order) {
+                j.A = Ein; j.ldA = s.b;                     // E (a x b), K-contiguous
+                j.B = s.B; j.ldB = int64_t(s.n) * s.b2;     // B_k (b x n b')
+                j.M = s.a; j.N = int64_t(s.n) * s.b2; j.kend = s.b;
+            } else {
+                j.A = Ein; j.ldA = s.b;                     // E^T (b x a): A(m, k) = E[k * b + m]
+                j.B = s.A; j.ldB = int64_t(s.n) * s.a2;     // A_k (a x n a')
+                j.M = s.b; j.N = int64_t(s.n) * s.a2; j.kend = s.a;
+            }
+            j.ldc = j.N;
+            const int tm = int((j.M + CfgT::BM - 1) / CfgT::BM);
+            const int tn = int((j.N + CfgT::BN - 1) / CfgT::BN);
+            for (int w = blockIdx.x; w < tm * tn; w += gridDim.x) {
+                j.m0 = int64_t(w % tm) * CfgT::BM;
+                j.n0 = int64_t(w / tm) * CfgT::BN;
+                if (s.eb_order)
+                    gemm_tile<CfgT, true, false, true>(j, smem);
+                else
+                    gemm_tile<CfgT, false, false, true>(j, smem);
+            }
+            grid_barrier(p.barrier, epoch);
+            if (s.eb_order) {
+                A2 = s.A; B2 = p.T; K2 = int64_t(s.a) * s.n;   // E' = A_k (a n x a')^T . T (a n x b')
+            } else {
+                A2 = p.T; B2 = s.B; K2 = int64_t(s.b) * s.n;   // E' = T (b n x a')^T . B_k (b n x b')
+            }
+        } else {
+            A2 = s.A; B2 = s.B; K2 = s.n;                      // E_1 = A_0^T B_0
+        }
+        // ---------------- phase 2: E' (split-K partials) ----------------
+        {
+            TileJob j;
+            j.A = A2; j.ldA = s.a2;
+            j.B = B2; j.ldB = s.b2;
+            j.M = s.a2; j.N = s.b2;
+            j.ldc = s.b2;
+            j.alpha = 1.0;
+            j.beta = 0.0;
+            j.plain = s.splits > 1;
+            const int tm = (s.a2 + CfgE::BM - 1) / CfgE::BM;
+            const int tn = (s.b2 + CfgE::BN - 1) / CfgE::BN;
+            const int tiles = tm * tn;
+            for (int w = blockIdx.x; w < tiles * s.splits; w += gridDim.x) {
+                const int tile = w % tiles, split = w / tiles;
+                j.m0 = int64_t(tile % tm) * CfgE::BM;
+                j.n0 = int64_t(tile / tm) * CfgE::BN;
+                j.kbeg = int64_t(split) * s.kchunk;
+                j.kend = min(K2, j.kbeg + int64_t(s.kchunk));
+                j.C = (s.splits > 1) ? p.P + int64_t(split) * s.a2 * s.b2 : Eout;
+                gemm_tile<CfgE, false, false, true>(j, smem);
+            }
+        }
+        grid_barrier(p.barrier, epoch);
+        // ---------------- phase 3: deterministic reduction of the partials ----------------
+        if (s.splits > 1) {
+            const int64_t total2 = (int64_t(s.a2) * s.b2) >> 1;  // ranks are even: double2 elements
+            const double2* P2 = reinterpret_cast<const double2*>(p.P);
+            double2* E2 = reinterpret_cast<double2*>(Eout);
+            for (int64_t idx = int64_t(blockIdx.x) * FS_NT + tid; idx < total2; idx += int64_t(gridDim.x) * FS_NT) {
+                double2 acc = make_double2(0.0, 0.0);
+                for (int z = 0; z < s.splits; ++z) {
+                    const double2 v = __ldcg(P2 + int64_t(z) * total2 + idx);
+                    acc.x += v.x;
+                    acc.y += v.y;
+                }
+                E2[idx] = acc;
+            }
+            grid_barrier(p.barrier, epoch);
+        }
+        cur ^= 1;
+    }
+
+    // ---------------- last core: <A,B> = sum_{i,s} A_d[i][s] * (E . B_d)[i][s] ----------------
+    {
+        const SweepStep s = p.steps[p.d - 1];
+        const double* Ein = cur ? p.E1 : p.E0;
+        double acc = 0.0;
+        const int64_t total = int64_t(s.a) * s.n;
+        for (int64_t idx = int64_t(blockIdx.x) * FS_NT + tid; idx < total; idx += int64_t(gridDim.x) * FS_NT) {
+            const int64_t i = idx / s.n;
+            const int sn = int(idx % s.n);
+            double t = 0.0;
+            for (int jj = 0; jj < s.b; ++jj) t = fma(__ldcg(Ein + i * s.b + jj), s.B[int64_t(jj) * s.n + sn], t);
+            acc = fma(s.A[idx], t, acc);
+        }
+        acc = warp_sum(acc);
+        if ((tid & 31) == 0) red[tid >> 5] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double v = 0.0;
+            for (int w = 0; w < FS_NT / 32; ++w) v += red[w];
+            p.P[blockIdx.x] = v;
+        }
+        grid_barrier(p.barrier, epoch);
+        if (blockIdx.x == 0 && tid == 0) {
+            double v = 0.0;
+            for (unsigned w = 0; w < gridDim.x; ++w) v += __ldcg(p.P + w);
+            p.out[0] = v;
+        }
+    }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+struct FusedPlan {
+    std::vector<SweepStep> steps;
+    size_t e_elems = 1, t_elems = 1, p_elems = 1;
+    double flops = 0.0;
+};
+
+bool plan_fused(const TTDesc& A, const TTDesc& B, FusedPlan* plan) {
+    const int d = A.d;
+    if (d < 2 || d != B.d) return false;
+    const int sms = num_sms();
+    double min_step_flops = 1e300;
+    plan->steps.resize(d);
+    for (int k = 0; k < d; ++k) {
+        if (A.n[k] != B.n[k]) return false;
+        const int64_t a = A.r[k], a2 = A.r[k + 1], b = B.r[k], b2 = B.r[k + 1], n = A.n[k];
+        if (a > 16384 || b > 16384 || n > 1 << 20) return false;
+        if (k > 0 && ((a & 1) || (b & 1))) return false;  // 16-byte cp.async chunks need even ranks
+        if (!aligned16(A.core[k]) || !aligned16(B.core[k])) return false;
+        SweepStep s{};
+        s.A = A.core[k];
+        s.B = B.core[k];
+        s.a = int(a); s.a2 = int(a2); s.b = int(b); s.b2 = int(b2); s.n = int(n);
+        const double c_eb = double(a) * b * n * b2 + double(a) * n * a2 * b2;
+        const double c_ea = double(a) * b * n * a2 + double(b) * n * a2 * b2;
+        s.eb_order = c_eb <= c_ea;
+        const double fl = 2.0 * std::min(c_eb, c_ea);
+        plan->flops += (k == 0) ? 2.0 * n * a2 * b2 : fl;
+        if (k > 0 && k < d - 1) min_step_flops = std::min(min_step_flops, fl);
+        if (k < d - 1) {
+            const int64_t K2 = (k == 0) ? n : (s.eb_order ? a * n : b * n);
+            const int64_t tiles = ceil_div<int64_t>(a2, CfgE::BM) * ceil_div<int64_t>(b2, CfgE::BN);
+            const int64_t ktiles = std::max<int64_t>(1, ceil_div<int64_t>(K2, BK));
+            int64_t splits = std::max<int64_t>(1, std::min<int64_t>(sms / std::max<int64_t>(tiles, 1), ktiles / 2));
+            splits = std::max<int64_t>(1, std::min<int64_t>(splits, 64));
+            const int64_t kt_per = ceil_div<int64_t>(ktiles, splits);
+            s.splits = int(ceil_div<int64_t>(ktiles, kt_per));
+            s.kchunk = int(kt_per * BK);
+            plan->e_elems = std::max<size_t>(plan->e_elems, size_t(a2) * b2);
+            plan->p_elems = std::max<size_t>(plan->p_elems, size_t(s.splits) * a2 * b2);
+            if (k > 0)
+                plan->t_elems = std::max<size_t>(plan->t_elems, s.eb_order ? size_t(a) * n * b2 : size_t(b) * n * a2);
+        }
+        plan->steps[k] = s;
+    }
+    plan->p_elems = std::max<size_t>(plan->p_elems, size_t(sms) + 8);
+    // only worth a persistent grid when every interior step keeps 148 SMs busy for a while
+    return d >= 3 && min_step_flops >= 2.0e8;
+}
+
+size_t fused_bytes(const FusedPlan& pl, int d) {
+    return 2 * round_up<size_t>(pl.e_elems * 8, 256) + round_up<size_t>(pl.t_elems * 8, 256) +
+           round_up<size_t>(pl.p_elems * 8, 256) + round_up<size_t>(size_t(d) * sizeof(SweepStep), 256) + 1024;
+}
+
+}  // namespace
+
+size_t inner_fused_workspace_bytes(const TTDesc& a, const TTDesc& b) {
+    FusedPlan pl;
+    if (!plan_fused(a, b, &pl)) return 0;
+    return fused_bytes(pl, a.d);
+}
+
+// Returns kUnsupported when the shapes do not qualify (caller falls back to the per-GEMM path).
+int inner_fused(const TTDesc& A, const TTDesc& B, double* out_dev, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    FusedPlan pl;
+    if (!plan_fused(A, B, &pl)) return kUnsupported;
+    if (ws == nullptr || ws_bytes < fused_bytes(pl, A.d)) return kUnsupported;
+    static int coop = -1, max_blocks = 0;
+    if (coop < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        if (cudaFuncSetAttribute(inner_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFusedSmem)) !=
+            cudaSuccess)
+            coop = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, inner_sweep_kernel, FS_NT, kFusedSmem) !=
+            cudaSuccess)
+            max_blocks = 0;
+        cudaGetLastError();
+    }
+    if (!coop || max_blocks < 1) return kUnsupported;
+
+    Workspace W(ws, ws_bytes);
+    double* E0 = W.take<double>(pl.e_elems);
+    double* E1 = W.take<double>(pl.e_elems);
+    double* T = W.take<double>(pl.t_elems);
+    double* P = W.take<double>(pl.p_elems);
+    SweepStep* steps_dev = W.take<SweepStep>(A.d);
+    unsigned* barrier = W.take<unsigned>(64);
+    if (!E0 || !E1 || !T || !P || !steps_dev || !barrier) return kUnsupported;
+
+    TTB_CHECK_CUDA(cudaMemcpyAsync(steps_dev, pl.steps.data(), size_t(A.d) * sizeof(SweepStep),
+                                   cudaMemcpyHostToDevice, stream));
+    TTB_CHECK_CUDA(cudaMemsetAsync(barrier, 0, 256, stream));
+    SweepParams sp;
+    sp.steps = steps_dev;
+    sp.d = A.d;
+    sp.E0 = E0;
+    sp.E1 = E1;
+    sp.T = T;
+    sp.P = P;
+    sp.out = out_dev;
+    sp.barrier = barrier;
+    void* args[] = {&sp};
+    const int slot = profile_begin(stream);
+    TTB_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(inner_sweep_kernel), dim3(num_sms()),
+                                               dim3(FS_NT), args, kFusedSmem, stream));
+    ++g_launch_count;
+    profile_end(slot, pl.flops, stream);
+    return kOk;
+}
+
+}  // namespace ttb

@@ -24,6 +24,11 @@ size_t inner_workspace_bytes(const TTDesc& a, const TTDesc& b);
 int inner(const TTDesc& a, const TTDesc& b, double* out_dev, void* ws, size_t ws_bytes,
           cudaStream_t stream);
 
+// persistent fused sweep (inner_fused.cu); kUnsupported when the shapes do not qualify
+size_t inner_fused_workspace_bytes(const TTDesc& a, const TTDesc& b);
+int inner_fused(const TTDesc& a, const TTDesc& b, double* out_dev, void* ws, size_t ws_bytes,
+                cudaStream_t stream);
+
 // --- dense contraction of a chain (inner.cu) ---
 int tt_to_dense(const TTDesc& a, double* out_dev, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t tt_to_dense_workspace_bytes(const TTDesc& a);
