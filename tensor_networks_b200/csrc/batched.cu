@@ -10,9 +10,9 @@
 // i * r_k n_k r_{k+1} and shards over GPUs are plain slices of dimension 0.
 //
 // inner_batched_kernel (bond ranks <= 32): the environment E (<= 32 x 32) lives in
-// shared memory; for core k each warp takes mode slices s = warp, warp + 8, ... and
-// computes, with DMMA on fragments loaded straight from HBM (every core element is
-// read exactly once -- the kernel is HBM/FP64 balanced at 8 FLOP/B),
+// shared memory; the cores stream through a double-buffered cp.async pipeline in chunks
+// of 4 mode slices (every core element is read exactly once from HBM -- the kernel is
+// HBM/FP64 balanced at 8 FLOP/B); two warps share a slice and compute with DMMA
 //     T^T  = B_k[:, s, :]^T  E^T            (b' x a,  K = b)
 //     E'^T += T^T  A_k[:, s, :]             (b' x a', K = a)
 // The accumulator fragments of the first product are fed directly as the A operand
@@ -31,8 +31,7 @@ namespace ttb {
 
 namespace {
 
-constexpr int IB_NT = 256;
-constexpr int IB_NWARP = IB_NT / 32;
+constexpr int IB_NT = 512;
 constexpr int IB_R = 32;        // max bond rank handled on chip
 constexpr int IB_EP = IB_R + 4; // pitch of E and of the partial buffers
 
@@ -48,90 +47,193 @@ struct InnerBatchParams {
     double* out;
 };
 
-__global__ void __launch_bounds__(IB_NT, 2) inner_batched_kernel(const __grid_constant__ InnerBatchParams p) {
-    __shared__ double E[IB_R * IB_EP];
-    extern __shared__ __align__(16) double red[];  // [IB_NWARP][IB_R][IB_EP]
+// Shared-memory staging: a "chunk" is up to IB_CS mode slices of both cores,
+//   Bst[j][bk][bp] (pitch 36) feeds the A operand of GEMM 1,  Ast[j][ak][ap] (pitch 34) the B
+//   operand of GEMM 2; both pitches make the 64-bit fragment loads bank-conflict free.
+// Chunks are double-buffered with cp.async across cores and items, so HBM latency is hidden
+// behind the DMMA work of the previous chunk.
+constexpr int IB_CS = 4;
+constexpr int IB_BP = 36, IB_AP = 34;
+constexpr int IB_BST = IB_CS * IB_R * IB_BP;
+constexpr int IB_AST = IB_CS * IB_R * IB_AP;
+constexpr int IB_STAGE = IB_BST + IB_AST;
+constexpr int IB_RED = IB_CS * IB_R * IB_EP;
+
+struct ChunkIter {
+    int64_t item;
+    int k, c;
+};
+
+__device__ __forceinline__ bool chunk_valid(const InnerBatchParams& p, const ChunkIter& it) { return it.item < p.batch; }
+
+__device__ __forceinline__ void chunk_advance(const InnerBatchParams& p, ChunkIter& it, int64_t item_stride) {
+    const int nch = (p.n[it.k] + IB_CS - 1) / IB_CS;
+    if (++it.c < nch) return;
+    it.c = 0;
+    if (++it.k < p.d) return;
+    it.k = 0;
+    it.item += item_stride;
+}
+
+__device__ __forceinline__ void chunk_issue(const InnerBatchParams& p, const ChunkIter& it, double* stage) {
+    const int tid = threadIdx.x;
+    const int k = it.k;
+    const int a = p.ra[k], a2 = p.ra[k + 1], b = p.rb[k], b2 = p.rb[k + 1], n = p.n[k];
+    const double* __restrict__ Ak = p.A[k] + it.item * (int64_t(a) * n * a2);
+    const double* __restrict__ Bk = p.B[k] + it.item * (int64_t(b) * n * b2);
+    double* Bst = stage;
+    double* Ast = stage + IB_BST;
+    const int s0 = it.c * IB_CS;
+    {   // B_k slices: rows bk < 4*kt, columns bp < 8*mt
+        const int rows = ((b + 3) >> 2) << 2, cols = ((b2 + 7) >> 3) << 3;
+        const bool vec = ((b2 & 1) == 0) && ((reinterpret_cast<uintptr_t>(Bk) & 15) == 0);
+        if (vec) {
+            // fixed thread -> (row, 16-byte column chunk) map, no divisions: 16 chunks per row,
+            // IB_NT / 16 rows per pass
+            const int cc = (tid & 15) * 2, r0 = tid >> 4;
+#pragma unroll
+            for (int j = 0; j < IB_CS; ++j) {
+                const int sl = s0 + j;
+#pragma unroll
+                for (int rr = 0; rr < IB_R; rr += IB_NT / 16) {
+                    const int bk = r0 + rr;
+                    if (bk < rows && cc < cols) {
+                        const bool ok = sl < n && bk < b && cc < b2;
+                        const double* src = ok ? Bk + (int64_t(bk) * n + sl) * b2 + cc : Bk;
+                        cp_async16(Bst + (j * IB_R + bk) * IB_BP + cc, src, ok);
+                    }
+                }
+            }
+        } else {
+            for (int idx = tid; idx < IB_CS * rows * cols; idx += IB_NT) {
+                const int j = idx / (rows * cols), rem = idx % (rows * cols);
+                const int bk = rem / cols, bp = rem % cols;
+                const int sl = s0 + j;
+                const bool ok = sl < n && bk < b && bp < b2;
+                const double* src = ok ? Bk + (int64_t(bk) * n + sl) * b2 + bp : Bk;
+                cp_async8(Bst + (j * IB_R + bk) * IB_BP + bp, src, ok);
+            }
+        }
+    }
+    {   // A_k slices: rows ak < 8*nt, columns ap < 8*lt
+        const int rows = ((a + 7) >> 3) << 3, cols = ((a2 + 7) >> 3) << 3;
+        const bool vec = ((a2 & 1) == 0) && ((reinterpret_cast<uintptr_t>(Ak) & 15) == 0);
+        if (vec) {
+            const int cc = (tid & 15) * 2, r0 = tid >> 4;
+#pragma unroll
+            for (int j = 0; j < IB_CS; ++j) {
+                const int sl = s0 + j;
+#pragma unroll
+                for (int rr = 0; rr < IB_R; rr += IB_NT / 16) {
+                    const int ak = r0 + rr;
+                    if (ak < rows && cc < cols) {
+                        const bool ok = sl < n && ak < a && cc < a2;
+                        const double* src = ok ? Ak + (int64_t(ak) * n + sl) * a2 + cc : Ak;
+                        cp_async16(Ast + (j * IB_R + ak) * IB_AP + cc, src, ok);
+                    }
+                }
+            }
+        } else {
+            for (int idx = tid; idx < IB_CS * rows * cols; idx += IB_NT) {
+                const int j = idx / (rows * cols), rem = idx % (rows * cols);
+                const int ak = rem / cols, ap = rem % cols;
+                const int sl = s0 + j;
+                const bool ok = sl < n && ak < a && ap < a2;
+                const double* src = ok ? Ak + (int64_t(ak) * n + sl) * a2 + ap : Ak;
+                cp_async8(Ast + (j * IB_R + ak) * IB_AP + ap, src, ok);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(IB_NT, 1) inner_batched_kernel(const __grid_constant__ InnerBatchParams p) {
+    extern __shared__ __align__(16) double sm[];
+    double* stages = sm;                      // [2][IB_STAGE]
+    double* red = sm + 2 * IB_STAGE;          // [IB_CS][IB_R][IB_EP]
+    double* E = red + IB_RED;                 // [IB_R][IB_EP]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2;  // fragment row / column index 0..7
     const int fq = lane & 3;   // fragment k slot 0..3
+    const int wj = warp >> 2;  // slice of the chunk this warp works on
+    const int wi = warp & 3;   // which b' tile (row of T^T tiles)
 
-    for (int64_t item = blockIdx.x; item < p.batch; item += gridDim.x) {
-        for (int idx = tid; idx < IB_R * IB_EP; idx += IB_NT) E[idx] = 0.0;
+    ChunkIter cur{int64_t(blockIdx.x), 0, 0};
+    ChunkIter nxt = cur;
+    if (!chunk_valid(p, cur)) return;
+    chunk_issue(p, cur, stages);
+    cp_async_commit();
+    chunk_advance(p, nxt, gridDim.x);
+
+    double acc[4][2];
+    int t = 0;
+    while (chunk_valid(p, cur)) {
+        if (chunk_valid(p, nxt)) chunk_issue(p, nxt, stages + ((t + 1) & 1) * IB_STAGE);
+        cp_async_commit();
+        if (cur.k == 0 && cur.c == 0) {  // new item: E = [1]
+            for (int idx = tid; idx < IB_R * IB_EP; idx += IB_NT) E[idx] = (idx == 0) ? 1.0 : 0.0;
+        }
+        if (cur.c == 0) {
+#pragma unroll
+            for (int l = 0; l < 4; ++l) acc[l][0] = acc[l][1] = 0.0;
+        }
+        cp_async_wait<1>();
         __syncthreads();
-        if (tid == 0) E[0] = 1.0;
-        __syncthreads();
 
-        for (int k = 0; k < p.d; ++k) {
-            const int a = p.ra[k], a2 = p.ra[k + 1], b = p.rb[k], b2 = p.rb[k + 1], n = p.n[k];
-            const double* __restrict__ Ak = p.A[k] + item * (int64_t(a) * n * a2);
-            const double* __restrict__ Bk = p.B[k] + item * (int64_t(b) * n * b2);
-            const int mt = (b2 + 7) >> 3;  // tiles over b'
-            const int nt = (a + 7) >> 3;   // tiles over a
-            const int kt = (b + 3) >> 2;   // k steps over b
-            const int lt = (a2 + 7) >> 3;  // tiles over a'
-
-            double acc[4][4][2];
+        const int k = cur.k;
+        const int a = p.ra[k], a2 = p.ra[k + 1], b = p.rb[k], b2 = p.rb[k + 1], n = p.n[k];
+        const int mt = (b2 + 7) >> 3, nt = (a + 7) >> 3, kt = (b + 3) >> 2, lt = (a2 + 7) >> 3;
+        const double* Bst = stages + (t & 1) * IB_STAGE + wj * IB_R * IB_BP;
+        const double* Ast = stages + (t & 1) * IB_STAGE + IB_BST + wj * IB_R * IB_AP;
+        if (cur.c * IB_CS + wj < n && wi < mt) {
+            {
+                const int i = wi;
+                // ---- T^T tile row i: C(i, j) = B_s^T (b' x b) . E^T (b x a) ----
+                double c[4][2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) c[j][0] = c[j][1] = 0.0;
 #pragma unroll
-                for (int l = 0; l < 4; ++l) acc[i][l][0] = acc[i][l][1] = 0.0;
-
-            for (int s = warp; s < n; s += IB_NWARP) {
-                const double* __restrict__ Bs = Bk + int64_t(s) * b2;  // B_k[bk][s][bp] = Bs[bk * n * b2 + bp]
-                const double* __restrict__ As = Ak + int64_t(s) * a2;  // A_k[ak][s][ap] = As[ak * n * a2 + ap]
-                const int64_t ldb = int64_t(n) * b2, lda = int64_t(n) * a2;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (i >= mt) break;
-                    // ---- T^T tile row i: C(i, j) for j < nt ----
-                    double c[4][2];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) c[j][0] = c[j][1] = 0.0;
-                    const int bp = 8 * i + fr;
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {
-                        if (kk >= kt) break;
-                        const int bk = 4 * kk + fq;
-                        const double af = (bk < b && bp < b2) ? __ldg(Bs + bk * ldb + bp) : 0.0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (j >= nt) break;
-                            const double bf = E[(8 * j + fr) * IB_EP + bk];  // E^T[bk][aj]
-                            dmma884(c[j][0], c[j][1], af, bf);
-                        }
-                    }
-                    // ---- E'^T(i, l) += C(i, j) . A_s(j, l): C fragments reused as A operand ----
+                for (int kk = 0; kk < 8; ++kk) {
+                    if (kk >= kt) break;
+                    const int bk = 4 * kk + fq;
+                    const double af = Bst[bk * IB_BP + 8 * i + fr];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (j >= nt) break;
-                        const int ak0 = 8 * j + 2 * fq;
+                        dmma884(c[j][0], c[j][1], af, E[(8 * j + fr) * IB_EP + bk]);
+                    }
+                }
+                // ---- E'^T(i, l) += C(i, j) . A_s(j, l): C fragments reused as the A operand ----
 #pragma unroll
-                        for (int l = 0; l < 4; ++l) {
-                            if (l >= lt) break;
-                            const int ap = 8 * l + fr;
-                            const double b0 = (ak0 < a && ap < a2) ? __ldg(As + ak0 * lda + ap) : 0.0;
-                            const double b1 = (ak0 + 1 < a && ap < a2) ? __ldg(As + (ak0 + 1) * lda + ap) : 0.0;
-                            dmma884(acc[i][l][0], acc[i][l][1], c[j][0], b0);
-                            dmma884(acc[i][l][0], acc[i][l][1], c[j][1], b1);
-                        }
+                for (int j = 0; j < 4; ++j) {
+                    if (j >= nt) break;
+                    const double* arow = Ast + (8 * j + 2 * fq) * IB_AP + fr;
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) {
+                        if (l >= lt) break;
+                        dmma884(acc[l][0], acc[l][1], c[j][0], arow[8 * l]);
+                        dmma884(acc[l][0], acc[l][1], c[j][1], arow[IB_AP + 8 * l]);
                     }
                 }
             }
-            // ---- deterministic cross-warp sum: red[warp][ap][bp] = E'^T(bp, ap) ----
-            double* mine = red + warp * (IB_R * IB_EP);
+        }
+        const int nch = (n + IB_CS - 1) / IB_CS;
+        const bool last_chunk = cur.c == nch - 1;
+        if (last_chunk) {
+            // ---- deterministic cross-warp sum: red[slice][ap][bp] = E'^T(bp, ap) ----
+            double* mine = red + wj * (IB_R * IB_EP);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int l = 0; l < 4; ++l) {
-                    if (i < mt && l < lt) {
-                        const int bp = 8 * i + fr, ap = 8 * l + 2 * fq;
-                        mine[ap * IB_EP + bp] = acc[i][l][0];
-                        mine[(ap + 1) * IB_EP + bp] = acc[i][l][1];
-                    }
+            for (int l = 0; l < 4; ++l) {
+                if (wi < mt && l < lt) {
+                    const int bp = 8 * wi + fr, ap = 8 * l + 2 * fq;
+                    mine[ap * IB_EP + bp] = acc[l][0];
+                    mine[(ap + 1) * IB_EP + bp] = acc[l][1];
                 }
-            __syncthreads();
-            const int nw = min(IB_NWARP, n);  // warps that had at least one slice
+            }
+        }
+        __syncthreads();  // stage (t & 1) is free again; partial sums are visible
+        if (last_chunk) {
+            const int nw = min(IB_CS, n);
             for (int idx = tid; idx < IB_R * IB_R; idx += IB_NT) {
                 const int ap = idx / IB_R, bp = idx % IB_R;
                 double v = 0.0;
@@ -141,13 +243,16 @@ __global__ void __launch_bounds__(IB_NT, 2) inner_batched_kernel(const __grid_co
                 E[ap * IB_EP + bp] = v;
             }
             __syncthreads();
+            if (k == p.d - 1 && tid == 0) p.out[cur.item] = E[0];
         }
-        if (tid == 0) p.out[item] = E[0];
-        __syncthreads();
+        cur = nxt;
+        chunk_advance(p, nxt, gridDim.x);
+        ++t;
     }
+    cp_async_wait<0>();
 }
 
-constexpr size_t kInnerBatchSmem = size_t(IB_NWARP) * IB_R * IB_EP * sizeof(double);
+constexpr size_t kInnerBatchSmem = size_t(2 * IB_STAGE + IB_RED + IB_R * IB_EP) * sizeof(double);
 
 }  // namespace
 
@@ -204,7 +309,7 @@ int inner_batched(const TTBatchDesc& a, const TTBatchDesc& b, double* out_dev, v
                                                 int(kInnerBatchSmem)));
             configured = true;
         }
-        const int grid = int(std::min<int64_t>(a.batch, int64_t(num_sms()) * 2));
+        const int grid = int(std::min<int64_t>(a.batch, int64_t(num_sms())));
         inner_batched_kernel<<<grid, IB_NT, kInnerBatchSmem, stream>>>(p);
         ++g_launch_count;
         TTB_CHECK_CUDA(cudaGetLastError());
