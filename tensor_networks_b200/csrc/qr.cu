@@ -26,6 +26,7 @@
 #include "qr.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "gemm.cuh"
@@ -36,6 +37,9 @@ namespace ttb {
 namespace {
 
 using namespace hh;
+
+constexpr int QF_W = 64;  // width of a fast (Cholesky-QR) panel
+constexpr int QF_P = QF_W + 1;
 
 struct TsqrLevelParams {
     double* X;        // (ww x mlen) row-space, leading dimension ldx; tile stored back in place
@@ -120,6 +124,7 @@ __global__ void __launch_bounds__(QR_NT) tsqr_kernel(const TsqrLevelParams p) {
     }
 }
 
+constexpr size_t kCholSmem = 2 * size_t(QF_W) * QF_P * sizeof(double);
 constexpr size_t kSmemFactor = size_t(QR_W) * QR_PITCH * sizeof(double);
 constexpr size_t kSmemApply = 2 * kSmemFactor;
 
@@ -218,6 +223,99 @@ int tsqr_panel(double* P, int ww, int64_t m, int64_t ld, double* R, int64_t ldr,
     return kOk;
 }
 
+// Cholesky-QR panel factor: G = P P^T (w x w) -> L (lower), outputs Rt = L^T (upper, w x w),
+// Linv = L^{-1} (lower, w x w) and status[0] = min_v L_vv / nrm_prev[v]  (DGKS ratio; nrm_prev
+// == nullptr -> 1), status[1] = min_v L_vv / sqrt(G_vv)  (how much of a vector is left after
+// removing the earlier vectors of the same panel: the panel's conditioning), status[2] = 1 on
+// breakdown (non-positive pivot).  One CTA.
+__global__ void __launch_bounds__(256) chol_panel_kernel(const double* __restrict__ G, int w,
+                                                         const double* __restrict__ nrm_prev,
+                                                         double* __restrict__ Rt, double* __restrict__ Linv,
+                                                         double* __restrict__ status) {
+    extern __shared__ __align__(16) double chol_sm[];
+    double* A = chol_sm;
+    double* X = chol_sm + QF_W * QF_P;
+    __shared__ double diag0[QF_W];
+    __shared__ int bad;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < w * w; idx += blockDim.x) A[(idx / w) * QF_P + idx % w] = G[idx];
+    if (tid == 0) bad = 0;
+    __syncthreads();
+    if (tid < w) diag0[tid] = A[tid * QF_P + tid];
+    __syncthreads();
+    for (int j = 0; j < w; ++j) {
+        const double d = A[j * QF_P + j];
+        if (!(d > 0.0)) {
+            if (tid == 0) bad = 1;
+            break;  // uniform: d is read by all threads from shared memory
+        }
+        const double ljj = sqrt(d);
+        const double inv = 1.0 / ljj;
+        __syncthreads();
+        // scale column j
+        for (int i = j + tid; i < w; i += blockDim.x) A[i * QF_P + j] = (i == j) ? ljj : A[i * QF_P + j] * inv;
+        __syncthreads();
+        // trailing update of the lower triangle
+        const int rem = w - j - 1;
+        for (int idx = tid; idx < rem * rem; idx += blockDim.x) {
+            const int i = j + 1 + idx / rem, k = j + 1 + idx % rem;
+            if (k <= i) A[i * QF_P + k] = fma(-A[i * QF_P + j], A[k * QF_P + j], A[i * QF_P + k]);
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (bad) {
+        if (tid == 0) {
+            status[0] = 0.0;
+            status[1] = 0.0;
+            status[2] = 1.0;
+        }
+        return;
+    }
+    // Rt = L^T ; L^{-1} by forward substitution, one column per thread
+    for (int idx = tid; idx < w * w; idx += blockDim.x) {
+        const int r = idx / w, c = idx % w;
+        Rt[idx] = (r <= c) ? A[c * QF_P + r] : 0.0;
+    }
+    if (tid < w) {
+        const int c = tid;
+        for (int i = 0; i < w; ++i) {
+            double s = (i == c) ? 1.0 : 0.0;
+            for (int k = c; k < i; ++k) s = fma(-A[i * QF_P + k], X[k * QF_P + c], s);
+            X[i * QF_P + c] = (i < c) ? 0.0 : s / A[i * QF_P + i];
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < w * w; idx += blockDim.x) Linv[idx] = X[(idx / w) * QF_P + idx % w];
+    if (tid < 32) {
+        double r0 = 1e300, r1 = 1e300;
+        for (int v = tid; v < w; v += 32) {
+            const double l = A[v * QF_P + v];
+            const double prev = nrm_prev ? nrm_prev[v] : 1.0;
+            r0 = fmin(r0, prev > 0.0 ? l / prev : 0.0);
+            r1 = fmin(r1, l / sqrt(diag0[v]));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            r0 = fmin(r0, __shfl_xor_sync(0xffffffffu, r0, o));
+            r1 = fmin(r1, __shfl_xor_sync(0xffffffffu, r1, o));
+        }
+        if (tid == 0) {
+            status[0] = r0;
+            status[1] = r1;
+            status[2] = 0.0;
+        }
+    }
+}
+
+int configure_chol() {
+    static bool done = false;
+    if (done) return kOk;
+    TTB_CHECK_CUDA(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCholSmem)));
+    done = true;
+    return kOk;
+}
+
 // One BCGS pass of a panel, coefficient bookkeeping.  With P = C Qp + Rp^T Qnew applied on
 // top of the passes already accumulated (vectors = Rb^T Qp + Rd_old^T P):
 //     R[0:j0, panel] += C^T Rd_old          (skipped when C == nullptr, i.e. j0 == 0)
@@ -227,7 +325,7 @@ __global__ void accumulate_r_kernel(double* __restrict__ R, int64_t ldr, int64_t
                                     const double* __restrict__ C, int64_t ldcc,
                                     const double* __restrict__ Rp, const double* __restrict__ Rd_old,
                                     double* __restrict__ Rd_new) {
-    __shared__ double rd[QR_W * QR_W];
+    __shared__ double rd[QF_W * QF_W];
     for (int i = threadIdx.x; i < w * w; i += blockDim.x) rd[i] = Rd_old[i];
     __syncthreads();
     const int64_t total = (j0 + w) * w;
@@ -236,13 +334,19 @@ __global__ void accumulate_r_kernel(double* __restrict__ R, int64_t ldr, int64_t
         const int64_t i = idx / w;
         const int t = int(idx % w);
         if (i < j0) {
-            double s = 0.0;
-            for (int u = 0; u <= t; ++u) s = fma(C[u * ldcc + i], rd[u * w + t], s);
-            R[i * ldr + j0 + t] += s;
+            if (C) {
+                double s = 0.0;
+                for (int u = 0; u <= t; ++u) s = fma(C[u * ldcc + i], rd[u * w + t], s);
+                R[i * ldr + j0 + t] += s;
+            }
         } else {
             const int s_ = int(i - j0);
             double s = 0.0;
-            for (int u = s_; u <= t; ++u) s = fma(Rp[s_ * w + u], rd[u * w + t], s);
+            if (Rp) {
+                for (int u = s_; u <= t; ++u) s = fma(Rp[s_ * w + u], rd[u * w + t], s);
+            } else {
+                s = rd[s_ * w + t];  // Rp = identity
+            }
             const double v = (s_ <= t) ? s : 0.0;
             Rd_new[s_ * w + t] = v;
             R[i * ldr + j0 + t] = v;
@@ -316,17 +420,19 @@ struct OrthLayout {
 
 OrthLayout orth_layout(int64_t c, int64_t m) {
     OrthLayout L;
-    L.cbuf = size_t(QR_W) * size_t(std::max<int64_t>(c, 1));
-    L.rp = L.rd = QR_W * QR_W;
-    L.nrm = 64;
+    L.cbuf = size_t(QF_W) * size_t(std::max<int64_t>(c, 1));
+    L.rp = 4 * QF_W * QF_W;  // Rp / Gram / Linv / spare
+    L.rd = QF_W * QF_W;
+    L.nrm = 128;
     L.tsqr = tsqr_scratch_doubles(m);
-    L.gemm_ws = std::min<size_t>(std::max(gemm_workspace_bytes(QR_W, c, m), gemm_workspace_bytes(c, c, m)),
+    L.gemm_ws = std::min<size_t>(std::max(gemm_workspace_bytes(QF_W, c, m), gemm_workspace_bytes(c, c, m)),
                                  size_t(64) << 20);
     return L;
 }
 
 struct OrthHost {
     unsigned long long* flag = nullptr;  // pinned
+    double* status = nullptr;            // pinned, 4 doubles
 };
 int orth_host(OrthHost* h) {
     static OrthHost g;
@@ -334,6 +440,7 @@ int orth_host(OrthHost* h) {
         void* p = nullptr;
         TTB_CHECK_CUDA(cudaHostAlloc(&p, 64, cudaHostAllocDefault));
         g.flag = static_cast<unsigned long long*>(p);
+        g.status = reinterpret_cast<double*>(static_cast<char*>(p) + 16);
     }
     *h = g;
     return kOk;
@@ -357,6 +464,8 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
     }
     OrthHost host;
     TTB_PROPAGATE(orth_host(&host));
+    TTB_PROPAGATE(configure_tsqr());
+    TTB_PROPAGATE(configure_chol());
     Workspace W(ws, ws_bytes);
     double* Cb = W.take<double>(L.cbuf);
     double* Rp = W.take<double>(L.rp);
@@ -373,7 +482,112 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
     constexpr int kMaxPasses = 6;
     constexpr double kDgks = 0.3;  // reorthogonalise again while a pass removes > 70 % of some vector
 
-    for (int64_t j0 = 0; j0 < kmax; j0 += QR_W) {
+    double* Gm = Rp + QF_W * QF_W;       // Gram of a fast panel
+    double* Linv = Gm + QF_W * QF_W;     // inverse Cholesky factor
+    double* status = nrm[1] + 64;        // device status of chol_panel_kernel
+    static const bool fast_enabled = [] {
+        const char* e = getenv("TTB_QR_FAST");
+        return e == nullptr || e[0] != '0';
+    }();
+
+    // Fast panel: Cholesky-QR2 on up to QF_W vectors (Gram by DMMA GEMM, one-CTA Cholesky, in-place
+    // triangular solve as a GEMM), inside the same DGKS-controlled projection passes.  It is only
+    // taken when the first Cholesky shows a benign panel (every vector keeps >= 5 % of its norm
+    // against the earlier vectors of the panel, no breakdown); otherwise -- rank-deficient X (+) X
+    // inputs, duplicates, zero vectors -- the panel is handed to the Householder TSQR path below,
+    // which has no conditioning requirement.  Returns 1 = done, 0 = declined (P was projected once
+    // and R already carries that projection), < 0 = error.
+    auto fast_panel = [&](int64_t j0, int w) -> int {
+        double* P = M + j0 * ldm;
+        set_identity_small_kernel<<<1, 256, 0, stream>>>(Rd[0], w);
+        ++g_launch_count;
+        int cur = 0;
+        if (j0 > 0) {
+            rownorm_kernel<<<w, 256, 0, stream>>>(P, m, ldm, nullptr, nrm[0], nullptr);
+            ++g_launch_count;
+        }
+        for (int pass = 1; pass <= kMaxPasses; ++pass) {
+            if (j0 > 0) {
+                GemmArgs g;  // C (w x j0) = P . Qp^T
+                g.M = w; g.N = j0; g.K = m;
+                g.A = P; g.sAm = ldm; g.sAk = 1;
+                g.B = M; g.sBk = 1; g.sBn = ldm;
+                g.C = Cb; g.ldc = j0;
+                if (gemm(g, gws, gws_bytes, stream) != kOk) return -1;
+                GemmArgs u;  // P -= C . Qp
+                u.M = w; u.N = m; u.K = j0;
+                u.A = Cb; u.sAm = j0; u.sAk = 1;
+                u.B = M; u.sBk = ldm; u.sBn = 1;
+                u.C = P; u.ldc = ldm;
+                u.alpha = -1.0; u.beta = 1.0;
+                if (gemm(u, gws, gws_bytes, stream) != kOk) return -1;
+            }
+            for (int rep = 0; rep < 2; ++rep) {  // Cholesky-QR twice
+                GemmArgs gg;  // G = P P^T
+                gg.M = w; gg.N = w; gg.K = m;
+                gg.A = P; gg.sAm = ldm; gg.sAk = 1;
+                gg.B = P; gg.sBk = 1; gg.sBn = ldm;
+                gg.C = Gm; gg.ldc = w;
+                if (gemm(gg, gws, gws_bytes, stream) != kOk) return -1;
+                const bool first = rep == 0;
+                chol_panel_kernel<<<1, 256, kCholSmem, stream>>>(Gm, w, (first && pass == 1 && j0 > 0) ? nrm[0] : nullptr, Rp,
+                                                         Linv, first ? status : status + 4);
+                ++g_launch_count;
+                if (first) {
+                    if (cudaMemcpyAsync(host.status, status, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream) !=
+                            cudaSuccess ||
+                        cudaStreamSynchronize(stream) != cudaSuccess)
+                        return -1;
+                    const bool broke = host.status[2] != 0.0;
+                    const bool ill = !(host.status[1] >= 0.05);
+                    if (broke || ill) {
+                        if (pass > 1) return -2;  // cannot happen for near-orthonormal rows; refuse loudly
+                        if (j0 > 0) {  // keep the projection that was already applied to P
+                            const int64_t total = (j0 + w) * w;
+                            const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(total, 128), 1024));
+                            accumulate_r_kernel<<<blocks, 128, 0, stream>>>(R, ldr, j0, w, Cb, j0, nullptr, Rd[cur],
+                                                                            Rd[cur ^ 1]);
+                            ++g_launch_count;
+                        }
+                        return 0;
+                    }
+                }
+                GemmArgs sv;  // P <- Linv P  (one M tile, no split: safe in place)
+                sv.M = w; sv.N = m; sv.K = w;
+                sv.A = Linv; sv.sAm = w; sv.sAk = 1;
+                sv.B = P; sv.sBk = ldm; sv.sBn = 1;
+                sv.C = P; sv.ldc = ldm;
+                sv.force_tile = kTile64x64;
+                sv.force_splits = 1;
+                if (gemm(sv, nullptr, 0, stream) != kOk) return -1;
+                const int64_t total = (j0 + w) * w;
+                const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(total, 128), 1024));
+                accumulate_r_kernel<<<blocks, 128, 0, stream>>>(R, ldr, j0, w, (first && j0 > 0) ? Cb : nullptr, j0, Rp,
+                                                                Rd[cur], Rd[cur ^ 1]);
+                ++g_launch_count;
+                cur ^= 1;
+            }
+            if (cudaGetLastError() != cudaSuccess) return -1;
+            if (j0 == 0) break;
+            if (host.status[0] >= kDgks) break;  // DGKS: this pass removed < 70 % of every vector
+        }
+        return 1;
+    };
+
+    int64_t j0 = 0;
+    while (j0 < kmax) {
+        if (fast_enabled && m >= 2 * QF_W) {
+            const int wf = int(std::min<int64_t>(QF_W, kmax - j0));
+            const int fs = fast_panel(j0, wf);
+            if (fs < 0) {
+                set_last_error("orth_rows: Cholesky-QR panel failed (status " + std::to_string(fs) + ")");
+                return fs == -2 ? kNotConverged : kCudaError;
+            }
+            if (fs == 1) {
+                j0 += wf;
+                continue;
+            }
+        }
         const int w = int(std::min<int64_t>(QR_W, kmax - j0));
         double* P = M + j0 * ldm;
         set_identity_small_kernel<<<1, 256, 0, stream>>>(Rd[0], w);
@@ -419,6 +633,7 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
             memcpy(&ratio, host.flag, sizeof(double));
             if (ratio >= kDgks) break;
         }
+        j0 += w;
     }
     if (c > kmax) {
         // vectors kmax..c-1 lie in span(Q): R[0:kmax, kmax:c] = Q . M[kmax:c, :]^T, rows zeroed

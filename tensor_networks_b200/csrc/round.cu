@@ -17,7 +17,9 @@
 #include "round.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "gemm.cuh"
@@ -27,6 +29,28 @@
 namespace ttb {
 
 namespace {
+
+// TTB_DEBUG=1: wall-clock phase timers (each tick synchronises the stream -- debug only)
+struct PhaseTimer {
+    bool on;
+    cudaStream_t stream;
+    std::chrono::steady_clock::time_point t0;
+    explicit PhaseTimer(cudaStream_t s) : on(getenv("TTB_DEBUG") != nullptr), stream(s) {
+        if (on) {
+            cudaStreamSynchronize(stream);
+            t0 = std::chrono::steady_clock::now();
+        }
+    }
+    double tick() {
+        if (!on) return 0.0;
+        cudaStreamSynchronize(stream);
+        const auto t1 = std::chrono::steady_clock::now();
+        const double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        t0 = t1;
+        return ms;
+    }
+};
+double g_t_qr = 0, g_t_jac = 0, g_t_rest = 0, g_t_rq = 0, g_t_push = 0;
 
 __global__ void transpose_kernel(const double* __restrict__ in, int64_t rows, int64_t cols, int64_t ldi,
                                  double* __restrict__ out, int64_t ldo) {
@@ -136,6 +160,7 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
     const size_t rest = ws_bytes - W.off;
     void* sub = W.base + W.off;
 
+    PhaseTimer pt(stream);
     double* X;  // rows to rotate (p x q)
     if (path == kPathTall) {
         // M^T (c x m): rows orthonormalised in place, R (c x c) holds M^T = Q^T R  =>  M = Q_col R
@@ -154,9 +179,11 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
             X = big;
         }
     }
+    g_t_qr += pt.tick();
     int sweeps = 0;
     const int jst = jacobi_rows(X, p, q, q, J, jacobi_abs_tol, 40, &sweeps, conv, hw.conv, stream);
     if (jst != kOk && jst != kNotConverged) return jst;
+    g_t_jac += pt.tick();
     TTB_PROPAGATE(svd_select(X, p, q, q, delta, with_normalizing ? 1 : 0, max_rank, perm, sigma, info, nrm2,
                              stream));
     TTB_CHECK_CUDA(cudaMemcpyAsync(hw.info, info, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -198,6 +225,7 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
         // U (m x rho) = J^T[:, sel]  -> U[i][s] = J[perm[s]][i]
         TTB_PROPAGATE(gather_rows(J, p, perm, rho, p, U_out, rho, true, stream));
     }
+    g_t_rest += pt.tick();
     return kOk;
 }
 
@@ -297,12 +325,15 @@ int round_tt(const TTDesc& t, double eps, int max_rank, int64_t* ranks_out, doub
     void* sub = W.base + W.off;
 
     // ---- RQ pass (pytens/algs.py:1864-1867) ----
+    PhaseTimer pt(stream);
+    g_t_qr = g_t_jac = g_t_rest = g_t_rq = g_t_push = 0;
     for (int k = d - 1; k >= 1; --k) {
         int64_t c_new = r[k];
         TTB_PROPAGATE(right_orth_step(t.core[k], r[k], t.n[k] * r[k + 1], t.core[k - 1], r[k - 1] * t.n[k - 1],
                                       /*shrink=*/true, &c_new, sub, rest, stream));
         r[k] = c_new;
     }
+    g_t_rq += pt.tick();
 
     // ---- forward truncation sweep (pytens/algs.py:1869-1901) ----
     double delta_abs = 0.0, fro = 0.0;
@@ -337,6 +368,11 @@ int round_tt(const TTDesc& t, double eps, int max_rank, int64_t* ranks_out, doub
         TTB_PROPAGATE(gemm(g, sub, rest, stream));
         TTB_CHECK_CUDA(cudaMemcpyAsync(t.core[k + 1], tmp, size_t(rho) * ncols * 8, cudaMemcpyDeviceToDevice, stream));
         r[k + 1] = rho;
+    }
+    if (pt.on) {
+        const double fwd = pt.tick();
+        fprintf(stderr, "[round] RQ pass %.2f ms | forward %.2f ms: qr %.2f, jacobi %.2f, select+U %.2f, carry+other %.2f\n",
+                g_t_rq, fwd, g_t_qr, g_t_jac, g_t_rest, fwd - g_t_qr - g_t_jac - g_t_rest);
     }
     for (int k = 0; k <= d; ++k) ranks_out[k] = r[k];
     if (delta_out) *delta_out = delta_abs;

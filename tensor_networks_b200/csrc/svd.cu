@@ -75,8 +75,10 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_block_kernel(const JacobiPara
     const int R2 = 2 * p.b;
     double* G = T + size_t(R2) * p.pitch;   // [R2][JB_GP]
     double* W = G + JB_MAXR * JB_GP;        // [R2][JB_GP]
-    __shared__ double rot_c[JB_MAXR / 2], rot_s[JB_MAXR / 2];
-    __shared__ int rot_i[JB_MAXR / 2], rot_j[JB_MAXR / 2];
+    double* G2 = W + JB_MAXR * JB_GP;       // ping-pong partners
+    double* W2 = G2 + JB_MAXR * JB_GP;
+    __shared__ double rot_a[JB_MAXR], rot_b[JB_MAXR];
+    __shared__ int rot_p[JB_MAXR];
     __shared__ double blk_max;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -86,21 +88,43 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_block_kernel(const JacobiPara
         return (a < p.b) ? bi * p.b + a : bj * p.b + (a - p.b);
     };
 
-    // ---- stage rows ----
-    for (int a = warp; a < R2; a += JB_NWARP) {
-        const int gr = grow(a);
-        double* t = T + size_t(a) * p.pitch;
-        const bool live = gr < p.p;
-        const double* xr = p.X + int64_t(gr) * p.ldx;
-        const double* jr = p.J + int64_t(gr) * p.p;
-        for (int k = lane; k < p.qx; k += 32) t[k] = (live && k < p.q) ? xr[k] : 0.0;
-        for (int k = lane; k < p.ncol - p.qx; k += 32) t[p.qx + k] = (live && k < p.p) ? jr[k] : 0.0;
+    // ---- stage rows (cp.async: all copies in flight at once, zero-filled padding) ----
+    const bool vec_ok = ((p.ldx & 1) == 0) && ((p.q & 1) == 0) && ((p.p & 1) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.J) & 15) == 0);
+    if (vec_ok) {
+        const int cpr = p.ncol >> 1;  // 16-byte chunks per staged row
+        for (int idx = tid; idx < R2 * cpr; idx += JB_NT) {
+            const int a = idx / cpr, k = (idx % cpr) * 2;
+            const int gr = grow(a);
+            const bool live = gr < p.p;
+            double* dst = T + size_t(a) * p.pitch + k;
+            if (k < p.qx) {
+                const bool ok = live && k < p.q;
+                cp_async16(dst, ok ? p.X + int64_t(gr) * p.ldx + k : p.X, ok);
+            } else {
+                const int kk = k - p.qx;
+                const bool ok = live && kk < p.p;
+                cp_async16(dst, ok ? p.J + int64_t(gr) * p.p + kk : p.J, ok);
+            }
+        }
+        cp_async_commit();
+    } else {
+        for (int a = warp; a < R2; a += JB_NWARP) {
+            const int gr = grow(a);
+            double* t = T + size_t(a) * p.pitch;
+            const bool live = gr < p.p;
+            const double* xr = p.X + int64_t(gr) * p.ldx;
+            const double* jr = p.J + int64_t(gr) * p.p;
+            for (int k = lane; k < p.qx; k += 32) t[k] = (live && k < p.q) ? xr[k] : 0.0;
+            for (int k = lane; k < p.ncol - p.qx; k += 32) t[p.qx + k] = (live && k < p.p) ? jr[k] : 0.0;
+        }
     }
     for (int idx = tid; idx < JB_MAXR * JB_GP; idx += JB_NT) {
         G[idx] = 0.0;
         W[idx] = 0.0;
     }
     if (tid == 0) blk_max = 0.0;
+    cp_async_wait<0>();
     __syncthreads();
     if (tid < R2) W[tid * JB_GP + tid] = 1.0;
 
@@ -135,6 +159,14 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_block_kernel(const JacobiPara
     __syncthreads();
 
     // ---- cyclic two-sided Jacobi sweeps on G, accumulating W (rows) ----
+    // Per round: (1) R2/2 threads compute the rotations, (2) every element of G' = Rot G Rot^T and
+    // W' = Rot W is produced from the OLD matrices (ping-pong buffers), so a round costs two
+    // block barriers.  ra/rb/rp describe row k of the rotation: row_k' = ra row_k + rb row_{rp}.
+    double* Gc = G;   // current / next buffers, swapped by value (no indexed pointer arrays:
+    double* Gn = G2;  // those end up in local memory)
+    double* Wc = W;
+    double* Wn = W2;
+    int gcur = 0;
     const int npairs = R2 / 2;
     bool any_rot = false;
     for (int sw = 0; sw < p.inner_sweeps; ++sw) {
@@ -142,57 +174,54 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_block_kernel(const JacobiPara
             if (tid < npairs) {
                 int i, j;
                 rr_pair(R2, rd, tid, i, j);
-                const double a = G[i * JB_GP + i], b = G[j * JB_GP + j], c = G[i * JB_GP + j];
+                const double a = Gc[i * JB_GP + i], b = Gc[j * JB_GP + j], c = Gc[i * JB_GP + j];
                 double cs = 1.0, sn = 0.0;
                 if (a > 0.0 && b > 0.0 && c != 0.0) {
-                    const double rel = fabs(c) / sqrt(a * b);
-                    const bool small_abs = c * c <= p.abs_tol2 * fmax(a, b);
+                    const double ab = a * b;
+                    const double c2 = c * c;
+                    const bool small_abs = c2 <= p.abs_tol2 * fmax(a, b);
                     if (sw == 0 && !small_abs) {
+                        const double rel = fabs(c) * rsqrt(ab);
                         // non-negative doubles order like their bit patterns
                         atomicMax(reinterpret_cast<unsigned long long*>(&blk_max),
                                   static_cast<unsigned long long>(__double_as_longlong(rel)));
                     }
-                    if (rel > p.tol && !small_abs) {
-                        const double zeta = (b - a) / (2.0 * c);
-                        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                        cs = 1.0 / sqrt(1.0 + t * t);
+                    if (c2 > p.tol * p.tol * ab && !small_abs) {
+                        // tan(theta) = 2c / (tau + sign(tau) sqrt(tau^2 + 4 c^2)), tau = b - a
+                        const double tau = b - a;
+                        const double tc = 2.0 * c;
+                        const double t = tc / (tau + copysign(sqrt(fma(tau, tau, tc * tc)), tau));
+                        cs = rsqrt(fma(t, t, 1.0));
                         sn = cs * t;
                     }
                 }
-                rot_i[tid] = i;
-                rot_j[tid] = j;
-                rot_c[tid] = cs;
-                rot_s[tid] = sn;
+                rot_a[i] = cs;  rot_b[i] = -sn; rot_p[i] = j;
+                rot_a[j] = cs;  rot_b[j] = sn;  rot_p[j] = i;
             }
             __syncthreads();
-            // row rotations of G and W: rows (i, j) <- (cs*ri - sn*rj, sn*ri + cs*rj)
-            for (int idx = tid; idx < npairs * R2 * 2; idx += JB_NT) {
-                const int pr = idx / (2 * R2);
-                const int rem = idx % (2 * R2);
-                const double sn = rot_s[pr];
-                if (sn == 0.0) continue;
-                const double cs = rot_c[pr];
-                double* Mx = (rem < R2) ? G : W;
-                const int col = rem % R2;
-                const int i = rot_i[pr], j = rot_j[pr];
-                const double vi = Mx[i * JB_GP + col], vj = Mx[j * JB_GP + col];
-                Mx[i * JB_GP + col] = cs * vi - sn * vj;
-                Mx[j * JB_GP + col] = sn * vi + cs * vj;
+            for (int idx = tid; idx < R2 * R2; idx += JB_NT) {
+                const int k = idx / R2, l = idx % R2;
+                const double ak = rot_a[k], bk = rot_b[k], al = rot_a[l], bl = rot_b[l];
+                const int pk = rot_p[k], pl = rot_p[l];
+                const double gkl = Gc[k * JB_GP + l], gkp = Gc[k * JB_GP + pl];
+                const double gpl = Gc[pk * JB_GP + l], gpp = Gc[pk * JB_GP + pl];
+                Gn[k * JB_GP + l] = ak * (al * gkl + bl * gkp) + bk * (al * gpl + bl * gpp);
+                Wn[k * JB_GP + l] = ak * Wc[k * JB_GP + l] + bk * Wc[pk * JB_GP + l];
             }
-            __syncthreads();
-            // column rotations of G
-            for (int idx = tid; idx < npairs * R2; idx += JB_NT) {
-                const int pr = idx / R2, row = idx % R2;
-                const double sn = rot_s[pr];
-                if (sn == 0.0) continue;
-                const double cs = rot_c[pr];
-                const int i = rot_i[pr], j = rot_j[pr];
-                const double vi = G[row * JB_GP + i], vj = G[row * JB_GP + j];
-                G[row * JB_GP + i] = cs * vi - sn * vj;
-                G[row * JB_GP + j] = sn * vi + cs * vj;
+            {
+                double* tg = Gc; Gc = Gn; Gn = tg;
+                double* tw = Wc; Wc = Wn; Wn = tw;
             }
+            gcur ^= 1;
             __syncthreads();
         }
+    }
+    if (gcur) {  // results live in the second buffers: W is what the apply phase reads
+        for (int idx = tid; idx < R2 * R2; idx += JB_NT) {
+            const int k = idx / R2, l = idx % R2;
+            W[k * JB_GP + l] = W2[k * JB_GP + l];
+        }
+        __syncthreads();
     }
     // did anything rotate?  (W != I)
     {
@@ -353,7 +382,7 @@ int pick_block(int p, int q, int* ncol_out, int* qx_out, size_t* smem_out) {
     cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (maxsm <= 0) maxsm = 227 * 1024;
     for (int R2 = JB_MAXR; R2 >= 8; R2 /= 2) {
-        const size_t bytes = (size_t(R2) * pitch + 2 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
+        const size_t bytes = (size_t(R2) * pitch + 4 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
         if (bytes + 2048 <= size_t(maxsm)) {
             *ncol_out = ncol;
             *qx_out = qx;
@@ -404,11 +433,11 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
     jp.b = b;
     jp.nb = nb;
     jp.pitch = jp.ncol + 4;
-    jp.inner_sweeps = (nb == 2) ? 3 : 2;
+    jp.inner_sweeps = (nb == 2) ? 2 : 1;
     jp.tol = 1e-15 * std::sqrt(double(std::max(q, 16)));
     jp.abs_tol2 = abs_tol * abs_tol;
     jp.conv = conv_dev;
-    smem = (size_t(2 * b) * jp.pitch + 2 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
+    smem = (size_t(2 * b) * jp.pitch + 4 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
     static size_t configured = 0;
     if (smem > configured) {
         TTB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
