@@ -103,12 +103,18 @@ __device__ int jacobi_rows_smem(double* __restrict__ X, double* __restrict__ J, 
                     g += __shfl_xor_sync(hmask, g, o);
                 }
                 if (a > 0.0 && b > 0.0 && g != 0.0) {
-                    const double rel = fabs(g) / sqrt(a * b);
-                    worst = fmax(worst, rel);
-                    if (rel > tol) {
-                        const double zeta = (b - a) / (2.0 * g);
-                        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                        const double cs = 1.0 / sqrt(1.0 + t * t);
+                    // 2 x 2 problem scaled by a power of two so that max(a, b) is in [1, 2)
+                    const double sc = pow2_scale(fmax(a, b));
+                    const double as = a * sc, bs = b * sc, gs = g * sc;
+                    const double ab = as * bs;
+                    const double rel2 = (ab > 1e-30) ? gs * gs * fast_rcp(ab) : gs * gs / ab;
+                    worst = fmax(worst, rel2);
+                    if (rel2 > tol * tol) {
+                        const double tau = bs - as;
+                        const double tc = 2.0 * gs;
+                        const double h2 = fma(tau, tau, tc * tc);
+                        const double t = tc * fast_rcp(tau + copysign(h2 * fast_rsqrt(h2), tau));
+                        const double cs = fast_rsqrt(fma(t, t, 1.0));
                         const double sn = cs * t;
                         for (int k = l; k < c; k += 16) {
                             const double u = xi[k], v = xj[k];
@@ -129,18 +135,19 @@ __device__ int jacobi_rows_smem(double* __restrict__ X, double* __restrict__ J, 
         }
         if (worst > 0.0) atomicMax(flag, static_cast<unsigned long long>(__double_as_longlong(worst)));
         __syncthreads();
-        const double mx = __longlong_as_double(static_cast<long long>(*flag));
+        const double mx = sqrt(__longlong_as_double(static_cast<long long>(*flag)));  // flag holds rel^2
         __syncthreads();
-        if (mx <= tol) return sweep + 1;
+        // quadratic convergence: once the largest pre-rotation off-diagonal of a sweep is below
+        // 1e-9 the rotations of that sweep have already pushed it to the 1e-18 level
+        if (mx <= fmax(tol, 1e-9)) return sweep + 1;
     }
     return max_sweeps + 1;
 }
 
-__global__ void __launch_bounds__(RB_NT, 1) round_batched_kernel(const __grid_constant__ RoundBatchParams p) {
+__global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_constant__ RoundBatchParams p) {
     extern __shared__ __align__(16) double sm[];
     double* As = sm;
-    double* Bs = As + QR_W * QR_PITCH;
-    double* Rm = Bs + QR_W * QR_PITCH;  // R factor / rows handed to Jacobi
+    double* Rm = As + QR_W * QR_PITCH;  // R factor / rows handed to Jacobi
     double* Jm = Rm + 32 * RB_SP;
     double* Cm = Jm + 32 * RB_SP;       // carry diag(s) V^T
     __shared__ double sdot[QR_W], arow[QR_W], tau_s[QR_W], nrm2[32], sig[32];
@@ -193,13 +200,9 @@ __global__ void __launch_bounds__(RB_NT, 1) round_batched_kernel(const __grid_co
                 const int j = idx / RB_SP, i = idx % RB_SP;
                 Rm[idx] = (j < nsteps && i < c && j <= i) ? As[i * QR_PITCH + j] : 0.0;
             }
-            for (int idx = tid; idx < ww * QR_H; idx += RB_NT) {
-                const int v = idx / QR_H, i = idx % QR_H;
-                Bs[v * QR_PITCH + i] = (i == v) ? 1.0 : 0.0;
-            }
             __syncthreads();
-            for (int j = nsteps - 1; j >= 0; --j) house_apply(As, Bs, ww, hlen, j, tau_s[j], sdot);
-            for (int idx = tid; idx < nsteps * m; idx += RB_NT) core[idx] = Bs[(idx / m) * QR_PITCH + idx % m];
+            house_formq_inplace(As, nsteps, hlen, tau_s, sdot);
+            for (int idx = tid; idx < nsteps * m; idx += RB_NT) core[idx] = As[(idx / m) * QR_PITCH + idx % m];
             if (tid == 0) rq[k] = nsteps;
             __syncthreads();
         }
@@ -249,12 +252,8 @@ __global__ void __launch_bounds__(RB_NT, 1) round_batched_kernel(const __grid_co
                 const int i = idx / RB_SP, j = idx % RB_SP;
                 Rm[idx] = (i < psv && j < c && i <= j) ? As[j * QR_PITCH + i] : 0.0;
             }
-            for (int idx = tid; idx < ww * QR_H; idx += RB_NT) {
-                const int v = idx / QR_H, i = idx % QR_H;
-                Bs[v * QR_PITCH + i] = (i == v) ? 1.0 : 0.0;
-            }
             __syncthreads();
-            for (int j = psv - 1; j >= 0; --j) house_apply(As, Bs, ww, hlen, j, tau_s[j], sdot);
+            house_formq_inplace(As, psv, hlen, tau_s, sdot);
 
             const double tol = 1e-15 * sqrt(double(max(c, 16)));
             const int sweeps = jacobi_rows_smem(Rm, Jm, psv, c, tol, 40, &flag);
@@ -307,7 +306,7 @@ __global__ void __launch_bounds__(RB_NT, 1) round_batched_kernel(const __grid_co
             for (int i = tid; i < mrows; i += RB_NT) {
                 double qv[32];
 #pragma unroll
-                for (int t = 0; t < 32; ++t) qv[t] = (t < psv) ? Bs[t * QR_PITCH + i] : 0.0;
+                for (int t = 0; t < 32; ++t) qv[t] = (t < psv) ? As[t * QR_PITCH + i] : 0.0;
                 for (int s = 0; s < rho_new; ++s) {
                     const double* jr = Jm + perm[s] * RB_SP;
                     double u = 0.0;
@@ -353,7 +352,7 @@ __global__ void __launch_bounds__(RB_NT, 1) round_batched_kernel(const __grid_co
     }
 }
 
-constexpr size_t kRoundBatchSmem = (2 * size_t(QR_W) * QR_PITCH + 3 * 32 * RB_SP) * sizeof(double);
+constexpr size_t kRoundBatchSmem = (size_t(QR_W) * QR_PITCH + 3 * 32 * RB_SP) * sizeof(double);
 
 bool fits_small(const TTBatchDesc& t) {
     if (t.d > kMaxDR) return false;
@@ -400,7 +399,7 @@ int round_batched(const TTBatchDesc& t, double eps, int max_rank, int64_t* ranks
                                                 int(kRoundBatchSmem)));
             configured = true;
         }
-        const int grid = int(std::min<int64_t>(t.batch, int64_t(num_sms())));
+        const int grid = int(std::min<int64_t>(t.batch, int64_t(num_sms()) * 2));
         round_batched_kernel<<<grid, RB_NT, kRoundBatchSmem, stream>>>(p);
         ++g_launch_count;
         TTB_CHECK_CUDA(cudaGetLastError());

@@ -123,6 +123,42 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// ---------------------------------------------------------------------------
+// Fast fp64 reciprocal / reciprocal square root / square root for the strictly sequential
+// critical paths (Jacobi rotation parameters, Householder norms): a single-precision
+// hardware seed (MUFU) + two Newton steps in fp64 gives ~1e-27 relative error before the
+// final rounding, i.e. results within 1-2 ulp, at a fraction of the latency of the
+// ~30-instruction library sequences.  The *_any variants first scale the argument into
+// [1, 4) with an exact power of two, so they accept any positive normal double.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double x) {  // x in float range
+    double r = double(__frcp_rn(float(x)));
+    r = r * fma(-x, r, 2.0);
+    r = r * fma(-x, r, 2.0);
+    return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {  // x in float range
+    double y = double(rsqrtf(float(x)));
+    const double hx = 0.5 * x;
+    y = y * fma(-hx, y * y, 1.5);
+    y = y * fma(-hx, y * y, 1.5);
+    return y;
+}
+__device__ __forceinline__ int dbl_exponent(double x) { return ((__double2hiint(x) >> 20) & 0x7ff) - 1023; }
+__device__ __forceinline__ double dbl_pow2(int e) { return __hiloint2double((e + 1023) << 20, 0); }  // 2^e, |e| < 1023
+// 2^(-e) with e = exponent of x (x > 0, normal): x * pow2_scale(x) is in [1, 2)
+__device__ __forceinline__ double pow2_scale(double x) { return dbl_pow2(-dbl_exponent(x)); }
+__device__ __forceinline__ double fast_rcp_any(double x) {  // any normal x != 0
+    const int e = dbl_exponent(fabs(x));
+    const double s = dbl_pow2(-e);
+    return fast_rcp(x * s) * s;
+}
+__device__ __forceinline__ double fast_sqrt_any(double x) {  // any normal x > 0
+    const int e = dbl_exponent(x) & ~1;      // even exponent
+    const double xs = x * dbl_pow2(-e);      // in [1, 4)
+    return xs * fast_rsqrt(xs) * dbl_pow2(e >> 1);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -70,8 +70,9 @@ __device__ __forceinline__ void house_step(double* __restrict__ As, int ww, int 
         return;
     }
     const double alpha = arow[j];
-    const double beta = -copysign(sqrt(nrm2), alpha);
-    const double inv = 1.0 / (beta * (beta - alpha));
+    const double beta = -copysign(fast_sqrt_any(nrm2), alpha);
+    const double inv = fast_rcp_any(beta * (beta - alpha));
+    const double inv_v0 = fast_rcp_any(alpha - beta);  // |alpha - beta| >= |beta| > 0: no cancellation
     const int t = tid;
     if (t >= j && t < hh) {
         const double ut = (t == j) ? (alpha - beta) : xj[t];
@@ -91,9 +92,9 @@ __device__ __forceinline__ void house_step(double* __restrict__ As, int ww, int 
         }
         if (t == j) {
             As[j * QR_PITCH + j] = beta;
-            tau_s[j] = (beta - alpha) / beta;
+            tau_s[j] = (beta - alpha) * fast_rcp_any(beta);
         } else {
-            As[j * QR_PITCH + t] = ut / (alpha - beta);
+            As[j * QR_PITCH + t] = ut * inv_v0;
         }
     }
     __syncthreads();
@@ -153,6 +154,69 @@ __device__ __forceinline__ void house_apply(const double* __restrict__ As, doubl
     __syncthreads();
 }
 
+
+// Form the explicit Q in place over the reflectors (the row-space analogue of LAPACK dorg2r):
+// on entry As holds v_j below the diagonal of vector j (unit diagonal implicit) for j < nq, on
+// exit vector j of As is column j of Q = H_0 ... H_{nq-1} [I; 0].  The upper triangle (R) must
+// have been exported before.  Only vectors < nq are touched.
+__device__ __forceinline__ void house_formq_inplace(double* __restrict__ As, int nq, int hh,
+                                                    const double* __restrict__ tau_s,
+                                                    double* __restrict__ sdot) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int j = nq - 1; j >= 0; --j) {
+        const double tau = tau_s[j];
+        double* vj = As + j * QR_PITCH;
+        if (tau != 0.0 && j + 1 < nq) {
+            constexpr int NC = QR_W / QR_NWARP;
+            double s[NC];
+#pragma unroll
+            for (int t = 0; t < NC; ++t) s[t] = 0.0;
+            for (int i = j + lane; i < hh; i += 32) {
+                const double v = (i == j) ? 1.0 : vj[i];
+#pragma unroll
+                for (int t = 0; t < NC; ++t) {
+                    const int c = j + 1 + warp + QR_NWARP * t;
+                    if (c < nq) s[t] = fma(v, As[c * QR_PITCH + i], s[t]);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int t = 0; t < NC; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], o);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int t = 0; t < NC; ++t) {
+                    const int c = j + 1 + warp + QR_NWARP * t;
+                    if (c < nq) sdot[c] = s[t];
+                }
+            }
+        }
+        __syncthreads();
+        const int t = tid;
+        if (t < hh) {
+            const double vt = (t == j) ? 1.0 : (t > j ? vj[t] : 0.0);
+            if (tau != 0.0 && t >= j) {
+                const double tv = -tau * vt;
+                for (int c0 = j + 1; c0 < nq; c0 += 8) {
+                    double f[8], v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int c = min(c0 + u, nq - 1);
+                        f[u] = sdot[c];
+                        v[u] = As[c * QR_PITCH + t];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (c0 + u < nq) As[(c0 + u) * QR_PITCH + t] = fma(tv, f[u], v[u]);
+                }
+            }
+            // column j of Q: (0 .. 0, 1 - tau, -tau v)
+            vj[t] = (t < j) ? 0.0 : ((t == j) ? 1.0 - tau : -tau * vt);
+        }
+        __syncthreads();
+    }
+}
 
 }  // namespace hh
 }  // namespace ttb

@@ -55,30 +55,6 @@ struct JacobiParams {
     unsigned long long* conv;  // max relative off-diagonal (double bits, non-negative)
 };
 
-// Fast reciprocal / reciprocal square root for normal-range doubles: single-precision hardware
-// seed (MUFU) + two Newton steps in fp64 (relative error ~1e-27 before rounding).  The rotation
-// parameters of the inner Jacobi sweep sit on a strictly sequential critical path, so the
-// ~30-instruction library sqrt / division sequences are replaced by these.
-__device__ __forceinline__ double fast_rcp(double x) {
-    double r = double(__frcp_rn(float(x)));
-    r = r * fma(-x, r, 2.0);
-    r = r * fma(-x, r, 2.0);
-    return r;
-}
-__device__ __forceinline__ double fast_rsqrt(double x) {
-    double y = double(rsqrtf(float(x)));
-    const double hx = 0.5 * x;
-    y = y * fma(-hx, y * y, 1.5);
-    y = y * fma(-hx, y * y, 1.5);
-    return y;
-}
-// 2^(-e) with e = exponent of x (x > 0, normal): scales x into [1, 2) exactly
-__device__ __forceinline__ double pow2_scale(double x) {
-    const int hi = __double2hiint(x);
-    const int e = (hi >> 20) & 0x7ff;
-    return __hiloint2double((2046 - e) << 20, 0);
-}
-
 __device__ __forceinline__ void rr_pair(int n, int round, int k, int& a, int& b) {
     // circle method on n (even) players; k = 0..n/2-1
     if (k == 0) {
