@@ -71,6 +71,18 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
     __syncthreads();
 }
 
+// Pull `rows` rows of `doubles_per_row` contiguous doubles (leading dimension ld) into L2 while the
+// CTA waits at a grid barrier: the core tiles of the next phase do not depend on the values the
+// barrier protects, only the small E / T operands do.
+__device__ __forceinline__ void prefetch_rows_l2(const double* base, int64_t ld, int rows, int doubles_per_row) {
+    const int lines = (doubles_per_row + 15) >> 4;  // 128-byte lines per row
+    for (int idx = threadIdx.x; idx < rows * lines; idx += FS_NT) {
+        const double* ptr = base + int64_t(idx / lines) * ld + int64_t(idx % lines) * 16;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+    }
+}
+constexpr int kPrefetchRows = 3 * BK;  // the first three k tiles of the pipeline
+
 __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[FS_NT / 32];
@@ -113,6 +125,21 @@ __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams
                 else
                     gemm_tile<CfgT, false, false, true>(j, smem);
             }
+            {   // phase 2 streams the other core of this step: warm its first k tiles in L2
+                const int tm2 = (s.a2 + CfgE::BM - 1) / CfgE::BM, tn2 = (s.b2 + CfgE::BN - 1) / CfgE::BN;
+                const int w2 = blockIdx.x;
+                if (w2 < tm2 * tn2 * s.splits) {
+                    const int tile = w2 % (tm2 * tn2), split = w2 / (tm2 * tn2);
+                    const int64_t kb = int64_t(split) * s.kchunk;
+                    if (s.eb_order) {
+                        const int m0 = (tile % tm2) * CfgE::BM;
+                        prefetch_rows_l2(s.A + kb * s.a2 + m0, s.a2, kPrefetchRows, min(CfgE::BM, s.a2 - m0));
+                    } else {
+                        const int n0 = (tile / tm2) * CfgE::BN;
+                        prefetch_rows_l2(s.B + kb * s.b2 + n0, s.b2, kPrefetchRows, min(CfgE::BN, s.b2 - n0));
+                    }
+                }
+            }
             grid_barrier(p.barrier, epoch);
             if (s.eb_order) {
                 A2 = s.A; B2 = p.T; K2 = int64_t(s.a) * s.n;   // E' = A_k (a n x a')^T . T (a n x b')
@@ -143,6 +170,19 @@ __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams
                 j.kend = min(K2, j.kbeg + int64_t(s.kchunk));
                 j.C = (s.splits > 1) ? p.P + int64_t(split) * s.a2 * s.b2 : Eout;
                 gemm_tile<CfgE, false, false, true>(j, smem);
+            }
+        }
+        if (k + 1 < p.d - 1) {  // phase 1 of the next core streams B_{k+1} (or A_{k+1}): warm L2
+            const SweepStep nx = p.steps[k + 1];
+            const int64_t N1 = int64_t(nx.n) * (nx.eb_order ? nx.b2 : nx.a2);
+            const int M1 = nx.eb_order ? nx.a : nx.b;
+            const int tm1 = (M1 + CfgT::BM - 1) / CfgT::BM;
+            const int tn1 = int((N1 + CfgT::BN - 1) / CfgT::BN);
+            if (int(blockIdx.x) < tm1 * tn1) {
+                const int64_t n0 = int64_t(blockIdx.x / tm1) * CfgT::BN;
+                const int K1 = nx.eb_order ? nx.b : nx.a;
+                prefetch_rows_l2((nx.eb_order ? nx.B : nx.A) + n0, N1, min(kPrefetchRows, K1),
+                                 int(min(int64_t(CfgT::BN), N1 - n0)));
             }
         }
         grid_barrier(p.barrier, epoch);

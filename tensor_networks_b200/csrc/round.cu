@@ -181,7 +181,10 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
     }
     g_t_qr += pt.tick();
     int sweeps = 0;
-    const int jst = jacobi_rows(X, p, q, q, J, jacobi_abs_tol, 40, &sweeps, conv, hw.conv, stream);
+    // rows below 1e-3 delta are discarded whatever happens to them (their total energy is
+    // < 1e-6 p delta^2): no need to orthogonalise them against each other
+    const double noise_floor = (!with_normalizing && delta > 0.0 && jacobi_abs_tol > 0.0) ? 1e-3 * delta : 0.0;
+    const int jst = jacobi_rows(X, p, q, q, J, jacobi_abs_tol, noise_floor, 40, &sweeps, conv, hw.conv, stream);
     if (jst != kOk && jst != kNotConverged) return jst;
     g_t_jac += pt.tick();
     TTB_PROPAGATE(svd_select(X, p, q, q, delta, with_normalizing ? 1 : 0, max_rank, perm, sigma, info, nrm2,

@@ -52,6 +52,7 @@ struct JacobiParams {
     int inner_sweeps;
     double tol;       // relative threshold
     double abs_tol2;  // skip rotation when g_ij^2 <= abs_tol2 * max(g_ii, g_jj)
+    double noise2;    // skip pairs whose rows are both below this squared norm (certain to be truncated)
     unsigned long long* conv;  // max relative off-diagonal (double bits, non-negative)
 };
 
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_block_kernel(const JacobiPara
             if (have) {
                 const double a = Gc[i * JB_GP + i], b = Gc[j * JB_GP + j], c = Gc[i * JB_GP + j];
                 double cs = 1.0, sn = 0.0;
-                if (a > 0.0 && b > 0.0 && c != 0.0) {
+                if (a > 0.0 && b > 0.0 && c != 0.0 && fmax(a, b) > p.noise2) {
                     // scale the 2 x 2 problem by a power of two so that max(a, b) is in [1, 2)
                     const double sc = pow2_scale(fmax(a, b));
                     const double as = a * sc, bs = b * sc, cs_ = c * sc;
@@ -455,7 +456,7 @@ int pick_block(int p, int q, int* ncol_out, int* qx_out, size_t* smem_out) {
 
 size_t jacobi_workspace_bytes(int p) { return round_up<size_t>(size_t(p) * p * 8, 256) + 1024; }
 
-int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol, int max_sweeps,
+int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol, double noise_floor, int max_sweeps,
                 int* sweeps_out, unsigned long long* conv_dev, unsigned long long* conv_host_pinned,
                 cudaStream_t stream) {
     TTB_REQUIRE(X && J && conv_dev && conv_host_pinned, "jacobi_rows: null pointer");
@@ -494,6 +495,7 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
     jp.inner_sweeps = 1;
     jp.tol = 1e-15 * std::sqrt(double(std::max(q, 16)));
     jp.abs_tol2 = abs_tol * abs_tol;
+    jp.noise2 = noise_floor * noise_floor;
     jp.conv = conv_dev;
     smem = (size_t(2 * b) * jp.pitch + 4 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
     static size_t configured = 0;

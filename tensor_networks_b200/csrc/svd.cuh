@@ -8,10 +8,12 @@ namespace ttb {
 // Rotate the rows of X (p x q, row-major, ld = ldx) until mutually orthogonal:
 // X <- J X_in with J (p x p, row-major, ld = p) orthogonal, initialised here.
 // abs_tol: rotations with |g_ij| <= abs_tol * sqrt(max(g_ii, g_jj)) are skipped
-// (0 = purely relative criterion).  conv_dev / conv_host_pinned: one 8-byte
+// (0 = purely relative criterion).  noise_floor: pairs of rows whose norms are BOTH below it
+// are not rotated at all (rows that are certain to be truncated: rotating them among
+// themselves changes neither the retained subspace nor the discarded energy); 0 = off.  conv_dev / conv_host_pinned: one 8-byte
 // device word and one pinned host word used for the per-sweep convergence read.
 // Synchronises `stream` once per sweep.
-int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol, int max_sweeps,
+int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol, double noise_floor, int max_sweeps,
                 int* sweeps_out, unsigned long long* conv_dev, unsigned long long* conv_host_pinned,
                 cudaStream_t stream);
 
