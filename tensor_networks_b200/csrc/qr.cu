@@ -243,6 +243,18 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(const double* __restric
     __syncthreads();
     if (tid < w) diag0[tid] = A[tid * QF_P + tid];
     __syncthreads();
+    if (tid < 32) {
+        // status[3] = max_v ||P_v|| / nrm_prev[v]: how much of the panel is left after the projection
+        // (1e300 when there was no projection); decides the deflation of numerically dependent panels
+        double r3 = nrm_prev ? 0.0 : 1e300;
+        if (nrm_prev)
+            for (int v = tid; v < w; v += 32) {
+                const double prev = nrm_prev[v];
+                r3 = fmax(r3, prev > 0.0 ? sqrt(fmax(diag0[v], 0.0)) / prev : 0.0);
+            }
+        r3 = warp_max(r3);
+        if (tid == 0) status[3] = r3;
+    }
     for (int j = 0; j < w; ++j) {
         const double d = A[j * QF_P + j];
         if (!(d > 0.0)) {
@@ -321,14 +333,18 @@ int configure_chol() {
 //     R[0:j0, panel] += C^T Rd_old          (skipped when C == nullptr, i.e. j0 == 0)
 //     Rd_new = Rp Rd_old  ->  also written to R[j0:j0+w, panel]
 // Rd_old / Rd_new live in scratch (ping-pong) so that no block reads a half-updated factor.
-__global__ void accumulate_r_kernel(double* __restrict__ R, int64_t ldr, int64_t j0, int w,
+// jq = orthonormal rows produced before this panel (row offset in R), jc = index of the panel's first
+// input vector (column offset in R); they differ once panels have been deflated.  diag == 0: only
+// the projection coefficients are accumulated (deflated panel: no new orthonormal rows).
+__global__ void accumulate_r_kernel(double* __restrict__ R, int64_t ldr, int64_t jq, int64_t jc, int w,
                                     const double* __restrict__ C, int64_t ldcc,
                                     const double* __restrict__ Rp, const double* __restrict__ Rd_old,
-                                    double* __restrict__ Rd_new) {
+                                    double* __restrict__ Rd_new, int diag) {
+    const int64_t j0 = jq;
     __shared__ double rd[QF_W * QF_W];
     for (int i = threadIdx.x; i < w * w; i += blockDim.x) rd[i] = Rd_old[i];
     __syncthreads();
-    const int64_t total = (j0 + w) * w;
+    const int64_t total = (j0 + (diag ? w : 0)) * w;
     for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
          idx += int64_t(gridDim.x) * blockDim.x) {
         const int64_t i = idx / w;
@@ -337,7 +353,7 @@ __global__ void accumulate_r_kernel(double* __restrict__ R, int64_t ldr, int64_t
             if (C) {
                 double s = 0.0;
                 for (int u = 0; u <= t; ++u) s = fma(C[u * ldcc + i], rd[u * w + t], s);
-                R[i * ldr + j0 + t] += s;
+                R[i * ldr + jc + t] += s;
             }
         } else {
             const int s_ = int(i - j0);
@@ -349,7 +365,7 @@ __global__ void accumulate_r_kernel(double* __restrict__ R, int64_t ldr, int64_t
             }
             const double v = (s_ <= t) ? s : 0.0;
             Rd_new[s_ * w + t] = v;
-            R[i * ldr + j0 + t] = v;
+            R[i * ldr + jc + t] = v;
         }
     }
 }
@@ -454,7 +470,7 @@ size_t orth_rows_workspace_bytes(int64_t c, int64_t m) {
 }
 
 int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t ldr, void* ws,
-              size_t ws_bytes, cudaStream_t stream) {
+              size_t ws_bytes, cudaStream_t stream, double deflate_tol, int64_t* rank_out) {
     TTB_REQUIRE(M && R, "orth_rows: null pointer");
     TTB_REQUIRE(c >= 1 && m >= 1 && ldm >= m && ldr >= c, "orth_rows: bad extents");
     const OrthLayout L = orth_layout(c, m);
@@ -478,7 +494,6 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
     const size_t gws_bytes = ws_bytes - W.off;
 
     TTB_CHECK_CUDA(cudaMemsetAsync(R, 0, size_t(c - 1) * ldr * 8 + size_t(c) * 8, stream));
-    const int64_t kmax = std::min(c, m);  // at most m orthonormal vectors of length m
     constexpr int kMaxPasses = 6;
     constexpr double kDgks = 0.3;  // reorthogonalise again while a pass removes > 70 % of some vector
 
@@ -489,6 +504,12 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
         const char* e = getenv("TTB_QR_FAST");
         return e == nullptr || e[0] != '0';
     }();
+    static const bool debug = getenv("TTB_DEBUG") != nullptr;
+
+    // jq: orthonormal rows produced so far (they sit compactly in M[0:jq]); jc: input vectors
+    // consumed so far.  They differ once a panel has been deflated; the panel being worked on is
+    // first moved up to M[jq ...].  R row index = orthonormal row, column index = input vector.
+    int64_t jq = 0, jc = 0;
 
     // Fast panel: Cholesky-QR2 on up to QF_W vectors (Gram by DMMA GEMM, one-CTA Cholesky, in-place
     // triangular solve as a GEMM), inside the same DGKS-controlled projection passes.  It is only
@@ -496,27 +517,29 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
     // against the earlier vectors of the panel, no breakdown); otherwise -- rank-deficient X (+) X
     // inputs, duplicates, zero vectors -- the panel is handed to the Householder TSQR path below,
     // which has no conditioning requirement.  Returns 1 = done, 0 = declined (P was projected once
-    // and R already carries that projection), < 0 = error.
-    auto fast_panel = [&](int64_t j0, int w) -> int {
-        double* P = M + j0 * ldm;
+    // and R already carries that projection), 2 = deflated (every vector of the panel is, to
+    // deflate_tol, a combination of the rows already produced: R carries the coefficients and no new
+    // row is emitted), < 0 = error.
+    auto fast_panel = [&](int w) -> int {
+        double* P = M + jq * ldm;
         set_identity_small_kernel<<<1, 256, 0, stream>>>(Rd[0], w);
         ++g_launch_count;
         int cur = 0;
-        if (j0 > 0) {
+        if (jq > 0) {
             rownorm_kernel<<<w, 256, 0, stream>>>(P, m, ldm, nullptr, nrm[0], nullptr);
             ++g_launch_count;
         }
         for (int pass = 1; pass <= kMaxPasses; ++pass) {
-            if (j0 > 0) {
-                GemmArgs g;  // C (w x j0) = P . Qp^T
-                g.M = w; g.N = j0; g.K = m;
+            if (jq > 0) {
+                GemmArgs g;  // C (w x jq) = P . Qp^T
+                g.M = w; g.N = jq; g.K = m;
                 g.A = P; g.sAm = ldm; g.sAk = 1;
                 g.B = M; g.sBk = 1; g.sBn = ldm;
-                g.C = Cb; g.ldc = j0;
+                g.C = Cb; g.ldc = jq;
                 if (gemm(g, gws, gws_bytes, stream) != kOk) return -1;
                 GemmArgs u;  // P -= C . Qp
-                u.M = w; u.N = m; u.K = j0;
-                u.A = Cb; u.sAm = j0; u.sAk = 1;
+                u.M = w; u.N = m; u.K = jq;
+                u.A = Cb; u.sAm = jq; u.sAk = 1;
                 u.B = M; u.sBk = ldm; u.sBn = 1;
                 u.C = P; u.ldc = ldm;
                 u.alpha = -1.0; u.beta = 1.0;
@@ -530,7 +553,7 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                 gg.C = Gm; gg.ldc = w;
                 if (gemm(gg, gws, gws_bytes, stream) != kOk) return -1;
                 const bool first = rep == 0;
-                chol_panel_kernel<<<1, 256, kCholSmem, stream>>>(Gm, w, (first && pass == 1 && j0 > 0) ? nrm[0] : nullptr, Rp,
+                chol_panel_kernel<<<1, 256, kCholSmem, stream>>>(Gm, w, (first && pass == 1 && jq > 0) ? nrm[0] : nullptr, Rp,
                                                          Linv, first ? status : status + 4);
                 ++g_launch_count;
                 if (first) {
@@ -538,15 +561,26 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                             cudaSuccess ||
                         cudaStreamSynchronize(stream) != cudaSuccess)
                         return -1;
+                    const int64_t total = (jq + w) * w;
+                    const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(total, 128), 1024));
+                    if (debug && pass == 1 && jq > 0)
+                        fprintf(stderr, "[orth_rows] panel jc=%lld jq=%lld w=%d residual ratio %.2e dgks %.2e cond %.2e\n",
+                                (long long)jc, (long long)jq, w, host.status[3], host.status[0], host.status[1]);
+                    if (pass == 1 && jq > 0 && deflate_tol > 0.0 && host.status[3] <= deflate_tol) {
+                        if (debug) fprintf(stderr, "[orth_rows] deflate panel jc=%lld w=%d (residual ratio %.2e)\n",
+                                           (long long)jc, w, host.status[3]);
+                        accumulate_r_kernel<<<blocks, 128, 0, stream>>>(R, ldr, jq, jc, w, Cb, jq, nullptr, Rd[cur],
+                                                                        Rd[cur ^ 1], 0);
+                        ++g_launch_count;
+                        return 2;
+                    }
                     const bool broke = host.status[2] != 0.0;
                     const bool ill = !(host.status[1] >= 0.05);
                     if (broke || ill) {
                         if (pass > 1) return -2;  // cannot happen for near-orthonormal rows; refuse loudly
-                        if (j0 > 0) {  // keep the projection that was already applied to P
-                            const int64_t total = (j0 + w) * w;
-                            const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(total, 128), 1024));
-                            accumulate_r_kernel<<<blocks, 128, 0, stream>>>(R, ldr, j0, w, Cb, j0, nullptr, Rd[cur],
-                                                                            Rd[cur ^ 1]);
+                        if (jq > 0) {  // keep the projection that was already applied to P
+                            accumulate_r_kernel<<<blocks, 128, 0, stream>>>(R, ldr, jq, jc, w, Cb, jq, nullptr, Rd[cur],
+                                                                            Rd[cur ^ 1], 0);
                             ++g_launch_count;
                         }
                         return 0;
@@ -560,95 +594,121 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                 sv.force_tile = kTile64x64;
                 sv.force_splits = 1;
                 if (gemm(sv, nullptr, 0, stream) != kOk) return -1;
-                const int64_t total = (j0 + w) * w;
+                const int64_t total = (jq + w) * w;
                 const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(total, 128), 1024));
-                accumulate_r_kernel<<<blocks, 128, 0, stream>>>(R, ldr, j0, w, (first && j0 > 0) ? Cb : nullptr, j0, Rp,
-                                                                Rd[cur], Rd[cur ^ 1]);
+                accumulate_r_kernel<<<blocks, 128, 0, stream>>>(R, ldr, jq, jc, w, (first && jq > 0) ? Cb : nullptr, jq, Rp,
+                                                                Rd[cur], Rd[cur ^ 1], 1);
                 ++g_launch_count;
                 cur ^= 1;
             }
             if (cudaGetLastError() != cudaSuccess) return -1;
-            if (j0 == 0) break;
+            if (jq == 0) break;
             if (host.status[0] >= kDgks) break;  // DGKS: this pass removed < 70 % of every vector
         }
         return 1;
     };
 
-    int64_t j0 = 0;
-    while (j0 < kmax) {
+    // move the next w input vectors up to M[jq ...] (no-op until something was deflated)
+    auto stage_panel = [&](int w) -> int {
+        if (jq == jc) return kOk;
+        TTB_REQUIRE(jc - jq >= w, "orth_rows: overlapping panel move");
+        TTB_CHECK_CUDA(cudaMemcpy2DAsync(M + jq * ldm, size_t(ldm) * 8, M + jc * ldm, size_t(ldm) * 8, size_t(m) * 8,
+                                         size_t(w), cudaMemcpyDeviceToDevice, stream));
+        return kOk;
+    };
+
+    while (jc < c && jq < m) {  // at most m orthonormal vectors of length m
+        const int64_t room = std::min(c - jc, m - jq);
         if (fast_enabled && m >= 2 * QF_W) {
-            const int wf = int(std::min<int64_t>(QF_W, kmax - j0));
-            const int fs = fast_panel(j0, wf);
+            const int wf = int(std::min<int64_t>(QF_W, room));
+            TTB_PROPAGATE(stage_panel(wf));
+            const int fs = fast_panel(wf);
             if (fs < 0) {
                 set_last_error("orth_rows: Cholesky-QR panel failed (status " + std::to_string(fs) + ")");
                 return fs == -2 ? kNotConverged : kCudaError;
             }
             if (fs == 1) {
-                j0 += wf;
+                jq += wf;
+                jc += wf;
                 continue;
             }
+            if (fs == 2) {
+                jc += wf;
+                continue;
+            }
+            // declined: the staged copy was projected (and R carries those coefficients); keep the
+            // source rows in step with it, the second half is staged again by a later panel
+            if (jq != jc)
+                TTB_CHECK_CUDA(cudaMemcpy2DAsync(M + jc * ldm, size_t(ldm) * 8, M + jq * ldm, size_t(ldm) * 8,
+                                                 size_t(m) * 8, size_t(wf), cudaMemcpyDeviceToDevice, stream));
         }
-        const int w = int(std::min<int64_t>(QR_W, kmax - j0));
-        double* P = M + j0 * ldm;
+        const int w = int(std::min<int64_t>(QR_W, room));
+        if (!(fast_enabled && m >= 2 * QF_W)) TTB_PROPAGATE(stage_panel(w));  // else already staged (wf >= w)
+        double* P = M + jq * ldm;
         set_identity_small_kernel<<<1, 256, 0, stream>>>(Rd[0], w);
         ++g_launch_count;
         int cur = 0;
-        if (j0 > 0) {
+        if (jq > 0) {
             rownorm_kernel<<<w, 256, 0, stream>>>(P, m, ldm, nullptr, nrm[0], nullptr);
             ++g_launch_count;
         }
         for (int pass = 1; pass <= kMaxPasses; ++pass) {
-            if (j0 > 0) {
-                GemmArgs g;  // C (w x j0) = P . Qp^T
-                g.M = w; g.N = j0; g.K = m;
+            if (jq > 0) {
+                GemmArgs g;  // C (w x jq) = P . Qp^T
+                g.M = w; g.N = jq; g.K = m;
                 g.A = P; g.sAm = ldm; g.sAk = 1;
                 g.B = M; g.sBk = 1; g.sBn = ldm;
-                g.C = Cb; g.ldc = j0;
+                g.C = Cb; g.ldc = jq;
                 TTB_PROPAGATE(gemm(g, gws, gws_bytes, stream));
                 GemmArgs u;  // P -= C . Qp
-                u.M = w; u.N = m; u.K = j0;
-                u.A = Cb; u.sAm = j0; u.sAk = 1;
+                u.M = w; u.N = m; u.K = jq;
+                u.A = Cb; u.sAm = jq; u.sAk = 1;
                 u.B = M; u.sBk = ldm; u.sBn = 1;
                 u.C = P; u.ldc = ldm;
                 u.alpha = -1.0; u.beta = 1.0;
                 TTB_PROPAGATE(gemm(u, gws, gws_bytes, stream));
             }
             TTB_PROPAGATE(tsqr_panel(P, w, m, ldm, Rp, w, tsq, stream));
-            if (j0 > 0) {
+            if (jq > 0) {
                 // DGKS test: how much of each vector survived this pass (projection + panel QR)
                 dgks_kernel<<<1, 32, 0, stream>>>(Rp, w, pass == 1 ? nrm[0] : nullptr, flag);
                 ++g_launch_count;
             }
-            const int64_t total = (j0 + w) * w;
+            const int64_t total = (jq + w) * w;
             const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(total, 128), 1024));
-            accumulate_r_kernel<<<blocks, 128, 0, stream>>>(R, ldr, j0, w, j0 > 0 ? Cb : nullptr, j0, Rp, Rd[cur],
-                                                            Rd[cur ^ 1]);
+            accumulate_r_kernel<<<blocks, 128, 0, stream>>>(R, ldr, jq, jc, w, jq > 0 ? Cb : nullptr, jq, Rp, Rd[cur],
+                                                            Rd[cur ^ 1], 1);
             ++g_launch_count;
             TTB_CHECK_CUDA(cudaGetLastError());
             cur ^= 1;
-            if (j0 == 0) break;  // nothing to be orthogonal to: Householder TSQR alone is stable
+            if (jq == 0) break;  // nothing to be orthogonal to: Householder TSQR alone is stable
             TTB_CHECK_CUDA(cudaMemcpyAsync(host.flag, flag, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
             TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
             double ratio;
             memcpy(&ratio, host.flag, sizeof(double));
             if (ratio >= kDgks) break;
         }
-        j0 += w;
+        jq += w;
+        jc += w;
     }
-    if (c > kmax) {
-        // vectors kmax..c-1 lie in span(Q): R[0:kmax, kmax:c] = Q . M[kmax:c, :]^T, rows zeroed
-        const int64_t extra = c - kmax;
+    if (jc < c) {
+        // jq == m: the remaining vectors lie in span(Q): R[0:jq, jc:c] = Q . M[jc:c, :]^T
+        const int64_t extra = c - jc;
         GemmArgs g;
-        g.M = kmax; g.N = extra; g.K = m;
+        g.M = jq; g.N = extra; g.K = m;
         g.A = M; g.sAm = ldm; g.sAk = 1;
-        g.B = M + kmax * ldm; g.sBk = 1; g.sBn = ldm;
-        g.C = R + kmax; g.ldc = ldr;
+        g.B = M + jc * ldm; g.sBk = 1; g.sBn = ldm;
+        g.C = R + jc; g.ldc = ldr;
         TTB_PROPAGATE(gemm(g, gws, gws_bytes, stream));
+    }
+    if (jq < c) {  // rows that hold no orthonormal vector are zero (the reference's padding)
+        const int64_t extra = c - jq;
         const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(extra * m, 256), 2048));
-        zero_rows_kernel<<<blocks, 256, 0, stream>>>(M + kmax * ldm, extra, m, ldm);
+        zero_rows_kernel<<<blocks, 256, 0, stream>>>(M + jq * ldm, extra, m, ldm);
         ++g_launch_count;
         TTB_CHECK_CUDA(cudaGetLastError());
     }
+    if (rank_out) *rank_out = jq;
     return kOk;
 }
 

@@ -254,7 +254,8 @@ size_t right_orth_workspace_bytes(int64_t r_prev_n_prev, int64_t c, int64_t m) {
 // shrink: c_new = min(c, m) (rounding sweep / last core); otherwise c_new = c with the
 // reference's zero padding.
 int right_orth_step(double* core_k, int64_t c, int64_t m, double* core_prev, int64_t P, bool shrink,
-                    int64_t* c_new_out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                    int64_t* c_new_out, void* ws, size_t ws_bytes, cudaStream_t stream, double deflate_tol) {
+    TTB_REQUIRE(shrink || deflate_tol == 0.0, "right_orth: deflation needs shrink");
     const size_t need = right_orth_required(P, c, m);
     if (ws == nullptr || ws_bytes < need) {
         set_last_error("right_orth: workspace too small, need " + std::to_string(need) + " bytes");
@@ -267,8 +268,9 @@ int right_orth_step(double* core_k, int64_t c, int64_t m, double* core_prev, int
     const size_t rest = ws_bytes - W.off;
     void* sub = W.base + W.off;
 
-    TTB_PROPAGATE(orth_rows(core_k, c, m, m, R, c, sub, rest, stream));
-    const int64_t c_new = shrink ? std::min(c, m) : c;
+    int64_t rank = std::min(c, m);
+    TTB_PROPAGATE(orth_rows(core_k, c, m, m, R, c, sub, rest, stream, deflate_tol, &rank));
+    const int64_t c_new = shrink ? rank : c;
     GemmArgs g;  // pushed (P x c_new) = core_prev (P x c) . R^T[:, :c_new] ; B(k, n) = R[n][k]
     g.M = P; g.N = c_new; g.K = c;
     g.A = core_prev; g.sAm = c; g.sAk = 1;
@@ -328,12 +330,21 @@ int round_tt(const TTDesc& t, double eps, int max_rank, int64_t* ranks_out, doub
     void* sub = W.base + W.off;
 
     // ---- RQ pass (pytens/algs.py:1864-1867) ----
+    // Safe deflation: a panel of rows whose residual after projection on the rows already
+    // orthonormalised is <= deflate_tol of its norm is dependent at working precision (the residual
+    // is roundoff of the projection itself, below the backward error of LAPACK's QR in the
+    // reference), so the bond shrinks already here and every later step works on the smaller rank.
+    static const double deflate_env = [] {
+        const char* e = getenv("TTB_DEFLATE_TOL");
+        return e ? atof(e) : 1e-13;
+    }();
+    const double deflate_tol = (eps > 0.0) ? std::min(deflate_env, 1e-3 * eps) : 0.0;
     PhaseTimer pt(stream);
     g_t_qr = g_t_jac = g_t_rest = g_t_rq = g_t_push = 0;
     for (int k = d - 1; k >= 1; --k) {
         int64_t c_new = r[k];
         TTB_PROPAGATE(right_orth_step(t.core[k], r[k], t.n[k] * r[k + 1], t.core[k - 1], r[k - 1] * t.n[k - 1],
-                                      /*shrink=*/true, &c_new, sub, rest, stream));
+                                      /*shrink=*/true, &c_new, sub, rest, stream, deflate_tol));
         r[k] = c_new;
     }
     g_t_rq += pt.tick();

@@ -35,7 +35,7 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
 // One RQ step (tt_right_orth, pytens/algs.py:1654-1704).
 size_t right_orth_workspace_bytes(int64_t r_prev_n_prev, int64_t c, int64_t m);
 int right_orth_step(double* core_k, int64_t c, int64_t m, double* core_prev, int64_t P, bool shrink,
-                    int64_t* c_new_out, void* ws, size_t ws_bytes, cudaStream_t stream);
+                    int64_t* c_new_out, void* ws, size_t ws_bytes, cudaStream_t stream, double deflate_tol = 0.0);
 
 // tt_svd_round (pytens/algs.py:1841-1903) in place on the cores of `t`;
 // ranks_out: host array of d+1 bond ranks after rounding.
