@@ -227,25 +227,34 @@ int tsqr_panel(double* P, int ww, int64_t m, int64_t ld, double* R, int64_t ldr,
 // Linv = L^{-1} (lower, w x w) and status[0] = min_v L_vv / nrm_prev[v]  (DGKS ratio; nrm_prev
 // == nullptr -> 1), status[1] = min_v L_vv / sqrt(G_vv)  (how much of a vector is left after
 // removing the earlier vectors of the same panel: the panel's conditioning), status[2] = 1 on
-// breakdown (non-positive pivot).  One CTA.
-__global__ void __launch_bounds__(256) chol_panel_kernel(const double* __restrict__ G, int w,
-                                                         const double* __restrict__ nrm_prev,
-                                                         double* __restrict__ Rt, double* __restrict__ Linv,
-                                                         double* __restrict__ status) {
+// breakdown (non-positive pivot), status[3] = max_v sqrt(G_vv) / nrm_prev[v] (what the projection
+// left of the panel; 1e300 without nrm_prev).
+// One CTA of QF_W threads, thread i owns row i of the matrix in REGISTERS (the j / k loops are fully
+// unrolled so every index is static); a step costs one block barrier: the un-scaled column j is
+// broadcast through a double-buffered shared vector and every thread derives the scaling itself.
+// w < QF_W is padded with the identity.  L^{-1} by column sweep, one column per thread.
+__global__ void __launch_bounds__(QF_W) chol_panel_kernel(const double* __restrict__ G, int w,
+                                                          const double* __restrict__ nrm_prev,
+                                                          double* __restrict__ Rt, double* __restrict__ Linv,
+                                                          double* __restrict__ status) {
     extern __shared__ __align__(16) double chol_sm[];
-    double* A = chol_sm;
-    double* X = chol_sm + QF_W * QF_P;
-    __shared__ double diag0[QF_W];
-    __shared__ int bad;
+    double* Ls = chol_sm;                 // [QF_W][QF_P]
+    double* Xs = chol_sm + QF_W * QF_P;   // [QF_W][QF_P]
+    __shared__ double col[2][QF_W];
+    __shared__ double diag0[QF_W], rdiag[QF_W];
     const int tid = threadIdx.x;
-    for (int idx = tid; idx < w * w; idx += blockDim.x) A[(idx / w) * QF_P + idx % w] = G[idx];
-    if (tid == 0) bad = 0;
+    // coalesced load through shared memory, identity padding
+    for (int idx = tid; idx < QF_W * QF_W; idx += QF_W) {
+        const int r = idx / QF_W, c = idx % QF_W;
+        Ls[r * QF_P + c] = (r < w && c < w) ? G[r * w + c] : (r == c ? 1.0 : 0.0);
+    }
     __syncthreads();
-    if (tid < w) diag0[tid] = A[tid * QF_P + tid];
+    double a[QF_W];
+#pragma unroll
+    for (int k = 0; k < QF_W; ++k) a[k] = Ls[tid * QF_P + k];
+    diag0[tid] = Ls[tid * QF_P + tid];
     __syncthreads();
     if (tid < 32) {
-        // status[3] = max_v ||P_v|| / nrm_prev[v]: how much of the panel is left after the projection
-        // (1e300 when there was no projection); decides the deflation of numerically dependent panels
         double r3 = nrm_prev ? 0.0 : 1e300;
         if (nrm_prev)
             for (int v = tid; v < w; v += 32) {
@@ -255,27 +264,22 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(const double* __restric
         r3 = warp_max(r3);
         if (tid == 0) status[3] = r3;
     }
-    for (int j = 0; j < w; ++j) {
-        const double d = A[j * QF_P + j];
-        if (!(d > 0.0)) {
-            if (tid == 0) bad = 1;
-            break;  // uniform: d is read by all threads from shared memory
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < QF_W; ++j) {
+        col[j & 1][tid] = a[j];
+        __syncthreads();
+        const double d = col[j & 1][j];
+        if (!(d > 0.0) || !(d < 1e300)) {  // uniform: every thread reads the same word
+            bad = true;
+            break;
         }
-        const double ljj = sqrt(d);
-        const double inv = 1.0 / ljj;
-        __syncthreads();
-        // scale column j
-        for (int i = j + tid; i < w; i += blockDim.x) A[i * QF_P + j] = (i == j) ? ljj : A[i * QF_P + j] * inv;
-        __syncthreads();
-        // trailing update of the lower triangle
-        const int rem = w - j - 1;
-        for (int idx = tid; idx < rem * rem; idx += blockDim.x) {
-            const int i = j + 1 + idx / rem, k = j + 1 + idx % rem;
-            if (k <= i) A[i * QF_P + k] = fma(-A[i * QF_P + j], A[k * QF_P + j], A[i * QF_P + k]);
-        }
-        __syncthreads();
+        const double invd = fast_rcp_any(d);
+        const double t = a[j] * invd;
+#pragma unroll
+        for (int k = j + 1; k < QF_W; ++k) a[k] = fma(-t, col[j & 1][k], a[k]);
+        a[j] = (tid == j) ? fast_sqrt_any(d) : t * fast_sqrt_any(d);  // L_ij = a_ij / sqrt(d)
     }
-    __syncthreads();
     if (bad) {
         if (tid == 0) {
             status[0] = 0.0;
@@ -284,25 +288,34 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(const double* __restric
         }
         return;
     }
-    // Rt = L^T ; L^{-1} by forward substitution, one column per thread
-    for (int idx = tid; idx < w * w; idx += blockDim.x) {
-        const int r = idx / w, c = idx % w;
-        Rt[idx] = (r <= c) ? A[c * QF_P + r] : 0.0;
-    }
-    if (tid < w) {
-        const int c = tid;
-        for (int i = 0; i < w; ++i) {
-            double s = (i == c) ? 1.0 : 0.0;
-            for (int k = c; k < i; ++k) s = fma(-A[i * QF_P + k], X[k * QF_P + c], s);
-            X[i * QF_P + c] = (i < c) ? 0.0 : s / A[i * QF_P + i];
-        }
-    }
     __syncthreads();
-    for (int idx = tid; idx < w * w; idx += blockDim.x) Linv[idx] = X[(idx / w) * QF_P + idx % w];
+#pragma unroll
+    for (int k = 0; k < QF_W; ++k) Ls[tid * QF_P + k] = (k <= tid) ? a[k] : 0.0;
+    rdiag[tid] = fast_rcp_any(Ls[tid * QF_P + tid]);
+    __syncthreads();
+    // column sweep: thread c owns column c of X = L^{-1}
+    double x[QF_W];
+#pragma unroll
+    for (int i = 0; i < QF_W; ++i) x[i] = (i == tid) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < QF_W; ++k) {
+        const double xk = x[k] * rdiag[k];
+        x[k] = xk;
+#pragma unroll
+        for (int i = k + 1; i < QF_W; ++i) x[i] = fma(-Ls[i * QF_P + k], xk, x[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < QF_W; ++i) Xs[i * QF_P + tid] = x[i];
+    __syncthreads();
+    for (int idx = tid; idx < w * w; idx += QF_W) {
+        const int r = idx / w, c = idx % w;
+        Rt[idx] = (r <= c) ? Ls[c * QF_P + r] : 0.0;
+        Linv[idx] = Xs[r * QF_P + c];
+    }
     if (tid < 32) {
         double r0 = 1e300, r1 = 1e300;
         for (int v = tid; v < w; v += 32) {
-            const double l = A[v * QF_P + v];
+            const double l = Ls[v * QF_P + v];
             const double prev = nrm_prev ? nrm_prev[v] : 1.0;
             r0 = fmin(r0, prev > 0.0 ? l / prev : 0.0);
             r1 = fmin(r1, l / sqrt(diag0[v]));
@@ -336,37 +349,47 @@ int configure_chol() {
 // jq = orthonormal rows produced before this panel (row offset in R), jc = index of the panel's first
 // input vector (column offset in R); they differ once panels have been deflated.  diag == 0: only
 // the projection coefficients are accumulated (deflated panel: no new orthonormal rows).
-__global__ void accumulate_r_kernel(double* __restrict__ R, int64_t ldr, int64_t jq, int64_t jc, int w,
-                                    const double* __restrict__ C, int64_t ldcc,
-                                    const double* __restrict__ Rp, const double* __restrict__ Rd_old,
-                                    double* __restrict__ Rd_new, int diag) {
-    const int64_t j0 = jq;
+__global__ void __launch_bounds__(256) accumulate_r_kernel(double* __restrict__ R, int64_t ldr, int64_t jq, int64_t jc,
+                                                           int w, const double* __restrict__ C, int64_t ldcc,
+                                                           const double* __restrict__ Rp,
+                                                           const double* __restrict__ Rd_old,
+                                                           double* __restrict__ Rd_new, int diag) {
     __shared__ double rd[QF_W * QF_W];
-    for (int i = threadIdx.x; i < w * w; i += blockDim.x) rd[i] = Rd_old[i];
-    __syncthreads();
-    const int64_t total = (j0 + (diag ? w : 0)) * w;
-    for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-         idx += int64_t(gridDim.x) * blockDim.x) {
-        const int64_t i = idx / w;
-        const int t = int(idx % w);
-        if (i < j0) {
-            if (C) {
-                double s = 0.0;
-                for (int u = 0; u <= t; ++u) s = fma(C[u * ldcc + i], rd[u * w + t], s);
-                R[i * ldr + jc + t] += s;
-            }
-        } else {
-            const int s_ = int(i - j0);
-            double s = 0.0;
-            if (Rp) {
-                for (int u = s_; u <= t; ++u) s = fma(Rp[s_ * w + u], rd[u * w + t], s);
-            } else {
-                s = rd[s_ * w + t];  // Rp = identity
-            }
-            const double v = (s_ <= t) ? s : 0.0;
-            Rd_new[s_ * w + t] = v;
-            R[i * ldr + jc + t] = v;
+    __shared__ double cs[QF_W][17];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < w * w; i += blockDim.x) rd[i] = Rd_old[i];
+    const int64_t nblk = (jq + 15) / 16;
+    if (int64_t(blockIdx.x) < nblk) {
+        // 16 earlier rows per block: R[i][jc + t] += sum_u C[u][i] Rd_old[u][t]
+        if (!C) return;
+        const int64_t i0 = int64_t(blockIdx.x) * 16;
+        for (int idx = tid; idx < w * 16; idx += blockDim.x) {
+            const int u = idx >> 4, ii = idx & 15;
+            cs[u][ii] = (i0 + ii < jq) ? C[u * ldcc + i0 + ii] : 0.0;
         }
+        __syncthreads();
+        for (int idx = tid; idx < 16 * w; idx += blockDim.x) {
+            const int ii = idx / w, t = idx % w;
+            if (i0 + ii >= jq) continue;
+            double s = 0.0;
+            for (int u = 0; u <= t; ++u) s = fma(cs[u][ii], rd[u * w + t], s);
+            R[(i0 + ii) * ldr + jc + t] += s;
+        }
+        return;
+    }
+    if (!diag) return;
+    __syncthreads();
+    for (int idx = tid; idx < w * w; idx += blockDim.x) {
+        const int s_ = idx / w, t = idx % w;
+        double s = 0.0;
+        if (Rp) {
+            for (int u = s_; u <= t; ++u) s = fma(Rp[s_ * w + u], rd[u * w + t], s);
+        } else {
+            s = rd[s_ * w + t];  // Rp = identity
+        }
+        const double v = (s_ <= t) ? s : 0.0;
+        Rd_new[s_ * w + t] = v;
+        R[(jq + s_) * ldr + jc + t] = v;
     }
 }
 
@@ -553,7 +576,7 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                 gg.C = Gm; gg.ldc = w;
                 if (gemm(gg, gws, gws_bytes, stream) != kOk) return -1;
                 const bool first = rep == 0;
-                chol_panel_kernel<<<1, 256, kCholSmem, stream>>>(Gm, w, (first && pass == 1 && jq > 0) ? nrm[0] : nullptr, Rp,
+                chol_panel_kernel<<<1, QF_W, kCholSmem, stream>>>(Gm, w, (first && pass == 1 && jq > 0) ? nrm[0] : nullptr, Rp,
                                                          Linv, first ? status : status + 4);
                 ++g_launch_count;
                 if (first) {
@@ -561,15 +584,14 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                             cudaSuccess ||
                         cudaStreamSynchronize(stream) != cudaSuccess)
                         return -1;
-                    const int64_t total = (jq + w) * w;
-                    const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(total, 128), 1024));
+                    const int blocks = int((jq + 15) / 16 + 1);
                     if (debug && pass == 1 && jq > 0)
                         fprintf(stderr, "[orth_rows] panel jc=%lld jq=%lld w=%d residual ratio %.2e dgks %.2e cond %.2e\n",
                                 (long long)jc, (long long)jq, w, host.status[3], host.status[0], host.status[1]);
                     if (pass == 1 && jq > 0 && deflate_tol > 0.0 && host.status[3] <= deflate_tol) {
                         if (debug) fprintf(stderr, "[orth_rows] deflate panel jc=%lld w=%d (residual ratio %.2e)\n",
                                            (long long)jc, w, host.status[3]);
-                        accumulate_r_kernel<<<blocks, 128, 0, stream>>>(R, ldr, jq, jc, w, Cb, jq, nullptr, Rd[cur],
+                        accumulate_r_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jq, jc, w, Cb, jq, nullptr, Rd[cur],
                                                                         Rd[cur ^ 1], 0);
                         ++g_launch_count;
                         return 2;
@@ -579,7 +601,7 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                     if (broke || ill) {
                         if (pass > 1) return -2;  // cannot happen for near-orthonormal rows; refuse loudly
                         if (jq > 0) {  // keep the projection that was already applied to P
-                            accumulate_r_kernel<<<blocks, 128, 0, stream>>>(R, ldr, jq, jc, w, Cb, jq, nullptr, Rd[cur],
+                            accumulate_r_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jq, jc, w, Cb, jq, nullptr, Rd[cur],
                                                                             Rd[cur ^ 1], 0);
                             ++g_launch_count;
                         }
@@ -594,9 +616,8 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                 sv.force_tile = kTile64x64;
                 sv.force_splits = 1;
                 if (gemm(sv, nullptr, 0, stream) != kOk) return -1;
-                const int64_t total = (jq + w) * w;
-                const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(total, 128), 1024));
-                accumulate_r_kernel<<<blocks, 128, 0, stream>>>(R, ldr, jq, jc, w, (first && jq > 0) ? Cb : nullptr, jq, Rp,
+                const int blocks = int((jq + 15) / 16 + 1);
+                accumulate_r_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jq, jc, w, (first && jq > 0) ? Cb : nullptr, jq, Rp,
                                                                 Rd[cur], Rd[cur ^ 1], 1);
                 ++g_launch_count;
                 cur ^= 1;
@@ -674,9 +695,8 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                 dgks_kernel<<<1, 32, 0, stream>>>(Rp, w, pass == 1 ? nrm[0] : nullptr, flag);
                 ++g_launch_count;
             }
-            const int64_t total = (jq + w) * w;
-            const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(total, 128), 1024));
-            accumulate_r_kernel<<<blocks, 128, 0, stream>>>(R, ldr, jq, jc, w, jq > 0 ? Cb : nullptr, jq, Rp, Rd[cur],
+            const int blocks = int((jq + 15) / 16 + 1);
+            accumulate_r_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jq, jc, w, jq > 0 ? Cb : nullptr, jq, Rp, Rd[cur],
                                                             Rd[cur ^ 1], 1);
             ++g_launch_count;
             TTB_CHECK_CUDA(cudaGetLastError());

@@ -25,6 +25,8 @@
 #include <algorithm>
 #include <cmath>
 
+#include <cooperative_groups.h>
+
 #include "gemm.cuh"
 
 namespace ttb {
@@ -73,6 +75,129 @@ __device__ __forceinline__ void rr_pair(int n, int round, int k, int& a, int& b)
         b = t;
     }
 }
+
+struct RotTol {
+    double tol2;      // squared relative threshold
+    double abs_tol2;  // skip rotation when g_ij^2 <= abs_tol2 * max(g_ii, g_jj)
+    double noise2;    // skip pairs whose rows are both below this squared norm
+};
+struct JacobiRoundState {
+    double* Gc;  // current / next Gram and accumulated rotation (ping-pong, swapped by value)
+    double* Gn;
+    double* Wc;
+    double* Wn;
+    int flipped;  // 1: the current buffers are the second pair
+};
+
+// One pass of disjoint-pair rounds on the R2 x R2 Gram matrix (R2 = 2 bsz = 8, 16 or 32) of the
+// staged rows.  mode 0: pairs INSIDE each of the two blocks (two independent tournaments of bsz
+// players, bsz - 1 rounds); mode 1: CROSS pairs (i in the first block, j in the second, bsz rounds:
+// i <-> bsz + (i + rd) mod bsz).  Per round: (1) R2/2 threads compute the rotations, (2) every
+// element of G' = Rot G Rot^T and W' = Rot W is produced from the OLD matrices (ping-pong buffers),
+// so a round costs two block barriers.  rot_a/rot_b/rot_p describe row k of the rotation:
+// row_k' = rot_a row_k + rot_b row_{rot_p}.  Must be called by all JB_NT threads.
+__device__ __forceinline__ void jacobi_rounds(JacobiRoundState& st, int R2, int bsz, int mode, const RotTol rt,
+                                              bool track, double* rot_a, double* rot_b, int* rot_p,
+                                              double* blk_max) {
+    const int tid = threadIdx.x;
+    const int lg2 = (R2 == 32) ? 5 : (R2 == 16 ? 4 : 3);
+    const int nrounds = (mode == 0) ? ((bsz & 1) ? bsz : bsz - 1) : bsz;
+    double* Gc = st.Gc;
+    double* Gn = st.Gn;
+    double* Wc = st.Wc;
+    double* Wn = st.Wn;
+    for (int rd = 0; rd < nrounds; ++rd) {
+        if (tid < R2) {  // identity rotation unless a pair is assigned below
+            rot_a[tid] = 1.0;
+            rot_b[tid] = 0.0;
+            rot_p[tid] = tid;
+        }
+        __syncwarp();
+        bool have = false;
+        int i = 0, j = 0;
+        if (mode == 0) {
+            // two half-tournaments: threads [0, b/2) work on rows [0, b), threads [b/2, b) on [b, 2b)
+            const int hp = bsz >> 1;
+            if (bsz >= 2 && tid < 2 * hp) {
+                const int half = tid / hp, k = tid % hp;
+                rr_pair(bsz, rd, k, i, j);
+                i += half * bsz;
+                j += half * bsz;
+                have = true;
+            }
+        } else if (tid < bsz) {
+            i = tid;
+            j = tid + rd;
+            if (j >= bsz) j -= bsz;
+            j += bsz;
+            have = true;
+        }
+        double myrel = 0.0;
+        if (have) {
+            const double a = Gc[i * JB_GP + i], b = Gc[j * JB_GP + j], c = Gc[i * JB_GP + j];
+            double cs = 1.0, sn = 0.0;
+            if (a > 0.0 && b > 0.0 && c != 0.0 && fmax(a, b) > rt.noise2) {
+                // scale the 2 x 2 problem by a power of two so that max(a, b) is in [1, 2)
+                const double sc = pow2_scale(fmax(a, b));
+                const double as = a * sc, bs = b * sc, cs_ = c * sc;
+                const double ab = as * bs;
+                const double c2 = cs_ * cs_;
+                const bool small_abs = c * c <= rt.abs_tol2 * fmax(a, b);
+                if (ab > 1e-30) {
+                    if (track && !small_abs) myrel = c2 * fast_rcp(ab);  // off the critical path
+                    if (c2 > rt.tol2 * ab && !small_abs) {
+                        // cos(2 theta) = |tau| / h, sin(2 theta) = 2c / h with tau = b - a, h = hypot(tau, 2c):
+                        // cs^2 = (1 + cos 2theta) / 2 in [1/2, 1] (no cancellation), sn = sin(2 theta) / (2 cs).
+                        // Two reciprocal square roots, no division; cs^2 + sn^2 = 1 to rounding.
+                        const double tau = bs - as;
+                        const double tc = 2.0 * cs_;
+                        const double h2 = fma(tau, tau, tc * tc);
+                        const double rs = fast_rsqrt(h2);
+                        const double cs2 = fma(0.5 * fabs(tau), rs, 0.5);
+                        const double rcs = fast_rsqrt(cs2);
+                        cs = cs2 * rcs;
+                        sn = copysign(0.5 * tc * rs * rcs, tc * tau);
+                    }
+                } else {
+                    // extremely graded pair (b / a < 1e-30): exact library arithmetic
+                    const double rel2 = c2 / ab;
+                    if (track && !small_abs) myrel = rel2;
+                    if (rel2 > rt.tol2 && !small_abs) {
+                        const double tau = bs - as;
+                        const double tc = 2.0 * cs_;
+                        const double t = tc / (tau + copysign(sqrt(fma(tau, tau, tc * tc)), tau));
+                        cs = rsqrt(fma(t, t, 1.0));
+                        sn = cs * t;
+                    }
+                }
+            }
+            rot_a[i] = cs;  rot_b[i] = -sn; rot_p[i] = j;
+            rot_a[j] = cs;  rot_b[j] = sn;  rot_p[j] = i;
+        }
+        if (track && tid < 32) {  // the pair owners all sit in warp 0: one shuffle reduction, no atomics
+            myrel = warp_max(myrel);
+            if (tid == 0 && myrel > *blk_max) *blk_max = myrel;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < R2 * R2; idx += JB_NT) {
+            const int k = idx >> lg2, l = idx & (R2 - 1);  // R2 is 8, 16 or 32
+            const double ak = rot_a[k], bk = rot_b[k], al = rot_a[l], bl = rot_b[l];
+            const int pk = rot_p[k], pl = rot_p[l];
+            const double gkl = Gc[k * JB_GP + l], gkp = Gc[k * JB_GP + pl];
+            const double gpl = Gc[pk * JB_GP + l], gpp = Gc[pk * JB_GP + pl];
+            Gn[k * JB_GP + l] = ak * (al * gkl + bl * gkp) + bk * (al * gpl + bl * gpp);
+            Wn[k * JB_GP + l] = ak * Wc[k * JB_GP + l] + bk * Wc[pk * JB_GP + l];
+        }
+        {
+            double* tg = Gc; Gc = Gn; Gn = tg;
+            double* tw = Wc; Wc = Wn; Wn = tw;
+        }
+        st.flipped ^= 1;
+        __syncthreads();
+    }
+    st.Gc = Gc; st.Gn = Gn; st.Wc = Wc; st.Wn = Wn;
+}
+
 
 __global__ void __launch_bounds__(JB_NT, 1) jacobi_block_kernel(const JacobiParams p) {
     extern __shared__ __align__(16) double sm[];
@@ -168,120 +293,19 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_block_kernel(const JacobiPara
     }
     __syncthreads();
 
-    // ---- cyclic two-sided Jacobi sweeps on G, accumulating W (rows) ----
-    // Per round: (1) R2/2 threads compute the rotations, (2) every element of G' = Rot G Rot^T and
-    // W' = Rot W is produced from the OLD matrices (ping-pong buffers), so a round costs two
-    // block barriers.  ra/rb/rp describe row k of the rotation: row_k' = ra row_k + rb row_{rp}.
-    double* Gc = G;   // current / next buffers, swapped by value (no indexed pointer arrays:
-    double* Gn = G2;  // those end up in local memory)
-    double* Wc = W;
-    double* Wn = W2;
-    int gcur = 0;
-    const int lg2 = (R2 == 32) ? 5 : (R2 == 16 ? 4 : 3);
-    bool any_rot = false;
-    // Every pair of rows meets exactly once per outer sweep: pairs inside a block in the mode-0
-    // launch (two independent tournaments of b players), cross pairs (i in block I, j in block J)
-    // in the nb-1 mode-1 launches (b rounds: i <-> b + (i + rd) mod b).  The sequential depth of
-    // a sweep is (b-1) + (nb-1) b = p - 1 rounds -- the same as the unblocked algorithm.
-    const int bsz = p.b;
-    const int nrounds = (p.mode == 0) ? ((bsz & 1) ? bsz : bsz - 1) : bsz;
-    for (int sw = 0; sw < p.inner_sweeps; ++sw) {
-        for (int rd = 0; rd < nrounds; ++rd) {
-            if (tid < R2) {  // identity rotation unless a pair is assigned below
-                rot_a[tid] = 1.0;
-                rot_b[tid] = 0.0;
-                rot_p[tid] = tid;
-            }
-            __syncwarp();
-            bool have = false;
-            int i = 0, j = 0;
-            if (p.mode == 0) {
-                // two half-tournaments: threads [0, b/2) work on rows [0, b), threads [b/2, b) on [b, 2b)
-                const int hp = bsz >> 1;
-                if (bsz >= 2 && tid < 2 * hp) {
-                    const int half = tid / hp, k = tid % hp;
-                    rr_pair(bsz, rd, k, i, j);
-                    i += half * bsz;
-                    j += half * bsz;
-                    have = true;
-                }
-            } else if (tid < bsz) {
-                i = tid;
-                j = tid + rd;
-                if (j >= bsz) j -= bsz;
-                j += bsz;
-                have = true;
-            }
-            if (have) {
-                const double a = Gc[i * JB_GP + i], b = Gc[j * JB_GP + j], c = Gc[i * JB_GP + j];
-                double cs = 1.0, sn = 0.0;
-                if (a > 0.0 && b > 0.0 && c != 0.0 && fmax(a, b) > p.noise2) {
-                    // scale the 2 x 2 problem by a power of two so that max(a, b) is in [1, 2)
-                    const double sc = pow2_scale(fmax(a, b));
-                    const double as = a * sc, bs = b * sc, cs_ = c * sc;
-                    const double ab = as * bs;
-                    const double c2 = cs_ * cs_;
-                    const bool small_abs = c * c <= p.abs_tol2 * fmax(a, b);
-                    if (ab > 1e-30) {
-                        const double rel2 = c2 * fast_rcp(ab);
-                        if (sw == 0 && !small_abs) {
-                            // non-negative doubles order like their bit patterns; rel^2 is monotone in rel
-                            atomicMax(reinterpret_cast<unsigned long long*>(&blk_max),
-                                      static_cast<unsigned long long>(__double_as_longlong(rel2)));
-                        }
-                        if (rel2 > p.tol * p.tol && !small_abs) {
-                            // tan(theta) = 2c / (tau + sign(tau) sqrt(tau^2 + 4 c^2)), tau = b - a
-                            const double tau = bs - as;
-                            const double tc = 2.0 * cs_;
-                            const double h2 = fma(tau, tau, tc * tc);
-                            const double h = h2 * fast_rsqrt(h2);
-                            const double t = tc * fast_rcp(tau + copysign(h, tau));
-                            cs = fast_rsqrt(fma(t, t, 1.0));
-                            sn = cs * t;
-                        }
-                    } else {
-                        // extremely graded pair (b / a < 1e-30): exact library arithmetic
-                        const double rel2 = c2 / ab;
-                        if (sw == 0 && !small_abs)
-                            atomicMax(reinterpret_cast<unsigned long long*>(&blk_max),
-                                      static_cast<unsigned long long>(__double_as_longlong(rel2)));
-                        if (rel2 > p.tol * p.tol && !small_abs) {
-                            const double tau = bs - as;
-                            const double tc = 2.0 * cs_;
-                            const double t = tc / (tau + copysign(sqrt(fma(tau, tau, tc * tc)), tau));
-                            cs = rsqrt(fma(t, t, 1.0));
-                            sn = cs * t;
-                        }
-                    }
-                }
-                rot_a[i] = cs;  rot_b[i] = -sn; rot_p[i] = j;
-                rot_a[j] = cs;  rot_b[j] = sn;  rot_p[j] = i;
-            }
-            __syncthreads();
-            for (int idx = tid; idx < R2 * R2; idx += JB_NT) {
-                const int k = idx >> lg2, l = idx & (R2 - 1);  // R2 is 8, 16 or 32
-                const double ak = rot_a[k], bk = rot_b[k], al = rot_a[l], bl = rot_b[l];
-                const int pk = rot_p[k], pl = rot_p[l];
-                const double gkl = Gc[k * JB_GP + l], gkp = Gc[k * JB_GP + pl];
-                const double gpl = Gc[pk * JB_GP + l], gpp = Gc[pk * JB_GP + pl];
-                Gn[k * JB_GP + l] = ak * (al * gkl + bl * gkp) + bk * (al * gpl + bl * gpp);
-                Wn[k * JB_GP + l] = ak * Wc[k * JB_GP + l] + bk * Wc[pk * JB_GP + l];
-            }
-            {
-                double* tg = Gc; Gc = Gn; Gn = tg;
-                double* tw = Wc; Wc = Wn; Wn = tw;
-            }
-            gcur ^= 1;
-            __syncthreads();
-        }
-    }
-    if (gcur) {  // results live in the second buffers: W is what the apply phase reads
+    // ---- cyclic two-sided Jacobi rounds on G, accumulating W (rows) ----
+    JacobiRoundState st{G, G2, W, W2, 0};
+    RotTol rt{p.tol * p.tol, p.abs_tol2, p.noise2};
+    for (int sw = 0; sw < p.inner_sweeps; ++sw)
+        jacobi_rounds(st, R2, p.b, p.mode, rt, sw == 0, rot_a, rot_b, rot_p, &blk_max);
+    if (st.flipped) {  // results live in the second buffers: W is what the apply phase reads
         for (int idx = tid; idx < R2 * R2; idx += JB_NT) {
             const int k = idx / R2, l = idx % R2;
             W[k * JB_GP + l] = W2[k * JB_GP + l];
         }
         __syncthreads();
     }
+    bool any_rot = false;
     // did anything rotate?  (W != I)
     {
         bool mine = false;
@@ -344,6 +368,224 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_block_kernel(const JacobiPara
         double* jr = p.J + int64_t(gr) * p.p;
         for (int k = lane; k < p.q; k += 32) xr[k] = t[k];
         for (int k = lane; k < p.p; k += 32) jr[k] = t[p.qx + k];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Whole SVD in ONE launch: a thread-block cluster of h = nb/2 CTAs (nb <= 16 blocks of 16 rows, i.e.
+// p <= 256 with the portable cluster size) keeps all rows of [X | J] resident in shared memory.
+// A sweep is nb - 1 phases; CTA k works on the block pair at tournament position k (circle method,
+// position top[0] fixed).  Phase 0 of a sweep rotates every pair inside the 32 staged rows (intra
+// + cross rounds), the other phases only the cross pairs.  After a phase the rotated rows -- held
+// in registers by the DMMA apply -- are written straight into the shared memory of the CTA that
+// owns them in the next phase (distributed shared memory), so between the first load and the
+// final store nothing touches global memory and there is no host round trip: the convergence word
+// of a sweep is exchanged through DSMEM as well.  J starts as the identity (generated in place).
+// ---------------------------------------------------------------------------
+struct JacobiClusterParams {
+    double* X;
+    int64_t ldx;
+    double* J;  // p x p, ld = p
+    int p, q;
+    int nb;     // blocks of JC_B rows (even)
+    int qx, ncol, pitch;
+    double tol, abs_tol2, noise2;
+    double stop_rel;  // a sweep whose largest relative off-diagonal (before rotation) is below this ends the iteration
+    int max_sweeps;
+    double* out;  // out[0] = sweeps done, out[1] = 1 when converged
+};
+constexpr int JC_B = 16;
+constexpr int JC_MAXH = 16;
+
+__global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiClusterParams p) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) double sm[];
+    double* T = sm;  // [32][pitch]
+    constexpr int R2 = 2 * JC_B;
+    double* G = T + size_t(R2) * p.pitch;   // [R2][JB_GP]
+    double* W = G + JB_MAXR * JB_GP;
+    double* G2 = W + JB_MAXR * JB_GP;
+    double* W2 = G2 + JB_MAXR * JB_GP;
+    __shared__ double rot_a[JB_MAXR], rot_b[JB_MAXR];
+    __shared__ int rot_p[JB_MAXR];
+    __shared__ double blk_max;
+    __shared__ double conv_in[JC_MAXH];
+    __shared__ int arr_top[JC_MAXH], arr_bot[JC_MAXH];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int h = p.nb >> 1;
+    const int rank = int(cluster.block_rank());
+    if (tid < h) {
+        arr_top[tid] = 2 * tid;
+        arr_bot[tid] = 2 * tid + 1;
+    }
+    // ---- stage: X rows by cp.async, J rows = identity ----
+    {
+        const bool vec_ok = ((p.ldx & 1) == 0) && ((p.q & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0);
+        const int cpr = p.ncol >> 1;  // 16-byte chunks per staged row
+        for (int idx = tid; idx < R2 * cpr; idx += JB_NT) {
+            const int a = idx / cpr, k = (idx % cpr) * 2;
+            const int gr = (2 * rank + (a >> 4)) * JC_B + (a & 15);
+            const bool live = gr < p.p;
+            double* dst = T + size_t(a) * p.pitch + k;
+            if (k < p.qx) {
+                if (vec_ok) {
+                    const bool ok = live && k < p.q;
+                    cp_async16(dst, ok ? p.X + int64_t(gr) * p.ldx + k : p.X, ok);
+                } else {
+                    dst[0] = (live && k < p.q) ? p.X[int64_t(gr) * p.ldx + k] : 0.0;
+                    dst[1] = (live && k + 1 < p.q) ? p.X[int64_t(gr) * p.ldx + k + 1] : 0.0;
+                }
+            } else {
+                const int kk = k - p.qx;
+                dst[0] = (live && kk == gr) ? 1.0 : 0.0;
+                dst[1] = (live && kk + 1 == gr) ? 1.0 : 0.0;
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+    }
+    __syncthreads();
+    cluster.sync();  // every CTA of the cluster is resident before any DSMEM traffic
+
+    const RotTol rt{p.tol * p.tol, p.abs_tol2, p.noise2};
+    const int nphase = p.nb - 1;
+    int sweeps = 0;
+    bool converged = false;
+    double sweep_max = 0.0;  // meaningful on thread 0
+    for (int sweep = 0; sweep < p.max_sweeps && !converged; ++sweep) {
+        for (int phase = 0; phase < nphase; ++phase) {
+            // ---- Gram matrix of the staged rows over the first q columns (DMMA) ----
+            for (int idx = tid; idx < JB_MAXR * JB_GP; idx += JB_NT) {
+                G[idx] = 0.0;
+                W[idx] = 0.0;
+            }
+            if (tid == 0) blk_max = 0.0;
+            __syncthreads();
+            if (tid < R2) W[tid * JB_GP + tid] = 1.0;
+            {
+                constexpr int mt = R2 / 8;
+                constexpr int ntiles = mt * mt;
+                constexpr int nslices = JB_NWARP / ntiles > 0 ? JB_NWARP / ntiles : 1;
+                const int ksteps = ((p.q + 3) & ~3) / 4;
+                for (int job = warp; job < ntiles * nslices; job += JB_NWARP) {
+                    const int tile = job % ntiles, slice = job / ntiles;
+                    const int a0 = (tile / mt) * 8, b0 = (tile % mt) * 8;
+                    if (b0 < a0) continue;  // symmetric: upper tiles only
+                    const int ks0 = int((int64_t(ksteps) * slice) / nslices);
+                    const int ks1 = int((int64_t(ksteps) * (slice + 1)) / nslices);
+                    double c0 = 0.0, c1 = 0.0;
+                    const double* ra = T + size_t(a0 + (lane >> 2)) * p.pitch + (lane & 3);
+                    const double* rb = T + size_t(b0 + (lane >> 2)) * p.pitch + (lane & 3);
+                    for (int ks = ks0; ks < ks1; ++ks) dmma884(c0, c1, ra[ks * 4], rb[ks * 4]);
+                    const int r = a0 + (lane >> 2), c = b0 + 2 * (lane & 3);
+                    atomicAdd(&G[r * JB_GP + c], c0);
+                    atomicAdd(&G[r * JB_GP + c + 1], c1);
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < R2 * R2; idx += JB_NT) {  // mirror the strictly-lower tiles
+                const int r = idx / R2, c = idx % R2;
+                if ((r / 8) > (c / 8)) G[r * JB_GP + c] = G[c * JB_GP + r];
+            }
+            __syncthreads();
+
+            // ---- rotations ----
+            JacobiRoundState st{G, G2, W, W2, 0};
+            if (phase == 0) jacobi_rounds(st, R2, JC_B, 0, rt, true, rot_a, rot_b, rot_p, &blk_max);
+            jacobi_rounds(st, R2, JC_B, 1, rt, true, rot_a, rot_b, rot_p, &blk_max);
+            const double* Wf = st.Wc;
+            if (tid == 0) sweep_max = fmax(sweep_max, blk_max);
+
+            // ---- apply: rows' = Wf . T, one 32-column slab per warp, results stay in registers ----
+            const int n0 = warp * 32;
+            const int nt = (n0 < p.ncol) ? min(4, (p.ncol - n0) / 8) : 0;
+            double acc[R2 / 8][4][2];
+#pragma unroll
+            for (int i = 0; i < R2 / 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            if (nt > 0) {
+#pragma unroll
+                for (int ks = 0; ks < R2 / 4; ++ks) {
+                    double a[R2 / 8], bf[4];
+#pragma unroll
+                    for (int i = 0; i < R2 / 8; ++i) a[i] = Wf[(8 * i + (lane >> 2)) * JB_GP + ks * 4 + (lane & 3)];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        bf[j] = (j < nt) ? T[size_t(ks * 4 + (lane & 3)) * p.pitch + n0 + 8 * j + (lane >> 2)] : 0.0;
+#pragma unroll
+                    for (int i = 0; i < R2 / 8; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < nt) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
+                }
+            }
+            cluster.sync();  // (A) every CTA has finished reading its tile
+
+            // ---- exchange: circle-method rotation of the blocks, position top[0] fixed ----
+            int dst_top_rank = rank, dst_top_slot = 0, dst_bot_rank = rank, dst_bot_slot = 1;
+            if (h > 1) {
+                if (rank == 0) {
+                    dst_bot_rank = 1; dst_bot_slot = 0;          // bottom[0] -> top[1]
+                } else {
+                    dst_bot_rank = rank - 1;                      // bottom[k] -> bottom[k-1]
+                    if (rank < h - 1) dst_top_rank = rank + 1;    // top[k] -> top[k+1]
+                    else dst_top_slot = 1;                        // top[h-1] -> bottom[h-1]
+                }
+            }
+            if (nt > 0) {
+                double* Ttop = cluster.map_shared_rank(T, dst_top_rank) + size_t(dst_top_slot * JC_B) * p.pitch;
+                double* Tbot = cluster.map_shared_rank(T, dst_bot_rank) + size_t(dst_bot_slot * JC_B) * p.pitch;
+#pragma unroll
+                for (int i = 0; i < R2 / 8; ++i) {
+                    double* base = ((i < 2) ? Ttop : Tbot) + size_t(8 * (i & 1) + (lane >> 2)) * p.pitch + n0 + 2 * (lane & 3);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < nt) *reinterpret_cast<double2*>(base + 8 * j) = make_double2(acc[i][j][0], acc[i][j][1]);
+                }
+            }
+            if (tid == 0) {
+                if (h > 1) {  // every CTA tracks the whole arrangement
+                    int nt_[JC_MAXH], nb_[JC_MAXH];
+                    for (int k = 0; k < h; ++k) {
+                        nt_[k] = (k == 0) ? arr_top[0] : (k == 1 ? arr_bot[0] : arr_top[k - 1]);
+                        nb_[k] = (k == h - 1) ? arr_top[h - 1] : arr_bot[k + 1];
+                    }
+                    for (int k = 0; k < h; ++k) {
+                        arr_top[k] = nt_[k];
+                        arr_bot[k] = nb_[k];
+                    }
+                }
+                if (phase == nphase - 1) {
+                    for (int k = 0; k < h; ++k) cluster.map_shared_rank(conv_in, k)[rank] = sweep_max;
+                    sweep_max = 0.0;
+                }
+            }
+            cluster.sync();  // (B) the rows of the next phase have arrived
+        }
+        ++sweeps;
+        double mx = 0.0;
+        for (int k = 0; k < h; ++k) mx = fmax(mx, conv_in[k]);
+        // mx is the largest squared relative off-diagonal met BEFORE its rotation in this sweep; Jacobi
+        // converges quadratically, so below stop_rel the rotations of this very sweep have finished the job
+        converged = sqrt(mx) <= p.stop_rel;
+    }
+    // ---- write back ----
+    for (int a = warp; a < R2; a += JB_NWARP) {
+        const int blk = (a < JC_B) ? arr_top[rank] : arr_bot[rank];
+        const int gr = blk * JC_B + (a & 15);
+        if (gr >= p.p) continue;
+        const double* t = T + size_t(a) * p.pitch;
+        double* xr = p.X + int64_t(gr) * p.ldx;
+        double* jr = p.J + int64_t(gr) * p.p;
+        for (int k = lane; k < p.q; k += 32) xr[k] = t[k];
+        for (int k = lane; k < p.p; k += 32) jr[k] = t[p.qx + k];
+    }
+    if (rank == 0 && tid == 0) {
+        p.out[0] = double(sweeps);
+        p.out[1] = converged ? 1.0 : 0.0;
     }
 }
 
@@ -461,14 +703,75 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
                 cudaStream_t stream) {
     TTB_REQUIRE(X && J && conv_dev && conv_host_pinned, "jacobi_rows: null pointer");
     TTB_REQUIRE(p >= 1 && q >= 1 && ldx >= q, "jacobi_rows: bad extents");
+    if (sweeps_out) *sweeps_out = 0;
+    if (p == 1) {
+        set_identity_kernel<<<1, 32, 0, stream>>>(J, p);
+        ++g_launch_count;
+        TTB_CHECK_CUDA(cudaGetLastError());
+        return kOk;
+    }
+
+    // ---- single-launch cluster path: all rows resident in the shared memory of <= 8 CTAs ----
+    static const bool cluster_enabled = [] {
+        const char* e = getenv("TTB_JACOBI_CLUSTER");
+        return e == nullptr || e[0] != '0';
+    }();
+    {
+        JacobiClusterParams cp{};
+        cp.qx = round_up(q, 8);
+        cp.ncol = round_up(cp.qx + p, 8);
+        cp.pitch = cp.ncol + 4;
+        int nbc = std::max(2, ceil_div(p, JC_B));
+        if (nbc & 1) ++nbc;
+        const size_t csmem = (size_t(2 * JC_B) * cp.pitch + 4 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
+        int dev = 0, maxsm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (cluster_enabled && nbc / 2 <= 8 && cp.ncol <= 32 * JB_NWARP && csmem + 4096 <= size_t(maxsm)) {
+            cp.X = X; cp.ldx = ldx; cp.J = J; cp.p = p; cp.q = q; cp.nb = nbc;
+            cp.tol = 1e-15 * std::sqrt(double(std::max(q, 16)));
+            cp.abs_tol2 = abs_tol * abs_tol;
+            cp.noise2 = noise_floor * noise_floor;
+            cp.stop_rel = std::max(cp.tol, 1e-9);
+            cp.max_sweeps = max_sweeps;
+            cp.out = reinterpret_cast<double*>(conv_dev);
+            static size_t cconfigured = 0;
+            if (csmem > cconfigured) {
+                TTB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(csmem)));
+                cconfigured = csmem;
+            }
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(unsigned(nbc / 2));
+            cfg.blockDim = dim3(JB_NT);
+            cfg.dynamicSmemBytes = csmem;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = unsigned(nbc / 2);
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            const cudaError_t le = cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel, cp);
+            if (le == cudaSuccess) {
+                ++g_launch_count;
+                double* hout = reinterpret_cast<double*>(conv_host_pinned);
+                TTB_CHECK_CUDA(cudaMemcpyAsync(hout, cp.out, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+                TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
+                if (sweeps_out) *sweeps_out = int(hout[0]);
+                if (hout[1] != 0.0) return kOk;
+                set_last_error("jacobi_rows: not converged after " + std::to_string(max_sweeps) + " sweeps");
+                return kNotConverged;
+            }
+            (void)cudaGetLastError();  // cluster shape not schedulable here: fall through to the multi-launch path
+        }
+    }
     {
         const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(int64_t(p) * p, 256), 1024));
         set_identity_kernel<<<blocks, 256, 0, stream>>>(J, p);
         ++g_launch_count;
         TTB_CHECK_CUDA(cudaGetLastError());
     }
-    if (sweeps_out) *sweeps_out = 0;
-    if (p == 1) return kOk;
 
     JacobiParams jp{};
     size_t smem = 0;
