@@ -9,6 +9,9 @@
 #include "batched.cuh"
 #include "ttsvd.cuh"
 
+namespace ttb {
+double debug_chol_bench_us(int w, int reps);
+}
 namespace {
 inline ttb::TTDesc to_desc(const ttb_tt* t) {
     ttb::TTDesc d;
@@ -35,6 +38,8 @@ extern "C" {
 const char* ttb_version(void) { return "ttb200 0.1.0 (sm_100a, fp64 DMMA)"; }
 const char* ttb_last_error(void) { return ttb::last_error_cstr(); }
 uint64_t ttb_launch_count(void) { return ttb::g_launch_count; }
+// debug aid for tools/ (not declared in the public header)
+double ttb_debug_chol_bench_us(int w, int reps) { return ttb::debug_chol_bench_us(w, reps); }
 
 size_t ttb_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K) {
     return ttb::gemm_workspace_bytes(M, N, K, 1);

@@ -50,6 +50,26 @@ const char* last_error_cstr();
         if (_s != ::ttb::kOk) return _s;    \
     } while (0)
 
+// ---------------------------------------------------------------------------
+// TTB_PROF=1: per-category device timing of the launches inside a scope (CUDA events on the
+// launching stream; prof_report() synchronises, prints the totals to stderr and resets).
+// Debug aid only -- the event records add a few microseconds of gaps.
+// ---------------------------------------------------------------------------
+bool prof_enabled();
+void prof_begin(const char* name, cudaStream_t stream);
+void prof_end(cudaStream_t stream);
+void prof_report(const char* title);
+struct ProfScope {
+    cudaStream_t s;
+    bool on;
+    ProfScope(const char* name, cudaStream_t stream) : s(stream), on(prof_enabled()) {
+        if (on) prof_begin(name, s);
+    }
+    ~ProfScope() {
+        if (on) prof_end(s);
+    }
+};
+
 inline int num_sms() {
     static int cached = 0;
     if (cached == 0) {
@@ -143,6 +163,24 @@ __device__ __forceinline__ double fast_rsqrt(double x) {  // x in float range
     y = y * fma(-hx, y * y, 1.5);
     y = y * fma(-hx, y * y, 1.5);
     return y;
+}
+// MUFU.RSQ64H / MUFU.RCP64H seeds (~2^-20 relative, no fp32 round trip) + ONE third-order step:
+// with r = 1 - x y^2 the update y (1 + r/2 + 3 r^2 / 8) leaves an O(r^3) ~ 2^-58 error, in four
+// dependent fp64 operations instead of the six of two Newton steps.  x: positive normal double.
+__device__ __forceinline__ double rsqrt_seed64(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+__device__ __forceinline__ double rcp_seed64(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+__device__ __forceinline__ double fast_rsqrt3(double x) {
+    const double y = rsqrt_seed64(x);
+    const double r = fma(-(x * y), y, 1.0);
+    return fma(y * r, fma(0.375, r, 0.5), y);
 }
 __device__ __forceinline__ int dbl_exponent(double x) { return ((__double2hiint(x) >> 20) & 0x7ff) - 1023; }
 __device__ __forceinline__ double dbl_pow2(int e) { return __hiloint2double((e + 1023) << 20, 0); }  // 2^e, |e| < 1023

@@ -26,6 +26,7 @@
 #include "qr.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <vector>
 
@@ -229,30 +230,42 @@ int tsqr_panel(double* P, int ww, int64_t m, int64_t ld, double* R, int64_t ldr,
 // removing the earlier vectors of the same panel: the panel's conditioning), status[2] = 1 on
 // breakdown (non-positive pivot), status[3] = max_v sqrt(G_vv) / nrm_prev[v] (what the projection
 // left of the panel; 1e300 without nrm_prev).
-// One CTA of QF_W threads, thread i owns row i of the matrix in REGISTERS (the j / k loops are fully
-// unrolled so every index is static); a step costs one block barrier: the un-scaled column j is
-// broadcast through a double-buffered shared vector and every thread derives the scaling itself.
-// w < QF_W is padded with the identity.  L^{-1} by column sweep, one column per thread.
-__global__ void __launch_bounds__(QF_W) chol_panel_kernel(const double* __restrict__ G, int w,
-                                                          const double* __restrict__ nrm_prev,
-                                                          double* __restrict__ Rt, double* __restrict__ Linv,
-                                                          double* __restrict__ status) {
+// One CTA on a shared-memory copy (pitch 65); 256 threads move data, the first QF_W (thread i =
+// row i) factor.  LEFT-looking (dot-product) Cholesky: step j only LOADS in its inner loop
+// (v_i = A_ij - sum_{k<j} L_ik L_jk, four accumulators, loads pipeline freely) and stores one value
+// per thread, with one barrier per step: the un-scaled v are exchanged through a double-buffered
+// shared vector, every thread derives 1/sqrt(d) itself, and the newest column enters the next dot
+// product from registers.  (A right-looking version -- (63-j)^2 shared read-modify-writes per step --
+// and a fully unrolled register version -- instruction-cache misses, every instruction executed
+// once -- both took ~85 us.)  L^{-1} by forward substitution, thread c owns column c: no barriers.
+constexpr int CH_NT = 256;
+//
+// Two shortcuts keep the sequential factorisation off the common paths:
+//  * deflate_tol > 0 and status[3] <= deflate_tol: the panel is numerically dependent on the rows
+//    already produced; nothing is factored (status[2] = 2) -- the host drops the panel.
+//  * near_identity: the second pass of Cholesky-QR2 sees G = I + E with |E| ~ eps cond^2; when
+//    max |E| <= 3e-8 the first-order factors L = I + strict_lower(E) + diag(E)/2 and
+//    L^{-1} = I - strict_lower(E) - diag(E)/2 are exact to O(|E|^2) <= 1e-15 and need no
+//    sequential step at all; otherwise the kernel falls through to the full factorisation.
+__global__ void __launch_bounds__(CH_NT) chol_panel_kernel(const double* __restrict__ G, int w,
+                                                           const double* __restrict__ nrm_prev,
+                                                           double* __restrict__ Rt, double* __restrict__ Linv,
+                                                           double* __restrict__ status, double deflate_tol,
+                                                           int near_identity) {
     extern __shared__ __align__(16) double chol_sm[];
-    double* Ls = chol_sm;                 // [QF_W][QF_P]
-    double* Xs = chol_sm + QF_W * QF_P;   // [QF_W][QF_P]
-    __shared__ double col[2][QF_W];
-    __shared__ double diag0[QF_W], rdiag[QF_W];
+    double* A = chol_sm;                 // [QF_W][QF_P]
+    double* X = chol_sm + QF_W * QF_P;   // [QF_W][QF_P]
+    __shared__ double diag0[QF_W], rdiag[QF_W], vsh[2][QF_W], emax_sh[CH_NT / 32];
+    __shared__ int flag_sh;
     const int tid = threadIdx.x;
-    // coalesced load through shared memory, identity padding
-    for (int idx = tid; idx < QF_W * QF_W; idx += QF_W) {
+    const long long tk0 = clock64();
+    for (int idx = tid; idx < QF_W * QF_W; idx += CH_NT) {
         const int r = idx / QF_W, c = idx % QF_W;
-        Ls[r * QF_P + c] = (r < w && c < w) ? G[r * w + c] : (r == c ? 1.0 : 0.0);
+        A[r * QF_P + c] = (r < w && c < w) ? G[r * w + c] : (r == c ? 1.0 : 0.0);  // identity padding
+        X[r * QF_P + c] = 0.0;
     }
     __syncthreads();
-    double a[QF_W];
-#pragma unroll
-    for (int k = 0; k < QF_W; ++k) a[k] = Ls[tid * QF_P + k];
-    diag0[tid] = Ls[tid * QF_P + tid];
+    if (tid < QF_W) diag0[tid] = A[tid * QF_P + tid];
     __syncthreads();
     if (tid < 32) {
         double r3 = nrm_prev ? 0.0 : 1e300;
@@ -262,23 +275,101 @@ __global__ void __launch_bounds__(QF_W) chol_panel_kernel(const double* __restri
                 r3 = fmax(r3, prev > 0.0 ? sqrt(fmax(diag0[v], 0.0)) / prev : 0.0);
             }
         r3 = warp_max(r3);
-        if (tid == 0) status[3] = r3;
+        if (tid == 0) {
+            status[3] = r3;
+            flag_sh = (deflate_tol > 0.0 && r3 <= deflate_tol) ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    if (flag_sh) {  // numerically dependent panel: nothing to factor
+        if (tid == 0) {
+            status[0] = 0.0;
+            status[1] = 0.0;
+            status[2] = 2.0;
+        }
+        return;
+    }
+    if (near_identity) {
+        double e = 0.0;
+        for (int idx = tid; idx < QF_W * QF_W; idx += CH_NT) {
+            const int r = idx / QF_W, c = idx % QF_W;
+            e = fmax(e, fabs(A[r * QF_P + c] - (r == c ? 1.0 : 0.0)));
+        }
+        e = warp_max(e);
+        if ((tid & 31) == 0) emax_sh[tid >> 5] = e;
+        __syncthreads();
+        double emax = 0.0;
+        for (int k = 0; k < CH_NT / 32; ++k) emax = fmax(emax, emax_sh[k]);
+        if (emax <= 3e-8) {
+            for (int idx = tid; idx < w * w; idx += CH_NT) {
+                const int r = idx / w, c = idx % w;
+                const double eu = A[r * QF_P + c] - (r == c ? 1.0 : 0.0);  // E is symmetric
+                Rt[idx] = (r < c) ? eu : (r == c ? 1.0 + 0.5 * eu : 0.0);
+                Linv[idx] = (r > c) ? -eu : (r == c ? 1.0 - 0.5 * eu : 0.0);
+            }
+            if (tid == 0) {
+                status[0] = 1.0;
+                status[1] = 1.0;
+                status[2] = 0.0;
+            }
+            return;
+        }
     }
     bool bad = false;
-#pragma unroll
-    for (int j = 0; j < QF_W; ++j) {
-        col[j & 1][tid] = a[j];
-        __syncthreads();
-        const double d = col[j & 1][j];
-        if (!(d > 0.0) || !(d < 1e300)) {  // uniform: every thread reads the same word
-            bad = true;
-            break;
+    const long long tk1 = clock64();
+    {
+        // four lanes per row: lane `part` sums the terms k = part (mod 4); every load of a batch is
+        // issued before the first FMA needs it (a single warp per scheduler has nobody else to hide
+        // the ~30-cycle shared-memory latency behind)
+        const int i = tid >> 2, part = tid & 3;
+        const double* li = A + i * QF_P;
+        double lprev_i = 0.0;           // L[i][j-1], still in a register
+        double rs_prev = 0.0;
+        for (int j = 0; j < QF_W; ++j) {
+            double v = 0.0;
+            if (i >= j) {
+                const double* lj = A + j * QF_P;
+                double s0 = 0.0, s1 = 0.0;
+                int k = part;
+                for (; k + 12 < j - 1; k += 16) {  // columns 0 .. j-2 are in shared memory
+                    const double a0 = li[k], a1 = li[k + 4], a2 = li[k + 8], a3 = li[k + 12];
+                    const double b0 = lj[k], b1 = lj[k + 4], b2 = lj[k + 8], b3 = lj[k + 12];
+                    s0 = fma(a0, b0, s0);
+                    s1 = fma(a1, b1, s1);
+                    s0 = fma(a2, b2, s0);
+                    s1 = fma(a3, b3, s1);
+                }
+                {
+                    const double a0 = (k < j - 1) ? li[k] : 0.0, a1 = (k + 4 < j - 1) ? li[k + 4] : 0.0;
+                    const double a2 = (k + 8 < j - 1) ? li[k + 8] : 0.0;
+                    const double b0 = (k < j - 1) ? lj[k] : 0.0, b1 = (k + 4 < j - 1) ? lj[k + 4] : 0.0;
+                    const double b2 = (k + 8 < j - 1) ? lj[k + 8] : 0.0;
+                    s0 = fma(a0, b0, s0);
+                    s1 = fma(a1, b1, s1);
+                    s0 = fma(a2, b2, s0);
+                }
+                if (j > 0 && part == 0) s1 = fma(lprev_i, vsh[(j - 1) & 1][j] * rs_prev, s1);  // column j-1 from registers
+                v = s0 + s1;
+            }
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (i >= j) {
+                v = li[j] - v;
+                if (part == 0) vsh[j & 1][i] = v;
+            }
+            __syncthreads();
+            const double d = vsh[j & 1][j];
+            if (!(d > 0.0) || !(d < 1e300)) {  // uniform: every thread reads the same word
+                bad = true;
+                break;
+            }
+            const double rs = fast_rsqrt3(d);
+            if (i >= j) {
+                lprev_i = (i == j) ? d * rs : v * rs;
+                if (part == (j & 3)) A[i * QF_P + j] = lprev_i;  // the lane that reads it back as a term
+            }
+            rs_prev = rs;
         }
-        const double invd = fast_rcp_any(d);
-        const double t = a[j] * invd;
-#pragma unroll
-        for (int k = j + 1; k < QF_W; ++k) a[k] = fma(-t, col[j & 1][k], a[k]);
-        a[j] = (tid == j) ? fast_sqrt_any(d) : t * fast_sqrt_any(d);  // L_ij = a_ij / sqrt(d)
     }
     if (bad) {
         if (tid == 0) {
@@ -289,33 +380,58 @@ __global__ void __launch_bounds__(QF_W) chol_panel_kernel(const double* __restri
         return;
     }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < QF_W; ++k) Ls[tid * QF_P + k] = (k <= tid) ? a[k] : 0.0;
-    rdiag[tid] = fast_rcp_any(Ls[tid * QF_P + tid]);
+    const long long tk2 = clock64();
+    if (tid < QF_W) rdiag[tid] = 1.0 / A[tid * QF_P + tid];
     __syncthreads();
-    // column sweep: thread c owns column c of X = L^{-1}
-    double x[QF_W];
-#pragma unroll
-    for (int i = 0; i < QF_W; ++i) x[i] = (i == tid) ? 1.0 : 0.0;
-#pragma unroll
-    for (int k = 0; k < QF_W; ++k) {
-        const double xk = x[k] * rdiag[k];
-        x[k] = xk;
-#pragma unroll
-        for (int i = k + 1; i < QF_W; ++i) x[i] = fma(-Ls[i * QF_P + k], xk, x[i]);
+    {
+        // X = L^{-1}: X[i][c] = ((i == c) - sum_{k=c}^{i-1} L[i][k] X[k][c]) / L[i][i]; column c on the four
+        // lanes (c, part); lane `part` owns the terms k = part (mod 4) and is the one that stored them
+        const int c = tid >> 2, part = tid & 3;
+        const unsigned gmask = 0xFu << (tid & 28);
+        for (int i = c; i < QF_W; ++i) {
+            const double* li = A + i * QF_P;
+            double s0 = 0.0, s1 = 0.0;
+            int k = c + ((part - c) & 3);
+            for (; k + 12 < i; k += 16) {
+                const double a0 = li[k], a1 = li[k + 4], a2 = li[k + 8], a3 = li[k + 12];
+                const double b0 = X[k * QF_P + c], b1 = X[(k + 4) * QF_P + c], b2 = X[(k + 8) * QF_P + c],
+                             b3 = X[(k + 12) * QF_P + c];
+                s0 = fma(a0, b0, s0);
+                s1 = fma(a1, b1, s1);
+                s0 = fma(a2, b2, s0);
+                s1 = fma(a3, b3, s1);
+            }
+            {
+                const double a0 = (k < i) ? li[k] : 0.0, a1 = (k + 4 < i) ? li[k + 4] : 0.0, a2 = (k + 8 < i) ? li[k + 8] : 0.0;
+                const double b0 = (k < i) ? X[k * QF_P + c] : 0.0, b1 = (k + 4 < i) ? X[(k + 4) * QF_P + c] : 0.0;
+                const double b2 = (k + 8 < i) ? X[(k + 8) * QF_P + c] : 0.0;
+                s0 = fma(a0, b0, s0);
+                s1 = fma(a1, b1, s1);
+                s0 = fma(a2, b2, s0);
+            }
+            double sum = s0 + s1;
+            sum += __shfl_xor_sync(gmask, sum, 1);  // the four lanes of a column share the trip count, the warp does not
+            sum += __shfl_xor_sync(gmask, sum, 2);
+            if (part == (i & 3)) X[i * QF_P + c] = (((i == c) ? 1.0 : 0.0) - sum) * rdiag[i];
+        }
     }
-#pragma unroll
-    for (int i = 0; i < QF_W; ++i) Xs[i * QF_P + tid] = x[i];
     __syncthreads();
-    for (int idx = tid; idx < w * w; idx += QF_W) {
+    const long long tk3 = clock64();
+    for (int idx = tid; idx < w * w; idx += CH_NT) {
         const int r = idx / w, c = idx % w;
-        Rt[idx] = (r <= c) ? Ls[c * QF_P + r] : 0.0;
-        Linv[idx] = Xs[r * QF_P + c];
+        Rt[idx] = (r <= c) ? A[c * QF_P + r] : 0.0;
+        Linv[idx] = X[r * QF_P + c];
+    }
+    if (tid == 0) {
+        status[4] = double(tk1 - tk0);
+        status[5] = double(tk2 - tk1);
+        status[6] = double(tk3 - tk2);
+        status[7] = double(clock64() - tk3);
     }
     if (tid < 32) {
         double r0 = 1e300, r1 = 1e300;
         for (int v = tid; v < w; v += 32) {
-            const double l = Ls[v * QF_P + v];
+            const double l = A[v * QF_P + v];
             const double prev = nrm_prev ? nrm_prev[v] : 1.0;
             r0 = fmin(r0, prev > 0.0 ? l / prev : 0.0);
             r1 = fmin(r1, l / sqrt(diag0[v]));
@@ -379,17 +495,38 @@ __global__ void __launch_bounds__(256) accumulate_r_kernel(double* __restrict__ 
     }
     if (!diag) return;
     __syncthreads();
-    for (int idx = tid; idx < w * w; idx += blockDim.x) {
-        const int s_ = idx / w, t = idx % w;
-        double s = 0.0;
-        if (Rp) {
-            for (int u = s_; u <= t; ++u) s = fma(Rp[s_ * w + u], rd[u * w + t], s);
-        } else {
-            s = rd[s_ * w + t];  // Rp = identity
+    // Rd_new = Rp Rd_old (both upper triangular), one row s_ per warp at a time: the lanes hold row s_
+    // of Rp (coalesced load) and broadcast its entries by shuffle; Rd_old comes from shared memory.
+    {
+        const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+        for (int s_ = warp; s_ < w; s_ += nwarp) {
+            double rp0 = 0.0, rp1 = 0.0;
+            if (Rp) {
+                rp0 = (lane < w) ? Rp[s_ * w + lane] : 0.0;
+                rp1 = (lane + 32 < w) ? Rp[s_ * w + lane + 32] : 0.0;
+            }
+            double a0 = 0.0, a1 = 0.0;  // columns t = lane, lane + 32
+            if (Rp) {
+                for (int u = s_; u < w; ++u) {
+                    const double r = __shfl_sync(0xffffffffu, (u < 32) ? rp0 : rp1, u & 31);
+                    if (lane < w) a0 = fma(r, rd[u * w + lane], a0);         // rd is upper triangular: zero below the diagonal
+                    if (lane + 32 < w) a1 = fma(r, rd[u * w + lane + 32], a1);
+                }
+            } else {
+                if (lane < w) a0 = rd[s_ * w + lane];
+                if (lane + 32 < w) a1 = rd[s_ * w + lane + 32];
+            }
+            if (lane < w) {
+                const double v = (s_ <= lane) ? a0 : 0.0;
+                Rd_new[s_ * w + lane] = v;
+                R[(jq + s_) * ldr + jc + lane] = v;
+            }
+            if (lane + 32 < w) {
+                const double v = (s_ <= lane + 32) ? a1 : 0.0;
+                Rd_new[s_ * w + lane + 32] = v;
+                R[(jq + s_) * ldr + jc + lane + 32] = v;
+            }
         }
-        const double v = (s_ <= t) ? s : 0.0;
-        Rd_new[s_ * w + t] = v;
-        R[(jq + s_) * ldr + jc + t] = v;
     }
 }
 
@@ -487,6 +624,38 @@ int orth_host(OrthHost* h) {
 
 }  // namespace
 
+// Debug aid (tools/ only, not in the public header): average device time of `reps` back-to-back
+// launches of the panel Cholesky on a fixed SPD matrix, in microseconds; < 0 on error.
+double debug_chol_bench_us(int w, int reps) {
+    if (configure_chol() != kOk) return -1.0;
+    double *G = nullptr, *out = nullptr;
+    if (cudaMalloc(&G, QF_W * QF_W * 8) != cudaSuccess || cudaMalloc(&out, (2 * QF_W * QF_W + 16) * 8) != cudaSuccess)
+        return -1.0;
+    std::vector<double> h(size_t(w) * w);
+    for (int i = 0; i < w; ++i)
+        for (int j = 0; j < w; ++j) h[size_t(i) * w + j] = (i == j ? w + 1.0 : 1.0 / (1.0 + std::abs(i - j)));
+    cudaMemcpy(G, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i)
+        chol_panel_kernel<<<1, CH_NT, kCholSmem>>>(G, w, nullptr, out, out + QF_W * QF_W, out + 2 * QF_W * QF_W, 0.0, 0);
+    cudaEventRecord(e0);
+    for (int i = 0; i < reps; ++i)
+        chol_panel_kernel<<<1, CH_NT, kCholSmem>>>(G, w, nullptr, out, out + QF_W * QF_W, out + 2 * QF_W * QF_W, 0.0, 0);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double st[8];
+    cudaMemcpy(st, out + 2 * QF_W * QF_W, 64, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[chol] clocks: load %.0f chol %.0f inv %.0f store %.0f\n", st[4], st[5], st[6], st[7]);
+    cudaFree(G);
+    cudaFree(out);
+    if (st[2] != 0.0) return -2.0;
+    return 1e3 * ms / reps;
+}
+
 size_t orth_rows_workspace_bytes(int64_t c, int64_t m) {
     if (c <= 0 || m <= 0) return 256;
     return orth_layout(c, m).total();
@@ -559,14 +728,14 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                 g.A = P; g.sAm = ldm; g.sAk = 1;
                 g.B = M; g.sBk = 1; g.sBn = ldm;
                 g.C = Cb; g.ldc = jq;
-                if (gemm(g, gws, gws_bytes, stream) != kOk) return -1;
+                { ProfScope ps_("qr.gemm_proj_C", stream); if (gemm(g, gws, gws_bytes, stream) != kOk) return -1; }
                 GemmArgs u;  // P -= C . Qp
                 u.M = w; u.N = m; u.K = jq;
                 u.A = Cb; u.sAm = jq; u.sAk = 1;
                 u.B = M; u.sBk = ldm; u.sBn = 1;
                 u.C = P; u.ldc = ldm;
                 u.alpha = -1.0; u.beta = 1.0;
-                if (gemm(u, gws, gws_bytes, stream) != kOk) return -1;
+                { ProfScope ps_("qr.gemm_proj_update", stream); if (gemm(u, gws, gws_bytes, stream) != kOk) return -1; }
             }
             for (int rep = 0; rep < 2; ++rep) {  // Cholesky-QR twice
                 GemmArgs gg;  // G = P P^T
@@ -574,10 +743,12 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                 gg.A = P; gg.sAm = ldm; gg.sAk = 1;
                 gg.B = P; gg.sBk = 1; gg.sBn = ldm;
                 gg.C = Gm; gg.ldc = w;
-                if (gemm(gg, gws, gws_bytes, stream) != kOk) return -1;
+                { ProfScope ps_("qr.gemm_gram", stream); if (gemm(gg, gws, gws_bytes, stream) != kOk) return -1; }
                 const bool first = rep == 0;
-                chol_panel_kernel<<<1, QF_W, kCholSmem, stream>>>(Gm, w, (first && pass == 1 && jq > 0) ? nrm[0] : nullptr, Rp,
-                                                         Linv, first ? status : status + 4);
+                { ProfScope ps_(first ? "qr.chol_panel" : "qr.chol_panel2", stream);
+                chol_panel_kernel<<<1, CH_NT, kCholSmem, stream>>>(Gm, w, (first && pass == 1 && jq > 0) ? nrm[0] : nullptr, Rp,
+                                                         Linv, first ? status : status + 8,
+                                                         (first && pass == 1 && jq > 0) ? deflate_tol : 0.0, first ? 0 : 1); }
                 ++g_launch_count;
                 if (first) {
                     if (cudaMemcpyAsync(host.status, status, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream) !=
@@ -591,8 +762,9 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                     if (pass == 1 && jq > 0 && deflate_tol > 0.0 && host.status[3] <= deflate_tol) {
                         if (debug) fprintf(stderr, "[orth_rows] deflate panel jc=%lld w=%d (residual ratio %.2e)\n",
                                            (long long)jc, w, host.status[3]);
+                        { ProfScope ps_("qr.accumulate_r", stream);
                         accumulate_r_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jq, jc, w, Cb, jq, nullptr, Rd[cur],
-                                                                        Rd[cur ^ 1], 0);
+                                                                        Rd[cur ^ 1], 0); }
                         ++g_launch_count;
                         return 2;
                     }
@@ -601,8 +773,9 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                     if (broke || ill) {
                         if (pass > 1) return -2;  // cannot happen for near-orthonormal rows; refuse loudly
                         if (jq > 0) {  // keep the projection that was already applied to P
+                            { ProfScope ps_("qr.accumulate_r", stream);
                             accumulate_r_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jq, jc, w, Cb, jq, nullptr, Rd[cur],
-                                                                            Rd[cur ^ 1], 0);
+                                                                            Rd[cur ^ 1], 0); }
                             ++g_launch_count;
                         }
                         return 0;
@@ -615,10 +788,11 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                 sv.C = P; sv.ldc = ldm;
                 sv.force_tile = kTile64x64;
                 sv.force_splits = 1;
-                if (gemm(sv, nullptr, 0, stream) != kOk) return -1;
+                { ProfScope ps_("qr.gemm_solve", stream); if (gemm(sv, nullptr, 0, stream) != kOk) return -1; }
                 const int blocks = int((jq + 15) / 16 + 1);
+                { ProfScope ps_("qr.accumulate_r", stream);
                 accumulate_r_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jq, jc, w, (first && jq > 0) ? Cb : nullptr, jq, Rp,
-                                                                Rd[cur], Rd[cur ^ 1], 1);
+                                                                Rd[cur], Rd[cur ^ 1], 1); }
                 ++g_launch_count;
                 cur ^= 1;
             }
@@ -689,15 +863,16 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                 u.alpha = -1.0; u.beta = 1.0;
                 TTB_PROPAGATE(gemm(u, gws, gws_bytes, stream));
             }
-            TTB_PROPAGATE(tsqr_panel(P, w, m, ldm, Rp, w, tsq, stream));
+            { ProfScope ps_("qr.tsqr_panel", stream); TTB_PROPAGATE(tsqr_panel(P, w, m, ldm, Rp, w, tsq, stream)); }
             if (jq > 0) {
                 // DGKS test: how much of each vector survived this pass (projection + panel QR)
                 dgks_kernel<<<1, 32, 0, stream>>>(Rp, w, pass == 1 ? nrm[0] : nullptr, flag);
                 ++g_launch_count;
             }
             const int blocks = int((jq + 15) / 16 + 1);
+            { ProfScope ps_("qr.accumulate_r", stream);
             accumulate_r_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jq, jc, w, jq > 0 ? Cb : nullptr, jq, Rp, Rd[cur],
-                                                            Rd[cur ^ 1], 1);
+                                                            Rd[cur ^ 1], 1); }
             ++g_launch_count;
             TTB_CHECK_CUDA(cudaGetLastError());
             cur ^= 1;

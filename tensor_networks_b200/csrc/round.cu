@@ -164,7 +164,7 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
     double* X;  // rows to rotate (p x q)
     if (path == kPathTall) {
         // M^T (c x m): rows orthonormalised in place, R (c x c) holds M^T = Q^T R  =>  M = Q_col R
-        TTB_PROPAGATE(transpose(M, m, c, c, big, m, stream));
+        { ProfScope ps_("svd.transpose", stream); TTB_PROPAGATE(transpose(M, m, c, c, big, m, stream)); }
         TTB_PROPAGATE(orth_rows(big, c, m, m, Rm, c, sub, rest, stream));
         X = Rm;
     } else {
@@ -184,7 +184,11 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
     // rows below 1e-3 delta are discarded whatever happens to them (their total energy is
     // < 1e-6 p delta^2): no need to orthogonalise them against each other
     const double noise_floor = (!with_normalizing && delta > 0.0 && jacobi_abs_tol > 0.0) ? 1e-3 * delta : 0.0;
-    const int jst = jacobi_rows(X, p, q, q, J, jacobi_abs_tol, noise_floor, 40, &sweeps, conv, hw.conv, stream);
+    int jst;
+    {
+        ProfScope ps_("svd.jacobi", stream);
+        jst = jacobi_rows(X, p, q, q, J, jacobi_abs_tol, noise_floor, 40, &sweeps, conv, hw.conv, stream);
+    }
     if (jst != kOk && jst != kNotConverged) return jst;
     g_t_jac += pt.tick();
     TTB_PROPAGATE(svd_select(X, p, q, q, delta, with_normalizing ? 1 : 0, max_rank, perm, sigma, info, nrm2,
@@ -212,7 +216,7 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
         g.A = big; g.sAm = 1; g.sAk = m;
         g.B = Jsel; g.sBk = 1; g.sBn = p;
         g.C = U_out; g.ldc = rho;
-        TTB_PROPAGATE(gemm(g, sub, rest, stream));
+        { ProfScope ps_("svd.gemm_U", stream); TTB_PROPAGATE(gemm(g, sub, rest, stream)); }
     } else if (path == kPathWideLQ) {
         // L = J^T Xrot  =>  M = J^T Xrot Q:  U = J^T[:, sel],  carry = Xrot[sel] (rho x m) . Q (m x c)
         TTB_PROPAGATE(gather_rows(J, p, perm, rho, p, U_out, rho, true, stream));
@@ -276,8 +280,9 @@ int right_orth_step(double* core_k, int64_t c, int64_t m, double* core_prev, int
     g.A = core_prev; g.sAm = c; g.sAk = 1;
     g.B = R; g.sBk = 1; g.sBn = c;
     g.C = pushed; g.ldc = c_new;
+    { ProfScope ps_("rq.gemm_push+copy", stream);
     TTB_PROPAGATE(gemm(g, sub, rest, stream));
-    TTB_CHECK_CUDA(cudaMemcpyAsync(core_prev, pushed, size_t(P) * c_new * 8, cudaMemcpyDeviceToDevice, stream));
+    TTB_CHECK_CUDA(cudaMemcpyAsync(core_prev, pushed, size_t(P) * c_new * 8, cudaMemcpyDeviceToDevice, stream)); }
     if (c_new_out) *c_new_out = c_new;
     return kOk;
 }
@@ -379,8 +384,9 @@ int round_tt(const TTDesc& t, double eps, int max_rank, int64_t* ranks_out, doub
         g.A = SVt; g.sAm = c; g.sAk = 1;
         g.B = t.core[k + 1]; g.sBk = ncols; g.sBn = 1;
         g.C = tmp; g.ldc = ncols;
+        { ProfScope ps_("fwd.gemm_carry+copy", stream);
         TTB_PROPAGATE(gemm(g, sub, rest, stream));
-        TTB_CHECK_CUDA(cudaMemcpyAsync(t.core[k + 1], tmp, size_t(rho) * ncols * 8, cudaMemcpyDeviceToDevice, stream));
+        TTB_CHECK_CUDA(cudaMemcpyAsync(t.core[k + 1], tmp, size_t(rho) * ncols * 8, cudaMemcpyDeviceToDevice, stream)); }
         r[k + 1] = rho;
     }
     if (pt.on) {
@@ -388,6 +394,7 @@ int round_tt(const TTDesc& t, double eps, int max_rank, int64_t* ranks_out, doub
         fprintf(stderr, "[round] RQ pass %.2f ms | forward %.2f ms: qr %.2f, jacobi %.2f, select+U %.2f, carry+other %.2f\n",
                 g_t_rq, fwd, g_t_qr, g_t_jac, g_t_rest, fwd - g_t_qr - g_t_jac - g_t_rest);
     }
+    prof_report("round_tt");
     for (int k = 0; k <= d; ++k) ranks_out[k] = r[k];
     if (delta_out) *delta_out = delta_abs;
     return kOk;

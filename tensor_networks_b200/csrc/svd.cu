@@ -81,60 +81,39 @@ struct RotTol {
     double abs_tol2;  // skip rotation when g_ij^2 <= abs_tol2 * max(g_ii, g_jj)
     double noise2;    // skip pairs whose rows are both below this squared norm
 };
-struct JacobiRoundState {
-    double* Gc;  // current / next Gram and accumulated rotation (ping-pong, swapped by value)
-    double* Gn;
-    double* Wc;
-    double* Wn;
-    int flipped;  // 1: the current buffers are the second pair
-};
-
-// One pass of disjoint-pair rounds on the R2 x R2 Gram matrix (R2 = 2 bsz = 8, 16 or 32) of the
-// staged rows.  mode 0: pairs INSIDE each of the two blocks (two independent tournaments of bsz
-// players, bsz - 1 rounds); mode 1: CROSS pairs (i in the first block, j in the second, bsz rounds:
-// i <-> bsz + (i + rd) mod bsz).  Per round: (1) R2/2 threads compute the rotations, (2) every
-// element of G' = Rot G Rot^T and W' = Rot W is produced from the OLD matrices (ping-pong buffers),
-// so a round costs two block barriers.  rot_a/rot_b/rot_p describe row k of the rotation:
-// row_k' = rot_a row_k + rot_b row_{rot_p}.  Must be called by all JB_NT threads.
-__device__ __forceinline__ void jacobi_rounds(JacobiRoundState& st, int R2, int bsz, int mode, const RotTol rt,
-                                              bool track, double* rot_a, double* rot_b, int* rot_p,
-                                              double* blk_max) {
+// One pass of disjoint-pair rounds on the R2 x R2 Gram matrix G (R2 = 2 bsz = 8, 16 or 32) of the
+// staged rows, accumulating the rotations in W (both updated IN PLACE).
+// mode 0: pairs INSIDE each of the two blocks (two independent tournaments of bsz players, bsz - 1
+// rounds); mode 1: CROSS pairs (i in the first block, j in the second, bsz rounds:
+// i <-> bsz + (i + rd) mod bsz).  A round has bsz disjoint pairs (i_a, j_a).  (1) bsz threads of
+// warp 0 compute the rotations; (2) the two-sided update G <- Rot G Rot^T is done by 2 x 2 blocks
+// {i_a, j_a} x {i_b, j_b}: each block is read and written by exactly one thread, so no second buffer
+// is needed and shared-memory traffic is 4 loads + 4 stores per 4 elements (the per-element
+// formulation re-read every input 4 times and was bound by shared-memory bandwidth); W <- Rot W by
+// row pairs.  Two block barriers per round.  Must be called by all JB_NT threads.
+template <int R2C>  // R2C > 0: compile-time row count, 0: use the R2 argument
+__device__ __forceinline__ void jacobi_rounds(double* G, double* W, int R2_arg, int bsz, int mode, const RotTol rt,
+                                              bool track, double2* pcs, int2* pij, double* blk_max) {
     const int tid = threadIdx.x;
-    const int lg2 = (R2 == 32) ? 5 : (R2 == 16 ? 4 : 3);
-    const int nrounds = (mode == 0) ? ((bsz & 1) ? bsz : bsz - 1) : bsz;
-    double* Gc = st.Gc;
-    double* Gn = st.Gn;
-    double* Wc = st.Wc;
-    double* Wn = st.Wn;
+    const int R2 = R2C > 0 ? R2C : R2_arg;
+    const int np = R2 >> 1;  // pairs per round (bsz is a multiple of 4)
+    const int nrounds = (mode == 0) ? bsz - 1 : bsz;
+    double run_max = 0.0;  // largest squared relative off-diagonal this thread has met (pair owners only)
     for (int rd = 0; rd < nrounds; ++rd) {
-        if (tid < R2) {  // identity rotation unless a pair is assigned below
-            rot_a[tid] = 1.0;
-            rot_b[tid] = 0.0;
-            rot_p[tid] = tid;
-        }
-        __syncwarp();
-        bool have = false;
-        int i = 0, j = 0;
-        if (mode == 0) {
-            // two half-tournaments: threads [0, b/2) work on rows [0, b), threads [b/2, b) on [b, 2b)
-            const int hp = bsz >> 1;
-            if (bsz >= 2 && tid < 2 * hp) {
-                const int half = tid / hp, k = tid % hp;
-                rr_pair(bsz, rd, k, i, j);
+        if (tid < np) {
+            int i, j;
+            if (mode == 0) {
+                const int hp = bsz >> 1, half = tid / hp;
+                rr_pair(bsz, rd, tid % hp, i, j);
                 i += half * bsz;
                 j += half * bsz;
-                have = true;
+            } else {
+                i = tid;
+                j = tid + rd;
+                if (j >= bsz) j -= bsz;
+                j += bsz;
             }
-        } else if (tid < bsz) {
-            i = tid;
-            j = tid + rd;
-            if (j >= bsz) j -= bsz;
-            j += bsz;
-            have = true;
-        }
-        double myrel = 0.0;
-        if (have) {
-            const double a = Gc[i * JB_GP + i], b = Gc[j * JB_GP + j], c = Gc[i * JB_GP + j];
+            const double a = G[i * JB_GP + i], b = G[j * JB_GP + j], c = G[i * JB_GP + j];
             double cs = 1.0, sn = 0.0;
             if (a > 0.0 && b > 0.0 && c != 0.0 && fmax(a, b) > rt.noise2) {
                 // scale the 2 x 2 problem by a power of two so that max(a, b) is in [1, 2)
@@ -144,7 +123,8 @@ __device__ __forceinline__ void jacobi_rounds(JacobiRoundState& st, int R2, int 
                 const double c2 = cs_ * cs_;
                 const bool small_abs = c * c <= rt.abs_tol2 * fmax(a, b);
                 if (ab > 1e-30) {
-                    if (track && !small_abs) myrel = c2 * fast_rcp(ab);  // off the critical path
+                    // convergence monitor only: a 2^-20 reciprocal is plenty, and it stays off the critical path
+                    if (track && !small_abs) run_max = fmax(run_max, c2 * rcp_seed64(ab));
                     if (c2 > rt.tol2 * ab && !small_abs) {
                         // cos(2 theta) = |tau| / h, sin(2 theta) = 2c / h with tau = b - a, h = hypot(tau, 2c):
                         // cs^2 = (1 + cos 2theta) / 2 in [1/2, 1] (no cancellation), sn = sin(2 theta) / (2 cs).
@@ -152,16 +132,16 @@ __device__ __forceinline__ void jacobi_rounds(JacobiRoundState& st, int R2, int 
                         const double tau = bs - as;
                         const double tc = 2.0 * cs_;
                         const double h2 = fma(tau, tau, tc * tc);
-                        const double rs = fast_rsqrt(h2);
+                        const double rs = fast_rsqrt3(h2);
                         const double cs2 = fma(0.5 * fabs(tau), rs, 0.5);
-                        const double rcs = fast_rsqrt(cs2);
+                        const double rcs = fast_rsqrt3(cs2);
                         cs = cs2 * rcs;
-                        sn = copysign(0.5 * tc * rs * rcs, tc * tau);
+                        sn = copysign((0.5 * tc * rs) * rcs, tc * tau);
                     }
                 } else {
                     // extremely graded pair (b / a < 1e-30): exact library arithmetic
                     const double rel2 = c2 / ab;
-                    if (track && !small_abs) myrel = rel2;
+                    if (track && !small_abs) run_max = fmax(run_max, rel2);
                     if (rel2 > rt.tol2 && !small_abs) {
                         const double tau = bs - as;
                         const double tc = 2.0 * cs_;
@@ -171,33 +151,44 @@ __device__ __forceinline__ void jacobi_rounds(JacobiRoundState& st, int R2, int 
                     }
                 }
             }
-            rot_a[i] = cs;  rot_b[i] = -sn; rot_p[i] = j;
-            rot_a[j] = cs;  rot_b[j] = sn;  rot_p[j] = i;
-        }
-        if (track && tid < 32) {  // the pair owners all sit in warp 0: one shuffle reduction, no atomics
-            myrel = warp_max(myrel);
-            if (tid == 0 && myrel > *blk_max) *blk_max = myrel;
+            // row_i' = cs row_i - sn row_j,  row_j' = sn row_i + cs row_j
+            pcs[tid] = make_double2(cs, sn);
+            pij[tid] = make_int2(i, j);
         }
         __syncthreads();
-        for (int idx = tid; idx < R2 * R2; idx += JB_NT) {
-            const int k = idx >> lg2, l = idx & (R2 - 1);  // R2 is 8, 16 or 32
-            const double ak = rot_a[k], bk = rot_b[k], al = rot_a[l], bl = rot_b[l];
-            const int pk = rot_p[k], pl = rot_p[l];
-            const double gkl = Gc[k * JB_GP + l], gkp = Gc[k * JB_GP + pl];
-            const double gpl = Gc[pk * JB_GP + l], gpp = Gc[pk * JB_GP + pl];
-            Gn[k * JB_GP + l] = ak * (al * gkl + bl * gkp) + bk * (al * gpl + bl * gpp);
-            Wn[k * JB_GP + l] = ak * Wc[k * JB_GP + l] + bk * Wc[pk * JB_GP + l];
+        const int nG = np * np;
+        for (int idx = tid; idx < nG + np * R2; idx += JB_NT) {
+            if (idx < nG) {
+                const int ra = idx / np, cb = idx % np;
+                const double2 ca = pcs[ra], cbv = pcs[cb];
+                const int2 ia = pij[ra], ib = pij[cb];
+                double* gi = G + ia.x * JB_GP;
+                double* gj = G + ia.y * JB_GP;
+                const double gii = gi[ib.x], gij = gi[ib.y], gji = gj[ib.x], gjj = gj[ib.y];
+                const double tii = fma(ca.x, gii, -ca.y * gji), tij = fma(ca.x, gij, -ca.y * gjj);
+                const double tji = fma(ca.y, gii, ca.x * gji), tjj = fma(ca.y, gij, ca.x * gjj);
+                gi[ib.x] = fma(cbv.x, tii, -cbv.y * tij);
+                gi[ib.y] = fma(cbv.y, tii, cbv.x * tij);
+                gj[ib.x] = fma(cbv.x, tji, -cbv.y * tjj);
+                gj[ib.y] = fma(cbv.y, tji, cbv.x * tjj);
+            } else {
+                const int it = idx - nG;
+                const int ra = it / R2, l = it % R2;
+                const double2 ca = pcs[ra];
+                const int2 ia = pij[ra];
+                const double wi = W[ia.x * JB_GP + l], wj = W[ia.y * JB_GP + l];
+                W[ia.x * JB_GP + l] = fma(ca.x, wi, -ca.y * wj);
+                W[ia.y * JB_GP + l] = fma(ca.y, wi, ca.x * wj);
+            }
         }
-        {
-            double* tg = Gc; Gc = Gn; Gn = tg;
-            double* tw = Wc; Wc = Wn; Wn = tw;
-        }
-        st.flipped ^= 1;
         __syncthreads();
     }
-    st.Gc = Gc; st.Gn = Gn; st.Wc = Wc; st.Wn = Wn;
+    if (track && tid < 32) {  // the pair owners all sit in warp 0: one shuffle reduction per call, no atomics
+        run_max = warp_max(run_max);
+        if (tid == 0 && run_max > *blk_max) *blk_max = run_max;
+    }
+    __syncthreads();
 }
-
 
 __global__ void __launch_bounds__(JB_NT, 1) jacobi_block_kernel(const JacobiParams p) {
     extern __shared__ __align__(16) double sm[];
@@ -205,10 +196,8 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_block_kernel(const JacobiPara
     const int R2 = 2 * p.b;
     double* G = T + size_t(R2) * p.pitch;   // [R2][JB_GP]
     double* W = G + JB_MAXR * JB_GP;        // [R2][JB_GP]
-    double* G2 = W + JB_MAXR * JB_GP;       // ping-pong partners
-    double* W2 = G2 + JB_MAXR * JB_GP;
-    __shared__ double rot_a[JB_MAXR], rot_b[JB_MAXR];
-    __shared__ int rot_p[JB_MAXR];
+    __shared__ double2 pcs[JB_MAXR / 2];
+    __shared__ int2 pij[JB_MAXR / 2];
     __shared__ double blk_max;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -293,18 +282,10 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_block_kernel(const JacobiPara
     }
     __syncthreads();
 
-    // ---- cyclic two-sided Jacobi rounds on G, accumulating W (rows) ----
-    JacobiRoundState st{G, G2, W, W2, 0};
+    // ---- cyclic two-sided Jacobi rounds on G, accumulating W (rows), in place ----
     RotTol rt{p.tol * p.tol, p.abs_tol2, p.noise2};
     for (int sw = 0; sw < p.inner_sweeps; ++sw)
-        jacobi_rounds(st, R2, p.b, p.mode, rt, sw == 0, rot_a, rot_b, rot_p, &blk_max);
-    if (st.flipped) {  // results live in the second buffers: W is what the apply phase reads
-        for (int idx = tid; idx < R2 * R2; idx += JB_NT) {
-            const int k = idx / R2, l = idx % R2;
-            W[k * JB_GP + l] = W2[k * JB_GP + l];
-        }
-        __syncthreads();
-    }
+        jacobi_rounds<0>(G, W, R2, p.b, p.mode, rt, sw == 0, pcs, pij, &blk_max);
     bool any_rot = false;
     // did anything rotate?  (W != I)
     {
@@ -392,7 +373,8 @@ struct JacobiClusterParams {
     double tol, abs_tol2, noise2;
     double stop_rel;  // a sweep whose largest relative off-diagonal (before rotation) is below this ends the iteration
     int max_sweeps;
-    double* out;  // out[0] = sweeps done, out[1] = 1 when converged
+    double* out;  // out[0] = sweeps done, out[1] = 1 when converged, out[2..7] = phase clocks (debug)
+    int timing;   // 1: thread 0 of CTA 0 accumulates clock64() per phase section into out[2..7]
 };
 constexpr int JC_B = 16;
 constexpr int JC_MAXH = 16;
@@ -405,10 +387,8 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
     constexpr int R2 = 2 * JC_B;
     double* G = T + size_t(R2) * p.pitch;   // [R2][JB_GP]
     double* W = G + JB_MAXR * JB_GP;
-    double* G2 = W + JB_MAXR * JB_GP;
-    double* W2 = G2 + JB_MAXR * JB_GP;
-    __shared__ double rot_a[JB_MAXR], rot_b[JB_MAXR];
-    __shared__ int rot_p[JB_MAXR];
+    __shared__ double2 pcs[JB_MAXR / 2];
+    __shared__ int2 pij[JB_MAXR / 2];
     __shared__ double blk_max;
     __shared__ double conv_in[JC_MAXH];
     __shared__ int arr_top[JC_MAXH], arr_bot[JC_MAXH];
@@ -454,6 +434,15 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
     int sweeps = 0;
     bool converged = false;
     double sweep_max = 0.0;  // meaningful on thread 0
+    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = 0;
+    const bool timing = p.timing != 0 && tid == 0 && rank == 0;
+#define JC_TICK(slot)                       \
+    if (timing) {                           \
+        const long long now_ = clock64();   \
+        tacc[slot] += now_ - tlast;         \
+        tlast = now_;                       \
+    }
+    if (timing) tlast = clock64();
     for (int sweep = 0; sweep < p.max_sweeps && !converged; ++sweep) {
         for (int phase = 0; phase < nphase; ++phase) {
             // ---- Gram matrix of the staged rows over the first q columns (DMMA) ----
@@ -491,59 +480,84 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
             }
             __syncthreads();
 
+            JC_TICK(0)
             // ---- rotations ----
-            JacobiRoundState st{G, G2, W, W2, 0};
-            if (phase == 0) jacobi_rounds(st, R2, JC_B, 0, rt, true, rot_a, rot_b, rot_p, &blk_max);
-            jacobi_rounds(st, R2, JC_B, 1, rt, true, rot_a, rot_b, rot_p, &blk_max);
-            const double* Wf = st.Wc;
+            if (phase == 0) jacobi_rounds<2 * JC_B>(G, W, R2, JC_B, 0, rt, true, pcs, pij, &blk_max);
+            jacobi_rounds<2 * JC_B>(G, W, R2, JC_B, 1, rt, true, pcs, pij, &blk_max);
+            const double* Wf = W;
             if (tid == 0) sweep_max = fmax(sweep_max, blk_max);
+            JC_TICK(1)
 
-            // ---- apply: rows' = Wf . T, one 32-column slab per warp, results stay in registers ----
-            const int n0 = warp * 32;
-            const int nt = (n0 < p.ncol) ? min(4, (p.ncol - n0) / 8) : 0;
-            double acc[R2 / 8][4][2];
-#pragma unroll
-            for (int i = 0; i < R2 / 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-            if (nt > 0) {
-#pragma unroll
-                for (int ks = 0; ks < R2 / 4; ++ks) {
-                    double a[R2 / 8], bf[4];
-#pragma unroll
-                    for (int i = 0; i < R2 / 8; ++i) a[i] = Wf[(8 * i + (lane >> 2)) * JB_GP + ks * 4 + (lane & 3)];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        bf[j] = (j < nt) ? T[size_t(ks * 4 + (lane & 3)) * p.pitch + n0 + 8 * j + (lane >> 2)] : 0.0;
+            // ---- apply: rows' = Wf . T in place, one 32-column slab per warp (slabs are disjoint) ----
+            {
+                const int n0 = warp * 32;
+                const int nt = (n0 < p.ncol) ? min(4, (p.ncol - n0) / 8) : 0;
+                if (nt > 0) {
+                    double acc[R2 / 8][4][2];
 #pragma unroll
                     for (int i = 0; i < R2 / 8; ++i)
 #pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < R2 / 4; ++ks) {
+                        double a[R2 / 8], bf[4];
+#pragma unroll
+                        for (int i = 0; i < R2 / 8; ++i) a[i] = Wf[(8 * i + (lane >> 2)) * JB_GP + ks * 4 + (lane & 3)];
+#pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            if (j < nt) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
+                            bf[j] = (j < nt) ? T[size_t(ks * 4 + (lane & 3)) * p.pitch + n0 + 8 * j + (lane >> 2)] : 0.0;
+#pragma unroll
+                        for (int i = 0; i < R2 / 8; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (j < nt) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < R2 / 8; ++i) {
+                        double* base = T + size_t(8 * i + (lane >> 2)) * p.pitch + n0 + 2 * (lane & 3);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < nt) *reinterpret_cast<double2*>(base + 8 * j) = make_double2(acc[i][j][0], acc[i][j][1]);
+                    }
                 }
             }
-            cluster.sync();  // (A) every CTA has finished reading its tile
+            JC_TICK(2)
+            if (h == 1) {  // a single pair: nothing moves
+                __syncthreads();
+                if (tid == 0) {
+                    conv_in[0] = sweep_max;
+                    sweep_max = 0.0;
+                }
+                __syncthreads();
+                continue;
+            }
+            cluster.sync();  // (A) the tiles of every CTA are final for this phase
+            JC_TICK(3)
 
-            // ---- exchange: circle-method rotation of the blocks, position top[0] fixed ----
-            int dst_top_rank = rank, dst_top_slot = 0, dst_bot_rank = rank, dst_bot_slot = 1;
-            if (h > 1) {
-                if (rank == 0) {
-                    dst_bot_rank = 1; dst_bot_slot = 0;          // bottom[0] -> top[1]
-                } else {
-                    dst_bot_rank = rank - 1;                      // bottom[k] -> bottom[k-1]
-                    if (rank < h - 1) dst_top_rank = rank + 1;    // top[k] -> top[k+1]
-                    else dst_top_slot = 1;                        // top[h-1] -> bottom[h-1]
-                }
-            }
-            if (nt > 0) {
-                double* Ttop = cluster.map_shared_rank(T, dst_top_rank) + size_t(dst_top_slot * JC_B) * p.pitch;
-                double* Tbot = cluster.map_shared_rank(T, dst_bot_rank) + size_t(dst_bot_slot * JC_B) * p.pitch;
+            // ---- exchange: circle-method rotation of the blocks, position top[0] fixed.  Every CTA
+            // PULLS the rows it owns next (coalesced 16-byte DSMEM loads into registers), then, once
+            // all CTAs have pulled, overwrites its own tile. ----
+            int src_top_rank, src_top_slot = 0, src_bot_rank, src_bot_slot = 1;
+            if (rank == 0) src_top_rank = 0;                                    // top[0] stays
+            else if (rank == 1) { src_top_rank = 0; src_top_slot = 1; }         // top[1] <- bottom[0]
+            else src_top_rank = rank - 1;                                       // top[k] <- top[k-1]
+            if (rank == h - 1) { src_bot_rank = rank; src_bot_slot = 0; }       // bottom[h-1] <- top[h-1]
+            else src_bot_rank = rank + 1;                                       // bottom[k] <- bottom[k+1]
+            constexpr int kPull = (R2 * 32 * JB_NWARP / 2) / JB_NT;  // 16-byte chunks per thread at ncol = 32 * JB_NWARP
+            double2 pulled[kPull];
+            {
+                const double* Stop = cluster.map_shared_rank(T, src_top_rank) + size_t(src_top_slot * JC_B) * p.pitch;
+                const double* Sbot = cluster.map_shared_rank(T, src_bot_rank) + size_t(src_bot_slot * JC_B) * p.pitch;
+                const int cpr = p.ncol >> 1;
 #pragma unroll
-                for (int i = 0; i < R2 / 8; ++i) {
-                    double* base = ((i < 2) ? Ttop : Tbot) + size_t(8 * (i & 1) + (lane >> 2)) * p.pitch + n0 + 2 * (lane & 3);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j < nt) *reinterpret_cast<double2*>(base + 8 * j) = make_double2(acc[i][j][0], acc[i][j][1]);
+                for (int u = 0; u < kPull; ++u) {
+                    const int idx = tid + u * JB_NT;
+                    if (idx < R2 * cpr) {
+                        const int a = idx / cpr, k2 = (idx % cpr) * 2;
+                        const double* src = ((a < JC_B) ? Stop : Sbot) + size_t(a & (JC_B - 1)) * p.pitch + k2;
+                        pulled[u] = *reinterpret_cast<const double2*>(src);
+                    }
                 }
             }
             if (tid == 0) {
@@ -563,7 +577,20 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
                     sweep_max = 0.0;
                 }
             }
-            cluster.sync();  // (B) the rows of the next phase have arrived
+            JC_TICK(4)
+            cluster.sync();  // (B) every CTA has pulled its rows: the tiles may be overwritten
+            {
+                const int cpr = p.ncol >> 1;
+#pragma unroll
+                for (int u = 0; u < kPull; ++u) {
+                    const int idx = tid + u * JB_NT;
+                    if (idx < R2 * cpr) {
+                        const int a = idx / cpr, k2 = (idx % cpr) * 2;
+                        *reinterpret_cast<double2*>(T + size_t(a) * p.pitch + k2) = pulled[u];
+                    }
+                }
+            }
+            JC_TICK(5)
         }
         ++sweeps;
         double mx = 0.0;
@@ -586,7 +613,10 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
     if (rank == 0 && tid == 0) {
         p.out[0] = double(sweeps);
         p.out[1] = converged ? 1.0 : 0.0;
+        if (timing)
+            for (int k = 0; k < 6; ++k) p.out[2 + k] = double(tacc[k]);
     }
+#undef JC_TICK
 }
 
 __global__ void set_identity_kernel(double* J, int p) {
@@ -683,7 +713,7 @@ int pick_block(int p, int q, int* ncol_out, int* qx_out, size_t* smem_out) {
     cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (maxsm <= 0) maxsm = 227 * 1024;
     for (int R2 = JB_MAXR; R2 >= 8; R2 /= 2) {
-        const size_t bytes = (size_t(R2) * pitch + 4 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
+        const size_t bytes = (size_t(R2) * pitch + 2 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
         if (bytes + 2048 <= size_t(maxsm)) {
             *ncol_out = ncol;
             *qx_out = qx;
@@ -723,7 +753,7 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
         cp.pitch = cp.ncol + 4;
         int nbc = std::max(2, ceil_div(p, JC_B));
         if (nbc & 1) ++nbc;
-        const size_t csmem = (size_t(2 * JC_B) * cp.pitch + 4 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
+        const size_t csmem = (size_t(2 * JC_B) * cp.pitch + 2 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
         int dev = 0, maxsm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -735,6 +765,8 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
             cp.stop_rel = std::max(cp.tol, 1e-9);
             cp.max_sweeps = max_sweeps;
             cp.out = reinterpret_cast<double*>(conv_dev);
+            static const bool jtiming = getenv("TTB_JACOBI_TIMING") != nullptr;
+            cp.timing = jtiming ? 1 : 0;
             static size_t cconfigured = 0;
             if (csmem > cconfigured) {
                 TTB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(csmem)));
@@ -756,8 +788,11 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
             if (le == cudaSuccess) {
                 ++g_launch_count;
                 double* hout = reinterpret_cast<double*>(conv_host_pinned);
-                TTB_CHECK_CUDA(cudaMemcpyAsync(hout, cp.out, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+                TTB_CHECK_CUDA(cudaMemcpyAsync(hout, cp.out, (jtiming ? 8 : 2) * sizeof(double), cudaMemcpyDeviceToHost, stream));
                 TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
+                if (jtiming)
+                    fprintf(stderr, "[jacobi] p=%d q=%d sweeps=%d clocks: gram %.0f rounds %.0f apply %.0f syncA %.0f xchg %.0f syncB %.0f\n",
+                            p, q, int(hout[0]), hout[2], hout[3], hout[4], hout[5], hout[6], hout[7]);
                 if (sweeps_out) *sweeps_out = int(hout[0]);
                 if (hout[1] != 0.0) return kOk;
                 set_last_error("jacobi_rows: not converged after " + std::to_string(max_sweeps) + " sweeps");
@@ -800,7 +835,7 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
     jp.abs_tol2 = abs_tol * abs_tol;
     jp.noise2 = noise_floor * noise_floor;
     jp.conv = conv_dev;
-    smem = (size_t(2 * b) * jp.pitch + 4 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
+    smem = (size_t(2 * b) * jp.pitch + 2 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
     static size_t configured = 0;
     if (smem > configured) {
         TTB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
