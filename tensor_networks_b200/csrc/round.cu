@@ -180,6 +180,32 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
         }
     }
     g_t_qr += pt.tick();
+    // ---- no-truncation certificate (tall path): sigma_min(R) >= 1 / ||R^{-1}||_F > delta means the
+    // tail-energy rule keeps every singular value; Q and R then already are a valid (U, carry) pair ----
+    static const bool cert_enabled = [] {
+        const char* e = getenv("TTB_SVD_CERT");
+        return e == nullptr || e[0] != '0';
+    }();
+    if (cert_enabled && path == kPathTall && sigma_out == nullptr && U_out != big && tri_inv_fro_supported(p) &&
+        (max_rank <= 0 || max_rank >= p)) {
+        { ProfScope ps_("svd.certificate", stream); TTB_PROPAGATE(tri_inv_fro(Rm, p, c, info, stream)); }
+        TTB_CHECK_CUDA(cudaMemcpyAsync(hw.info, info, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
+        const double inv_f2 = hw.info[0], fro2 = hw.info[1];
+        const double d_abs = with_normalizing ? delta * std::sqrt(fro2) : delta;
+        if (hw.info[2] == 0.0 && inv_f2 > 0.0 && 1.0 / std::sqrt(inv_f2) > d_abs * (1.0 + 1e-6)) {
+            res->rank = p;
+            res->delta_abs = d_abs;
+            res->remaining_delta = d_abs;
+            res->fro2 = fro2;
+            res->sweeps = 0;
+            res->converged = true;
+            TTB_CHECK_CUDA(cudaMemcpyAsync(SVt_out, Rm, size_t(p) * c * 8, cudaMemcpyDeviceToDevice, stream));
+            { ProfScope ps_("svd.transpose", stream); TTB_PROPAGATE(transpose(big, c, m, m, U_out, c, stream)); }
+            g_t_rest += pt.tick();
+            return kOk;
+        }
+    }
     int sweeps = 0;
     // rows below 1e-3 delta are discarded whatever happens to them (their total energy is
     // < 1e-6 p delta^2): no need to orthogonalise them against each other

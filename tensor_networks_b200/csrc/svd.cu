@@ -619,6 +619,103 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
 #undef JC_TICK
 }
 
+// ---------------------------------------------------------------------------
+// No-truncation certificate.  R (p x p, upper triangular, p <= TI_MAXP) is the factor of the tall
+// unfolding M = Q R.  With Y = R^{-1}: sigma_min(R) >= 1 / ||Y||_2 >= 1 / ||Y||_F.  If that bound
+// exceeds the truncation threshold, the reference's tail-energy rule (pytens/utils.py:74-85) cannot
+// drop a single singular value (its first step already fails: sigma_min^2 > delta^2), so the rank is
+// p and ANY orthonormal basis of the column space -- Q itself -- with carry R represents the same
+// tensor as U and diag(s) V^T: the SVD is not needed.  out[0] = ||Y||_F^2, out[1] = ||R||_F^2,
+// out[2] = 1 when R is singular / not finite.
+// One CTA; the tile holds R in its upper triangle and Y^T in its strict lower triangle.  Column j of
+// Y is solved by back substitution on the four lanes (j, part): lane `part` owns the terms k = part
+// (mod 4) and is the lane that stored them, so a column needs no barrier at all.
+// ---------------------------------------------------------------------------
+constexpr int TI_MAXP = 128;
+constexpr int TI_NT = 4 * TI_MAXP;
+__global__ void __launch_bounds__(TI_NT, 1) tri_inv_fro_kernel(const double* __restrict__ R, int p, int64_t ldr,
+                                                               double* __restrict__ out) {
+    extern __shared__ __align__(16) double sm[];
+    const int pitch = p + 1;
+    double* S = sm;  // [p][pitch]
+    __shared__ double yd[TI_MAXP];
+    __shared__ double red[2][TI_NT / 32];
+    __shared__ int bad_sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) bad_sh = 0;
+    double fro2 = 0.0;
+    for (int idx = tid; idx < p * p; idx += TI_NT) {
+        const int r = idx / p, c = idx % p;
+        const double v = (c >= r) ? R[int64_t(r) * ldr + c] : 0.0;
+        S[r * pitch + c] = v;
+        fro2 = fma(v, v, fro2);
+    }
+    __syncthreads();
+    if (tid < p) {
+        const double d = S[tid * pitch + tid];
+        if (!(fabs(d) > 0.0) || !(fabs(d) < 1e300)) bad_sh = 1;
+        yd[tid] = 1.0 / d;
+    }
+    __syncthreads();
+    double f2 = 0.0;
+    if (!bad_sh) {
+        const int j = tid >> 2, part = tid & 3;
+        const unsigned gmask = 0xFu << (tid & 28);
+        if (j < p) {
+            const double ydj = yd[j];
+            if (part == 0) f2 = ydj * ydj;
+            const double* yj = S + j * pitch;  // Y[k][j] for k < j lives at S[j][k]
+            for (int i = j - 1; i >= 0; --i) {
+                const double* ri = S + i * pitch;
+                // terms k = i+1 .. j-1 from the tile, k = j from the diagonal inverse
+                double s0 = 0.0, s1 = 0.0;
+                int k = i + 1 + ((part - (i + 1)) & 3);
+                for (; k + 12 < j; k += 16) {
+                    const double a0 = ri[k], a1 = ri[k + 4], a2 = ri[k + 8], a3 = ri[k + 12];
+                    const double b0 = yj[k], b1 = yj[k + 4], b2 = yj[k + 8], b3 = yj[k + 12];
+                    s0 = fma(a0, b0, s0);
+                    s1 = fma(a1, b1, s1);
+                    s0 = fma(a2, b2, s0);
+                    s1 = fma(a3, b3, s1);
+                }
+                {
+                    const double a0 = (k < j) ? ri[k] : 0.0, a1 = (k + 4 < j) ? ri[k + 4] : 0.0, a2 = (k + 8 < j) ? ri[k + 8] : 0.0;
+                    const double b0 = (k < j) ? yj[k] : 0.0, b1 = (k + 4 < j) ? yj[k + 4] : 0.0, b2 = (k + 8 < j) ? yj[k + 8] : 0.0;
+                    s0 = fma(a0, b0, s0);
+                    s1 = fma(a1, b1, s1);
+                    s0 = fma(a2, b2, s0);
+                }
+                if (part == 0) s1 = fma(ri[j], ydj, s1);
+                double sum = s0 + s1;
+                sum += __shfl_xor_sync(gmask, sum, 1);
+                sum += __shfl_xor_sync(gmask, sum, 2);
+                const double y = -sum * yd[i];
+                if (part == (i & 3)) {
+                    S[j * pitch + i] = y;
+                    f2 = fma(y, y, f2);
+                }
+            }
+        }
+    }
+    fro2 = warp_sum(fro2);
+    f2 = warp_sum(f2);
+    if (lane == 0) {
+        red[0][warp] = f2;
+        red[1][warp] = fro2;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < TI_NT / 32; ++w) {
+            a += red[0][w];
+            b += red[1][w];
+        }
+        out[0] = a;
+        out[1] = b;
+        out[2] = (bad_sh || !(a < 1e300) || !(a == a)) ? 1.0 : 0.0;
+    }
+}
+
 __global__ void set_identity_kernel(double* J, int p) {
     const int64_t total = int64_t(p) * p;
     for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -869,6 +966,22 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
     }
     set_last_error("jacobi_rows: not converged after " + std::to_string(max_sweeps) + " sweeps");
     return kNotConverged;
+}
+
+bool tri_inv_fro_supported(int p) { return p >= 1 && p <= TI_MAXP; }
+
+int tri_inv_fro(const double* R, int p, int64_t ldr, double* out_dev, cudaStream_t stream) {
+    TTB_REQUIRE(tri_inv_fro_supported(p), "tri_inv_fro: unsupported size");
+    const size_t smem = size_t(p) * (p + 1) * sizeof(double);
+    static size_t configured = 0;
+    if (smem > configured) {
+        TTB_CHECK_CUDA(cudaFuncSetAttribute(tri_inv_fro_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured = smem;
+    }
+    tri_inv_fro_kernel<<<1, TI_NT, smem, stream>>>(R, p, ldr, out_dev);
+    ++g_launch_count;
+    TTB_CHECK_CUDA(cudaGetLastError());
+    return kOk;
 }
 
 int svd_select(const double* X, int p, int q, int64_t ldx, double delta, int with_normalizing,

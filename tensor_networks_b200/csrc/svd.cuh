@@ -29,4 +29,10 @@ int svd_select(const double* X, int p, int q, int64_t ldx, double delta, int wit
 int gather_rows(const double* src, int64_t lds, const int* perm_dev, int rho, int cols, double* dst,
                 int64_t ldd, bool transpose, cudaStream_t stream);
 
+// No-truncation certificate on the triangular factor R (p x p upper triangular):
+// out_dev[0] = ||R^{-1}||_F^2 (so sigma_min(R) >= out[0]^{-1/2}), out_dev[1] = ||R||_F^2,
+// out_dev[2] = 1 when R is singular.  One CTA, p <= 128.
+bool tri_inv_fro_supported(int p);
+int tri_inv_fro(const double* R, int p, int64_t ldr, double* out_dev, cudaStream_t stream);
+
 }  // namespace ttb
