@@ -579,6 +579,37 @@ __global__ void dgks_kernel(const double* __restrict__ Rp, int w, const double* 
     if (v == 0) *flag = static_cast<unsigned long long>(__double_as_longlong(ratio));
 }
 
+// out[0] = max_v after[v] / before[v] (0 / 0 counts as 0): what a projection left of a set of rows
+__global__ void __launch_bounds__(256) ratio_max_kernel(const double* __restrict__ after,
+                                                        const double* __restrict__ before, int n,
+                                                        double* __restrict__ out) {
+    __shared__ double red[8];
+    double r = 0.0;
+    for (int v = threadIdx.x; v < n; v += blockDim.x) {
+        const double b = before[v];
+        r = fmax(r, b > 0.0 ? after[v] / b : 0.0);
+    }
+    r = warp_max(r);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t = fmax(t, red[i]);
+        out[0] = t;
+    }
+}
+
+// R[i][jc + t] += C[t][i] for i < jq, t < n  (C is n x jq, row-major)
+__global__ void add_transposed_kernel(double* __restrict__ R, int64_t ldr, int64_t jc, const double* __restrict__ C,
+                                      int64_t n, int64_t jq) {
+    const int64_t total = n * jq;
+    for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t i = idx / n, t = idx % n;
+        R[i * ldr + jc + t] += C[t * jq + i];
+    }
+}
+
 __global__ void zero_rows_kernel(double* X, int64_t rows, int64_t cols, int64_t ld) {
     const int64_t total = rows * cols;
     for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -589,8 +620,8 @@ __global__ void zero_rows_kernel(double* X, int64_t rows, int64_t cols, int64_t 
 // gemm_ws is a recommendation (split-K partials); gemm() degrades gracefully with less,
 // so only `required()` is enforced.
 struct OrthLayout {
-    size_t cbuf, rp, rd, nrm, tsqr, gemm_ws;
-    size_t required() const { return (cbuf + rp + 2 * rd + 2 * nrm + tsqr) * 8 + 10 * 256; }
+    size_t cbuf, rp, rd, nrm, tsqr, gemm_ws, bulk, bulk_nrm;
+    size_t required() const { return (cbuf + rp + 2 * rd + 2 * nrm + tsqr + bulk + 2 * bulk_nrm) * 8 + 14 * 256; }
     size_t total() const { return required() + round_up<size_t>(gemm_ws, 256); }
 };
 
@@ -601,6 +632,8 @@ OrthLayout orth_layout(int64_t c, int64_t m) {
     L.rd = QF_W * QF_W;
     L.nrm = 128;
     L.tsqr = tsqr_scratch_doubles(m);
+    L.bulk = std::min<size_t>(size_t(c) * size_t(c), size_t(4) << 20);  // bulk deflation coefficients (rest x jq)
+    L.bulk_nrm = size_t(c) + 32;
     L.gemm_ws = std::min<size_t>(std::max(gemm_workspace_bytes(QF_W, c, m), gemm_workspace_bytes(c, c, m)),
                                  size_t(64) << 20);
     return L;
@@ -681,7 +714,10 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
     double* nrm[2] = {W.take<double>(L.nrm), W.take<double>(L.nrm)};
     unsigned long long* flag = W.take<unsigned long long>(8);
     double* tsq = W.take<double>(L.tsqr);
-    TTB_REQUIRE(Cb && Rp && Rd[0] && Rd[1] && nrm[0] && nrm[1] && flag && tsq, "orth_rows: workspace carve failed");
+    double* Cbulk = W.take<double>(L.bulk);
+    double* bnrm[2] = {W.take<double>(L.bulk_nrm), W.take<double>(L.bulk_nrm)};
+    TTB_REQUIRE(Cb && Rp && Rd[0] && Rd[1] && nrm[0] && nrm[1] && flag && tsq && Cbulk && bnrm[0] && bnrm[1],
+                "orth_rows: workspace carve failed");
     void* gws = W.base + W.off;
     const size_t gws_bytes = ws_bytes - W.off;
 
@@ -702,6 +738,7 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
     // consumed so far.  They differ once a panel has been deflated; the panel being worked on is
     // first moved up to M[jq ...].  R row index = orthonormal row, column index = input vector.
     int64_t jq = 0, jc = 0;
+    bool bulk_done = false;
 
     // Fast panel: Cholesky-QR2 on up to QF_W vectors (Gram by DMMA GEMM, one-CTA Cholesky, in-place
     // triangular solve as a GEMM), inside the same DGKS-controlled projection passes.  It is only
@@ -829,6 +866,43 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
             }
             if (fs == 2) {
                 jc += wf;
+                // The rank is probably exhausted: test ALL remaining rows in one projection instead of
+                // panel by panel (one pair of large GEMMs).  Whatever the outcome the projection is
+                // kept (R accumulates its coefficients), so a negative test costs one extra BCGS pass.
+                const int64_t rest_rows = c - jc;
+                if (!bulk_done && rest_rows > wf && jq < m && size_t(rest_rows) * size_t(jq) <= L.bulk) {
+                    bulk_done = true;
+                    double* Arest = M + jc * ldm;
+                    rownorm_kernel<<<unsigned(rest_rows), 256, 0, stream>>>(Arest, m, ldm, nullptr, bnrm[0], nullptr);
+                    ++g_launch_count;
+                    {
+                        ProfScope ps_("qr.bulk_deflate_gemms", stream);
+                        GemmArgs g;  // C (rest x jq) = Arest . Qp^T
+                        g.M = rest_rows; g.N = jq; g.K = m;
+                        g.A = Arest; g.sAm = ldm; g.sAk = 1;
+                        g.B = M; g.sBk = 1; g.sBn = ldm;
+                        g.C = Cbulk; g.ldc = jq;
+                        TTB_PROPAGATE(gemm(g, gws, gws_bytes, stream));
+                        GemmArgs u;  // Arest -= C . Qp
+                        u.M = rest_rows; u.N = m; u.K = jq;
+                        u.A = Cbulk; u.sAm = jq; u.sAk = 1;
+                        u.B = M; u.sBk = ldm; u.sBn = 1;
+                        u.C = Arest; u.ldc = ldm;
+                        u.alpha = -1.0; u.beta = 1.0;
+                        TTB_PROPAGATE(gemm(u, gws, gws_bytes, stream));
+                    }
+                    rownorm_kernel<<<unsigned(rest_rows), 256, 0, stream>>>(Arest, m, ldm, nullptr, bnrm[1], nullptr);
+                    ratio_max_kernel<<<1, 256, 0, stream>>>(bnrm[1], bnrm[0], int(rest_rows), status + 16);
+                    const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(rest_rows * jq, 256), 2048));
+                    add_transposed_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jc, Cbulk, rest_rows, jq);
+                    g_launch_count += 3;
+                    TTB_CHECK_CUDA(cudaMemcpyAsync(host.status, status + 16, sizeof(double), cudaMemcpyDeviceToHost, stream));
+                    TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
+                    if (debug)
+                        fprintf(stderr, "[orth_rows] bulk deflation test of %lld rows: residual ratio %.2e\n",
+                                (long long)rest_rows, host.status[0]);
+                    if (host.status[0] <= deflate_tol) jc = c;  // every remaining row is dependent
+                }
                 continue;
             }
             // declined: the staged copy was projected (and R carries those coefficients); keep the

@@ -129,7 +129,7 @@ size_t trunc_svd_workspace_bytes(int64_t m, int64_t c, bool inplace) {
 
 int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizing, int max_rank,
               double jacobi_abs_tol, bool inplace, double* U_out, double* SVt_out, double* sigma_out,
-              TruncSvdInfo* res, void* ws, size_t ws_bytes, cudaStream_t stream) {
+              TruncSvdInfo* res, void* ws, size_t ws_bytes, cudaStream_t stream, double deflate_tol) {
     TTB_REQUIRE(M && U_out && SVt_out && res, "trunc_svd: null pointer");
     TTB_REQUIRE(m >= 1 && c >= 1, "trunc_svd: empty matrix");
     TTB_REQUIRE(std::min(m, c) <= 8192, "trunc_svd: min(m, n) > 8192 unsupported");
@@ -141,8 +141,8 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
     HostWords hw;
     TTB_PROPAGATE(host_words(&hw));
     const SvdPath path = svd_path(m, c);
-    const int p = int(std::min(m, c));                      // number of singular values
-    const int q = (path == kPathWideLQ) ? p : int(c);       // length of the rows handed to Jacobi
+    int p = int(std::min(m, c));                            // number of singular values (shrinks under deflation)
+    const int q = (path == kPathWideLQ) ? int(m) : int(c);  // length of the rows handed to Jacobi
     const size_t small = size_t(p) * size_t(std::max<int64_t>(p, q));
 
     Workspace W(ws, ws_bytes);
@@ -163,18 +163,22 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
     PhaseTimer pt(stream);
     double* X;  // rows to rotate (p x q)
     if (path == kPathTall) {
-        // M^T (c x m): rows orthonormalised in place, R (c x c) holds M^T = Q^T R  =>  M = Q_col R
+        // M^T (c x m): rows orthonormalised in place, R (p x c) holds M^T = R^T Q  =>  M = Q_col R
         { ProfScope ps_("svd.transpose", stream); TTB_PROPAGATE(transpose(M, m, c, c, big, m, stream)); }
-        TTB_PROPAGATE(orth_rows(big, c, m, m, Rm, c, sub, rest, stream));
+        int64_t rk = p;
+        TTB_PROPAGATE(orth_rows(big, c, m, m, Rm, c, sub, rest, stream, deflate_tol, &rk));
+        p = int(rk);
         X = Rm;
     } else {
         if (big != M)
             TTB_CHECK_CUDA(cudaMemcpyAsync(big, M, size_t(m) * c * 8, cudaMemcpyDeviceToDevice, stream));
         if (path == kPathWideLQ) {
-            // rows of M orthonormalised in place: M^T = Q^T R  =>  M = L Q with L = R^T (m x m)
-            TTB_PROPAGATE(orth_rows(big, m, c, c, Rm, m, sub, rest, stream));
-            TTB_PROPAGATE(transpose(Rm, m, m, m, Lm, m, stream));
-            X = Lm;
+            // rows of M orthonormalised in place: M = R^T Q with Q (p x c) orthonormal rows, R (p x m).
+            // The rows of R are rotated: R = J^T Xrot with Xrot = diag(s) W^T  =>  M = W diag(s) (J Q).
+            int64_t rk = p;
+            TTB_PROPAGATE(orth_rows(big, m, c, c, Rm, m, sub, rest, stream, deflate_tol, &rk));
+            p = int(rk);
+            X = Rm;
         } else {
             X = big;
         }
@@ -186,8 +190,8 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
         const char* e = getenv("TTB_SVD_CERT");
         return e == nullptr || e[0] != '0';
     }();
-    if (cert_enabled && path == kPathTall && sigma_out == nullptr && U_out != big && tri_inv_fro_supported(p) &&
-        (max_rank <= 0 || max_rank >= p)) {
+    if (cert_enabled && path == kPathTall && p == c && sigma_out == nullptr && U_out != big &&
+        tri_inv_fro_supported(p) && (max_rank <= 0 || max_rank >= p)) {
         { ProfScope ps_("svd.certificate", stream); TTB_PROPAGATE(tri_inv_fro(Rm, p, c, info, stream)); }
         TTB_CHECK_CUDA(cudaMemcpyAsync(hw.info, info, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
         TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
@@ -213,7 +217,10 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
     int jst;
     {
         ProfScope ps_("svd.jacobi", stream);
-        jst = jacobi_rows(X, p, q, q, J, jacobi_abs_tol, noise_floor, 40, &sweeps, conv, hw.conv, stream);
+        // wide-LQ builds U from the rotated rows themselves: their mutual orthogonality must hold in
+        // the relative sense, so no absolute skip threshold there
+        jst = jacobi_rows(X, p, q, q, J, path == kPathWideLQ ? 0.0 : jacobi_abs_tol, noise_floor, 40, &sweeps, conv,
+                          hw.conv, stream);
     }
     if (jst != kOk && jst != kNotConverged) return jst;
     g_t_jac += pt.tick();
@@ -238,21 +245,21 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
         // U (m x rho) = Q_col (m x c) . Jsel^T (c x rho);  Q_col(i, k) = big[k * m + i]
         TTB_PROPAGATE(gather_rows(J, p, perm, rho, p, Jsel, p, false, stream));
         GemmArgs g;
-        g.M = m; g.N = rho; g.K = c;
+        g.M = m; g.N = rho; g.K = p;
         g.A = big; g.sAm = 1; g.sAk = m;
         g.B = Jsel; g.sBk = 1; g.sBn = p;
         g.C = U_out; g.ldc = rho;
         { ProfScope ps_("svd.gemm_U", stream); TTB_PROPAGATE(gemm(g, sub, rest, stream)); }
     } else if (path == kPathWideLQ) {
-        // L = J^T Xrot  =>  M = J^T Xrot Q:  U = J^T[:, sel],  carry = Xrot[sel] (rho x m) . Q (m x c)
-        TTB_PROPAGATE(gather_rows(J, p, perm, rho, p, U_out, rho, true, stream));
-        TTB_PROPAGATE(gather_rows(X, q, perm, rho, q, Jsel, q, false, stream));
+        // U (m x rho) = normalised selected rows of Xrot, transposed;  carry (rho x c) = (diag(s) J[sel]) . Q
+        TTB_PROPAGATE(gather_rows(X, q, perm, rho, q, U_out, rho, true, stream, sigma, 2));
+        TTB_PROPAGATE(gather_rows(J, p, perm, rho, p, Jsel, p, false, stream, sigma, 1));
         GemmArgs g;
-        g.M = rho; g.N = c; g.K = m;
-        g.A = Jsel; g.sAm = m; g.sAk = 1;
+        g.M = rho; g.N = c; g.K = p;
+        g.A = Jsel; g.sAm = p; g.sAk = 1;
         g.B = big; g.sBk = c; g.sBn = 1;
         g.C = SVt_out; g.ldc = c;
-        TTB_PROPAGATE(gemm(g, sub, rest, stream));
+        { ProfScope ps_("svd.gemm_carry_wide", stream); TTB_PROPAGATE(gemm(g, sub, rest, stream)); }
     } else {
         TTB_PROPAGATE(gather_rows(X, q, perm, rho, q, SVt_out, q, false, stream));
         // U (m x rho) = J^T[:, sel]  -> U[i][s] = J[perm[s]][i]

@@ -28,9 +28,11 @@ struct RoundStats {
 // inplace: M may be destroyed (saves the m x c scratch copy on the wide paths); then
 // SVt_out must not alias M.
 size_t trunc_svd_workspace_bytes(int64_t m, int64_t c, bool inplace);
+// deflate_tol > 0: rows / columns that are numerically dependent at that relative level are dropped
+// by the orthogonalisation (see orth_rows) before the small factor reaches the Jacobi kernel.
 int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizing, int max_rank,
               double jacobi_abs_tol, bool inplace, double* U_out, double* SVt_out, double* sigma_out,
-              TruncSvdInfo* res, void* ws, size_t ws_bytes, cudaStream_t stream);
+              TruncSvdInfo* res, void* ws, size_t ws_bytes, cudaStream_t stream, double deflate_tol = 0.0);
 
 // One RQ step (tt_right_orth, pytens/algs.py:1654-1704).
 size_t right_orth_workspace_bytes(int64_t r_prev_n_prev, int64_t c, int64_t m);

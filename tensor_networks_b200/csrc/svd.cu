@@ -785,15 +785,20 @@ __global__ void __launch_bounds__(SEL_NT) svd_select_kernel(const double* __rest
     }
 }
 
-// dst (rho x cols) rows = src[perm[i]] ; optionally transposed destination (cols x rho)
+// dst (rho x cols) rows = src[perm[i]] ; optionally transposed destination (cols x rho).
+// scale_mode 1: row i multiplied by sigma[i]; 2: divided by sigma[i] (zero rows stay zero).
 __global__ void gather_rows_kernel(const double* __restrict__ src, int64_t lds, const int* __restrict__ perm,
                                    int rho, int cols, double* __restrict__ dst, int64_t ldd,
-                                   int transpose) {
+                                   int transpose, const double* __restrict__ sigma, int scale_mode) {
     const int64_t total = int64_t(rho) * cols;
     for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
          idx += int64_t(gridDim.x) * blockDim.x) {
+        // consecutive threads walk the contiguous index of the DESTINATION when transposing small
+        // outputs would not matter; keep reads coalesced (rows of src are long)
         const int i = int(idx / cols), k = int(idx % cols);
-        const double v = src[int64_t(perm[i]) * lds + k];
+        double v = src[int64_t(perm[i]) * lds + k];
+        if (scale_mode == 1) v *= sigma[i];
+        if (scale_mode == 2) v = (sigma[i] > 0.0) ? v / sigma[i] : 0.0;
         if (transpose)
             dst[int64_t(k) * ldd + i] = v;
         else
@@ -996,10 +1001,12 @@ int svd_select(const double* X, int p, int q, int64_t ldx, double delta, int wit
 }
 
 int gather_rows(const double* src, int64_t lds, const int* perm_dev, int rho, int cols, double* dst,
-                int64_t ldd, bool transpose, cudaStream_t stream) {
+                int64_t ldd, bool transpose, cudaStream_t stream, const double* sigma_dev, int scale_mode) {
     if (rho <= 0 || cols <= 0) return kOk;
+    TTB_REQUIRE(scale_mode == 0 || sigma_dev != nullptr, "gather_rows: scaling needs sigma");
     const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(int64_t(rho) * cols, 256), 4096));
-    gather_rows_kernel<<<blocks, 256, 0, stream>>>(src, lds, perm_dev, rho, cols, dst, ldd, transpose ? 1 : 0);
+    gather_rows_kernel<<<blocks, 256, 0, stream>>>(src, lds, perm_dev, rho, cols, dst, ldd, transpose ? 1 : 0, sigma_dev,
+                                                   scale_mode);
     ++g_launch_count;
     TTB_CHECK_CUDA(cudaGetLastError());
     return kOk;

@@ -27,7 +27,8 @@ int svd_select(const double* X, int p, int q, int64_t ldx, double delta, int wit
 
 // dst[i, :] = src[perm[i], :] for i < rho (or the transpose of that when `transpose`).
 int gather_rows(const double* src, int64_t lds, const int* perm_dev, int rho, int cols, double* dst,
-                int64_t ldd, bool transpose, cudaStream_t stream);
+                int64_t ldd, bool transpose, cudaStream_t stream, const double* sigma_dev = nullptr,
+                int scale_mode = 0);  // scale_mode 1: row i * sigma[i], 2: row i / sigma[i]
 
 // No-truncation certificate on the triangular factor R (p x p upper triangular):
 // out_dev[0] = ||R^{-1}||_F^2 (so sigma_min(R) >= out[0]^{-1/2}), out_dev[1] = ||R||_F^2,

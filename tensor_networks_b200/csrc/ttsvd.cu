@@ -129,8 +129,11 @@ int ttsvd(const double* dense, int d, const int64_t* shape, double eps, int max_
             return kWorkspaceTooSmall;
         }
         TruncSvdInfo info{};
+        // rows of an unfolding that are dependent at working precision are dropped before the SVD
+        // (same safe deflation as the RQ pass of the rounding sweep, see round.cu)
+        const double deflate_tol = (eps > 0.0) ? std::min(1e-13, 1e-3 * eps) : 0.0;
         TTB_PROPAGATE(trunc_svd(bufA, m, c, delta, false, max_rank, 1e-14 * fro, /*inplace=*/true, arena + off,
-                                bufB, nullptr, &info, sub, rest, stream));
+                                bufB, nullptr, &info, sub, rest, stream, deflate_tol));
         const int64_t rho = info.rank;
         if (getenv("TTB_DEBUG"))
             fprintf(stderr, "[ttsvd] step %d: m=%lld c=%lld rank=%lld sweeps=%d converged=%d fro2=%.6e delta=%.3e\n", k,
@@ -144,6 +147,7 @@ int ttsvd(const double* dense, int d, const int64_t* shape, double eps, int max_
     const size_t last = size_t(r) * size_t(shape[d - 1]);
     TTB_REQUIRE(off + last <= arena_doubles, "ttsvd: core arena too small");
     TTB_CHECK_CUDA(cudaMemcpyAsync(arena + off, bufA, last * 8, cudaMemcpyDeviceToDevice, stream));
+    prof_report("ttsvd");
     return kOk;
 }
 
