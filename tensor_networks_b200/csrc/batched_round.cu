@@ -150,8 +150,9 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
     double* Rm = As + QR_W * QR_PITCH;  // R factor / rows handed to Jacobi
     double* Jm = Rm + 32 * RB_SP;
     double* Cm = Jm + 32 * RB_SP;       // carry diag(s) V^T
-    __shared__ double sdot[QR_W], arow[QR_W], tau_s[QR_W], nrm2[32], sig[32];
-    __shared__ int perm[32];
+    __shared__ double sdot[QR_W], arow[QR_W], tau_s[QR_W], nrm2[32], sig[32], nrm0[32];
+    __shared__ int perm[32], pvs[32], pvec[32];
+    __shared__ double sh_cert[3];
     __shared__ int rq[kMaxDR + 1], rk[kMaxDR + 1];
     __shared__ unsigned long long flag;
     __shared__ double sh_delta;
@@ -169,6 +170,8 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
         __syncthreads();
 
         // =========================== RQ pass ===========================
+        const double deflate_tol = (p.eps > 0.0) ? fmin(1e-13, 1e-3 * p.eps) : 0.0;
+        const double deflate_tol2 = deflate_tol * deflate_tol;
         for (int k = d - 1; k >= 1; --k) {
             const int c = p.r[k], nn = p.n[k], ro = p.r[k + 1], rn = rq[k + 1];
             double* core = p.core[k] + item * (int64_t(c) * nn * ro);
@@ -193,13 +196,41 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
             }
             __syncthreads();
             const int ww = c, hlen = m;
-            const int nsteps = min(ww, hlen);
-            for (int j = 0; j < nsteps; ++j) house_step(As, ww, hlen, j, sdot, arow, tau_s);
-            // R (nsteps x c): R[j][i] = As[i][j] for j <= i
+            // squared norms of the vectors before the factorisation: a vector whose remainder below the
+            // pivot drops to deflate_tol of its norm is dependent at working precision and consumes no
+            // pivot (echelon form) -- the bond shrinks already in this pass (same rule as round.cu)
+            for (int v = warp; v < ww; v += RB_NT / 32) {
+                double sq = 0.0;
+                for (int i = lane; i < hlen; i += 32) sq = fma(As[v * QR_PITCH + i], As[v * QR_PITCH + i], sq);
+                sq = warp_sum(sq);
+                if (lane == 0) nrm0[v] = sq;
+            }
+            __syncthreads();
+            int nsteps = 0;  // pivots consumed = orthonormal rows produced
+            for (int v = 0; v < ww; ++v) {
+                bool ok = false;
+                if (nsteps < hlen)
+                    ok = house_step_ex(As, ww, hlen, v, nsteps, fmax(deflate_tol2 * nrm0[v], 1e-300), sdot, arow, tau_s);
+                if (tid == 0) {
+                    if (ok) pvec[nsteps] = v;
+                    pvs[v] = nsteps + (ok ? 1 : 0);  // rows of R that vector v reaches
+                }
+                nsteps += ok ? 1 : 0;
+            }
+            __syncthreads();
+            // R (nsteps x c): R[j][i] = As[i][j] for j < pvs[i]
             for (int idx = tid; idx < 32 * RB_SP; idx += RB_NT) {
                 const int j = idx / RB_SP, i = idx % RB_SP;
-                Rm[idx] = (j < nsteps && i < c && j <= i) ? As[i * QR_PITCH + j] : 0.0;
+                Rm[idx] = (j < nsteps && i < c && j < pvs[i]) ? As[i * QR_PITCH + j] : 0.0;
             }
+            __syncthreads();
+            // compact the reflectors: reflector j lives in vector pvec[j] >= j (thread t moves element t of
+            // every vector itself, so no barrier is needed between the moves)
+            if (tid < hlen)
+                for (int j = 0; j < nsteps; ++j) {
+                    const int src = pvec[j];
+                    if (src != j) As[j * QR_PITCH + tid] = As[src * QR_PITCH + tid];
+                }
             __syncthreads();
             house_formq_inplace(As, nsteps, hlen, tau_s, sdot);
             for (int idx = tid; idx < nsteps * m; idx += RB_NT) core[idx] = As[(idx / m) * QR_PITCH + idx % m];
@@ -254,6 +285,62 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
             }
             __syncthreads();
             house_formq_inplace(As, psv, hlen, tau_s, sdot);
+
+            // ---- no-truncation certificate (see tri_inv_fro_kernel in svd.cu): Y = R^{-1} by back
+            // substitution, one column per thread; sigma_min(R) >= 1 / ||Y||_F > delta keeps every
+            // singular value, and then Q, R already are a valid (U, carry) pair ----
+            bool keep_all = false;
+            if (psv == c) {
+                if (tid < 32) {
+                    double f2 = 0.0, fr2 = 0.0;
+                    bool bad = false;
+                    if (tid < c) {
+                        const int j = tid;
+                        for (int i = 0; i <= j; ++i) fr2 = fma(Rm[i * RB_SP + j], Rm[i * RB_SP + j], fr2);
+                        const double rjj = Rm[j * RB_SP + j];
+                        bad = !(fabs(rjj) > 0.0);
+                        const double yjj = 1.0 / rjj;
+                        Jm[j * RB_SP + j] = yjj;
+                        f2 = yjj * yjj;
+                        for (int i = j - 1; i >= 0; --i) {
+                            double sacc = 0.0;
+                            for (int t = i + 1; t <= j; ++t) sacc = fma(Rm[i * RB_SP + t], Jm[t * RB_SP + j], sacc);
+                            const double rii = Rm[i * RB_SP + i];
+                            bad = bad || !(fabs(rii) > 0.0);
+                            const double y = -sacc / rii;
+                            Jm[i * RB_SP + j] = y;
+                            f2 = fma(y, y, f2);
+                        }
+                    }
+                    f2 = warp_sum(f2);
+                    fr2 = warp_sum(fr2);
+                    const bool anybad = __any_sync(0xffffffffu, bad);
+                    if (tid == 0) {
+                        sh_cert[0] = f2;
+                        sh_cert[1] = fr2;
+                        sh_cert[2] = (anybad || !(f2 < 1e300) || !(f2 == f2)) ? 1.0 : 0.0;
+                    }
+                }
+                __syncthreads();
+                const double dl = (k == 0) ? p.eps / sqrt(double(d - 1)) * sqrt(sh_cert[1]) : delta_abs;
+                keep_all = sh_cert[2] == 0.0 && sh_cert[0] > 0.0 && 1.0 / sqrt(sh_cert[0]) > dl * (1.0 + 1e-6) &&
+                           (p.max_rank <= 0 || p.max_rank >= c);
+                if (keep_all) {
+                    if (tid == 0) rk[k + 1] = c;
+                    delta_abs = dl;
+                    for (int idx = tid; idx < mrows * c; idx += RB_NT) {
+                        const int i = idx / c, sidx = idx % c;
+                        core[idx] = As[sidx * QR_PITCH + i];  // U = Q
+                    }
+                    for (int idx = tid; idx < 32 * RB_SP; idx += RB_NT) {
+                        const int sidx = idx / RB_SP, j = idx % RB_SP;
+                        Cm[idx] = (sidx < c && j < c) ? Rm[idx] : 0.0;  // carry = R
+                    }
+                    __syncthreads();
+                    continue;
+                }
+                __syncthreads();
+            }
 
             const double tol = 1e-15 * sqrt(double(max(c, 16)));
             const int sweeps = jacobi_rows_smem(Rm, Jm, psv, c, tol, 40, &flag);

@@ -22,26 +22,31 @@ struct LeafGeom {
     __host__ __device__ int len(int64_t i) const { return int(base + (i < rem ? 1 : 0)); }
 };
 
-// One Householder step j on the tile As[c][i] (c < ww vectors, i < hh elements):
-// annihilates As[j][j+1..], leaves beta on the diagonal, normalised v below it,
-// and applies the reflection to vectors j+1..ww-1.  Must be called by all threads.
-__device__ __forceinline__ void house_step(double* __restrict__ As, int ww, int hh, int j,
-                                           double* __restrict__ sdot, double* __restrict__ arow,
-                                           double* __restrict__ tau_s) {
+// One Householder step on the tile As[c][i] (c < ww vectors, i < hh elements) in ECHELON form:
+// vector v is reduced against pivot position pp <= v.  If what is left of vector v at and below pp
+// has squared norm <= thresh2 the vector is (numerically) a combination of the earlier ones: its
+// elements i >= pp are zeroed, nothing else changes, and the function returns false -- the caller
+// keeps the pivot for the next vector.  Otherwise the reflection annihilates As[v][pp+1..], leaves
+// beta at As[v][pp] and the normalised reflector below it, is applied to vectors v+1..ww-1,
+// tau_s[pp] is set, and the function returns true.  Must be called by all threads (the result is
+// uniform).  house_step(j) is the classical step v = pp = j without deflation.
+__device__ __forceinline__ bool house_step_ex(double* __restrict__ As, int ww, int hh, int v, int pp,
+                                              double thresh2, double* __restrict__ sdot,
+                                              double* __restrict__ arow, double* __restrict__ tau_s) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double* xj = As + j * QR_PITCH;
+    const double* xj = As + v * QR_PITCH;
     {
-        // each warp owns vectors c = j + warp + 8 t (t < 4); partial dots first, then the
+        // each warp owns vectors c = v + warp + 8 t (t < 4); partial dots first, then the
         // four shuffle reductions interleaved so their latencies overlap
         constexpr int NC = QR_W / QR_NWARP;
         double s[NC];
 #pragma unroll
         for (int t = 0; t < NC; ++t) s[t] = 0.0;
-        for (int i = j + lane; i < hh; i += 32) {
+        for (int i = pp + lane; i < hh; i += 32) {
             const double x = xj[i];
 #pragma unroll
             for (int t = 0; t < NC; ++t) {
-                const int c = j + warp + QR_NWARP * t;
+                const int c = v + warp + QR_NWARP * t;
                 if (c < ww) s[t] = fma(x, As[c * QR_PITCH + i], s[t]);
             }
         }
@@ -53,51 +58,60 @@ __device__ __forceinline__ void house_step(double* __restrict__ As, int ww, int 
         if (lane == 0) {
 #pragma unroll
             for (int t = 0; t < NC; ++t) {
-                const int c = j + warp + QR_NWARP * t;
+                const int c = v + warp + QR_NWARP * t;
                 if (c < ww) {
                     sdot[c] = s[t];
-                    arow[c] = As[c * QR_PITCH + j];
+                    arow[c] = As[c * QR_PITCH + pp];
                 }
             }
         }
     }
     __syncthreads();
-    const double nrm2 = sdot[j];
-    if (!(nrm2 > 1e-300)) {  // zero (or NaN-free denormal) vector: H = I
-        if (tid == 0) tau_s[j] = 0.0;
-        if (tid > j && tid < hh) As[j * QR_PITCH + tid] = 0.0;
+    const double nrm2 = sdot[v];
+    if (!(nrm2 > thresh2)) {  // dependent (or zero) vector: H = I, the pivot is not consumed
+        if (tid >= pp && tid < hh) As[v * QR_PITCH + tid] = 0.0;
         __syncthreads();
-        return;
+        return false;
     }
-    const double alpha = arow[j];
+    const double alpha = arow[v];
     const double beta = -copysign(fast_sqrt_any(nrm2), alpha);
     const double inv = fast_rcp_any(beta * (beta - alpha));
     const double inv_v0 = fast_rcp_any(alpha - beta);  // |alpha - beta| >= |beta| > 0: no cancellation
     const int t = tid;
-    if (t >= j && t < hh) {
-        const double ut = (t == j) ? (alpha - beta) : xj[t];
+    if (t >= pp && t < hh) {
+        const double ut = (t == pp) ? (alpha - beta) : xj[t];
         const double uti = -ut * inv;
         // batches of 8 vectors: all loads first, then the stores (no load waits on a store)
-        for (int c0 = j + 1; c0 < ww; c0 += 8) {
-            double f[8], v[8];
+        for (int c0 = v + 1; c0 < ww; c0 += 8) {
+            double f[8], w[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int c = min(c0 + u, ww - 1);
                 f[u] = sdot[c] - beta * arow[c];
-                v[u] = As[c * QR_PITCH + t];
+                w[u] = As[c * QR_PITCH + t];
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-                if (c0 + u < ww) As[(c0 + u) * QR_PITCH + t] = fma(uti, f[u], v[u]);
+                if (c0 + u < ww) As[(c0 + u) * QR_PITCH + t] = fma(uti, f[u], w[u]);
         }
-        if (t == j) {
-            As[j * QR_PITCH + j] = beta;
-            tau_s[j] = (beta - alpha) * fast_rcp_any(beta);
+        if (t == pp) {
+            As[v * QR_PITCH + pp] = beta;
+            tau_s[pp] = (beta - alpha) * fast_rcp_any(beta);
         } else {
-            As[j * QR_PITCH + t] = ut * inv_v0;
+            As[v * QR_PITCH + t] = ut * inv_v0;
         }
     }
     __syncthreads();
+    return true;
+}
+
+__device__ __forceinline__ void house_step(double* __restrict__ As, int ww, int hh, int j,
+                                           double* __restrict__ sdot, double* __restrict__ arow,
+                                           double* __restrict__ tau_s) {
+    if (!house_step_ex(As, ww, hh, j, j, 1e-300, sdot, arow, tau_s)) {
+        if (threadIdx.x == 0) tau_s[j] = 0.0;
+        __syncthreads();
+    }
 }
 
 // Apply H_j = I - tau v v^T (v from As[j][j..], v_j = 1) to the ww vectors of Bs.
