@@ -372,17 +372,17 @@ int round_tt(const TTDesc& t, double eps, int max_rank, int64_t* ranks_out, doub
     // orthonormalised is <= deflate_tol of its norm is dependent at working precision (the residual
     // is roundoff of the projection itself, below the backward error of LAPACK's QR in the
     // reference), so the bond shrinks already here and every later step works on the smaller rank.
-    static const double deflate_env = [] {
-        const char* e = getenv("TTB_DEFLATE_TOL");
-        return e ? atof(e) : 1e-13;
+    static const bool deflate_enabled = [] {
+        const char* e = getenv("TTB_DEFLATE");
+        return e == nullptr || e[0] != '0';
     }();
-    const double deflate_tol = (eps > 0.0) ? std::min(deflate_env, 1e-3 * eps) : 0.0;
     PhaseTimer pt(stream);
     g_t_qr = g_t_jac = g_t_rest = g_t_rq = g_t_push = 0;
     for (int k = d - 1; k >= 1; --k) {
         int64_t c_new = r[k];
         TTB_PROPAGATE(right_orth_step(t.core[k], r[k], t.n[k] * r[k + 1], t.core[k - 1], r[k - 1] * t.n[k - 1],
-                                      /*shrink=*/true, &c_new, sub, rest, stream, deflate_tol));
+                                      /*shrink=*/true, &c_new, sub, rest, stream,
+                                      deflate_enabled ? deflation_tolerance(eps, t.n[k] * r[k + 1]) : 0.0));
         r[k] = c_new;
     }
     g_t_rq += pt.tick();

@@ -6,6 +6,16 @@
 
 namespace ttb {
 
+// Relative level below which the remainder of a vector (after projection on the vectors already
+// orthonormalised) counts as roundoff of the projection itself.  Grows like sqrt(m) with the vector
+// length (accumulated rounding of the m-term dot products, measured 1e-15 at m = 8e3 and 4e-14 at
+// m = 1e6), and never exceeds 1e-3 of the requested accuracy; 0 disables deflation.
+inline double deflation_tolerance(double eps, int64_t m) {
+    if (!(eps > 0.0)) return 0.0;
+    const double base = 1e-13 * (m > 4096 ? __builtin_sqrt(double(m) / 4096.0) : 1.0);
+    return base < 1e-3 * eps ? base : 1e-3 * eps;
+}
+
 struct TruncSvdInfo {
     int rank;
     double delta_abs;        // absolute delta used (after optional normalisation)

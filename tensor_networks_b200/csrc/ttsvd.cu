@@ -131,7 +131,7 @@ int ttsvd(const double* dense, int d, const int64_t* shape, double eps, int max_
         TruncSvdInfo info{};
         // rows of an unfolding that are dependent at working precision are dropped before the SVD
         // (same safe deflation as the RQ pass of the rounding sweep, see round.cu)
-        const double deflate_tol = (eps > 0.0) ? std::min(1e-13, 1e-3 * eps) : 0.0;
+        const double deflate_tol = deflation_tolerance(eps, std::max(m, c));
         TTB_PROPAGATE(trunc_svd(bufA, m, c, delta, false, max_rank, 1e-14 * fro, /*inplace=*/true, arena + off,
                                 bufB, nullptr, &info, sub, rest, stream, deflate_tol));
         const int64_t rho = info.rank;

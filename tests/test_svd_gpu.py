@@ -1,0 +1,130 @@
+"""On-device SVD (cluster block-Jacobi kernel) and truncation paths against numpy / the oracle.
+
+Shapes are chosen so that every launch shape of the single-launch cluster kernel is hit
+(1, 2, 3, 4, 5, 8 CTAs per cluster, padded last blocks), plus the multi-launch fallback
+(p > 256) and the tall / wide-LQ / wide-direct paths of trunc_svd.
+"""
+
+import copy
+
+import numpy as np
+import pytest
+
+from oracle import tt_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _graded(m, n, decay, rng):
+    """Random m x n matrix with singular values 1, decay, decay^2, ... (graded spectrum)."""
+    p = min(m, n)
+    u, _ = np.linalg.qr(rng.standard_normal((m, p)))
+    v, _ = np.linalg.qr(rng.standard_normal((n, p)))
+    s = decay ** np.arange(p)
+    return (u * s) @ v.T, s
+
+
+@pytest.mark.parametrize(
+    "m,n,decay",
+    [
+        (24, 24, 0.5),      # one CTA
+        (40, 40, 0.7),      # cluster of 2, padded block
+        (96, 96, 0.8),      # cluster of 3
+        (100, 70, 0.75),    # tall, cluster of 3 (p = 70)
+        (130, 200, 0.85),   # wide direct (c < 2m), cluster of 5
+        (256, 256, 0.9),    # cluster of 8
+        (300, 64, 0.6),     # tall: QR first
+        (64, 300, 0.6),     # wide LQ
+        (1000, 250, 0.9),   # tall, 4 panels
+        (300, 300, 0.93),   # p > 256: multi-launch fallback
+    ],
+)
+def test_delta_svd_graded_vs_numpy(m, n, decay):
+    from tensor_networks_b200.utils import delta_svd_dev
+
+    rng = np.random.default_rng(m * 1000 + n)
+    a, s_true = _graded(m, n, decay, rng)
+    u, s, svt, info = delta_svd_dev(torch.from_numpy(a).cuda(), 0.0)
+    u, s, svt = u.cpu().numpy(), s.cpu().numpy(), svt.cpu().numpy()
+    s_np = np.linalg.svd(a, compute_uv=False)
+    assert info["rank"] == min(m, n)
+    big = s_np > 1e-9 * s_np[0]
+    # LAPACK (and the construction of `a` itself) is only accurate to eps * sigma_max in the absolute
+    # sense, so that is the yardstick; the large values also agree relatively
+    assert np.max(np.abs(s - s_np)) < 2e-13 * s_np[0]  # rotations accumulate a few hundred ulp
+    top = s_np > 1e-4 * s_np[0]
+    assert np.max(np.abs(s[top] - s_np[top]) / s_np[top]) < 1e-10
+    assert np.linalg.norm(u @ svt - a) <= 1e-13 * np.linalg.norm(a)
+    k = int(big.sum())
+    g = u[:, :k].T @ u[:, :k]
+    assert np.max(np.abs(g - np.eye(k))) < 1e-12
+
+
+@pytest.mark.parametrize("m,n,rank", [(200, 96, 40), (96, 200, 40), (512, 128, 17), (64, 64, 1)])
+def test_delta_svd_rank_deficient(m, n, rank):
+    """Exactly rank-deficient input: the dropped part is roundoff, the kept part is exact."""
+    from tensor_networks_b200.utils import delta_svd_dev
+
+    rng = np.random.default_rng(7 + m + n)
+    a = rng.standard_normal((m, rank)) @ rng.standard_normal((rank, n))
+    u, s, svt, info = delta_svd_dev(torch.from_numpy(a).cuda(), 1e-10 * np.linalg.norm(a))
+    assert info["rank"] == rank
+    s_np = np.linalg.svd(a, compute_uv=False)[:rank]
+    assert np.max(np.abs(s.cpu().numpy() - s_np) / s_np) < 1e-11
+    rec = (u @ svt).cpu().numpy()
+    assert np.linalg.norm(rec - a) <= 1e-12 * np.linalg.norm(a)
+
+
+def test_round_large_rank_genuine_truncation():
+    """Ranks 72 with a decaying spectrum: the SVD really truncates (no deflation, no certificate)."""
+    from tensor_networks_b200 import TensorTrain
+
+    rng = np.random.default_rng(11)
+    shape = [12] * 5
+    y = orc.rand_tt(shape, [24] * 4, rng)
+    for j in range(1, 5):
+        zt = orc.rand_tt(shape, [12] * 4, rng)
+        zt[0] = zt[0] * 10.0 ** (-2 * j)
+        y = orc.tt_add(y, zt)
+    dense = orc.to_dense(y)
+    for eps in (1e-3, 1e-5, 1e-7):
+        ref, _ = orc.svd_round(copy.deepcopy(y), eps)
+        tt = TensorTrain.from_cores(copy.deepcopy(y)).round(eps)
+        assert tt.ranks() == orc.ranks_of(ref), (eps, tt.ranks(), orc.ranks_of(ref))
+        err = np.linalg.norm(tt.dense() - dense) / np.linalg.norm(dense)
+        err_ref = np.linalg.norm(orc.to_dense(ref) - dense) / np.linalg.norm(dense)
+        assert abs(err - err_ref) <= 1e-10
+        assert err <= eps
+
+
+def test_round_full_rank_is_identity():
+    """Well-conditioned full-rank TT and a tiny eps: nothing may be truncated (certificate path)."""
+    from tensor_networks_b200 import TensorTrain
+
+    x = TensorTrain.rand([20] * 5, [40] * 4, seed=77)
+    ref, _ = orc.svd_round([c.copy() for c in x.to_cores()], 1e-12)
+    z = x.clone().round(1e-12)
+    assert z.ranks() == orc.ranks_of(ref)
+    nx, nz = x.norm(), z.norm()
+    assert abs(nx - nz) <= 1e-12 * nx
+    assert abs(float(z.inner(x)) / (nx * nz) - 1.0) < 1e-12
+
+
+def test_round_partial_deflation():
+    """X (+) X (+) noise-free third term of different rank: some panels deflate, some do not."""
+    from tensor_networks_b200 import TensorTrain
+
+    rng = np.random.default_rng(3)
+    shape = [16] * 5
+    x = orc.rand_tt(shape, [40] * 4, rng)
+    w = orc.rand_tt(shape, [9] * 4, rng)
+    y = orc.tt_add(orc.tt_add(x, w), x)  # bonds 89, true ranks <= 49
+    ref, _ = orc.svd_round(copy.deepcopy(y), 1e-9)
+    tt = TensorTrain.from_cores(copy.deepcopy(y)).round(1e-9)
+    assert tt.ranks() == orc.ranks_of(ref)
+    dense = orc.to_dense(y)
+    err = np.linalg.norm(tt.dense() - dense) / np.linalg.norm(dense)
+    err_ref = np.linalg.norm(orc.to_dense(ref) - dense) / np.linalg.norm(dense)
+    assert abs(err - err_ref) <= 1e-10
