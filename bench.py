@@ -315,7 +315,10 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dgemm_bytes_per_launch")
+                tj = json.load(open(tpath))
+                # the persistent sweep kernel is ONE launch per sweep; the per-dgemm figure applies to
+                # the multi-launch path only
+                traffic = tj.get("inner_sweep_bytes_per_launch" if int(nl.value) <= psteps else "dgemm_bytes_per_launch")
             except Exception:
                 traffic = None
         roofline = {
@@ -336,6 +339,9 @@ def main():
             "flops_per_launch": tot_fl.value / max(1, nl.value),
             "kernel_time_share_of_step": (tot_ms.value / psteps) / (ms / a.steps),
             "traffic": traffic,
+            "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/traffic.json); "
+                              "algorithmic bytes per launch = 2080636928",
+            "algorithmic_bytes_per_launch": int(nbytes),
         }
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D inside the timed region
