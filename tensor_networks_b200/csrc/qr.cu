@@ -28,6 +28,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <map>
+#include <tuple>
 #include <vector>
 
 #include "gemm.cuh"
@@ -251,7 +253,8 @@ __global__ void __launch_bounds__(CH_NT) chol_panel_kernel(const double* __restr
                                                            const double* __restrict__ nrm_prev,
                                                            double* __restrict__ Rt, double* __restrict__ Linv,
                                                            double* __restrict__ status, double deflate_tol,
-                                                           int near_identity) {
+                                                           int near_identity, int expect, int dgks_check,
+                                                           int* __restrict__ abort_flag) {
     extern __shared__ __align__(16) double chol_sm[];
     double* A = chol_sm;                 // [QF_W][QF_P]
     double* X = chol_sm + QF_W * QF_P;   // [QF_W][QF_P]
@@ -281,6 +284,13 @@ __global__ void __launch_bounds__(CH_NT) chol_panel_kernel(const double* __restr
         }
     }
     __syncthreads();
+    // expect >= 0: the host replays a recorded plan without reading the status back (0 = the panel is
+    // factored, 1 = the panel is deflated); any outcome that contradicts the plan raises the abort
+    // flag and the host redoes the whole orthogonalisation synchronously.
+    if (expect >= 0 && (flag_sh != 0) != (expect == 1)) {
+        if (tid == 0) *abort_flag = 1;
+        return;
+    }
     if (flag_sh) {  // numerically dependent panel: nothing to factor
         if (tid == 0) {
             status[0] = 0.0;
@@ -376,6 +386,7 @@ __global__ void __launch_bounds__(CH_NT) chol_panel_kernel(const double* __restr
             status[0] = 0.0;
             status[1] = 0.0;
             status[2] = 1.0;
+            if (expect >= 0) *abort_flag = 1;
         }
         return;
     }
@@ -445,6 +456,9 @@ __global__ void __launch_bounds__(CH_NT) chol_panel_kernel(const double* __restr
             status[0] = r0;
             status[1] = r1;
             status[2] = 0.0;
+            // replay: an ill-conditioned panel (the host would hand it to the Householder path) or a
+            // last planned pass that still fails the DGKS test contradicts the plan
+            if (expect >= 0 && (!(r1 >= 0.05) || (dgks_check && !(r0 >= 0.3)))) *abort_flag = 1;
         }
     }
 }
@@ -470,18 +484,47 @@ __global__ void __launch_bounds__(256) accumulate_r_kernel(double* __restrict__ 
                                                            const double* __restrict__ Rp,
                                                            const double* __restrict__ Rd_old,
                                                            double* __restrict__ Rd_new, int diag) {
-    __shared__ double rd[QF_W * QF_W];
+    __shared__ __align__(16) double rd[QF_W * QF_W];
     __shared__ double cs[QF_W][17];
     const int tid = threadIdx.x;
-    for (int i = tid; i < w * w; i += blockDim.x) rd[i] = Rd_old[i];
+    {
+        // all loads of the w x w factor in flight at once (16-byte vectors, fixed trip count): a
+        // strided scalar loop here costs one DRAM latency per iteration
+        const int n2 = (w * w) >> 1;
+        const double2* src = reinterpret_cast<const double2*>(Rd_old);
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = tid + u * 256;
+            v[u] = (idx < n2) ? src[idx] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = tid + u * 256;
+            if (idx < n2) reinterpret_cast<double2*>(rd)[idx] = v[u];
+        }
+        if ((w * w) & 1) {
+            if (tid == 0) rd[w * w - 1] = Rd_old[w * w - 1];
+        }
+    }
     const int64_t nblk = (jq + 15) / 16;
     if (int64_t(blockIdx.x) < nblk) {
         // 16 earlier rows per block: R[i][jc + t] += sum_u C[u][i] Rd_old[u][t]
         if (!C) return;
         const int64_t i0 = int64_t(blockIdx.x) * 16;
-        for (int idx = tid; idx < w * 16; idx += blockDim.x) {
-            const int u = idx >> 4, ii = idx & 15;
-            cs[u][ii] = (i0 + ii < jq) ? C[u * ldcc + i0 + ii] : 0.0;
+        {
+            double cv[4];
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) {
+                const int idx = tid + u4 * 256;
+                const int u = idx >> 4, ii = idx & 15;
+                cv[u4] = (idx < w * 16 && i0 + ii < jq) ? C[u * ldcc + i0 + ii] : 0.0;
+            }
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) {
+                const int idx = tid + u4 * 256;
+                if (idx < w * 16) cs[idx >> 4][idx & 15] = cv[u4];
+            }
         }
         __syncthreads();
         for (int idx = tid; idx < 16 * w; idx += blockDim.x) {
@@ -582,7 +625,8 @@ __global__ void dgks_kernel(const double* __restrict__ Rp, int w, const double* 
 // out[0] = max_v after[v] / before[v] (0 / 0 counts as 0): what a projection left of a set of rows
 __global__ void __launch_bounds__(256) ratio_max_kernel(const double* __restrict__ after,
                                                         const double* __restrict__ before, int n,
-                                                        double* __restrict__ out) {
+                                                        double* __restrict__ out, double tol, int expect,
+                                                        int* __restrict__ abort_flag) {
     __shared__ double red[8];
     double r = 0.0;
     for (int v = threadIdx.x; v < n; v += blockDim.x) {
@@ -596,6 +640,7 @@ __global__ void __launch_bounds__(256) ratio_max_kernel(const double* __restrict
         double t = 0.0;
         for (int i = 0; i < 8; ++i) t = fmax(t, red[i]);
         out[0] = t;
+        if (expect >= 0 && (t <= tol) != (expect == 1)) *abort_flag = 1;  // replayed plan contradicted
     }
 }
 
@@ -620,8 +665,10 @@ __global__ void zero_rows_kernel(double* X, int64_t rows, int64_t cols, int64_t 
 // gemm_ws is a recommendation (split-K partials); gemm() degrades gracefully with less,
 // so only `required()` is enforced.
 struct OrthLayout {
-    size_t cbuf, rp, rd, nrm, tsqr, gemm_ws, bulk, bulk_nrm;
-    size_t required() const { return (cbuf + rp + 2 * rd + 2 * nrm + tsqr + bulk + 2 * bulk_nrm) * 8 + 14 * 256; }
+    size_t cbuf, rp, rd, nrm, tsqr, gemm_ws, bulk, bulk_nrm, backup;
+    size_t required() const {
+        return (cbuf + rp + 2 * rd + 2 * nrm + tsqr + bulk + 2 * bulk_nrm + backup) * 8 + 16 * 256;
+    }
     size_t total() const { return required() + round_up<size_t>(gemm_ws, 256); }
 };
 
@@ -634,6 +681,8 @@ OrthLayout orth_layout(int64_t c, int64_t m) {
     L.tsqr = tsqr_scratch_doubles(m);
     L.bulk = std::min<size_t>(size_t(c) * size_t(c), size_t(4) << 20);  // bulk deflation coefficients (rest x jq)
     L.bulk_nrm = size_t(c) + 32;
+    // copy of the input for the speculative (sync-free) replay of a recorded plan; none for very large inputs
+    L.backup = (size_t(c) * size_t(m) <= (size_t(32) << 20)) ? size_t(c) * size_t(m) : 0;
     L.gemm_ws = std::min<size_t>(std::max(gemm_workspace_bytes(QF_W, c, m), gemm_workspace_bytes(c, c, m)),
                                  size_t(64) << 20);
     return L;
@@ -672,10 +721,10 @@ double debug_chol_bench_us(int w, int reps) {
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     for (int i = 0; i < 3; ++i)
-        chol_panel_kernel<<<1, CH_NT, kCholSmem>>>(G, w, nullptr, out, out + QF_W * QF_W, out + 2 * QF_W * QF_W, 0.0, 0);
+        chol_panel_kernel<<<1, CH_NT, kCholSmem>>>(G, w, nullptr, out, out + QF_W * QF_W, out + 2 * QF_W * QF_W, 0.0, 0, -1, 0, nullptr);
     cudaEventRecord(e0);
     for (int i = 0; i < reps; ++i)
-        chol_panel_kernel<<<1, CH_NT, kCholSmem>>>(G, w, nullptr, out, out + QF_W * QF_W, out + 2 * QF_W * QF_W, 0.0, 0);
+        chol_panel_kernel<<<1, CH_NT, kCholSmem>>>(G, w, nullptr, out, out + QF_W * QF_W, out + 2 * QF_W * QF_W, 0.0, 0, -1, 0, nullptr);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms = 0.f;
@@ -694,8 +743,27 @@ size_t orth_rows_workspace_bytes(int64_t c, int64_t m) {
     return orth_layout(c, m).total();
 }
 
-int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t ldr, void* ws,
-              size_t ws_bytes, cudaStream_t stream, double deflate_tol, int64_t* rank_out) {
+namespace {
+// Outcome of the data-dependent decisions of one orth_rows call, in the order they are taken.
+// Recorded by a synchronous run (every decision is read back from the device) and replayed by later
+// calls with the same shape WITHOUT host synchronisation: the kernels validate each speculated
+// outcome on the device and raise an abort flag if the data disagrees, in which case the call is
+// redone synchronously from a copy of its input.  In a rounding sweep all interior cores share one
+// shape and one pattern, so the replay almost always holds.
+struct OrthDecision {
+    int kind;     // 1 = panel factored, 2 = panel deflated, 3 = bulk deflation test
+    int value;    // kind 1: projection passes used; kind 3: 1 = every remaining row was dependent
+};
+struct OrthPlan {
+    std::vector<OrthDecision> seq;
+    bool valid = false;
+};
+constexpr int kSpecFailed = 1000;  // internal status: the replayed plan was contradicted by the data
+}  // namespace
+
+static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t ldr, void* ws,
+                          size_t ws_bytes, cudaStream_t stream, double deflate_tol, int64_t* rank_out,
+                          OrthPlan* plan, bool replay) {
     TTB_REQUIRE(M && R, "orth_rows: null pointer");
     TTB_REQUIRE(c >= 1 && m >= 1 && ldm >= m && ldr >= c, "orth_rows: bad extents");
     const OrthLayout L = orth_layout(c, m);
@@ -716,8 +784,17 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
     double* tsq = W.take<double>(L.tsqr);
     double* Cbulk = W.take<double>(L.bulk);
     double* bnrm[2] = {W.take<double>(L.bulk_nrm), W.take<double>(L.bulk_nrm)};
+    double* backup = W.take<double>(L.backup);
+    (void)backup;  // owned by the caller (orth_rows), carved here only to keep the layout in one place
     TTB_REQUIRE(Cb && Rp && Rd[0] && Rd[1] && nrm[0] && nrm[1] && flag && tsq && Cbulk && bnrm[0] && bnrm[1],
                 "orth_rows: workspace carve failed");
+    int* abort_flag = reinterpret_cast<int*>(flag + 4);
+    size_t plan_pos = 0;
+    if (replay) TTB_CHECK_CUDA(cudaMemsetAsync(abort_flag, 0, sizeof(int), stream));
+    if (plan && !replay) {
+        plan->seq.clear();
+        plan->valid = true;
+    }
     void* gws = W.base + W.off;
     const size_t gws_bytes = ws_bytes - W.off;
 
@@ -758,7 +835,15 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
             rownorm_kernel<<<w, 256, 0, stream>>>(P, m, ldm, nullptr, nrm[0], nullptr);
             ++g_launch_count;
         }
+        // replay: the outcome of this panel comes from the plan, nothing is read back
+        OrthDecision planned{1, 1};
+        if (replay) {
+            if (plan_pos >= plan->seq.size() || plan->seq[plan_pos].kind == 3) return -3;  // structure mismatch
+            planned = plan->seq[plan_pos++];
+        }
+        int passes_used = 0;
         for (int pass = 1; pass <= kMaxPasses; ++pass) {
+            passes_used = pass;
             if (jq > 0) {
                 GemmArgs g;  // C (w x jq) = P . Qp^T
                 g.M = w; g.N = jq; g.K = m;
@@ -774,6 +859,7 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                 u.alpha = -1.0; u.beta = 1.0;
                 { ProfScope ps_("qr.gemm_proj_update", stream); if (gemm(u, gws, gws_bytes, stream) != kOk) return -1; }
             }
+            const bool last_planned = replay && (jq == 0 || pass >= planned.value || planned.kind == 2);
             for (int rep = 0; rep < 2; ++rep) {  // Cholesky-QR twice
                 GemmArgs gg;  // G = P P^T
                 gg.M = w; gg.N = w; gg.K = m;
@@ -782,32 +868,43 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                 gg.C = Gm; gg.ldc = w;
                 { ProfScope ps_("qr.gemm_gram", stream); if (gemm(gg, gws, gws_bytes, stream) != kOk) return -1; }
                 const bool first = rep == 0;
+                const bool defl_test = first && pass == 1 && jq > 0;
+                int expect = -1;
+                if (replay && first) expect = (defl_test && deflate_tol > 0.0 && planned.kind == 2) ? 1 : 0;
                 { ProfScope ps_(first ? "qr.chol_panel" : "qr.chol_panel2", stream);
-                chol_panel_kernel<<<1, CH_NT, kCholSmem, stream>>>(Gm, w, (first && pass == 1 && jq > 0) ? nrm[0] : nullptr, Rp,
-                                                         Linv, first ? status : status + 8,
-                                                         (first && pass == 1 && jq > 0) ? deflate_tol : 0.0, first ? 0 : 1); }
+                chol_panel_kernel<<<1, CH_NT, kCholSmem, stream>>>(Gm, w, defl_test ? nrm[0] : nullptr, Rp, Linv,
+                                                         first ? status : status + 8, defl_test ? deflate_tol : 0.0,
+                                                         first ? 0 : 1, expect,
+                                                         (replay && first && jq > 0 && last_planned) ? 1 : 0, abort_flag); }
                 ++g_launch_count;
                 if (first) {
-                    if (cudaMemcpyAsync(host.status, status, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream) !=
-                            cudaSuccess ||
-                        cudaStreamSynchronize(stream) != cudaSuccess)
-                        return -1;
+                    bool deflated, declined = false;
+                    if (replay) {
+                        deflated = defl_test && deflate_tol > 0.0 && planned.kind == 2;
+                    } else {
+                        if (cudaMemcpyAsync(host.status, status, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream) !=
+                                cudaSuccess ||
+                            cudaStreamSynchronize(stream) != cudaSuccess)
+                            return -1;
+                        if (debug && pass == 1 && jq > 0)
+                            fprintf(stderr, "[orth_rows] panel jc=%lld jq=%lld w=%d residual ratio %.2e dgks %.2e cond %.2e\n",
+                                    (long long)jc, (long long)jq, w, host.status[3], host.status[0], host.status[1]);
+                        deflated = defl_test && deflate_tol > 0.0 && host.status[3] <= deflate_tol;
+                        declined = !deflated && (host.status[2] != 0.0 || !(host.status[1] >= 0.05));
+                    }
                     const int blocks = int((jq + 15) / 16 + 1);
-                    if (debug && pass == 1 && jq > 0)
-                        fprintf(stderr, "[orth_rows] panel jc=%lld jq=%lld w=%d residual ratio %.2e dgks %.2e cond %.2e\n",
-                                (long long)jc, (long long)jq, w, host.status[3], host.status[0], host.status[1]);
-                    if (pass == 1 && jq > 0 && deflate_tol > 0.0 && host.status[3] <= deflate_tol) {
-                        if (debug) fprintf(stderr, "[orth_rows] deflate panel jc=%lld w=%d (residual ratio %.2e)\n",
-                                           (long long)jc, w, host.status[3]);
+                    if (deflated) {
+                        if (debug && !replay)
+                            fprintf(stderr, "[orth_rows] deflate panel jc=%lld w=%d (residual ratio %.2e)\n", (long long)jc, w,
+                                    host.status[3]);
                         { ProfScope ps_("qr.accumulate_r", stream);
                         accumulate_r_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jq, jc, w, Cb, jq, nullptr, Rd[cur],
                                                                         Rd[cur ^ 1], 0); }
                         ++g_launch_count;
+                        if (plan && !replay) plan->seq.push_back({2, 1});
                         return 2;
                     }
-                    const bool broke = host.status[2] != 0.0;
-                    const bool ill = !(host.status[1] >= 0.05);
-                    if (broke || ill) {
+                    if (declined) {
                         if (pass > 1) return -2;  // cannot happen for near-orthonormal rows; refuse loudly
                         if (jq > 0) {  // keep the projection that was already applied to P
                             { ProfScope ps_("qr.accumulate_r", stream);
@@ -815,6 +912,7 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                                                                             Rd[cur ^ 1], 0); }
                             ++g_launch_count;
                         }
+                        if (plan) plan->valid = false;  // Householder panels are never replayed
                         return 0;
                     }
                 }
@@ -835,8 +933,13 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
             }
             if (cudaGetLastError() != cudaSuccess) return -1;
             if (jq == 0) break;
-            if (host.status[0] >= kDgks) break;  // DGKS: this pass removed < 70 % of every vector
+            if (replay) {
+                if (pass >= planned.value) break;
+            } else if (host.status[0] >= kDgks) {
+                break;  // DGKS: this pass removed < 70 % of every vector
+            }
         }
+        if (plan && !replay) plan->seq.push_back({1, passes_used});
         return 1;
     };
 
@@ -855,6 +958,7 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
             const int wf = int(std::min<int64_t>(QF_W, room));
             TTB_PROPAGATE(stage_panel(wf));
             const int fs = fast_panel(wf);
+            if (fs == -3) return kSpecFailed;
             if (fs < 0) {
                 set_last_error("orth_rows: Cholesky-QR panel failed (status " + std::to_string(fs) + ")");
                 return fs == -2 ? kNotConverged : kCudaError;
@@ -892,16 +996,29 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                         TTB_PROPAGATE(gemm(u, gws, gws_bytes, stream));
                     }
                     rownorm_kernel<<<unsigned(rest_rows), 256, 0, stream>>>(Arest, m, ldm, nullptr, bnrm[1], nullptr);
-                    ratio_max_kernel<<<1, 256, 0, stream>>>(bnrm[1], bnrm[0], int(rest_rows), status + 16);
+                    int expect_bulk = -1;
+                    if (replay) {
+                        if (plan_pos >= plan->seq.size() || plan->seq[plan_pos].kind != 3) return kSpecFailed;
+                        expect_bulk = plan->seq[plan_pos++].value;
+                    }
+                    ratio_max_kernel<<<1, 256, 0, stream>>>(bnrm[1], bnrm[0], int(rest_rows), status + 16, deflate_tol,
+                                                            expect_bulk, abort_flag);
                     const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(rest_rows * jq, 256), 2048));
                     add_transposed_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jc, Cbulk, rest_rows, jq);
                     g_launch_count += 3;
-                    TTB_CHECK_CUDA(cudaMemcpyAsync(host.status, status + 16, sizeof(double), cudaMemcpyDeviceToHost, stream));
-                    TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
-                    if (debug)
-                        fprintf(stderr, "[orth_rows] bulk deflation test of %lld rows: residual ratio %.2e\n",
-                                (long long)rest_rows, host.status[0]);
-                    if (host.status[0] <= deflate_tol) jc = c;  // every remaining row is dependent
+                    bool all_dependent;
+                    if (replay) {
+                        all_dependent = expect_bulk == 1;
+                    } else {
+                        TTB_CHECK_CUDA(cudaMemcpyAsync(host.status, status + 16, sizeof(double), cudaMemcpyDeviceToHost, stream));
+                        TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
+                        if (debug)
+                            fprintf(stderr, "[orth_rows] bulk deflation test of %lld rows: residual ratio %.2e\n",
+                                    (long long)rest_rows, host.status[0]);
+                        all_dependent = host.status[0] <= deflate_tol;
+                        if (plan) plan->seq.push_back({3, all_dependent ? 1 : 0});
+                    }
+                    if (all_dependent) jc = c;  // every remaining row is dependent
                 }
                 continue;
             }
@@ -911,6 +1028,8 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
                 TTB_CHECK_CUDA(cudaMemcpy2DAsync(M + jc * ldm, size_t(ldm) * 8, M + jq * ldm, size_t(ldm) * 8,
                                                  size_t(m) * 8, size_t(wf), cudaMemcpyDeviceToDevice, stream));
         }
+        if (replay) return kSpecFailed;  // Householder panels are never replayed
+        if (plan) plan->valid = false;
         const int w = int(std::min<int64_t>(QR_W, room));
         if (!(fast_enabled && m >= 2 * QF_W)) TTB_PROPAGATE(stage_panel(w));  // else already staged (wf >= w)
         double* P = M + jq * ldm;
@@ -978,7 +1097,50 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
         TTB_CHECK_CUDA(cudaGetLastError());
     }
     if (rank_out) *rank_out = jq;
+    if (replay) {
+        if (plan_pos != plan->seq.size()) return kSpecFailed;
+        TTB_CHECK_CUDA(cudaMemcpyAsync(host.flag, abort_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
+        int aborted;
+        memcpy(&aborted, host.flag, sizeof(int));
+        if (aborted) return kSpecFailed;
+    }
     return kOk;
+}
+
+int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t ldr, void* ws,
+              size_t ws_bytes, cudaStream_t stream, double deflate_tol, int64_t* rank_out) {
+    TTB_REQUIRE(M && R, "orth_rows: null pointer");
+    TTB_REQUIRE(c >= 1 && m >= 1 && ldm >= m && ldr >= c, "orth_rows: bad extents");
+    static const bool spec_enabled = [] {
+        const char* e = getenv("TTB_QR_SPEC");
+        return e == nullptr || e[0] != '0';
+    }();
+    static const bool debug = getenv("TTB_DEBUG") != nullptr;
+    static std::map<std::tuple<int64_t, int64_t, bool>, OrthPlan> plans;
+    OrthPlan& plan = plans[std::make_tuple(c, m, deflate_tol > 0.0)];
+    const OrthLayout L = orth_layout(c, m);
+    if (debug)
+        fprintf(stderr, "[orth_rows] c=%lld m=%lld plan valid=%d steps=%zu backup=%zu ws ok=%d\n", (long long)c, (long long)m,
+                int(plan.valid), plan.seq.size(), L.backup, int(ws != nullptr && ws_bytes >= L.required()));
+    if (spec_enabled && plan.valid && L.backup > 0 && ws != nullptr && ws_bytes >= L.required()) {
+        // the backup slot is the last carve of the layout (see orth_rows_impl)
+        Workspace W(ws, ws_bytes);
+        W.take<double>(L.cbuf); W.take<double>(L.rp); W.take<double>(L.rd); W.take<double>(L.rd);
+        W.take<double>(L.nrm); W.take<double>(L.nrm); W.take<unsigned long long>(8); W.take<double>(L.tsqr);
+        W.take<double>(L.bulk); W.take<double>(L.bulk_nrm); W.take<double>(L.bulk_nrm);
+        double* backup = W.take<double>(L.backup);
+        TTB_REQUIRE(backup != nullptr, "orth_rows: backup carve failed");
+        TTB_CHECK_CUDA(cudaMemcpy2DAsync(backup, size_t(m) * 8, M, size_t(ldm) * 8, size_t(m) * 8, size_t(c),
+                                         cudaMemcpyDeviceToDevice, stream));
+        const int rc = orth_rows_impl(M, c, m, ldm, R, ldr, ws, ws_bytes, stream, deflate_tol, rank_out, &plan, true);
+        if (rc != kSpecFailed) return rc;
+        if (debug) fprintf(stderr, "[orth_rows] replayed plan contradicted (c=%lld m=%lld): synchronous redo\n",
+                           (long long)c, (long long)m);
+        TTB_CHECK_CUDA(cudaMemcpy2DAsync(M, size_t(ldm) * 8, backup, size_t(m) * 8, size_t(m) * 8, size_t(c),
+                                         cudaMemcpyDeviceToDevice, stream));
+    }
+    return orth_rows_impl(M, c, m, ldm, R, ldr, ws, ws_bytes, stream, deflate_tol, rank_out, &plan, false);
 }
 
 }  // namespace ttb
