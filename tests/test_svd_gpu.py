@@ -128,3 +128,27 @@ def test_round_partial_deflation():
     err = np.linalg.norm(tt.dense() - dense) / np.linalg.norm(dense)
     err_ref = np.linalg.norm(orc.to_dense(ref) - dense) / np.linalg.norm(dense)
     assert abs(err - err_ref) <= 1e-10
+
+
+def test_round_plan_replay_contradiction():
+    """orth_rows replays the decisions recorded for the previous call of the same shape; data that
+    contradicts the plan must trigger the synchronous redo and still give the reference result.
+    Alternate between inputs WITH exact rank deficiency (panels deflate) and WITHOUT (nothing
+    deflates) on identical shapes, several times."""
+    from tensor_networks_b200 import TensorTrain
+
+    rng = np.random.default_rng(21)
+    shape = [16] * 5
+    x = orc.rand_tt(shape, [72] * 4, rng)
+    doubled = orc.tt_add(x, x)                      # bonds 144, true ranks 72 (first/last 16)
+    generic = orc.rand_tt(shape, [144] * 4, rng)    # same shapes, full rank
+    for trial in range(3):
+        for y in (doubled, generic):
+            ref, _ = orc.svd_round(copy.deepcopy(y), 1e-9)
+            tt = TensorTrain.from_cores(copy.deepcopy(y)).round(1e-9)
+            assert tt.ranks() == orc.ranks_of(ref), (trial, tt.ranks(), orc.ranks_of(ref))
+            ny = np.sqrt(orc.inner(y, y))
+            z = TensorTrain.from_cores(copy.deepcopy(y))
+            nz = tt.norm()
+            assert abs(nz - ny) <= 1e-9 * ny
+            assert abs(float(tt.inner(z)) / (ny * nz) - 1.0) < 1e-12
