@@ -42,6 +42,12 @@ namespace {
 using namespace hh;
 
 constexpr int QF_W = 64;  // width of a fast (Cholesky-QR) panel
+// A panel is "benign" for Cholesky-QR2 when every vector keeps at least this fraction of its norm
+// against the earlier vectors of the panel (cond(panel) <~ sqrt(w) / kIllMin).  Deliberately strict:
+// with 5e-3 the factorisation itself is still fine, but the basis of a cond ~ 1e3 panel is only
+// accurate to eps cond^2, and the residuals of truly dependent later rows rise from 1e-14 to 1e-13 --
+// enough to defeat the deflation test (measured on the TT-SVD 16^7 case: 75 -> 113 ms).
+constexpr double kIllMin = 0.05;
 constexpr int QF_P = QF_W + 1;
 
 struct TsqrLevelParams {
@@ -258,14 +264,24 @@ __global__ void __launch_bounds__(CH_NT) chol_panel_kernel(const double* __restr
     extern __shared__ __align__(16) double chol_sm[];
     double* A = chol_sm;                 // [QF_W][QF_P]
     double* X = chol_sm + QF_W * QF_P;   // [QF_W][QF_P]
-    __shared__ double diag0[QF_W], rdiag[QF_W], vsh[2][QF_W], emax_sh[CH_NT / 32];
+    __shared__ double diag0[QF_W], rdiag[QF_W], emax_sh[CH_NT / 32];
     __shared__ int flag_sh;
     const int tid = threadIdx.x;
     const long long tk0 = clock64();
-    for (int idx = tid; idx < QF_W * QF_W; idx += CH_NT) {
-        const int r = idx / QF_W, c = idx % QF_W;
-        A[r * QF_P + c] = (r < w && c < w) ? G[r * w + c] : (r == c ? 1.0 : 0.0);  // identity padding
-        X[r * QF_P + c] = 0.0;
+    {
+        // all 16 loads of a thread in flight at once (a strided loop pays one DRAM latency per trip)
+        double g[QF_W * QF_W / CH_NT];
+#pragma unroll
+        for (int u = 0; u < QF_W * QF_W / CH_NT; ++u) {
+            const int idx = tid + u * CH_NT;
+            const int r = idx / QF_W, c = idx % QF_W;
+            g[u] = (r < w && c < w) ? G[r * w + c] : (r == c ? 1.0 : 0.0);  // identity padding
+        }
+#pragma unroll
+        for (int u = 0; u < QF_W * QF_W / CH_NT; ++u) {
+            const int idx = tid + u * CH_NT;
+            A[(idx / QF_W) * QF_P + idx % QF_W] = g[u];
+        }
     }
     __syncthreads();
     if (tid < QF_W) diag0[tid] = A[tid * QF_P + tid];
@@ -327,59 +343,49 @@ __global__ void __launch_bounds__(CH_NT) chol_panel_kernel(const double* __restr
     }
     bool bad = false;
     const long long tk1 = clock64();
-    {
-        // four lanes per row: lane `part` sums the terms k = part (mod 4); every load of a batch is
-        // issued before the first FMA needs it (a single warp per scheduler has nobody else to hide
-        // the ~30-cycle shared-memory latency behind)
-        const int i = tid >> 2, part = tid & 3;
-        const double* li = A + i * QF_P;
-        double lprev_i = 0.0;           // L[i][j-1], still in a register
-        double rs_prev = 0.0;
-        for (int j = 0; j < QF_W; ++j) {
-            double v = 0.0;
-            if (i >= j) {
-                const double* lj = A + j * QF_P;
-                double s0 = 0.0, s1 = 0.0;
-                int k = part;
-                for (; k + 12 < j - 1; k += 16) {  // columns 0 .. j-2 are in shared memory
-                    const double a0 = li[k], a1 = li[k + 4], a2 = li[k + 8], a3 = li[k + 12];
-                    const double b0 = lj[k], b1 = lj[k + 4], b2 = lj[k + 8], b3 = lj[k + 12];
-                    s0 = fma(a0, b0, s0);
-                    s1 = fma(a1, b1, s1);
-                    s0 = fma(a2, b2, s0);
-                    s1 = fma(a3, b3, s1);
-                }
-                {
-                    const double a0 = (k < j - 1) ? li[k] : 0.0, a1 = (k + 4 < j - 1) ? li[k + 4] : 0.0;
-                    const double a2 = (k + 8 < j - 1) ? li[k + 8] : 0.0;
-                    const double b0 = (k < j - 1) ? lj[k] : 0.0, b1 = (k + 4 < j - 1) ? lj[k + 4] : 0.0;
-                    const double b2 = (k + 8 < j - 1) ? lj[k + 8] : 0.0;
-                    s0 = fma(a0, b0, s0);
-                    s1 = fma(a1, b1, s1);
-                    s0 = fma(a2, b2, s0);
-                }
-                if (j > 0 && part == 0) s1 = fma(lprev_i, vsh[(j - 1) & 1][j] * rs_prev, s1);  // column j-1 from registers
-                v = s0 + s1;
-            }
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            if (i >= j) {
-                v = li[j] - v;
-                if (part == 0) vsh[j & 1][i] = v;
+    // ---- register-resident right-looking factorisation: thread (ty, tx) of a 16 x 16 grid owns the
+    // 4 x 4 elements A[ty + 16 ii][tx + 16 kk].  Per column: the owners broadcast the (un-scaled)
+    // column through a double-buffered shared vector, ONE barrier, then every thread updates its own
+    // registers with a rank-1 term -- 8 shared loads and <= 16 FMAs, no shared-memory read-modify-write.
+    // The column loop is split (jq static, jj dynamic) so that every register index is static.
+    const int ty = tid >> 4, tx = tid & 15;
+    double a[4][4];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) a[ii][kk] = A[(ty + 16 * ii) * QF_P + tx + 16 * kk];
+    __shared__ double colb[2][QF_W], rowb[2][QF_W], dsave[QF_W];
+#pragma unroll
+    for (int jq = 0; jq < 4; ++jq) {
+        for (int jj = 0; jj < 16; ++jj) {
+            const int j = 16 * jq + jj;
+            double* cb = colb[j & 1];
+            if (tx == jj) {
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) cb[ty + 16 * ii] = a[ii][jq];
             }
             __syncthreads();
-            const double d = vsh[j & 1][j];
+            const double d = cb[j];
             if (!(d > 0.0) || !(d < 1e300)) {  // uniform: every thread reads the same word
                 bad = true;
                 break;
             }
-            const double rs = fast_rsqrt3(d);
-            if (i >= j) {
-                lprev_i = (i == j) ? d * rs : v * rs;
-                if (part == (j & 3)) A[i * QF_P + j] = lprev_i;  // the lane that reads it back as a term
+            if (tid == 0) dsave[j] = d;
+            const double invd = 1.0 / d;
+            double ci[4], ck[4];
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) ci[ii] = cb[ty + 16 * ii] * invd;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) ck[kk] = cb[tx + 16 * kk];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                if (kk < jq) continue;               // columns already final (static)
+                if (kk == jq && tx <= jj) continue;  // column j itself and the finished ones of this group
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) a[ii][kk] = fma(-ci[ii], ck[kk], a[ii][kk]);
             }
-            rs_prev = rs;
         }
+        if (bad) break;
     }
     if (bad) {
         if (tid == 0) {
@@ -391,41 +397,68 @@ __global__ void __launch_bounds__(CH_NT) chol_panel_kernel(const double* __restr
         return;
     }
     __syncthreads();
-    const long long tk2 = clock64();
-    if (tid < QF_W) rdiag[tid] = 1.0 / A[tid * QF_P + tid];
-    __syncthreads();
-    {
-        // X = L^{-1}: X[i][c] = ((i == c) - sum_{k=c}^{i-1} L[i][k] X[k][c]) / L[i][i]; column c on the four
-        // lanes (c, part); lane `part` owns the terms k = part (mod 4) and is the one that stored them
-        const int c = tid >> 2, part = tid & 3;
-        const unsigned gmask = 0xFu << (tid & 28);
-        for (int i = c; i < QF_W; ++i) {
-            const double* li = A + i * QF_P;
-            double s0 = 0.0, s1 = 0.0;
-            int k = c + ((part - c) & 3);
-            for (; k + 12 < i; k += 16) {
-                const double a0 = li[k], a1 = li[k + 4], a2 = li[k + 8], a3 = li[k + 12];
-                const double b0 = X[k * QF_P + c], b1 = X[(k + 4) * QF_P + c], b2 = X[(k + 8) * QF_P + c],
-                             b3 = X[(k + 12) * QF_P + c];
-                s0 = fma(a0, b0, s0);
-                s1 = fma(a1, b1, s1);
-                s0 = fma(a2, b2, s0);
-                s1 = fma(a3, b3, s1);
-            }
-            {
-                const double a0 = (k < i) ? li[k] : 0.0, a1 = (k + 4 < i) ? li[k + 4] : 0.0, a2 = (k + 8 < i) ? li[k + 8] : 0.0;
-                const double b0 = (k < i) ? X[k * QF_P + c] : 0.0, b1 = (k + 4 < i) ? X[(k + 4) * QF_P + c] : 0.0;
-                const double b2 = (k + 8 < i) ? X[(k + 8) * QF_P + c] : 0.0;
-                s0 = fma(a0, b0, s0);
-                s1 = fma(a1, b1, s1);
-                s0 = fma(a2, b2, s0);
-            }
-            double sum = s0 + s1;
-            sum += __shfl_xor_sync(gmask, sum, 1);  // the four lanes of a column share the trip count, the warp does not
-            sum += __shfl_xor_sync(gmask, sum, 2);
-            if (part == (i & 3)) X[i * QF_P + c] = (((i == c) ? 1.0 : 0.0) - sum) * rdiag[i];
+    // deferred scaling: L_ik = A_ik / sqrt(d_k); only the lower triangle is meaningful
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        const int k = tx + 16 * kk;
+        const double rs = rsqrt(dsave[k]);
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            const int i = ty + 16 * ii;
+            a[ii][kk] = (i >= k) ? a[ii][kk] * rs : 0.0;
         }
     }
+    if (tid < QF_W) rdiag[tid] = rsqrt(dsave[tid]);  // 1 / L_kk
+    const long long tk2 = clock64();
+    // ---- X = L^{-1} the same way: row k of X becomes final when divided by L_kk, then the rank-1 term
+    // L[:, k] X[k, :] leaves the rows below ----
+    double x[4][4];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) x[ii][cc] = (ty + 16 * ii == tx + 16 * cc) ? 1.0 : 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int kq = 0; kq < 4; ++kq) {
+        for (int kr = 0; kr < 16; ++kr) {
+            const int k = 16 * kq + kr;
+            double* cb = colb[k & 1];
+            double* rb = rowb[k & 1];
+            if (ty == kr) {  // owners of row k of X: scale and publish
+                const double rk = rdiag[k];
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    x[kq][cc] *= rk;
+                    rb[tx + 16 * cc] = x[kq][cc];
+                }
+            }
+            if (tx == kr) {  // owners of column k of L
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) cb[ty + 16 * ii] = a[ii][kq];
+            }
+            __syncthreads();
+            double li[4], xr[4];
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) li[ii] = cb[ty + 16 * ii];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) xr[cc] = rb[tx + 16 * cc];
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+                if (ii < kq) continue;               // rows above k (static)
+                if (ii == kq && ty <= kr) continue;  // row k itself and the rows above it in this group
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) x[ii][cc] = fma(-li[ii], xr[cc], x[ii][cc]);
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            A[(ty + 16 * ii) * QF_P + tx + 16 * kk] = a[ii][kk];
+            X[(ty + 16 * ii) * QF_P + tx + 16 * kk] = x[ii][kk];
+        }
     __syncthreads();
     const long long tk3 = clock64();
     for (int idx = tid; idx < w * w; idx += CH_NT) {
@@ -458,7 +491,7 @@ __global__ void __launch_bounds__(CH_NT) chol_panel_kernel(const double* __restr
             status[2] = 0.0;
             // replay: an ill-conditioned panel (the host would hand it to the Householder path) or a
             // last planned pass that still fails the DGKS test contradicts the plan
-            if (expect >= 0 && (!(r1 >= 0.05) || (dgks_check && !(r0 >= 0.3)))) *abort_flag = 1;
+            if (expect >= 0 && (!(r1 >= kIllMin) || (dgks_check && !(r0 >= 0.3)))) *abort_flag = 1;
         }
     }
 }
@@ -890,7 +923,7 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
                             fprintf(stderr, "[orth_rows] panel jc=%lld jq=%lld w=%d residual ratio %.2e dgks %.2e cond %.2e\n",
                                     (long long)jc, (long long)jq, w, host.status[3], host.status[0], host.status[1]);
                         deflated = defl_test && deflate_tol > 0.0 && host.status[3] <= deflate_tol;
-                        declined = !deflated && (host.status[2] != 0.0 || !(host.status[1] >= 0.05));
+                        declined = !deflated && (host.status[2] != 0.0 || !(host.status[1] >= kIllMin));
                     }
                     const int blocks = int((jq + 15) / 16 + 1);
                     if (deflated) {
