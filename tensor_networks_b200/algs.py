@@ -32,10 +32,12 @@ import numpy as np
 from .types import Index, IntOrStr, NodeName, SVDConfig  # noqa: F401
 from .utils import TruncSVD, delta_svd  # noqa: F401
 from .tt import TensorTrain
+from .solvers import TTOperator, gmres, ttop_apply, ttop_rank1  # noqa: F401  (device-resident TT-GMRES)
 
 __all__ = [
     "Index", "SVDConfig", "Tensor", "TensorNetwork", "TensorTrain", "TruncSVD",
     "delta_svd", "tt_right_orth", "tt_svd_round", "tt_svd", "round",
+    "TTOperator", "ttop_rank1", "ttop_apply", "gmres",
 ]
 
 

@@ -22,6 +22,7 @@
 #include "batched.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "gemm.cuh"
@@ -45,6 +46,7 @@ struct InnerBatchParams {
     const double* A[kMaxD];
     const double* B[kMaxD];
     double* out;
+    long long* dbg;  // TTB_BINNER_TIMING: clock64 sums of CTA 0 {top wait, compute, tail, chunks}
 };
 
 // Shared-memory staging: a "chunk" is up to IB_CS mode slices of both cores,
@@ -167,9 +169,9 @@ __global__ void __launch_bounds__(IB_NT, 1) inner_batched_kernel(const __grid_co
 
     double acc[4][2];
     int t = 0;
+    long long tacc0 = 0, tacc1 = 0, tacc2 = 0, tchunks = 0, tprev = clock64();
+    const bool timing = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
     while (chunk_valid(p, cur)) {
-        if (chunk_valid(p, nxt)) chunk_issue(p, nxt, stages + ((t + 1) & 1) * IB_STAGE);
-        cp_async_commit();
         if (cur.k == 0 && cur.c == 0) {  // new item: E = [1]
             for (int idx = tid; idx < IB_R * IB_EP; idx += IB_NT) E[idx] = (idx == 0) ? 1.0 : 0.0;
         }
@@ -177,15 +179,54 @@ __global__ void __launch_bounds__(IB_NT, 1) inner_batched_kernel(const __grid_co
 #pragma unroll
             for (int l = 0; l < 4; ++l) acc[l][0] = acc[l][1] = 0.0;
         }
-        cp_async_wait<1>();
+        cp_async_wait<0>();
         __syncthreads();
+        if (timing) { const long long now = clock64(); tacc0 += now - tprev; tprev = now; }
 
         const int k = cur.k;
         const int a = p.ra[k], a2 = p.ra[k + 1], b = p.rb[k], b2 = p.rb[k + 1], n = p.n[k];
         const int mt = (b2 + 7) >> 3, nt = (a + 7) >> 3, kt = (b + 3) >> 2, lt = (a2 + 7) >> 3;
         const double* Bst = stages + (t & 1) * IB_STAGE + wj * IB_R * IB_BP;
         const double* Ast = stages + (t & 1) * IB_STAGE + IB_BST + wj * IB_R * IB_AP;
-        if (cur.c * IB_CS + wj < n && wi < mt) {
+        bool issued = false;
+        const bool full = (a == IB_R) && (a2 == IB_R) && (b == IB_R) && (b2 == IB_R);
+        if (full && cur.c * IB_CS + wj < n) {
+            // ---- all four ranks are 32: fixed trip counts, no bounds checks, operand addresses are
+            // immediates off two base pointers (the generic path below spends ~6 non-DMMA instructions
+            // per DMMA on loop tests and address arithmetic, which is what kept the pipe at 50 %) ----
+            const double* bsp = Bst + fq * IB_BP + 8 * wi + fr;      // af(kk)  = bsp[4 kk * IB_BP]
+            const double* ep = E + fr * IB_EP + fq;                   // b(kk,j) = ep[8 j * IB_EP + 4 kk]
+            double c[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j][0] = c[j][1] = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const double af = bsp[4 * kk * IB_BP];
+                double bf[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bf[j] = ep[8 * j * IB_EP + 4 * kk];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(c[j][0], c[j][1], af, bf[j]);
+            }
+            if (chunk_valid(p, nxt)) chunk_issue(p, nxt, stages + ((t + 1) & 1) * IB_STAGE);
+            cp_async_commit();
+            issued = true;
+            const double* asp = Ast + 2 * fq * IB_AP + fr;            // arow(j)[8 l] = asp[8 j * IB_AP + 8 l]
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double a0[4], a1[4];
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    a0[l] = asp[8 * j * IB_AP + 8 * l];
+                    a1[l] = asp[8 * j * IB_AP + IB_AP + 8 * l];
+                }
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    dmma884(acc[l][0], acc[l][1], c[j][0], a0[l]);
+                    dmma884(acc[l][0], acc[l][1], c[j][1], a1[l]);
+                }
+            }
+        } else if (cur.c * IB_CS + wj < n && wi < mt) {
             {
                 const int i = wi;
                 // ---- T^T tile row i: C(i, j) = B_s^T (b' x b) . E^T (b x a) ----
@@ -203,6 +244,13 @@ __global__ void __launch_bounds__(IB_NT, 1) inner_batched_kernel(const __grid_co
                         dmma884(c[j][0], c[j][1], af, E[(8 * j + fr) * IB_EP + bk]);
                     }
                 }
+                // The copies of the next chunk are issued HERE, between the two products: the warps of a
+                // scheduler reach this point one DMMA burst apart, so the address arithmetic of one warp
+                // hides behind the tensor work of the others (issued at the top of the iteration, all 16
+                // warps did it at once and the DMMA pipe sat idle meanwhile).
+                if (chunk_valid(p, nxt)) chunk_issue(p, nxt, stages + ((t + 1) & 1) * IB_STAGE);
+                cp_async_commit();
+                issued = true;
                 // ---- E'^T(i, l) += C(i, j) . A_s(j, l): C fragments reused as the A operand ----
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -217,6 +265,11 @@ __global__ void __launch_bounds__(IB_NT, 1) inner_batched_kernel(const __grid_co
                 }
             }
         }
+        if (!issued) {  // warps without work in this chunk still move their share of the next one
+            if (chunk_valid(p, nxt)) chunk_issue(p, nxt, stages + ((t + 1) & 1) * IB_STAGE);
+            cp_async_commit();
+        }
+        if (timing) { const long long now = clock64(); tacc1 += now - tprev; tprev = now; }
         const int nch = (n + IB_CS - 1) / IB_CS;
         const bool last_chunk = cur.c == nch - 1;
         if (last_chunk) {
@@ -248,8 +301,10 @@ __global__ void __launch_bounds__(IB_NT, 1) inner_batched_kernel(const __grid_co
         cur = nxt;
         chunk_advance(p, nxt, gridDim.x);
         ++t;
+        if (timing) { const long long now = clock64(); tacc2 += now - tprev; tprev = now; ++tchunks; }
     }
     cp_async_wait<0>();
+    if (timing) { p.dbg[0] = tacc0; p.dbg[1] = tacc1; p.dbg[2] = tacc2; p.dbg[3] = tchunks; }
 }
 
 constexpr size_t kInnerBatchSmem = size_t(2 * IB_STAGE + IB_RED + IB_R * IB_EP) * sizeof(double);
@@ -303,6 +358,10 @@ int inner_batched(const TTBatchDesc& a, const TTBatchDesc& b, double* out_dev, v
             p.rb[k] = int(b.r[k]);
         }
         p.out = out_dev;
+        static long long* dbg_dev = nullptr;
+        static const bool btiming = getenv("TTB_BINNER_TIMING") != nullptr;
+        if (btiming && !dbg_dev) cudaMalloc(&dbg_dev, 64);
+        p.dbg = btiming ? dbg_dev : nullptr;
         static bool configured = false;
         if (!configured) {
             TTB_CHECK_CUDA(cudaFuncSetAttribute(inner_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -311,6 +370,12 @@ int inner_batched(const TTBatchDesc& a, const TTBatchDesc& b, double* out_dev, v
         }
         const int grid = int(std::min<int64_t>(a.batch, int64_t(num_sms())));
         inner_batched_kernel<<<grid, IB_NT, kInnerBatchSmem, stream>>>(p);
+        if (btiming) {
+            long long h[4];
+            cudaMemcpy(h, dbg_dev, 32, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[binner] CTA0: %lld chunks; cycles per chunk: top wait %.0f, compute %.0f, tail %.0f\n", h[3],
+                    double(h[0]) / h[3], double(h[1]) / h[3], double(h[2]) / h[3]);
+        }
         ++g_launch_count;
         TTB_CHECK_CUDA(cudaGetLastError());
         return kOk;
