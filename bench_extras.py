@@ -116,7 +116,7 @@ def run_round_generic(d=20, n=64, parts=4, r_part=32, eps=1e-5, reps=2):
     }
 
 
-def run_ttsvd(n=16, d=7, ranks=(16, 64, 64, 64, 64, 16), eps=1e-10, reps=1):
+def run_ttsvd(n=16, d=7, ranks=(16, 64, 64, 64, 64, 16), eps=1e-10, reps=3):
     """configs[3]: TT-SVD of a dense n^d tensor built from a random TT with the given ranks."""
     x = TensorTrain.rand([n] * d, list(ranks), seed=3001)
     dense = x.dense_dev()

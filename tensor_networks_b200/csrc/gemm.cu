@@ -203,7 +203,7 @@ int max_splits_for(int64_t M, int64_t N, int64_t batch) {
     const int64_t t128 = ceil_div<int64_t>(M, 128) * ceil_div<int64_t>(N, 128) * batch;
     const int sms = num_sms();
     if (t128 >= sms) return 1;
-    return int(std::min<int64_t>(64, ceil_div<int64_t>(2 * sms, t128)));
+    return int(std::min<int64_t>(2 * sms, ceil_div<int64_t>(2 * sms, t128)));  // up to two CTAs per SM for one-tile outputs
 }
 
 }  // namespace
