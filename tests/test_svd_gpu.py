@@ -152,3 +152,37 @@ def test_round_plan_replay_contradiction():
             nz = tt.norm()
             assert abs(nz - ny) <= 1e-9 * ny
             assert abs(float(tt.inner(z)) / (ny * nz) - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_round_randomised_structures(seed):
+    """Random mixtures X1 (+) X2 (+) X1 (+) ... with bonds of 70-200: several Cholesky-QR panels per
+    core with deflated panels in arbitrary positions, compaction moves, the bulk test, plan replay
+    across cores, certificate on some cores and real truncation on others."""
+    from tensor_networks_b200 import TensorTrain
+
+    rng = np.random.default_rng(1000 + seed)
+    d = int(rng.integers(3, 6))
+    shape = [int(rng.integers(6, 15)) for _ in range(d)]
+    while np.prod(shape) > 1_500_000:
+        shape[int(np.argmax(shape))] -= 2
+    parts = []
+    for _ in range(int(rng.integers(2, 4))):
+        r = [int(rng.integers(8, 60)) for _ in range(d - 1)]
+        parts.append(orc.rand_tt(shape, r, rng))
+    order = [0, 1, 0] + ([2, 1] if len(parts) > 2 else [])
+    rng.shuffle(order)
+    y = None
+    for j, idx in enumerate(order):
+        t = copy.deepcopy(parts[idx])
+        t[0] = t[0] * float(10.0 ** (-rng.integers(0, 4)))
+        y = t if y is None else orc.tt_add(y, t)
+    eps = float(10.0 ** (-rng.integers(5, 10)))
+    ref, _ = orc.svd_round(copy.deepcopy(y), eps)
+    tt = TensorTrain.from_cores(copy.deepcopy(y)).round(eps)
+    dense = orc.to_dense(y)
+    err = np.linalg.norm(tt.dense() - dense) / np.linalg.norm(dense)
+    err_ref = np.linalg.norm(orc.to_dense(ref) - dense) / np.linalg.norm(dense)
+    assert tt.ranks() == orc.ranks_of(ref), (shape, eps, tt.ranks(), orc.ranks_of(ref))
+    assert abs(err - err_ref) <= 1e-10
+    assert err <= eps * 1.0000001 + 1e-13
