@@ -508,10 +508,36 @@ __global__ void __launch_bounds__(256) accumulate_r_kernel(double* __restrict__ 
                                                            int w, const double* __restrict__ C, int64_t ldcc,
                                                            const double* __restrict__ Rp,
                                                            const double* __restrict__ Rd_old,
-                                                           double* __restrict__ Rd_new, int diag) {
+                                                           double* __restrict__ Rd_new, int diag, int rd_identity) {
     __shared__ __align__(16) double rd[QF_W * QF_W];
     __shared__ double cs[QF_W][17];
     const int tid = threadIdx.x;
+    if (rd_identity) {
+        // first accumulation of a panel: Rd_old = I, so R[i][jc + t] += C[t][i] and Rd_new = Rp -- no products
+        const int64_t nblk0 = (jq + 15) / 16;
+        if (int64_t(blockIdx.x) < nblk0) {
+            if (!C) return;
+            const int64_t i0 = int64_t(blockIdx.x) * 16;
+            for (int idx = tid; idx < 16 * w; idx += blockDim.x) {
+                const int t = idx >> 4, ii = idx & 15;  // consecutive threads read consecutive i of C[t][:]
+                if (i0 + ii < jq) cs[t][ii] = C[t * ldcc + i0 + ii];
+            }
+            __syncthreads();
+            for (int idx = tid; idx < 16 * w; idx += blockDim.x) {
+                const int ii = idx / w, t = idx % w;
+                if (i0 + ii < jq) R[(i0 + ii) * ldr + jc + t] += cs[t][ii];
+            }
+            return;
+        }
+        if (!diag) return;
+        for (int idx = tid; idx < w * w; idx += blockDim.x) {
+            const int s_ = idx / w, t = idx % w;
+            const double v = (s_ <= t) ? (Rp ? Rp[idx] : (s_ == t ? 1.0 : 0.0)) : 0.0;
+            Rd_new[idx] = v;
+            R[(jq + s_) * ldr + jc + t] = v;
+        }
+        return;
+    }
     {
         // all loads of the w x w factor in flight at once (16-byte vectors, fixed trip count): a
         // strided scalar loop here costs one DRAM latency per iteration
@@ -852,9 +878,8 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
     // row is emitted), < 0 = error.
     auto fast_panel = [&](int w) -> int {
         double* P = M + jq * ldm;
-        set_identity_small_kernel<<<1, 256, 0, stream>>>(Rd[0], w);
-        ++g_launch_count;
         int cur = 0;
+        bool rd_ident = true;  // Rd[cur] is (implicitly) the identity until the first factor is accumulated
         if (jq > 0) {
             rownorm_kernel<<<w, 256, 0, stream>>>(P, m, ldm, nullptr, nrm[0], nullptr);
             ++g_launch_count;
@@ -929,7 +954,7 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
                                     host.status[3]);
                         { ProfScope ps_("qr.accumulate_r", stream);
                         accumulate_r_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jq, jc, w, Cb, jq, nullptr, Rd[cur],
-                                                                        Rd[cur ^ 1], 0); }
+                                                                        Rd[cur ^ 1], 0, rd_ident ? 1 : 0); }
                         ++g_launch_count;
                         if (plan && !replay) plan->seq.push_back({2, 1});
                         return 2;
@@ -939,7 +964,7 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
                         if (jq > 0) {  // keep the projection that was already applied to P
                             { ProfScope ps_("qr.accumulate_r", stream);
                             accumulate_r_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jq, jc, w, Cb, jq, nullptr, Rd[cur],
-                                                                            Rd[cur ^ 1], 0); }
+                                                                            Rd[cur ^ 1], 0, rd_ident ? 1 : 0); }
                             ++g_launch_count;
                         }
                         if (plan) plan->valid = false;  // Householder panels are never replayed
@@ -957,8 +982,9 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
                 const int blocks = int((jq + 15) / 16 + 1);
                 { ProfScope ps_("qr.accumulate_r", stream);
                 accumulate_r_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jq, jc, w, (first && jq > 0) ? Cb : nullptr, jq, Rp,
-                                                                Rd[cur], Rd[cur ^ 1], 1); }
+                                                                Rd[cur], Rd[cur ^ 1], 1, rd_ident ? 1 : 0); }
                 ++g_launch_count;
+                rd_ident = false;
                 cur ^= 1;
             }
             if (cudaGetLastError() != cudaSuccess) return -1;
@@ -1095,7 +1121,7 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
             const int blocks = int((jq + 15) / 16 + 1);
             { ProfScope ps_("qr.accumulate_r", stream);
             accumulate_r_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jq, jc, w, jq > 0 ? Cb : nullptr, jq, Rp, Rd[cur],
-                                                            Rd[cur ^ 1], 1); }
+                                                            Rd[cur ^ 1], 1, 0); }
             ++g_launch_count;
             TTB_CHECK_CUDA(cudaGetLastError());
             cur ^= 1;
