@@ -12,6 +12,7 @@
 // stale L1 line is ever consumed across a barrier.  Same arithmetic and the same summation
 // order as the per-GEMM path whenever the tile/split choices coincide.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "gemm.cuh"
@@ -24,6 +25,9 @@ namespace {
 
 using namespace gemm_detail;
 
+// 8 warps (2 per scheduler).  A 16-warp variant (128x112 as 8x2 warps of 16x56, 128x64 as 4x4 warps of
+// 32x16) was measured 3 % SLOWER: the smaller warp tiles need 0.64-0.75 shared-memory fragment loads per
+// DMMA instead of 0.38, which costs more than the extra latency hiding buys.
 using CfgT = TileCfg<128, 112, 32, 56, 4, 1>;  // phase 1
 using CfgE = TileCfg<128, 64, 32, 32, 3, 1>;   // phase 2
 static_assert(CfgT::NT == 256 && CfgE::NT == 256, "both phases run with 256 threads");
@@ -51,6 +55,7 @@ struct SweepParams {
     double* P;
     double* out;
     unsigned* barrier;
+    long long* timing;  // TTB_SWEEP_TIMING: clock64 sums of CTA 0 {phase1, barrier1, phase2, barrier2, phase3, barrier3}
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
@@ -89,6 +94,15 @@ __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams
     unsigned epoch = 0;
     int cur = 0;
     const int tid = threadIdx.x;
+    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = 0;
+    const bool timing = p.timing != nullptr && blockIdx.x == 0 && tid == 0;
+#define FS_TICK(slot)                     \
+    if (timing) {                         \
+        const long long now_ = clock64(); \
+        tacc[slot] += now_ - tlast;       \
+        tlast = now_;                     \
+    }
+    if (timing) tlast = clock64();
 
     for (int k = 0; k < p.d - 1; ++k) {
         const SweepStep s = p.steps[k];
@@ -140,7 +154,9 @@ __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams
                     }
                 }
             }
+            FS_TICK(0)
             grid_barrier(p.barrier, epoch);
+            FS_TICK(1)
             if (s.eb_order) {
                 A2 = s.A; B2 = p.T; K2 = int64_t(s.a) * s.n;   // E' = A_k (a n x a')^T . T (a n x b')
             } else {
@@ -185,7 +201,9 @@ __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams
                                  int(min(int64_t(CfgT::BN), N1 - n0)));
             }
         }
+        FS_TICK(2)
         grid_barrier(p.barrier, epoch);
+        FS_TICK(3)
         // ---------------- phase 3: deterministic reduction of the partials ----------------
         if (s.splits > 1) {
             const int64_t total2 = (int64_t(s.a2) * s.b2) >> 1;  // ranks are even: double2 elements
@@ -200,7 +218,9 @@ __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams
                 }
                 E2[idx] = acc;
             }
+            FS_TICK(4)
             grid_barrier(p.barrier, epoch);
+            FS_TICK(5)
         }
         cur ^= 1;
     }
@@ -233,6 +253,9 @@ __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams
             p.out[0] = v;
         }
     }
+    if (timing)
+        for (int i = 0; i < 6; ++i) p.timing[i] = tacc[i];
+#undef FS_TICK
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -340,12 +363,23 @@ int inner_fused(const TTDesc& A, const TTDesc& B, double* out_dev, void* ws, siz
     sp.P = P;
     sp.out = out_dev;
     sp.barrier = barrier;
+    static long long* timing_dev = nullptr;
+    static const bool sweep_timing = getenv("TTB_SWEEP_TIMING") != nullptr;
+    if (sweep_timing && !timing_dev) cudaMalloc(&timing_dev, 64);
+    sp.timing = sweep_timing ? timing_dev : nullptr;
     void* args[] = {&sp};
     const int slot = profile_begin(stream);
     TTB_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(inner_sweep_kernel), dim3(num_sms()),
                                                dim3(FS_NT), args, kFusedSmem, stream));
     ++g_launch_count;
     profile_end(slot, pl.flops, stream);
+    if (sweep_timing) {
+        long long h[6];
+        cudaMemcpy(h, timing_dev, 48, cudaMemcpyDeviceToHost);
+        const double tot = double(h[0] + h[1] + h[2] + h[3] + h[4] + h[5]);
+        fprintf(stderr, "[sweep] CTA0 cycles: phase1 %.1f%% barrier1 %.1f%% phase2 %.1f%% barrier2 %.1f%% phase3 %.1f%% barrier3 %.1f%% (total %.0f)\n",
+                100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot, 100 * h[5] / tot, tot);
+    }
     return kOk;
 }
 
