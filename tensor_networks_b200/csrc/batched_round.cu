@@ -138,8 +138,8 @@ __device__ int jacobi_rows_smem(double* __restrict__ X, double* __restrict__ J, 
         const double mx = sqrt(__longlong_as_double(static_cast<long long>(*flag)));  // flag holds rel^2
         __syncthreads();
         // quadratic convergence: once the largest pre-rotation off-diagonal of a sweep is below
-        // 1e-9 the rotations of that sweep have already pushed it to the 1e-18 level
-        if (mx <= fmax(tol, 1e-9)) return sweep + 1;
+        // 3e-8 the rotations of that sweep have already pushed it to the 1e-15 level
+        if (mx <= fmax(tol, 3e-8)) return sweep + 1;
     }
     return max_sweeps + 1;
 }

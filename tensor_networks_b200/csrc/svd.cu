@@ -864,7 +864,7 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
             cp.tol = 1e-15 * std::sqrt(double(std::max(q, 16)));
             cp.abs_tol2 = abs_tol * abs_tol;
             cp.noise2 = noise_floor * noise_floor;
-            cp.stop_rel = std::max(cp.tol, 1e-9);
+            cp.stop_rel = std::max(cp.tol, 3e-8);  // quadratic convergence: the rotations of that sweep leave ~1e-15
             cp.max_sweeps = max_sweeps;
             cp.out = reinterpret_cast<double*>(conv_dev);
             static const bool jtiming = getenv("TTB_JACOBI_TIMING") != nullptr;
@@ -965,9 +965,9 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
         mx = std::sqrt(mx);  // the kernel tracks the squared relative off-diagonal
         if (sweeps_out) *sweeps_out = sweep + 1;
         // mx is the largest relative off-diagonal met BEFORE its rotation in this sweep; Jacobi
-        // converges quadratically, so once it is below 1e-9 the rotations of this very sweep have
+        // converges quadratically, so once it is below 3e-8 the rotations of this very sweep have
         // pushed it to the 1e-18 level and no verification sweep is needed.
-        if (mx <= std::max(jp.tol, 1e-9)) return kOk;
+        if (mx <= std::max(jp.tol, 3e-8)) return kOk;
     }
     set_last_error("jacobi_rows: not converged after " + std::to_string(max_sweeps) + " sweeps");
     return kNotConverged;
