@@ -376,9 +376,11 @@ struct JacobiClusterParams {
     double* out;  // out[0] = sweeps done, out[1] = 1 when converged, out[2..7] = phase clocks (debug)
     int timing;   // 1: thread 0 of CTA 0 accumulates clock64() per phase section into out[2..7]
 };
-constexpr int JC_B = 16;
+// Rows per block: 16 (32 staged rows per CTA) or 8 (16 staged rows: twice the CTAs and phases, but the
+// 16 x 16 Gram makes every rotation round ~40 % cheaper and the tiles to exchange half as large).
 constexpr int JC_MAXH = 16;
 
+template <int JC_B>
 __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiClusterParams p) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
         const int cpr = p.ncol >> 1;  // 16-byte chunks per staged row
         for (int idx = tid; idx < R2 * cpr; idx += JB_NT) {
             const int a = idx / cpr, k = (idx % cpr) * 2;
-            const int gr = (2 * rank + (a >> 4)) * JC_B + (a & 15);
+            const int gr = (2 * rank + a / JC_B) * JC_B + (a % JC_B);
             const bool live = gr < p.p;
             double* dst = T + size_t(a) * p.pitch + k;
             if (k < p.qx) {
@@ -602,7 +604,7 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
     // ---- write back ----
     for (int a = warp; a < R2; a += JB_NWARP) {
         const int blk = (a < JC_B) ? arr_top[rank] : arr_bot[rank];
-        const int gr = blk * JC_B + (a & 15);
+        const int gr = blk * JC_B + (a % JC_B);
         if (gr >= p.p) continue;
         const double* t = T + size_t(a) * p.pitch;
         double* xr = p.X + int64_t(gr) * p.ldx;
@@ -853,9 +855,17 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
         cp.qx = round_up(q, 8);
         cp.ncol = round_up(cp.qx + p, 8);
         cp.pitch = cp.ncol + 4;
-        int nbc = std::max(2, ceil_div(p, JC_B));
+        // block size: 16 rows for tiny factors (a single CTA, no exchange at all) and whenever 8-row
+        // blocks would need more than the portable cluster size; 8 rows otherwise
+        static const int forced_b = [] {
+            const char* e = getenv("TTB_JACOBI_B");
+            return e ? atoi(e) : 0;
+        }();
+        int jcb = (p > 32 && ceil_div(p, 8) <= 16) ? 8 : 16;
+        if (forced_b == 8 || forced_b == 16) jcb = forced_b;
+        int nbc = std::max(2, ceil_div(p, jcb));
         if (nbc & 1) ++nbc;
-        const size_t csmem = (size_t(2 * JC_B) * cp.pitch + 2 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
+        const size_t csmem = (size_t(2 * jcb) * cp.pitch + 2 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
         int dev = 0, maxsm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -869,10 +879,12 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
             cp.out = reinterpret_cast<double*>(conv_dev);
             static const bool jtiming = getenv("TTB_JACOBI_TIMING") != nullptr;
             cp.timing = jtiming ? 1 : 0;
-            static size_t cconfigured = 0;
-            if (csmem > cconfigured) {
-                TTB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(csmem)));
-                cconfigured = csmem;
+            auto kern = (jcb == 8) ? jacobi_cluster_kernel<8> : jacobi_cluster_kernel<16>;
+            static size_t cconfigured[2] = {0, 0};
+            size_t& cconf = cconfigured[jcb == 8 ? 0 : 1];
+            if (csmem > cconf) {
+                TTB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(csmem)));
+                cconf = csmem;
             }
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(unsigned(nbc / 2));
@@ -886,15 +898,15 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            const cudaError_t le = cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel, cp);
+            const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, cp);
             if (le == cudaSuccess) {
                 ++g_launch_count;
                 double* hout = reinterpret_cast<double*>(conv_host_pinned);
                 TTB_CHECK_CUDA(cudaMemcpyAsync(hout, cp.out, (jtiming ? 8 : 2) * sizeof(double), cudaMemcpyDeviceToHost, stream));
                 TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
                 if (jtiming)
-                    fprintf(stderr, "[jacobi] p=%d q=%d sweeps=%d clocks: gram %.0f rounds %.0f apply %.0f syncA %.0f xchg %.0f syncB %.0f\n",
-                            p, q, int(hout[0]), hout[2], hout[3], hout[4], hout[5], hout[6], hout[7]);
+                    fprintf(stderr, "[jacobi] p=%d q=%d b=%d sweeps=%d clocks: gram %.0f rounds %.0f apply %.0f syncA %.0f xchg %.0f syncB %.0f\n",
+                            p, q, jcb, int(hout[0]), hout[2], hout[3], hout[4], hout[5], hout[6], hout[7]);
                 if (sweeps_out) *sweeps_out = int(hout[0]);
                 if (hout[1] != 0.0) return kOk;
                 set_last_error("jacobi_rows: not converged after " + std::to_string(max_sweeps) + " sweeps");
