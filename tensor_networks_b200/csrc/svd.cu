@@ -861,7 +861,10 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
             const char* e = getenv("TTB_JACOBI_B");
             return e ? atoi(e) : 0;
         }();
-        int jcb = (p > 32 && ceil_div(p, 8) <= 16) ? 8 : 16;
+        // (up to 16 CTAs with 8-row blocks: the non-portable cluster size, tried first and abandoned for
+        // good if the device refuses to schedule it)
+        static bool nonportable_ok = true;
+        int jcb = (p > 32 && ceil_div(p, 8) <= (nonportable_ok ? 32 : 16)) ? 8 : 16;
         if (forced_b == 8 || forced_b == 16) jcb = forced_b;
         int nbc = std::max(2, ceil_div(p, jcb));
         if (nbc & 1) ++nbc;
@@ -869,7 +872,8 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
         int dev = 0, maxsm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        if (cluster_enabled && nbc / 2 <= 8 && cp.ncol <= 32 * JB_NWARP && csmem + 4096 <= size_t(maxsm)) {
+        if (cluster_enabled && nbc / 2 <= (jcb == 8 && nonportable_ok ? 16 : 8) && cp.ncol <= 32 * JB_NWARP &&
+            csmem + 4096 <= size_t(maxsm)) {
             cp.X = X; cp.ldx = ldx; cp.J = J; cp.p = p; cp.q = q; cp.nb = nbc;
             cp.tol = 1e-15 * std::sqrt(double(std::max(q, 16)));
             cp.abs_tol2 = abs_tol * abs_tol;
@@ -885,6 +889,16 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
             if (csmem > cconf) {
                 TTB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(csmem)));
                 cconf = csmem;
+            }
+            if (nbc / 2 > 8) {
+                static bool np_set = false;
+                if (!np_set) {
+                    if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+                        (void)cudaGetLastError();
+                        nonportable_ok = false;
+                    }
+                    np_set = true;
+                }
             }
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(unsigned(nbc / 2));
@@ -911,6 +925,12 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
                 if (hout[1] != 0.0) return kOk;
                 set_last_error("jacobi_rows: not converged after " + std::to_string(max_sweeps) + " sweeps");
                 return kNotConverged;
+            }
+            if (nbc / 2 > 8) {  // the 16-CTA cluster is not schedulable here: use 16-row blocks from now on
+                (void)cudaGetLastError();
+                nonportable_ok = false;
+                return jacobi_rows(X, p, q, ldx, J, abs_tol, noise_floor, max_sweeps, sweeps_out, conv_dev, conv_host_pinned,
+                                   stream);
             }
             (void)cudaGetLastError();  // cluster shape not schedulable here: fall through to the multi-launch path
         }
