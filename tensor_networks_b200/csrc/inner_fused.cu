@@ -88,6 +88,7 @@ __device__ __forceinline__ void prefetch_rows_l2(const double* base, int64_t ld,
 }
 constexpr int kPrefetchRows = 3 * BK;  // the first three k tiles of the pipeline
 
+template <bool TIMING>
 __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[FS_NT / 32];
@@ -95,14 +96,14 @@ __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams
     int cur = 0;
     const int tid = threadIdx.x;
     long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = 0;
-    const bool timing = p.timing != nullptr && blockIdx.x == 0 && tid == 0;
+    const bool timing = TIMING && p.timing != nullptr && blockIdx.x == 0 && tid == 0;
 #define FS_TICK(slot)                     \
-    if (timing) {                         \
+    if (TIMING && timing) {               \
         const long long now_ = clock64(); \
         tacc[slot] += now_ - tlast;       \
         tlast = now_;                     \
     }
-    if (timing) tlast = clock64();
+    if (TIMING && timing) tlast = clock64();
 
     for (int k = 0; k < p.d - 1; ++k) {
         const SweepStep s = p.steps[k];
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams
             p.out[0] = v;
         }
     }
-    if (timing)
+    if (TIMING && timing)
         for (int i = 0; i < 6; ++i) p.timing[i] = tacc[i];
 #undef FS_TICK
 }
@@ -332,10 +333,10 @@ int inner_fused(const TTDesc& A, const TTDesc& B, double* out_dev, void* ws, siz
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-        if (cudaFuncSetAttribute(inner_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFusedSmem)) !=
+        if (cudaFuncSetAttribute(inner_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFusedSmem)) !=
             cudaSuccess)
             coop = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, inner_sweep_kernel, FS_NT, kFusedSmem) !=
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, inner_sweep_kernel<false>, FS_NT, kFusedSmem) !=
             cudaSuccess)
             max_blocks = 0;
         cudaGetLastError();
@@ -369,8 +370,17 @@ int inner_fused(const TTDesc& A, const TTDesc& B, double* out_dev, void* ws, siz
     sp.timing = sweep_timing ? timing_dev : nullptr;
     void* args[] = {&sp};
     const int slot = profile_begin(stream);
-    TTB_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(inner_sweep_kernel), dim3(num_sms()),
-                                               dim3(FS_NT), args, kFusedSmem, stream));
+    if (sweep_timing) {
+        static bool tconf = false;
+        if (!tconf) {
+            TTB_CHECK_CUDA(cudaFuncSetAttribute(inner_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                int(kFusedSmem)));
+            tconf = true;
+        }
+    }
+    TTB_CHECK_CUDA(cudaLaunchCooperativeKernel(sweep_timing ? reinterpret_cast<void*>(inner_sweep_kernel<true>)
+                                                            : reinterpret_cast<void*>(inner_sweep_kernel<false>),
+                                               dim3(num_sms()), dim3(FS_NT), args, kFusedSmem, stream));
     ++g_launch_count;
     profile_end(slot, pl.flops, stream);
     if (sweep_timing) {

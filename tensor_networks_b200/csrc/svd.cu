@@ -380,7 +380,7 @@ struct JacobiClusterParams {
 // 16 x 16 Gram makes every rotation round ~40 % cheaper and the tiles to exchange half as large).
 constexpr int JC_MAXH = 16;
 
-template <int JC_B>
+template <int JC_B, bool TIMING>
 __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiClusterParams p) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -437,14 +437,14 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
     bool converged = false;
     double sweep_max = 0.0;  // meaningful on thread 0
     long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = 0;
-    const bool timing = p.timing != 0 && tid == 0 && rank == 0;
+    const bool timing = TIMING && p.timing != 0 && tid == 0 && rank == 0;
 #define JC_TICK(slot)                       \
-    if (timing) {                           \
+    if (TIMING && timing) {                 \
         const long long now_ = clock64();   \
         tacc[slot] += now_ - tlast;         \
         tlast = now_;                       \
     }
-    if (timing) tlast = clock64();
+    if (TIMING && timing) tlast = clock64();
     for (int sweep = 0; sweep < p.max_sweeps && !converged; ++sweep) {
         for (int phase = 0; phase < nphase; ++phase) {
             // ---- Gram matrix of the staged rows over the first q columns (DMMA) ----
@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
     if (rank == 0 && tid == 0) {
         p.out[0] = double(sweeps);
         p.out[1] = converged ? 1.0 : 0.0;
-        if (timing)
+        if (TIMING && timing)
             for (int k = 0; k < 6; ++k) p.out[2 + k] = double(tacc[k]);
     }
 #undef JC_TICK
@@ -883,7 +883,8 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
             cp.out = reinterpret_cast<double*>(conv_dev);
             static const bool jtiming = getenv("TTB_JACOBI_TIMING") != nullptr;
             cp.timing = jtiming ? 1 : 0;
-            auto kern = (jcb == 8) ? jacobi_cluster_kernel<8> : jacobi_cluster_kernel<16>;
+            auto kern = jtiming ? ((jcb == 8) ? jacobi_cluster_kernel<8, true> : jacobi_cluster_kernel<16, true>)
+                                : ((jcb == 8) ? jacobi_cluster_kernel<8, false> : jacobi_cluster_kernel<16, false>);
             static size_t cconfigured[2] = {0, 0};
             size_t& cconf = cconfigured[jcb == 8 ? 0 : 1];
             if (csmem > cconf) {
