@@ -57,6 +57,8 @@ def run_round(d=50, n=64, r=128, eps=1e-8, reps=2, cpu_sample_d=4):
         "ranks_out": [out_ranks[0], out_ranks[len(out_ranks) // 2], out_ranks[-1]],
         "ranks_out_expected": [min(n, r), r, min(n, r)],
         "stats": stats,
+        "note": "FLOP rate in reference-algorithm FLOPs; stats.bonds_deflated / stats.svds_certified count the steps where "
+                "rank deflation in the RQ pass and the no-truncation certificate (DESIGN.md section 4) replaced work",
         "launches": launches,
     }
     # CPU: oracle (= reference algorithm) on a short chain of the same n, r

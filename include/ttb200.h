@@ -123,7 +123,9 @@ int ttb_tt_to_dense_f64(const ttb_tt* a, double* out_dev, void* workspace, size_
  * buffer.  max_rank <= 0: unlimited (the reference has no max_rank; when given,
  * rank = min(rank_eps, max_rank)).  ranks_out: HOST array of d+1 entries.
  * delta_out (HOST, may be NULL): the absolute delta used.  stats_out (HOST, may
- * be NULL): {number of SVDs, total Jacobi sweeps, SVDs that hit the sweep cap}.
+ * be NULL, 5 entries): {truncation steps, total Jacobi sweeps, SVDs that hit the
+ * sweep cap, steps where the no-truncation certificate replaced the SVD, bonds
+ * that were deflated (numerically dependent rows dropped) in the RQ pass}.
  * Synchronises the stream. */
 size_t ttb_round_workspace_bytes(const ttb_tt* t);
 int ttb_round_f64(const ttb_tt* t, double eps, int32_t max_rank, int64_t* ranks_out, double* delta_out,

@@ -135,6 +135,8 @@ int ttb_round_f64(const ttb_tt* t, double eps, int32_t max_rank, int64_t* ranks_
         stats_out[0] = st.svds;
         stats_out[1] = st.jacobi_sweeps;
         stats_out[2] = st.not_converged;
+        stats_out[3] = st.svds_certified;
+        stats_out[4] = st.bonds_deflated;
     }
     return rc;
 }

@@ -204,6 +204,7 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
             res->fro2 = fro2;
             res->sweeps = 0;
             res->converged = true;
+            res->certified = true;
             TTB_CHECK_CUDA(cudaMemcpyAsync(SVt_out, Rm, size_t(p) * c * 8, cudaMemcpyDeviceToDevice, stream));
             { ProfScope ps_("svd.transpose", stream); TTB_PROPAGATE(transpose(big, c, m, m, U_out, c, stream)); }
             g_t_rest += pt.tick();
@@ -383,6 +384,7 @@ int round_tt(const TTDesc& t, double eps, int max_rank, int64_t* ranks_out, doub
         TTB_PROPAGATE(right_orth_step(t.core[k], r[k], t.n[k] * r[k + 1], t.core[k - 1], r[k - 1] * t.n[k - 1],
                                       /*shrink=*/true, &c_new, sub, rest, stream,
                                       deflate_enabled ? deflation_tolerance(eps, t.n[k] * r[k + 1]) : 0.0));
+        if (stats && c_new < std::min<int64_t>(r[k], t.n[k] * r[k + 1])) stats->bonds_deflated += 1;
         r[k] = c_new;
     }
     g_t_rq += pt.tick();
@@ -409,6 +411,7 @@ int round_tt(const TTDesc& t, double eps, int max_rank, int64_t* ranks_out, doub
             stats->jacobi_sweeps += info.sweeps;
             stats->svds += 1;
             if (!info.converged) stats->not_converged += 1;
+            if (info.certified) stats->svds_certified += 1;
         }
         // next core: (rho x c) . (c x n r'') -> tmp, then back in place (compact)
         const int64_t ncols = t.n[k + 1] * r[k + 2];

@@ -23,12 +23,15 @@ struct TruncSvdInfo {
     double fro2;             // sum of sigma^2
     int sweeps;
     bool converged;
+    bool certified = false;  // the no-truncation certificate held: U = Q, carry = R, no SVD was run
 };
 
 struct RoundStats {
-    int svds = 0;
+    int svds = 0;            // forward-pass truncation steps
     int jacobi_sweeps = 0;
     int not_converged = 0;
+    int svds_certified = 0;  // steps where the no-truncation certificate replaced the SVD
+    int bonds_deflated = 0;  // bonds that shrank below min(c, m) during the RQ pass
 };
 
 // delta-truncated SVD of M (m x c, row-major contiguous), the device form of

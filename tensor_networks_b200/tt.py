@@ -309,7 +309,7 @@ class TensorTrain:
         ws = workspace(nbytes, self.device)
         ranks = (ctypes.c_int64 * (d + 1))()
         delta = ctypes.c_double(0.0)
-        stats = (ctypes.c_int32 * 3)()
+        stats = (ctypes.c_int32 * 5)()
         check(
             L.ttb_round_f64(
                 desc.ref(), float(eps), int(max_rank) if max_rank else 0, ranks, ctypes.byref(delta), stats,
@@ -326,6 +326,8 @@ class TensorTrain:
             "svds": int(stats[0]),
             "jacobi_sweeps": int(stats[1]),
             "not_converged": int(stats[2]),
+            "svds_certified": int(stats[3]),
+            "bonds_deflated": int(stats[4]),
         }
         return self
 

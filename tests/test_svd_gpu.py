@@ -107,6 +107,7 @@ def test_round_full_rank_is_identity():
     ref, _ = orc.svd_round([c.copy() for c in x.to_cores()], 1e-12)
     z = x.clone().round(1e-12)
     assert z.ranks() == orc.ranks_of(ref)
+    assert z.last_round["svds_certified"] >= 1 and z.last_round["bonds_deflated"] == 0
     nx, nz = x.norm(), z.norm()
     assert abs(nx - nz) <= 1e-12 * nx
     assert abs(float(z.inner(x)) / (nx * nz) - 1.0) < 1e-12
@@ -117,13 +118,14 @@ def test_round_partial_deflation():
     from tensor_networks_b200 import TensorTrain
 
     rng = np.random.default_rng(3)
-    shape = [16] * 5
-    x = orc.rand_tt(shape, [40] * 4, rng)
-    w = orc.rand_tt(shape, [9] * 4, rng)
-    y = orc.tt_add(orc.tt_add(x, w), x)  # bonds 89, true ranks <= 49
+    shape = [12] * 5
+    x = orc.rand_tt(shape, [70] * 4, rng)
+    w = orc.rand_tt(shape, [20] * 4, rng)
+    y = orc.tt_add(orc.tt_add(x, w), x)  # bonds 160 in panels of 64: [X | X,W,X' | X'] -> only the last panel is dependent
     ref, _ = orc.svd_round(copy.deepcopy(y), 1e-9)
     tt = TensorTrain.from_cores(copy.deepcopy(y)).round(1e-9)
     assert tt.ranks() == orc.ranks_of(ref)
+    assert tt.last_round["bonds_deflated"] >= 1
     dense = orc.to_dense(y)
     err = np.linalg.norm(tt.dense() - dense) / np.linalg.norm(dense)
     err_ref = np.linalg.norm(orc.to_dense(ref) - dense) / np.linalg.norm(dense)
