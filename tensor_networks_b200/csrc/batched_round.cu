@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "gemm.cuh"
@@ -41,6 +42,7 @@ struct RoundBatchParams {
     int max_rank;
     int64_t* ranks_out;     // (batch, d+1)
     int* status_out;        // (batch): Jacobi sweeps that hit the cap
+    long long* dbg;         // TTB_BROUND_TIMING: clock64 sums of CTA 0 (see RB_TICK slots)
 };
 
 __device__ __forceinline__ void rr_pair_dev(int n, int round, int k, int& a, int& b) {
@@ -144,6 +146,9 @@ __device__ int jacobi_rows_smem(double* __restrict__ X, double* __restrict__ J, 
     return max_sweeps + 1;
 }
 
+// timing slots: 0 RQ load+push, 1 RQ norms+QR, 2 RQ R export+compaction, 3 RQ form Q+store,
+//               4 FWD load+carry, 5 FWD QR+R export, 6 FWD form Q, 7 FWD certificate / SVD + store
+template <bool TIMING>
 __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_constant__ RoundBatchParams p) {
     extern __shared__ __align__(16) double sm[];
     double* As = sm;
@@ -160,6 +165,15 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = p.d;
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+    const bool timing = TIMING && p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+#define RB_TICK(slot)                     \
+    if (TIMING && timing) {               \
+        const long long now_ = clock64(); \
+        tacc[slot] += now_ - tlast;       \
+        tlast = now_;                     \
+    }
+    if (TIMING && timing) tlast = clock64();
 
     for (int64_t item = blockIdx.x; item < p.batch; item += gridDim.x) {
         for (int k = tid; k <= d; k += RB_NT) {
@@ -195,6 +209,7 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
                 }
             }
             __syncthreads();
+            RB_TICK(0)
             const int ww = c, hlen = m;
             // squared norms of the vectors before the factorisation: a vector whose remainder below the
             // pivot drops to deflate_tol of its norm is dependent at working precision and consumes no
@@ -218,6 +233,7 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
                 nsteps += ok ? 1 : 0;
             }
             __syncthreads();
+            RB_TICK(1)
             // R (nsteps x c): R[j][i] = As[i][j] for j < pvs[i]
             for (int idx = tid; idx < 32 * RB_SP; idx += RB_NT) {
                 const int j = idx / RB_SP, i = idx % RB_SP;
@@ -232,10 +248,12 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
                     if (src != j) As[j * QR_PITCH + tid] = As[src * QR_PITCH + tid];
                 }
             __syncthreads();
+            RB_TICK(2)
             house_formq_inplace(As, nsteps, hlen, tau_s, sdot);
             for (int idx = tid; idx < nsteps * m; idx += RB_NT) core[idx] = As[(idx / m) * QR_PITCH + idx % m];
             if (tid == 0) rq[k] = nsteps;
             __syncthreads();
+            RB_TICK(3)
         }
 
         // =========================== forward pass ===========================
@@ -275,6 +293,7 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
                 }
             }
             __syncthreads();
+            RB_TICK(4)
             const int ww = c, hlen = mrows;
             const int psv = min(ww, hlen);  // number of singular values
             for (int j = 0; j < psv; ++j) house_step(As, ww, hlen, j, sdot, arow, tau_s);
@@ -284,7 +303,9 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
                 Rm[idx] = (i < psv && j < c && i <= j) ? As[j * QR_PITCH + i] : 0.0;
             }
             __syncthreads();
+            RB_TICK(5)
             house_formq_inplace(As, psv, hlen, tau_s, sdot);
+            RB_TICK(6)
 
             // ---- no-truncation certificate (see tri_inv_fro_kernel in svd.cu): Y = R^{-1} by back
             // substitution, one column per thread; sigma_min(R) >= 1 / ||Y||_F > delta keeps every
@@ -337,6 +358,7 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
                         Cm[idx] = (sidx < c && j < c) ? Rm[idx] : 0.0;  // carry = R
                     }
                     __syncthreads();
+                    RB_TICK(7)
                     continue;
                 }
                 __syncthreads();
@@ -409,6 +431,7 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
             }
             __syncthreads();
         }
+        RB_TICK(7)
         // last core: (rho x ck) carry times (ck x n) core, compact
         {
             const int k = d - 1;
@@ -437,6 +460,9 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
         if (tid == 0 && p.status_out) p.status_out[item] = sh_bad;
         __syncthreads();
     }
+    if (TIMING && timing)
+        for (int i = 0; i < 8; ++i) p.dbg[i] = tacc[i];
+#undef RB_TICK
 }
 
 constexpr size_t kRoundBatchSmem = (size_t(QR_W) * QR_PITCH + 3 * 32 * RB_SP) * sizeof(double);
@@ -481,13 +507,29 @@ int round_batched(const TTBatchDesc& t, double eps, int max_rank, int64_t* ranks
         p.ranks_out = ranks_out_dev;
         p.status_out = status_out_dev;
         static bool configured = false;
+        static const bool btiming = getenv("TTB_BROUND_TIMING") != nullptr;
+        static long long* dbg_dev = nullptr;
         if (!configured) {
-            TTB_CHECK_CUDA(cudaFuncSetAttribute(round_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            TTB_CHECK_CUDA(cudaFuncSetAttribute(round_batched_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 int(kRoundBatchSmem)));
+            TTB_CHECK_CUDA(cudaFuncSetAttribute(round_batched_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                int(kRoundBatchSmem)));
+            if (btiming) cudaMalloc(&dbg_dev, 64);
             configured = true;
         }
+        p.dbg = btiming ? dbg_dev : nullptr;
         const int grid = int(std::min<int64_t>(t.batch, int64_t(num_sms()) * 2));
-        round_batched_kernel<<<grid, RB_NT, kRoundBatchSmem, stream>>>(p);
+        if (btiming) {
+            round_batched_kernel<true><<<grid, RB_NT, kRoundBatchSmem, stream>>>(p);
+            long long h[8];
+            cudaMemcpy(h, dbg_dev, 64, cudaMemcpyDeviceToHost);
+            const double items = double((t.batch + grid - 1) / grid);
+            fprintf(stderr, "[bround] CTA0 kcycles per item: RQ load+push %.0f, norms+QR %.0f, R+compact %.0f, formQ+store %.0f | "
+                            "FWD load+carry %.0f, QR %.0f, formQ %.0f, cert/SVD+store %.0f\n",
+                    h[0] / items / 1e3, h[1] / items / 1e3, h[2] / items / 1e3, h[3] / items / 1e3, h[4] / items / 1e3,
+                    h[5] / items / 1e3, h[6] / items / 1e3, h[7] / items / 1e3);
+        } else
+            round_batched_kernel<false><<<grid, RB_NT, kRoundBatchSmem, stream>>>(p);
         ++g_launch_count;
         TTB_CHECK_CUDA(cudaGetLastError());
         return kOk;

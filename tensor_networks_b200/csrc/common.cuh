@@ -182,6 +182,12 @@ __device__ __forceinline__ double fast_rsqrt3(double x) {
     const double r = fma(-(x * y), y, 1.0);
     return fma(y * r, fma(0.375, r, 0.5), y);
 }
+// 1 / x for any normal x != 0: r = 1 - x y, y (1 + r + r^2) leaves an O(r^3) error
+__device__ __forceinline__ double fast_rcp3(double x) {
+    const double y = rcp_seed64(x);
+    const double r = fma(-x, y, 1.0);
+    return fma(y * r, 1.0 + r, y);
+}
 __device__ __forceinline__ int dbl_exponent(double x) { return ((__double2hiint(x) >> 20) & 0x7ff) - 1023; }
 __device__ __forceinline__ double dbl_pow2(int e) { return __hiloint2double((e + 1023) << 20, 0); }  // 2^e, |e| < 1023
 // 2^(-e) with e = exponent of x (x > 0, normal): x * pow2_scale(x) is in [1, 2)

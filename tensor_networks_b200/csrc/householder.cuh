@@ -74,9 +74,11 @@ __device__ __forceinline__ bool house_step_ex(double* __restrict__ As, int ww, i
         return false;
     }
     const double alpha = arow[v];
-    const double beta = -copysign(fast_sqrt_any(nrm2), alpha);
-    const double inv = fast_rcp_any(beta * (beta - alpha));
-    const double inv_v0 = fast_rcp_any(alpha - beta);  // |alpha - beta| >= |beta| > 0: no cancellation
+    // f64-seeded rsqrt / reciprocals (no fp32 round trip: 19-cycle MUFU + one third-order step each,
+    // the two reciprocals are independent of each other)
+    const double beta = -copysign(nrm2 * fast_rsqrt3(nrm2), alpha);
+    const double inv = fast_rcp3(beta * (beta - alpha));
+    const double inv_v0 = fast_rcp3(alpha - beta);  // |alpha - beta| >= |beta| > 0: no cancellation
     const int t = tid;
     if (t >= pp && t < hh) {
         const double ut = (t == pp) ? (alpha - beta) : xj[t];
@@ -96,7 +98,7 @@ __device__ __forceinline__ bool house_step_ex(double* __restrict__ As, int ww, i
         }
         if (t == pp) {
             As[v * QR_PITCH + pp] = beta;
-            tau_s[pp] = (beta - alpha) * fast_rcp_any(beta);
+            tau_s[pp] = (beta - alpha) * fast_rcp3(beta);
         } else {
             As[v * QR_PITCH + t] = ut * inv_v0;
         }
