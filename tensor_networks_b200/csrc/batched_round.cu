@@ -43,6 +43,7 @@ struct RoundBatchParams {
     int64_t* ranks_out;     // (batch, d+1)
     int* status_out;        // (batch): Jacobi sweeps that hit the cap
     long long* dbg;         // TTB_BROUND_TIMING: clock64 sums of CTA 0 (see RB_TICK slots)
+    int use_cholqr;         // 1: Cholesky-QR2 fast path with Householder fallback (TTB_BROUND_CHOL=0 disables)
 };
 
 __device__ __forceinline__ void rr_pair_dev(int n, int round, int k, int& a, int& b) {
@@ -146,6 +147,313 @@ __device__ int jacobi_rows_smem(double* __restrict__ X, double* __restrict__ J, 
     return max_sweeps + 1;
 }
 
+// ---------------------------------------------------------------------------
+// Cholesky-QR2 with deflation on the shared-memory tile (fast path of both passes; the Householder
+// code below remains the fallback for anything ill-conditioned).
+//
+//   As[v][i], v < ww <= 32 vectors of length hlen <= 256.  On success:
+//     * the vectors of the index set I (in order) are orthonormal, every other vector (set D) was, to
+//       deflate_tol, a combination of them;  nq = |I|, posI[v] = rank of v inside I (or -1);
+//     * Rout[b][v] (b < nq) = coefficient of q_b in vector v, for ALL v (A = R^T Q);
+//     * the tile holds q at the rows of I (not compacted) -- the caller compacts.
+//   Steps (all dense work on the FP64 tensor pipe, 8 warps):
+//     G = A A^T -> echelon Cholesky in registers (a pivot below flag_thr of its vector's norm^2 is
+//     skipped: the vector is a candidate for D) + L^{-1} -> T <- L^{-1} T (rows of I: first-pass q,
+//     rows of D: first-pass residuals) -> G2 = T T^T -> first-order second pass W2 (I: I - strict_lower(E)
+//     - diag(E)/2, D: e_k - G2[k][I]) -> T <- W2 T -> explicit residual norms of D against
+//     deflate_tol -> R^T = (L + G2[D][I]) L2.
+//   Returns false (uniformly) when a pivot falls in the grey zone between "dependent" and "benign"
+//   (cond > ~20 sqrt(w)), when the first pass leaves |E| > 3e-8, when a D residual is too large, or
+//   on non-finite data: the caller reloads the tile and takes the Householder path.
+// ---------------------------------------------------------------------------
+struct CholQrScratch {
+    double* B1;    // G -> L
+    double* B2;    // L^{-1} -> W2
+    double* B3;    // G2
+    double* Rout;  // result
+    double* colb;  // [2][32]
+    double* rowb;  // [2][32]
+    double* dsv;   // [32]
+    double* rdg;   // [32]
+    double* g0;    // [32]
+    int* flg;      // [32]
+    int* posI;     // [32]
+    int* ibuf;     // [4]: fail flag, nq
+};
+
+// G[32][RB_SP] = T T^T over the first hlen columns (rows >= ww count as zero); all RB_NT threads
+__device__ __forceinline__ void tile_gram32(const double* __restrict__ T, int ww, int hlen, double* __restrict__ G) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int idx = tid; idx < 32 * RB_SP; idx += RB_NT) G[idx] = 0.0;
+    __syncthreads();
+    const int fr = lane >> 2, fq = lane & 3;
+    const int ksteps = (hlen + 3) >> 2;
+    // 10 upper 8x8 tiles x 2 k-halves = 20 jobs over 8 warps; two accumulator chains per job
+    for (int job = warp; job < 20; job += RB_NT / 32) {
+        const int t10 = job % 10, half = job / 10;
+        int ti = 0, tj = t10;  // enumerate (ti <= tj): (0,0..3) (1,1..3) (2,2..3) (3,3)
+        if (t10 >= 4) { ti = 1; tj = t10 - 3; }
+        if (t10 >= 7) { ti = 2; tj = t10 - 5; }
+        if (t10 >= 9) { ti = 3; tj = 3; }
+        const int ra = 8 * ti + fr, rb = 8 * tj + fr;
+        const bool la = ra < ww, lb = rb < ww;
+        const double* pa = T + ra * QR_PITCH + fq;
+        const double* pb = T + rb * QR_PITCH + fq;
+        const int ks0 = half ? (ksteps >> 1) : 0, ks1 = half ? ksteps : (ksteps >> 1);
+        double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+        int ks = ks0;
+        for (; ks + 1 < ks1; ks += 2) {
+            const bool k0 = 4 * ks + fq < hlen, k1 = 4 * ks + 4 + fq < hlen;
+            const double a0 = (la && k0) ? pa[4 * ks] : 0.0, b0 = (lb && k0) ? pb[4 * ks] : 0.0;
+            const double a1 = (la && k1) ? pa[4 * ks + 4] : 0.0, b1 = (lb && k1) ? pb[4 * ks + 4] : 0.0;
+            dmma884(c0, c1, a0, b0);
+            dmma884(e0, e1, a1, b1);
+        }
+        if (ks < ks1) {
+            const bool k0 = 4 * ks + fq < hlen;
+            dmma884(c0, c1, (la && k0) ? pa[4 * ks] : 0.0, (lb && k0) ? pb[4 * ks] : 0.0);
+        }
+        const int r = 8 * ti + fr, c = 8 * tj + 2 * fq;
+        atomicAdd(&G[r * RB_SP + c], c0 + e0);
+        atomicAdd(&G[r * RB_SP + c + 1], c1 + e1);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 32 * 32; idx += RB_NT) {
+        const int r = idx >> 5, c = idx & 31;
+        if ((r >> 3) > (c >> 3)) G[r * RB_SP + c] = G[c * RB_SP + r];
+    }
+    __syncthreads();
+}
+
+// T <- W T for the first ww rows, in place (each warp owns a 32-column slab); W is 32 x 32 (pitch RB_SP)
+__device__ __forceinline__ void tile_apply32(double* __restrict__ T, int ww, int hlen, const double* __restrict__ W) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane >> 2, fq = lane & 3;
+    const int n0 = warp * 32;
+    if (n0 < hlen) {
+        const int nt = min(4, (hlen - n0 + 7) >> 3);
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            double a[4], bf[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = W[(8 * i + fr) * RB_SP + 4 * ks + fq];
+            const int trow = 4 * ks + fq;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = (j < nt && trow < ww) ? T[trow * QR_PITCH + n0 + 8 * j + fr] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < nt) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = 8 * i + fr;
+            if (r < ww) {
+                double* base = T + r * QR_PITCH + n0 + 2 * fq;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < nt) *reinterpret_cast<double2*>(base + 8 * j) = make_double2(acc[i][j][0], acc[i][j][1]);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ bool cholqr_tile(double* __restrict__ As, int ww, int hlen, double deflate_tol2,
+                            const double* __restrict__ nrm0, const CholQrScratch sc, int* nq_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr double kFlagThr = 1e-12;  // pivot below this fraction of the vector's norm^2: candidate for D
+    constexpr double kIllThr = 2.5e-3;  // (0.05)^2: the benign bound of the large-rank path (qr.cu kIllMin)
+    if (tid == 0) {
+        sc.ibuf[0] = 0;
+        sc.ibuf[1] = 0;
+    }
+    // ---- first pass: G, echelon Cholesky + inverse in registers (16 x 16 threads, 2 x 2 elements each) ----
+    tile_gram32(As, ww, hlen, sc.B1);
+    const int ty = tid >> 4, tx = tid & 15;
+    double a[2][2];
+#pragma unroll
+    for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) a[ii][kk] = sc.B1[(ty + 16 * ii) * RB_SP + tx + 16 * kk];
+    if (tid < 32) sc.g0[tid] = sc.B1[tid * RB_SP + tid];
+    __syncthreads();
+    bool fail = false;
+#pragma unroll
+    for (int jq = 0; jq < 2; ++jq) {
+        for (int jj = 0; jj < 16; ++jj) {
+            const int j = 16 * jq + jj;
+            double* cb = sc.colb + (j & 1) * 32;
+            if (tx == jj) {
+#pragma unroll
+                for (int ii = 0; ii < 2; ++ii) cb[ty + 16 * ii] = a[ii][jq];
+            }
+            __syncthreads();
+            const double d = cb[j], g = sc.g0[j];
+            const bool pad = j >= ww;
+            const bool finite = (d == d) && (fabs(d) < 1e300) && (g == g) && (g < 1e300);
+            const bool flagged = pad || !finite || !(d > kFlagThr * g);
+            if (!pad && (!finite || (!flagged && !(d > kIllThr * g)))) fail = true;  // uniform
+            if (tid == 0) {
+                sc.flg[j] = flagged ? 1 : 0;
+                sc.dsv[j] = flagged ? 1.0 : d;
+            }
+            if (!flagged) {
+                const double invd = 1.0 / d;
+                double ci[2], ck[2];
+#pragma unroll
+                for (int ii = 0; ii < 2; ++ii) ci[ii] = cb[ty + 16 * ii] * invd;
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) ck[kk] = cb[tx + 16 * kk];
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    if (kk < jq) continue;
+                    if (kk == jq && tx <= jj) continue;
+#pragma unroll
+                    for (int ii = 0; ii < 2; ++ii) a[ii][kk] = fma(-ci[ii], ck[kk], a[ii][kk]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (fail) return false;
+    // deferred scaling; a flagged column is e_k, so that L^{-1} leaves the first-pass RESIDUAL in a flagged row
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+        const int k = tx + 16 * kk;
+        const bool fl = sc.flg[k] != 0;
+        const double rs = rsqrt(sc.dsv[k]);
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii) {
+            const int i = ty + 16 * ii;
+            a[ii][kk] = fl ? (i == k ? 1.0 : 0.0) : (i >= k ? a[ii][kk] * rs : 0.0);
+        }
+    }
+    if (tid < 32) sc.rdg[tid] = sc.flg[tid] ? 1.0 : rsqrt(sc.dsv[tid]);
+    double x[2][2];
+#pragma unroll
+    for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) x[ii][cc] = (ty + 16 * ii == tx + 16 * cc) ? 1.0 : 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int kq = 0; kq < 2; ++kq) {
+        for (int kr = 0; kr < 16; ++kr) {
+            const int k = 16 * kq + kr;
+            double* cb = sc.colb + (k & 1) * 32;
+            double* rb = sc.rowb + (k & 1) * 32;
+            if (ty == kr) {
+                const double rk = sc.rdg[k];
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    x[kq][cc] *= rk;
+                    rb[tx + 16 * cc] = x[kq][cc];
+                }
+            }
+            if (tx == kr) {
+#pragma unroll
+                for (int ii = 0; ii < 2; ++ii) cb[ty + 16 * ii] = a[ii][kq];
+            }
+            __syncthreads();
+            double li[2], xr[2];
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii) li[ii] = cb[ty + 16 * ii];
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) xr[cc] = rb[tx + 16 * cc];
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii) {
+                if (ii < kq) continue;
+                if (ii == kq && ty <= kr) continue;
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) x[ii][cc] = fma(-li[ii], xr[cc], x[ii][cc]);
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            sc.B1[(ty + 16 * ii) * RB_SP + tx + 16 * kk] = a[ii][kk];  // L
+            sc.B2[(ty + 16 * ii) * RB_SP + tx + 16 * kk] = x[ii][kk];  // L^{-1}
+        }
+    if (tid == 0) {
+        int n = 0;
+        for (int v = 0; v < 32; ++v) sc.posI[v] = (v < ww && !sc.flg[v]) ? n++ : -1;
+        sc.ibuf[1] = n;
+    }
+    __syncthreads();
+    tile_apply32(As, ww, hlen, sc.B2);
+    // ---- second pass ----
+    tile_gram32(As, ww, hlen, sc.B3);
+    {
+        double emax = 0.0;
+        for (int idx = tid; idx < 32 * 32; idx += RB_NT) {
+            const int i = idx >> 5, j = idx & 31;
+            const bool ii_ = i < ww && !sc.flg[i], jj_ = j < ww && !sc.flg[j];
+            const double g = sc.B3[i * RB_SP + j];
+            double w = (i == j) ? 1.0 : 0.0;
+            if (ii_ && jj_) {
+                const double e = g - ((i == j) ? 1.0 : 0.0);
+                emax = fmax(emax, fabs(e));
+                if (!(e == e)) emax = 1e300;
+                if (j < i) w -= e;
+                if (j == i) w -= 0.5 * e;
+            } else if (i < ww && !ii_ && jj_) {
+                w -= g;  // row of D: remove what is left along q_j
+            }
+            sc.B2[i * RB_SP + j] = w;
+        }
+        emax = warp_max(emax);
+        if (lane == 0 && emax > 3e-8) atomicExch(&sc.ibuf[0], 1);
+    }
+    __syncthreads();
+    if (sc.ibuf[0]) return false;
+    tile_apply32(As, ww, hlen, sc.B2);
+    // explicit residuals of D against the deflation tolerance
+    for (int v = warp; v < ww; v += RB_NT / 32) {
+        if (!sc.flg[v]) continue;
+        double sq = 0.0;
+        for (int i = lane; i < hlen; i += 32) sq = fma(As[v * QR_PITCH + i], As[v * QR_PITCH + i], sq);
+        sq = warp_sum(sq);
+        if (lane == 0 && !(sq <= deflate_tol2 * nrm0[v])) atomicExch(&sc.ibuf[0], 1);
+    }
+    __syncthreads();
+    if (sc.ibuf[0]) return false;
+    // ---- R^T = (L + G2[D][I]) L2,  Rout[pos(b)][v] = R^T[v][b] ----
+    for (int idx = tid; idx < 32 * RB_SP; idx += RB_NT) sc.Rout[idx] = 0.0;
+    __syncthreads();
+    for (int idx = tid; idx < 32 * 32; idx += RB_NT) {
+        const int v = idx >> 5, b = idx & 31;
+        const int pb = sc.posI[b];
+        if (v >= ww || pb < 0) continue;
+        const bool vd = sc.flg[v] != 0;
+        double acc = 0.0;
+        for (int j = b; j < ww; ++j) {
+            if (sc.flg[j]) continue;
+            // (L + Delta)[v][j]: L is lower; Delta[v][j] = G2[v][j] for v in D, j in I
+            double lv = (j <= v) ? sc.B1[v * RB_SP + j] : 0.0;
+            if (vd) lv += sc.B3[v * RB_SP + j];
+            // L2[j][b] = delta + strict_lower(E) + diag(E)/2 on I
+            double l2 = 0.0;
+            if (j == b) l2 = 1.0 + 0.5 * (sc.B3[b * RB_SP + b] - 1.0);
+            else l2 = sc.B3[j * RB_SP + b];  // j > b: E[j][b]
+            acc = fma(lv, l2, acc);
+        }
+        sc.Rout[pb * RB_SP + v] = acc;
+    }
+    __syncthreads();
+    *nq_out = sc.ibuf[1];
+    return true;
+}
+
 // timing slots: 0 RQ load+push, 1 RQ norms+QR, 2 RQ R export+compaction, 3 RQ form Q+store,
 //               4 FWD load+carry, 5 FWD QR+R export, 6 FWD form Q, 7 FWD certificate / SVD + store
 template <bool TIMING>
@@ -155,8 +463,26 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
     double* Rm = As + QR_W * QR_PITCH;  // R factor / rows handed to Jacobi
     double* Jm = Rm + 32 * RB_SP;
     double* Cm = Jm + 32 * RB_SP;       // carry diag(s) V^T
-    __shared__ double sdot[QR_W], arow[QR_W], tau_s[QR_W], nrm2[32], sig[32], nrm0[32];
+    double* Xa = Cm + 32 * RB_SP;       // Cholesky-QR scratch
+    double* Xb = Xa + 32 * RB_SP;
+    // one block of small vectors: the Householder path uses sdot / arow / tau_s / nrm2 / sig, the
+    // Cholesky-QR path re-uses the same words (the two never run at the same time); nrm0 is shared
+    __shared__ double small_sh[8 * 32];
+    double* sdot = small_sh;
+    double* arow = small_sh + 32;
+    double* tau_s = small_sh + 64;
+    double* nrm2 = small_sh + 96;
+    double* sig = small_sh + 128;
+    double* nrm0 = small_sh + 160;
     __shared__ int perm[32], pvs[32], pvec[32];
+    CholQrScratch sc;
+    sc.B1 = Jm; sc.B2 = Xa; sc.B3 = Xb; sc.Rout = Rm;
+    sc.colb = small_sh;        // 64 doubles (sdot, arow)
+    sc.rowb = small_sh + 64;   // 64 doubles (tau_s, nrm2)
+    sc.dsv = small_sh + 128;   // sig
+    sc.rdg = small_sh + 192;
+    sc.g0 = small_sh + 224;
+    sc.flg = perm; sc.posI = pvec; sc.ibuf = pvs;
     __shared__ double sh_cert[3];
     __shared__ int rq[kMaxDR + 1], rk[kMaxDR + 1];
     __shared__ unsigned long long flag;
@@ -165,7 +491,7 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = p.d;
-    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+    long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
     const bool timing = TIMING && p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
 #define RB_TICK(slot)                     \
     if (TIMING && timing) {               \
@@ -190,25 +516,28 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
             const int c = p.r[k], nn = p.n[k], ro = p.r[k + 1], rn = rq[k + 1];
             double* core = p.core[k] + item * (int64_t(c) * nn * ro);
             const int m = nn * rn;
+            auto load_tile = [&]() {
             if (k == d - 1) {
-                for (int idx = tid; idx < c * m; idx += RB_NT) As[(idx / m) * QR_PITCH + idx % m] = core[idx];
-            } else {
-                // push of the previous step while loading: new[v][s][j] = sum_i old[v][s][i] R[j][i]
-                for (int t = tid; t < c * nn; t += RB_NT) {
-                    const int v = t / nn, s = t % nn;
-                    const double* src = core + int64_t(t) * ro;
-                    double x[32];
+                    for (int idx = tid; idx < c * m; idx += RB_NT) As[(idx / m) * QR_PITCH + idx % m] = core[idx];
+                } else {
+                    // push of the previous step while loading: new[v][s][j] = sum_i old[v][s][i] R[j][i]
+                    for (int t = tid; t < c * nn; t += RB_NT) {
+                        const int v = t / nn, s = t % nn;
+                        const double* src = core + int64_t(t) * ro;
+                        double x[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) x[i] = (i < ro) ? src[i] : 0.0;
-                    for (int j = 0; j < rn; ++j) {
-                        double y = 0.0;
+                        for (int i = 0; i < 32; ++i) x[i] = (i < ro) ? src[i] : 0.0;
+                        for (int j = 0; j < rn; ++j) {
+                            double y = 0.0;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) y = fma(x[i], Rm[j * RB_SP + i], y);
-                        As[v * QR_PITCH + s * rn + j] = y;
+                            for (int i = 0; i < 32; ++i) y = fma(x[i], Rm[j * RB_SP + i], y);
+                            As[v * QR_PITCH + s * rn + j] = y;
+                        }
                     }
                 }
-            }
-            __syncthreads();
+                __syncthreads();
+            };
+            load_tile();
             RB_TICK(0)
             const int ww = c, hlen = m;
             // squared norms of the vectors before the factorisation: a vector whose remainder below the
@@ -222,6 +551,36 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
             }
             __syncthreads();
             int nsteps = 0;  // pivots consumed = orthonormal rows produced
+            bool fast_done = false;
+            if (p.use_cholqr) {
+                int nq = 0;
+                fast_done = cholqr_tile(As, ww, hlen, deflate_tol2, nrm0, sc, &nq);
+                if (TIMING && timing) tacc[fast_done ? 8 : 9] += 1;
+                if (fast_done) {
+                    nsteps = nq;
+                    // compact the orthonormal rows (I is increasing: thread t moves element t of every row itself)
+                    if (tid < hlen)
+                        for (int v = 0; v < ww; ++v) {
+                            const int b = sc.posI[v];
+                            if (b >= 0 && b != v) As[b * QR_PITCH + tid] = As[v * QR_PITCH + tid];
+                        }
+                    __syncthreads();
+                    RB_TICK(1)
+                    for (int idx = tid; idx < nsteps * m; idx += RB_NT) core[idx] = As[(idx / m) * QR_PITCH + idx % m];
+                    if (tid == 0) rq[k] = nsteps;
+                    __syncthreads();
+                    RB_TICK(3)
+                    continue;
+                }
+                load_tile();  // grey-zone conditioning or a large residual: Householder on a fresh tile
+                for (int v = warp; v < ww; v += RB_NT / 32) {
+                    double sq = 0.0;
+                    for (int i = lane; i < hlen; i += 32) sq = fma(As[v * QR_PITCH + i], As[v * QR_PITCH + i], sq);
+                    sq = warp_sum(sq);
+                    if (lane == 0) nrm0[v] = sq;
+                }
+                __syncthreads();
+            }
             for (int v = 0; v < ww; ++v) {
                 bool ok = false;
                 if (nsteps < hlen)
@@ -264,47 +623,68 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
             const int c = rq[k + 1];
             int mrows;
             double* core = p.core[k] + item * (int64_t(p.r[k]) * nn * p.r[k + 1]);
+            auto load_tile = [&]() {
             if (k == 0) {
-                // M[s][j] = sum_i core0[s][i] R[j][i]
-                const int ro = p.r[1];
-                mrows = nn;
-                for (int t = tid; t < nn * c; t += RB_NT) {
-                    const int s = t / c, j = t % c;
-                    const double* src = core + int64_t(s) * ro;
-                    double y = 0.0;
-                    for (int i = 0; i < ro; ++i) y = fma(src[i], Rm[j * RB_SP + i], y);
-                    As[j * QR_PITCH + s] = y;
-                }
-            } else {
-                // M[(q, s)][j] = sum_t carry[q][t] core_k[t][s][j]
-                const int ck = rq[k], rho = rk[k];
-                mrows = rho * nn;
-                for (int t = tid; t < nn * c; t += RB_NT) {
-                    const int s = t / c, j = t % c;
-                    double x[32];
-#pragma unroll
-                    for (int u = 0; u < 32; ++u) x[u] = (u < ck) ? core[(int64_t(u) * nn + s) * c + j] : 0.0;
-                    for (int q = 0; q < rho; ++q) {
+                    // M[s][j] = sum_i core0[s][i] R[j][i]
+                    const int ro = p.r[1];
+                    mrows = nn;
+                    for (int t = tid; t < nn * c; t += RB_NT) {
+                        const int s = t / c, j = t % c;
+                        const double* src = core + int64_t(s) * ro;
                         double y = 0.0;
+                        for (int i = 0; i < ro; ++i) y = fma(src[i], Rm[j * RB_SP + i], y);
+                        As[j * QR_PITCH + s] = y;
+                    }
+                } else {
+                    // M[(q, s)][j] = sum_t carry[q][t] core_k[t][s][j]
+                    const int ck = rq[k], rho = rk[k];
+                    mrows = rho * nn;
+                    for (int t = tid; t < nn * c; t += RB_NT) {
+                        const int s = t / c, j = t % c;
+                        double x[32];
 #pragma unroll
-                        for (int u = 0; u < 32; ++u) y = fma(Cm[q * RB_SP + u], x[u], y);
-                        As[j * QR_PITCH + q * nn + s] = y;
+                        for (int u = 0; u < 32; ++u) x[u] = (u < ck) ? core[(int64_t(u) * nn + s) * c + j] : 0.0;
+                        for (int q = 0; q < rho; ++q) {
+                            double y = 0.0;
+#pragma unroll
+                            for (int u = 0; u < 32; ++u) y = fma(Cm[q * RB_SP + u], x[u], y);
+                            As[j * QR_PITCH + q * nn + s] = y;
+                        }
                     }
                 }
-            }
-            __syncthreads();
+                __syncthreads();
+            };
+            load_tile();
             RB_TICK(4)
             const int ww = c, hlen = mrows;
             const int psv = min(ww, hlen);  // number of singular values
-            for (int j = 0; j < psv; ++j) house_step(As, ww, hlen, j, sdot, arow, tau_s);
-            // rows handed to Jacobi: X[i][j] = R[i][j] = As[j][i], i <= j
-            for (int idx = tid; idx < 32 * RB_SP; idx += RB_NT) {
-                const int i = idx / RB_SP, j = idx % RB_SP;
-                Rm[idx] = (i < psv && j < c && i <= j) ? As[j * QR_PITCH + i] : 0.0;
+            bool fast_done = false;
+            if (p.use_cholqr && hlen >= ww) {
+                // full column rank is expected here (the RQ pass deflated): any candidate for D or any other
+                // failure sends the step to the Householder path
+                for (int v = warp; v < ww; v += RB_NT / 32) {
+                    double sq = 0.0;
+                    for (int i = lane; i < hlen; i += 32) sq = fma(As[v * QR_PITCH + i], As[v * QR_PITCH + i], sq);
+                    sq = warp_sum(sq);
+                    if (lane == 0) nrm0[v] = sq;
+                }
+                __syncthreads();
+                int nq = 0;
+                fast_done = cholqr_tile(As, ww, hlen, 0.0, nrm0, sc, &nq) && nq == ww;
+                if (TIMING && timing) tacc[fast_done ? 10 : 11] += 1;
+                if (!fast_done) load_tile();
             }
-            __syncthreads();
-            RB_TICK(5)
-            house_formq_inplace(As, psv, hlen, tau_s, sdot);
+            if (!fast_done) {
+                for (int j = 0; j < psv; ++j) house_step(As, ww, hlen, j, sdot, arow, tau_s);
+                // rows handed to Jacobi: X[i][j] = R[i][j] = As[j][i], i <= j
+                for (int idx = tid; idx < 32 * RB_SP; idx += RB_NT) {
+                    const int i = idx / RB_SP, j = idx % RB_SP;
+                    Rm[idx] = (i < psv && j < c && i <= j) ? As[j * QR_PITCH + i] : 0.0;
+                }
+                __syncthreads();
+                RB_TICK(5)
+                house_formq_inplace(As, psv, hlen, tau_s, sdot);
+            }
             RB_TICK(6)
 
             // ---- no-truncation certificate (see tri_inv_fro_kernel in svd.cu): Y = R^{-1} by back
@@ -461,11 +841,11 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
         __syncthreads();
     }
     if (TIMING && timing)
-        for (int i = 0; i < 8; ++i) p.dbg[i] = tacc[i];
+        for (int i = 0; i < 12; ++i) p.dbg[i] = tacc[i];
 #undef RB_TICK
 }
 
-constexpr size_t kRoundBatchSmem = (size_t(QR_W) * QR_PITCH + 3 * 32 * RB_SP) * sizeof(double);
+constexpr size_t kRoundBatchSmem = (size_t(QR_W) * QR_PITCH + 5 * 32 * RB_SP) * sizeof(double);
 
 bool fits_small(const TTBatchDesc& t) {
     if (t.d > kMaxDR) return false;
@@ -514,15 +894,22 @@ int round_batched(const TTBatchDesc& t, double eps, int max_rank, int64_t* ranks
                                                 int(kRoundBatchSmem)));
             TTB_CHECK_CUDA(cudaFuncSetAttribute(round_batched_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 int(kRoundBatchSmem)));
-            if (btiming) cudaMalloc(&dbg_dev, 64);
+            if (btiming) cudaMalloc(&dbg_dev, 128);
             configured = true;
         }
         p.dbg = btiming ? dbg_dev : nullptr;
+        static const bool use_chol = [] {
+            const char* e = getenv("TTB_BROUND_CHOL");
+            return e == nullptr || e[0] != '0';
+        }();
+        p.use_cholqr = use_chol ? 1 : 0;
         const int grid = int(std::min<int64_t>(t.batch, int64_t(num_sms()) * 2));
         if (btiming) {
             round_batched_kernel<true><<<grid, RB_NT, kRoundBatchSmem, stream>>>(p);
-            long long h[8];
-            cudaMemcpy(h, dbg_dev, 64, cudaMemcpyDeviceToHost);
+            long long h[12];
+            cudaMemcpy(h, dbg_dev, 96, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[bround] Cholesky-QR fast path: RQ %lld ok / %lld fallback, FWD %lld ok / %lld fallback\n", h[8], h[9],
+                    h[10], h[11]);
             const double items = double((t.batch + grid - 1) / grid);
             fprintf(stderr, "[bround] CTA0 kcycles per item: RQ load+push %.0f, norms+QR %.0f, R+compact %.0f, formQ+store %.0f | "
                             "FWD load+carry %.0f, QR %.0f, formQ %.0f, cert/SVD+store %.0f\n",
