@@ -147,6 +147,28 @@ __device__ int jacobi_rows_smem(double* __restrict__ X, double* __restrict__ J, 
     return max_sweeps + 1;
 }
 
+// As[r][0:wid] <- src[r * wid + 0:wid] for r < rows: all copies in flight at once (cp.async, 16 bytes when
+// the row length is even and the source 16-byte aligned); a strided scalar loop pays one memory latency
+// per trip.  Ends with a block barrier.
+__device__ __forceinline__ void stage_rows(double* __restrict__ As, const double* __restrict__ src, int rows, int wid) {
+    const int tid = threadIdx.x;
+    if (((wid & 1) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+        const int cpr = wid >> 1;
+        for (int idx = tid; idx < rows * cpr; idx += RB_NT) {
+            const int r = idx / cpr, c2 = (idx % cpr) * 2;
+            cp_async16(As + r * QR_PITCH + c2, src + int64_t(r) * wid + c2, true);
+        }
+    } else {
+        for (int idx = tid; idx < rows * wid; idx += RB_NT) {
+            const int r = idx / wid, c1 = idx % wid;
+            cp_async8(As + r * QR_PITCH + c1, src + int64_t(r) * wid + c1, true);
+        }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------
 // Cholesky-QR2 with deflation on the shared-memory tile (fast path of both passes; the Householder
 // code below remains the fallback for anything ill-conditioned).
@@ -286,10 +308,15 @@ __device__ bool cholqr_tile(double* __restrict__ As, int ww, int hlen, double de
     if (tid < 32) sc.g0[tid] = sc.B1[tid * RB_SP + tid];
     __syncthreads();
     bool fail = false;
+    if (tid >= ww && tid < 32) {  // padding vectors: flagged from the start, never visited
+        sc.flg[tid] = 1;
+        sc.dsv[tid] = 1.0;
+    }
 #pragma unroll
     for (int jq = 0; jq < 2; ++jq) {
         for (int jj = 0; jj < 16; ++jj) {
             const int j = 16 * jq + jj;
+            if (j >= ww) break;  // uniform
             double* cb = sc.colb + (j & 1) * 32;
             if (tx == jj) {
 #pragma unroll
@@ -347,6 +374,7 @@ __device__ bool cholqr_tile(double* __restrict__ As, int ww, int hlen, double de
     for (int kq = 0; kq < 2; ++kq) {
         for (int kr = 0; kr < 16; ++kr) {
             const int k = 16 * kq + kr;
+            if (k >= ww) break;  // the padding block of L is the identity: nothing below it to eliminate
             double* cb = sc.colb + (k & 1) * 32;
             double* rb = sc.rowb + (k & 1) * 32;
             if (ty == kr) {
@@ -430,24 +458,27 @@ __device__ bool cholqr_tile(double* __restrict__ As, int ww, int hlen, double de
     // ---- R^T = (L + G2[D][I]) L2,  Rout[pos(b)][v] = R^T[v][b] ----
     for (int idx = tid; idx < 32 * RB_SP; idx += RB_NT) sc.Rout[idx] = 0.0;
     __syncthreads();
-    for (int idx = tid; idx < 32 * 32; idx += RB_NT) {
-        const int v = idx >> 5, b = idx & 31;
-        const int pb = sc.posI[b];
-        if (v >= ww || pb < 0) continue;
-        const bool vd = sc.flg[v] != 0;
-        double acc = 0.0;
-        for (int j = b; j < ww; ++j) {
-            if (sc.flg[j]) continue;
-            // (L + Delta)[v][j]: L is lower; Delta[v][j] = G2[v][j] for v in D, j in I
-            double lv = (j <= v) ? sc.B1[v * RB_SP + j] : 0.0;
-            if (vd) lv += sc.B3[v * RB_SP + j];
-            // L2[j][b] = delta + strict_lower(E) + diag(E)/2 on I
-            double l2 = 0.0;
-            if (j == b) l2 = 1.0 + 0.5 * (sc.B3[b * RB_SP + b] - 1.0);
-            else l2 = sc.B3[j * RB_SP + b];  // j > b: E[j][b]
-            acc = fma(lv, l2, acc);
+    {
+        unsigned dmask = 0;  // bit j: vector j is in D (or padding)
+        for (int j = 0; j < 32; ++j) dmask |= (sc.flg[j] ? 1u : 0u) << j;
+        for (int idx = tid; idx < 32 * 32; idx += RB_NT) {
+            const int v = idx >> 5, b = idx & 31;
+            if (v >= ww || ((dmask >> b) & 1u)) continue;
+            const int pb = sc.posI[b];
+            const bool vd = (dmask >> v) & 1u;
+            // (L + Delta)[v][j] L2[j][b] over j in I, j >= b; L is lower (j <= v), Delta only on rows of D
+            const int jend = vd ? ww - 1 : v;
+            double lvb = (b <= v) ? sc.B1[v * RB_SP + b] : 0.0;
+            if (vd) lvb += sc.B3[v * RB_SP + b];
+            double acc = lvb * (1.0 + 0.5 * (sc.B3[b * RB_SP + b] - 1.0));
+            for (int j = b + 1; j <= jend; ++j) {
+                if ((dmask >> j) & 1u) continue;
+                double lv = (j <= v) ? sc.B1[v * RB_SP + j] : 0.0;
+                if (vd) lv += sc.B3[v * RB_SP + j];
+                acc = fma(lv, sc.B3[j * RB_SP + b], acc);  // L2[j][b] = E[j][b] for j > b
+            }
+            sc.Rout[pb * RB_SP + v] = acc;
         }
-        sc.Rout[pb * RB_SP + v] = acc;
     }
     __syncthreads();
     *nq_out = sc.ibuf[1];
@@ -518,9 +549,55 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
             const int m = nn * rn;
             auto load_tile = [&]() {
             if (k == d - 1) {
-                    for (int idx = tid; idx < c * m; idx += RB_NT) As[(idx / m) * QR_PITCH + idx % m] = core[idx];
+                    stage_rows(As, core, c, m);
                 } else {
                     // push of the previous step while loading: new[v][s][j] = sum_i old[v][s][i] R[j][i]
+                    if (nn <= 8 && (ro & 3) == 0 && nn * ro <= QR_H) {
+                        // tensor-pipe version: the raw core is staged in the tile (coalesced), every warp keeps
+                        // the products of its (8 vectors) x (mode slice) jobs in registers, and only after a
+                        // barrier are they written back -- the output of slice s overlaps the input of later ones
+                        const int wid = nn * ro;
+                        stage_rows(As, core, c, wid);
+                        const int fr = lane >> 2, fq = lane & 3;
+                        const int njobs = ((c + 7) >> 3) * nn, ntl = (rn + 7) >> 3;
+                        double acc[4][4][2];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) acc[q][t][0] = acc[q][t][1] = 0.0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int job = warp + q * (RB_NT / 32);
+                            if (job < njobs) {
+                                const int vt = job / nn, sl = job % nn;
+                                const int vrow = 8 * vt + fr;
+                                const double* ap = As + vrow * QR_PITCH + sl * ro + fq;
+                                for (int ks = 0; ks < (ro >> 2); ++ks) {
+                                    const double af = (vrow < c) ? ap[4 * ks] : 0.0;
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t)
+                                        if (t < ntl) dmma884(acc[q][t][0], acc[q][t][1], af, Rm[(8 * t + fr) * RB_SP + 4 * ks + fq]);
+                                }
+                            }
+                        }
+                        __syncthreads();
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int job = warp + q * (RB_NT / 32);
+                            if (job < njobs) {
+                                const int vt = job / nn, sl = job % nn;
+                                const int vrow = 8 * vt + fr;
+                                if (vrow < c) {
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t) {
+                                        const int j = 8 * t + 2 * fq;
+                                        if (t < ntl && j < rn) As[vrow * QR_PITCH + sl * rn + j] = acc[q][t][0];
+                                        if (t < ntl && j + 1 < rn) As[vrow * QR_PITCH + sl * rn + j + 1] = acc[q][t][1];
+                                    }
+                                }
+                            }
+                        }
+                    } else
                     for (int t = tid; t < c * nn; t += RB_NT) {
                         const int v = t / nn, s = t % nn;
                         const double* src = core + int64_t(t) * ro;
@@ -639,6 +716,46 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
                     // M[(q, s)][j] = sum_t carry[q][t] core_k[t][s][j]
                     const int ck = rq[k], rho = rk[k];
                     mrows = rho * nn;
+                    const int wid = nn * c;  // <= QR_H (fits_small)
+                    if (((rho + 7) >> 3) * ((wid + 7) >> 3) <= 16 * (RB_NT / 32)) {
+                        // tensor-pipe version: stage the raw core (ck x nn c) in the tile, out = carry . core as
+                        // (rho x nn c) DMMA tiles held in registers, barrier, then scatter to As[j][q nn + s]
+                        stage_rows(As, core, ck, wid);
+                        const int fr = lane >> 2, fq = lane & 3;
+                        const int mtl = (rho + 7) >> 3, etl = (wid + 7) >> 3, njobs = mtl * etl;
+                        const int kst = (ck + 3) >> 2;
+                        double acc[16][2];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) acc[q][0] = acc[q][1] = 0.0;
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const int job = warp + q * (RB_NT / 32);
+                            if (job < njobs) {
+                                const int mt = job % mtl, et = job / mtl;
+                                const int e = 8 * et + fr;
+                                for (int ks = 0; ks < kst; ++ks) {
+                                    const int u = 4 * ks + fq;
+                                    const double af = Cm[(8 * mt + fr) * RB_SP + u];  // rows >= rho / cols >= ck are zero
+                                    const double bf = (u < ck && e < wid) ? As[u * QR_PITCH + e] : 0.0;
+                                    dmma884(acc[q][0], acc[q][1], af, bf);
+                                }
+                            }
+                        }
+                        __syncthreads();
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const int job = warp + q * (RB_NT / 32);
+                            if (job < njobs) {
+                                const int mt = job % mtl, et = job / mtl;
+                                const int qrow = 8 * mt + fr;
+#pragma unroll
+                                for (int h2 = 0; h2 < 2; ++h2) {
+                                    const int e = 8 * et + 2 * fq + h2;
+                                    if (qrow < rho && e < wid) As[(e % c) * QR_PITCH + qrow * nn + e / c] = acc[q][h2];
+                                }
+                            }
+                        }
+                    } else
                     for (int t = tid; t < nn * c; t += RB_NT) {
                         const int s = t / c, j = t % c;
                         double x[32];

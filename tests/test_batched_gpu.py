@@ -105,6 +105,9 @@ def _round_case(batch, shape, xr, eps, seed, mode="double"):
         (3, [7, 5], [4], 1e-8, "double"),  # d = 2
         (200, [5] * 4, [2] * 3, 1e-6, "double"),  # more items than SMs
         (2, [3, 2, 2, 3], [4, 7, 5], 1e-8, "double"),  # n*b < r (pad branch of the reference)
+        (4, [8] * 8, [14] * 7, 1e-8, "double"),  # bonds 28: Cholesky-QR fast path with deflation candidates
+        (4, [8] * 6, [12] * 5, 1e-4, "decay"),  # bonds 18, graded: grey-zone pivots -> Householder fallback
+        (3, [9, 7, 8, 6, 9], [11, 13, 9, 10], 1e-9, "double"),  # odd tile extents (hlen not a multiple of 4 / 8)
     ],
 )
 def test_round_batched_vs_oracle(batch, shape, xr, eps, mode):
