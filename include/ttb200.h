@@ -100,6 +100,18 @@ size_t ttb_inner_workspace_bytes(const ttb_tt* a, const ttb_tt* b);
 int ttb_inner_f64(const ttb_tt* a, const ttb_tt* b, double* out_dev, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* <a, b> for operands whose cores still sit in pinned HOST memory (a_host[k] / b_host[k], same
+ * layout as the device cores of a / b, which receive the copies).  The copies run on copy_stream
+ * (copy engines) while the persistent sweep kernel already runs on `stream` and waits, core by core,
+ * for per-core ready flags set by the copy stream: the 2 GB host->device transfer of the headline
+ * workload overlaps the contraction instead of preceding it.  Replaces the same reference call as
+ * ttb_inner_f64 (TensorNetwork.inner, pytens/algs.py:585-587) for callers that hold numpy cores.
+ * copy_stream must differ from stream.  Asynchronous: the result is ready when `stream` is. */
+size_t ttb_inner_streamed_workspace_bytes(const ttb_tt* a, const ttb_tt* b);
+int ttb_inner_streamed_f64(const ttb_tt* a, const ttb_tt* b, const double* const* a_host,
+                           const double* const* b_host, double* out_dev, void* workspace,
+                           size_t workspace_bytes, void* stream, void* copy_stream);
+
 /* out_dev[i] = <A_i, B_i> for every item of two batches of equal mode sizes:
  * TensorNetwork.inner (pytens/algs.py:585-587) applied item by item, fused into one
  * kernel when all bond ranks are <= 32. */

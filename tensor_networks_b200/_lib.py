@@ -88,6 +88,13 @@ def _declare(lib):
     lib.ttb_inner_f64.restype = c_int
     lib.ttb_inner_f64.argtypes = [P(ttb_tt), P(ttb_tt), c_void_p, c_void_p, c_size_t, c_void_p]
 
+    lib.ttb_inner_streamed_workspace_bytes.restype = c_size_t
+    lib.ttb_inner_streamed_workspace_bytes.argtypes = [P(ttb_tt), P(ttb_tt)]
+    lib.ttb_inner_streamed_f64.restype = c_int
+    lib.ttb_inner_streamed_f64.argtypes = [
+        P(ttb_tt), P(ttb_tt), P(c_void_p), P(c_void_p), c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
+    ]
+
     lib.ttb_round_workspace_bytes.restype = c_size_t
     lib.ttb_round_workspace_bytes.argtypes = [P(ttb_tt)]
     lib.ttb_round_f64.restype = c_int

@@ -89,6 +89,21 @@ int ttb_inner_f64(const ttb_tt* a, const ttb_tt* b, double* out_dev, void* works
     return ttb::inner(to_desc(a), to_desc(b), out_dev, workspace, workspace_bytes, as_stream(stream));
 }
 
+size_t ttb_inner_streamed_workspace_bytes(const ttb_tt* a, const ttb_tt* b) {
+    if (!a || !b) return 0;
+    return ttb::inner_streamed_workspace_bytes(to_desc(a), to_desc(b));
+}
+
+int ttb_inner_streamed_f64(const ttb_tt* a, const ttb_tt* b, const double* const* a_host, const double* const* b_host,
+                           double* out_dev, void* workspace, size_t workspace_bytes, void* stream, void* copy_stream) {
+    if (!a || !b) {
+        ttb::set_last_error("ttb_inner_streamed_f64: null descriptor");
+        return TTB_INVALID_ARGUMENT;
+    }
+    return ttb::inner_streamed(to_desc(a), to_desc(b), a_host, b_host, out_dev, workspace, workspace_bytes,
+                               as_stream(stream), as_stream(copy_stream));
+}
+
 size_t ttb_inner_batched_workspace_bytes(const ttb_tt_batch* a, const ttb_tt_batch* b) {
     if (!a || !b) return 0;
     return ttb::inner_batched_workspace_bytes(to_bdesc(a), to_bdesc(b));

@@ -98,6 +98,52 @@ size_t inner_workspace_bytes(const TTDesc& a, const TTDesc& b) {
     return std::max(inner_layout(a, b).total(), inner_fused_workspace_bytes(a, b));
 }
 
+size_t inner_streamed_workspace_bytes(const TTDesc& a, const TTDesc& b) {
+    return inner_workspace_bytes(a, b) + round_up<size_t>(size_t(a.d + 2) * sizeof(int), 256) + 256;
+}
+
+int inner_streamed(const TTDesc& A, const TTDesc& B, const double* const* a_host, const double* const* b_host,
+                   double* out_dev, void* ws, size_t ws_bytes, cudaStream_t stream, cudaStream_t copy_stream) {
+    TTB_PROPAGATE(validate(A, "inner_streamed: A"));
+    TTB_PROPAGATE(validate(B, "inner_streamed: B"));
+    TTB_REQUIRE(A.d == B.d && a_host && b_host && out_dev, "inner_streamed: bad arguments");
+    TTB_REQUIRE(stream != copy_stream, "inner_streamed: the copy stream must differ from the compute stream");
+    const int d = A.d;
+    const size_t flag_bytes = round_up<size_t>(size_t(d + 2) * sizeof(int), 256);
+    TTB_REQUIRE(ws != nullptr && ws_bytes >= flag_bytes + 256, "inner_streamed: workspace too small");
+    int* flags = static_cast<int*>(ws);  // [0..d-1] ready, [d] fail
+    char* rest = static_cast<char*>(ws) + flag_bytes;
+    const size_t rest_bytes = ws_bytes - flag_bytes;
+
+    static cudaEvent_t ev_reset = nullptr, ev_copied = nullptr;
+    if (!ev_reset) {
+        TTB_CHECK_CUDA(cudaEventCreateWithFlags(&ev_reset, cudaEventDisableTiming));
+        TTB_CHECK_CUDA(cudaEventCreateWithFlags(&ev_copied, cudaEventDisableTiming));
+    }
+    // the device buffers may still be read by earlier work on `stream`: the copies wait for it
+    TTB_CHECK_CUDA(cudaMemsetAsync(flags, 0, size_t(d + 2) * sizeof(int), stream));
+    TTB_CHECK_CUDA(cudaEventRecord(ev_reset, stream));
+    TTB_CHECK_CUDA(cudaStreamWaitEvent(copy_stream, ev_reset, 0));
+    for (int k = 0; k < d; ++k) {
+        const size_t na = size_t(A.r[k]) * A.n[k] * A.r[k + 1] * sizeof(double);
+        const size_t nb = size_t(B.r[k]) * B.n[k] * B.r[k + 1] * sizeof(double);
+        TTB_CHECK_CUDA(cudaMemcpyAsync(A.core[k], a_host[k], na, cudaMemcpyHostToDevice, copy_stream));
+        TTB_CHECK_CUDA(cudaMemcpyAsync(B.core[k], b_host[k], nb, cudaMemcpyHostToDevice, copy_stream));
+        TTB_CHECK_CUDA(cudaMemsetAsync(flags + k, 1, sizeof(int), copy_stream));  // 0x01010101: ready
+    }
+    TTB_CHECK_CUDA(cudaEventRecord(ev_copied, copy_stream));
+    // every copy is already queued, so the kernel can only ever wait for work that is in flight
+    int st = kUnsupported;
+    if (fused_enabled()) st = inner_fused(A, B, out_dev, rest, rest_bytes, stream, flags, flags + d);
+    if (st == kUnsupported) {
+        TTB_CHECK_CUDA(cudaStreamWaitEvent(stream, ev_copied, 0));
+        return inner(A, B, out_dev, rest, rest_bytes, stream);
+    }
+    // later work on `stream` may overwrite the device cores: it must also be behind the copies (it is:
+    // the kernel has consumed every flag before it ends)
+    return st;
+}
+
 int inner(const TTDesc& A, const TTDesc& B, double* out_dev, void* ws, size_t ws_bytes,
           cudaStream_t stream) {
     TTB_PROPAGATE(validate(A, "inner: A"));

@@ -56,7 +56,39 @@ struct SweepParams {
     double* out;
     unsigned* barrier;
     long long* timing;  // TTB_SWEEP_TIMING: clock64 sums of CTA 0 {phase1, barrier1, phase2, barrier2, phase3, barrier3}
+    const int* ready;   // streamed mode: ready[k] != 0 once cores k of A and B have landed in HBM (copy engine); else null
+    int* fail;          // streamed mode: set when a core did not arrive within the time-out
 };
+
+// Streamed mode: the cores are being copied host -> device by the copy engines on another stream while
+// this kernel runs; thread 0 polls the per-core flag that the copy stream sets (stream-ordered after the
+// data) with system scope, then the CTA proceeds.  A generous time-out turns a lost copy into an error
+// instead of a hung GPU.  Returns false (uniformly) on time-out.
+__device__ __forceinline__ bool wait_core_ready(const int* ready, int k, int* fail) {
+    __shared__ int ok_sh;
+    if (threadIdx.x == 0) {
+        int ok = 1;
+        const long long t0 = clock64();
+        int v;
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(ready + k) : "memory");
+            if (v == 0) {
+                __nanosleep(200);
+                if (clock64() - t0 > 8000000000ll) {  // ~4 s
+                    ok = 0;
+                    *fail = 1;
+                    break;
+                }
+            }
+        } while (v == 0);
+        __threadfence_system();
+        ok_sh = ok;
+    }
+    __syncthreads();
+    const bool ok = ok_sh != 0;
+    __syncthreads();
+    return ok;
+}
 
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
     __syncthreads();
@@ -88,7 +120,7 @@ __device__ __forceinline__ void prefetch_rows_l2(const double* base, int64_t ld,
 }
 constexpr int kPrefetchRows = 3 * BK;  // the first three k tiles of the pipeline
 
-template <bool TIMING>
+template <bool TIMING, bool STREAMED>
 __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[FS_NT / 32];
@@ -106,6 +138,7 @@ __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams
     if (TIMING && timing) tlast = clock64();
 
     for (int k = 0; k < p.d - 1; ++k) {
+        if (STREAMED && !wait_core_ready(p.ready, k, p.fail)) return;  // every CTA times out alike
         const SweepStep s = p.steps[k];
         const double* Ein = cur ? p.E1 : p.E0;
         double* Eout = cur ? p.E0 : p.E1;
@@ -227,6 +260,7 @@ __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams
     }
 
     // ---------------- last core: <A,B> = sum_{i,s} A_d[i][s] * (E . B_d)[i][s] ----------------
+    if (STREAMED && !wait_core_ready(p.ready, p.d - 1, p.fail)) return;
     {
         const SweepStep s = p.steps[p.d - 1];
         const double* Ein = cur ? p.E1 : p.E0;
@@ -324,7 +358,8 @@ size_t inner_fused_workspace_bytes(const TTDesc& a, const TTDesc& b) {
 }
 
 // Returns kUnsupported when the shapes do not qualify (caller falls back to the per-GEMM path).
-int inner_fused(const TTDesc& A, const TTDesc& B, double* out_dev, void* ws, size_t ws_bytes, cudaStream_t stream) {
+int inner_fused(const TTDesc& A, const TTDesc& B, double* out_dev, void* ws, size_t ws_bytes, cudaStream_t stream,
+                const int* ready_dev, int* fail_dev) {
     FusedPlan pl;
     if (!plan_fused(A, B, &pl)) return kUnsupported;
     if (ws == nullptr || ws_bytes < fused_bytes(pl, A.d)) return kUnsupported;
@@ -333,10 +368,10 @@ int inner_fused(const TTDesc& A, const TTDesc& B, double* out_dev, void* ws, siz
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-        if (cudaFuncSetAttribute(inner_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFusedSmem)) !=
+        if (cudaFuncSetAttribute(inner_sweep_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFusedSmem)) !=
             cudaSuccess)
             coop = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, inner_sweep_kernel<false>, FS_NT, kFusedSmem) !=
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, inner_sweep_kernel<false, false>, FS_NT, kFusedSmem) !=
             cudaSuccess)
             max_blocks = 0;
         cudaGetLastError();
@@ -364,23 +399,28 @@ int inner_fused(const TTDesc& A, const TTDesc& B, double* out_dev, void* ws, siz
     sp.P = P;
     sp.out = out_dev;
     sp.barrier = barrier;
+    sp.ready = ready_dev;
+    sp.fail = fail_dev;
     static long long* timing_dev = nullptr;
     static const bool sweep_timing = getenv("TTB_SWEEP_TIMING") != nullptr;
     if (sweep_timing && !timing_dev) cudaMalloc(&timing_dev, 64);
     sp.timing = sweep_timing ? timing_dev : nullptr;
     void* args[] = {&sp};
     const int slot = profile_begin(stream);
-    if (sweep_timing) {
+    void* kern = reinterpret_cast<void*>(inner_sweep_kernel<false, false>);
+    if (sweep_timing || ready_dev != nullptr) {
+        kern = ready_dev != nullptr ? reinterpret_cast<void*>(inner_sweep_kernel<false, true>)
+                                    : reinterpret_cast<void*>(inner_sweep_kernel<true, false>);
         static bool tconf = false;
         if (!tconf) {
-            TTB_CHECK_CUDA(cudaFuncSetAttribute(inner_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            TTB_CHECK_CUDA(cudaFuncSetAttribute(inner_sweep_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                int(kFusedSmem)));
+            TTB_CHECK_CUDA(cudaFuncSetAttribute(inner_sweep_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 int(kFusedSmem)));
             tconf = true;
         }
     }
-    TTB_CHECK_CUDA(cudaLaunchCooperativeKernel(sweep_timing ? reinterpret_cast<void*>(inner_sweep_kernel<true>)
-                                                            : reinterpret_cast<void*>(inner_sweep_kernel<false>),
-                                               dim3(num_sms()), dim3(FS_NT), args, kFusedSmem, stream));
+    TTB_CHECK_CUDA(cudaLaunchCooperativeKernel(kern, dim3(num_sms()), dim3(FS_NT), args, kFusedSmem, stream));
     ++g_launch_count;
     profile_end(slot, pl.flops, stream);
     if (sweep_timing) {

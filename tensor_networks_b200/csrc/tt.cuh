@@ -27,7 +27,15 @@ int inner(const TTDesc& a, const TTDesc& b, double* out_dev, void* ws, size_t ws
 // persistent fused sweep (inner_fused.cu); kUnsupported when the shapes do not qualify
 size_t inner_fused_workspace_bytes(const TTDesc& a, const TTDesc& b);
 int inner_fused(const TTDesc& a, const TTDesc& b, double* out_dev, void* ws, size_t ws_bytes,
-                cudaStream_t stream);
+                cudaStream_t stream, const int* ready_dev = nullptr, int* fail_dev = nullptr);
+
+// <A, B> of two trains whose cores still sit in (pinned) HOST memory: the cores are copied to the device
+// buffers of `a` / `b` on `copy_stream` while the persistent sweep kernel already runs on `stream` and
+// waits, core by core, for the data (per-core ready flags set by the copy stream).  Falls back to
+// copy-then-compute when the fused kernel does not apply.  The result is complete when `stream` is.
+size_t inner_streamed_workspace_bytes(const TTDesc& a, const TTDesc& b);
+int inner_streamed(const TTDesc& a, const TTDesc& b, const double* const* a_host, const double* const* b_host,
+                   double* out_dev, void* ws, size_t ws_bytes, cudaStream_t stream, cudaStream_t copy_stream);
 
 // --- dense contraction of a chain (inner.cu) ---
 int tt_to_dense(const TTDesc& a, double* out_dev, void* ws, size_t ws_bytes, cudaStream_t stream);

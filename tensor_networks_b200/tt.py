@@ -41,6 +41,9 @@ def workspace(nbytes: int, device: torch.device, slot: str = "main") -> torch.Te
     return buf
 
 
+_COPY_STREAM = None  # side stream of the streamed (copy-overlapped) inner product
+
+
 def _stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -246,6 +249,47 @@ class TensorTrain:
         return TensorTrain(out)
 
     # ------------------------------------------------------------------ hot path
+    @staticmethod
+    def inner_streamed(host_a: Sequence[torch.Tensor], host_b: Sequence[torch.Tensor],
+                       dev_a: Optional["TensorTrain"] = None, dev_b: Optional["TensorTrain"] = None) -> torch.Tensor:
+        """<A, B> for two trains whose cores are PINNED HOST tensors (3-d float64, unit boundary bonds).
+
+        The host->device copies run on a side stream (copy engines) while the persistent sweep kernel
+        already runs and waits, core by core, for the data, so the transfer overlaps the contraction
+        (`ttb_inner_streamed_f64`).  `dev_a` / `dev_b` may supply device trains of the same shapes to
+        receive the copies (re-used across calls); otherwise they are allocated.  Returns a 0-d CUDA
+        tensor; asynchronous with respect to the host like `inner_dev`."""
+        import ctypes
+
+        _require_cuda()
+        L = _lib.lib()
+        for h in list(host_a) + list(host_b):
+            if h.dtype != torch.float64 or h.dim() != 3 or h.is_cuda or not h.is_pinned() or not h.is_contiguous():
+                raise ValueError("inner_streamed needs contiguous pinned host float64 cores of shape (r, n, r')")
+        if dev_a is None:
+            dev_a = TensorTrain([torch.empty(h.shape, dtype=torch.float64, device="cuda") for h in host_a])
+        if dev_b is None:
+            dev_b = TensorTrain([torch.empty(h.shape, dtype=torch.float64, device="cuda") for h in host_b])
+        if [tuple(c.shape) for c in dev_a.cores] != [tuple(h.shape) for h in host_a] or \
+                [tuple(c.shape) for c in dev_b.cores] != [tuple(h.shape) for h in host_b]:
+            raise AssertionError("inner_streamed: device trains do not match the host cores")
+        if dev_a.shape() != dev_b.shape():
+            raise AssertionError("inner: free indices (mode sizes) differ")
+        da, db = dev_a.descriptor(), dev_b.descriptor()
+        d = dev_a.d
+        pa = (ctypes.c_void_p * d)(*[int(h.data_ptr()) for h in host_a])
+        pb = (ctypes.c_void_p * d)(*[int(h.data_ptr()) for h in host_b])
+        ws = workspace(L.ttb_inner_streamed_workspace_bytes(da.ref(), db.ref()), dev_a.device)
+        out = torch.empty((), dtype=torch.float64, device=dev_a.device)
+        global _COPY_STREAM
+        if _COPY_STREAM is None:
+            _COPY_STREAM = torch.cuda.Stream()
+        check(L.ttb_inner_streamed_f64(da.ref(), db.ref(), pa, pb, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       _stream_ptr(), _COPY_STREAM.cuda_stream))
+        # the device trains are written by the copy stream: keep them alive until the compute stream is done
+        out._ttb_keepalive = (dev_a, dev_b, host_a, host_b)
+        return out
+
     def inner_dev(self, other: "TensorTrain", out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """<self, other> as a 0-d CUDA tensor; no host synchronisation."""
         L = _lib.lib()
