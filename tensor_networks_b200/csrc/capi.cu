@@ -198,6 +198,7 @@ int ttb_delta_svd_f64(const double* data, int64_t m, int64_t n, double delta, in
                       void* workspace, size_t workspace_bytes, void* stream) {
     ttb::TruncSvdInfo info{};
     const double abs_tol = 0.0;  // full-accuracy SVD for the stand-alone entry point
+    ttb::trunc_svd_reset_heuristics();
     const int rc = ttb::trunc_svd(const_cast<double*>(data), m, n, delta, with_normalizing != 0, max_rank, abs_tol,
                                   /*inplace=*/false, u_out, svt_out,
                                   s_out, &info, workspace, workspace_bytes, as_stream(stream));

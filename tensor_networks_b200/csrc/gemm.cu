@@ -29,6 +29,8 @@ struct GemmProfile {
 } g_prof;
 }  // namespace
 
+bool gemm_profile_active() { return g_prof.enabled; }
+
 int gemm_profile_enable(int enable) {
     g_prof.enabled = enable != 0;
     if (enable) {

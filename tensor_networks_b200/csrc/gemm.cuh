@@ -50,6 +50,7 @@ int gemm(const GemmArgs& args, void* ws, size_t ws_bytes, cudaStream_t stream);
 // Per-launch CUDA-event timing of the dgemm kernels only (not the split-K reduce):
 // enable(1) resets the counters, read() synchronises the recorded events.
 int gemm_profile_enable(int enable);
+bool gemm_profile_active();  // true while per-launch event timing is on (stream capture must be avoided)
 int gemm_profile_read(double* total_ms, double* total_flops, unsigned long long* launches);
 
 int profile_begin(cudaStream_t stream);

@@ -807,13 +807,40 @@ struct OrthDecision {
 struct OrthPlan {
     std::vector<OrthDecision> seq;
     bool valid = false;
+    size_t version = 0;  // bumped by every recording run (a captured graph of an older version is stale)
 };
+// A replayed plan is a fixed launch sequence: once the same call signature has been seen twice it is
+// captured into a CUDA graph (on a staging copy of the input, so that the node arguments do not depend
+// on the caller's core pointer) and later calls cost one graph launch instead of ~50 kernel launches.
+struct OrthGraph {
+    cudaGraphExec_t exec = nullptr;
+    double* R = nullptr;
+    int64_t ldr = 0;
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    double tol = 0.0;
+    size_t version = 0;
+    int64_t rank = 0;
+    unsigned long long launches = 0;
+    int hits = 0;
+};
+
+__global__ void __launch_bounds__(256) copy_back_unless_aborted_kernel(double* __restrict__ dst, int64_t ldd,
+                                                                       const double* __restrict__ src, int64_t cols,
+                                                                       const int* __restrict__ abort_flag) {
+    if (*abort_flag) return;
+    const int64_t r = blockIdx.y;
+    const double* s = src + r * cols;
+    double* d = dst + r * ldd;
+    for (int64_t j = int64_t(blockIdx.x) * 1024 + threadIdx.x; j < min(cols, (int64_t(blockIdx.x) + 1) * 1024); j += 256)
+        d[j] = s[j];
+}
 constexpr int kSpecFailed = 1000;  // internal status: the replayed plan was contradicted by the data
 }  // namespace
 
 static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t ldr, void* ws,
                           size_t ws_bytes, cudaStream_t stream, double deflate_tol, int64_t* rank_out,
-                          OrthPlan* plan, bool replay) {
+                          OrthPlan* plan, bool replay, bool capturing = false) {
     TTB_REQUIRE(M && R, "orth_rows: null pointer");
     TTB_REQUIRE(c >= 1 && m >= 1 && ldm >= m && ldr >= c, "orth_rows: bad extents");
     const OrthLayout L = orth_layout(c, m);
@@ -844,6 +871,7 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
     if (plan && !replay) {
         plan->seq.clear();
         plan->valid = true;
+        ++plan->version;
     }
     void* gws = W.base + W.off;
     const size_t gws_bytes = ws_bytes - W.off;
@@ -1155,6 +1183,7 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
     if (rank_out) *rank_out = jq;
     if (replay) {
         if (plan_pos != plan->seq.size()) return kSpecFailed;
+        if (capturing) return kOk;  // the caller reads the abort flag after launching the graph
         TTB_CHECK_CUDA(cudaMemcpyAsync(host.flag, abort_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
         TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
         int aborted;
@@ -1187,6 +1216,71 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
         W.take<double>(L.bulk); W.take<double>(L.bulk_nrm); W.take<double>(L.bulk_nrm);
         double* backup = W.take<double>(L.backup);
         TTB_REQUIRE(backup != nullptr, "orth_rows: backup carve failed");
+        // same carve as orth_rows_impl: flag is the 8-word slot after the two norm buffers
+        int* abort_flag = nullptr;
+        {
+            Workspace W2(ws, ws_bytes);
+            W2.take<double>(L.cbuf); W2.take<double>(L.rp); W2.take<double>(L.rd); W2.take<double>(L.rd);
+            W2.take<double>(L.nrm); W2.take<double>(L.nrm);
+            abort_flag = reinterpret_cast<int*>(W2.take<unsigned long long>(8) + 4);
+        }
+        static const bool graph_enabled = [] {
+            const char* e = getenv("TTB_QR_GRAPH");
+            return e == nullptr || e[0] != '0';
+        }();
+        if (graph_enabled && !debug && !prof_enabled() && !gemm_profile_active()) {
+            static std::map<std::tuple<int64_t, int64_t, bool>, OrthGraph> graphs;
+            static cudaStream_t cap_stream = nullptr;
+            OrthGraph& G = graphs[std::make_tuple(c, m, deflate_tol > 0.0)];
+            const bool same = G.R == R && G.ldr == ldr && G.ws == ws && G.ws_bytes == ws_bytes && G.tol == deflate_tol &&
+                              G.version == plan.version;
+            if (!same) {
+                if (G.exec) cudaGraphExecDestroy(G.exec);
+                G = OrthGraph{};
+                G.R = R; G.ldr = ldr; G.ws = ws; G.ws_bytes = ws_bytes; G.tol = deflate_tol; G.version = plan.version;
+            }
+            ++G.hits;
+            if (!G.exec && G.hits == 2) {
+                if (!cap_stream) TTB_CHECK_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+                const unsigned long long before = g_launch_count;
+                int64_t rk = 0;
+                int rc = kCudaError;
+                cudaGraph_t graph = nullptr;
+                if (cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                    rc = orth_rows_impl(backup, c, m, m, R, ldr, ws, ws_bytes, cap_stream, deflate_tol, &rk, &plan, true, true);
+                    if (cudaStreamEndCapture(cap_stream, &graph) != cudaSuccess) rc = kCudaError;
+                }
+                G.launches = g_launch_count - before;
+                g_launch_count = before;  // captured, not executed
+                if (rc == kOk && graph != nullptr && cudaGraphInstantiate(&G.exec, graph, 0) == cudaSuccess) {
+                    G.rank = rk;
+                } else {
+                    G.exec = nullptr;
+                    cudaGetLastError();
+                }
+                if (graph) cudaGraphDestroy(graph);
+            }
+            if (G.exec) {
+                OrthHost host;
+                TTB_PROPAGATE(orth_host(&host));
+                TTB_CHECK_CUDA(cudaMemcpy2DAsync(backup, size_t(m) * 8, M, size_t(ldm) * 8, size_t(m) * 8, size_t(c),
+                                                 cudaMemcpyDeviceToDevice, stream));
+                TTB_CHECK_CUDA(cudaGraphLaunch(G.exec, stream));
+                dim3 cgrid(unsigned(ceil_div<int64_t>(m, 1024)), unsigned(c));
+                copy_back_unless_aborted_kernel<<<cgrid, 256, 0, stream>>>(M, ldm, backup, m, abort_flag);
+                TTB_CHECK_CUDA(cudaMemcpyAsync(host.flag, abort_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
+                g_launch_count += G.launches + 1;
+                int aborted;
+                memcpy(&aborted, host.flag, sizeof(int));
+                if (!aborted) {
+                    if (rank_out) *rank_out = G.rank;
+                    return kOk;
+                }
+                // contradicted: M is untouched (the graph worked on the staging copy) -- record afresh
+                return orth_rows_impl(M, c, m, ldm, R, ldr, ws, ws_bytes, stream, deflate_tol, rank_out, &plan, false);
+            }
+        }
         TTB_CHECK_CUDA(cudaMemcpy2DAsync(backup, size_t(m) * 8, M, size_t(ldm) * 8, size_t(m) * 8, size_t(c),
                                          cudaMemcpyDeviceToDevice, stream));
         const int rc = orth_rows_impl(M, c, m, ldm, R, ldr, ws, ws_bytes, stream, deflate_tol, rank_out, &plan, true);

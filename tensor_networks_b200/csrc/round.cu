@@ -51,6 +51,7 @@ struct PhaseTimer {
     }
 };
 double g_t_qr = 0, g_t_jac = 0, g_t_rest = 0, g_t_rq = 0, g_t_push = 0;
+int g_cert_skip = 0, g_cert_backoff = 0;  // certificate back-off (see trunc_svd)
 
 __global__ void transpose_kernel(const double* __restrict__ in, int64_t rows, int64_t cols, int64_t ldi,
                                  double* __restrict__ out, int64_t ldo) {
@@ -127,6 +128,8 @@ size_t trunc_svd_workspace_bytes(int64_t m, int64_t c, bool inplace) {
     return trunc_svd_required(m, c, inplace) + kGemmWsCap;
 }
 
+void trunc_svd_reset_heuristics() { g_cert_skip = g_cert_backoff = 0; }
+
 int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizing, int max_rank,
               double jacobi_abs_tol, bool inplace, double* U_out, double* SVt_out, double* sigma_out,
               TruncSvdInfo* res, void* ws, size_t ws_bytes, cudaStream_t stream, double deflate_tol) {
@@ -190,8 +193,16 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
         const char* e = getenv("TTB_SVD_CERT");
         return e == nullptr || e[0] != '0';
     }();
-    if (cert_enabled && path == kPathTall && p == c && sigma_out == nullptr && U_out != big &&
-        tri_inv_fro_supported(p) && (max_rank <= 0 || max_rank >= p)) {
+    // A failed certificate costs one sequential triangular inversion for nothing; after a failure the
+    // next attempts of the same sweep are skipped with exponential back-off (state reset per sweep by
+    // trunc_svd_reset_heuristics, so a call's result never depends on earlier calls).
+    bool try_cert = cert_enabled && path == kPathTall && p == c && sigma_out == nullptr && U_out != big &&
+                    tri_inv_fro_supported(p) && (max_rank <= 0 || max_rank >= p);
+    if (try_cert && g_cert_skip > 0) {
+        --g_cert_skip;
+        try_cert = false;
+    }
+    if (try_cert) {
         { ProfScope ps_("svd.certificate", stream); TTB_PROPAGATE(tri_inv_fro(Rm, p, c, info, stream)); }
         TTB_CHECK_CUDA(cudaMemcpyAsync(hw.info, info, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
         TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
@@ -205,11 +216,14 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
             res->sweeps = 0;
             res->converged = true;
             res->certified = true;
+            g_cert_backoff = 0;
             TTB_CHECK_CUDA(cudaMemcpyAsync(SVt_out, Rm, size_t(p) * c * 8, cudaMemcpyDeviceToDevice, stream));
             { ProfScope ps_("svd.transpose", stream); TTB_PROPAGATE(transpose(big, c, m, m, U_out, c, stream)); }
             g_t_rest += pt.tick();
             return kOk;
         }
+        g_cert_backoff = std::min(64, std::max(1, 2 * g_cert_backoff));
+        g_cert_skip = g_cert_backoff;
     }
     int sweeps = 0;
     // rows below 1e-3 delta are discarded whatever happens to them (their total energy is
@@ -379,6 +393,7 @@ int round_tt(const TTDesc& t, double eps, int max_rank, int64_t* ranks_out, doub
     }();
     PhaseTimer pt(stream);
     g_t_qr = g_t_jac = g_t_rest = g_t_rq = g_t_push = 0;
+    trunc_svd_reset_heuristics();
     for (int k = d - 1; k >= 1; --k) {
         int64_t c_new = r[k];
         TTB_PROPAGATE(right_orth_step(t.core[k], r[k], t.n[k] * r[k + 1], t.core[k - 1], r[k - 1] * t.n[k - 1],

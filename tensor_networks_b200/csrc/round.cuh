@@ -43,6 +43,9 @@ struct RoundStats {
 size_t trunc_svd_workspace_bytes(int64_t m, int64_t c, bool inplace);
 // deflate_tol > 0: rows / columns that are numerically dependent at that relative level are dropped
 // by the orthogonalisation (see orth_rows) before the small factor reaches the Jacobi kernel.
+// forget the certificate back-off state (call at the start of every sweep / standalone SVD)
+void trunc_svd_reset_heuristics();
+
 int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizing, int max_rank,
               double jacobi_abs_tol, bool inplace, double* U_out, double* SVt_out, double* sigma_out,
               TruncSvdInfo* res, void* ws, size_t ws_bytes, cudaStream_t stream, double deflate_tol = 0.0);

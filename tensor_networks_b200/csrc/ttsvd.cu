@@ -118,6 +118,7 @@ int ttsvd(const double* dense, int d, const int64_t* shape, double eps, int max_
     int64_t r = 1;
     int64_t c = int64_t(N);
     size_t off = 0;
+    trunc_svd_reset_heuristics();
     for (int k = 0; k < d - 1; ++k) {
         const int64_t m = r * shape[k];
         c /= shape[k];

@@ -113,6 +113,40 @@ def test_round_full_rank_is_identity():
     assert abs(float(z.inner(x)) / (nx * nz) - 1.0) < 1e-12
 
 
+@pytest.mark.parametrize("r", [17, 33, 64, 65, 100, 128])
+def test_round_certificate_sizes(r):
+    """The no-truncation certificate (blocked triangular inverse, padded to 128) at bond ranks on
+    both sides of its 32- and 64-wide block boundaries."""
+    from tensor_networks_b200 import TensorTrain
+
+    x = TensorTrain.rand([130, 5, 5, 130], [r, r, r], seed=300 + r)
+    ref, _ = orc.svd_round([c.copy() for c in x.to_cores()], 1e-12)
+    z = x.clone().round(1e-12)
+    assert z.ranks() == orc.ranks_of(ref)
+    assert z.ranks() == [r, r, r]
+    assert z.last_round["svds_certified"] >= 1
+    nx, nz = x.norm(), z.norm()
+    assert abs(nx - nz) <= 1e-12 * nx
+    assert abs(float(z.inner(x)) / (nx * nz) - 1.0) < 1e-12
+
+
+def test_round_certificate_rejects_small_sigma():
+    """Full numerical rank but sigma_min below delta: the certificate must NOT fire and the SVD truncates."""
+    from tensor_networks_b200 import TensorTrain
+
+    rng = np.random.default_rng(5)
+    shape = [40, 6, 40]
+    big = orc.rand_tt(shape, [20, 20], rng)
+    small = orc.rand_tt(shape, [12, 12], rng)
+    small[0] = small[0] * 1e-7
+    y = orc.tt_add(big, small)
+    ref, _ = orc.svd_round(copy.deepcopy(y), 1e-4)
+    tt = TensorTrain.from_cores(copy.deepcopy(y)).round(1e-4)
+    assert tt.ranks() == orc.ranks_of(ref)
+    assert tt.ranks() == [20, 20]
+    assert tt.last_round["svds_certified"] == 0
+
+
 def test_round_partial_deflation():
     """X (+) X (+) noise-free third term of different rank: some panels deflate, some do not."""
     from tensor_networks_b200 import TensorTrain
