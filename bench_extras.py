@@ -118,6 +118,60 @@ def run_round_generic(d=20, n=64, parts=4, r_part=32, eps=1e-5, reps=2):
     }
 
 
+def run_gramsvd(d=20, n=64, parts=4, r_part=32, eps=1e-5, reps=2, cpu_sample_d=5):
+    """Gram-SVD rounding on the generic-rounding workload: same input as
+    run_round_generic, so the two rounding backends can be compared directly."""
+    y = None
+    for j in range(parts):
+        t = TensorTrain.rand([n] * d, [r_part] * (d - 1), seed=5001 + j)
+        t.cores[0].mul_(10.0 ** (-3 * j))
+        y = t if y is None else y + t
+    in_ranks = y.ranks()
+    z = y.clone().gramsvd_round(eps)
+    out_ranks = z.ranks()
+    times = []
+    L = _lib.lib()
+    for _ in range(reps):
+        z = y.clone()
+        torch.cuda.synchronize()
+        l0 = L.ttb_launch_count()
+        t0 = time.perf_counter()
+        z.gramsvd_round(eps)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+        launches = int(L.ttb_launch_count() - l0)
+    ms = 1e3 * min(times)
+    ny, nz = y.norm(), z.norm()
+    err = float(np.sqrt(max(ny * ny + nz * nz - 2.0 * float(z.inner(y)), 0.0)) / ny)
+    res = {
+        "workload": f"tt_gramsvd_round generic d={d} n={n} bond {in_ranks[len(in_ranks) // 2]} decaying spectrum eps={eps}",
+        "ms": ms,
+        "ranks_in": [in_ranks[0], in_ranks[len(in_ranks) // 2], in_ranks[-1]],
+        "ranks_out": [out_ranks[0], out_ranks[len(out_ranks) // 2], out_ranks[-1]],
+        "rel_err": err,
+        "launches": launches,
+    }
+    if cpu_sample_d:
+        ds = cpu_sample_d
+        rng = np.random.default_rng(5001)
+        ys = None
+        for j in range(parts):
+            t = orc.rand_tt([n] * ds, [r_part] * (ds - 1), rng)
+            t[0] = t[0] * 10.0 ** (-3 * j)
+            ys = t if ys is None else orc.tt_add(ys, t)
+        t0 = time.perf_counter()
+        orc.gramsvd_round(ys, eps)
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {
+            "value": 1e3 * dt / (ds - 1),
+            "unit": "ms per bond",
+            "kind": "port",
+            "sample": f"numpy oracle gramsvd_round on a d={ds} chain of the same n, bonds; {dt:.2f} s",
+        }
+        res["ms_per_bond"] = ms / (d - 1)
+    return res
+
+
 def run_ttsvd(n=16, d=7, ranks=(16, 64, 64, 64, 64, 16), eps=1e-10, reps=3):
     """configs[3]: TT-SVD of a dense n^d tensor built from a random TT with the given ranks."""
     x = TensorTrain.rand([n] * d, list(ranks), seed=3001)
@@ -249,6 +303,7 @@ def run_all():
     out = {}
     out["round_cfg3"] = run_round()
     out["round_generic"] = run_round_generic()
+    out["gramsvd_generic"] = run_gramsvd()
     out["ttsvd_cfg4"] = run_ttsvd()
     out["batched_cfg5"] = run_batched()
     out["batched_cfg5"]["cpu_baseline"] = cpu_batched_sample()

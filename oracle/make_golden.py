@@ -7,7 +7,7 @@ Run in the build container only (needs /root/reference):
 Every fixture stores the seeded INPUT cores and what the unmodified reference
 functions returned for them (through the import shim in `oracle/refshim.py`):
 `TensorNetwork.inner` / `norm` (pytens/algs.py:585-594), `tt_right_orth`
-(:1654-1704), `tt_svd_round` (:1841-1903), `delta_svd` (pytens/utils.py:19-100)
+(:1654-1704), `tt_svd_round` (:1841-1903), `tt_gramsvd_round` (:1771-1838), `delta_svd` (pytens/utils.py:19-100)
 and the TT-SVD composition `TensorNetwork.svd` + `merge` (:633-702, :735-761).
 The fixtures are what pins `oracle/tt_oracle.py` (tests/test_oracle.py) and the
 CUDA path (tests/test_*gpu*.py) on the GPU box, where the reference is absent.
@@ -27,7 +27,7 @@ import refshim  # noqa: E402
 
 pt = refshim.load_reference()
 from pytens import Index, SVDConfig, Tensor, TensorNetwork  # noqa: E402
-from pytens.algs import tt_right_orth, tt_svd_round  # noqa: E402
+from pytens.algs import tt_gramsvd_round, tt_right_orth, tt_svd_round  # noqa: E402
 from pytens.utils import delta_svd  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
@@ -246,10 +246,53 @@ def gen_ttsvd():
         print("ttsvd", i, shape, "->", ranks_out, err)
 
 
+def gen_gramsvd():
+    cases = [
+        # (seed, shape, ranks of X, eps, mode); first case = tests/main_test.py:245-262
+        (61, [5, 10, 20], [2, 2], 1e-5, "double"),
+        (62, [6] * 6, [3, 5, 5, 4, 2], 1e-5, "double"),
+        (63, [8] * 5, [6, 6, 6, 6], 1e-3, "noise"),
+        (64, [8] * 8, [8] * 7, 1e-2, "decay"),
+        (65, [7, 5], [4], 1e-6, "double"),
+        (66, [4] * 10, [4] * 9, 1e-6, "double"),
+    ]
+    for i, (seed, shape, ranks, eps, mode) in enumerate(cases):
+        np.random.seed(seed)
+        x = scaled_rand_tt(shape, ranks, True)
+        if mode == "double":
+            y = x + x
+        elif mode == "noise":
+            z = scaled_rand_tt(shape, ranks, True)
+            z.scale(1e-5)
+            y = x + z
+        else:
+            y = x
+            for j in range(1, 4):
+                z = scaled_rand_tt(shape, [2] * (len(shape) - 1), True)
+                z.scale(10.0 ** (-2 * j))
+                y = y + z
+        dense = y.contract().value
+        d = dict(shape=np.array(shape), eps=np.array(eps))
+        d.update(pack("in", ref_cores(y)))
+        out = tt_gramsvd_round(copy.deepcopy(y), eps)
+        oc = ref_cores(out)
+        ranks_out = [c.shape[-1] for c in oc[:-1]]
+        dense_out = out.contract().value
+        err = np.linalg.norm(dense_out - dense) / np.linalg.norm(dense)
+        d.update(pack("out", oc))
+        d.update(ranks_out=np.array(ranks_out), rel_err=np.array(err), norm_in=np.array(np.linalg.norm(dense)))
+        np.savez(os.path.join(OUT, f"gramsvd_{i}.npz"), **d)
+        print("gramsvd", i, [c.shape[-1] for c in ref_cores(y)[:-1]], "->", ranks_out, err)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "gramsvd":  # add the Gram-SVD fixtures without touching the others
+        gen_gramsvd()
+        sys.exit(0)
     gen_inner()
     gen_right_orth()
     gen_round()
     gen_delta_svd()
     gen_ttsvd()
+    gen_gramsvd()
     print("fixtures written to", OUT)

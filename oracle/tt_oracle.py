@@ -253,6 +253,78 @@ def svd_round(cores: Cores, eps: float) -> Tuple[Cores, float]:
 
 
 # ----------------------------------------------------------------------------
+# Gram-SVD rounding
+# ----------------------------------------------------------------------------
+def eps_to_rank(s: np.ndarray, eps: float) -> int:
+    """Rank kept by a truncated SVD with tail energy <= eps (eps_to_rank, pytens/algs.py:1707-1717)."""
+    tail = np.sqrt(np.cumsum(np.square(s[::-1])))[::-1] <= eps
+    res = int(np.argmax(tail))
+    if res == 0 and not tail[0]:
+        return int(s.shape[0])
+    if res == 0 and tail[0]:
+        return 1
+    return res
+
+
+def round_sqrt_eigs(eig: np.ndarray) -> np.ndarray:
+    """sqrt(|eig|) rounded to the decimal position of 1e-8 of the largest value
+    (pytens/algs.py:1729-1739): square roots of noise-level eigenvalues become exactly 0."""
+    pos_tol = 1e-15
+    e12 = np.sqrt(np.abs(eig))
+    threshold = np.ceil(np.log10(np.max(e12) * 1e-8 + pos_tol))
+    return np.round(e12, min(-int(threshold), 16))
+
+
+def gram_eig_and_svd(gl: np.ndarray, gr: np.ndarray, delta: float) -> Tuple[np.ndarray, np.ndarray]:
+    """Low-rank factors of one bond from its left / right Gram matrices
+    (gram_eig_and_svd, pytens/algs.py:1720-1768)."""
+    eigl, vl = np.linalg.eigh(gl)
+    eigr, vr = np.linalg.eigh(gr)
+    eigl12 = round_sqrt_eigs(eigl)
+    eigr12 = round_sqrt_eigs(eigr)
+    eiglm12 = np.zeros_like(eigl12)
+    eigrm12 = np.zeros_like(eigr12)
+    eiglm12[eigl12 != 0] = 1.0 / eigl12[eigl12 != 0]
+    eigrm12[eigr12 != 0] = 1.0 / eigr12[eigr12 != 0]
+    tmp = (eigl12[:, None] * vl.T) @ (vr * eigr12[None, :])
+    u, s, v = np.linalg.svd(tmp)
+    rk = min(tmp.shape[0], tmp.shape[1], eps_to_rank(s, delta))
+    curr = vl @ (eiglm12[:, None] * u[:, :rk])
+    nxt = (s[:rk, None] * v[:rk] * eigrm12[None, :]) @ vr.T
+    return curr, nxt
+
+
+def gramsvd_round(cores: Cores, eps: float) -> Tuple[Cores, float]:
+    """Gram-SVD TT rounding (tt_gramsvd_round, pytens/algs.py:1771-1838): right Gram matrices by a
+    right-to-left sweep (:1808-1815), delta = eps ||X|| / sqrt(d-1) from the last of them (:1817-1818),
+    then per bond the left Gram of the updated core, gram_eig_and_svd, and the two core updates
+    (:1822-1836).  Mutates and returns `cores` (3-d form) plus the absolute delta."""
+    d = len(cores)
+    assert d >= 2
+    last = cores[d - 1].reshape(cores[d - 1].shape[0], -1)
+    gr = [last @ last.T]
+    for i in range(d - 2, -1, -1):
+        c = cores[i]
+        r0, n, r1 = c.shape
+        tmp = (c.reshape(-1, r1) @ gr[-1]).reshape(r0, n * r1)
+        gr.append(tmp @ c.reshape(r0, n * r1).T)
+    norm = np.sqrt(gr[-1])[0, 0]
+    delta = eps * norm / (d - 1) ** 0.5
+    gr = gr[::-1]
+    for i in range(d - 1):
+        c = cores[i]
+        r0, n, r1 = c.shape
+        m2 = c.reshape(-1, r1)
+        gl = m2.T @ m2
+        curr, nxt = gram_eig_and_svd(gl, gr[i + 1], delta)
+        rk = curr.shape[1]
+        cores[i] = (m2 @ curr).reshape(r0, n, rk)
+        c1 = cores[i + 1]
+        cores[i + 1] = (nxt @ c1.reshape(c1.shape[0], -1)).reshape(rk, c1.shape[1], c1.shape[2])
+    return cores, float(delta)
+
+
+# ----------------------------------------------------------------------------
 # TT-SVD of a dense tensor
 # ----------------------------------------------------------------------------
 def tt_svd(dense: np.ndarray, eps: float) -> Tuple[Cores, float]:

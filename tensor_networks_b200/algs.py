@@ -9,6 +9,8 @@ library through `TensorTrain` (ctypes -> libttb200.so):
     TensorNetwork.inner / norm / scale / rand_tt     :585-594, :578-583, :1180-1218
     tt_right_orth(tn, node)                          :1654-1704
     tt_svd_round(tn, eps)                            :1841-1903
+    tt_gramsvd_round(tn, eps), gram_eig_and_svd,
+    eps_to_rank (from .gramsvd)                      :1707-1838
     delta_svd (re-exported from .utils)              pytens/utils.py:19-100
     tt_svd(dense, eps)   [composition, no single reference function: SURVEY 3.3]
 
@@ -31,12 +33,13 @@ import numpy as np
 
 from .types import Index, IntOrStr, NodeName, SVDConfig  # noqa: F401
 from .utils import TruncSVD, delta_svd  # noqa: F401
+from .gramsvd import eps_to_rank, gram_eig_and_svd  # noqa: F401
 from .tt import TensorTrain
 from .solvers import TTOperator, gmres, ttop_apply, ttop_rank1  # noqa: F401  (device-resident TT-GMRES)
 
 __all__ = [
     "Index", "SVDConfig", "Tensor", "TensorNetwork", "TensorTrain", "TruncSVD",
-    "delta_svd", "tt_right_orth", "tt_svd_round", "tt_svd", "round",
+    "delta_svd", "tt_right_orth", "tt_svd_round", "tt_gramsvd_round", "eps_to_rank", "gram_eig_and_svd", "tt_svd", "round",
     "TTOperator", "ttop_rank1", "ttop_apply", "gmres",
 ]
 
@@ -270,6 +273,17 @@ def tt_svd_round(tn, eps: float):
     _tt_cores(tn)
     tt = TensorTrain.from_network(tn)
     tt.round(eps)
+    _write_back(tn, tt)
+    return tn
+
+
+def tt_gramsvd_round(tn, eps: float):
+    """Gram-SVD rounding of a TT, in place; returns the same object (pytens/algs.py:1771-1838)."""
+    from .gramsvd import gramsvd_round
+
+    _tt_cores(tn)
+    tt = TensorTrain.from_network(tn)
+    gramsvd_round(tt, eps)
     _write_back(tn, tt)
     return tn
 

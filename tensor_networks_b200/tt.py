@@ -375,6 +375,12 @@ class TensorTrain:
         }
         return self
 
+    def gramsvd_round(self, eps: float) -> "TensorTrain":
+        """Round in place by Gram SVD -- tt_gramsvd_round, pytens/algs.py:1771-1838 (see gramsvd.py)."""
+        from .gramsvd import gramsvd_round
+
+        return gramsvd_round(self, eps)
+
     def compact(self) -> "TensorTrain":
         """Re-own the cores (drop the slack left in the buffers by an in-place rounding)."""
         self.cores = [c.clone() for c in self.cores]

@@ -76,6 +76,32 @@ def test_round_matches_reference(path):
     assert delta > 0
 
 
+@pytest.mark.parametrize("path", golden_files("gramsvd"))
+def test_gramsvd_round_matches_reference(path):
+    """oracle.gramsvd_round against what the reference's tt_gramsvd_round returned (make_golden.py)."""
+    z = np.load(path)
+    cores = orc.as_cores3(load_cores(z, "in"))
+    dense = orc.to_dense(cores)
+    out, delta = orc.gramsvd_round(copy.deepcopy(cores), float(z["eps"]))
+    assert orc.ranks_of(out) == list(z["ranks_out"])
+    err = np.linalg.norm(orc.to_dense(out) - dense) / np.linalg.norm(dense)
+    # Gram-SVD is accurate to ~sqrt(machine eps) relative to ||X|| at best
+    assert abs(err - float(z["rel_err"])) <= 1e-8
+    ref = orc.as_cores3(load_cores(z, "out"))
+    for c, r in zip(out, ref):
+        assert c.shape == r.shape
+    assert np.allclose(orc.to_dense(out), orc.to_dense(ref), rtol=0, atol=1e-8 * np.linalg.norm(dense))
+    assert delta > 0
+
+
+def test_eps_to_rank_cases():
+    s = np.array([4.0, 2.0, 1.0, 0.5])
+    assert orc.eps_to_rank(s, 0.4) == 4          # nothing can go
+    assert orc.eps_to_rank(s, 0.5) == 3          # tail {0.5}
+    assert orc.eps_to_rank(s, 1.2) == 2          # tail {1, 0.5} = 1.118
+    assert orc.eps_to_rank(s, 100.0) == 1        # everything fits: rank clamps to 1
+
+
 @pytest.mark.parametrize("path", golden_files("delta_svd"))
 def test_delta_svd_matches_reference(path):
     z = np.load(path)
