@@ -632,21 +632,42 @@ __global__ void set_identity_small_kernel(double* Rd, int w) {
 // flag = min over v of nrm_out[v] / nrm_prev[v] (nrm_prev == nullptr: previous norms are 1,
 // the rows are an orthonormal Q from the last pass; a zero previous norm counts as ratio 0).
 // Positive doubles order like their bit patterns, so the min is an integer atomicMin.
-__global__ void __launch_bounds__(256) rownorm_kernel(const double* __restrict__ P, int64_t m, int64_t ld,
-                                                       const double* __restrict__ nrm_prev,
-                                                       double* __restrict__ nrm_out,
-                                                       unsigned long long* __restrict__ flag) {
+__global__ void __launch_bounds__(1024) rownorm_kernel(const double* __restrict__ P, int64_t m, int64_t ld,
+                                                        const double* __restrict__ nrm_prev,
+                                                        double* __restrict__ nrm_out,
+                                                        unsigned long long* __restrict__ flag) {
     const int v = blockIdx.x;
     const double* x = P + int64_t(v) * ld;
-    double s = 0.0;
-    for (int64_t i = threadIdx.x; i < m; i += blockDim.x) s = fma(x[i], x[i], s);
-    __shared__ double red[8];
+    // four independent accumulators over 16-byte loads (long rows: one CTA has to pull ~100 GB/s)
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const int nt = blockDim.x, tid = threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const double2* x2 = reinterpret_cast<const double2*>(x);
+        const int64_t m2 = m >> 1;
+        int64_t i = tid;
+        for (; i + 3 * int64_t(nt) < m2; i += 4 * int64_t(nt)) {
+            const double2 a = x2[i], b = x2[i + nt], c = x2[i + 2 * int64_t(nt)], d = x2[i + 3 * int64_t(nt)];
+            s0 = fma(a.x, a.x, s0); s1 = fma(a.y, a.y, s1);
+            s2 = fma(b.x, b.x, s2); s3 = fma(b.y, b.y, s3);
+            s0 = fma(c.x, c.x, s0); s1 = fma(c.y, c.y, s1);
+            s2 = fma(d.x, d.x, s2); s3 = fma(d.y, d.y, s3);
+        }
+        for (; i < m2; i += nt) {
+            const double2 a = x2[i];
+            s0 = fma(a.x, a.x, s0); s1 = fma(a.y, a.y, s1);
+        }
+        if ((m & 1) && tid == 0) s2 = fma(x[m - 1], x[m - 1], s2);
+    } else {
+        for (int64_t i = tid; i < m; i += nt) s0 = fma(x[i], x[i], s0);
+    }
+    double s = (s0 + s1) + (s2 + s3);
+    __shared__ double red[32];
     s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    if ((tid & 31) == 0) red[tid >> 5] = s;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         double t = 0.0;
-        for (int i = 0; i < 8; ++i) t += red[i];
+        for (int i = 0; i < (nt >> 5); ++i) t += red[i];
         const double nv = sqrt(t);
         nrm_out[v] = nv;
         if (flag) {
@@ -656,6 +677,9 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const double* __restrict__
         }
     }
 }
+
+// threads per CTA of rownorm_kernel: short rows keep 256, long rows need the loads of 1024 threads in flight
+static inline int rownorm_threads(int64_t m) { return m >= 32768 ? 1024 : 256; }
 
 // flag = min_v |Rp[v][v]| / nrm_prev[v]: the fraction of vector v that was left after projecting
 // out the previous panels and the earlier vectors of this panel.  nrm_prev == nullptr: the
@@ -909,7 +933,7 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
         int cur = 0;
         bool rd_ident = true;  // Rd[cur] is (implicitly) the identity until the first factor is accumulated
         if (jq > 0) {
-            rownorm_kernel<<<w, 256, 0, stream>>>(P, m, ldm, nullptr, nrm[0], nullptr);
+            rownorm_kernel<<<w, rownorm_threads(m), 0, stream>>>(P, m, ldm, nullptr, nrm[0], nullptr);
             ++g_launch_count;
         }
         // The strict conditioning bound protects the deflation test of LATER rows (see kIllMin); the last
@@ -1061,7 +1085,7 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
                 if (!bulk_done && rest_rows > wf && jq < m && size_t(rest_rows) * size_t(jq) <= L.bulk) {
                     bulk_done = true;
                     double* Arest = M + jc * ldm;
-                    rownorm_kernel<<<unsigned(rest_rows), 256, 0, stream>>>(Arest, m, ldm, nullptr, bnrm[0], nullptr);
+                    rownorm_kernel<<<unsigned(rest_rows), rownorm_threads(m), 0, stream>>>(Arest, m, ldm, nullptr, bnrm[0], nullptr);
                     ++g_launch_count;
                     {
                         ProfScope ps_("qr.bulk_deflate_gemms", stream);
@@ -1079,7 +1103,7 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
                         u.alpha = -1.0; u.beta = 1.0;
                         TTB_PROPAGATE(gemm(u, gws, gws_bytes, stream));
                     }
-                    rownorm_kernel<<<unsigned(rest_rows), 256, 0, stream>>>(Arest, m, ldm, nullptr, bnrm[1], nullptr);
+                    rownorm_kernel<<<unsigned(rest_rows), rownorm_threads(m), 0, stream>>>(Arest, m, ldm, nullptr, bnrm[1], nullptr);
                     int expect_bulk = -1;
                     if (replay) {
                         if (plan_pos >= plan->seq.size() || plan->seq[plan_pos].kind != 3) return kSpecFailed;
@@ -1121,7 +1145,7 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
         ++g_launch_count;
         int cur = 0;
         if (jq > 0) {
-            rownorm_kernel<<<w, 256, 0, stream>>>(P, m, ldm, nullptr, nrm[0], nullptr);
+            rownorm_kernel<<<w, rownorm_threads(m), 0, stream>>>(P, m, ldm, nullptr, nrm[0], nullptr);
             ++g_launch_count;
         }
         for (int pass = 1; pass <= kMaxPasses; ++pass) {
