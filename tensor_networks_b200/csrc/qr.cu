@@ -43,11 +43,14 @@ using namespace hh;
 
 constexpr int QF_W = 64;  // width of a fast (Cholesky-QR) panel
 // A panel is "benign" for Cholesky-QR2 when every vector keeps at least this fraction of its norm
-// against the earlier vectors of the panel (cond(panel) <~ sqrt(w) / kIllMin).  Deliberately strict:
-// with 5e-3 the factorisation itself is still fine, but the basis of a cond ~ 1e3 panel is only
-// accurate to eps cond^2, and the residuals of truly dependent later rows rise from 1e-14 to 1e-13 --
-// enough to defeat the deflation test (measured on the TT-SVD 16^7 case: 75 -> 113 ms).
+// against the earlier vectors of the panel (cond(panel) <~ sqrt(w) / bound).  With deflation the bound
+// follows the deflation tolerance (see fast_panel): the factorisation P = R^T Q of a cond ~ 1e3 panel
+// carries a backward error of ~ eps_mach cond ~ 1e-13, which lifts the residuals of truly dependent later
+// rows from 1e-14 to 1e-13; the tolerance must sit above that or the deflation test is defeated and the
+// rank grows by noise rows (measured on the TT-SVD 16^7 case: 5e-3 with tolerance 1e-13 -> 113 ms, with
+// tolerance 1e-12 -> 32 ms, against 52 ms for the strict bound that sends such panels to Householder TSQR).
 constexpr double kIllMin = 0.05;
+constexpr double kIllMinStrictFloor = 5e-3;
 constexpr double kIllMinRelaxed = 2e-3;
 constexpr int QF_P = QF_W + 1;
 
@@ -940,7 +943,14 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
         // panel of a call has no later rows, and without deflation nobody tests residuals at all: there
         // Cholesky-QR2 is used up to cond ~ 1e4 (first-pass defect eps cond^2 ~ 1e-8, removed by the second
         // pass) instead of falling back to the much slower Householder TSQR.
-        const double ill_min = (deflate_tol == 0.0 || jc + w >= c) ? kIllMinRelaxed : kIllMin;
+        static const double ill_env = [] {
+            const char* e = getenv("TTB_ILL_MIN");
+            return e ? atof(e) : 0.0;
+        }();
+        // with deflation: the backward error of Cholesky-QR2, ~ eps_mach sqrt(w) / ill_min, has to stay below
+        // the residual level the deflation test accepts (deflate_tol <= 1e-2 of the caller's eps)
+        const double ill_strict = ill_env > 0.0 ? ill_env : std::min(kIllMin, std::max(kIllMinStrictFloor, 1e-15 / std::max(deflate_tol, 1e-300)));
+        const double ill_min = (deflate_tol == 0.0 || jc + w >= c) ? kIllMinRelaxed : ill_strict;
         // replay: the outcome of this panel comes from the plan, nothing is read back
         OrthDecision planned{1, 1};
         if (replay) {

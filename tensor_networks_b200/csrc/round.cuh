@@ -1,5 +1,6 @@
 // TT rounding drivers; see round.cu.
 #pragma once
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tt.cuh"
@@ -12,8 +13,16 @@ namespace ttb {
 // m = 1e6), and never exceeds 1e-3 of the requested accuracy; 0 disables deflation.
 inline double deflation_tolerance(double eps, int64_t m) {
     if (!(eps > 0.0)) return 0.0;
-    const double base = 1e-13 * (m > 4096 ? __builtin_sqrt(double(m) / 4096.0) : 1.0);
-    return base < 1e-3 * eps ? base : 1e-3 * eps;
+    static const double cap = [] {
+        const char* e = getenv("TTB_DEFLATE_CAP");
+        return e ? atof(e) : 1e-2;
+    }();
+    static const double base0 = [] {
+        const char* e = getenv("TTB_DEFLATE_BASE");
+        return e ? atof(e) : 1e-13;
+    }();
+    const double base = base0 * (m > 4096 ? __builtin_sqrt(double(m) / 4096.0) : 1.0);
+    return base < cap * eps ? base : cap * eps;
 }
 
 struct TruncSvdInfo {

@@ -87,3 +87,27 @@ def test_ttsvd_medium_16_5():
     err = float((back - dense).norm() / dense.norm())
     assert err < 1e-10
     assert _left_orth_defect(tt) < 1e-12
+
+
+@pytest.mark.parametrize("eps", [1e-8, 1e-10, 1e-11, 1e-12])
+def test_ttsvd_ill_conditioned_leading_rows(eps):
+    """Exact-rank tensor whose leading unfolding rows are a SQUARE Gaussian mix (cond ~ 1e2-1e3): the
+    Cholesky-QR conditioning bound follows the deflation tolerance, so the same input goes through the
+    relaxed bound at loose eps and the strict bound / Householder path at tight eps.  Ranks must equal
+    the oracle's and the reconstruction error must stay in the 1e-10 parity class AND below eps-level.
+    (eps = 1e-13 puts the threshold inside the rounding noise of the earlier steps: the rank there is a
+    coin flip for any implementation, with or without deflation, and is not tested.)"""
+    from tensor_networks_b200 import TensorTrain
+
+    rng = np.random.default_rng(2024)
+    shape = [12] * 5
+    x = orc.rand_tt(shape, [12, 64, 64, 12], rng)
+    dense = orc.to_dense(x)
+    ref, _ = orc.tt_svd(dense, eps)
+    tt = TensorTrain.from_dense(dense, eps)
+    assert tt.ranks() == orc.ranks_of(ref) == [12, 64, 64, 12]
+    err = np.linalg.norm(tt.dense() - dense) / np.linalg.norm(dense)
+    err_ref = np.linalg.norm(orc.to_dense(ref) - dense) / np.linalg.norm(dense)
+    assert abs(err - err_ref) <= ERR_TOL
+    assert err <= max(eps, 5e-13)
+    assert _left_orth_defect(tt) < 1e-12
