@@ -259,34 +259,16 @@ constexpr int CH_NT = 256;
 //    max |E| <= 3e-8 the first-order factors L = I + strict_lower(E) + diag(E)/2 and
 //    L^{-1} = I - strict_lower(E) - diag(E)/2 are exact to O(|E|^2) <= 1e-15 and need no
 //    sequential step at all; otherwise the kernel falls through to the full factorisation.
-__global__ void __launch_bounds__(CH_NT) chol_panel_kernel(const double* __restrict__ G, int w,
-                                                           const double* __restrict__ nrm_prev,
-                                                           double* __restrict__ Rt, double* __restrict__ Linv,
-                                                           double* __restrict__ status, double deflate_tol,
-                                                           int near_identity, int expect, int dgks_check,
-                                                           int* __restrict__ abort_flag, double ill_min) {
-    extern __shared__ __align__(16) double chol_sm[];
-    double* A = chol_sm;                 // [QF_W][QF_P]
-    double* X = chol_sm + QF_W * QF_P;   // [QF_W][QF_P]
+// The factorisation proper, shared by chol_panel_kernel and the fused panel kernel.  On entry A holds G
+// (identity-padded beyond w, pitch QF_P) and the CTA is synchronised; on return (synchronised) A holds
+// L (lower triangle, zeros above), X holds L^{-1}, st[0..3] the status words described above, and the
+// (uniform) return value is 0 = factored, 1 = breakdown, 2 = deflated (nothing factored).
+__device__ __forceinline__ int chol_core(double* __restrict__ A, double* __restrict__ X, int w,
+                                         const double* __restrict__ nrm_prev, double deflate_tol,
+                                         int near_identity, double* __restrict__ st) {
     __shared__ double diag0[QF_W], rdiag[QF_W], emax_sh[CH_NT / 32];
     __shared__ int flag_sh;
     const int tid = threadIdx.x;
-    {
-        // all 16 loads of a thread in flight at once (a strided loop pays one DRAM latency per trip)
-        double g[QF_W * QF_W / CH_NT];
-#pragma unroll
-        for (int u = 0; u < QF_W * QF_W / CH_NT; ++u) {
-            const int idx = tid + u * CH_NT;
-            const int r = idx / QF_W, c = idx % QF_W;
-            g[u] = (r < w && c < w) ? G[r * w + c] : (r == c ? 1.0 : 0.0);  // identity padding
-        }
-#pragma unroll
-        for (int u = 0; u < QF_W * QF_W / CH_NT; ++u) {
-            const int idx = tid + u * CH_NT;
-            A[(idx / QF_W) * QF_P + idx % QF_W] = g[u];
-        }
-    }
-    __syncthreads();
     if (tid < QF_W) diag0[tid] = A[tid * QF_P + tid];
     __syncthreads();
     if (tid < 32) {
@@ -298,25 +280,19 @@ __global__ void __launch_bounds__(CH_NT) chol_panel_kernel(const double* __restr
             }
         r3 = warp_max(r3);
         if (tid == 0) {
-            status[3] = r3;
+            st[3] = r3;
             flag_sh = (deflate_tol > 0.0 && r3 <= deflate_tol) ? 1 : 0;
         }
     }
     __syncthreads();
-    // expect >= 0: the host replays a recorded plan without reading the status back (0 = the panel is
-    // factored, 1 = the panel is deflated); any outcome that contradicts the plan raises the abort
-    // flag and the host redoes the whole orthogonalisation synchronously.
-    if (expect >= 0 && (flag_sh != 0) != (expect == 1)) {
-        if (tid == 0) *abort_flag = 1;
-        return;
-    }
     if (flag_sh) {  // numerically dependent panel: nothing to factor
         if (tid == 0) {
-            status[0] = 0.0;
-            status[1] = 0.0;
-            status[2] = 2.0;
+            st[0] = 0.0;
+            st[1] = 0.0;
+            st[2] = 2.0;
         }
-        return;
+        __syncthreads();
+        return 2;
     }
     if (near_identity) {
         double e = 0.0;
@@ -330,18 +306,19 @@ __global__ void __launch_bounds__(CH_NT) chol_panel_kernel(const double* __restr
         double emax = 0.0;
         for (int k = 0; k < CH_NT / 32; ++k) emax = fmax(emax, emax_sh[k]);
         if (emax <= 3e-8) {
-            for (int idx = tid; idx < w * w; idx += CH_NT) {
-                const int r = idx / w, c = idx % w;
+            for (int idx = tid; idx < QF_W * QF_W; idx += CH_NT) {
+                const int r = idx / QF_W, c = idx % QF_W;
                 const double eu = A[r * QF_P + c] - (r == c ? 1.0 : 0.0);  // E is symmetric
-                Rt[idx] = (r < c) ? eu : (r == c ? 1.0 + 0.5 * eu : 0.0);
-                Linv[idx] = (r > c) ? -eu : (r == c ? 1.0 - 0.5 * eu : 0.0);
+                A[r * QF_P + c] = (r > c) ? eu : (r == c ? 1.0 + 0.5 * eu : 0.0);
+                X[r * QF_P + c] = (r > c) ? -eu : (r == c ? 1.0 - 0.5 * eu : 0.0);
             }
             if (tid == 0) {
-                status[0] = 1.0;
-                status[1] = 1.0;
-                status[2] = 0.0;
+                st[0] = 1.0;
+                st[1] = 1.0;
+                st[2] = 0.0;
             }
-            return;
+            __syncthreads();
+            return 0;
         }
     }
     bool bad = false;
@@ -391,12 +368,12 @@ __global__ void __launch_bounds__(CH_NT) chol_panel_kernel(const double* __restr
     }
     if (bad) {
         if (tid == 0) {
-            status[0] = 0.0;
-            status[1] = 0.0;
-            status[2] = 1.0;
-            if (expect >= 0) *abort_flag = 1;
+            st[0] = 0.0;
+            st[1] = 0.0;
+            st[2] = 1.0;
         }
-        return;
+        __syncthreads();
+        return 1;
     }
     __syncthreads();
     // deferred scaling: L_ik = A_ik / sqrt(d_k); only the lower triangle is meaningful
@@ -461,12 +438,6 @@ __global__ void __launch_bounds__(CH_NT) chol_panel_kernel(const double* __restr
             X[(ty + 16 * ii) * QF_P + tx + 16 * kk] = x[ii][kk];
         }
     __syncthreads();
-    for (int idx = tid; idx < w * w; idx += CH_NT) {
-        const int r = idx / w, c = idx % w;
-        Rt[idx] = (r <= c) ? A[c * QF_P + r] : 0.0;
-        Linv[idx] = X[r * QF_P + c];
-    }
-
     if (tid < 32) {
         double r0 = 1e300, r1 = 1e300;
         for (int v = tid; v < w; v += 32) {
@@ -481,13 +452,66 @@ __global__ void __launch_bounds__(CH_NT) chol_panel_kernel(const double* __restr
             r1 = fmin(r1, __shfl_xor_sync(0xffffffffu, r1, o));
         }
         if (tid == 0) {
-            status[0] = r0;
-            status[1] = r1;
-            status[2] = 0.0;
-            // replay: an ill-conditioned panel (the host would hand it to the Householder path) or a
-            // last planned pass that still fails the DGKS test contradicts the plan
-            if (expect >= 0 && (!(r1 >= ill_min) || (dgks_check && !(r0 >= 0.3)))) *abort_flag = 1;
+            st[0] = r0;
+            st[1] = r1;
+            st[2] = 0.0;
         }
+    }
+    __syncthreads();
+    return 0;
+}
+
+// expect >= 0: the host replays a recorded plan without reading the status back (0 = the panel is
+// factored, 1 = the panel is deflated); any outcome that contradicts the plan -- including an
+// ill-conditioned panel (the host would hand it to the Householder path) or a last planned pass that still
+// fails the DGKS test -- raises the abort flag and the host redoes the whole orthogonalisation synchronously.
+// Returns true (uniform) when the outcome contradicts the plan.
+__device__ __forceinline__ bool chol_contradicts(int code, const double* st, int expect, int dgks_check, double ill_min) {
+    if (expect < 0) return false;
+    if ((code == 2) != (expect == 1)) return true;
+    if (code == 1) return true;
+    if (code == 0 && (!(st[1] >= ill_min) || (dgks_check && !(st[0] >= 0.3)))) return true;
+    return false;
+}
+
+__global__ void __launch_bounds__(CH_NT) chol_panel_kernel(const double* __restrict__ G, int w,
+                                                           const double* __restrict__ nrm_prev,
+                                                           double* __restrict__ Rt, double* __restrict__ Linv,
+                                                           double* __restrict__ status, double deflate_tol,
+                                                           int near_identity, int expect, int dgks_check,
+                                                           int* __restrict__ abort_flag, double ill_min) {
+    extern __shared__ __align__(16) double chol_sm[];
+    double* A = chol_sm;                 // [QF_W][QF_P]
+    double* X = chol_sm + QF_W * QF_P;   // [QF_W][QF_P]
+    __shared__ double st[4];
+    const int tid = threadIdx.x;
+    {
+        // all 16 loads of a thread in flight at once (a strided loop pays one DRAM latency per trip)
+        double g[QF_W * QF_W / CH_NT];
+#pragma unroll
+        for (int u = 0; u < QF_W * QF_W / CH_NT; ++u) {
+            const int idx = tid + u * CH_NT;
+            const int r = idx / QF_W, c = idx % QF_W;
+            g[u] = (r < w && c < w) ? G[r * w + c] : (r == c ? 1.0 : 0.0);  // identity padding
+        }
+#pragma unroll
+        for (int u = 0; u < QF_W * QF_W / CH_NT; ++u) {
+            const int idx = tid + u * CH_NT;
+            A[(idx / QF_W) * QF_P + idx % QF_W] = g[u];
+        }
+    }
+    __syncthreads();
+    const int code = chol_core(A, X, w, nrm_prev, deflate_tol, near_identity, st);
+    if (tid < 4) status[tid] = st[tid];
+    if (chol_contradicts(code, st, expect, dgks_check, ill_min)) {
+        if (tid == 0) *abort_flag = 1;
+        return;
+    }
+    if (code != 0) return;
+    for (int idx = tid; idx < w * w; idx += CH_NT) {
+        const int r = idx / w, c = idx % w;
+        Rt[idx] = (r <= c) ? A[c * QF_P + r] : 0.0;
+        Linv[idx] = X[r * QF_P + c];
     }
 }
 
@@ -495,6 +519,307 @@ int configure_chol() {
     static bool done = false;
     if (done) return kOk;
     TTB_CHECK_CUDA(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCholSmem)));
+    done = true;
+    return kOk;
+}
+
+// ---------------------------------------------------------------------------
+// Fused Cholesky-QR2 of one panel (w <= 64 rows of length m <= 148 * 128): ONE cooperative launch does
+// Gram -> Cholesky -> P <- L^{-1} P twice.  CTA i keeps its 64 x 128 column slab of the panel in shared
+// memory across all phases (the panel is read from and written to global memory once); per repetition:
+//   slab Gram by DMMA (upper 8x8 tiles) -> partial in global scratch -> grid barrier -> the Gram entries
+//   are summed by the CTAs that own them (fixed order: deterministic) -> grid barrier -> EVERY CTA runs
+//   the same register-resident Cholesky on the same matrix (bitwise identical results, no broadcast
+//   step), decides deflated / declined / proceed uniformly, and applies L^{-1} to its slab by DMMA.
+// CTA 0 exports R^T factors and status words of both repetitions for the host-side bookkeeping.
+// ---------------------------------------------------------------------------
+constexpr int FP_SLAB = 128;
+constexpr int FP_SP = FP_SLAB + 4;   // slab pitch: == 4 (mod 16) doubles, conflict-free DMMA fragments
+constexpr int FP_WP = QF_W + 4;      // pitch of the DMMA copy of L^{-1}
+constexpr size_t kFusedPanelSmem =
+    (size_t(QF_W) * FP_SP + 3 * size_t(QF_W) * QF_P + size_t(QF_W) * FP_WP) * sizeof(double);
+
+struct FusedPanelParams {
+    double* P;            // w x m panel, leading dimension ld
+    int64_t ld, m;
+    int w;
+    double* partial;      // [gridDim.x][64 * 64] slab Grams
+    double* gfin;         // [2][64 * 64] reduced Grams of the two repetitions
+    unsigned* barrier;    // zeroed before the launch
+    const double* nrm_prev;
+    double deflate_tol, ill_min;
+    int expect, dgks_check;
+    int* abort_flag;
+    double* Rt;           // w x w: (L1 L2)^T, the combined factor of both repetitions (host bookkeeping)
+    double* status1;      // 4 doubles
+    double* status2;      // 4 doubles
+    long long* timing;    // debug (TTB_FUSED_TIMING): clock64 stamps of CTA 0, or nullptr
+};
+
+__device__ __forceinline__ void fp_grid_barrier(unsigned* counter, unsigned& epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++epoch;
+        const unsigned target = epoch * gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+        __threadfence();
+    } else {
+        ++epoch;
+    }
+    __syncthreads();
+}
+
+// slab Gram: upper 8x8 tiles of S S^T (K = FP_SLAB), written to this CTA's partial
+__device__ __forceinline__ void fp_slab_gram(const double* __restrict__ S, double* __restrict__ part) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane >> 2, fq = lane & 3;
+    for (int job = warp; job < 36; job += CH_NT / 32) {
+        // enumerate tiles (ti <= tj) of the 8 x 8 tile grid
+        int ti = 0, rem = job;
+        while (rem >= 8 - ti) {
+            rem -= 8 - ti;
+            ++ti;
+        }
+        const int tj = ti + rem;
+        const double* pa = S + (8 * ti + fr) * FP_SP + fq;
+        const double* pb = S + (8 * tj + fr) * FP_SP + fq;
+        double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+#pragma unroll 4
+        for (int ks = 0; ks < FP_SLAB / 4; ks += 2) {
+            dmma884(c0, c1, pa[4 * ks], pb[4 * ks]);
+            dmma884(e0, e1, pa[4 * ks + 4], pb[4 * ks + 4]);
+        }
+        const int r = 8 * ti + fr, c = 8 * tj + 2 * fq;
+        part[r * QF_W + c] = c0 + e0;
+        part[r * QF_W + c + 1] = c1 + e1;
+    }
+}
+
+// entries [e0, e0 + epc) of the Gram: sum over the partials in a fixed order; epc is a power of two >= 32
+__device__ __forceinline__ void fp_reduce(const double* __restrict__ partial, double* __restrict__ gout, int epc,
+                                          double* __restrict__ scratch /* CH_NT doubles */) {
+    const int tid = threadIdx.x;
+    const int nown = (QF_W * QF_W) / epc;  // CTAs that own entries
+    if (int(blockIdx.x) < nown) {
+        const int groups = CH_NT / epc;
+        const int el = tid % epc, g = tid / epc;
+        const int e = int(blockIdx.x) * epc + el;
+        const int r = e >> 6, c = e & 63;
+        const int src = ((r >> 3) <= (c >> 3)) ? e : (c * QF_W + r);  // lower tiles mirror the upper ones
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int pidx = g;
+        const int G = int(gridDim.x);
+        for (; pidx + 3 * groups < G; pidx += 4 * groups) {
+            const double v0 = __ldcg(partial + size_t(pidx) * (QF_W * QF_W) + src);
+            const double v1 = __ldcg(partial + size_t(pidx + groups) * (QF_W * QF_W) + src);
+            const double v2 = __ldcg(partial + size_t(pidx + 2 * groups) * (QF_W * QF_W) + src);
+            const double v3 = __ldcg(partial + size_t(pidx + 3 * groups) * (QF_W * QF_W) + src);
+            s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+        }
+        for (; pidx < G; pidx += groups) s0 += __ldcg(partial + size_t(pidx) * (QF_W * QF_W) + src);
+        scratch[tid] = (s0 + s1) + (s2 + s3);
+        __syncthreads();
+        if (g == 0) {
+            double t = 0.0;
+            for (int k = 0; k < groups; ++k) t += scratch[k * epc + el];
+            gout[e] = t;
+        }
+    }
+}
+
+// S <- W S with W = L^{-1} (lower triangular, pitch FP_WP): each warp owns a 16-column strip of the slab
+__device__ __forceinline__ void fp_apply(double* __restrict__ S, const double* __restrict__ W) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane >> 2, fq = lane & 3;
+    const int n0 = warp * 16;
+    double acc[8][2][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+    for (int kt = 0; kt < 8; ++kt) {      // k tile (8 rows of S)
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh) {  // two k-steps of 4 per tile
+            const int k = 8 * kt + 4 * kh + fq;
+            const double b0 = S[k * FP_SP + n0 + fr], b1 = S[k * FP_SP + n0 + 8 + fr];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i < kt) continue;  // L^{-1} is lower triangular: row tile i only sees k tiles <= i
+                const double a = W[(8 * i + fr) * FP_WP + k];
+                dmma884(acc[i][0][0], acc[i][0][1], a, b0);
+                dmma884(acc[i][1][0], acc[i][1][1], a, b1);
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+            *reinterpret_cast<double2*>(S + (8 * i + fr) * FP_SP + n0 + 8 * j + 2 * fq) = v;
+        }
+}
+
+__global__ void __launch_bounds__(CH_NT, 1) fused_panel_kernel(FusedPanelParams p) {
+    extern __shared__ __align__(16) double fp_sm[];
+    double* S = fp_sm;                          // [64][FP_SP]
+    double* A = S + QF_W * FP_SP;               // [64][QF_P]
+    double* X = A + QF_W * QF_P;                // [64][QF_P]
+    double* W = X + QF_W * QF_P;                // [64][FP_WP]
+    double* L1 = W + QF_W * FP_WP;              // [64][QF_P]: L of repetition 1
+    __shared__ double st[4];
+    __shared__ double red_scratch[CH_NT];
+    const int tid = threadIdx.x;
+    const int64_t col0 = int64_t(blockIdx.x) * FP_SLAB;
+    const int64_t left = p.m - col0;
+    const int ncol = left < FP_SLAB ? int(left) : FP_SLAB;
+    unsigned epoch = 0;
+    int tslot = 0;
+    auto stamp = [&]() {
+        if (p.timing && blockIdx.x == 0 && tid == 0) p.timing[tslot] = clock64();
+        ++tslot;
+    };
+    stamp();
+    int epc = 32;
+    while ((QF_W * QF_W) / epc > int(gridDim.x)) epc <<= 1;
+
+    // ---- load the slab (rows >= w and columns >= ncol are zero) ----
+    {
+        const bool vec = ((reinterpret_cast<uintptr_t>(p.P) & 15) == 0) && ((p.ld & 1) == 0) && ((ncol & 1) == 0);
+        if (vec) {
+            // all 16 loads of a thread in flight before the first shared store
+            constexpr int NL = QF_W * (FP_SLAB / 2) / CH_NT;
+            double2 v[NL];
+#pragma unroll
+            for (int u = 0; u < NL; ++u) {
+                const int idx = tid + u * CH_NT;
+                const int r = idx / (FP_SLAB / 2), c2 = idx % (FP_SLAB / 2);
+                v[u] = make_double2(0.0, 0.0);
+                if (r < p.w && 2 * c2 < ncol) v[u] = *reinterpret_cast<const double2*>(p.P + int64_t(r) * p.ld + col0 + 2 * c2);
+            }
+#pragma unroll
+            for (int u = 0; u < NL; ++u) {
+                const int idx = tid + u * CH_NT;
+                const int r = idx / (FP_SLAB / 2), c2 = idx % (FP_SLAB / 2);
+                *reinterpret_cast<double2*>(S + r * FP_SP + 2 * c2) = v[u];
+            }
+        } else {
+            for (int idx = tid; idx < QF_W * FP_SLAB; idx += CH_NT) {
+                const int r = idx / FP_SLAB, c = idx % FP_SLAB;
+                S[r * FP_SP + c] = (r < p.w && c < ncol) ? p.P[int64_t(r) * p.ld + col0 + c] : 0.0;
+            }
+        }
+    }
+    __syncthreads();
+    stamp();  // 1: slab loaded
+
+#pragma unroll 1
+    for (int rep = 0; rep < 2; ++rep) {
+        double* gf = p.gfin + rep * (QF_W * QF_W);
+        fp_slab_gram(S, p.partial + size_t(blockIdx.x) * (QF_W * QF_W));
+        stamp();  // gram
+        fp_grid_barrier(p.barrier, epoch);
+        stamp();  // barrier
+        fp_reduce(p.partial, gf, epc, red_scratch);
+        stamp();  // reduce
+        fp_grid_barrier(p.barrier, epoch);
+        stamp();  // barrier
+        // ---- every CTA factors the same matrix ----
+        {
+            double g[QF_W * QF_W / CH_NT];
+#pragma unroll
+            for (int u = 0; u < QF_W * QF_W / CH_NT; ++u) {
+                const int idx = tid + u * CH_NT;
+                const int r = idx / QF_W, c = idx % QF_W;
+                g[u] = (r < p.w && c < p.w) ? __ldcg(gf + idx) : (r == c ? 1.0 : 0.0);  // identity padding
+            }
+#pragma unroll
+            for (int u = 0; u < QF_W * QF_W / CH_NT; ++u) {
+                const int idx = tid + u * CH_NT;
+                A[(idx / QF_W) * QF_P + idx % QF_W] = g[u];
+            }
+        }
+        __syncthreads();
+        const bool first = rep == 0;
+        __syncthreads();
+        stamp();  // G loaded
+        const int code = chol_core(A, X, p.w, first ? p.nrm_prev : nullptr, first ? p.deflate_tol : 0.0, first ? 0 : 1, st);
+        stamp();  // chol
+        double* status = first ? p.status1 : p.status2;
+        if (blockIdx.x == 0 && tid < 4) status[tid] = st[tid];
+        if (first) {
+            if (chol_contradicts(code, st, p.expect, p.dgks_check, p.ill_min)) {
+                if (blockIdx.x == 0 && tid == 0) *p.abort_flag = 1;
+                return;  // uniform over the grid: every CTA factored the same matrix
+            }
+            // deflated, breakdown, or ill-conditioned (the host hands the panel to the Householder path):
+            // the panel is left untouched
+            if (code != 0 || !(st[1] >= p.ill_min)) return;
+        } else if (code != 0) {
+            // cannot happen for the near-orthonormal rows of the second repetition; flag it loudly
+            if (blockIdx.x == 0 && tid == 0) {
+                status[2] = 1.0;
+                if (p.expect >= 0) *p.abort_flag = 1;
+            }
+            return;
+        }
+        if (first) {
+            for (int idx = tid; idx < QF_W * QF_W; idx += CH_NT) L1[(idx >> 6) * QF_P + (idx & 63)] = A[(idx >> 6) * QF_P + (idx & 63)];
+        } else {
+            // P = L1 Q1 = L1 L2 Q2: export (L1 L2)^T, row r of it by CTA r (every CTA holds both factors),
+            // four threads per entry
+            for (int r = int(blockIdx.x); r < p.w; r += int(gridDim.x)) {
+                const int c = tid >> 2, part = tid & 3;
+                double t = 0.0;
+                if (c < p.w && r <= c)
+                    for (int k = r + part; k <= c; k += 4) t = fma(L1[c * QF_P + k], A[k * QF_P + r], t);
+                t += __shfl_xor_sync(0xffffffffu, t, 1);
+                t += __shfl_xor_sync(0xffffffffu, t, 2);
+                if (c < p.w && part == 0) p.Rt[r * p.w + c] = t;
+            }
+        }
+        for (int idx = tid; idx < QF_W * QF_W; idx += CH_NT) {
+            const int r = idx >> 6, c = idx & 63;
+            W[r * FP_WP + c] = X[r * QF_P + c];
+        }
+        __syncthreads();
+        stamp();  // export
+        fp_apply(S, W);
+        __syncthreads();
+        stamp();  // apply
+    }
+
+    // ---- store the orthonormalised slab ----
+    {
+        const bool vec = ((reinterpret_cast<uintptr_t>(p.P) & 15) == 0) && ((p.ld & 1) == 0) && ((ncol & 1) == 0);
+        if (vec) {
+            for (int idx = tid; idx < p.w * (FP_SLAB / 2); idx += CH_NT) {
+                const int r = idx / (FP_SLAB / 2), c2 = idx % (FP_SLAB / 2);
+                if (2 * c2 < ncol)
+                    *reinterpret_cast<double2*>(p.P + int64_t(r) * p.ld + col0 + 2 * c2) =
+                        *reinterpret_cast<const double2*>(S + r * FP_SP + 2 * c2);
+            }
+        } else {
+            for (int idx = tid; idx < p.w * FP_SLAB; idx += CH_NT) {
+                const int r = idx / FP_SLAB, c = idx % FP_SLAB;
+                if (c < ncol) p.P[int64_t(r) * p.ld + col0 + c] = S[r * FP_SP + c];
+            }
+        }
+    }
+}
+
+int configure_fused_panel() {
+    static bool done = false;
+    if (done) return kOk;
+    TTB_CHECK_CUDA(cudaFuncSetAttribute(fused_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        int(kFusedPanelSmem)));
     done = true;
     return kOk;
 }
@@ -915,6 +1240,10 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
         return e == nullptr || e[0] != '0';
     }();
     static const bool debug = getenv("TTB_DEBUG") != nullptr;
+    static const bool fused_enabled = [] {
+        const char* e = getenv("TTB_QR_FUSED");
+        return e == nullptr || e[0] != '0';
+    }();
 
     // jq: orthonormal rows produced so far (they sit compactly in M[0:jq]); jc: input vectors
     // consumed so far.  They differ once a panel has been deflated; the panel being worked on is
@@ -976,6 +1305,84 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
                 { ProfScope ps_("qr.gemm_proj_update", stream); if (gemm(u, gws, gws_bytes, stream) != kOk) return -1; }
             }
             const bool last_planned = replay && (jq == 0 || pass >= planned.value || planned.kind == 2);
+            // ---- fused path: Gram -> Cholesky -> solve, twice, in one cooperative launch ----
+            const int fp_grid = int(ceil_div<int64_t>(m, FP_SLAB));
+            const size_t fp_need = (size_t(fp_grid) + 2) * QF_W * QF_W * sizeof(double) + 256;
+            if (fused_enabled && m >= 16 * FP_SLAB && fp_grid <= num_sms() && gws_bytes >= fp_need) {
+                if (configure_fused_panel() != kOk) return -1;
+                const bool defl_test = pass == 1 && jq > 0;
+                FusedPanelParams fp;
+                fp.P = P; fp.ld = ldm; fp.m = m; fp.w = w;
+                fp.partial = static_cast<double*>(gws);
+                fp.gfin = fp.partial + size_t(fp_grid) * QF_W * QF_W;
+                fp.barrier = reinterpret_cast<unsigned*>(fp.gfin + 2 * QF_W * QF_W);
+                fp.nrm_prev = defl_test ? nrm[0] : nullptr;
+                fp.deflate_tol = defl_test ? deflate_tol : 0.0;
+                fp.ill_min = ill_min;
+                fp.expect = replay ? ((defl_test && deflate_tol > 0.0 && planned.kind == 2) ? 1 : 0) : -1;
+                fp.dgks_check = (replay && jq > 0 && last_planned) ? 1 : 0;
+                fp.abort_flag = abort_flag;
+                fp.Rt = Rp;
+                fp.status1 = status;
+                fp.status2 = status + 8;
+                static long long* timing_dev = nullptr;
+                static const bool fused_timing = getenv("TTB_FUSED_TIMING") != nullptr;
+                if (fused_timing && !timing_dev) cudaMalloc(&timing_dev, 64 * sizeof(long long));
+                fp.timing = fused_timing ? timing_dev : nullptr;
+                if (cudaMemsetAsync(fp.barrier, 0, sizeof(unsigned), stream) != cudaSuccess) return -1;
+                void* args[] = {&fp};
+                {
+                    ProfScope ps_("qr.fused_panel", stream);
+                    if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(fused_panel_kernel), dim3(fp_grid), dim3(CH_NT),
+                                                    args, kFusedPanelSmem, stream) != cudaSuccess)
+                        return -1;
+                }
+                ++g_launch_count;
+                if (fused_timing) {
+                    long long h[24];
+                    cudaStreamSynchronize(stream);
+                    cudaMemcpy(h, timing_dev, sizeof(h), cudaMemcpyDeviceToHost);
+                    fprintf(stderr, "[fused_panel] w=%d m=%lld clk:", w, (long long)m);
+                    for (int i = 1; i < 20; ++i) fprintf(stderr, " %lld", h[i] - h[i - 1]);
+                    fprintf(stderr, "\n");
+                }
+                bool deflated, declined = false;
+                if (replay) {
+                    deflated = defl_test && deflate_tol > 0.0 && planned.kind == 2;
+                } else {
+                    if (cudaMemcpyAsync(host.status, status, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+                        cudaStreamSynchronize(stream) != cudaSuccess)
+                        return -1;
+                    if (debug && pass == 1 && jq > 0)
+                        fprintf(stderr, "[orth_rows] fused panel jc=%lld jq=%lld w=%d residual ratio %.2e dgks %.2e cond %.2e\n",
+                                (long long)jc, (long long)jq, w, host.status[3], host.status[0], host.status[1]);
+                    deflated = defl_test && deflate_tol > 0.0 && host.status[2] == 2.0;
+                    declined = !deflated && (host.status[2] != 0.0 || !(host.status[1] >= ill_min));
+                }
+                const int blocks = int((jq + 15) / 16 + 1);
+                if (deflated || declined) {
+                    if (declined && pass > 1) return -2;
+                    if (deflated || jq > 0) {  // keep the projection that was already applied to P
+                        accumulate_r_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jq, jc, w, Cb, jq, nullptr, Rd[cur], Rd[cur ^ 1], 0,
+                                                                        rd_ident ? 1 : 0);
+                        ++g_launch_count;
+                    }
+                    if (deflated) {
+                        if (plan && !replay) plan->seq.push_back({2, 1});
+                        return 2;
+                    }
+                    if (plan) plan->valid = false;  // Householder panels are never replayed
+                    return 0;
+                }
+                {
+                    ProfScope ps_("qr.accumulate_r", stream);
+                    accumulate_r_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jq, jc, w, jq > 0 ? Cb : nullptr, jq, fp.Rt, Rd[cur],
+                                                                    Rd[cur ^ 1], 1, rd_ident ? 1 : 0);
+                    rd_ident = false;
+                    cur ^= 1;
+                    ++g_launch_count;
+                }
+            } else
             for (int rep = 0; rep < 2; ++rep) {  // Cholesky-QR twice
                 GemmArgs gg;  // G = P P^T
                 gg.M = w; gg.N = w; gg.K = m;
