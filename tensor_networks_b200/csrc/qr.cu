@@ -610,9 +610,10 @@ __device__ __forceinline__ void fp_reduce(const double* __restrict__ partial, do
         const int el = tid % epc, g = tid / epc;
         const int e = int(blockIdx.x) * epc + el;
         const int r = e >> 6, c = e & 63;
-        const int src = ((r >> 3) <= (c >> 3)) ? e : (c * QF_W + r);  // lower tiles mirror the upper ones
+        const bool upper = (r >> 3) <= (c >> 3);  // only the upper 8x8 tiles exist in the partials; the consumer mirrors
+        const int src = e;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int pidx = g;
+        int pidx = upper ? g : (1 << 30);
         const int G = int(gridDim.x);
         for (; pidx + 3 * groups < G; pidx += 4 * groups) {
             const double v0 = __ldcg(partial + size_t(pidx) * (QF_W * QF_W) + src);
@@ -624,7 +625,7 @@ __device__ __forceinline__ void fp_reduce(const double* __restrict__ partial, do
         for (; pidx < G; pidx += groups) s0 += __ldcg(partial + size_t(pidx) * (QF_W * QF_W) + src);
         scratch[tid] = (s0 + s1) + (s2 + s3);
         __syncthreads();
-        if (g == 0) {
+        if (g == 0 && upper) {
             double t = 0.0;
             for (int k = 0; k < groups; ++k) t += scratch[k * epc + el];
             gout[e] = t;
@@ -667,6 +668,7 @@ __device__ __forceinline__ void fp_apply(double* __restrict__ S, const double* _
         }
 }
 
+template <bool TIMING>
 __global__ void __launch_bounds__(CH_NT, 1) fused_panel_kernel(FusedPanelParams p) {
     extern __shared__ __align__(16) double fp_sm[];
     double* S = fp_sm;                          // [64][FP_SP]
@@ -683,8 +685,10 @@ __global__ void __launch_bounds__(CH_NT, 1) fused_panel_kernel(FusedPanelParams 
     unsigned epoch = 0;
     int tslot = 0;
     auto stamp = [&]() {
-        if (p.timing && blockIdx.x == 0 && tid == 0) p.timing[tslot] = clock64();
-        ++tslot;
+        if (TIMING) {
+            if (p.timing && blockIdx.x == 0 && tid == 0) p.timing[tslot] = clock64();
+            ++tslot;
+        }
     };
     stamp();
     int epc = 32;
@@ -738,7 +742,8 @@ __global__ void __launch_bounds__(CH_NT, 1) fused_panel_kernel(FusedPanelParams 
             for (int u = 0; u < QF_W * QF_W / CH_NT; ++u) {
                 const int idx = tid + u * CH_NT;
                 const int r = idx / QF_W, c = idx % QF_W;
-                g[u] = (r < p.w && c < p.w) ? __ldcg(gf + idx) : (r == c ? 1.0 : 0.0);  // identity padding
+                const int src = ((r >> 3) <= (c >> 3)) ? idx : (c * QF_W + r);  // lower tiles mirror the upper ones
+                g[u] = (r < p.w && c < p.w) ? __ldcg(gf + src) : (r == c ? 1.0 : 0.0);  // identity padding
             }
 #pragma unroll
             for (int u = 0; u < QF_W * QF_W / CH_NT; ++u) {
@@ -818,7 +823,9 @@ __global__ void __launch_bounds__(CH_NT, 1) fused_panel_kernel(FusedPanelParams 
 int configure_fused_panel() {
     static bool done = false;
     if (done) return kOk;
-    TTB_CHECK_CUDA(cudaFuncSetAttribute(fused_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TTB_CHECK_CUDA(cudaFuncSetAttribute(fused_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        int(kFusedPanelSmem)));
+    TTB_CHECK_CUDA(cudaFuncSetAttribute(fused_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         int(kFusedPanelSmem)));
     done = true;
     return kOk;
@@ -1333,7 +1340,9 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
                 void* args[] = {&fp};
                 {
                     ProfScope ps_("qr.fused_panel", stream);
-                    if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(fused_panel_kernel), dim3(fp_grid), dim3(CH_NT),
+                    if (cudaLaunchCooperativeKernel(fused_timing ? reinterpret_cast<void*>(fused_panel_kernel<true>)
+                                                                 : reinterpret_cast<void*>(fused_panel_kernel<false>),
+                                                    dim3(fp_grid), dim3(CH_NT),
                                                     args, kFusedPanelSmem, stream) != cudaSuccess)
                         return -1;
                 }
