@@ -54,3 +54,39 @@ def test_orth_rows_adversarial():
     _check(np.vstack([b, b]))  # X (+) X like: second half duplicates the first
     g = np.diag(np.logspace(0, -18, 96)) @ rng.standard_normal((96, 700))  # graded rows
     _check(g)
+
+
+@pytest.mark.parametrize("c,m", [(100, 3001), (37, 2049), (130, 18944), (64, 18945), (64, 2048), (200, 8190), (65, 16384)])
+def test_orth_rows_fused_panel_shapes(c, m):
+    """Shapes on both sides of the fused cooperative panel kernel's range (2048 <= m <= 148 * 128), with
+    odd row lengths (scalar slab loads, partial last slab) and panel widths that are not multiples of 64."""
+    rng = np.random.default_rng(c * 7 + m)
+    _check(rng.standard_normal((c, m)))
+
+
+def test_orth_rows_fused_panel_decisions():
+    """Inside the fused kernel's range: a duplicated block (deflation is NOT active through this entry
+    point, so the dependent panel breaks down and goes to the Householder path), an ill-conditioned
+    panel (declined on the device, panel left untouched) and a badly scaled one."""
+    rng = np.random.default_rng(5)
+    b = rng.standard_normal((64, 4096))
+    _check(np.vstack([b, b, rng.standard_normal((20, 4096))]))
+    mix = rng.standard_normal((64, 64))
+    mix[:, -1] = mix[:, 0] * (1 + 1e-7)  # two nearly parallel directions: cond ~ 1e7
+    _check(np.vstack([mix @ rng.standard_normal((64, 4096)), rng.standard_normal((64, 4096))]), orth_tol=1e-12)
+    s = rng.standard_normal((128, 4100)) * np.logspace(0, -12, 128)[:, None]
+    _check(s)
+
+
+def test_orth_rows_fused_repeatable():
+    """Plan replay and graph capture on the fused path: the same call five times gives bit-identical Q and R."""
+    from tensor_networks_b200.utils import orth_rows_dev
+
+    rng = np.random.default_rng(8)
+    a = torch.from_numpy(rng.standard_normal((192, 8192))).cuda()
+    outs = []
+    for _ in range(5):
+        q, r = orth_rows_dev(a.clone())
+        outs.append((q.clone(), r.clone()))
+    for q, r in outs[1:]:
+        assert torch.equal(q, outs[0][0]) and torch.equal(r, outs[0][1])

@@ -222,3 +222,26 @@ def test_round_randomised_structures(seed):
     assert tt.ranks() == orc.ranks_of(ref), (shape, eps, tt.ranks(), orc.ranks_of(ref))
     assert abs(err - err_ref) <= 1e-10
     assert err <= eps * 1.0000001 + 1e-13
+
+
+def test_round_zero_tensor_and_unit_modes():
+    """Edge cases the reference handles implicitly: an identically zero TT (delta = 0, every rank clamps to 1)
+    and modes of size 1."""
+    from tensor_networks_b200 import TensorTrain
+
+    rng = np.random.default_rng(1)
+    x = orc.rand_tt([4, 5, 6], [3, 3], rng)
+    x[1] = x[1] * 0.0
+    ref, _ = orc.svd_round(copy.deepcopy(x), 1e-8)
+    t = TensorTrain.from_cores(copy.deepcopy(x)).round(1e-8)
+    assert t.ranks() == orc.ranks_of(ref) == [1, 1]
+    assert float(t.norm()) == 0.0
+    x = orc.rand_tt([1, 7, 1, 5], [1, 3, 3], rng)
+    y = orc.tt_add(x, x)
+    ref, _ = orc.svd_round(copy.deepcopy(y), 1e-10)
+    t = TensorTrain.from_cores(copy.deepcopy(y)).round(1e-10)
+    assert t.ranks() == orc.ranks_of(ref) == [1, 3, 3]
+    assert np.abs(t.dense() - orc.to_dense(y)).max() <= 1e-13 * np.abs(orc.to_dense(y)).max()
+    t2 = TensorTrain.from_cores(copy.deepcopy(y)).gramsvd_round(1e-6)
+    r2, _ = orc.gramsvd_round(copy.deepcopy(y), 1e-6)
+    assert t2.ranks() == orc.ranks_of(r2) == [1, 3, 3]
