@@ -263,6 +263,7 @@ constexpr int CH_NT = 256;
 // (identity-padded beyond w, pitch QF_P) and the CTA is synchronised; on return (synchronised) A holds
 // L (lower triangle, zeros above), X holds L^{-1}, st[0..3] the status words described above, and the
 // (uniform) return value is 0 = factored, 1 = breakdown, 2 = deflated (nothing factored).
+template <bool WANT_INV>
 __device__ __forceinline__ int chol_core(double* __restrict__ A, double* __restrict__ X, int w,
                                          const double* __restrict__ nrm_prev, double deflate_tol,
                                          int near_identity, double* __restrict__ st) {
@@ -310,7 +311,7 @@ __device__ __forceinline__ int chol_core(double* __restrict__ A, double* __restr
                 const int r = idx / QF_W, c = idx % QF_W;
                 const double eu = A[r * QF_P + c] - (r == c ? 1.0 : 0.0);  // E is symmetric
                 A[r * QF_P + c] = (r > c) ? eu : (r == c ? 1.0 + 0.5 * eu : 0.0);
-                X[r * QF_P + c] = (r > c) ? -eu : (r == c ? 1.0 - 0.5 * eu : 0.0);
+                if (WANT_INV) X[r * QF_P + c] = (r > c) ? -eu : (r == c ? 1.0 - 0.5 * eu : 0.0);
             }
             if (tid == 0) {
                 st[0] = 1.0;
@@ -387,10 +388,11 @@ __device__ __forceinline__ int chol_core(double* __restrict__ A, double* __restr
             a[ii][kk] = (i >= k) ? a[ii][kk] * rs : 0.0;
         }
     }
+    double x[4][4];
+    if (WANT_INV) {
     if (tid < QF_W) rdiag[tid] = rsqrt(dsave[tid]);  // 1 / L_kk
     // ---- X = L^{-1} the same way: row k of X becomes final when divided by L_kk, then the rank-1 term
     // L[:, k] X[k, :] leaves the rows below ----
-    double x[4][4];
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
@@ -429,13 +431,14 @@ __device__ __forceinline__ int chol_core(double* __restrict__ A, double* __restr
             }
         }
     }
+    }
     __syncthreads();
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             A[(ty + 16 * ii) * QF_P + tx + 16 * kk] = a[ii][kk];
-            X[(ty + 16 * ii) * QF_P + tx + 16 * kk] = x[ii][kk];
+            if (WANT_INV) X[(ty + 16 * ii) * QF_P + tx + 16 * kk] = x[ii][kk];
         }
     __syncthreads();
     if (tid < 32) {
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(CH_NT) chol_panel_kernel(const double* __restr
         }
     }
     __syncthreads();
-    const int code = chol_core(A, X, w, nrm_prev, deflate_tol, near_identity, st);
+    const int code = chol_core<true>(A, X, w, nrm_prev, deflate_tol, near_identity, st);
     if (tid < 4) status[tid] = st[tid];
     if (chol_contradicts(code, st, expect, dgks_check, ill_min)) {
         if (tid == 0) *abort_flag = 1;
@@ -530,14 +533,16 @@ int configure_chol() {
 //   slab Gram by DMMA (upper 8x8 tiles) -> partial in global scratch -> grid barrier -> the Gram entries
 //   are summed by the CTAs that own them (fixed order: deterministic) -> grid barrier -> EVERY CTA runs
 //   the same register-resident Cholesky on the same matrix (bitwise identical results, no broadcast
-//   step), decides deflated / declined / proceed uniformly, and applies L^{-1} to its slab by DMMA.
+//   step), decides deflated / declined / proceed uniformly, and solves L X = slab by blocked forward
+//   substitution on DMMA (only the 8 x 8 diagonal blocks are inverted: backward stable, and the 64-step
+//   sequential inversion of L is gone).
 // CTA 0 exports R^T factors and status words of both repetitions for the host-side bookkeeping.
 // ---------------------------------------------------------------------------
 constexpr int FP_SLAB = 128;
 constexpr int FP_SP = FP_SLAB + 4;   // slab pitch: == 4 (mod 16) doubles, conflict-free DMMA fragments
 constexpr int FP_WP = QF_W + 4;      // pitch of the DMMA copy of L^{-1}
 constexpr size_t kFusedPanelSmem =
-    (size_t(QF_W) * FP_SP + 3 * size_t(QF_W) * QF_P + size_t(QF_W) * FP_WP) * sizeof(double);
+    (size_t(QF_W) * FP_SP + 2 * size_t(QF_W) * QF_P + size_t(QF_W) * FP_WP) * sizeof(double);
 
 struct FusedPanelParams {
     double* P;            // w x m panel, leading dimension ld
@@ -633,39 +638,74 @@ __device__ __forceinline__ void fp_reduce(const double* __restrict__ partial, do
     }
 }
 
-// S <- W S with W = L^{-1} (lower triangular, pitch FP_WP): each warp owns a 16-column strip of the slab
-__device__ __forceinline__ void fp_apply(double* __restrict__ S, const double* __restrict__ W) {
+// W <- L (pitch FP_WP) with every 8 x 8 diagonal block replaced by its inverse (warp b inverts block b by
+// forward substitution, one column per lane).  All CH_NT threads; synchronises.
+__device__ __forceinline__ void fp_prepare_solve(const double* __restrict__ A, double* __restrict__ W) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int idx = tid; idx < QF_W * QF_W; idx += CH_NT) {
+        const int r = idx >> 6, c = idx & 63;
+        if ((r >> 3) != (c >> 3)) W[r * FP_WP + c] = A[r * QF_P + c];
+    }
+    if (lane < 8) {
+        const int b0 = 8 * warp, c = lane;
+        double x[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            double sacc = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < r && k >= c) sacc = fma(-A[(b0 + r) * QF_P + b0 + k], x[k], sacc);
+            x[r] = (r >= c) ? sacc / A[(b0 + r) * QF_P + b0 + r] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) W[(b0 + r) * FP_WP + b0 + c] = x[r];
+    }
+    __syncthreads();
+}
+
+// S <- L^{-1} S by blocked forward substitution (backward stable, no explicit inverse of L): row tile i
+// first loses sum_{k<i} L_ik S_k (DMMA against the finished tiles), then is multiplied by the inverse of
+// its 8 x 8 diagonal block.  Each warp owns a 16-column strip of the slab; no block-level barrier.
+__device__ __forceinline__ void fp_solve(double* __restrict__ S, const double* __restrict__ W) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int fr = lane >> 2, fq = lane & 3;
     const int n0 = warp * 16;
-    double acc[8][2][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 8; ++i) {
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
-        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int k = 0; k < 8; ++k) {
+            if (k >= i) continue;
 #pragma unroll
-    for (int kt = 0; kt < 8; ++kt) {      // k tile (8 rows of S)
-#pragma unroll
-        for (int kh = 0; kh < 2; ++kh) {  // two k-steps of 4 per tile
-            const int k = 8 * kt + 4 * kh + fq;
-            const double b0 = S[k * FP_SP + n0 + fr], b1 = S[k * FP_SP + n0 + 8 + fr];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (i < kt) continue;  // L^{-1} is lower triangular: row tile i only sees k tiles <= i
-                const double a = W[(8 * i + fr) * FP_WP + k];
-                dmma884(acc[i][0][0], acc[i][0][1], a, b0);
-                dmma884(acc[i][1][0], acc[i][1][1], a, b1);
+            for (int kh = 0; kh < 2; ++kh) {
+                const int kk = 8 * k + 4 * kh + fq;
+                const double a = W[(8 * i + fr) * FP_WP + kk];
+                dmma884(acc[0][0], acc[0][1], a, S[kk * FP_SP + n0 + fr]);
+                dmma884(acc[1][0], acc[1][1], a, S[kk * FP_SP + n0 + 8 + fr]);
             }
         }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
+        double* row = S + (8 * i + fr) * FP_SP + n0 + 2 * fq;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
-            *reinterpret_cast<double2*>(S + (8 * i + fr) * FP_SP + n0 + 8 * j + 2 * fq) = v;
+            double2 v = *reinterpret_cast<double2*>(row + 8 * j);
+            v.x -= acc[j][0];
+            v.y -= acc[j][1];
+            *reinterpret_cast<double2*>(row + 8 * j) = v;
         }
+        __syncwarp();
+        double res[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh) {
+            const int kk = 8 * i + 4 * kh + fq;
+            const double a = W[(8 * i + fr) * FP_WP + kk];
+            dmma884(res[0][0], res[0][1], a, S[kk * FP_SP + n0 + fr]);
+            dmma884(res[1][0], res[1][1], a, S[kk * FP_SP + n0 + 8 + fr]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) *reinterpret_cast<double2*>(row + 8 * j) = make_double2(res[j][0], res[j][1]);
+        __syncwarp();
+    }
 }
 
 template <bool TIMING>
@@ -673,8 +713,7 @@ __global__ void __launch_bounds__(CH_NT, 1) fused_panel_kernel(FusedPanelParams 
     extern __shared__ __align__(16) double fp_sm[];
     double* S = fp_sm;                          // [64][FP_SP]
     double* A = S + QF_W * FP_SP;               // [64][QF_P]
-    double* X = A + QF_W * QF_P;                // [64][QF_P]
-    double* W = X + QF_W * QF_P;                // [64][FP_WP]
+    double* W = A + QF_W * QF_P;                // [64][FP_WP]: L with inverted 8x8 diagonal blocks
     double* L1 = W + QF_W * FP_WP;              // [64][QF_P]: L of repetition 1
     __shared__ double st[4];
     __shared__ double red_scratch[CH_NT];
@@ -755,7 +794,7 @@ __global__ void __launch_bounds__(CH_NT, 1) fused_panel_kernel(FusedPanelParams 
         const bool first = rep == 0;
         __syncthreads();
         stamp();  // G loaded
-        const int code = chol_core(A, X, p.w, first ? p.nrm_prev : nullptr, first ? p.deflate_tol : 0.0, first ? 0 : 1, st);
+        const int code = chol_core<false>(A, nullptr, p.w, first ? p.nrm_prev : nullptr, first ? p.deflate_tol : 0.0, first ? 0 : 1, st);
         stamp();  // chol
         double* status = first ? p.status1 : p.status2;
         if (blockIdx.x == 0 && tid < 4) status[tid] = st[tid];
@@ -790,13 +829,9 @@ __global__ void __launch_bounds__(CH_NT, 1) fused_panel_kernel(FusedPanelParams 
                 if (c < p.w && part == 0) p.Rt[r * p.w + c] = t;
             }
         }
-        for (int idx = tid; idx < QF_W * QF_W; idx += CH_NT) {
-            const int r = idx >> 6, c = idx & 63;
-            W[r * FP_WP + c] = X[r * QF_P + c];
-        }
-        __syncthreads();
+        fp_prepare_solve(A, W);
         stamp();  // export
-        fp_apply(S, W);
+        fp_solve(S, W);
         __syncthreads();
         stamp();  // apply
     }
