@@ -375,6 +375,8 @@ struct JacobiClusterParams {
     int max_sweeps;
     double* out;  // out[0] = sweeps done, out[1] = 1 when converged, out[2..7] = phase clocks (debug)
     int timing;   // 1: thread 0 of CTA 0 accumulates clock64() per phase section into out[2..7]
+    int dbuf;     // 1: two tile buffers per CTA -- the apply step PUSHES the rotated rows straight into the next
+                  // owner's other buffer (DSMEM stores), one cluster barrier per phase instead of pull + two
 };
 // Rows per block: 16 (32 staged rows per CTA) or 8 (16 staged rows: twice the CTAs and phases, but the
 // 16 x 16 Gram makes every rotation round ~40 % cheaper and the tiles to exchange half as large).
@@ -385,9 +387,10 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) double sm[];
-    double* T = sm;  // [32][pitch]
     constexpr int R2 = 2 * JC_B;
-    double* G = T + size_t(R2) * p.pitch;   // [R2][JB_GP]
+    double* const T0 = sm;  // [R2][pitch], twice when double-buffered
+    double* T = T0;         // the buffer that holds this phase's rows
+    double* G = T0 + size_t(p.dbuf ? 2 : 1) * size_t(R2) * p.pitch;   // [R2][JB_GP]
     double* W = G + JB_MAXR * JB_GP;
     __shared__ double2 pcs[JB_MAXR / 2];
     __shared__ int2 pij[JB_MAXR / 2];
@@ -398,6 +401,15 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h = p.nb >> 1;
     const int rank = int(cluster.block_rank());
+    // circle-method successor of my two blocks (position top[0] is fixed): where the rows I hold now are needed next
+    const bool dbuf = p.dbuf != 0 && h > 1;
+    int dst_rank[2], dst_slot[2];
+    if (rank == 0) { dst_rank[0] = 0; dst_slot[0] = 0; dst_rank[1] = (h > 1) ? 1 : 0; dst_slot[1] = (h > 1) ? 0 : 1; }
+    else {
+        if (rank < h - 1) { dst_rank[0] = rank + 1; dst_slot[0] = 0; } else { dst_rank[0] = rank; dst_slot[0] = 1; }
+        dst_rank[1] = rank - 1; dst_slot[1] = 1;
+    }
+    int cur = 0;
     if (tid < h) {
         arr_top[tid] = 2 * tid;
         arr_bot[tid] = 2 * tid + 1;
@@ -517,7 +529,16 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
                     __syncwarp();
 #pragma unroll
                     for (int i = 0; i < R2 / 8; ++i) {
-                        double* base = T + size_t(8 * i + (lane >> 2)) * p.pitch + n0 + 2 * (lane & 3);
+                        double* base;
+                        if (dbuf) {
+                            // push: the rows go straight into the other buffer of the CTA that owns them next
+                            const int blk = (8 * i) / JC_B, rin = (8 * i) % JC_B + (lane >> 2);
+                            double* Tn = T0 + size_t(cur ^ 1) * size_t(R2) * p.pitch;
+                            base = cluster.map_shared_rank(Tn, dst_rank[blk]) + size_t(dst_slot[blk] * JC_B + rin) * p.pitch + n0 +
+                                   2 * (lane & 3);
+                        } else {
+                            base = T + size_t(8 * i + (lane >> 2)) * p.pitch + n0 + 2 * (lane & 3);
+                        }
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             if (j < nt) *reinterpret_cast<double2*>(base + 8 * j) = make_double2(acc[i][j][0], acc[i][j][1]);
@@ -532,6 +553,28 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
                     sweep_max = 0.0;
                 }
                 __syncthreads();
+                continue;
+            }
+            if (dbuf) {
+                if (tid == 0) {
+                    int nt_[JC_MAXH], nb_[JC_MAXH];  // every CTA tracks the whole arrangement
+                    for (int k = 0; k < h; ++k) {
+                        nt_[k] = (k == 0) ? arr_top[0] : (k == 1 ? arr_bot[0] : arr_top[k - 1]);
+                        nb_[k] = (k == h - 1) ? arr_top[h - 1] : arr_bot[k + 1];
+                    }
+                    for (int k = 0; k < h; ++k) {
+                        arr_top[k] = nt_[k];
+                        arr_bot[k] = nb_[k];
+                    }
+                    if (phase == nphase - 1) {
+                        for (int k = 0; k < h; ++k) cluster.map_shared_rank(conv_in, k)[rank] = sweep_max;
+                        sweep_max = 0.0;
+                    }
+                }
+                cluster.sync();  // every push of this phase has landed; the old buffers are free again
+                cur ^= 1;
+                T = T0 + size_t(cur) * size_t(R2) * p.pitch;
+                JC_TICK(3)
                 continue;
             }
             cluster.sync();  // (A) the tiles of every CTA are final for this phase
@@ -937,7 +980,19 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
         if (forced_b == 8 || forced_b == 16) jcb = forced_b;
         int nbc = std::max(2, ceil_div(p, jcb));
         if (nbc & 1) ++nbc;
-        const size_t csmem = (size_t(2 * jcb) * cp.pitch + 2 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
+        static const bool push_enabled = [] {
+            const char* e = getenv("TTB_JACOBI_PUSH");
+            return e == nullptr || e[0] != '0';
+        }();
+        size_t csmem = (size_t(2 * jcb) * cp.pitch + 2 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
+        {
+            int dev0 = 0, maxsm0 = 0;
+            cudaGetDevice(&dev0);
+            cudaDeviceGetAttribute(&maxsm0, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev0);
+            const size_t csmem2 = csmem + size_t(2 * jcb) * cp.pitch * sizeof(double);
+            cp.dbuf = (push_enabled && nbc > 2 && csmem2 + 4096 <= size_t(maxsm0)) ? 1 : 0;
+            if (cp.dbuf) csmem = csmem2;
+        }
         int dev = 0, maxsm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
