@@ -672,144 +672,115 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
 // p and ANY orthonormal basis of the column space -- Q itself -- with carry R represents the same
 // tensor as U and diag(s) V^T: the SVD is not needed.  out[0] = ||Y||_F^2, out[1] = ||R||_F^2,
 // out[2] = 1 when R is singular / not finite.
-// One CTA; the tile holds R in its upper triangle and Y^T in its strict lower triangle.  Column j of
-// Y is solved by back substitution on the four lanes (j, part): lane `part` owns the terms k = part
-// (mod 4) and is the lane that stored them, so a column needs no barrier at all.
+// One CTA; the tile holds R in its upper triangle and Y^T in its strict lower triangle.
 // ---------------------------------------------------------------------------
 constexpr int TI_MAXP = 128;
 constexpr int TI_NT = 4 * TI_MAXP;
-constexpr int TI_PITCH = TI_MAXP + 1;
-constexpr int TI_TP = 65;  // pitch of the 64 x 64 product scratch
-constexpr size_t kTriInvSmem = (size_t(TI_MAXP) * TI_PITCH + size_t(64) * TI_TP) * sizeof(double);
-
-// Off-diagonal block of the inverse of a block upper-triangular matrix [[A, B], [0, C]]:
-// X = -A^{-1} B C^{-1}, A = rows/cols a0 .. a0+n-1, C = rows/cols b0 .. b0+n-1, both inverses already
-// in the tile (strict upper parts transposed into the lower triangle, diagonals in yd).  X is stored
-// like the rest of the inverse (transposed, below the diagonal).  Called by `nthr` consecutive threads
-// (local index lt), n * n outputs, NO = outputs per thread along a row.  Returns this thread's share of
-// ||X||_F^2 over entries with both indices < p.
-template <int N, int NO>
-__device__ __forceinline__ double tri_offdiag_block(double* __restrict__ S, const double* __restrict__ yd,
-                                                    double* __restrict__ T, int a0, int b0, int lt, int p,
-                                                    int bar_id, int nthr) {
-    constexpr int CG = N / NO;  // column groups per row
-    const int r = lt / CG, cg = lt % CG;
-    // T = B C^{-1}:  T[r][c] = sum_{k <= c} B[r][k] Cinv[k][c]
-    {
-        double acc[NO];
-#pragma unroll
-        for (int u = 0; u < NO; ++u) acc[u] = 0.0;
-        const double* brow = S + (a0 + r) * TI_PITCH + b0;
-        for (int k = 0; k < N; ++k) {
-            const double bk = brow[k];
-#pragma unroll
-            for (int u = 0; u < NO; ++u) {
-                const int c = cg + CG * u;
-                const double y = (k < c) ? S[(b0 + c) * TI_PITCH + b0 + k] : ((k == c) ? yd[b0 + c] : 0.0);
-                acc[u] = fma(bk, y, acc[u]);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < NO; ++u) T[r * TI_TP + cg + CG * u] = acc[u];
-    }
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthr) : "memory");
-    // X = -A^{-1} T:  X[r][c] = -sum_{k >= r} Ainv[r][k] T[k][c]
-    double f2 = 0.0;
-    {
-        double acc[NO];
-#pragma unroll
-        for (int u = 0; u < NO; ++u) acc[u] = 0.0;
-        for (int k = r; k < N; ++k) {
-            const double ak = (k == r) ? yd[a0 + r] : S[(a0 + k) * TI_PITCH + a0 + r];
-#pragma unroll
-            for (int u = 0; u < NO; ++u) acc[u] = fma(ak, T[k * TI_TP + cg + CG * u], acc[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < NO; ++u) {
-            const int c = cg + CG * u;
-            const double x = -acc[u];
-            S[(b0 + c) * TI_PITCH + a0 + r] = x;
-            if (a0 + r < p && b0 + c < p) f2 = fma(x, x, f2);
-        }
-    }
-    return f2;
-}
-
-// Blocked: the four 32 x 32 diagonal blocks are inverted concurrently (column j by back substitution on
-// the four lanes (j, part): lane `part` owns the terms k = part (mod 4) and is the lane that stored them,
-// so a column needs no barrier), then the off-diagonal blocks follow from two levels of small products.
-// The matrix is padded to 128 x 128 with an identity block, which never enters the norms.
-__global__ void __launch_bounds__(TI_NT, 1) tri_inv_fro_kernel(const double* __restrict__ R, int p, int64_t ldr,
-                                                               double* __restrict__ out) {
+// X = R^{-1} by blocked BACKWARD substitution with 8 x 8 blocks on the tensor pipe.
+// Warp w owns block column w of X (X_kw = 0 for k > w, X_ww = R_ww^{-1}) and works up the rows:
+//     X_iw = -R_ii^{-1} sum_{k = i+1 .. w} R_ik X_kw           (i = w-1 .. 0)
+// with the sum on the tensor pipe.  The block columns are independent, so after the diagonal blocks have
+// been inverted (one per warp, one column per lane) no block-level barrier is needed.  X_iw is stored
+// transposed in the strict lower triangle of the tile (R lives in the upper one), the inverted diagonal
+// blocks in a side array.  16 warps x 8 columns = 128 columns; padded with an identity block beyond p.
+constexpr int TD_P = TI_MAXP + 4;  // tile pitch: == 4 (mod 16) doubles, conflict-free DMMA fragments
+constexpr size_t kTriInvDmmaSmem = (size_t(TI_MAXP) * TD_P + 16 * 8 * 9 + 16 * 8 * 9) * sizeof(double);
+__global__ void __launch_bounds__(TI_NT, 1) tri_inv_fro_dmma_kernel(const double* __restrict__ R, int p, int64_t ldr,
+                                                                    double* __restrict__ out) {
     extern __shared__ __align__(16) double sm[];
-    constexpr int pitch = TI_PITCH;
-    double* S = sm;                          // [128][pitch]
-    double* T = sm + TI_MAXP * TI_PITCH;     // [64][TI_TP]
-    __shared__ double yd[TI_MAXP];
+    double* S = sm;                          // [128][TD_P]
+    double* Dinv = sm + TI_MAXP * TD_P;      // [16][8][9]: inverted diagonal blocks
+    double* Scr = Dinv + 16 * 8 * 9;         // [16][8][9]: per-warp staging of one 8 x 8 block
     __shared__ double red[2][TI_NT / 32];
     __shared__ int bad_sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fq = lane & 3;
     if (tid == 0) bad_sh = 0;
     double fro2 = 0.0;
-    for (int idx = tid; idx < TI_MAXP * TI_MAXP; idx += TI_NT) {
-        const int r = idx >> 7, c = idx & 127;
-        double v = 0.0;
-        if (r < p && c < p) {
-            if (c >= r) v = R[int64_t(r) * ldr + c];
-            fro2 = fma(v, v, fro2);
-        } else if (r == c) {
-            v = 1.0;
-        }
-        S[r * pitch + c] = v;
-    }
-    __syncthreads();
-    if (tid < TI_MAXP) {
-        const double d = S[tid * pitch + tid];
-        if (!(fabs(d) > 0.0) || !(fabs(d) < 1e300)) bad_sh = 1;
-        yd[tid] = 1.0 / d;
-    }
-    __syncthreads();
-    double f2 = 0.0;
-    if (!bad_sh) {  // uniform
-        {
-            const int j = tid >> 2, part = tid & 3;
-            const unsigned gmask = 0xFu << (tid & 28);
-            const int lo = j & ~31;  // first row of this column's diagonal block
-            const double ydj = yd[j];
-            if (part == 0 && j < p) f2 = ydj * ydj;
-            const double* yj = S + j * pitch;  // Y[k][j] for k < j lives at S[j][k]
-            for (int i = j - 1; i >= lo; --i) {
-                const double* ri = S + i * pitch;
-                // terms k = i+1 .. j-1 from the tile, k = j from the diagonal inverse
-                double s0 = 0.0, s1 = 0.0;
-                int k = i + 1 + ((part - (i + 1)) & 3);
-                for (; k + 4 < j; k += 8) {
-                    const double a0 = ri[k], a1 = ri[k + 4];
-                    const double b0 = yj[k], b1 = yj[k + 4];
-                    s0 = fma(a0, b0, s0);
-                    s1 = fma(a1, b1, s1);
-                }
-                if (k < j) s0 = fma(ri[k], yj[k], s0);
-                if (part == 0) s1 = fma(ri[j], ydj, s1);
-                double sum = s0 + s1;
-                sum += __shfl_xor_sync(gmask, sum, 1);
-                sum += __shfl_xor_sync(gmask, sum, 2);
-                const double y = -sum * yd[i];
-                if (part == (i & 3)) {
-                    S[j * pitch + i] = y;
-                    if (j < p) f2 = fma(y, y, f2);
-                }
+    {
+        constexpr int NL = TI_MAXP * TI_MAXP / TI_NT;  // 32 loads per thread, all in flight
+        double v[NL];
+#pragma unroll
+        for (int u = 0; u < NL; ++u) {
+            const int idx = tid + u * TI_NT;
+            const int r = idx >> 7, c = idx & 127;
+            v[u] = 0.0;
+            if (r < p && c < p) {
+                if (c >= r) v[u] = R[int64_t(r) * ldr + c];
+            } else if (r == c) {
+                v[u] = 1.0;
             }
         }
-        __syncthreads();
-        // level 1: blocks (0,1) and (2,3), 256 threads each, 32 x 32 outputs (4 per thread)
-        {
-            const int half = tid >> 8, lt = tid & 255;
-            f2 += tri_offdiag_block<32, 4>(S, yd, T + half * 32 * TI_TP, half * 64, half * 64 + 32, lt, p, 1 + half, 256);
+#pragma unroll
+        for (int u = 0; u < NL; ++u) {
+            const int idx = tid + u * TI_NT;
+            const int r = idx >> 7, c = idx & 127;
+            if (r < p && c < p) fro2 = fma(v[u], v[u], fro2);
+            S[r * TD_P + c] = v[u];
         }
-        __syncthreads();
-        // level 2: block (0..63, 64..127), all 512 threads, 64 x 64 outputs (8 per thread)
-        if (p > 64) f2 += tri_offdiag_block<64, 8>(S, yd, T, 0, 64, tid, p, 3, TI_NT);
+    }
+    __syncthreads();
+    // ---- inverted diagonal blocks: warp w, lane c < 8 solves R_ww x = e_c by back substitution ----
+    double f2 = 0.0;
+    if (lane < 8) {
+        const int b0 = 8 * warp, c = lane;
+        double x[8];
+        bool bad = false;
+#pragma unroll
+        for (int rr = 7; rr >= 0; --rr) {
+            double sacc = (rr == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k > rr && k <= c) sacc = fma(-S[(b0 + rr) * TD_P + b0 + k], x[k], sacc);
+            const double d = S[(b0 + rr) * TD_P + b0 + rr];
+            if (!(fabs(d) > 0.0) || !(fabs(d) < 1e300)) bad = true;
+            x[rr] = (rr <= c) ? sacc / d : 0.0;
+        }
+        if (bad) bad_sh = 1;
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+            Dinv[(warp * 8 + rr) * 9 + c] = x[rr];
+            if (b0 + rr < p && b0 + c < p) f2 = fma(x[rr], x[rr], f2);
+        }
+    }
+    __syncthreads();
+    if (!bad_sh) {  // uniform
+        const int w = warp;
+        double* scr = Scr + w * 72;
+        for (int i = (8 * w < p) ? w - 1 : -1; i >= 0; --i) {  // block columns beyond p are identity padding
+            double a0 = 0.0, a1 = 0.0;
+            for (int k = i + 1; k <= w; ++k) {
+#pragma unroll
+                for (int kh = 0; kh < 2; ++kh) {
+                    const int kk = 4 * kh + fq;
+                    const double a = S[(8 * i + fr) * TD_P + 8 * k + kk];  // R_ik[fr][kk]
+                    // X_kw[kk][fr]: the diagonal block from Dinv, the others transposed below the diagonal
+                    const double b = (k == w) ? Dinv[(w * 8 + kk) * 9 + fr] : S[(8 * w + fr) * TD_P + 8 * k + kk];
+                    dmma884(a0, a1, a, b);
+                }
+            }
+            // X_iw = -Dinv_i . acc: stage acc (C layout) so that it can be read back as a B operand
+            scr[fr * 9 + 2 * fq] = a0;
+            scr[fr * 9 + 2 * fq + 1] = a1;
+            __syncwarp();
+            double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+            for (int kh = 0; kh < 2; ++kh) {
+                const int kk = 4 * kh + fq;
+                dmma884(r0, r1, Dinv[(i * 8 + fr) * 9 + kk], scr[kk * 9 + fr]);
+            }
+            __syncwarp();
+            r0 = -r0;
+            r1 = -r1;
+            // element X[8i + fr][8w + 2fq (+1)] -> transposed storage S[8w + col][8i + fr]
+            S[(8 * w + 2 * fq) * TD_P + 8 * i + fr] = r0;
+            S[(8 * w + 2 * fq + 1) * TD_P + 8 * i + fr] = r1;
+            if (8 * i + fr < p) {
+                if (8 * w + 2 * fq < p) f2 = fma(r0, r0, f2);
+                if (8 * w + 2 * fq + 1 < p) f2 = fma(r1, r1, f2);
+            }
+            __syncwarp();
+        }
     }
     fro2 = warp_sum(fro2);
     f2 = warp_sum(f2);
@@ -1134,13 +1105,13 @@ bool tri_inv_fro_supported(int p) { return p >= 1 && p <= TI_MAXP; }
 
 int tri_inv_fro(const double* R, int p, int64_t ldr, double* out_dev, cudaStream_t stream) {
     TTB_REQUIRE(tri_inv_fro_supported(p), "tri_inv_fro: unsupported size");
-    const size_t smem = kTriInvSmem;
-    static bool configured = false;
-    if (!configured) {
-        TTB_CHECK_CUDA(cudaFuncSetAttribute(tri_inv_fro_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        configured = true;
+    static bool dconf = false;
+    if (!dconf) {
+        TTB_CHECK_CUDA(cudaFuncSetAttribute(tri_inv_fro_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            int(kTriInvDmmaSmem)));
+        dconf = true;
     }
-    tri_inv_fro_kernel<<<1, TI_NT, smem, stream>>>(R, p, ldr, out_dev);
+    tri_inv_fro_dmma_kernel<<<1, TI_NT, kTriInvDmmaSmem, stream>>>(R, p, ldr, out_dev);
     ++g_launch_count;
     TTB_CHECK_CUDA(cudaGetLastError());
     return kOk;
