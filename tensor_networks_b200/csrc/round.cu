@@ -234,8 +234,33 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
         ProfScope ps_("svd.jacobi", stream);
         // wide-LQ builds U from the rotated rows themselves: their mutual orthogonality must hold in
         // the relative sense, so no absolute skip threshold there
-        jst = jacobi_rows(X, p, q, q, J, path == kPathWideLQ ? 0.0 : jacobi_abs_tol, noise_floor, 40, &sweeps, conv,
-                          hw.conv, stream);
+        // After deflation X is p x q with q >> p (the first p rows of R).  Rotating such long rows is wasteful
+        // (and beyond ~512 columns does not fit the single-launch kernel): a second, tiny LQ  X = R2^T Q2
+        // leaves a p x p factor to rotate, and J X = (J R2^T) Q2 is one small GEMM.
+        static const bool lq2_enabled = [] {
+            const char* e = getenv("TTB_SVD_LQ2");
+            return e == nullptr || e[0] != '0';
+        }();
+        const double jtol = path == kPathWideLQ ? 0.0 : jacobi_abs_tol;
+        if (lq2_enabled && path != kPathWideDirect && p >= 2 && q >= 2 * p) {
+            double* R2 = Lm;                       // p x p
+            double* L2 = Lm + size_t(p) * p;       // p x p = R2^T, the rows to rotate
+            int64_t rk2 = p;
+            TTB_PROPAGATE(orth_rows(X, p, q, q, R2, p, sub, rest, stream, 0.0, &rk2));  // X <- Q2 (orthonormal rows)
+            TTB_PROPAGATE(transpose(R2, p, p, p, L2, p, stream));
+            jst = jacobi_rows(L2, p, p, p, J, jtol, noise_floor, 40, &sweeps, conv, hw.conv, stream);
+            if (jst == kOk || jst == kNotConverged) {
+                GemmArgs g;  // Xrot (p x q) = L2rot (p x p) . Q2 (p x q)
+                g.M = p; g.N = q; g.K = p;
+                g.A = L2; g.sAm = p; g.sAk = 1;
+                g.B = X; g.sBk = q; g.sBn = 1;
+                g.C = Jsel; g.ldc = q;
+                TTB_PROPAGATE(gemm(g, sub, rest, stream));
+                TTB_CHECK_CUDA(cudaMemcpyAsync(X, Jsel, size_t(p) * q * 8, cudaMemcpyDeviceToDevice, stream));
+            }
+        } else {
+            jst = jacobi_rows(X, p, q, q, J, jtol, noise_floor, 40, &sweeps, conv, hw.conv, stream);
+        }
     }
     if (jst != kOk && jst != kNotConverged) return jst;
     g_t_jac += pt.tick();
