@@ -181,6 +181,137 @@ __global__ void __launch_bounds__(256) splitk_reduce_small_kernel(const double* 
     }
 }
 
+// ---------------------------------------------------------------------------
+// Skinny shapes (at most 16 rows on the short side, a very long other side): the 64-row tiles would spend
+// 4-16x the useful DMMA work on padding -- the first TT-SVD unfolding (16 x 16.7M) ran its Gram and solve
+// GEMMs at full tensor rate on 94 % zeros.  These two kernels are bound by HBM instead.
+// ---------------------------------------------------------------------------
+// C-partials of A (M x K) . B^T (N x K)^T, M, N <= 16, both K-contiguous: every warp streams a contiguous
+// K range straight from global memory in DMMA fragment layout (8 rows x 4 consecutive doubles = whole
+// 32-byte sectors), block-level sum in shared memory, one partial per CTA: P[cta][M * N].
+__global__ void __launch_bounds__(256) skinny_gram_kernel(const double* __restrict__ A, int64_t lda,
+                                                          const double* __restrict__ B, int64_t ldb, int M, int N,
+                                                          int64_t K, double* __restrict__ P) {
+    __shared__ double red[8][16 * 17];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fq = lane & 3;
+    const int64_t ksteps = (K + 3) >> 2;
+    const int64_t tw = int64_t(gridDim.x) * 8, gw = int64_t(blockIdx.x) * 8 + warp;
+    const int64_t ks0 = (ksteps * gw) / tw, ks1 = (ksteps * (gw + 1)) / tw;
+    const bool va0 = fr < M, va1 = 8 + fr < M, vb0 = fr < N, vb1 = 8 + fr < N;
+    const double* a0p = A + int64_t(va0 ? fr : 0) * lda + fq;
+    const double* a1p = A + int64_t(va1 ? 8 + fr : 0) * lda + fq;
+    const double* b0p = B + int64_t(vb0 ? fr : 0) * ldb + fq;
+    const double* b1p = B + int64_t(vb1 ? 8 + fr : 0) * ldb + fq;
+    double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+    int64_t ks = ks0;
+    const int64_t full_end = ks0 + ((ks1 - ks0) & ~int64_t(3));
+    const bool tail_possible = (K & 3) != 0;
+    for (; ks < full_end; ks += 4) {
+        double a0[4], a1[4], b0[4], b1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t k = 4 * (ks + u);
+            const bool in = !tail_possible || (k + fq < K);
+            a0[u] = (va0 && in) ? a0p[k] : 0.0;
+            a1[u] = (va1 && in) ? a1p[k] : 0.0;
+            b0[u] = (vb0 && in) ? b0p[k] : 0.0;
+            b1[u] = (vb1 && in) ? b1p[k] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            dmma884(acc[0][0][0], acc[0][0][1], a0[u], b0[u]);
+            dmma884(acc[0][1][0], acc[0][1][1], a0[u], b1[u]);
+            dmma884(acc[1][0][0], acc[1][0][1], a1[u], b0[u]);
+            dmma884(acc[1][1][0], acc[1][1][1], a1[u], b1[u]);
+        }
+    }
+    for (; ks < ks1; ++ks) {
+        const int64_t k = 4 * ks;
+        const bool in = k + fq < K;
+        const double a0 = (va0 && in) ? a0p[k] : 0.0, a1 = (va1 && in) ? a1p[k] : 0.0;
+        const double b0 = (vb0 && in) ? b0p[k] : 0.0, b1 = (vb1 && in) ? b1p[k] : 0.0;
+        dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+        dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+        dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+        dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            red[warp][(8 * t + fr) * 17 + 8 * u + 2 * fq] = acc[t][u][0];
+            red[warp][(8 * t + fr) * 17 + 8 * u + 2 * fq + 1] = acc[t][u][1];
+        }
+    __syncthreads();
+    {
+        const int r = tid >> 4, c = tid & 15;
+        if (r < M && c < N) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) sum += red[w][r * 17 + c];
+            P[size_t(blockIdx.x) * size_t(M) * N + r * N + c] = sum;
+        }
+    }
+}
+
+// C (M x N) = alpha A (M x K) B (K x N) + beta C with M, K <= 16 and B, C contiguous along the long side n.
+// A thread owns one or two columns: it reads all K entries of them before it writes, so C may alias B.
+template <bool VEC>
+__global__ void __launch_bounds__(256) skinny_apply_kernel(const double* __restrict__ A, int64_t sAm, int64_t sAk,
+                                                           const double* B, int64_t ldb, double* C, int64_t ldc, int M,
+                                                           int K, int64_t N, double alpha, double beta) {
+    __shared__ double Ws[16][16];
+    {
+        const int r = threadIdx.x >> 4, k = threadIdx.x & 15;
+        Ws[r][k] = (r < M && k < K) ? alpha * A[r * sAm + k * sAk] : 0.0;
+    }
+    __syncthreads();
+    constexpr int W = VEC ? 2 : 1;
+    const int64_t ncols = (N + W - 1) / W;
+    for (int64_t cp = int64_t(blockIdx.x) * 256 + threadIdx.x; cp < ncols; cp += int64_t(gridDim.x) * 256) {
+        const int64_t n = cp * W;
+        double bx[16], by[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            bx[k] = 0.0;
+            by[k] = 0.0;
+            if (k < K) {
+                if (VEC) {
+                    const double2 v = *reinterpret_cast<const double2*>(B + int64_t(k) * ldb + n);
+                    bx[k] = v.x;
+                    by[k] = v.y;
+                } else {
+                    bx[k] = B[int64_t(k) * ldb + n];
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            if (r >= M) break;
+            double sx = 0.0, sy = 0.0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const double w = Ws[r][k];
+                sx = fma(w, bx[k], sx);
+                if (VEC) sy = fma(w, by[k], sy);
+            }
+            double* dst = C + int64_t(r) * ldc + n;
+            if (VEC) {
+                double2 o = make_double2(sx, sy);
+                if (beta != 0.0) {
+                    const double2 old = *reinterpret_cast<const double2*>(dst);
+                    o.x = fma(beta, old.x, o.x);
+                    o.y = fma(beta, old.y, o.y);
+                }
+                *reinterpret_cast<double2*>(dst) = o;
+            } else {
+                *dst = (beta != 0.0) ? fma(beta, *dst, sx) : sx;
+            }
+        }
+    }
+}
+
 struct TileInfo {
     int bm, bn, occ;
     double eff;
@@ -262,6 +393,48 @@ int gemm(const GemmArgs& g, void* ws, size_t ws_bytes, cudaStream_t stream) {
     TTB_REQUIRE(g.sAm == 1 || g.sAk == 1, "gemm: A must be contiguous along m or k");
     TTB_REQUIRE(g.sBk == 1 || g.sBn == 1, "gemm: B must be contiguous along k or n");
     TTB_REQUIRE(g.ldc >= g.N, "gemm: ldc < N");
+
+    // ---- skinny shapes: HBM-bound kernels instead of padded 64-row tiles ----
+    static const bool skinny_enabled = [] {
+        const char* e = getenv("TTB_GEMM_SKINNY");
+        return e == nullptr || e[0] != '0';
+    }();
+    if (skinny_enabled && g.batch == 1 && g.M <= 16) {
+        if (g.N <= 16 && g.K >= 32768 && g.sAk == 1 && g.sBk == 1) {
+            // A (M x K) . B (K x N) with both operands K-contiguous (Gram / projection coefficients)
+            const int grid = 2 * num_sms();
+            const size_t need = size_t(grid) * size_t(g.M) * size_t(g.N) * sizeof(double);
+            if (ws != nullptr && ws_bytes >= need) {
+                const int slot = profile_begin(stream);
+                skinny_gram_kernel<<<grid, 256, 0, stream>>>(g.A, g.sAm, g.B, g.sBn, int(g.M), int(g.N), g.K,
+                                                             static_cast<double*>(ws));
+                profile_end(slot, 2.0 * double(g.M) * double(g.N) * double(g.K), stream);
+                dim3 rgrid(static_cast<unsigned>(ceil_div<int64_t>(g.M * g.N, 32)), 1u);
+                splitk_reduce_small_kernel<<<rgrid, 256, 0, stream>>>(static_cast<double*>(ws), g.C, g.M, g.N, g.ldc, 0, grid,
+                                                                      g.alpha, g.beta);
+                g_launch_count += 2;
+                TTB_CHECK_CUDA(cudaGetLastError());
+                return kOk;
+            }
+        }
+        if (g.K <= 16 && g.N >= 32768 && g.sBn == 1) {
+            // A (M x K, tiny) . B (K x N, n-contiguous): one pass over B, C may alias B
+            const bool vec = ptr16(g.B) && ptr16(g.C) && (g.sBk % 2 == 0) && (g.ldc % 2 == 0) && (g.N % 2 == 0);
+            const int64_t cols = vec ? g.N / 2 : g.N;
+            const int grid = int(std::min<int64_t>(ceil_div<int64_t>(cols, 256), int64_t(num_sms()) * 16));
+            const int slot = profile_begin(stream);
+            if (vec)
+                skinny_apply_kernel<true><<<grid, 256, 0, stream>>>(g.A, g.sAm, g.sAk, g.B, g.sBk, g.C, g.ldc, int(g.M), int(g.K),
+                                                                    g.N, g.alpha, g.beta);
+            else
+                skinny_apply_kernel<false><<<grid, 256, 0, stream>>>(g.A, g.sAm, g.sAk, g.B, g.sBk, g.C, g.ldc, int(g.M), int(g.K),
+                                                                     g.N, g.alpha, g.beta);
+            profile_end(slot, 2.0 * double(g.M) * double(g.N) * double(g.K), stream);
+            ++g_launch_count;
+            TTB_CHECK_CUDA(cudaGetLastError());
+            return kOk;
+        }
+    }
 
     // layout: prefer the K-contiguous reading when both strides are 1
     const bool a_kc = (g.sAk == 1) && !(g.sAm == 1 && g.M > 1 && g.K == 1);

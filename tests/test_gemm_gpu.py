@@ -79,3 +79,34 @@ def test_sweep_shapes():
     # projection-like skinny shapes
     _run(32, 224, 4096, True, True)
     _run(32, 4096, 224, True, False, alpha=-1.0, beta=1.0)
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 1 << 20), (16, 16, 100003), (7, 5, 65536), (1, 16, 40000), (9, 16, 32769)])
+def test_skinny_gram_shapes(shape):
+    """<= 16 x <= 16 outputs over a very long K, both operands K-contiguous: the HBM-bound streaming kernel
+    (first TT-SVD unfolding), with and without a ragged tail / odd leading dimensions, alpha / beta."""
+    _run(*shape, True, True)
+    _run(*shape, True, True, alpha=-0.5, beta=2.0, pad=1)
+
+
+@pytest.mark.parametrize("shape", [(16, 1 << 20, 16), (16, 100001, 16), (5, 65536, 9), (1, 40000, 16), (16, 32768, 3)])
+def test_skinny_apply_shapes(shape):
+    """<= 16 x <= 16 coefficient matrix applied to a very long n-contiguous operand."""
+    _run(*shape, True, False)
+    _run(*shape, False, False, alpha=-1.0, beta=1.0, pad=1)
+
+
+def test_skinny_apply_in_place():
+    """C aliases B (the Cholesky-QR solve P <- L^{-1} P of a 16-row panel)."""
+    from tensor_networks_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    w, n = 16, 300000
+    A = torch.randn((w, w), dtype=torch.float64, device="cuda", generator=g)
+    P = torch.randn((w, n), dtype=torch.float64, device="cuda", generator=g)
+    ref = A.cpu().numpy() @ P.cpu().numpy()
+    _lib.check(L.ttb_gemm_f64(w, n, w, 1.0, A.data_ptr(), w, 1, P.data_ptr(), n, 1, 0.0, P.data_ptr(), n, None, 0, None))
+    torch.cuda.synchronize()
+    scale = np.abs(A.cpu().numpy()) @ np.abs(ref) + 1.0
+    assert np.max(np.abs(P.cpu().numpy() - ref) / scale) < 1e-14
