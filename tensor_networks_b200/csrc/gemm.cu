@@ -189,6 +189,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_small_kernel(const double* 
 // C-partials of A (M x K) . B^T (N x K)^T, M, N <= 16, both K-contiguous: every warp streams a contiguous
 // K range straight from global memory in DMMA fragment layout (8 rows x 4 consecutive doubles = whole
 // 32-byte sectors), block-level sum in shared memory, one partial per CTA: P[cta][M * N].
+// SAME: B is A (a Gram matrix): the B fragment of a lane IS its A fragment, nothing is loaded twice.
+template <bool SAME, bool VEC2>
 __global__ void __launch_bounds__(256) skinny_gram_kernel(const double* __restrict__ A, int64_t lda,
                                                           const double* __restrict__ B, int64_t ldb, int M, int N,
                                                           int64_t K, double* __restrict__ P) {
@@ -197,7 +199,11 @@ __global__ void __launch_bounds__(256) skinny_gram_kernel(const double* __restri
     const int fr = lane >> 2, fq = lane & 3;
     const int64_t ksteps = (K + 3) >> 2;
     const int64_t tw = int64_t(gridDim.x) * 8, gw = int64_t(blockIdx.x) * 8 + warp;
-    const int64_t ks0 = (ksteps * gw) / tw, ks1 = (ksteps * (gw + 1)) / tw;
+    int64_t ks0 = (ksteps * gw) / tw, ks1 = (ksteps * (gw + 1)) / tw;
+    if (VEC2) {  // even boundaries (pairs of k-steps); the last warp keeps the true end
+        ks0 &= ~int64_t(1);
+        if (gw + 1 < tw) ks1 &= ~int64_t(1);
+    }
     const bool va0 = fr < M, va1 = 8 + fr < M, vb0 = fr < N, vb1 = 8 + fr < N;
     const double* a0p = A + int64_t(va0 ? fr : 0) * lda + fq;
     const double* a1p = A + int64_t(va1 ? 8 + fr : 0) * lda + fq;
@@ -205,21 +211,68 @@ __global__ void __launch_bounds__(256) skinny_gram_kernel(const double* __restri
     const double* b1p = B + int64_t(vb1 ? 8 + fr : 0) * ldb + fq;
     double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
     int64_t ks = ks0;
-    const int64_t full_end = ks0 + ((ks1 - ks0) & ~int64_t(3));
-    const bool tail_possible = (K & 3) != 0;
-    for (; ks < full_end; ks += 4) {
-        double a0[4], a1[4], b0[4], b1[4];
+    if (VEC2) {
+        // 16-byte loads: a lane fetches columns (8 j + 2 fq, 8 j + 2 fq + 1) of its row; the .x halves of the four
+        // fq lanes form one DMMA k-step (columns 8j + {0, 2, 4, 6}), the .y halves the next -- any assignment of
+        // columns to k slots is valid as long as A and B fragments agree.  Requires K % 8 == 0 per pair range.
+        constexpr int UP = 8;  // pairs of k-steps per batch (64 columns = 512 contiguous bytes per row)
+        const int64_t pairs0 = ks0 >> 1;  // ks0 is even for VEC2 launches
+        const int64_t pairs1 = (ks1 >> 1) < (K >> 3) ? (ks1 >> 1) : (K >> 3);  // whole 8-column groups only
+        const double* a0v = A + int64_t(va0 ? fr : 0) * lda + 2 * fq;
+        const double* a1v = A + int64_t(va1 ? 8 + fr : 0) * lda + 2 * fq;
+        const double* b0v = B + int64_t(vb0 ? fr : 0) * ldb + 2 * fq;
+        const double* b1v = B + int64_t(vb1 ? 8 + fr : 0) * ldb + 2 * fq;
+        int64_t pr = pairs0;
+        for (; pr + UP <= pairs1; pr += UP) {
+            double2 a0[UP], a1[UP], b0[UP], b1[UP];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < UP; ++u) {
+                const int64_t k = 8 * (pr + u);
+                a0[u] = va0 ? *reinterpret_cast<const double2*>(a0v + k) : make_double2(0.0, 0.0);
+                a1[u] = va1 ? *reinterpret_cast<const double2*>(a1v + k) : make_double2(0.0, 0.0);
+                if (SAME) {
+                    b0[u] = a0[u];
+                    b1[u] = a1[u];
+                } else {
+                    b0[u] = vb0 ? *reinterpret_cast<const double2*>(b0v + k) : make_double2(0.0, 0.0);
+                    b1[u] = vb1 ? *reinterpret_cast<const double2*>(b1v + k) : make_double2(0.0, 0.0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UP; ++u) {
+                dmma884(acc[0][0][0], acc[0][0][1], a0[u].x, b0[u].x);
+                dmma884(acc[0][1][0], acc[0][1][1], a0[u].x, b1[u].x);
+                dmma884(acc[1][0][0], acc[1][0][1], a1[u].x, b0[u].x);
+                dmma884(acc[1][1][0], acc[1][1][1], a1[u].x, b1[u].x);
+                dmma884(acc[0][0][0], acc[0][0][1], a0[u].y, b0[u].y);
+                dmma884(acc[0][1][0], acc[0][1][1], a0[u].y, b1[u].y);
+                dmma884(acc[1][0][0], acc[1][0][1], a1[u].y, b0[u].y);
+                dmma884(acc[1][1][0], acc[1][1][1], a1[u].y, b1[u].y);
+            }
+        }
+        if (pr > pairs0) ks = 2 * pr;  // the remainder (fewer than UP pairs) goes through the scalar loops below
+    }
+    constexpr int UN = 8;  // k-steps per batch: all loads of a batch are in flight before the first DMMA
+    const int64_t full_end = ks0 + ((ks1 - ks0) / UN) * UN;
+    const bool tail_possible = (K & 3) != 0;
+    for (; ks < full_end; ks += UN) {
+        double a0[UN], a1[UN], b0[UN], b1[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
             const int64_t k = 4 * (ks + u);
             const bool in = !tail_possible || (k + fq < K);
             a0[u] = (va0 && in) ? a0p[k] : 0.0;
             a1[u] = (va1 && in) ? a1p[k] : 0.0;
-            b0[u] = (vb0 && in) ? b0p[k] : 0.0;
-            b1[u] = (vb1 && in) ? b1p[k] : 0.0;
+            if (SAME) {
+                b0[u] = a0[u];
+                b1[u] = a1[u];
+            } else {
+                b0[u] = (vb0 && in) ? b0p[k] : 0.0;
+                b1[u] = (vb1 && in) ? b1p[k] : 0.0;
+            }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < UN; ++u) {
             dmma884(acc[0][0][0], acc[0][0][1], a0[u], b0[u]);
             dmma884(acc[0][1][0], acc[0][1][1], a0[u], b1[u]);
             dmma884(acc[1][0][0], acc[1][0][1], a1[u], b0[u]);
@@ -230,7 +283,7 @@ __global__ void __launch_bounds__(256) skinny_gram_kernel(const double* __restri
         const int64_t k = 4 * ks;
         const bool in = k + fq < K;
         const double a0 = (va0 && in) ? a0p[k] : 0.0, a1 = (va1 && in) ? a1p[k] : 0.0;
-        const double b0 = (vb0 && in) ? b0p[k] : 0.0, b1 = (vb1 && in) ? b1p[k] : 0.0;
+        const double b0 = SAME ? a0 : ((vb0 && in) ? b0p[k] : 0.0), b1 = SAME ? a1 : ((vb1 && in) ? b1p[k] : 0.0);
         dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
         dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
         dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
@@ -406,8 +459,11 @@ int gemm(const GemmArgs& g, void* ws, size_t ws_bytes, cudaStream_t stream) {
             const size_t need = size_t(grid) * size_t(g.M) * size_t(g.N) * sizeof(double);
             if (ws != nullptr && ws_bytes >= need) {
                 const int slot = profile_begin(stream);
-                skinny_gram_kernel<<<grid, 256, 0, stream>>>(g.A, g.sAm, g.B, g.sBn, int(g.M), int(g.N), g.K,
-                                                             static_cast<double*>(ws));
+                const bool same = g.A == g.B && g.sAm == g.sBn && g.M == g.N;
+                const bool vec2 = ptr16(g.A) && ptr16(g.B) && (g.sAm % 2 == 0) && (g.sBn % 2 == 0);
+                auto kern = same ? (vec2 ? skinny_gram_kernel<true, true> : skinny_gram_kernel<true, false>)
+                                 : (vec2 ? skinny_gram_kernel<false, true> : skinny_gram_kernel<false, false>);
+                kern<<<grid, 256, 0, stream>>>(g.A, g.sAm, g.B, g.sBn, int(g.M), int(g.N), g.K, static_cast<double*>(ws));
                 profile_end(slot, 2.0 * double(g.M) * double(g.N) * double(g.K), stream);
                 dim3 rgrid(static_cast<unsigned>(ceil_div<int64_t>(g.M * g.N, 32)), 1u);
                 splitk_reduce_small_kernel<<<rgrid, 256, 0, stream>>>(static_cast<double*>(ws), g.C, g.M, g.N, g.ldc, 0, grid,

@@ -110,3 +110,23 @@ def test_skinny_apply_in_place():
     torch.cuda.synchronize()
     scale = np.abs(A.cpu().numpy()) @ np.abs(ref) + 1.0
     assert np.max(np.abs(P.cpu().numpy() - ref) / scale) < 1e-14
+
+
+def test_skinny_gram_same_operand():
+    """G = P P^T with A and B the same buffer (fragment reuse path)."""
+    from tensor_networks_b200 import _lib
+    from tensor_networks_b200.tt import workspace
+
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for w, n in ((16, 1 << 19), (11, 70001)):
+        P = torch.randn((w, n), dtype=torch.float64, device="cuda", generator=g)
+        G = torch.empty((w, w), dtype=torch.float64, device="cuda")
+        ws = workspace(L.ttb_gemm_workspace_bytes(w, w, n), P.device, "test")
+        _lib.check(L.ttb_gemm_f64(w, w, n, 1.0, P.data_ptr(), n, 1, P.data_ptr(), 1, n, 0.0, G.data_ptr(), w,
+                                  ws.data_ptr(), ws.numel(), None))
+        torch.cuda.synchronize()
+        Ph = P.cpu().numpy()
+        ref = Ph @ Ph.T
+        scale = np.abs(Ph) @ np.abs(Ph.T)
+        assert np.max(np.abs(G.cpu().numpy() - ref) / scale) < 1e-14
