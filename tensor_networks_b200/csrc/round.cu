@@ -244,7 +244,7 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
         const double jtol = path == kPathWideLQ ? 0.0 : jacobi_abs_tol;
         if (lq2_enabled && path != kPathWideDirect && p >= 2 && q >= 2 * p) {
             double* R2 = Lm;                       // p x p
-            double* L2 = Lm + size_t(p) * p;       // p x p = R2^T, the rows to rotate
+            double* L2 = Jsel;                     // p x p = R2^T, the rows to rotate (Jsel is free until the gathers)
             int64_t rk2 = p;
             TTB_PROPAGATE(orth_rows(X, p, q, q, R2, p, sub, rest, stream, 0.0, &rk2));  // X <- Q2 (orthonormal rows)
             TTB_PROPAGATE(transpose(R2, p, p, p, L2, p, stream));
@@ -254,9 +254,9 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
                 g.M = p; g.N = q; g.K = p;
                 g.A = L2; g.sAm = p; g.sAk = 1;
                 g.B = X; g.sBk = q; g.sBn = 1;
-                g.C = Jsel; g.ldc = q;
+                g.C = Lm; g.ldc = q;  // R2 is dead after the transpose
                 TTB_PROPAGATE(gemm(g, sub, rest, stream));
-                TTB_CHECK_CUDA(cudaMemcpyAsync(X, Jsel, size_t(p) * q * 8, cudaMemcpyDeviceToDevice, stream));
+                TTB_CHECK_CUDA(cudaMemcpyAsync(X, Lm, size_t(p) * q * 8, cudaMemcpyDeviceToDevice, stream));
             }
         } else {
             jst = jacobi_rows(X, p, q, q, J, jtol, noise_floor, 40, &sweeps, conv, hw.conv, stream);
