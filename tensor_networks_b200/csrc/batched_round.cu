@@ -288,6 +288,70 @@ __device__ __forceinline__ void tile_apply32(double* __restrict__ T, int ww, int
     __syncthreads();
 }
 
+// T <- L^{-1} T for the first ww rows by blocked forward substitution (8 x 8 blocks): W holds L with its
+// four diagonal blocks replaced by their inverses (pitch RB_SP).  Row tile i first loses sum_{k<i} L_ik T_k
+// (DMMA against the finished tiles), then is multiplied by the inverse of its diagonal block.  Each warp owns
+// a 32-column slab; no explicit inverse of L, so the 32 sequential steps that built it are gone.
+__device__ __forceinline__ void tile_solve32(double* __restrict__ T, int ww, int hlen, const double* __restrict__ W) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane >> 2, fq = lane & 3;
+    const int n0 = warp * 32;
+    if (n0 < hlen) {
+        const int nt = min(4, (hlen - n0 + 7) >> 3);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (8 * i >= ww) break;  // uniform: padding rows
+            const int r = 8 * i + fr;
+            double acc[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k >= i) continue;
+#pragma unroll
+                for (int kh = 0; kh < 2; ++kh) {
+                    const int kk = 8 * k + 4 * kh + fq;
+                    const double a = W[r * RB_SP + kk];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < nt) dmma884(acc[j][0], acc[j][1], a, T[kk * QR_PITCH + n0 + 8 * j + fr]);
+                }
+            }
+            double* base = T + r * QR_PITCH + n0 + 2 * fq;
+            if (r < ww) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < nt) {
+                        double2 v = *reinterpret_cast<double2*>(base + 8 * j);
+                        v.x -= acc[j][0];
+                        v.y -= acc[j][1];
+                        *reinterpret_cast<double2*>(base + 8 * j) = v;
+                    }
+            }
+            __syncwarp();
+            double res[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) res[j][0] = res[j][1] = 0.0;
+#pragma unroll
+            for (int kh = 0; kh < 2; ++kh) {
+                const int kk = 8 * i + 4 * kh + fq;
+                const double a = W[r * RB_SP + kk];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < nt) dmma884(res[j][0], res[j][1], a, (kk < ww) ? T[kk * QR_PITCH + n0 + 8 * j + fr] : 0.0);
+            }
+            __syncwarp();
+            if (r < ww) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < nt) *reinterpret_cast<double2*>(base + 8 * j) = make_double2(res[j][0], res[j][1]);
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
 __device__ bool cholqr_tile(double* __restrict__ As, int ww, int hlen, double deflate_tol2,
                             const double* __restrict__ nrm0, const CholQrScratch sc, int* nq_out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -364,61 +428,39 @@ __device__ bool cholqr_tile(double* __restrict__ As, int ww, int hlen, double de
         }
     }
     if (tid < 32) sc.rdg[tid] = sc.flg[tid] ? 1.0 : rsqrt(sc.dsv[tid]);
-    double x[2][2];
-#pragma unroll
-    for (int ii = 0; ii < 2; ++ii)
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) x[ii][cc] = (ty + 16 * ii == tx + 16 * cc) ? 1.0 : 0.0;
-    __syncthreads();
-#pragma unroll
-    for (int kq = 0; kq < 2; ++kq) {
-        for (int kr = 0; kr < 16; ++kr) {
-            const int k = 16 * kq + kr;
-            if (k >= ww) break;  // the padding block of L is the identity: nothing below it to eliminate
-            double* cb = sc.colb + (k & 1) * 32;
-            double* rb = sc.rowb + (k & 1) * 32;
-            if (ty == kr) {
-                const double rk = sc.rdg[k];
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    x[kq][cc] *= rk;
-                    rb[tx + 16 * cc] = x[kq][cc];
-                }
-            }
-            if (tx == kr) {
-#pragma unroll
-                for (int ii = 0; ii < 2; ++ii) cb[ty + 16 * ii] = a[ii][kq];
-            }
-            __syncthreads();
-            double li[2], xr[2];
-#pragma unroll
-            for (int ii = 0; ii < 2; ++ii) li[ii] = cb[ty + 16 * ii];
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) xr[cc] = rb[tx + 16 * cc];
-#pragma unroll
-            for (int ii = 0; ii < 2; ++ii) {
-                if (ii < kq) continue;
-                if (ii == kq && ty <= kr) continue;
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) x[ii][cc] = fma(-li[ii], xr[cc], x[ii][cc]);
-            }
-        }
-    }
     __syncthreads();
 #pragma unroll
     for (int ii = 0; ii < 2; ++ii)
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
-            sc.B1[(ty + 16 * ii) * RB_SP + tx + 16 * kk] = a[ii][kk];  // L
-            sc.B2[(ty + 16 * ii) * RB_SP + tx + 16 * kk] = x[ii][kk];  // L^{-1}
+            const int i = ty + 16 * ii, k = tx + 16 * kk;
+            sc.B1[i * RB_SP + k] = a[ii][kk];                          // L
+            if ((i >> 3) != (k >> 3)) sc.B2[i * RB_SP + k] = a[ii][kk];  // off-diagonal blocks of the solve operand
         }
+    __syncthreads();
+    // inverses of the four 8 x 8 diagonal blocks of L (unit diagonal on flagged / padding vectors): warp b,
+    // one column per lane, forward substitution
+    if (warp < 4 && lane < 8) {
+        const int b0 = 8 * warp, c = lane;
+        double xv[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            double sacc = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < r && k >= c) sacc = fma(-sc.B1[(b0 + r) * RB_SP + b0 + k], xv[k], sacc);
+            xv[r] = (r >= c) ? sacc / sc.B1[(b0 + r) * RB_SP + b0 + r] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) sc.B2[(b0 + r) * RB_SP + b0 + c] = xv[r];
+    }
     if (tid == 0) {
         int n = 0;
         for (int v = 0; v < 32; ++v) sc.posI[v] = (v < ww && !sc.flg[v]) ? n++ : -1;
         sc.ibuf[1] = n;
     }
     __syncthreads();
-    tile_apply32(As, ww, hlen, sc.B2);
+    tile_solve32(As, ww, hlen, sc.B2);
     // ---- second pass ----
     tile_gram32(As, ww, hlen, sc.B3);
     {
