@@ -353,7 +353,18 @@ __device__ __forceinline__ void tile_solve32(double* __restrict__ T, int ww, int
 }
 
 __device__ bool cholqr_tile(double* __restrict__ As, int ww, int hlen, double deflate_tol2,
-                            const double* __restrict__ nrm0, const CholQrScratch sc, int* nq_out) {
+                            const double* __restrict__ nrm0, const CholQrScratch sc, int* nq_out,
+                            long long* dbg = nullptr) {
+    long long tl_ = dbg ? clock64() : 0;
+    int ts_ = 0;
+    auto cq_stamp = [&]() {
+        if (dbg && threadIdx.x == 0) {
+            const long long n_ = clock64();
+            dbg[ts_] += n_ - tl_;
+            tl_ = n_;
+        }
+        ++ts_;
+    };
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr double kFlagThr = 1e-12;  // pivot below this fraction of the vector's norm^2: candidate for D
     constexpr double kIllThr = 2.5e-3;  // (0.05)^2: the benign bound of the large-rank path (qr.cu kIllMin)
@@ -363,6 +374,7 @@ __device__ bool cholqr_tile(double* __restrict__ As, int ww, int hlen, double de
     }
     // ---- first pass: G, echelon Cholesky + inverse in registers (16 x 16 threads, 2 x 2 elements each) ----
     tile_gram32(As, ww, hlen, sc.B1);
+    cq_stamp();  // 0: gram 1
     const int ty = tid >> 4, tx = tid & 15;
     double a[2][2];
 #pragma unroll
@@ -414,6 +426,7 @@ __device__ bool cholqr_tile(double* __restrict__ As, int ww, int hlen, double de
         }
     }
     __syncthreads();
+    cq_stamp();  // 1: cholesky factor
     if (fail) return false;
     // deferred scaling; a flagged column is e_k, so that L^{-1} leaves the first-pass RESIDUAL in a flagged row
 #pragma unroll
@@ -440,8 +453,11 @@ __device__ bool cholqr_tile(double* __restrict__ As, int ww, int hlen, double de
     __syncthreads();
     // inverses of the four 8 x 8 diagonal blocks of L (unit diagonal on flagged / padding vectors): warp b,
     // one column per lane, forward substitution
-    if (warp < 4 && lane < 8) {
-        const int b0 = 8 * warp, c = lane;
+    if (warp < 4) {
+        // every lane runs the loop (c = lane & 7) so that the reciprocal diagonal can travel by shuffle;
+        // lanes >= 8 only repeat the work of lanes 0..7 and store nothing
+        const int b0 = 8 * warp, c = lane & 7;
+        const double rinv = sc.rdg[b0 + c];  // 1 / L_cc (1 for flagged / padding vectors)
         double xv[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -449,10 +465,13 @@ __device__ bool cholqr_tile(double* __restrict__ As, int ww, int hlen, double de
 #pragma unroll
             for (int k = 0; k < 8; ++k)
                 if (k < r && k >= c) sacc = fma(-sc.B1[(b0 + r) * RB_SP + b0 + k], xv[k], sacc);
-            xv[r] = (r >= c) ? sacc / sc.B1[(b0 + r) * RB_SP + b0 + r] : 0.0;
+            const double rr = __shfl_sync(0xffffffffu, rinv, r);
+            xv[r] = (r >= c) ? sacc * rr : 0.0;
         }
+        if (lane < 8) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) sc.B2[(b0 + r) * RB_SP + b0 + c] = xv[r];
+            for (int r = 0; r < 8; ++r) sc.B2[(b0 + r) * RB_SP + b0 + c] = xv[r];
+        }
     }
     if (tid == 0) {
         int n = 0;
@@ -460,9 +479,12 @@ __device__ bool cholqr_tile(double* __restrict__ As, int ww, int hlen, double de
         sc.ibuf[1] = n;
     }
     __syncthreads();
+    cq_stamp();  // 2: diag inverses
     tile_solve32(As, ww, hlen, sc.B2);
+    cq_stamp();  // 3: solve
     // ---- second pass ----
     tile_gram32(As, ww, hlen, sc.B3);
+    cq_stamp();  // 4: gram 2
     {
         double emax = 0.0;
         for (int idx = tid; idx < 32 * 32; idx += RB_NT) {
@@ -486,7 +508,9 @@ __device__ bool cholqr_tile(double* __restrict__ As, int ww, int hlen, double de
     }
     __syncthreads();
     if (sc.ibuf[0]) return false;
+    cq_stamp();  // 5: W2
     tile_apply32(As, ww, hlen, sc.B2);
+    cq_stamp();  // 6: apply 2
     // explicit residuals of D against the deflation tolerance
     for (int v = warp; v < ww; v += RB_NT / 32) {
         if (!sc.flg[v]) continue;
@@ -497,6 +521,7 @@ __device__ bool cholqr_tile(double* __restrict__ As, int ww, int hlen, double de
     }
     __syncthreads();
     if (sc.ibuf[0]) return false;
+    cq_stamp();  // 7: residuals
     // ---- R^T = (L + G2[D][I]) L2,  Rout[pos(b)][v] = R^T[v][b] ----
     for (int idx = tid; idx < 32 * RB_SP; idx += RB_NT) sc.Rout[idx] = 0.0;
     __syncthreads();
@@ -673,7 +698,7 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
             bool fast_done = false;
             if (p.use_cholqr) {
                 int nq = 0;
-                fast_done = cholqr_tile(As, ww, hlen, deflate_tol2, nrm0, sc, &nq);
+                fast_done = cholqr_tile(As, ww, hlen, deflate_tol2, nrm0, sc, &nq, (TIMING && p.dbg && blockIdx.x == 0) ? p.dbg + 12 : nullptr);
                 if (TIMING && timing) tacc[fast_done ? 8 : 9] += 1;
                 if (fast_done) {
                     nsteps = nq;
@@ -1053,7 +1078,10 @@ int round_batched(const TTBatchDesc& t, double eps, int max_rank, int64_t* ranks
                                                 int(kRoundBatchSmem)));
             TTB_CHECK_CUDA(cudaFuncSetAttribute(round_batched_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 int(kRoundBatchSmem)));
-            if (btiming) cudaMalloc(&dbg_dev, 128);
+            if (btiming) {
+                cudaMalloc(&dbg_dev, 256);
+                cudaMemset(dbg_dev, 0, 256);
+            }
             configured = true;
         }
         p.dbg = btiming ? dbg_dev : nullptr;
@@ -1065,8 +1093,10 @@ int round_batched(const TTBatchDesc& t, double eps, int max_rank, int64_t* ranks
         const int grid = int(std::min<int64_t>(t.batch, int64_t(num_sms()) * 2));
         if (btiming) {
             round_batched_kernel<true><<<grid, RB_NT, kRoundBatchSmem, stream>>>(p);
-            long long h[12];
-            cudaMemcpy(h, dbg_dev, 96, cudaMemcpyDeviceToHost);
+            long long h[24];
+            cudaMemcpy(h, dbg_dev, 192, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[bround] RQ cholqr_tile kcycles (CTA 0, cumulative): gram1 %lld chol %lld dinv %lld solve %lld gram2 %lld W2 %lld apply2 %lld resid %lld rest(in tick 8) \n",
+                    h[12] / 1000, h[13] / 1000, h[14] / 1000, h[15] / 1000, h[16] / 1000, h[17] / 1000, h[18] / 1000, h[19] / 1000);
             fprintf(stderr, "[bround] Cholesky-QR fast path: RQ %lld ok / %lld fallback, FWD %lld ok / %lld fallback\n", h[8], h[9],
                     h[10], h[11]);
             const double items = double((t.batch + grid - 1) / grid);

@@ -646,8 +646,10 @@ __device__ __forceinline__ void fp_prepare_solve(const double* __restrict__ A, d
         const int r = idx >> 6, c = idx & 63;
         if ((r >> 3) != (c >> 3)) W[r * FP_WP + c] = A[r * QF_P + c];
     }
-    if (lane < 8) {
-        const int b0 = 8 * warp, c = lane;
+    {
+        // every lane runs the loop (c = lane & 7) so that the reciprocal diagonal can travel by shuffle
+        const int b0 = 8 * warp, c = lane & 7;
+        const double rinv = 1.0 / A[(b0 + c) * QF_P + b0 + c];
         double x[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -655,10 +657,13 @@ __device__ __forceinline__ void fp_prepare_solve(const double* __restrict__ A, d
 #pragma unroll
             for (int k = 0; k < 8; ++k)
                 if (k < r && k >= c) sacc = fma(-A[(b0 + r) * QF_P + b0 + k], x[k], sacc);
-            x[r] = (r >= c) ? sacc / A[(b0 + r) * QF_P + b0 + r] : 0.0;
+            const double rr = __shfl_sync(0xffffffffu, rinv, r);
+            x[r] = (r >= c) ? sacc * rr : 0.0;
         }
+        if (lane < 8) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) W[(b0 + r) * FP_WP + b0 + c] = x[r];
+            for (int r = 0; r < 8; ++r) W[(b0 + r) * FP_WP + b0 + c] = x[r];
+        }
     }
     __syncthreads();
 }
