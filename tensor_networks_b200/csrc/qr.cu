@@ -559,6 +559,15 @@ struct FusedPanelParams {
     double* status1;      // 4 doubles
     double* status2;      // 4 doubles
     long long* timing;    // debug (TTB_FUSED_TIMING): clock64 stamps of CTA 0, or nullptr
+    // R bookkeeping folded into this launch (first accumulation of a panel, Rd_old = I): R[jq + r][jc + c] and
+    // Rd_new receive the combined factor, R[i][jc + t] += C[t][i] the projection coefficients.  fold == 0: the host
+    // launches accumulate_r_kernel instead.
+    int fold;
+    double* R;
+    int64_t ldr, jq, jc;
+    const double* C;      // w x jq (ld = ldcc) or nullptr
+    int64_t ldcc;
+    double* Rd_new;
 };
 
 __device__ __forceinline__ void fp_grid_barrier(unsigned* counter, unsigned& epoch) {
@@ -831,7 +840,13 @@ __global__ void __launch_bounds__(CH_NT, 1) fused_panel_kernel(FusedPanelParams 
                     for (int k = r + part; k <= c; k += 4) t = fma(L1[c * QF_P + k], A[k * QF_P + r], t);
                 t += __shfl_xor_sync(0xffffffffu, t, 1);
                 t += __shfl_xor_sync(0xffffffffu, t, 2);
-                if (c < p.w && part == 0) p.Rt[r * p.w + c] = t;
+                if (c < p.w && part == 0) {
+                    p.Rt[r * p.w + c] = t;
+                    if (p.fold) {
+                        p.Rd_new[r * p.w + c] = t;
+                        p.R[(p.jq + r) * p.ldr + p.jc + c] = t;
+                    }
+                }
             }
         }
         fp_prepare_solve(A, W);
@@ -856,6 +871,13 @@ __global__ void __launch_bounds__(CH_NT, 1) fused_panel_kernel(FusedPanelParams 
                 const int r = idx / FP_SLAB, c = idx % FP_SLAB;
                 if (c < ncol) p.P[int64_t(r) * p.ld + col0 + c] = S[r * FP_SP + c];
             }
+        }
+    }
+    if (p.fold && p.C != nullptr) {
+        const int64_t total = int64_t(p.w) * p.jq;
+        for (int64_t idx = int64_t(blockIdx.x) * CH_NT + tid; idx < total; idx += int64_t(gridDim.x) * CH_NT) {
+            const int64_t t = idx / p.jq, i = idx % p.jq;
+            p.R[i * p.ldr + p.jc + t] += p.C[t * p.ldcc + i];
         }
     }
 }
@@ -1372,6 +1394,10 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
                 fp.Rt = Rp;
                 fp.status1 = status;
                 fp.status2 = status + 8;
+                fp.fold = rd_ident ? 1 : 0;
+                fp.R = R; fp.ldr = ldr; fp.jq = jq; fp.jc = jc;
+                fp.C = jq > 0 ? Cb : nullptr; fp.ldcc = jq;
+                fp.Rd_new = Rd[cur ^ 1];
                 static long long* timing_dev = nullptr;
                 static const bool fused_timing = getenv("TTB_FUSED_TIMING") != nullptr;
                 if (fused_timing && !timing_dev) cudaMalloc(&timing_dev, 64 * sizeof(long long));
@@ -1425,11 +1451,13 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
                 }
                 {
                     ProfScope ps_("qr.accumulate_r", stream);
-                    accumulate_r_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jq, jc, w, jq > 0 ? Cb : nullptr, jq, fp.Rt, Rd[cur],
-                                                                    Rd[cur ^ 1], 1, rd_ident ? 1 : 0);
+                    if (!fp.fold) {
+                        accumulate_r_kernel<<<blocks, 256, 0, stream>>>(R, ldr, jq, jc, w, jq > 0 ? Cb : nullptr, jq, fp.Rt, Rd[cur],
+                                                                        Rd[cur ^ 1], 1, 0);
+                        ++g_launch_count;
+                    }
                     rd_ident = false;
                     cur ^= 1;
-                    ++g_launch_count;
                 }
             } else
             for (int rep = 0; rep < 2; ++rep) {  // Cholesky-QR twice
