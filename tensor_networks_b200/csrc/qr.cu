@@ -1749,6 +1749,12 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
         if (graph_enabled && !debug && !prof_enabled() && !gemm_profile_active()) {
             static std::map<std::tuple<int64_t, int64_t, bool>, OrthGraph> graphs;
             static cudaStream_t cap_stream = nullptr;
+            if (graphs.size() > 64 && graphs.find(std::make_tuple(c, m, deflate_tol > 0.0)) == graphs.end()) {
+                // many distinct shapes (e.g. a long solver run): start over rather than grow without bound
+                for (auto& kv : graphs)
+                    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+                graphs.clear();
+            }
             OrthGraph& G = graphs[std::make_tuple(c, m, deflate_tol > 0.0)];
             const bool same = G.R == R && G.ldr == ldr && G.ws == ws && G.ws_bytes == ws_bytes && G.tol == deflate_tol &&
                               G.version == plan.version;

@@ -166,3 +166,25 @@ def test_live_reference_side_by_side():
     out = tt_svd_round(copy.deepcopy(y), 1e-9)
     mine, _ = orc.svd_round(cy, 1e-9)
     assert orc.ranks_of(mine) == [out.value(i).shape[-1] for i in range(len(shape) - 1)]
+
+
+def test_gramsvd_host_helpers_match_oracle():
+    """The host-side pieces of the device Gram-SVD rounding (decimal rounding of sqrt-eigenvalues, rank rule)
+    against the oracle restatement -- no GPU involved."""
+    import torch
+
+    from tensor_networks_b200.gramsvd import _rounded_sqrt, eps_to_rank
+
+    rng = np.random.default_rng(0)
+    for scale in (1.0, 1e-6, 1e8):
+        eig = scale * np.concatenate([np.sort(rng.random(12))[::-1], [1e-17, -3e-18, 0.0]])
+        e12, em12 = _rounded_sqrt(torch.from_numpy(eig))
+        ref = orc.round_sqrt_eigs(eig)
+        assert np.array_equal(e12.numpy(), ref)
+        inv = np.zeros_like(ref)
+        inv[ref != 0] = 1.0 / ref[ref != 0]
+        assert np.array_equal(em12.numpy(), inv)
+    for _ in range(50):
+        s = np.sort(rng.random(int(rng.integers(1, 9))))[::-1] * 10.0 ** rng.integers(-3, 3)
+        eps = float(rng.random() * 2.0 * s[0])
+        assert eps_to_rank(s, eps) == orc.eps_to_rank(s, eps)
