@@ -198,6 +198,31 @@ int ttb_ttsvd_f64(const double* dense, int32_t d, const int64_t* shape, double e
                   double* arena, size_t arena_doubles, int64_t* ranks_out, double* delta_out,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- dense-tensor data movement for the node-level network operations -------------
+ * The tensor-network API above the TT sweeps (Tensor.svd / Tensor.qr / Tensor.contract /
+ * Tensor.permute / Tensor.block_diagonal, pytens/algs.py:201-344; tt_sum, ttop_sum,
+ * ttop_apply, :2479-2697) permutes indices, places blocks and scales rows around the
+ * GEMM / QR / SVD kernels.  All pointers are DEVICE pointers; asynchronous on `stream`. */
+
+/* dst[i_0..i_{k-1}] = src[i_0..i_{k-1}] for every multi-index below `shape` (HOST array,
+ * ndim entries); dst_strides / src_strides are element strides (HOST arrays).  A
+ * permutation is a copy with permuted source strides (np.permute_dims + reshape,
+ * pytens/algs.py:244-248, :304); a block of a block-diagonal core is a copy with the
+ * destination strides of the large array (pytens/algs.py:326-338).  No overlap allowed. */
+int ttb_strided_copy_f64(double* dst, const double* src, int32_t ndim, const int64_t* shape,
+                         const int64_t* dst_strides, const int64_t* src_strides, void* stream);
+/* dst[0..count) = value (np.zeros of the block-diagonal builders, pytens/algs.py:324) */
+int ttb_fill_f64(double* dst, int64_t count, double value, void* stream);
+/* mode 1: row i of mat (rows x cols, ld) *= s[i]; mode 2: row i /= s[i] (rows with s[i] == 0
+ * become 0): v = svt / s of delta_svd's return value (pytens/utils.py:94-100) */
+int ttb_scale_rows_f64(double* mat, int64_t rows, int64_t cols, int64_t ld, const double* s, int32_t mode,
+                       void* stream);
+/* out (n x n, row-major) = diag(s): the S node of Tensor.svd (np.diag(s), pytens/algs.py:262) */
+int ttb_diag_f64(const double* s, int64_t n, double* out, void* stream);
+/* y = alpha * x + beta * y over count elements (x may be NULL: y *= beta): TensorNetwork.scale
+ * (pytens/algs.py:578-583) and the one-node case of TensorNetwork.__add__ */
+int ttb_axpby_f64(int64_t count, double alpha, const double* x, double beta, double* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

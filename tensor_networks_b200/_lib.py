@@ -142,6 +142,17 @@ def _declare(lib):
     lib.ttb_tt_to_dense_f64.restype = c_int
     lib.ttb_tt_to_dense_f64.argtypes = [P(ttb_tt), c_void_p, c_void_p, c_size_t, c_void_p]
 
+    lib.ttb_strided_copy_f64.restype = c_int
+    lib.ttb_strided_copy_f64.argtypes = [c_void_p, c_void_p, c_int32, P(c_int64), P(c_int64), P(c_int64), c_void_p]
+    lib.ttb_fill_f64.restype = c_int
+    lib.ttb_fill_f64.argtypes = [c_void_p, c_int64, c_double, c_void_p]
+    lib.ttb_scale_rows_f64.restype = c_int
+    lib.ttb_scale_rows_f64.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int32, c_void_p]
+    lib.ttb_diag_f64.restype = c_int
+    lib.ttb_diag_f64.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
+    lib.ttb_axpby_f64.restype = c_int
+    lib.ttb_axpby_f64.argtypes = [c_int64, c_double, c_void_p, c_double, c_void_p, c_void_p]
+
 
 def lib():
     """Load (once) and return the ctypes handle; raises if the .so is absent."""

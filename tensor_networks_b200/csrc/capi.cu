@@ -8,6 +8,7 @@
 #include "qr.cuh"
 #include "batched.cuh"
 #include "ttsvd.cuh"
+#include "tensor_ops.cuh"
 
 namespace ttb {
 double debug_chol_bench_us(int w, int reps);
@@ -233,6 +234,25 @@ int ttb_ttsvd_f64(const double* dense, int32_t d, const int64_t* shape, double e
                   void* workspace, size_t workspace_bytes, void* stream) {
     return ttb::ttsvd(dense, d, shape, eps, max_rank, arena, arena_doubles, ranks_out, delta_out, workspace,
                       workspace_bytes, as_stream(stream));
+}
+
+
+int ttb_strided_copy_f64(double* dst, const double* src, int32_t ndim, const int64_t* shape,
+                         const int64_t* dst_strides, const int64_t* src_strides, void* stream) {
+    return ttb::strided_copy(dst, src, ndim, shape, dst_strides, src_strides, as_stream(stream));
+}
+int ttb_fill_f64(double* dst, int64_t count, double value, void* stream) {
+    return ttb::fill(dst, count, value, as_stream(stream));
+}
+int ttb_scale_rows_f64(double* mat, int64_t rows, int64_t cols, int64_t ld, const double* s, int32_t mode,
+                       void* stream) {
+    return ttb::scale_rows(mat, rows, cols, ld, s, mode, as_stream(stream));
+}
+int ttb_diag_f64(const double* s, int64_t n, double* out, void* stream) {
+    return ttb::diag_embed(s, n, out, as_stream(stream));
+}
+int ttb_axpby_f64(int64_t count, double alpha, const double* x, double beta, double* y, void* stream) {
+    return ttb::axpby(count, alpha, x, beta, y, as_stream(stream));
 }
 
 }  // extern "C"

@@ -643,6 +643,7 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
         // mx is the largest squared relative off-diagonal met BEFORE its rotation in this sweep; Jacobi
         // converges quadratically, so below stop_rel the rotations of this very sweep have finished the job
         converged = sqrt(mx) <= p.stop_rel;
+        if (TIMING && timing && sweep < 48) p.out[8 + sweep] = sqrt(mx);
     }
     // ---- write back ----
     for (int a = warp; a < R2; a += JB_NWARP) {
@@ -1012,11 +1013,16 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
             if (le == cudaSuccess) {
                 ++g_launch_count;
                 double* hout = reinterpret_cast<double*>(conv_host_pinned);
-                TTB_CHECK_CUDA(cudaMemcpyAsync(hout, cp.out, (jtiming ? 8 : 2) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+                TTB_CHECK_CUDA(cudaMemcpyAsync(hout, cp.out, (jtiming ? 56 : 2) * sizeof(double), cudaMemcpyDeviceToHost, stream));
                 TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
                 if (jtiming)
                     fprintf(stderr, "[jacobi] p=%d q=%d b=%d sweeps=%d clocks: gram %.0f rounds %.0f apply %.0f syncA %.0f xchg %.0f syncB %.0f\n",
                             p, q, jcb, int(hout[0]), hout[2], hout[3], hout[4], hout[5], hout[6], hout[7]);
+                if (jtiming) {
+                    fprintf(stderr, "[jacobi] max rel off-diagonal per sweep:");
+                    for (int k = 0; k < int(hout[0]) && k < 48; ++k) fprintf(stderr, " %.1e", hout[8 + k]);
+                    fprintf(stderr, "\n");
+                }
                 if (sweeps_out) *sweeps_out = int(hout[0]);
                 if (hout[1] != 0.0) return kOk;
                 set_last_error("jacobi_rows: not converged after " + std::to_string(max_sweeps) + " sweeps");

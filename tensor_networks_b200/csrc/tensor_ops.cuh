@@ -1,0 +1,20 @@
+// Dense-tensor data movement behind the node-level tensor-network operations; see tensor_ops.cu.
+#pragma once
+
+#include "common.cuh"
+
+namespace ttb {
+
+// dst[i_0..i_{k-1}] = src[i_0..i_{k-1}] over `shape`; strides in elements, any order (permutations,
+// sub-block placement, broadcasts with stride 0 on the source side).  dst and src must not overlap.
+int strided_copy(double* dst, const double* src, int ndim, const int64_t* shape, const int64_t* dst_strides,
+                 const int64_t* src_strides, cudaStream_t stream);
+int fill(double* dst, int64_t count, double value, cudaStream_t stream);
+// mode 1: row i *= s[i]; mode 2: row i /= s[i] (zero rows stay zero)
+int scale_rows(double* mat, int64_t rows, int64_t cols, int64_t ld, const double* s, int mode, cudaStream_t stream);
+// out (n x n, row-major) = diag(s)
+int diag_embed(const double* s, int64_t n, double* out, cudaStream_t stream);
+// y = alpha x + beta y (x may be null: y *= beta)
+int axpby(int64_t count, double alpha, const double* x, double beta, double* y, cudaStream_t stream);
+
+}  // namespace ttb
