@@ -211,6 +211,12 @@ int ttb_ttsvd_f64(const double* dense, int32_t d, const int64_t* shape, double e
  * destination strides of the large array (pytens/algs.py:326-338).  No overlap allowed. */
 int ttb_strided_copy_f64(double* dst, const double* src, int32_t ndim, const int64_t* shape,
                          const int64_t* dst_strides, const int64_t* src_strides, void* stream);
+/* same traversal with an elementwise update: op 0: dst = src; op 1: dst *= src (the broadcast
+ * product of Tensor.mult, pytens/algs.py:143-199: a source stride of 0 repeats the operand along
+ * that dimension); op 2: dst += alpha * src */
+int ttb_strided_op_f64(double* dst, const double* src, int32_t ndim, const int64_t* shape,
+                       const int64_t* dst_strides, const int64_t* src_strides, int32_t op, double alpha,
+                       void* stream);
 /* dst[0..count) = value (np.zeros of the block-diagonal builders, pytens/algs.py:324) */
 int ttb_fill_f64(double* dst, int64_t count, double value, void* stream);
 /* mode 1: row i of mat (rows x cols, ld) *= s[i]; mode 2: row i /= s[i] (rows with s[i] == 0

@@ -144,6 +144,10 @@ def _declare(lib):
 
     lib.ttb_strided_copy_f64.restype = c_int
     lib.ttb_strided_copy_f64.argtypes = [c_void_p, c_void_p, c_int32, P(c_int64), P(c_int64), P(c_int64), c_void_p]
+    lib.ttb_strided_op_f64.restype = c_int
+    lib.ttb_strided_op_f64.argtypes = [
+        c_void_p, c_void_p, c_int32, P(c_int64), P(c_int64), P(c_int64), c_int32, c_double, c_void_p,
+    ]
     lib.ttb_fill_f64.restype = c_int
     lib.ttb_fill_f64.argtypes = [c_void_p, c_int64, c_double, c_void_p]
     lib.ttb_scale_rows_f64.restype = c_int

@@ -1,57 +1,81 @@
-"""Host-side mirror of the `pytens.algs` surface for the tensor-train hot path.
+"""Host-side mirror of the `pytens.algs` surface for the tensor-train hot path and its callers.
 
 The reference has no plugin/FFI boundary: its public API *is* the Python functions of
 `pytens/algs.py`.  This module keeps those names, argument meanings and mutation /
-error behaviour for the TT core-sweep path and routes the arithmetic to the CUDA
-library through `TensorTrain` (ctypes -> libttb200.so):
+error behaviour and routes all arithmetic to the CUDA library (ctypes -> libttb200.so):
 
-    Tensor, TensorNetwork (TT-shaped networks)      pytens/algs.py:46-345, :363-631
+    Tensor (svd / qr / contract / permute / ...)     pytens/algs.py:46-345
+    TensorNetwork container + graph operations       :363-631
     TensorNetwork.inner / norm / scale / rand_tt     :585-594, :578-583, :1180-1218
+    TensorNetwork.svd / qr / merge                   :633-761
+    TensorNetwork.round / orthonormalize / compress  :763-955
+    TensorNetwork + - * (tree networks)              :1310-1380
     tt_right_orth(tn, node)                          :1654-1704
     tt_svd_round(tn, eps)                            :1841-1903
     tt_gramsvd_round(tn, eps), gram_eig_and_svd,
     eps_to_rank (from .gramsvd)                      :1707-1838
+    TTRandRound, tt_randomized_round, ... (.randround)   :2133-2380
+    ttop_rank1/rank2/sum/sum_apply/apply, tt_sum, gmres (.ttops)   :2383-2793
     delta_svd (re-exported from .utils)              pytens/utils.py:19-100
     tt_svd(dense, eps)   [composition, no single reference function: SURVEY 3.3]
 
-Everything else in pytens (general trees, cross approximation, structure search,
-plotting) is out of scope and raises NotImplementedError here rather than falling
-back to a CPU implementation.  The functions also accept the reference's own
-`pytens.TensorNetwork` objects (duck-typed on `.network.nodes[k]["tensor"]`), which is
-how a pytens installation would adopt this path -- see INTEGRATION.md.
+Node values may be numpy arrays (as in the reference) or CUDA float64 torch tensors; every
+operation computes on the device and returns values where its inputs lived (numpy in -> numpy
+out).  There is no CPU fallback: without the CUDA library / a GPU the numerical entry points
+raise.  Cross approximation, structure search, plotting and serialisation are out of scope.
+The functions also accept the reference's own `pytens.TensorNetwork` objects (duck-typed on
+`.network.nodes[k]["tensor"]`), which is how a pytens installation would adopt this path -- see
+INTEGRATION.md.
 """
 
 from __future__ import annotations
 
 import copy
+import itertools
 from collections import Counter
 from dataclasses import dataclass
-from typing import List, Optional, Sequence
+from typing import Any, Dict, List, Optional, Sequence, Set, Tuple
 
 import networkx as nx
 import numpy as np
 
-from .types import Index, IntOrStr, NodeName, SVDConfig  # noqa: F401
+from . import dense
+from .types import DimTreeNode, Index, IndexName, IntOrStr, NodeInfo, NodeName, SVDConfig  # noqa: F401
 from .utils import TruncSVD, delta_svd  # noqa: F401
 from .gramsvd import eps_to_rank, gram_eig_and_svd  # noqa: F401
 from .tt import TensorTrain
-from .solvers import TTOperator, gmres, ttop_apply, ttop_rank1  # noqa: F401  (device-resident TT-GMRES)
 
 __all__ = [
     "Index", "SVDConfig", "Tensor", "TensorNetwork", "TensorTrain", "TruncSVD",
-    "delta_svd", "tt_right_orth", "tt_svd_round", "tt_gramsvd_round", "eps_to_rank", "gram_eig_and_svd", "tt_svd", "round",
-    "TTOperator", "ttop_rank1", "ttop_apply", "gmres",
+    "delta_svd", "tt_right_orth", "tt_svd_round", "tt_gramsvd_round", "eps_to_rank", "gram_eig_and_svd", "tt_svd",
+    "round", "vector", "tt_rank1", "tt_separable", "rand_tree",
+    "tt_sum", "ttop_rank1", "ttop_rank2", "ttop_sum", "ttop_sum_apply", "ttop_apply", "gmres",
+    "TTRandRound", "tt_randomized_round", "tt_sum_randomized_round", "tt_rand_precond_svd_round",
 ]
+
+
+def _size(indices: Sequence[Index], positions: Sequence[int]) -> int:
+    out = 1
+    for i in positions:
+        out *= int(indices[i].size)
+    return out
 
 
 @dataclass
 class Tensor:
-    """value + indices (pytens/algs.py:46-78)."""
+    """value + indices (pytens/algs.py:46-345).  `value` is a numpy array or a CUDA tensor."""
 
-    value: np.ndarray
+    value: Any
     indices: List[Index]
 
-    def update_val_size(self, value: np.ndarray) -> "Tensor":
+    def to_dict(self) -> dict:
+        return {"value": np.ascontiguousarray(dense.to_host(self.value)), "indices": [i.to_dict() for i in self.indices]}
+
+    @classmethod
+    def from_dict(cls, data_dict: dict) -> "Tensor":
+        return cls(value=data_dict["value"], indices=[Index.from_dict(d) for d in data_dict["indices"]])
+
+    def update_val_size(self, value) -> "Tensor":
         """Rebind the value (no copy) and resize the indices -- pytens/algs.py:70-78."""
         assert value.ndim == len(self.indices), f"{value.shape}, {self.indices}"
         self.value = value
@@ -59,18 +83,149 @@ class Tensor:
             self.indices[ii] = index.with_new_size(value.shape[ii])
         return self
 
+    def rename_indices(self, rename_map: Dict[IntOrStr, IntOrStr]) -> "Tensor":
+        """pytens/algs.py:80-86."""
+        for ii, index in enumerate(self.indices):
+            if index.name in rename_map:
+                self.indices[ii] = index.with_new_name(rename_map[index.name])
+        return self
+
+    def relabel_indices(self, relabel_map: Dict[IntOrStr, Any]) -> "Tensor":
+        """pytens/algs.py:88-93."""
+        for ii, index in enumerate(self.indices):
+            if index.name in relabel_map:
+                self.indices[ii] = index.with_new_size(relabel_map[index.name])
+        return self
+
+    # ---- two-tensor builders (block placement / broadcast product on the device) ----
+    def _stack(self, other: "Tensor", keep: Sequence[Index]) -> "Tensor":
+        """Zero tensor with the non-kept dimensions summed, self in the leading corner block and
+        other in the trailing one (the common core of concat_fill and block_diagonal)."""
+        assert len(self.indices) == len(other.indices)
+        shape, new_indices, off2 = [], [], []
+        for here, there in zip(self.indices, other.indices):
+            if here in keep:
+                assert here.size == there.size
+                shape.append(here.size)
+                new_indices.append(here)
+                off2.append(0)
+            else:
+                shape.append(here.size + there.size)
+                new_indices.append(Index(here.name, here.size + there.size))
+                off2.append(here.size)
+        a, b = dense.as_dev(self.value), dense.as_dev(other.value)
+        out = dense.zeros(shape, a.device)
+        dense.place(out, a, [0] * len(shape))
+        dense.place(out, b, off2)
+        return Tensor(dense.like(out, self.value), new_indices)
+
+    def concat_fill(self, other: "Tensor", indices_common: List[Index]) -> "Tensor":
+        """Concatenate on every non-common dimension, zero fill elsewhere -- pytens/algs.py:95-141."""
+        return self._stack(other, indices_common)
+
+    def block_diagonal(self, other: "Tensor", free_inds: Sequence[Index]) -> "Tensor":
+        """Block-diagonal sum over the contracted dimensions, free dimensions kept -- pytens/algs.py:308-344."""
+        return self._stack(other, free_inds)
+
+    def mult(self, other: "Tensor", indices_common: List[Index]) -> "Tensor":
+        """Outer (Kronecker) product on every non-common dimension, elementwise on the common ones;
+        naming of self -- pytens/algs.py:143-199 (an np.einsum 'ab..,ac..->abc..' there)."""
+        assert len(self.indices) == len(other.indices)
+        a, b = dense.as_dev(self.value), dense.as_dev(other.value)
+        wide, a_st, b_st, new_shape, new_indices = [], [], [], [], []
+        sa, sb = [int(s) for s in a.stride()], [int(s) for s in b.stride()]
+        for k, (here, there) in enumerate(zip(self.indices, other.indices)):
+            if here in indices_common:
+                assert here.size == there.size
+                wide.append(here.size)
+                a_st.append(sa[k])
+                b_st.append(sb[k])
+                new_shape.append(here.size)
+                new_indices.append(here)
+            else:
+                wide += [here.size, there.size]
+                a_st += [sa[k], 0]
+                b_st += [0, sb[k]]
+                new_shape.append(here.size * there.size)
+                new_indices.append(Index(here.name, here.size * there.size))
+        out = dense.empty(wide, a.device)
+        o_st = [int(s) for s in out.stride()]
+        dense.strided_op(out, 0, o_st, a, 0, a_st, wide, op=0)
+        dense.strided_op(out, 0, o_st, b, 0, b_st, wide, op=1)
+        return Tensor(dense.like(out.view(new_shape), self.value), new_indices)
+
+    def contract(self, other: "Tensor") -> "Tensor":
+        """Contract with `other` over the common indices -- pytens/algs.py:201-236.  Result indices:
+        self's remaining ones, then other's."""
+        val, inds = dense.contract(dense.as_dev(self.value), self.indices, dense.as_dev(other.value), other.indices)
+        return Tensor(dense.like(val, self.value), inds)
+
+    def _as_matrix(self, lefts: Sequence[int]):
+        lefts = [int(i) for i in lefts]
+        rights = [i for i in range(len(self.indices)) if i not in lefts]
+        x = dense.as_dev(self.value)
+        mat = dense.permute(x, lefts + rights).view(_size(self.indices, lefts), _size(self.indices, rights))
+        return lefts, rights, mat
+
+    def svd(self, lefts: Sequence[int], delta: float = 1e-5) -> Tuple[List["Tensor"], float]:
+        """Split into [U, diag(S), V] by a delta-truncated SVD of the (lefts | rest) unfolding --
+        pytens/algs.py:238-274 (delta is absolute: delta_svd without normalising)."""
+        lefts, rights, mat = self._as_matrix(lefts)
+        u, s, svt, info = dense.trunc_svd(mat, float(delta))
+        rank = int(s.shape[0])
+        v = dense.unscale_rows(svt, s)
+        u_t = Tensor(dense.like(u.reshape([self.indices[i].size for i in lefts] + [rank]), self.value),
+                     [self.indices[i] for i in lefts] + [Index("r_split_l", rank)])
+        s_t = Tensor(dense.like(dense.diag(s), self.value), [Index("r_split_l", rank), Index("r_split_r", rank)])
+        v_t = Tensor(dense.like(v.reshape([rank] + [self.indices[j].size for j in rights]), self.value),
+                     [Index("r_split_r", rank)] + [self.indices[j] for j in rights])
+        return [u_t, s_t, v_t], float(info["remaining_delta"])
+
+    def qr(self, lefts: Sequence[int]) -> Tuple["Tensor", "Tensor"]:
+        """Split into (Q, R) by the thin QR of the (lefts | rest) unfolding -- pytens/algs.py:276-297."""
+        lefts, rights, mat = self._as_matrix(lefts)
+        q, r = dense.qr(mat)
+        k = int(q.shape[1])
+        q_t = Tensor(dense.like(q.reshape([self.indices[i].size for i in lefts] + [k]), self.value),
+                     [self.indices[i] for i in lefts] + [Index("r_split", k)])
+        r_t = Tensor(dense.like(r.reshape([k] + [self.indices[j].size for j in rights]), self.value),
+                     [Index("r_split", k)] + [self.indices[j] for j in rights])
+        return q_t, r_t
+
+    def permute(self, target_indices: Optional[Sequence[int]]) -> "Tensor":
+        """New tensor with the dimensions reordered -- pytens/algs.py:299-306."""
+        if not target_indices:
+            return self
+        val = dense.permute(dense.as_dev(self.value), list(target_indices))
+        return Tensor(dense.like(val, self.value), [self.indices[i] for i in target_indices])
+
 
 def _is_chain(tn) -> bool:
     nodes = list(tn.network.nodes)
     return nodes == list(range(len(nodes)))
 
 
-def _tt_cores(tn) -> List[np.ndarray]:
+def _is_tt(tn) -> bool:
+    """Integer nodes 0..d-1 whose values have the TT core shapes (first/last 2-d, interior 3-d)."""
+    if not _is_chain(tn):
+        return False
+    d = len(tn.network.nodes)
+    for k in range(d):
+        want = 1 if d == 1 else (2 if k in (0, d - 1) else 3)
+        if tn.network.nodes[k]["tensor"].value.ndim != want:
+            return False
+    for k in range(d - 1):  # bond k links node k's last index with node k+1's first
+        if tn.network.nodes[k]["tensor"].indices[-1] != tn.network.nodes[k + 1]["tensor"].indices[0]:
+            return False
+    return True
+
+
+def _tt_cores(tn) -> list:
     """Cores of a TT-shaped network (int nodes 0..d-1 in a chain, pytens/algs.py:1188-1216)."""
     if not _is_chain(tn):
         raise NotImplementedError(
-            "only TT-shaped networks (integer nodes 0..d-1, as built by rand_tt) are supported on the "
-            "B200 path; general tensor networks are out of scope (DESIGN.md)"
+            "the TT sweeps need a TT-shaped network (integer nodes 0..d-1, as built by rand_tt); use the "
+            "tree methods (TensorNetwork.round / svd / merge) for general networks"
         )
     d = len(tn.network.nodes)
     vals = [tn.network.nodes[k]["tensor"].value for k in range(d)]
@@ -79,7 +234,7 @@ def _tt_cores(tn) -> List[np.ndarray]:
         if d == 1:
             want = 1
         if v.ndim != want:
-            raise NotImplementedError(f"node {k}: expected a {want}-d TT core, got shape {v.shape}")
+            raise NotImplementedError(f"node {k}: expected a {want}-d TT core, got shape {tuple(v.shape)}")
     return vals
 
 
@@ -90,26 +245,54 @@ def _free_index(tn, k: int, d: int) -> Index:
     return inds[0] if k == 0 else inds[1]
 
 
+def _train_of(tn) -> TensorTrain:
+    """Device TensorTrain holding (a copy of, for host values / a view of, for device values) the cores."""
+    vals = _tt_cores(tn)
+    d = len(vals)
+    if all(dense.is_dev(v) for v in vals):
+        cores = []
+        for k, v in enumerate(vals):
+            v = dense.as_dev(v)
+            if d == 1:
+                cores.append(v.view(1, -1, 1))
+            elif k == 0:
+                cores.append(v.view(1, v.shape[0], v.shape[1]))
+            elif k == d - 1:
+                cores.append(v.view(v.shape[0], v.shape[1], 1))
+            else:
+                cores.append(v)
+        return TensorTrain(cores)
+    host = [dense.to_host(v) for v in vals]
+    return TensorTrain.from_cores(host if d > 1 else [host[0].reshape(1, -1, 1)])
+
+
 def _write_back(tn, tt: TensorTrain) -> None:
-    """Store the device cores into the network in the reference's shapes (in place)."""
+    """Store the device cores into the network in the reference's shapes (in place); values go back
+    to where they lived (numpy nodes get numpy arrays)."""
     d = tt.d
-    host = tt.to_cores()
-    for k, c in enumerate(host):
-        if k == 0 and d > 1:
+    for k, c in enumerate(tt.cores):
+        old = tn.network.nodes[k]["tensor"].value
+        if d == 1:
+            c = c.reshape(-1)
+        elif k == 0:
             c = c.reshape(c.shape[1], c.shape[2])
-        elif k == d - 1 and d > 1:
+        elif k == d - 1:
             c = c.reshape(c.shape[0], c.shape[1])
-        tn.network.nodes[k]["tensor"].update_val_size(np.ascontiguousarray(c))
+        if dense.is_dev(old):
+            val = c.clone() if c.untyped_storage().size() > 4 * c.numel() * 8 else c
+        else:
+            val = np.ascontiguousarray(dense.to_host(c))
+        tn.network.nodes[k]["tensor"].update_val_size(val)
 
 
 class TensorNetwork:
-    """TT-shaped tensor network with the reference's container layout (pytens/algs.py:363-631):
-    `self.network` is an `nx.Graph`, node k carries attribute "tensor" = Tensor(value, indices)."""
+    """Tensor network with the reference's container layout (pytens/algs.py:363-631):
+    `self.network` is an `nx.Graph`, every node carries attribute "tensor" = Tensor(value, indices)."""
 
     def __init__(self) -> None:
         self.network = nx.Graph()
 
-    # ---- container (pytens/algs.py:370-444, :574-583) ----
+    # ---- container (pytens/algs.py:370-444, :574-583, :614-631) ----
     def add_node(self, name: NodeName, tensor: Tensor) -> None:
         self.network.add_node(name, tensor=tensor)
 
@@ -122,7 +305,7 @@ class TensorNetwork:
     def add_edge(self, name1: NodeName, name2: NodeName) -> None:
         self.network.add_edge(name1, name2)
 
-    def value(self, node_name: NodeName) -> np.ndarray:
+    def value(self, node_name: NodeName):
         return self.network.nodes[node_name]["tensor"].value
 
     def all_indices(self) -> Counter:
@@ -131,8 +314,23 @@ class TensorNetwork:
             indices += data["tensor"].indices
         return Counter(indices)
 
+    def rename_indices(self, rename_map: Dict[IntOrStr, IntOrStr]) -> "TensorNetwork":
+        for _, data in self.network.nodes(data=True):
+            data["tensor"].rename_indices(rename_map)
+        return self
+
+    def relabel_indices(self, relabel_map: Dict[IntOrStr, Any]) -> "TensorNetwork":
+        for _, data in self.network.nodes(data=True):
+            data["tensor"].relabel_indices(relabel_map)
+        return self
+
     def free_indices(self) -> List[Index]:
         return [i for i, v in self.all_indices().items() if v == 1]
+
+    def get_contraction_index(self, node1: NodeName, node2: NodeName) -> List[Index]:
+        """Indices shared by two nodes -- pytens/algs.py:418-427."""
+        both = list(self.network.nodes[node1]["tensor"].indices) + list(self.network.nodes[node2]["tensor"].indices)
+        return [i for i, v in Counter(both).items() if v > 1]
 
     def inner_indices(self) -> List[Index]:
         return [i for i, v in self.all_indices().items() if v > 1]
@@ -146,56 +344,499 @@ class TensorNetwork:
     def dim(self) -> int:
         return len(self.free_indices())
 
+    def cost(self) -> int:
+        """Sum of the node sizes -- pytens/algs.py:957-968."""
+        total = 0
+        for n in self.network.nodes:
+            total += int(np.prod([i.size for i in self.network.nodes[n]["tensor"].indices]))
+        return int(total)
+
+    def __lt__(self, other: "TensorNetwork") -> bool:
+        return self.cost() < other.cost()
+
+    def fresh_index(self) -> str:
+        names = [i.name for i in self.all_indices().keys()]
+        k = 0
+        while f"s_{k}" in names:
+            k += 1
+        return f"s_{k}"
+
+    def fresh_node(self) -> NodeName:
+        k = 0
+        while f"n{k}" in self.network.nodes:
+            k += 1
+        return f"n{k}"
+
+    def node_by_free_index(self, index: IndexName) -> NodeName:
+        for n in self.network.nodes:
+            if index in [ind.name for ind in self.node_tensor(n).indices]:
+                return n
+        raise KeyError(f"Cannot find index {index} in the network")
+
     def scale(self, scale_factor: float) -> "TensorNetwork":
         """Multiply the first node in place -- pytens/algs.py:578-583."""
         for _, data in self.network.nodes(data=True):
-            data["tensor"].value *= scale_factor
+            t = data["tensor"]
+            if dense.is_dev(t.value):
+                dense.scal(dense.as_dev(t.value), float(scale_factor))
+            else:
+                t.value *= scale_factor
             break
         return self
 
-    # ---- hot path ----
+    def to_device(self) -> "TensorNetwork":
+        """Move every node value to the GPU (in place); later operations then stay resident."""
+        for _, data in self.network.nodes(data=True):
+            t = data["tensor"]
+            if not dense.is_dev(t.value) and getattr(t.value, "size", 1) > 0:
+                t.value = dense.as_dev(t.value)
+        return self
+
+    def to_host(self) -> "TensorNetwork":
+        for _, data in self.network.nodes(data=True):
+            t = data["tensor"]
+            if dense.is_dev(t.value):
+                t.value = np.ascontiguousarray(dense.to_host(t.value))
+        return self
+
+    def _resident(self):
+        """Context: node values on the device for the duration, host nodes restored afterwards."""
+        tn = self
+
+        class _Ctx:
+            def __enter__(self_inner):
+                self_inner.was_host = any(
+                    not dense.is_dev(d["tensor"].value) for _, d in tn.network.nodes(data=True)
+                )
+                tn.to_device()
+
+            def __exit__(self_inner, *exc):
+                if self_inner.was_host:
+                    tn.to_host()
+                return False
+
+        return _Ctx()
+
+    # ---- hot path: inner product / norm / dense contraction ----
+    def _tt_compatible(self, other: "TensorNetwork") -> bool:
+        if not (_is_tt(self) and _is_tt(other)):
+            return False
+        d = len(self.network.nodes)
+        if d != len(other.network.nodes):
+            return False
+        if set(self.free_indices()) != set(other.free_indices()) or len(self.free_indices()) != d:
+            return False
+        return all(_free_index(self, k, d) == _free_index(other, k, d) for k in range(d))
+
     def inner(self, other: "TensorNetwork") -> np.ndarray:
-        """<self, other> over the shared free indices; 0-d float64 array like the reference
-        (pytens/algs.py:585-587).  Replaces attach() + contract() by the device sweep."""
-        a, b = _tt_cores(self), _tt_cores(other)
-        if len(a) != len(b):
-            raise AssertionError("inner: networks have different numbers of nodes")
-        d = len(a)
-        for k in range(d):
-            ia, ib = _free_index(self, k, d), _free_index(other, k, d)
-            if ia != ib:  # attach() only contracts indices with equal (name, size), algs.py:534-557
-                raise NotImplementedError(f"inner: free index of node {k} differs ({ia} vs {ib})")
-        ta = TensorTrain.from_cores(a if d > 1 else [a[0].reshape(1, -1, 1)])
-        tb = TensorTrain.from_cores(b if d > 1 else [b[0].reshape(1, -1, 1)])
-        return ta.inner(tb)
+        """<self, other> over the shared free indices (pytens/algs.py:585-587).  Two TTs over the same
+        free indices take the fused device sweep (0-d float64 array like the reference); any other
+        pair of networks takes the reference's own route, attach() + contract(), node by node on the
+        device -- free indices that are not shared stay open, as in the reference."""
+        if self._tt_compatible(other):
+            return _train_of(self).inner(_train_of(other))
+        return np.asarray(dense.to_host(self.attach(other).contract().value), dtype=np.float64)
 
     def norm(self) -> float:
         """sqrt(|<self, self>|) -- pytens/algs.py:589-594."""
         val = float(self.inner(self))
         return float(np.sqrt(np.abs(val)))
 
-    def contract(self) -> Tensor:
-        """Dense tensor of a chain (TensorNetwork.contract, pytens/algs.py:469-485), on the device."""
-        cores = _tt_cores(self)
-        d = len(cores)
-        tt = TensorTrain.from_cores(cores if d > 1 else [cores[0].reshape(1, -1, 1)])
-        return Tensor(tt.dense(), [_free_index(self, k, d) for k in range(d)])
+    def contract(self, eargs=None) -> Tensor:
+        """Dense tensor of the network, indices in free_indices() order (TensorNetwork.contract,
+        pytens/algs.py:469-485; opt_einsum there).  A TT chain goes through the fused chain kernel,
+        any other network through pairwise GEMM contractions (smallest intermediate first)."""
+        free = self.free_indices()
+        if _is_tt(self) and len(free) == len(self.network.nodes):
+            d = len(self.network.nodes)
+            if [_free_index(self, k, d) for k in range(d)] == free:
+                host = not any(dense.is_dev(self.value(k)) for k in range(d))
+                tt = _train_of(self)
+                return Tensor(tt.dense() if host else tt.dense_dev(), free)
+        if any(v > 2 for v in self.all_indices().values()):
+            raise NotImplementedError("contract(): an index shared by more than two nodes is not supported")
+        host = True
+        ops = []
+        for _, data in self.network.nodes(data=True):
+            t = data["tensor"]
+            host = host and not dense.is_dev(t.value)
+            ops.append((dense.as_dev(t.value), list(t.indices)))
+        while len(ops) > 1:
+            best = None
+            for i, j in itertools.combinations(range(len(ops)), 2):
+                li, lj = ops[i][1], ops[j][1]
+                shared = [x for x in li if x in lj]
+                out = 1
+                for x in li + lj:
+                    if x not in shared:
+                        out *= x.size
+                key = (0 if shared else 1, out)
+                if best is None or key < best[0]:
+                    best = (key, i, j)
+            _, i, j = best
+            val, inds = dense.contract(ops[i][0], ops[i][1], ops[j][0], ops[j][1])
+            ops = [o for k, o in enumerate(ops) if k not in (i, j)] + [(val, inds)]
+        val, inds = ops[0]
+        perm = [inds.index(f) for f in free]
+        val = dense.permute(val, perm) if perm != list(range(len(perm))) else val
+        return Tensor(val if not host else dense.to_host(val), free)
 
+    def attach(self, other: "TensorNetwork", rename: Tuple[str, str] = ("G", "H")) -> "TensorNetwork":
+        """Union of two networks that share their free indices -- pytens/algs.py:521-572.  Node n
+        becomes f"{rename[k]}{n}", bond indices get the same prefix, free indices keep their names (so
+        equal free indices of the two sides become contracted), and every pair of nodes that ends up
+        sharing an index is linked.  Values are copied, like the deepcopy of the reference."""
+        sides = []
+        for net, prefix in ((self, rename[0]), (other, rename[1])):
+            free = net.free_indices()
+            ren = {i.name: (i.name if i in free else f"{prefix}{i.name}") for i in net.all_indices()}
+            part = []
+            for n, data in net.network.nodes(data=True):
+                t = data["tensor"]
+                v = t.value.clone() if dense.is_dev(t.value) else np.array(t.value, copy=True)
+                part.append((f"{prefix}{n}", Tensor(v, list(t.indices)).rename_indices(ren)))
+            sides.append((net, prefix, part))
+        tn = TensorNetwork()
+        for net, prefix, part in sides:
+            for name, t in part:
+                if name in tn.network.nodes:
+                    raise nx.NetworkXError(f"attach: node name {name} appears on both sides")
+                tn.add_node(name, t)
+            for a, b in net.network.edges():
+                tn.add_edge(f"{prefix}{a}", f"{prefix}{b}")
+        for n1, t1 in sides[0][2]:
+            for n2, t2 in sides[1][2]:
+                both = t1.indices + t2.indices
+                if len(both) > len(set(both)):
+                    tn.add_edge(n1, n2)
+        return tn
+
+    def integrate(self, indices: Sequence[Index], weights) -> "TensorNetwork":
+        """Contract the chosen free indices with weight vectors -- pytens/algs.py:596-612."""
+        out = self
+        for weight, index in zip(weights, indices):
+            v = np.ones(index.size) * weight if isinstance(weight, float) else weight
+            out = out.attach(vector(f"w_{index.name}", index, v), rename=("", ""))
+        return out
+
+    # ---- node-level graph operations (pytens/algs.py:633-761) ----
+    def _relink(self, old_nbrs, parts, strict: bool) -> None:
+        """Re-attach the former neighbours of a split node to whichever part shares an index with them."""
+        for y in old_nbrs:
+            y_inds = self.network.nodes[y]["tensor"].indices
+            hit = False
+            for name, tensor in parts:
+                if any(i in y_inds for i in tensor.indices):
+                    self.add_edge(name, y)
+                    hit = True
+                    if strict:
+                        break
+            if strict and not hit:
+                raise ValueError(f"Indices {y_inds} does not exist in splits (", parts[0][1].indices, ",",
+                                 parts[1][1].indices)
+
+    def svd(self, node_name: NodeName, lefts: Sequence[int],
+            config: SVDConfig = SVDConfig()) -> Tuple[Tuple[NodeName, NodeName, NodeName], float]:
+        """Split node `node_name` into u - s - v by a truncated SVD over the index partition
+        (lefts | rest) -- pytens/algs.py:633-702.  u keeps the node name, s and v get fresh names, the
+        new bond indices fresh `s_k` names; returns ((u, s, v), remaining_delta)."""
+        x = self.network.nodes[node_name]["tensor"]
+        rights = [i for i in range(len(x.indices)) if i not in lefts]
+        if not config.compute_data:
+            nothing = np.array([])
+            u = Tensor(nothing, [x.indices[i] for i in lefts] + [Index("r_split_l", -1)])
+            v = Tensor(nothing, [Index("r_split_r", -1)] + [x.indices[i] for i in rights])
+            s = Tensor(nothing, [Index("r_split_l", -1), Index("r_split_r", -1)])
+            d = config.delta
+        else:
+            if config.with_orthonormal:
+                node_name = self.orthonormalize(node_name)
+            x = self.network.nodes[node_name]["tensor"]
+            [u, s, v], d = x.svd(lefts, delta=config.delta)
+
+        v_name = self.fresh_node()
+        index_r = self.fresh_index()
+        self.add_node(v_name, v.rename_indices({"r_split_r": index_r}))
+        u_name = node_name
+        index_l = self.fresh_index()
+        nbrs = list(self.network.neighbors(node_name))
+        self.network.remove_node(node_name)
+        self.add_node(u_name, u.rename_indices({"r_split_l": index_l}))
+        s_name = self.fresh_node()
+        self.add_node(s_name, s.rename_indices({"r_split_l": index_l, "r_split_r": index_r}))
+        self._relink(nbrs, [(u_name, u), (v_name, v)], strict=True)
+        self.add_edge(u_name, s_name)
+        self.add_edge(s_name, v_name)
+        return (u_name, s_name, v_name), d
+
+    def qr(self, node_name: NodeName, lefts: Sequence[int]) -> Tuple[NodeName, NodeName]:
+        """Split a node into q - r by QR over (lefts | rest) -- pytens/algs.py:704-733."""
+        x = self.network.nodes[node_name]["tensor"]
+        q, r = x.qr(lefts)
+        new_index = self.fresh_index()
+        nbrs = list(self.network.neighbors(node_name))
+        self.network.remove_node(node_name)
+        q_name = node_name
+        self.add_node(q_name, q.rename_indices({"r_split": new_index}))
+        r_name = self.fresh_node()
+        self.add_node(r_name, r.rename_indices({"r_split": new_index}))
+        self._relink(nbrs, [(q_name, q), (r_name, r)], strict=False)
+        self.add_edge(q_name, r_name)
+        return q_name, r_name
+
+    def merge(self, name1: NodeName, name2: NodeName, compute_data: bool = True) -> NodeName:
+        """Contract two adjacent nodes into `name1` -- pytens/algs.py:735-761."""
+        if not self.network.has_edge(name1, name2):
+            raise RuntimeError(f"Cannot merge nodes that are not adjacent: {name1}, {name2}")
+        t1 = self.network.nodes[name1]["tensor"]
+        t2 = self.network.nodes[name2]["tensor"]
+        if compute_data:
+            result = t1.contract(t2)
+        else:
+            result = Tensor(np.array([]), [i for i in t1.indices if i not in t2.indices] +
+                            [i for i in t2.indices if i not in t1.indices])
+        nbrs2 = list(self.network.neighbors(name2))
+        self.network.remove_node(name2)
+        self.network.nodes[name1]["tensor"] = result
+        for n in nbrs2:
+            if n != name1:
+                self.add_edge(name1, n)
+        return name1
+
+    def compress(self) -> None:
+        """Merge away nodes one of whose indices is as large as all the others together --
+        pytens/algs.py:829-848."""
+        for n, nd in list(self.network.nodes(data=True)):
+            indices = nd["tensor"].indices
+            for ind in indices:
+                if ind.size != np.prod([j.size for j in indices if j != ind]):
+                    continue
+                merged = False
+                for nbr in list(self.network.neighbors(n)):
+                    if ind in self.network.nodes[nbr]["tensor"].indices:
+                        self.merge(nbr, n)
+                        merged = True
+                        break
+                if merged:
+                    break
+
+    # ---- tree rounding (pytens/algs.py:763-827, :850-955) ----
+    def round(self, node_name: NodeName, delta: float, visited: Optional[set] = None) -> Tuple[NodeName, float]:
+        """Round the tree rooted at `node_name` with absolute accuracy budget delta --
+        pytens/algs.py:763-827: orthonormalise the environment of the root, then walk down: for every
+        bond of the current node split off the neighbour side by a delta-truncated SVD, push s v into
+        the neighbour, recurse, and merge the returned R factor back.  Mutates the network (node
+        names survive, bond indices get fresh names); returns (node, remaining_delta)."""
+        if visited is None:
+            with self._resident():
+                self.orthonormalize(node_name)
+                return self._round(node_name, delta, set(), True)
+        return self._round(node_name, delta, visited, False)
+
+    def _round(self, node_name: NodeName, delta: float, visited: set, top: bool) -> Tuple[NodeName, float]:
+        start_indices = self.network.nodes[node_name]["tensor"].indices
+        kept, free = [], []
+        r = node_name
+        for idx in start_indices:
+            if idx in visited:
+                kept.append(idx)
+                continue
+            nbr = None
+            for cand in self.network.neighbors(node_name):
+                if idx in self.network.nodes[cand]["tensor"].indices:
+                    nbr = cand
+                    break
+            if nbr is None:
+                free.append(idx)
+                continue
+            curr = self.network.nodes[node_name]["tensor"].indices
+            lefts = [curr.index(i) for i in curr if i != idx]
+            (node_name, s, v), delta = self.svd(node_name, lefts, SVDConfig(delta=delta, with_orthonormal=False))
+            self.merge(v, s)
+            self.merge(nbr, v)
+            for shared in self.get_contraction_index(node_name, nbr):
+                visited.add(shared)
+            r, delta = self._round(nbr, delta, visited, False)
+            self.merge(node_name, r)
+        if not top:
+            inds = self.network.nodes[node_name]["tensor"].indices
+            lefts = [i for i, idx in enumerate(inds) if idx in free or idx not in kept]
+            _, r = self.qr(node_name, lefts)
+        return r, delta
+
+    def orthonormalize(self, name: NodeName) -> NodeName:
+        """Make every node but `name` an isometry towards it (QR sweeps from the leaves) --
+        pytens/algs.py:850-955.  Leaves whose single free dimension is not larger than their bond are
+        absorbed into their parent instead of being split (the shortcut of :932-936, which the cost
+        function of the structure search depends on).  Returns the name of the root node."""
+        with self._resident():
+            state: Dict[NodeName, int] = {}  # 1: on the stack, 2: done
+            return self._orth_visit(None, name, state)
+
+    def _orth_visit(self, parent: Optional[NodeName], name: NodeName, state: Dict[NodeName, int]) -> NodeName:
+        state[name] = 1
+        merged = name
+        for n in list(self.network.neighbors(name)):
+            if n in state:
+                continue
+            child = self._orth_visit(name, n, state)
+            # merging appends the child's remaining index at the end; put it back where the bond was
+            inds = self.network.nodes[merged]["tensor"].indices
+            pos = inds.index(self.get_contraction_index(merged, child)[0])
+            order = list(range(pos)) + [len(inds) - 1] + list(range(pos, len(inds) - 1))
+            merged = self.merge(merged, child)
+            self.network.nodes[merged]["tensor"] = self.network.nodes[merged]["tensor"].permute(order)
+        if parent is None:
+            return merged
+
+        lefts, rights = [], []
+        m_inds = self.network.nodes[merged]["tensor"].indices
+        for i, index in enumerate(m_inds):
+            owner = None
+            for n in self.network.neighbors(merged):
+                if index in self.network.nodes[n]["tensor"].indices:
+                    owner = n
+                    break
+            if owner is None or owner not in state or state[owner] == 2:
+                lefts.append(i)  # free, or shared with a finished child
+            else:
+                rights.append(i)  # shared with the parent (still on the stack)
+        state[name] = 2
+        state[merged] = 2
+        right_sz = np.prod([m_inds[i].size for i in rights])
+        if len(lefts) == 1 and m_inds[lefts[0]].size <= right_sz:
+            return merged
+        q, r = self.qr(merged, lefts)
+        # q comes back as (lefts..., r_split); move r_split to where the parent bond was
+        order = list(range(rights[0])) + [len(lefts)] + list(range(rights[0], len(lefts)))
+        self.network.nodes[q]["tensor"] = self.network.nodes[q]["tensor"].permute(order)
+        return r
+
+    # ---- dimension tree and elementwise network arithmetic (pytens/algs.py:1012-1101, :1310-1380) ----
+    def canonicalize_indices(self, tree: DimTreeNode) -> None:
+        order: List[Index] = list(tree.free_indices)
+        node_indices = self.node_tensor(tree.node).indices
+        for child in tree.down_info.nodes:
+            self.canonicalize_indices(child)
+            order.append(self.get_contraction_index(child.node, tree.node)[0])
+        up = [ind for ind in node_indices if ind not in order]
+        assert len(up) <= 1, f"should have at most one parent index, but get {up}"
+        order.extend(up)
+        tree.perm = [node_indices.index(ind) for ind in order]
+
+    def dimension_tree(self, root: NodeName) -> DimTreeNode:
+        """Rooted view of a tree network: for every node the free indices below it --
+        pytens/algs.py:1038-1101."""
+        free = self.free_indices()
+
+        def build(seen: Set[NodeName], node: NodeName) -> DimTreeNode:
+            seen.add(node)
+            kids = [build(seen, nbr) for nbr in self.network.neighbors(node) if nbr not in seen]
+            own = [ind for ind in self.node_tensor(node).indices if ind in free]
+            below, up = list(own), list(own)
+            kids = sorted(kids, key=lambda k: k.indices)
+            for k in kids:
+                up.extend(k.indices)
+                below.extend(k.indices)
+            res = DimTreeNode(node=node, indices=below, free_indices=sorted(own),
+                              down_info=NodeInfo(kids, [], np.empty(0)),
+                              up_info=NodeInfo([], up, np.empty((0, len(up)))))
+            for k in kids:
+                k.up_info.nodes = [res]
+            return res
+
+        def assign(tree: DimTreeNode) -> None:
+            if tree.up_info.nodes:
+                p = tree.up_info.nodes[0]
+                tree.down_info.indices = p.free_indices[:] + list(p.down_info.indices)
+                for c in p.down_info.nodes:
+                    if c.node != tree.node:
+                        tree.down_info.indices.extend(c.up_info.indices)
+                tree.down_info.vals = np.empty((0, len(tree.down_info.indices)))
+            for c in tree.down_info.nodes:
+                assign(c)
+
+        tree = build(set(), root)
+        assign(tree)
+        self.canonicalize_indices(tree)
+        return tree
+
+    def _binary_op(self, other: "TensorNetwork", op: str, trees: Tuple[DimTreeNode, DimTreeNode],
+                   result_net: "TensorNetwork") -> None:
+        tree1, tree2 = trees
+        t1, t2 = self.node_tensor(tree1.node), other.node_tensor(tree2.node)
+        assert len(t1.indices) == len(t2.indices)
+        if op == "add":
+            res = t1.block_diagonal(t2, tree1.free_indices)
+        elif op == "mul":
+            res = t1.mult(t2, self.free_indices())
+        else:
+            raise ValueError(f"Unknown operation {op}")
+        result_net.set_node_tensor(tree1.node, res)
+        for c1, c2 in zip(tree1.down_info.nodes, tree2.down_info.nodes):
+            self._binary_op(other, op, (c1, c2), result_net)
+
+    def _elementwise(self, other: "TensorNetwork", op: str) -> "TensorNetwork":
+        assert nx.is_isomorphic(self.network, other.network)
+        root_ind = self.free_indices()[0]
+        tree1 = self.dimension_tree(self.node_by_free_index(root_ind.name))
+        tree2 = other.dimension_tree(other.node_by_free_index(root_ind.name))
+        result = copy.deepcopy(self)
+        self._binary_op(other, op, (tree1, tree2), result)
+        return result
+
+    def __add__(self, other: "TensorNetwork") -> "TensorNetwork":
+        """Sum of two tree networks of the same structure by block-diagonal bond growth
+        (pytens/algs.py:1339-1353).  A one-node network is summed value by value."""
+        if len(self.network.nodes) == 1 and len(other.network.nodes) == 1:
+            out = copy.deepcopy(self)
+            (n1,), (n2,) = list(self.network.nodes), list(other.network.nodes)
+            a, b = dense.as_dev(self.value(n1)), dense.as_dev(other.value(n2))
+            s = a.clone()
+            dense.axpy(1.0, b, s)
+            out.node_tensor(n1).value = dense.like(s, self.value(n1))
+            return out
+        return self._elementwise(other, "add")
+
+    def __sub__(self, other: "TensorNetwork") -> "TensorNetwork":
+        """pytens/algs.py:1355-1365: negate the first node of a copy of `other`, then add."""
+        assert nx.is_isomorphic(self.network, other.network)
+        neg = copy.deepcopy(other)
+        neg.scale(-1.0)
+        return self + neg
+
+    def __mul__(self, other: "TensorNetwork") -> "TensorNetwork":
+        """Elementwise (Hadamard) product of two tree networks: Kronecker product of the bonds
+        (pytens/algs.py:1367-1380)."""
+        return self._elementwise(other, "mul")
+
+    def __str__(self) -> str:
+        lines = ["Nodes:", "------"]
+        for node, data in self.network.nodes(data=True):
+            lines.append(f"\t{node}: shape = {tuple(data['tensor'].value.shape)},indices = {[i.name for i in data['tensor'].indices]}")
+        lines += ["Edges:", "------"]
+        for a, b in self.network.edges():
+            lines.append(f"\t{a} -> {b}")
+        return "\n".join(lines) + "\n"
+
+    # ---- TT-specific constructors / conversions ----
     def to_tensor_train(self) -> TensorTrain:
-        return TensorTrain.from_network(self)
+        return _train_of(self)
 
     @staticmethod
-    def from_tensor_train(tt: TensorTrain, names: Optional[Sequence[IntOrStr]] = None) -> "TensorNetwork":
-        """Chain network with the reference's naming (rand_tt, pytens/algs.py:1180-1218)."""
+    def from_tensor_train(tt: TensorTrain, names: Optional[Sequence[IntOrStr]] = None,
+                          device: bool = False) -> "TensorNetwork":
+        """Chain network with the reference's naming (rand_tt, pytens/algs.py:1180-1218); node
+        values are numpy arrays unless `device`."""
         d = tt.d
         shape, ranks = tt.shape(), tt.ranks()
         names = list(names) if names is not None else [f"x{k}" for k in range(d)]
         free = [Index(names[k], shape[k]) for k in range(d)]
         bonds = [Index(f"r{k + 1}", ranks[k]) for k in range(d - 1)]
-        host = tt.to_cores()
+        vals = [c.clone() for c in tt.cores] if device else tt.to_cores()
         tn = TensorNetwork()
         for k in range(d):
-            c = host[k]
+            c = vals[k]
             if d == 1:
                 tn.add_node(0, Tensor(c.reshape(-1), [free[0]]))
             elif k == 0:
@@ -227,41 +868,124 @@ class TensorNetwork:
         tt.add_edge(dim - 2, dim - 1)
         return tt
 
-    def __add__(self, other: "TensorNetwork") -> "TensorNetwork":
-        """TT sum by block-diagonal rank growth (pytens/algs.py:1339-1353): host-side fixture
-        builder, no arithmetic."""
-        a, b = _tt_cores(self), _tt_cores(other)
-        d = len(a)
-        out = copy.deepcopy(self)
-        for k in range(d):
-            x, y = a[k], b[k]
-            if d == 1:
-                v = x + y
-            elif k == 0:
-                v = np.concatenate([x, y], axis=1)
-            elif k == d - 1:
-                v = np.concatenate([x, y], axis=0)
-            else:
-                v = np.zeros((x.shape[0] + y.shape[0], x.shape[1], x.shape[2] + y.shape[2]))
-                v[: x.shape[0], :, : x.shape[2]] = x
-                v[x.shape[0]:, :, x.shape[2]:] = y
-            out.network.nodes[k]["tensor"].update_val_size(v)
-        return out
-
-    # ---- out of scope ----
-    def attach(self, *_a, **_k):
-        raise NotImplementedError("attach() is bypassed on the B200 path; use inner()")
-
-    def round(self, node_name, delta, visited=None):
-        raise NotImplementedError(
-            "general-tree TensorNetwork.round (pytens/algs.py:763-827) is out of scope; use tt_svd_round / round()"
-        )
+    @staticmethod
+    def rand_tucker(indices: List[Index], rank: int = 1) -> "TensorNetwork":
+        """Random Tucker network -- pytens/algs.py:1286-1299 (same draw order)."""
+        tucker = TensorNetwork()
+        root_inds = [Index(f"s_{i}", rank) for i in range(len(indices))]
+        tucker.add_node("root", Tensor(np.random.random([rank] * len(indices)), root_inds))
+        for i, ind in enumerate(indices):
+            tucker.add_node(f"G{i}", Tensor(np.random.random((ind.size, rank)), [ind, root_inds[i]]))
+            tucker.add_edge(f"G{i}", "root")
+        return tucker
 
 
+# ---------------------------------------------------------------------------
+# small constructors (pytens/algs.py:1583-1651, :2796-2865)
+# ---------------------------------------------------------------------------
+def vector(name: IntOrStr, index: Index, value: np.ndarray) -> TensorNetwork:
+    vec = TensorNetwork()
+    vec.add_node(name, Tensor(value, [index]))
+    return vec
+
+
+def tt_rank1(indices: List[Index], vals: List[np.ndarray]) -> TensorNetwork:
+    """Rank-1 TT from one vector per mode -- pytens/algs.py:1592-1618."""
+    dim = len(indices)
+    tt = TensorNetwork()
+    r = [Index("r1", 1)]
+    tt.add_node(0, Tensor(vals[0][:, np.newaxis], [indices[0], r[0]]))
+    for ii, index in enumerate(indices[1:-1]):
+        r.append(Index(f"r{ii + 2}", 1))
+        tt.add_node(ii + 1, Tensor(vals[ii + 1][np.newaxis, :, np.newaxis], [r[ii], index, r[ii + 1]]))
+        tt.add_edge(ii, ii + 1)
+    tt.add_node(dim - 1, Tensor(vals[-1][np.newaxis, :], [r[-1], indices[-1]]))
+    tt.add_edge(dim - 2, dim - 1)
+    return tt
+
+
+def tt_separable(indices: List[Index], funcs: List[np.ndarray]) -> TensorNetwork:
+    """Rank-2 TT of f_1(x_1) + ... + f_d(x_d) -- pytens/algs.py:1621-1651."""
+    dim = len(indices)
+    tt = TensorNetwork()
+    ranks: List[Index] = []
+    for ii, index in enumerate(indices):
+        ranks.append(Index(f"r_{ii + 1}", 2))
+        if ii == 0:
+            val = np.ones((index.size, 2))
+            val[:, 0] = funcs[ii]
+            tt.add_node(ii, Tensor(val, [index, ranks[-1]]))
+        elif ii < dim - 1:
+            val = np.zeros((2, index.size, 2))
+            val[0, :, 0] = 1.0
+            val[1, :, 0] = funcs[ii]
+            val[1, :, 1] = 1.0
+            tt.add_node(ii, Tensor(val, [ranks[-2], index, ranks[-1]]))
+        else:
+            val = np.ones((2, index.size))
+            val[1, :] = funcs[ii]
+            tt.add_node(ii, Tensor(val, [ranks[-2], index]))
+        if ii > 0:
+            tt.add_edge(ii - 1, ii)
+    return tt
+
+
+def rand_tree(indices: List[Index], ranks: List[int]) -> TensorNetwork:
+    """Random tree network: same sequence of np.random draws as the reference
+    (pytens/algs.py:2796-2865), so a seeded call builds the same tree."""
+    ndims = len(indices)
+    num_of_nodes = len(ranks) + 1
+    assert ndims <= num_of_nodes
+    np.random.shuffle(ranks)
+    nodes_with_free = np.random.choice(num_of_nodes, len(indices), replace=False)
+    parent: Dict[int, Tuple[NodeName, int]] = {}
+    nodes = list(range(num_of_nodes))
+
+    def draw_other(node):
+        p = np.random.choice(num_of_nodes, 1)[0]
+        while p == node:
+            p = np.random.choice(num_of_nodes, 1)[0]
+        return p
+
+    while len(nodes) > 1:
+        node = np.random.choice(nodes, 1)[0]
+        nodes.remove(node)
+        p = draw_other(node)
+        ancestor = p
+        while ancestor in parent:  # walk up; a cycle back to `node` forces a new draw
+            ancestor, _ = parent[ancestor]
+            if ancestor == node:
+                p = draw_other(node)
+                ancestor = p
+        parent[node] = (p, len(nodes) - 1)
+
+    tree = TensorNetwork()
+    for i in range(num_of_nodes):
+        inds, dims = [], []
+        if i in nodes_with_free:
+            ind = indices[list(nodes_with_free).index(i)]
+            inds.append(ind)
+            dims.append(ind.size)
+        if i in parent:
+            _, ridx = parent[i]
+            inds.append(Index(f"r_{ridx}", ranks[ridx]))
+            dims.append(ranks[ridx])
+        for p, ridx in parent.values():
+            if p == i:
+                inds.append(Index(f"r_{ridx}", ranks[ridx]))
+                dims.append(ranks[ridx])
+        tree.add_node(i, Tensor(np.random.randn(*dims), inds))
+    for i, (p, _) in parent.items():
+        tree.add_edge(i, p)
+    return tree
+
+
+# ---------------------------------------------------------------------------
+# TT sweeps (the hot path)
+# ---------------------------------------------------------------------------
 def tt_right_orth(tn, node: int):
     """Right-orthogonalise core `node`, in place; returns tn -- pytens/algs.py:1654-1704."""
-    _tt_cores(tn)
-    tt = TensorTrain.from_network(tn)
+    tt = _train_of(tn)
     tt.right_orth(node)
     _write_back(tn, tt)
     return tn
@@ -270,8 +994,7 @@ def tt_right_orth(tn, node: int):
 def tt_svd_round(tn, eps: float):
     """Round a TT with relative accuracy eps, in place; returns the same object
     (pytens/algs.py:1841-1903)."""
-    _tt_cores(tn)
-    tt = TensorTrain.from_network(tn)
+    tt = _train_of(tn)
     tt.round(eps)
     _write_back(tn, tt)
     return tn
@@ -281,8 +1004,7 @@ def tt_gramsvd_round(tn, eps: float):
     """Gram-SVD rounding of a TT, in place; returns the same object (pytens/algs.py:1771-1838)."""
     from .gramsvd import gramsvd_round
 
-    _tt_cores(tn)
-    tt = TensorTrain.from_network(tn)
+    tt = _train_of(tn)
     gramsvd_round(tt, eps)
     _write_back(tn, tt)
     return tn
@@ -291,16 +1013,21 @@ def tt_gramsvd_round(tn, eps: float):
 def round(tn, eps: float, max_rank: Optional[int] = None):  # noqa: A001 (name fixed by north_star)
     """tt_svd_round with an optional rank cap: rank = min(rank_eps, max_rank).  The reference
     has no max_rank in rounding; parity of the cap is unpinned."""
-    _tt_cores(tn)
-    tt = TensorTrain.from_network(tn)
+    tt = _train_of(tn)
     tt.round(eps, max_rank=max_rank)
     _write_back(tn, tt)
     return tn
 
 
-def tt_svd(dense: np.ndarray, eps: float, max_rank: Optional[int] = None,
+def tt_svd(dense_array: np.ndarray, eps: float, max_rank: Optional[int] = None,
            names: Optional[Sequence[IntOrStr]] = None) -> TensorNetwork:
     """TT-SVD of a dense array with delta = eps / sqrt(d-1) * ||X||_F; the composition
     TensorNetwork.svd + merge of the reference (pytens/algs.py:633-702, :735-761)."""
-    tt = TensorTrain.from_dense(np.asarray(dense, dtype=np.float64), eps, max_rank=max_rank)
+    tt = TensorTrain.from_dense(np.asarray(dense_array, dtype=np.float64), eps, max_rank=max_rank)
     return TensorNetwork.from_tensor_train(tt, names)
+
+
+from .ttops import gmres, tt_sum, ttop_apply, ttop_rank1, ttop_rank2, ttop_sum, ttop_sum_apply  # noqa: E402,F401
+from .randround import (  # noqa: E402,F401
+    TTRandRound, tt_rand_precond_svd_round, tt_randomized_round, tt_sum_randomized_round,
+)

@@ -241,6 +241,10 @@ int ttb_strided_copy_f64(double* dst, const double* src, int32_t ndim, const int
                          const int64_t* dst_strides, const int64_t* src_strides, void* stream) {
     return ttb::strided_copy(dst, src, ndim, shape, dst_strides, src_strides, as_stream(stream));
 }
+int ttb_strided_op_f64(double* dst, const double* src, int32_t ndim, const int64_t* shape,
+                       const int64_t* dst_strides, const int64_t* src_strides, int32_t op, double alpha, void* stream) {
+    return ttb::strided_op(dst, src, ndim, shape, dst_strides, src_strides, op, alpha, as_stream(stream));
+}
 int ttb_fill_f64(double* dst, int64_t count, double value, void* stream) {
     return ttb::fill(dst, count, value, as_stream(stream));
 }

@@ -33,8 +33,10 @@ struct CopyDims {
     int64_t ss[kMaxDims];
 };
 
+// OP 0: dst = src; 1: dst *= src; 2: dst += alpha * src
+template <int OP>
 __global__ void __launch_bounds__(256) copy_direct_kernel(double* __restrict__ dst, const double* __restrict__ src,
-                                                          const CopyDims cd, int64_t total) {
+                                                          const CopyDims cd, int64_t total, double alpha) {
     for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
          idx += int64_t(gridDim.x) * blockDim.x) {
         int64_t rem = idx, od = 0, os = 0;
@@ -45,7 +47,9 @@ __global__ void __launch_bounds__(256) copy_direct_kernel(double* __restrict__ d
             od += c * cd.ds[k];
             os += c * cd.ss[k];
         }
-        dst[od] = src[os];
+        if (OP == 0) dst[od] = src[os];
+        else if (OP == 1) dst[od] *= src[os];
+        else dst[od] = fma(alpha, src[os], dst[od]);
     }
 }
 
@@ -136,8 +140,9 @@ inline int grid_for(int64_t total, int per_block = 256) {
 
 }  // namespace
 
-int strided_copy(double* dst, const double* src, int ndim, const int64_t* shape, const int64_t* dst_strides,
-                 const int64_t* src_strides, cudaStream_t stream) {
+int strided_op(double* dst, const double* src, int ndim, const int64_t* shape, const int64_t* dst_strides,
+               const int64_t* src_strides, int op, double alpha, cudaStream_t stream) {
+    TTB_REQUIRE(op >= 0 && op <= 2, "strided_op: unknown op");
     TTB_REQUIRE(dst && src, "strided_copy: null pointer");
     TTB_REQUIRE(ndim >= 0 && (ndim == 0 || (shape && dst_strides && src_strides)), "strided_copy: bad descriptor");
     // drop unit dimensions, order by destination stride (largest first), merge what is mergeable on both sides
@@ -174,7 +179,7 @@ int strided_copy(double* dst, const double* src, int ndim, const int64_t* shape,
         cd.ss[k] = m[k].ss;
     }
     const int last = cd.nd - 1;
-    if (cd.nd == 1 && cd.ds[0] == 1 && cd.ss[0] == 1) {
+    if (op == 0 && cd.nd == 1 && cd.ds[0] == 1 && cd.ss[0] == 1) {
         TTB_CHECK_CUDA(cudaMemcpyAsync(dst, src, size_t(total) * 8, cudaMemcpyDeviceToDevice, stream));
         return kOk;
     }
@@ -182,7 +187,7 @@ int strided_copy(double* dst, const double* src, int ndim, const int64_t* shape,
     if (cd.ds[last] == 1 && cd.ss[last] != 1)
         for (int k = 0; k < last; ++k)
             if (cd.ss[k] == 1 && cd.shape[k] >= 8) jdim = k;
-    if (jdim >= 0 && cd.shape[last] >= 8) {
+    if (op == 0 && jdim >= 0 && cd.shape[last] >= 8) {
         const int64_t ti = ceil_div<int64_t>(cd.shape[last], 32), tj = ceil_div<int64_t>(cd.shape[jdim], 32);
         int64_t outer = 1;
         for (int k = 0; k < last; ++k)
@@ -191,11 +196,18 @@ int strided_copy(double* dst, const double* src, int ndim, const int64_t* shape,
         const int grid = int(std::min<int64_t>(ntiles, int64_t(num_sms()) * 32));
         copy_tiled_kernel<<<grid, 256, 0, stream>>>(dst, src, cd, jdim, ti, tj, ntiles);
     } else {
-        copy_direct_kernel<<<grid_for(total), 256, 0, stream>>>(dst, src, cd, total);
+        if (op == 0) copy_direct_kernel<0><<<grid_for(total), 256, 0, stream>>>(dst, src, cd, total, alpha);
+        else if (op == 1) copy_direct_kernel<1><<<grid_for(total), 256, 0, stream>>>(dst, src, cd, total, alpha);
+        else copy_direct_kernel<2><<<grid_for(total), 256, 0, stream>>>(dst, src, cd, total, alpha);
     }
     ++g_launch_count;
     TTB_CHECK_CUDA(cudaGetLastError());
     return kOk;
+}
+
+int strided_copy(double* dst, const double* src, int ndim, const int64_t* shape, const int64_t* dst_strides,
+                 const int64_t* src_strides, cudaStream_t stream) {
+    return strided_op(dst, src, ndim, shape, dst_strides, src_strides, 0, 1.0, stream);
 }
 
 int fill(double* dst, int64_t count, double value, cudaStream_t stream) {

@@ -9,6 +9,9 @@ namespace ttb {
 // sub-block placement, broadcasts with stride 0 on the source side).  dst and src must not overlap.
 int strided_copy(double* dst, const double* src, int ndim, const int64_t* shape, const int64_t* dst_strides,
                  const int64_t* src_strides, cudaStream_t stream);
+// op 0: dst = src; 1: dst *= src (broadcast multiply, Tensor.mult); 2: dst += alpha * src
+int strided_op(double* dst, const double* src, int ndim, const int64_t* shape, const int64_t* dst_strides,
+               const int64_t* src_strides, int op, double alpha, cudaStream_t stream);
 int fill(double* dst, int64_t count, double value, cudaStream_t stream);
 // mode 1: row i *= s[i]; mode 2: row i /= s[i] (zero rows stay zero)
 int scale_rows(double* mat, int64_t rows, int64_t cols, int64_t ld, const double* s, int mode, cudaStream_t stream);

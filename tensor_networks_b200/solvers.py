@@ -3,8 +3,7 @@
 Mirror of `ttop_rank1` / `ttop_apply` / `gmres` of the reference (pytens/algs.py:2383-2420,
 :2662-2697, :2701-2793; exercised by tests/main_test.py:428-448).  Everything stays resident in HBM:
 the Arnoldi loop calls `TensorTrain.round` (tt_svd_round), `inner` and `norm` -- the kernels of this
-package -- per step, and the operator application is one einsum per core on the device (glue, not a
-hot-path kernel).  Only the small Hessenberg least-squares problem runs on the host, as in the
+package -- per step, and the operator application is one DMMA GEMM per core between permuted operands.  Only the small Hessenberg least-squares problem runs on the host, as in the
 reference.
 """
 
@@ -15,6 +14,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
+from . import dense
 from .tt import TensorTrain, _require_cuda
 
 
@@ -69,8 +69,10 @@ def ttop_apply(op: TTOperator, tt: TensorTrain) -> TensorTrain:
     for a, v in zip(op.cores, tt.cores):
         if a.shape[2] != v.shape[1]:
             raise AssertionError("operator input mode size does not match the tensor train")
-        c = torch.einsum("ijkl,mkp->mijpl", a, v)
-        out.append(c.reshape(c.shape[0] * c.shape[1], c.shape[2], c.shape[3] * c.shape[4]))
+        c, _ = dense.contract(a, "ijkl", v, "mkp")  # one DMMA GEMM -> (i, j, l, m, p)
+        c = dense.permute(c, [3, 0, 1, 4, 2])  # (m, i, j, p, l)
+        s = [int(x) for x in c.shape]
+        out.append(c.reshape(s[0] * s[1], s[2], s[3] * s[4]))
     return TensorTrain(out)
 
 
@@ -88,7 +90,7 @@ def gmres(
     against the Krylov basis with `inner`, `tt_svd_round(w, round_eps)` twice per step, `norm`, a dense
     least-squares solve of the Hessenberg system on the host, stop when the least-squares residual is
     below eps.  Returns (x, ||rhs - op(x)||)."""
-    r0 = (rhs + op(x0).scale(-1.0)).round(round_eps)
+    r0 = (rhs + op(x0).scale(-1.0)).round(round_eps).compact()  # re-own: do not pin the unrounded buffers
     beta = float(r0.norm())
     if beta == 0.0:
         return x0.clone(), 0.0
@@ -103,7 +105,7 @@ def gmres(
         for ii in range(jj + 1):
             H[ii, jj] = float(w.inner(v[ii]))
             w = w + v[ii].clone().scale(-H[ii, jj])
-        w = w.round(round_eps)
+        w = w.round(round_eps).compact()
         H[jj + 1, jj] = float(w.norm())
         if H[jj + 1, jj] > 0.0:
             v.append(w.scale(1.0 / H[jj + 1, jj]))

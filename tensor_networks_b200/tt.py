@@ -221,31 +221,40 @@ class TensorTrain:
 
     def scale(self, alpha: float) -> "TensorTrain":
         """In place, on the first core -- TensorNetwork.scale, pytens/algs.py:578-583."""
-        self.cores[0] *= float(alpha)
+        from . import dense
+
+        dense.scal(self.cores[0], float(alpha))
         return self
 
     def __add__(self, other: "TensorTrain") -> "TensorTrain":
-        """Formal sum by block-diagonal rank growth (pytens/algs.py:1339-1353, :308-344)."""
+        """Formal sum by block-diagonal rank growth (pytens/algs.py:1339-1353, :308-344): block
+        placements into zero-filled cores (`ttb_fill_f64` + `ttb_strided_copy_f64`)."""
+        from . import dense
+
         if self.shape() != other.shape():
             raise AssertionError("TT sum needs equal mode sizes")
         d = self.d
         out = []
         for k, (a, b) in enumerate(zip(self.cores, other.cores)):
+            ra, n, rb = (int(x) for x in a.shape)
+            sa, _, sb = (int(x) for x in b.shape)
             if d == 1:
-                out.append(a + b)
+                c = dense.empty(a.shape, a.device)
+                dense.place(c, a, (0, 0, 0))
+                dense.axpy(1.0, b, c)
             elif k == 0:
-                out.append(torch.cat([a, b], dim=2))
+                c = dense.empty((1, n, rb + sb), a.device)
+                dense.place(c, a, (0, 0, 0))
+                dense.place(c, b, (0, 0, rb))
             elif k == d - 1:
-                out.append(torch.cat([a, b], dim=0))
+                c = dense.empty((ra + sa, n, 1), a.device)
+                dense.place(c, a, (0, 0, 0))
+                dense.place(c, b, (ra, 0, 0))
             else:
-                c = torch.zeros(
-                    (a.shape[0] + b.shape[0], a.shape[1], a.shape[2] + b.shape[2]),
-                    dtype=torch.float64,
-                    device=a.device,
-                )
-                c[: a.shape[0], :, : a.shape[2]] = a
-                c[a.shape[0] :, :, a.shape[2] :] = b
-                out.append(c)
+                c = dense.zeros((ra + sa, n, rb + sb), a.device)
+                dense.place(c, a, (0, 0, 0))
+                dense.place(c, b, (ra, 0, rb))
+            out.append(c)
         return TensorTrain(out)
 
     # ------------------------------------------------------------------ hot path

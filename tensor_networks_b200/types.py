@@ -57,3 +57,35 @@ class SVDConfig:
     delta: float = 1e-5
     with_orthonormal: bool = True
     compute_data: bool = True
+
+
+class NodeInfo:
+    """Children / parent side of a dimension-tree node (pytens/types.py:69-81)."""
+
+    def __init__(self, nodes, indices, vals):
+        self.nodes = nodes
+        self.indices = indices
+        self.vals = vals
+        self.rank = 0
+
+
+class DimTreeNode:
+    """Node of the dimension tree of a tree network (pytens/types.py:84-120): `indices` are the free
+    indices below the node, `down_info.nodes` its children, `up_info.nodes` its parent (0 or 1)."""
+
+    def __init__(self, node, indices, free_indices, up_info: NodeInfo, down_info: NodeInfo):
+        self.node = node
+        self.indices = indices
+        self.free_indices = free_indices
+        self.up_info = up_info
+        self.down_info = down_info
+        self.perm = list(range(len(free_indices) + len(down_info.nodes) + len(up_info.nodes)))
+
+    def __lt__(self, other: "DimTreeNode") -> bool:
+        return sorted(self.indices) < sorted(other.indices)
+
+    def preorder(self):
+        out = [self]
+        for child in self.down_info.nodes:
+            out.extend(child.preorder())
+        return out

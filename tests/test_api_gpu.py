@@ -88,10 +88,17 @@ def test_tt_svd_and_errors():
     assert tn.ranks() == [3, 2]
     assert np.allclose(tn.contract().value, dense, atol=1e-12 * np.abs(dense).max() * 10)
     assert [i.name for i in tn.free_indices()] == ["x0", "x1", "x2"]
-    # non-TT networks are refused, not silently computed on the CPU
-    bad = algs.TensorNetwork()
-    bad.add_node("a", algs.Tensor(np.ones((2, 2)), [algs.Index("i", 2), algs.Index("j", 2)]))
+    # non-TT networks take the node-level route (attach + contract on the device), like the reference
+    other = algs.TensorNetwork()
+    other.add_node("a", algs.Tensor(np.ones((2, 2)), [algs.Index("i", 2), algs.Index("j", 2)]))
+    assert abs(other.norm() - 2.0) < 1e-14
+    # the TT sweeps proper still need a TT-shaped network
     with pytest.raises(NotImplementedError):
-        bad.norm()
-    with pytest.raises(NotImplementedError):
-        tn.round(0, 1e-3)
+        algs.tt_svd_round(other, 1e-3)
+    # tree rounding of the TT-shaped result (pytens/algs.py:763-827) works on it as on any tree
+    before = tn.contract().value
+    free = [i.name for i in tn.free_indices()]
+    tn.round(0, 1e-8)
+    t = tn.contract()
+    have = [i.name for i in t.indices]
+    assert np.allclose(np.transpose(t.value, [have.index(n) for n in free]), before, atol=1e-7)
