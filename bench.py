@@ -62,6 +62,20 @@ def workload_name(a):
     return f"tt_inner d={a.d} n={a.n} r={a.r} fp64 (BASELINE configs[1])"
 
 
+def workload_config(a):
+    """The `config` object of the JSON line -- identical for both arms (the driver compares them)."""
+    r = [1] + [a.r] * (a.d - 1) + [1]
+    flops = sum(2 * r[k] * r[k] * a.n * r[k + 1] + 2 * r[k] * a.n * r[k + 1] * r[k + 1] for k in range(a.d))
+    nbytes = 2 * 8 * sum(r[k] * a.n * r[k + 1] for k in range(a.d))
+    return {
+        "workload": workload_name(a),
+        "flops_per_step": int(flops),
+        "bytes_resident": int(nbytes),
+        "l2": "inputs (2.08 GB per TT pair) larger than the 126 MB L2; no flush needed",
+        "multi_gpu": "replicas only (one independent TT pair per rank, no collective)",
+    }
+
+
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons every 100 ms in the background."""
@@ -132,13 +146,24 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU arms
+def _host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_inner_sample(a, steps: int, warmup: int, min_seconds: float = 0.0):
     """Oracle (numpy port of the reference path) on the host cores.
 
     Bounded sample: the first d_s cores of the same workload (same n, r), so one
     pass is ~1/8 of the full sweep; GFLOP/s is size-independent because the sweep
-    cost is linear in d."""
+    cost is linear in d.  The BLAS pool is set to every core this process may use:
+    `torch.distributed.run` exports OMP_NUM_THREADS=1, which would otherwise time a
+    single-threaded reference."""
     import numpy as np
+    from threadpoolctl import threadpool_info, threadpool_limits
+
     from oracle import tt_oracle as orc
 
     d_s = min(a.d, 8)
@@ -146,21 +171,17 @@ def cpu_inner_sample(a, steps: int, warmup: int, min_seconds: float = 0.0):
     ranks = [a.r] * (d_s - 1)
     ca = orc.rand_tt([a.n] * d_s, ranks, rng)
     cb = orc.rand_tt([a.n] * d_s, ranks, rng)
-    # make the truncated chain end in a closed (rank-1) bond like the full one
     flops = orc.inner_flops([a.n] * d_s, ranks, ranks)
-    for _ in range(max(1, min(warmup, 2))):
-        orc.inner(ca, cb)
-    times = []
-    while len(times) < max(1, steps) or (sum(times) < min_seconds and len(times) < 2000):
-        t = time.perf_counter()
-        orc.inner(ca, cb)
-        times.append(time.perf_counter() - t)
-    try:
-        from threadpoolctl import threadpool_info
-
+    want = _host_threads()
+    with threadpool_limits(limits=want):
         threads = max([i.get("num_threads", 1) for i in threadpool_info()] or [1])
-    except Exception:
-        threads = os.cpu_count() or 1
+        for _ in range(max(1, warmup)):
+            orc.inner(ca, cb)
+        times = []
+        while len(times) < max(1, steps) or (sum(times) < min_seconds and len(times) < 2000):
+            t = time.perf_counter()
+            orc.inner(ca, cb)
+            times.append(time.perf_counter() - t)
     total = sum(times)
     return {
         "value": flops * len(times) / total / 1e9,
@@ -168,35 +189,40 @@ def cpu_inner_sample(a, steps: int, warmup: int, min_seconds: float = 0.0):
         "cores": int(threads),
         "kind": "port",
         "sample": f"numpy oracle sweep on a d={d_s} slice of the workload (n={a.n}, r={a.r}), "
-                  f"{len(times)} passes, {total:.1f} s of CPU work; host has {os.cpu_count()} logical cores",
+                  f"{len(times)} passes, {total:.1f} s of CPU work; BLAS threads {threads} of "
+                  f"{os.cpu_count()} logical cores (OMP_NUM_THREADS={os.environ.get('OMP_NUM_THREADS', 'unset')} overridden)",
         "ms_per_pass": 1e3 * total / len(times),
+        "passes": len(times),
     }
 
 
 def run_reference(a):
+    """`--impl reference`: the reference's CPU implementation of the path (numpy oracle port -- the
+    reference is pure Python and /root/reference does not exist on the GPU box) on all host cores.
+    Same metric / unit / config / steps / warm-up as our arm; rank 0 alone runs it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(a.steps, 20))
-    res = cpu_inner_sample(a, steps, a.warmup)
+    res = cpu_inner_sample(a, a.steps, max(a.warmup, 3))
     line = {
         "impl": "reference",
         "metric": METRIC,
         "value": res["value"],
         "unit": UNIT,
         "n_gpus": a.gpus,
-        "steps": steps,
-        "warmup": min(a.warmup, 2),
+        "steps": a.steps,
+        "warmup": max(a.warmup, 3),
         "ms_per_step": res["ms_per_pass"],
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(a), "note": "reference's CPU path (numpy oracle port; the "
-                   "reference is pure Python and cannot be imported on the GPU box)"},
+        "config": workload_config(a),
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "each step is one pass of the numpy sweep over a d=8 slice of the workload (1/8 of the cores; the "
+                "sweep cost is linear in d, so GFLOP/s is the full workload's)",
     }
     print(json.dumps(line), flush=True)
 
@@ -417,14 +443,8 @@ def main():
             "vs_baseline": None,
             "dtype": "f64",
             "data": "synthetic",
-            "config": {
-                "workload": workload_name(a),
-                "flops_per_step": int(flops),
-                "bytes_resident": int(nbytes),
-                "l2": "inputs (2.08 GB per TT pair) larger than the 126 MB L2; no flush needed",
-                "multi_gpu": "replicas only (one independent TT pair per rank, no collective)",
-                "inner_value": result_val,
-            },
+            "config": workload_config(a),
+            "inner_value": result_val,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,

@@ -225,6 +225,13 @@ int ttb_scale_rows_f64(double* mat, int64_t rows, int64_t cols, int64_t ld, cons
                        void* stream);
 /* out (n x n, row-major) = diag(s): the S node of Tensor.svd (np.diag(s), pytens/algs.py:262) */
 int ttb_diag_f64(const double* s, int64_t n, double* out, void* stream);
+/* Core k of a batch rounded in place by ttb_round_batched_f64 (item i: C-order (rl_i, n, rr_i) at the
+ * start of its slab of `slab` doubles, ranks from the DEVICE (batch, d+1) table) -> out, the uniform
+ * zero-padded C-order array (batch, RL, n, RR): a valid core of bond ranks (RL, RR) for every item, so
+ * the rounded cores of all shards can be all-gathered as one array (north_star item 4: "all-gather of
+ * scalar and core results"). */
+int ttb_pack_rounded_cores_f64(const double* core, int64_t batch, int64_t slab, int64_t n, const int64_t* ranks_dev,
+                               int32_t d, int32_t k, int64_t RL, int64_t RR, double* out, void* stream);
 /* y = alpha * x + beta * y over count elements (x may be NULL: y *= beta): TensorNetwork.scale
  * (pytens/algs.py:578-583) and the one-node case of TensorNetwork.__add__ */
 int ttb_axpby_f64(int64_t count, double alpha, const double* x, double beta, double* y, void* stream);

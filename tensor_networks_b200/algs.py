@@ -54,6 +54,9 @@ __all__ = [
 ]
 
 
+_STREAM_MIN_BYTES = 32 << 20  # host-resident TT pairs at least this large take the streamed inner product
+
+
 def _size(indices: Sequence[Index], positions: Sequence[int]) -> int:
     out = 1
     for i in positions:
@@ -434,6 +437,11 @@ class TensorNetwork:
         pair of networks takes the reference's own route, attach() + contract(), node by node on the
         device -- free indices that are not shared stay open, as in the reference."""
         if self._tt_compatible(other):
+            a, b = _tt_cores(self), _tt_cores(other)
+            host = not any(dense.is_dev(v) for v in a + b)
+            if host and sum(v.nbytes for v in a + b) >= _STREAM_MIN_BYTES:
+                # numpy cores: the sweep starts at once and the cores stream in underneath it
+                return TensorTrain.inner_host(a, b)
             return _train_of(self).inner(_train_of(other))
         return np.asarray(dense.to_host(self.attach(other).contract().value), dtype=np.float64)
 

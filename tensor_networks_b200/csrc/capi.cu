@@ -255,6 +255,10 @@ int ttb_scale_rows_f64(double* mat, int64_t rows, int64_t cols, int64_t ld, cons
 int ttb_diag_f64(const double* s, int64_t n, double* out, void* stream) {
     return ttb::diag_embed(s, n, out, as_stream(stream));
 }
+int ttb_pack_rounded_cores_f64(const double* core, int64_t batch, int64_t slab, int64_t n, const int64_t* ranks_dev,
+                               int32_t d, int32_t k, int64_t RL, int64_t RR, double* out, void* stream) {
+    return ttb::pack_rounded_cores(core, batch, slab, n, ranks_dev, d, k, RL, RR, out, as_stream(stream));
+}
 int ttb_axpby_f64(int64_t count, double alpha, const double* x, double beta, double* y, void* stream) {
     return ttb::axpby(count, alpha, x, beta, y, as_stream(stream));
 }

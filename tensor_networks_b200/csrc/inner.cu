@@ -14,6 +14,7 @@
 // interest (16 MiB at r = 256, n = 32).
 #include "gemm.cuh"
 #include "tt.cuh"
+#include "staging.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -124,17 +125,27 @@ int inner_streamed(const TTDesc& A, const TTDesc& B, const double* const* a_host
     TTB_CHECK_CUDA(cudaMemsetAsync(flags, 0, size_t(d + 2) * sizeof(int), stream));
     TTB_CHECK_CUDA(cudaEventRecord(ev_reset, stream));
     TTB_CHECK_CUDA(cudaStreamWaitEvent(copy_stream, ev_reset, 0));
+    // debug hook for the time-out test: never raise the ready flag of one core
+    static const int drop_flag = [] {
+        const char* e = getenv("TTB_STREAM_DROP_FLAG");
+        return e ? atoi(e) : -1;
+    }();
+    std::vector<HostCopy> copies;
+    copies.reserve(size_t(2 * d));
     for (int k = 0; k < d; ++k) {
         const size_t na = size_t(A.r[k]) * A.n[k] * A.r[k + 1] * sizeof(double);
         const size_t nb = size_t(B.r[k]) * B.n[k] * B.r[k + 1] * sizeof(double);
-        TTB_CHECK_CUDA(cudaMemcpyAsync(A.core[k], a_host[k], na, cudaMemcpyHostToDevice, copy_stream));
-        TTB_CHECK_CUDA(cudaMemcpyAsync(B.core[k], b_host[k], nb, cudaMemcpyHostToDevice, copy_stream));
-        TTB_CHECK_CUDA(cudaMemsetAsync(flags + k, 1, sizeof(int), copy_stream));  // 0x01010101: ready
+        copies.push_back({A.core[k], a_host[k], na, -1});
+        copies.push_back({B.core[k], b_host[k], nb, k == drop_flag ? -1 : k});
     }
-    TTB_CHECK_CUDA(cudaEventRecord(ev_copied, copy_stream));
-    // every copy is already queued, so the kernel can only ever wait for work that is in flight
+    // The persistent kernel is launched FIRST and polls the per-core flags; the copies (pinned: enqueued
+    // directly; pageable: staged through the pinned ring by host threads, which takes about as long as the
+    // transfer itself) then stream in underneath it.  A copy that never arrives ends in the kernel's
+    // time-out (NaN result + fail flag), not in a hang.
     int st = kUnsupported;
     if (fused_enabled()) st = inner_fused(A, B, out_dev, rest, rest_bytes, stream, flags, flags + d);
+    TTB_PROPAGATE(staged_h2d(copies, flags, copy_stream));
+    TTB_CHECK_CUDA(cudaEventRecord(ev_copied, copy_stream));
     if (st == kUnsupported) {
         TTB_CHECK_CUDA(cudaStreamWaitEvent(stream, ev_copied, 0));
         return inner(A, B, out_dev, rest, rest_bytes, stream);

@@ -58,13 +58,23 @@ struct SweepParams {
     long long* timing;  // TTB_SWEEP_TIMING: clock64 sums of CTA 0 {phase1, barrier1, phase2, barrier2, phase3, barrier3}
     const int* ready;   // streamed mode: ready[k] != 0 once cores k of A and B have landed in HBM (copy engine); else null
     int* fail;          // streamed mode: set when a core did not arrive within the time-out
+    long long timeout_cycles;  // streamed mode: how long a CTA waits for one core
 };
 
 // Streamed mode: the cores are being copied host -> device by the copy engines on another stream while
 // this kernel runs; thread 0 polls the per-core flag that the copy stream sets (stream-ordered after the
-// data) with system scope, then the CTA proceeds.  A generous time-out turns a lost copy into an error
-// instead of a hung GPU.  Returns false (uniformly) on time-out.
-__device__ __forceinline__ bool wait_core_ready(const int* ready, int k, int* fail) {
+// data) with system scope, then the CTA proceeds.  A time-out (p.timeout_cycles, ~4 s by default) turns a
+// lost copy into an error instead of a hung GPU: the first CTA that gives up raises *fail and writes NaN
+// to the result; every other CTA sees *fail in its own polling loop -- here or inside grid_barrier -- and
+// returns as well, so no CTA is left spinning at a barrier that can never complete.
+__device__ __forceinline__ bool abort_raised(const int* fail) {
+    int f;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(fail) : "memory");
+    return f != 0;
+}
+
+__device__ __forceinline__ bool wait_core_ready(const int* ready, int k, int* fail, long long timeout_cycles,
+                                                double* out) {
     __shared__ int ok_sh;
     if (threadIdx.x == 0) {
         int ok = 1;
@@ -74,9 +84,14 @@ __device__ __forceinline__ bool wait_core_ready(const int* ready, int k, int* fa
             asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(ready + k) : "memory");
             if (v == 0) {
                 __nanosleep(200);
-                if (clock64() - t0 > 8000000000ll) {  // ~4 s
+                if (abort_raised(fail)) {
                     ok = 0;
-                    *fail = 1;
+                    break;
+                }
+                if (clock64() - t0 > timeout_cycles) {
+                    ok = 0;
+                    if (atomicExch(fail, 1) == 0) out[0] = __longlong_as_double(0x7ff8000000000000ll);  // NaN
+                    __threadfence();
                     break;
                 }
             }
@@ -90,22 +105,36 @@ __device__ __forceinline__ bool wait_core_ready(const int* ready, int k, int* fa
     return ok;
 }
 
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
+// Returns false (uniformly over the CTA) when the sweep was aborted while waiting (streamed mode only).
+template <bool STREAMED>
+__device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& epoch, const int* fail) {
+    __shared__ int alive_sh;
     __syncthreads();
     if (threadIdx.x == 0) {
         ++epoch;
         const unsigned target = epoch * gridDim.x;
+        int alive = 1;
         __threadfence();
         atomicAdd(counter, 1u);
         unsigned v;
+        unsigned spins = 0;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (STREAMED && v < target && (++spins & 1023u) == 0 && abort_raised(fail)) {
+                alive = 0;
+                break;
+            }
         } while (v < target);
         __threadfence();
+        if (STREAMED) alive_sh = alive;
     } else {
         ++epoch;
     }
     __syncthreads();
+    if (!STREAMED) return true;
+    const bool alive = alive_sh != 0;
+    __syncthreads();
+    return alive;
 }
 
 // Pull `rows` rows of `doubles_per_row` contiguous doubles (leading dimension ld) into L2 while the
@@ -138,7 +167,7 @@ __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams
     if (TIMING && timing) tlast = clock64();
 
     for (int k = 0; k < p.d - 1; ++k) {
-        if (STREAMED && !wait_core_ready(p.ready, k, p.fail)) return;  // every CTA times out alike
+        if (STREAMED && !wait_core_ready(p.ready, k, p.fail, p.timeout_cycles, p.out)) return;
         const SweepStep s = p.steps[k];
         const double* Ein = cur ? p.E1 : p.E0;
         double* Eout = cur ? p.E0 : p.E1;
@@ -189,7 +218,7 @@ __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams
                 }
             }
             FS_TICK(0)
-            grid_barrier(p.barrier, epoch);
+            if (!grid_barrier<STREAMED>(p.barrier, epoch, p.fail)) return;
             FS_TICK(1)
             if (s.eb_order) {
                 A2 = s.A; B2 = p.T; K2 = int64_t(s.a) * s.n;   // E' = A_k (a n x a')^T . T (a n x b')
@@ -236,7 +265,7 @@ __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams
             }
         }
         FS_TICK(2)
-        grid_barrier(p.barrier, epoch);
+        if (!grid_barrier<STREAMED>(p.barrier, epoch, p.fail)) return;
         FS_TICK(3)
         // ---------------- phase 3: deterministic reduction of the partials ----------------
         if (s.splits > 1) {
@@ -253,14 +282,14 @@ __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams
                 E2[idx] = acc;
             }
             FS_TICK(4)
-            grid_barrier(p.barrier, epoch);
+            if (!grid_barrier<STREAMED>(p.barrier, epoch, p.fail)) return;
             FS_TICK(5)
         }
         cur ^= 1;
     }
 
     // ---------------- last core: <A,B> = sum_{i,s} A_d[i][s] * (E . B_d)[i][s] ----------------
-    if (STREAMED && !wait_core_ready(p.ready, p.d - 1, p.fail)) return;
+    if (STREAMED && !wait_core_ready(p.ready, p.d - 1, p.fail, p.timeout_cycles, p.out)) return;
     {
         const SweepStep s = p.steps[p.d - 1];
         const double* Ein = cur ? p.E1 : p.E0;
@@ -281,7 +310,7 @@ __global__ void __launch_bounds__(FS_NT, 1) inner_sweep_kernel(const SweepParams
             for (int w = 0; w < FS_NT / 32; ++w) v += red[w];
             p.P[blockIdx.x] = v;
         }
-        grid_barrier(p.barrier, epoch);
+        if (!grid_barrier<STREAMED>(p.barrier, epoch, p.fail)) return;
         if (blockIdx.x == 0 && tid == 0) {
             double v = 0.0;
             for (unsigned w = 0; w < gridDim.x; ++w) v += __ldcg(p.P + w);
@@ -363,20 +392,29 @@ int inner_fused(const TTDesc& A, const TTDesc& B, double* out_dev, void* ws, siz
     FusedPlan pl;
     if (!plan_fused(A, B, &pl)) return kUnsupported;
     if (ws == nullptr || ws_bytes < fused_bytes(pl, A.d)) return kUnsupported;
-    static int coop = -1, max_blocks = 0;
-    if (coop < 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
+    // which instantiation runs: plain, in-kernel timing (TTB_SWEEP_TIMING), or streamed (per-core ready flags)
+    static const bool sweep_timing = getenv("TTB_SWEEP_TIMING") != nullptr;
+    const int variant = ready_dev != nullptr ? 2 : (sweep_timing ? 1 : 0);
+    void* const kerns[3] = {reinterpret_cast<void*>(inner_sweep_kernel<false, false>),
+                            reinterpret_cast<void*>(inner_sweep_kernel<true, false>),
+                            reinterpret_cast<void*>(inner_sweep_kernel<false, true>)};
+    // cooperative-launch feasibility is a property of the instantiation actually launched (register
+    // use differs) and of the current device
+    static int conf_dev[3] = {-1, -1, -1}, feasible[3] = {0, 0, 0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (conf_dev[variant] != dev) {
+        int coop = 0, max_blocks = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-        if (cudaFuncSetAttribute(inner_sweep_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFusedSmem)) !=
-            cudaSuccess)
+        if (cudaFuncSetAttribute(kerns[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFusedSmem)) != cudaSuccess)
             coop = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, inner_sweep_kernel<false, false>, FS_NT, kFusedSmem) !=
-            cudaSuccess)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, kerns[variant], FS_NT, kFusedSmem) != cudaSuccess)
             max_blocks = 0;
         cudaGetLastError();
+        feasible[variant] = (coop && max_blocks >= 1) ? 1 : 0;
+        conf_dev[variant] = dev;
     }
-    if (!coop || max_blocks < 1) return kUnsupported;
+    if (!feasible[variant]) return kUnsupported;
 
     Workspace W(ws, ws_bytes);
     double* E0 = W.take<double>(pl.e_elems);
@@ -402,25 +440,22 @@ int inner_fused(const TTDesc& A, const TTDesc& B, double* out_dev, void* ws, siz
     sp.ready = ready_dev;
     sp.fail = fail_dev;
     static long long* timing_dev = nullptr;
-    static const bool sweep_timing = getenv("TTB_SWEEP_TIMING") != nullptr;
     if (sweep_timing && !timing_dev) cudaMalloc(&timing_dev, 64);
     sp.timing = sweep_timing ? timing_dev : nullptr;
+    static const long long timeout_cycles = [] {
+        const char* e = getenv("TTB_STREAM_TIMEOUT_CYCLES");
+        return e ? atoll(e) : 8000000000ll;  // ~4 s at 1.97 GHz
+    }();
+    sp.timeout_cycles = timeout_cycles;
     void* args[] = {&sp};
     const int slot = profile_begin(stream);
-    void* kern = reinterpret_cast<void*>(inner_sweep_kernel<false, false>);
-    if (sweep_timing || ready_dev != nullptr) {
-        kern = ready_dev != nullptr ? reinterpret_cast<void*>(inner_sweep_kernel<false, true>)
-                                    : reinterpret_cast<void*>(inner_sweep_kernel<true, false>);
-        static bool tconf = false;
-        if (!tconf) {
-            TTB_CHECK_CUDA(cudaFuncSetAttribute(inner_sweep_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                int(kFusedSmem)));
-            TTB_CHECK_CUDA(cudaFuncSetAttribute(inner_sweep_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                int(kFusedSmem)));
-            tconf = true;
-        }
+    const cudaError_t le = cudaLaunchCooperativeKernel(kerns[variant], dim3(num_sms()), dim3(FS_NT), args, kFusedSmem, stream);
+    if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources) {
+        (void)cudaGetLastError();
+        feasible[variant] = 0;  // the caller falls back to the per-GEMM path
+        return kUnsupported;
     }
-    TTB_CHECK_CUDA(cudaLaunchCooperativeKernel(kern, dim3(num_sms()), dim3(FS_NT), args, kFusedSmem, stream));
+    TTB_CHECK_CUDA(le);
     ++g_launch_count;
     profile_end(slot, pl.flops, stream);
     if (sweep_timing) {

@@ -133,6 +133,25 @@ __global__ void __launch_bounds__(256) axpby_kernel(int64_t count, double alpha,
     }
 }
 
+
+// Rounded batch cores, compact per item -> uniform zero-padded layout.  Item i of `core` (slab
+// stride `slab` doubles) holds its core as the C-order array (rl_i, n, rr_i) at the slab start, with
+// rl_i = ranks[i * (d + 1) + k], rr_i = ranks[i * (d + 1) + k + 1] (what ttb_round_batched_f64 leaves);
+// out is (batch, RL, n, RR) with zeros beyond the item's own ranks -- a valid core of bond ranks
+// (RL, RR) for every item, so that the cores of a whole batch can be all-gathered as one array.
+__global__ void __launch_bounds__(256) pack_rounded_kernel(const double* __restrict__ core, int64_t batch, int64_t slab,
+                                                           int64_t n, const int64_t* __restrict__ ranks, int d, int k,
+                                                           int64_t RL, int64_t RR, double* __restrict__ out) {
+    const int64_t per = RL * n * RR, total = batch * per;
+    for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t i = idx / per, rem = idx % per;
+        const int64_t a = rem / (n * RR), jn = (rem / RR) % n, b = rem % RR;
+        const int64_t rl = ranks[i * (d + 1) + k], rr = ranks[i * (d + 1) + k + 1];
+        out[idx] = (a < rl && b < rr) ? core[i * slab + (a * n + jn) * rr + b] : 0.0;
+    }
+}
+
 inline int grid_for(int64_t total, int per_block = 256) {
     const int64_t want = ceil_div<int64_t>(total, per_block);
     return int(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(num_sms()) * 16)));
@@ -236,6 +255,17 @@ int diag_embed(const double* s, int64_t n, double* out, cudaStream_t stream) {
     if (n <= 0) return kOk;
     TTB_REQUIRE(s && out, "diag: null pointer");
     diag_kernel<<<grid_for(n * n), 256, 0, stream>>>(s, n, out);
+    ++g_launch_count;
+    TTB_CHECK_CUDA(cudaGetLastError());
+    return kOk;
+}
+
+int pack_rounded_cores(const double* core, int64_t batch, int64_t slab, int64_t n, const int64_t* ranks_dev, int d,
+                       int k, int64_t RL, int64_t RR, double* out, cudaStream_t stream) {
+    if (batch <= 0) return kOk;
+    TTB_REQUIRE(core && ranks_dev && out, "pack_rounded_cores: null pointer");
+    TTB_REQUIRE(k >= 0 && k < d && n >= 1 && RL >= 1 && RR >= 1 && slab >= 1, "pack_rounded_cores: bad extents");
+    pack_rounded_kernel<<<grid_for(batch * RL * n * RR), 256, 0, stream>>>(core, batch, slab, n, ranks_dev, d, k, RL, RR, out);
     ++g_launch_count;
     TTB_CHECK_CUDA(cudaGetLastError());
     return kOk;

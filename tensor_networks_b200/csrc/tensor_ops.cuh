@@ -17,6 +17,9 @@ int fill(double* dst, int64_t count, double value, cudaStream_t stream);
 int scale_rows(double* mat, int64_t rows, int64_t cols, int64_t ld, const double* s, int mode, cudaStream_t stream);
 // out (n x n, row-major) = diag(s)
 int diag_embed(const double* s, int64_t n, double* out, cudaStream_t stream);
+// compact per-item rounded cores of a batch -> uniform zero-padded (batch, RL, n, RR) array (see tensor_ops.cu)
+int pack_rounded_cores(const double* core, int64_t batch, int64_t slab, int64_t n, const int64_t* ranks_dev, int d,
+                       int k, int64_t RL, int64_t RR, double* out, cudaStream_t stream);
 // y = alpha x + beta y (x may be null: y *= beta)
 int axpby(int64_t count, double alpha, const double* x, double beta, double* y, cudaStream_t stream);
 

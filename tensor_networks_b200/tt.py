@@ -299,6 +299,58 @@ class TensorTrain:
         out._ttb_keepalive = (dev_a, dev_b, host_a, host_b)
         return out
 
+    @staticmethod
+    def inner_host(host_a: Sequence[np.ndarray], host_b: Sequence[np.ndarray]) -> np.ndarray:
+        """<A, B> for two trains whose cores are ordinary (pageable) numpy arrays -- what a pytens caller
+        holds (`TensorNetwork.inner`, pytens/algs.py:585-587).  The reference's core shapes are accepted
+        (2-d first / last core).  The persistent sweep kernel starts at once; host threads stage the cores
+        through a pinned ring to the copy engines underneath it (`ttb_inner_streamed_f64`, csrc/staging.cu),
+        so the transfer overlaps the contraction.  Returns a 0-d float64 array; synchronous."""
+        import ctypes
+
+        _require_cuda()
+        L = _lib.lib()
+        if len(host_a) != len(host_b):
+            raise AssertionError("inner: operands have different numbers of cores")
+        d = len(host_a)
+
+        def prep(cores):
+            out = []
+            for k, c in enumerate(cores):
+                a = np.ascontiguousarray(c, dtype=np.float64)
+                if a.ndim == 2 and k == 0 and d > 1:
+                    a = a.reshape(1, a.shape[0], a.shape[1])
+                elif a.ndim == 2 and k == d - 1:
+                    a = a.reshape(a.shape[0], a.shape[1], 1)
+                elif a.ndim == 1 and d == 1:
+                    a = a.reshape(1, -1, 1)
+                elif a.ndim != 3:
+                    raise ValueError(f"core {k} has unsupported shape {a.shape}")
+                out.append(a)
+            return out
+
+        ha, hb = prep(host_a), prep(host_b)
+        dev_a = TensorTrain([torch.empty(h.shape, dtype=torch.float64, device="cuda") for h in ha])
+        dev_b = TensorTrain([torch.empty(h.shape, dtype=torch.float64, device="cuda") for h in hb])
+        if dev_a.shape() != dev_b.shape():
+            raise AssertionError("inner: free indices (mode sizes) differ")
+        da, db = dev_a.descriptor(), dev_b.descriptor()
+        pa = (ctypes.c_void_p * d)(*[int(h.ctypes.data) for h in ha])
+        pb = (ctypes.c_void_p * d)(*[int(h.ctypes.data) for h in hb])
+        ws = workspace(L.ttb_inner_streamed_workspace_bytes(da.ref(), db.ref()), dev_a.device)
+        out = torch.empty((), dtype=torch.float64, device=dev_a.device)
+        global _COPY_STREAM
+        if _COPY_STREAM is None:
+            _COPY_STREAM = torch.cuda.Stream()
+        check(L.ttb_inner_streamed_f64(da.ref(), db.ref(), pa, pb, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       _stream_ptr(), _COPY_STREAM.cuda_stream))
+        val = out.item()  # synchronises the compute stream; ha / hb / dev_* stay alive until here
+        _COPY_STREAM.synchronize()
+        if val != val:
+            raise RuntimeError("streamed inner product: a core did not arrive within the time-out "
+                               "(or an operand contains NaN)")
+        return np.asarray(val, dtype=np.float64)
+
     def inner_dev(self, other: "TensorTrain", out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """<self, other> as a 0-d CUDA tensor; no host synchronisation."""
         L = _lib.lib()

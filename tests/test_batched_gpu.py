@@ -142,3 +142,31 @@ def test_round_batched_cfg5_items():
 
 def test_round_batched_large_rank_fallback():
     _round_case(2, [6] * 4, [20, 24, 18], 1e-8, 5, "double")
+
+
+def test_pack_rounded_cores_uniform_layout():
+    """All-gather of core results (north_star item 4): the pack kernel turns the per-item compact cores
+    of a rounded batch into one zero-padded array per core; every item still is the same tensor."""
+    from tensor_networks_b200.batch import TensorTrainBatch
+    from tensor_networks_b200.sharding import all_gather_cores, padded_ranks, round_sharded
+
+    rng = np.random.default_rng(17)
+    shape = [4, 5, 3, 4]
+    items = []
+    for i in range(6):  # items of different true ranks, stored with the same capacity ranks (6, 6, 6)
+        x = orc.rand_tt(shape, [1 + i % 3, 2 + i % 2, 1 + (i + 1) % 3], rng)
+        pad = orc.rand_tt(shape, [6 - c.shape[2] for c in x[:-1]], rng)
+        pad[0] = pad[0] * 0.0
+        items.append(orc.tt_add(x, pad))
+    y = TensorTrainBatch.from_numpy(items)
+    table, full = round_sharded(y, 1e-10, 6, gather_cores=True)  # single process: gathers are identities
+    ranks = table.cpu().numpy()
+    assert sorted(set(ranks[:, 1].tolist())) == [1, 2, 3]
+    rcap = padded_ranks(table)
+    assert full.bond_ranks() == rcap and full.batch == 6 and full.item_ranks is None
+    for i in range(6):
+        want = orc.to_dense(items[i])
+        got = full.item(i).dense()
+        assert np.linalg.norm(got - want) <= 1e-9 * np.linalg.norm(want)
+    same = all_gather_cores(y, 6, table)
+    assert all(torch.equal(a, b) for a, b in zip(same.cores, full.cores))

@@ -47,7 +47,17 @@ def _worker(rank, world, port, batch, q):
     ranks_local = torch.arange(lo, hi, dtype=torch.int64)[:, None] * torch.ones(1, 5, dtype=torch.int64)
     ranks_full = all_gather_items(ranks_local, batch)
     ok_ranks = bool(torch.equal(ranks_full[:, 0], torch.arange(batch, dtype=torch.int64)))
-    q.put((rank, ok_scalar and ok_ranks))
+    # uniformly padded cores (what all_gather_cores moves after the pack kernel) and the padded ranks
+    from tensor_networks_b200.sharding import all_gather_padded_cores, padded_ranks
+
+    table = torch.tensor([[1, 1 + (i % 3), 2 + (i % 2), 1] for i in range(batch)], dtype=torch.int64)
+    rcap = padded_ranks(table)
+    ok_cap = rcap == [1, min(3, batch), 3 if batch > 1 else 2, 1]
+    gen = torch.Generator().manual_seed(7)
+    full_cores = [torch.randn((batch, rcap[k], 4, rcap[k + 1]), dtype=torch.float64, generator=gen) for k in range(3)]
+    got = all_gather_padded_cores([c[lo:hi].clone() for c in full_cores], batch)
+    ok_cores = all(torch.equal(g, f) for g, f in zip(got, full_cores))
+    q.put((rank, ok_scalar and ok_ranks and ok_cap and ok_cores))
     dist.barrier()
     dist.destroy_process_group()
 
