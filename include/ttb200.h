@@ -198,6 +198,16 @@ int ttb_ttsvd_f64(const double* dense, int32_t d, const int64_t* shape, double e
                   double* arena, size_t arena_doubles, int64_t* ranks_out, double* delta_out,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- host -> device upload of pageable buffers -----------------------------------
+ * Copies count host buffers (ordinary pageable memory such as numpy arrays, or pinned memory) to
+ * device buffers on `stream`.  Pageable sources are staged in 4 MB chunks through a ring of pinned
+ * slots by a pool of host threads and handed to the copy engine chunk by chunk, in order (the same
+ * machinery that ttb_inner_streamed_f64 uses); pinned sources are enqueued directly.  This is how the
+ * numpy cores a pytens caller holds (Tensor.value, pytens/algs.py:46-52) reach HBM at near-PCIe rate.
+ * Returns once every chunk has been ENQUEUED; the data is complete when `stream` is. */
+int ttb_h2d_staged(void* const* dst_dev, const void* const* src_host, const size_t* bytes, int32_t count,
+                   void* stream);
+
 /* ---- dense-tensor data movement for the node-level network operations -------------
  * The tensor-network API above the TT sweeps (Tensor.svd / Tensor.qr / Tensor.contract /
  * Tensor.permute / Tensor.block_diagonal, pytens/algs.py:201-344; tt_sum, ttop_sum,

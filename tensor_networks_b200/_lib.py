@@ -142,6 +142,8 @@ def _declare(lib):
     lib.ttb_tt_to_dense_f64.restype = c_int
     lib.ttb_tt_to_dense_f64.argtypes = [P(ttb_tt), c_void_p, c_void_p, c_size_t, c_void_p]
 
+    lib.ttb_h2d_staged.restype = c_int
+    lib.ttb_h2d_staged.argtypes = [P(c_void_p), P(c_void_p), P(c_size_t), c_int32, c_void_p]
     lib.ttb_strided_copy_f64.restype = c_int
     lib.ttb_strided_copy_f64.argtypes = [c_void_p, c_void_p, c_int32, P(c_int64), P(c_int64), P(c_int64), c_void_p]
     lib.ttb_strided_op_f64.restype = c_int

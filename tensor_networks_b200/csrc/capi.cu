@@ -9,6 +9,7 @@
 #include "batched.cuh"
 #include "ttsvd.cuh"
 #include "tensor_ops.cuh"
+#include "staging.cuh"
 
 namespace ttb {
 double debug_chol_bench_us(int w, int reps);
@@ -236,6 +237,18 @@ int ttb_ttsvd_f64(const double* dense, int32_t d, const int64_t* shape, double e
                       workspace_bytes, as_stream(stream));
 }
 
+
+int ttb_h2d_staged(void* const* dst_dev, const void* const* src_host, const size_t* bytes, int32_t count, void* stream) {
+    if (count <= 0) return ttb::kOk;
+    if (!dst_dev || !src_host || !bytes) {
+        ttb::set_last_error("ttb_h2d_staged: null pointer");
+        return ttb::kInvalidArgument;
+    }
+    std::vector<ttb::HostCopy> copies;
+    copies.reserve(size_t(count));
+    for (int i = 0; i < count; ++i) copies.push_back({dst_dev[i], src_host[i], bytes[i], -1});
+    return ttb::staged_h2d(copies, nullptr, as_stream(stream));
+}
 
 int ttb_strided_copy_f64(double* dst, const double* src, int32_t ndim, const int64_t* shape,
                          const int64_t* dst_strides, const int64_t* src_strides, void* stream) {

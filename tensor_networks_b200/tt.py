@@ -81,7 +81,7 @@ class TensorTrain:
         """Upload host cores.  Accepts the reference's shapes (2-d first/last core)."""
         _require_cuda()
         d = len(cores)
-        out = []
+        host = []
         for k, c in enumerate(cores):
             a = np.ascontiguousarray(np.asarray(c, dtype=np.float64))
             if a.ndim == 2 and d == 1:
@@ -92,6 +92,21 @@ class TensorTrain:
                 a = a.reshape(a.shape[0], a.shape[1], 1)
             elif a.ndim != 3:
                 raise ValueError(f"core {k} has unsupported shape {a.shape}")
+            host.append(a)
+        if not pinned and sum(a.nbytes for a in host) >= (32 << 20):
+            # large pageable upload: staged through the pinned ring by the library's host threads
+            import ctypes
+
+            L = _lib.lib()
+            out = [torch.empty(a.shape, dtype=torch.float64, device=device) for a in host]
+            dst = (ctypes.c_void_p * d)(*[int(t.data_ptr()) for t in out])
+            src = (ctypes.c_void_p * d)(*[int(a.ctypes.data) for a in host])
+            nb = (ctypes.c_size_t * d)(*[int(a.nbytes) for a in host])
+            check(L.ttb_h2d_staged(dst, src, nb, d, _stream_ptr()))
+            torch.cuda.current_stream().synchronize()  # the numpy buffers may go away after this call
+            return cls(out)
+        out = []
+        for a in host:
             t = torch.from_numpy(a)
             if pinned:
                 t = t.pin_memory()
