@@ -96,7 +96,7 @@ static bool fused_enabled() {
 
 size_t inner_workspace_bytes(const TTDesc& a, const TTDesc& b) {
     if (a.d != b.d || a.d < 1) return 0;
-    return std::max(inner_layout(a, b).total(), inner_fused_workspace_bytes(a, b));
+    return std::max(std::max(inner_layout(a, b).total(), inner_fused_workspace_bytes(a, b)), inner_tma_workspace_bytes(a, b));
 }
 
 size_t inner_streamed_workspace_bytes(const TTDesc& a, const TTDesc& b) {
@@ -143,7 +143,8 @@ int inner_streamed(const TTDesc& A, const TTDesc& B, const double* const* a_host
     // transfer itself) then stream in underneath it.  A copy that never arrives ends in the kernel's
     // time-out (NaN result + fail flag), not in a hang.
     int st = kUnsupported;
-    if (fused_enabled()) st = inner_fused(A, B, out_dev, rest, rest_bytes, stream, flags, flags + d);
+    if (fused_enabled()) st = inner_tma(A, B, out_dev, rest, rest_bytes, stream, flags, flags + d);
+    if (fused_enabled() && st == kUnsupported) st = inner_fused(A, B, out_dev, rest, rest_bytes, stream, flags, flags + d);
     TTB_PROPAGATE(staged_h2d(copies, flags, copy_stream));
     TTB_CHECK_CUDA(cudaEventRecord(ev_copied, copy_stream));
     if (st == kUnsupported) {
@@ -165,8 +166,11 @@ int inner(const TTDesc& A, const TTDesc& B, double* out_dev, void* ws, size_t ws
     TTB_REQUIRE(out_dev != nullptr, "inner: null output");
 
     if (fused_enabled()) {
-        // one persistent cooperative kernel for the whole sweep when every step is large
-        const int st = inner_fused(A, B, out_dev, ws, ws_bytes, stream);
+        // one persistent cooperative kernel for the whole sweep when every step is large: the TMA-staged
+        // strip kernel for bond ranks <= 256, else the three-phase kernel
+        int st = inner_tma(A, B, out_dev, ws, ws_bytes, stream);
+        if (st != kUnsupported) return st;
+        st = inner_fused(A, B, out_dev, ws, ws_bytes, stream);
         if (st != kUnsupported) return st;
     }
     const InnerLayout L = inner_layout(A, B);

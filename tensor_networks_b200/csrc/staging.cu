@@ -18,13 +18,56 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 namespace ttb {
 
 namespace {
 
-constexpr size_t kSlotBytes = size_t(4) << 20;
-constexpr int kSlots = 24;
+// Ring geometry: TTB_STAGE_SLOT_MB (default 4) x TTB_STAGE_SLOTS (default 24, at most kMaxSlots).
+constexpr int kMaxSlots = 64;
+size_t env_slot_bytes() {
+    const char* e = getenv("TTB_STAGE_SLOT_MB");
+    const int mb = e ? atoi(e) : 0;
+    return size_t(mb > 0 && mb <= 256 ? mb : 4) << 20;
+}
+int env_slots() {
+    const char* e = getenv("TTB_STAGE_SLOTS");
+    const int n = e ? atoi(e) : 0;
+    return (n >= 2 && n <= kMaxSlots) ? n : 24;
+}
+const size_t kSlotBytes = env_slot_bytes();
+const int kSlots = env_slots();
+
+// Copy into the pinned ring.  TTB_STAGE_NT=1 uses streaming (non-temporal) stores: the destination is read
+// next by the copy engine, never by this core, so it need not be allocated in (or read into) the cache.
+const bool kNtStores = [] {
+    const char* e = getenv("TTB_STAGE_NT");
+    return e != nullptr && e[0] == '1';
+}();
+void stage_copy(char* dst, const char* src, size_t bytes) {
+#if defined(__x86_64__)
+    if (kNtStores && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
+        const size_t n16 = bytes / 64;
+        const __m128i* s = reinterpret_cast<const __m128i*>(src);
+        __m128i* d = reinterpret_cast<__m128i*>(dst);
+        for (size_t i = 0; i < n16; ++i) {
+            const __m128i a = _mm_load_si128(s + 4 * i), b = _mm_load_si128(s + 4 * i + 1);
+            const __m128i c = _mm_load_si128(s + 4 * i + 2), e = _mm_load_si128(s + 4 * i + 3);
+            _mm_stream_si128(d + 4 * i, a);
+            _mm_stream_si128(d + 4 * i + 1, b);
+            _mm_stream_si128(d + 4 * i + 2, c);
+            _mm_stream_si128(d + 4 * i + 3, e);
+        }
+        _mm_sfence();
+        if (bytes % 64) std::memcpy(dst + n16 * 64, src + n16 * 64, bytes % 64);
+        return;
+    }
+#endif
+    std::memcpy(dst, src, bytes);
+}
 
 struct Chunk {
     void* dst;
@@ -84,6 +127,7 @@ class Stager {
         const char* e = getenv("TTB_STAGE_THREADS");
         int want = e ? atoi(e) : 0;
         if (want <= 0) want = int(std::min<unsigned>(8u, std::max(2u, std::thread::hardware_concurrency() / 2)));
+        want = std::min(want, 64);
         nthreads_ = std::max(1, want);
         for (int i = 0; i < nthreads_; ++i) workers_.emplace_back([this] { loop(); });
     }
@@ -151,7 +195,7 @@ class Stager {
                     if (cudaEventSynchronize(slot_free_[slot]) != cudaSuccess) job.error = 1;
                 }
                 char* to = ring_ + size_t(slot) * kSlotBytes;
-                std::memcpy(to, c.src, c.bytes);
+                stage_copy(to, c.src, c.bytes);
                 from = to;
             }
             while (job.next_issue.load(std::memory_order_acquire) != i && !job.error.load()) std::this_thread::yield();
@@ -177,8 +221,8 @@ class Stager {
     int nthreads_ = 1;
     int device_ = 0;
     char* ring_ = nullptr;
-    cudaEvent_t slot_free_[kSlots];
-    bool slot_used_[kSlots];
+    cudaEvent_t slot_free_[kMaxSlots];
+    bool slot_used_[kMaxSlots];
 };
 
 bool is_pinned(const void* p) {

@@ -29,6 +29,11 @@ size_t inner_fused_workspace_bytes(const TTDesc& a, const TTDesc& b);
 int inner_fused(const TTDesc& a, const TTDesc& b, double* out_dev, void* ws, size_t ws_bytes,
                 cudaStream_t stream, const int* ready_dev = nullptr, int* fail_dev = nullptr);
 
+// TMA-staged persistent sweep for bond ranks <= 256 (inner_tma.cu); kUnsupported when the shapes do not qualify
+size_t inner_tma_workspace_bytes(const TTDesc& a, const TTDesc& b);
+int inner_tma(const TTDesc& a, const TTDesc& b, double* out_dev, void* ws, size_t ws_bytes, cudaStream_t stream,
+              const int* ready_dev = nullptr, int* fail_dev = nullptr);
+
 // <A, B> of two trains whose cores still sit in (pinned) HOST memory: the cores are copied to the device
 // buffers of `a` / `b` on `copy_stream` while the persistent sweep kernel already runs on `stream` and
 // waits, core by core, for the data (per-core ready flags set by the copy stream).  Falls back to
