@@ -349,8 +349,8 @@ def main():
                 traffic = None
         roofline = {
             "bound": "tensor",
-            "kernel": ("inner_sweep_kernel (persistent fused sweep: DMMA gemm_tile phases + grid barriers, "
-                       "one launch per sweep)" if int(nl.value) <= psteps else
+            "kernel": ("inner_tma_kernel (persistent TMA-staged strip sweep: cp.async.bulk.tensor + mbarrier ring, both DMMA GEMMs "
+                       "of a core chained in shared memory, one launch per sweep)" if int(nl.value) <= psteps else
                        "dgemm_kernel (FP64 DMMA mma.sync.m8n8k4)"),
             "achieved": achieved,
             "peak": peak,

@@ -89,16 +89,17 @@ struct TmaParams {
 };
 
 // ---- mbarrier / TMA primitives (PTX) ----
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+// (barriers are addressed by their 32-bit shared-memory address: no generic -> shared conversion in the hot loop)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n"
@@ -107,28 +108,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(bar), "r"(parity)
         : "memory");
     return ok != 0;
 }
 // A wait that can never complete (a lost TMA transaction) traps after ~2 s instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
@@ -178,16 +179,16 @@ __device__ __forceinline__ void mma_stage(double (&acc)[4][NJ][2], const double*
 // nk stages of one GEMM pass; B_RING: B fragments from the ring stage (GEMM 1) or from the T strip (GEMM 2)
 template <int JLO, int JHI, bool B_RING>
 __device__ __forceinline__ void run_pass(double (&acc)[4][NJ][2], uint32_t& it, int nk, const double* ring,
-                                         uint64_t* full_bar, uint64_t* empty_bar, int a_off, int b_off,
+                                         uint32_t full_bar, uint32_t empty_bar, int a_off, int b_off,
                                          const double* __restrict__ Tb, int lane) {
     for (int kt = 0; kt < nk; ++kt, ++it) {
         const int s = it % TM_STAGES;
-        mbar_wait(&full_bar[s], (it / TM_STAGES) & 1);
+        mbar_wait(full_bar + 8 * s, (it / TM_STAGES) & 1);
         const double* stg = ring + s * STAGE_ELEMS;
         mma_stage<JLO, JHI>(acc, stg + a_off, B_RING ? stg + 2 * F_HALF + b_off : Tb + kt * BKT * TP);
         // every fragment of this stage has been consumed by an issued DMMA: the stage may be refilled
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        if (lane == 0) mbar_arrive(empty_bar + 8 * s);
     }
 }
 
@@ -197,8 +198,9 @@ __global__ void __launch_bounds__(TM_NT, 1) inner_tma_kernel(const TmaParams p) 
     // 1024-byte aligned start, computed as an offset so that the pointer keeps its shared-memory provenance (LDS, not LD)
     double* ring = reinterpret_cast<double*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     double* Ts = ring + TM_STAGES * STAGE_ELEMS;
-    __shared__ __align__(8) uint64_t full_bar[TM_STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[TM_STAGES];
+    __shared__ __align__(8) uint64_t full_bar_sh[TM_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar_sh[TM_STAGES];
+    const uint32_t full_bar = smem_u32(full_bar_sh), empty_bar = smem_u32(empty_bar_sh);  // + 8 * stage
     __shared__ double red[TM_NT / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -217,8 +219,8 @@ __global__ void __launch_bounds__(TM_NT, 1) inner_tma_kernel(const TmaParams p) 
 
     if (tid == 0) {
         for (int s = 0; s < TM_STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], TM_CONS / 32);
+            mbar_init(full_bar + 8 * s, 1);
+            mbar_init(empty_bar + 8 * s, TM_CONS / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
@@ -235,7 +237,6 @@ __global__ void __launch_bounds__(TM_NT, 1) inner_tma_kernel(const TmaParams p) 
             for (int s = 0; s < p.n0; ++s) v = fma(p.A0[int64_t(s) * p.a1 + i], p.B0[int64_t(s) * p.b1 + j], v);
             p.F1[p.first_transposed ? int64_t(j) * p.a1 + i : int64_t(idx)] = v;
         }
-        __threadfence();
         fence_proxy_async();
         if (!grid_barrier<STREAMED>(p.barrier, epoch, p.fail)) return;
     }
@@ -257,22 +258,22 @@ __global__ void __launch_bounds__(TM_NT, 1) inner_tma_kernel(const TmaParams p) 
                     const int c0 = t * TW;
                     for (int kt = 0; kt < nk1; ++kt, ++it) {
                         const int s = it % TM_STAGES;
-                        mbar_wait(&empty_bar[s], ((it / TM_STAGES) & 1) ^ 1);
+                        mbar_wait(empty_bar + 8 * s, ((it / TM_STAGES) & 1) ^ 1);
                         double* stg = ring + s * STAGE_ELEMS;
-                        mbar_expect_tx(&full_bar[s], kBytesGemm1);
-                        tma_load_2d(stg, &st->mapF, 0, kt * BKT, &full_bar[s]);
-                        tma_load_2d(stg + F_HALF, &st->mapF, 128, kt * BKT, &full_bar[s]);
-                        tma_load_2d(stg + 2 * F_HALF, &st->mapC1, c0, kt * BKT, &full_bar[s]);
+                        mbar_expect_tx(full_bar + 8 * s, kBytesGemm1);
+                        tma_load_2d(stg, &st->mapF, 0, kt * BKT, full_bar + 8 * s);
+                        tma_load_2d(stg + F_HALF, &st->mapF, 128, kt * BKT, full_bar + 8 * s);
+                        tma_load_2d(stg + 2 * F_HALF, &st->mapC1, c0, kt * BKT, full_bar + 8 * s);
                     }
                     const StripSlices sl = strip_slices(c0, K2, ncols);
                     for (int ps = 0; ps < sl.passes; ++ps) {  // a straddling strip: slice s0, then slice s0 + 1
                         for (int kt = 0; kt < nk2; ++kt, ++it) {
                             const int s = it % TM_STAGES;
-                            mbar_wait(&empty_bar[s], ((it / TM_STAGES) & 1) ^ 1);
+                            mbar_wait(empty_bar + 8 * s, ((it / TM_STAGES) & 1) ^ 1);
                             double* stg = ring + s * STAGE_ELEMS;
-                            mbar_expect_tx(&full_bar[s], kBytesGemm2);
-                            tma_load_3d(stg, &st->mapC2, 0, sl.s0 + ps, kt * BKT, &full_bar[s]);
-                            tma_load_3d(stg + F_HALF, &st->mapC2, 128, sl.s0 + ps, kt * BKT, &full_bar[s]);
+                            mbar_expect_tx(full_bar + 8 * s, kBytesGemm2);
+                            tma_load_3d(stg, &st->mapC2, 0, sl.s0 + ps, kt * BKT, full_bar + 8 * s);
+                            tma_load_3d(stg + F_HALF, &st->mapC2, 128, sl.s0 + ps, kt * BKT, full_bar + 8 * s);
                         }
                     }
                 }
@@ -367,8 +368,7 @@ __global__ void __launch_bounds__(TM_NT, 1) inner_tma_kernel(const TmaParams p) 
                     *reinterpret_cast<double2*>(Fout + int64_t(m2) * K2 + j) = acc2;
                 }
             }
-            __threadfence();
-            fence_proxy_async();
+            fence_proxy_async();  // generic-proxy stores -> TMA reads of the next step; the grid barrier releases them
         }
         TM_TICK(3)
         if (!grid_barrier<STREAMED>(p.barrier, epoch, p.fail)) return;

@@ -61,8 +61,9 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& epoch,
         ++epoch;
         const unsigned target = epoch * gridDim.x;
         int alive = 1;
-        __threadfence();
-        atomicAdd(counter, 1u);
+        // release-arrive / acquire-poll: the bar.sync above orders the other threads' writes before this release
+        // (cumulativity), so no separate __threadfence() pair is needed around the counter (saves ~1k clk per barrier)
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         unsigned v;
         unsigned spins = 0;
         do {
@@ -72,7 +73,6 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& epoch,
                 break;
             }
         } while (v < target);
-        __threadfence();
         if (STREAMED) alive_sh = alive;
     } else {
         ++epoch;
