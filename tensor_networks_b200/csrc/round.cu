@@ -132,7 +132,8 @@ void trunc_svd_reset_heuristics() { g_cert_skip = g_cert_backoff = 0; }
 
 int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizing, int max_rank,
               double jacobi_abs_tol, bool inplace, double* U_out, double* SVt_out, double* sigma_out,
-              TruncSvdInfo* res, void* ws, size_t ws_bytes, cudaStream_t stream, double deflate_tol) {
+              TruncSvdInfo* res, void* ws, size_t ws_bytes, cudaStream_t stream, double deflate_tol,
+              double jacobi_stop_rel) {
     TTB_REQUIRE(M && U_out && SVt_out && res, "trunc_svd: null pointer");
     TTB_REQUIRE(m >= 1 && c >= 1, "trunc_svd: empty matrix");
     TTB_REQUIRE(std::min(m, c) <= 8192, "trunc_svd: min(m, n) > 8192 unsupported");
@@ -250,13 +251,15 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
             return e == nullptr || e[0] != '0';
         }();
         const double jtol = path == kPathWideLQ ? 0.0 : jacobi_abs_tol;
+        // (for the same reason the relaxed stopping level of a sweep applies only where U is built from J)
+        if (path == kPathWideLQ) jacobi_stop_rel = 0.0;
         if (lq2_enabled && path != kPathWideDirect && p >= 2 && q >= 2 * p) {
             double* R2 = Lm;                       // p x p
             double* L2 = Jsel;                     // p x p = R2^T, the rows to rotate (Jsel is free until the gathers)
             int64_t rk2 = p;
             TTB_PROPAGATE(orth_rows(X, p, q, q, R2, p, sub, rest, stream, 0.0, &rk2));  // X <- Q2 (orthonormal rows)
             TTB_PROPAGATE(transpose(R2, p, p, p, L2, p, stream));
-            jst = jacobi_rows(L2, p, p, p, J, jtol, noise_floor, 40, &sweeps, conv, hw.conv, stream);
+            jst = jacobi_rows(L2, p, p, p, J, jtol, noise_floor, 40, &sweeps, conv, hw.conv, stream, jacobi_stop_rel);
             if (jst == kOk || jst == kNotConverged) {
                 GemmArgs g;  // Xrot (p x q) = L2rot (p x p) . Q2 (p x q)
                 g.M = p; g.N = q; g.K = p;
@@ -267,7 +270,7 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
                 TTB_CHECK_CUDA(cudaMemcpyAsync(X, Lm, size_t(p) * q * 8, cudaMemcpyDeviceToDevice, stream));
             }
         } else {
-            jst = jacobi_rows(X, p, q, q, J, jtol, noise_floor, 40, &sweeps, conv, hw.conv, stream);
+            jst = jacobi_rows(X, p, q, q, J, jtol, noise_floor, 40, &sweeps, conv, hw.conv, stream, jacobi_stop_rel);
         }
     }
     if (jst != kOk && jst != kNotConverged) return jst;
@@ -449,7 +452,7 @@ int round_tt(const TTDesc& t, double eps, int max_rank, int64_t* ranks_out, doub
         const double abs_tol = first ? 0.0 : 1e-14 * fro;
         // M = core_k (m x c); U overwrites core_k compactly as (m x rho)
         TTB_PROPAGATE(trunc_svd(t.core[k], m, c, dl, first, max_rank, abs_tol, false, t.core[k], SVt, nullptr, &info,
-                                sub, rest, stream));
+                                sub, rest, stream, 0.0, kSweepJacobiStop));
         if (first) {
             delta_abs = info.delta_abs;
             fro = std::sqrt(info.fro2);

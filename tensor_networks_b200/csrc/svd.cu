@@ -918,8 +918,9 @@ size_t jacobi_workspace_bytes(int p) { return round_up<size_t>(size_t(p) * p * 8
 
 int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol, double noise_floor, int max_sweeps,
                 int* sweeps_out, unsigned long long* conv_dev, unsigned long long* conv_host_pinned,
-                cudaStream_t stream) {
+                cudaStream_t stream, double stop_rel) {
     TTB_REQUIRE(X && J && conv_dev && conv_host_pinned, "jacobi_rows: null pointer");
+    if (!(stop_rel > 0.0)) stop_rel = 3e-8;
     TTB_REQUIRE(p >= 1 && q >= 1 && ldx >= q, "jacobi_rows: bad extents");
     if (sweeps_out) *sweeps_out = 0;
     if (p == 1) {
@@ -974,7 +975,7 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
             cp.tol = 1e-15 * std::sqrt(double(std::max(q, 16)));
             cp.abs_tol2 = abs_tol * abs_tol;
             cp.noise2 = noise_floor * noise_floor;
-            cp.stop_rel = std::max(cp.tol, 3e-8);  // quadratic convergence: the rotations of that sweep leave ~1e-15
+            cp.stop_rel = std::max(cp.tol, stop_rel);  // quadratic convergence: the rotations of that sweep leave ~stop_rel^2
             cp.max_sweeps = max_sweeps;
             cp.out = reinterpret_cast<double*>(conv_dev);
             static const bool jtiming = getenv("TTB_JACOBI_TIMING") != nullptr;
@@ -1032,7 +1033,7 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
                 (void)cudaGetLastError();
                 nonportable_ok = false;
                 return jacobi_rows(X, p, q, ldx, J, abs_tol, noise_floor, max_sweeps, sweeps_out, conv_dev, conv_host_pinned,
-                                   stream);
+                                   stream, stop_rel);
             }
             (void)cudaGetLastError();  // cluster shape not schedulable here: fall through to the multi-launch path
         }
@@ -1101,7 +1102,7 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
         // mx is the largest relative off-diagonal met BEFORE its rotation in this sweep; Jacobi
         // converges quadratically, so once it is below 3e-8 the rotations of this very sweep have
         // pushed it to the 1e-18 level and no verification sweep is needed.
-        if (mx <= std::max(jp.tol, 3e-8)) return kOk;
+        if (mx <= std::max(jp.tol, stop_rel)) return kOk;
     }
     set_last_error("jacobi_rows: not converged after " + std::to_string(max_sweeps) + " sweeps");
     return kNotConverged;

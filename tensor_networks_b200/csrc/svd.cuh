@@ -15,7 +15,11 @@ namespace ttb {
 // Synchronises `stream` once per sweep.
 int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol, double noise_floor, int max_sweeps,
                 int* sweeps_out, unsigned long long* conv_dev, unsigned long long* conv_host_pinned,
-                cudaStream_t stream);
+                cudaStream_t stream, double stop_rel = 0.0);
+// stop_rel: the iteration ends after the first sweep whose largest relative off-diagonal, measured BEFORE its
+// rotation, is <= stop_rel (0 = 3e-8).  Jacobi converges quadratically, so that sweep itself leaves ~stop_rel^2.
+// J stays orthogonal to machine precision whatever the value; only the residual coupling of the rotated rows
+// (and with it the optimality of a truncation, at the stop_rel^4 level of the discarded energy) depends on it.
 
 // Row norms of X -> singular values (descending) with their row permutation, and
 // the reference's truncation rule (pytens/utils.py:70-85):

@@ -134,7 +134,7 @@ int ttsvd(const double* dense, int d, const int64_t* shape, double eps, int max_
         // (same safe deflation as the RQ pass of the rounding sweep, see round.cu)
         const double deflate_tol = deflation_tolerance(eps, std::max(m, c));
         TTB_PROPAGATE(trunc_svd(bufA, m, c, delta, false, max_rank, 1e-14 * fro, /*inplace=*/true, arena + off,
-                                bufB, nullptr, &info, sub, rest, stream, deflate_tol));
+                                bufB, nullptr, &info, sub, rest, stream, deflate_tol, kSweepJacobiStop));
         const int64_t rho = info.rank;
         if (getenv("TTB_DEBUG"))
             fprintf(stderr, "[ttsvd] step %d: m=%lld c=%lld rank=%lld sweeps=%d converged=%d fro2=%.6e delta=%.3e\n", k,
