@@ -101,6 +101,7 @@ int host_words(HostWords* hw) {
 // ---------------------------------------------------------------------------
 namespace {
 constexpr size_t kGemmWsCap = size_t(64) << 20;  // recommended split-K scratch, never required
+constexpr int kJacobiMaxSweeps = 40;
 
 enum SvdPath { kPathTall, kPathWideLQ, kPathWideDirect };
 SvdPath svd_path(int64_t m, int64_t c) {
@@ -118,6 +119,7 @@ size_t trunc_svd_required(int64_t m, int64_t c, bool inplace) {
     if (path == kPathTall || !inplace) b += round_up<size_t>(size_t(m) * c * 8, 256);  // M^T / copy of M
     b += 4 * round_up<size_t>(size_t(p) * std::max(p, path == kPathWideLQ ? p : c) * 8, 256);  // R, J, Jsel, L
     b += 4 * round_up<size_t>(size_t(p) * 8, 256) + 1024;  // perm, sigma, nrm2, info/conv
+    b += round_up<size_t>(jacobi_log_bytes(int(p), kJacobiMaxSweeps), 256);  // rotation log of the Jacobi kernel
     if (path == kPathTall) b += orth_rows_workspace_bytes(c, m);
     if (path == kPathWideLQ) b += orth_rows_workspace_bytes(m, c);
     return b + 4096;
@@ -160,6 +162,8 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
     double* nrm2 = W.take<double>(p);
     double* info = W.take<double>(8);
     unsigned long long* conv = W.take<unsigned long long>(64);
+    const size_t jlog_bytes = jacobi_log_bytes(int(std::min(m, c)), kJacobiMaxSweeps);
+    char* jlog = jlog_bytes ? W.take<char>(jlog_bytes) : nullptr;
     TTB_REQUIRE(big && Rm && J && Jsel && Lm && perm && sigma && nrm2 && info && conv, "trunc_svd: carve failed");
     const size_t rest = ws_bytes - W.off;
     void* sub = W.base + W.off;
@@ -259,7 +263,8 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
             int64_t rk2 = p;
             TTB_PROPAGATE(orth_rows(X, p, q, q, R2, p, sub, rest, stream, 0.0, &rk2));  // X <- Q2 (orthonormal rows)
             TTB_PROPAGATE(transpose(R2, p, p, p, L2, p, stream));
-            jst = jacobi_rows(L2, p, p, p, J, jtol, noise_floor, 40, &sweeps, conv, hw.conv, stream, jacobi_stop_rel);
+            jst = jacobi_rows(L2, p, p, p, J, jtol, noise_floor, kJacobiMaxSweeps, &sweeps, conv, hw.conv, stream, jacobi_stop_rel, jlog,
+                              jlog ? jlog_bytes : 0);
             if (jst == kOk || jst == kNotConverged) {
                 GemmArgs g;  // Xrot (p x q) = L2rot (p x p) . Q2 (p x q)
                 g.M = p; g.N = q; g.K = p;
@@ -270,7 +275,8 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
                 TTB_CHECK_CUDA(cudaMemcpyAsync(X, Lm, size_t(p) * q * 8, cudaMemcpyDeviceToDevice, stream));
             }
         } else {
-            jst = jacobi_rows(X, p, q, q, J, jtol, noise_floor, 40, &sweeps, conv, hw.conv, stream, jacobi_stop_rel);
+            jst = jacobi_rows(X, p, q, q, J, jtol, noise_floor, kJacobiMaxSweeps, &sweeps, conv, hw.conv, stream, jacobi_stop_rel, jlog,
+                              jlog ? jlog_bytes : 0);
         }
     }
     if (jst != kOk && jst != kNotConverged) return jst;

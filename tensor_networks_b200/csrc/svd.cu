@@ -377,6 +377,12 @@ struct JacobiClusterParams {
     int timing;   // 1: thread 0 of CTA 0 accumulates clock64() per phase section into out[2..7]
     int dbuf;     // 1: two tile buffers per CTA -- the apply step PUSHES the rotated rows straight into the next
                   // owner's other buffer (DSMEM stores), one cluster barrier per phase instead of pull + two
+    // Rotation log: when wlog != nullptr the kernel rotates ONLY the rows of X (ncol == qx, J is not staged, applied
+    // or exchanged) and writes the 2b x 2b rotation of every (sweep, phase, CTA) to wlog together with the two
+    // block indices it acted on; apply_wlog_kernel replays the log on column slices of the identity afterwards.
+    // Halves the rows' width in shared memory, in the DMMA apply and in the DSMEM exchange of every phase.
+    double* wlog;
+    int* blog;
 };
 // Rows per block: 16 (32 staged rows per CTA) or 8 (16 staged rows: twice the CTAs and phases, but the
 // 16 x 16 Gram makes every rotation round ~40 % cheaper and the tiles to exchange half as large).
@@ -500,6 +506,15 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
             jacobi_rounds<2 * JC_B>(G, W, R2, JC_B, 1, rt, true, pcs, pij, &blk_max);
             const double* Wf = W;
             if (tid == 0) sweep_max = fmax(sweep_max, blk_max);
+            if (p.wlog != nullptr) {
+                const size_t e = (size_t(sweep) * nphase + phase) * h + rank;
+                double* dst = p.wlog + e * (R2 * R2);
+                for (int idx = tid; idx < R2 * R2; idx += JB_NT) dst[idx] = W[(idx / R2) * JB_GP + (idx % R2)];
+                if (tid == 0) {
+                    p.blog[2 * e] = arr_top[rank];
+                    p.blog[2 * e + 1] = arr_bot[rank];
+                }
+            }
             JC_TICK(1)
 
             // ---- apply: rows' = Wf . T in place, one 32-column slab per warp (slabs are disjoint) ----
@@ -654,7 +669,8 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
         double* xr = p.X + int64_t(gr) * p.ldx;
         double* jr = p.J + int64_t(gr) * p.p;
         for (int k = lane; k < p.q; k += 32) xr[k] = t[k];
-        for (int k = lane; k < p.p; k += 32) jr[k] = t[p.qx + k];
+        if (p.wlog == nullptr)
+            for (int k = lane; k < p.p; k += 32) jr[k] = t[p.qx + k];
     }
     if (rank == 0 && tid == 0) {
         p.out[0] = double(sweeps);
@@ -802,6 +818,88 @@ __global__ void __launch_bounds__(TI_NT, 1) tri_inv_fro_dmma_kernel(const double
     }
 }
 
+// Replay of the rotation log on a column slice of J = I.  CTA c owns columns [c * AW, c * AW + AW) of all rows
+// (shared memory); a phase of the log is h independent 2b x 2b rotations on disjoint row-block pairs, staged
+// with cp.async one phase ahead; warp w applies the entries w, w + 8, ... as (2b x 2b) . (2b x 8) DMMA products
+// (the rows of an entry belong to that entry alone, so only a warp-level barrier separates read and write).
+// Reads the number of sweeps from the status words of the Jacobi kernel, so no host round trip sits between
+// the two launches.
+constexpr int AW = 8;        // columns per CTA (one DMMA n tile)
+constexpr int AWP = 12;      // pitch of the slice rows (== 12 mod 16: conflict-free B fragments)
+constexpr int AW_NT = 256;
+template <int JC_B>
+__global__ void __launch_bounds__(AW_NT) apply_wlog_kernel(const double* __restrict__ wlog, const int* __restrict__ blog,
+                                                           const double* __restrict__ status, int p, int nb,
+                                                           double* __restrict__ J) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int R2 = 2 * JC_B;
+    constexpr int WP = R2 + 4;                    // pitch of a staged rotation (conflict-free A fragments)
+    const int h = nb >> 1, nphase = nb - 1;
+    const int rows = nb * JC_B;
+    double* Js = sm;                              // [rows][AWP]
+    double* Wst = Js + size_t(rows) * AWP;        // 2 x [h][R2][WP]
+    int* Bst = reinterpret_cast<int*>(Wst + 2 * size_t(h) * R2 * WP);  // 2 x [h][2]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frow = lane >> 2, fk = lane & 3;
+    const int c0 = blockIdx.x * AW;
+    const int total_phases = int(status[0]) * nphase;
+    for (int idx = tid; idx < rows * AWP; idx += AW_NT) {
+        const int r = idx / AWP, c = idx % AWP;
+        Js[idx] = (c < AW && r == c0 + c) ? 1.0 : 0.0;
+    }
+    auto stage = [&](int ph, int buf) {
+        const double* src = wlog + size_t(ph) * h * R2 * R2;
+        double* dst = Wst + size_t(buf) * h * R2 * WP;
+        constexpr int CPR = R2 / 2;  // 16-byte chunks per rotation row
+        for (int idx = tid; idx < h * R2 * CPR; idx += AW_NT) {
+            const int row = idx / CPR, ch = idx % CPR;
+            cp_async16(dst + size_t(row) * WP + 2 * ch, src + size_t(row) * R2 + 2 * ch, true);
+        }
+        if (tid < 2 * h) Bst[buf * 2 * h + tid] = blog[size_t(ph) * 2 * h + tid];
+        cp_async_commit();
+    };
+    if (total_phases > 0) stage(0, 0);
+    for (int ph = 0; ph < total_phases; ++ph) {
+        const int buf = ph & 1;
+        if (ph + 1 < total_phases) {
+            stage(ph + 1, buf ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();  // the staged rotations of this phase are visible; every warp is done with the previous phase
+        const double* Wp = Wst + size_t(buf) * h * R2 * WP;
+        const int* Bp = Bst + buf * 2 * h;
+        for (int e = warp; e < h; e += AW_NT / 32) {
+            const int bt = Bp[2 * e] * JC_B, bb = Bp[2 * e + 1] * JC_B;
+            const double* w = Wp + size_t(e) * R2 * WP;
+            double acc[R2 / 8][2];
+#pragma unroll
+            for (int i = 0; i < R2 / 8; ++i) acc[i][0] = acc[i][1] = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < R2 / 4; ++kk) {
+                const int k = 4 * kk + fk;
+                const int src_row = k < JC_B ? bt + k : bb + (k - JC_B);
+                const double bfrag = Js[src_row * AWP + frow];
+#pragma unroll
+                for (int i = 0; i < R2 / 8; ++i) dmma884(acc[i][0], acc[i][1], w[(8 * i + frow) * WP + k], bfrag);
+            }
+            __syncwarp();  // all lanes have read the old rows of this entry
+#pragma unroll
+            for (int i = 0; i < R2 / 8; ++i) {
+                const int r = 8 * i + frow;
+                const int dst_row = r < JC_B ? bt + r : bb + (r - JC_B);
+                *reinterpret_cast<double2*>(Js + dst_row * AWP + 2 * fk) = make_double2(acc[i][0], acc[i][1]);
+            }
+        }
+        __syncthreads();  // the next stage() overwrites the buffer just used two iterations from now; rows are final
+    }
+    for (int idx = tid; idx < rows * AW; idx += AW_NT) {
+        const int r = idx / AW, c = idx % AW;
+        if (r < p && c0 + c < p) J[size_t(r) * p + c0 + c] = Js[r * AWP + c];
+    }
+}
+
 __global__ void set_identity_kernel(double* J, int p) {
     const int64_t total = int64_t(p) * p;
     for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -916,9 +1014,21 @@ int pick_block(int p, int q, int* ncol_out, int* qx_out, size_t* smem_out) {
 
 size_t jacobi_workspace_bytes(int p) { return round_up<size_t>(size_t(p) * p * 8, 256) + 1024; }
 
+// Bytes of the rotation log of the single-launch Jacobi kernel for p rows and max_sweeps sweeps (0 when the
+// cluster kernel cannot take the problem anyway).  Same block-size choice as jacobi_rows.
+size_t jacobi_log_bytes(int p, int max_sweeps) {
+    if (p <= 32 || p > 256) return 0;
+    const int jcb = ceil_div(p, 8) <= 32 ? 8 : 16;
+    int nbc = std::max(2, ceil_div(p, jcb));
+    if (nbc & 1) ++nbc;
+    // (if the 16-CTA cluster is refused the kernel falls back to 16-row blocks: fewer, larger entries, same volume)
+    const size_t entries = size_t(max_sweeps) * size_t(nbc - 1) * size_t(nbc / 2);
+    return round_up<size_t>(entries * size_t(2 * jcb) * size_t(2 * jcb) * sizeof(double), 256) + entries * 2 * sizeof(int) + 256;
+}
+
 int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol, double noise_floor, int max_sweeps,
                 int* sweeps_out, unsigned long long* conv_dev, unsigned long long* conv_host_pinned,
-                cudaStream_t stream, double stop_rel) {
+                cudaStream_t stream, double stop_rel, void* log_ws, size_t log_bytes) {
     TTB_REQUIRE(X && J && conv_dev && conv_host_pinned, "jacobi_rows: null pointer");
     if (!(stop_rel > 0.0)) stop_rel = 3e-8;
     TTB_REQUIRE(p >= 1 && q >= 1 && ldx >= q, "jacobi_rows: bad extents");
@@ -957,6 +1067,20 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
             const char* e = getenv("TTB_JACOBI_PUSH");
             return e == nullptr || e[0] != '0';
         }();
+        // rotation-log mode (see JacobiClusterParams): rows of X only, J replayed afterwards
+        static const bool log_enabled = [] {
+            const char* e = getenv("TTB_JACOBI_LOG");
+            return e == nullptr || e[0] != '0';
+        }();
+        const size_t log_entries = size_t(max_sweeps) * size_t(nbc - 1) * size_t(nbc / 2);
+        const size_t log_w_bytes = round_up<size_t>(log_entries * size_t(2 * jcb) * size_t(2 * jcb) * sizeof(double), 256);
+        const bool log_mode = log_enabled && nbc > 2 && log_ws != nullptr && log_bytes >= log_w_bytes + log_entries * 2 * sizeof(int);
+        if (log_mode) {
+            cp.ncol = cp.qx;
+            cp.pitch = cp.ncol + 4;
+            cp.wlog = static_cast<double*>(log_ws);
+            cp.blog = reinterpret_cast<int*>(static_cast<char*>(log_ws) + log_w_bytes);
+        }
         size_t csmem = (size_t(2 * jcb) * cp.pitch + 2 * size_t(JB_MAXR) * JB_GP) * sizeof(double);
         {
             int dev0 = 0, maxsm0 = 0;
@@ -1013,6 +1137,20 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
             const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, cp);
             if (le == cudaSuccess) {
                 ++g_launch_count;
+                if (log_mode) {
+                    const size_t asmem = (size_t(nbc) * jcb * AWP + 2 * size_t(nbc / 2) * (2 * jcb) * (2 * jcb + 4)) * sizeof(double) +
+                                         2 * size_t(nbc) * sizeof(int) + 64;
+                    auto akern = (jcb == 8) ? apply_wlog_kernel<8> : apply_wlog_kernel<16>;
+                    static size_t aconf[2] = {0, 0};
+                    size_t& ac = aconf[jcb == 8 ? 0 : 1];
+                    if (asmem > ac) {
+                        TTB_CHECK_CUDA(cudaFuncSetAttribute(akern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(asmem)));
+                        ac = asmem;
+                    }
+                    akern<<<ceil_div(p, AW), AW_NT, asmem, stream>>>(cp.wlog, cp.blog, cp.out, p, nbc, J);
+                    ++g_launch_count;
+                    TTB_CHECK_CUDA(cudaGetLastError());
+                }
                 double* hout = reinterpret_cast<double*>(conv_host_pinned);
                 TTB_CHECK_CUDA(cudaMemcpyAsync(hout, cp.out, (jtiming ? 56 : 2) * sizeof(double), cudaMemcpyDeviceToHost, stream));
                 TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
@@ -1033,7 +1171,7 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
                 (void)cudaGetLastError();
                 nonportable_ok = false;
                 return jacobi_rows(X, p, q, ldx, J, abs_tol, noise_floor, max_sweeps, sweeps_out, conv_dev, conv_host_pinned,
-                                   stream, stop_rel);
+                                   stream, stop_rel, log_ws, log_bytes);
             }
             (void)cudaGetLastError();  // cluster shape not schedulable here: fall through to the multi-launch path
         }

@@ -15,7 +15,10 @@ namespace ttb {
 // Synchronises `stream` once per sweep.
 int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol, double noise_floor, int max_sweeps,
                 int* sweeps_out, unsigned long long* conv_dev, unsigned long long* conv_host_pinned,
-                cudaStream_t stream, double stop_rel = 0.0);
+                cudaStream_t stream, double stop_rel = 0.0, void* log_ws = nullptr, size_t log_bytes = 0);
+// log_ws / log_bytes (jacobi_log_bytes): scratch for the rotation log of the single-launch kernel -- with it the
+// kernel rotates only the rows of X and J is rebuilt from the logged rotations by a second, fully parallel launch.
+size_t jacobi_log_bytes(int p, int max_sweeps);
 // stop_rel: the iteration ends after the first sweep whose largest relative off-diagonal, measured BEFORE its
 // rotation, is <= stop_rel (0 = 3e-8).  Jacobi converges quadratically, so that sweep itself leaves ~stop_rel^2.
 // J stays orthogonal to machine precision whatever the value; only the residual coupling of the rotated rows
