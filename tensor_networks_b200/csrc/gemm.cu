@@ -439,6 +439,118 @@ size_t gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t batch) {
     return round_up<size_t>(size_t(s) * size_t(M) * size_t(N) * size_t(batch) * sizeof(double), 256);
 }
 
+// ---------------------------------------------------------------------------
+// Fused pass of the Cholesky-QR2 of a skinny unfolding (m <= 16 rows, K columns):
+//     Y = W . X   (W = L1^{-1}, 16 x 16)   and   G2 += Y Y^T
+// in ONE sweep over X -- the second Gram matrix needs no pass of its own.  Every warp handles blocks of 16
+// columns: a lane loads (row 4 kk + fq, columns c0 + 2 fr, c0 + 2 fr + 1) as one 16-byte word (128 contiguous
+// bytes per row and block); the even columns form one DMMA n tile and the odd columns the other, so the
+// accumulator fragments of a lane are Y[8 i + fr][c0 + 4 fq .. c0 + 4 fq + 3]: 32 contiguous bytes to store,
+// and -- any assignment of columns to k slots being valid for a Gram matrix as long as both operands agree --
+// exactly the A and B fragments of four k steps of Y Y^T.  Nothing is shuffled or staged in shared memory.
+// ---------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) skinny_apply_gram_kernel(const double* __restrict__ Wm, const double* __restrict__ X,
+                                                                int64_t ldx, double* __restrict__ Y, int64_t ldy, int m,
+                                                                int64_t K, double* __restrict__ P) {
+    __shared__ double red[8][16 * 17];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fq = lane & 3;
+    double a[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) a[i][kk] = Wm[(8 * i + fr) * 16 + 4 * kk + fq];
+    double g00[2] = {0.0, 0.0}, g01[2] = {0.0, 0.0}, g11[2] = {0.0, 0.0};
+    const int64_t nblk = K >> 4;
+    const int64_t tw = int64_t(gridDim.x) * 8, gw = int64_t(blockIdx.x) * 8 + warp;
+    bool rv[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) rv[kk] = 4 * kk + fq < m;
+    constexpr int UB = 2;  // column blocks per iteration: all loads in flight before the first DMMA
+    for (int64_t b0 = gw * UB; b0 < nblk; b0 += tw * UB) {
+        double2 x[UB][4];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int64_t c0 = (b0 + u) << 4;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                x[u][kk] = (rv[kk] && b0 + u < nblk)
+                               ? *reinterpret_cast<const double2*>(X + int64_t(4 * kk + fq) * ldx + c0 + 2 * fr)
+                               : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            if (b0 + u >= nblk) break;
+            const int64_t c0 = (b0 + u) << 4;
+            double ye[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, yo[2][2] = {{0.0, 0.0}, {0.0, 0.0}};  // [m tile][c0 / c1]
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    dmma884(ye[i][0], ye[i][1], a[i][kk], x[u][kk].x);
+                    dmma884(yo[i][0], yo[i][1], a[i][kk], x[u][kk].y);
+                }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if (8 * i + fr < m) {
+                    double* dst = Y + int64_t(8 * i + fr) * ldy + c0 + 4 * fq;
+                    *reinterpret_cast<double2*>(dst) = make_double2(ye[i][0], yo[i][0]);
+                    *reinterpret_cast<double2*>(dst + 2) = make_double2(ye[i][1], yo[i][1]);
+                }
+            // Gram: four k steps (columns c0 + 4 fq + {0, 2, 1, 3}); the B fragment of a lane is its own A fragment
+#pragma unroll
+            for (int s2 = 0; s2 < 4; ++s2) {
+                const double v0 = s2 == 0 ? ye[0][0] : s2 == 1 ? ye[0][1] : s2 == 2 ? yo[0][0] : yo[0][1];
+                const double v1 = s2 == 0 ? ye[1][0] : s2 == 1 ? ye[1][1] : s2 == 2 ? yo[1][0] : yo[1][1];
+                dmma884(g00[0], g00[1], v0, v0);
+                dmma884(g01[0], g01[1], v0, v1);
+                dmma884(g11[0], g11[1], v1, v1);
+            }
+        }
+    }
+    // block-level sum in shared memory, one partial per CTA (upper tiles mirrored)
+    red[warp][fr * 17 + 2 * fq] = g00[0];
+    red[warp][fr * 17 + 2 * fq + 1] = g00[1];
+    red[warp][fr * 17 + 8 + 2 * fq] = g01[0];
+    red[warp][fr * 17 + 8 + 2 * fq + 1] = g01[1];
+    red[warp][(8 + fr) * 17 + 8 + 2 * fq] = g11[0];
+    red[warp][(8 + fr) * 17 + 8 + 2 * fq + 1] = g11[1];
+    __syncthreads();
+    {
+        const int r = tid >> 4, c = tid & 15;
+        const bool lower = (r >= 8 && c < 8);
+        const int rr = lower ? c : r, cc = lower ? r : c;
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += red[w][rr * 17 + cc];
+        P[size_t(blockIdx.x) * 256 + r * 16 + c] = sum;
+    }
+}
+}  // namespace
+
+size_t skinny_apply_gram_workspace_bytes() { return size_t(2 * 148 + 64) * 256 * sizeof(double); }
+
+// Y (m x K, ld ldy) = W (16 x 16 row-major, device; rows / columns >= m ignored) . X (m x K, ld ldx) and
+// G (16 x 16, device, ld 16) = Y Y^T in one pass over X.  Needs m <= 16, K % 16 == 0, even leading dimensions and
+// 16-byte aligned X / Y; returns kUnsupported otherwise (the caller takes the two-pass route).
+int skinny_apply_gram(const double* W_dev, const double* X, int64_t ldx, double* Y, int64_t ldy, int m, int64_t K,
+                      double* G_dev, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (m < 1 || m > 16 || K < 16 || (K & 15) || (ldx & 1) || (ldy & 1) || (reinterpret_cast<uintptr_t>(X) & 15) ||
+        (reinterpret_cast<uintptr_t>(Y) & 15))
+        return kUnsupported;
+    const int grid = int(std::min<int64_t>(int64_t(2) * num_sms(), std::max<int64_t>(1, (K >> 4) / 16)));
+    if (ws == nullptr || ws_bytes < size_t(grid) * 256 * sizeof(double)) return kUnsupported;
+    const int slot = profile_begin(stream);
+    skinny_apply_gram_kernel<<<grid, 256, 0, stream>>>(W_dev, X, ldx, Y, ldy, m, K, static_cast<double*>(ws));
+    profile_end(slot, 4.0 * double(m) * double(m) * double(K), stream);
+    dim3 rgrid(8u, 1u);
+    splitk_reduce_small_kernel<<<rgrid, 256, 0, stream>>>(static_cast<double*>(ws), G_dev, 16, 16, 16, 0, grid, 1.0, 0.0);
+    g_launch_count += 2;
+    TTB_CHECK_CUDA(cudaGetLastError());
+    return kOk;
+}
+
 int gemm(const GemmArgs& g, void* ws, size_t ws_bytes, cudaStream_t stream) {
     TTB_REQUIRE(g.M >= 0 && g.N >= 0 && g.K >= 0, "gemm: negative extent");
     if (g.M == 0 || g.N == 0 || g.batch <= 0) return kOk;

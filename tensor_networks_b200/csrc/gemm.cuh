@@ -47,6 +47,11 @@ size_t gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t batch = 1);
 // when force_splits == 1.
 int gemm(const GemmArgs& args, void* ws, size_t ws_bytes, cudaStream_t stream);
 
+// Fused Cholesky-QR2 pass over a skinny matrix (see gemm.cu): Y = W . X and G = Y Y^T in one sweep.
+size_t skinny_apply_gram_workspace_bytes();
+int skinny_apply_gram(const double* W_dev, const double* X, int64_t ldx, double* Y, int64_t ldy, int m, int64_t K,
+                      double* G_dev, void* ws, size_t ws_bytes, cudaStream_t stream);
+
 // Per-launch CUDA-event timing of the dgemm kernels only (not the split-K reduce):
 // enable(1) resets the counters, read() synchronises the recorded events.
 int gemm_profile_enable(int enable);

@@ -120,9 +120,125 @@ size_t trunc_svd_required(int64_t m, int64_t c, bool inplace) {
     b += 4 * round_up<size_t>(size_t(p) * std::max(p, path == kPathWideLQ ? p : c) * 8, 256);  // R, J, Jsel, L
     b += 4 * round_up<size_t>(size_t(p) * 8, 256) + 1024;  // perm, sigma, nrm2, info/conv
     b += round_up<size_t>(jacobi_log_bytes(int(p), kJacobiMaxSweeps), 256);  // rotation log of the Jacobi kernel
+    if (path == kPathWideLQ && m <= 16) b += 3 * round_up<size_t>(256 * 8, 256) + skinny_apply_gram_workspace_bytes() + 4096;
     if (path == kPathTall) b += orth_rows_workspace_bytes(c, m);
     if (path == kPathWideLQ) b += orth_rows_workspace_bytes(m, c);
     return b + 4096;
+}
+}  // namespace
+
+namespace {
+// ---- skinny LQ: the first TT-SVD unfolding (m <= 16 rows, millions of columns) ----
+// Cholesky-QR2 in THREE passes over the data instead of the seven of the generic panel machinery:
+//   G1 = X X^T (also ||X||_F^2 = trace)                       read X
+//   Y = L1^{-1} X and G2 = Y Y^T in one fused sweep            read X, write Y        (skinny_apply_gram)
+//   carry = (diag(s) J[sel] L2^{-1}) Y                         read Y, write carry    (folded into the last GEMM)
+// The 16 x 16 Cholesky factors are computed on the host (two 2 KB round trips).  X = (L1 L2) Q with
+// Q = L2^{-1} Y (orthonormal rows, never formed): R^T = L1 L2.  Declines (handled = false, nothing written) when the
+// Gram matrix is too ill-conditioned for Cholesky-QR2 -- the generic path with Householder panels and
+// deflation then takes over.
+bool skinny_lq_applicable(int64_t m, int64_t c, const double* X, const double* Y) {
+    static const bool enabled = [] {
+        const char* e = getenv("TTB_SKINNY_LQ");
+        return e == nullptr || e[0] != '0';
+    }();
+    return enabled && m >= 2 && m <= 16 && c >= 65536 && (c & 15) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
+           (reinterpret_cast<uintptr_t>(Y) & 15) == 0;
+}
+bool host_cholesky(const double* G, int m, double* L, double min_rel_pivot) {  // G (16-pitch) = L L^T, L lower (16-pitch)
+    double dmax = 0.0;
+    for (int i = 0; i < m; ++i) dmax = std::max(dmax, G[i * 16 + i]);
+    if (!(dmax > 0.0) || !std::isfinite(dmax)) return false;
+    for (int i = 0; i < 16 * 16; ++i) L[i] = 0.0;
+    for (int j = 0; j < m; ++j) {
+        double d = G[j * 16 + j];
+        for (int k = 0; k < j; ++k) d -= L[j * 16 + k] * L[j * 16 + k];
+        if (!(d > min_rel_pivot * dmax)) return false;
+        const double ljj = std::sqrt(d);
+        L[j * 16 + j] = ljj;
+        for (int i = j + 1; i < m; ++i) {
+            double s = G[i * 16 + j];
+            for (int k = 0; k < j; ++k) s -= L[i * 16 + k] * L[j * 16 + k];
+            L[i * 16 + j] = s / ljj;
+        }
+    }
+    return true;
+}
+void host_lower_inverse(const double* L, int m, double* Li) {  // 16-pitch, zero padded
+    for (int i = 0; i < 16 * 16; ++i) Li[i] = 0.0;
+    for (int c = 0; c < m; ++c) {
+        Li[c * 16 + c] = 1.0 / L[c * 16 + c];
+        for (int i = c + 1; i < m; ++i) {
+            double s = 0.0;
+            for (int k = c; k < i; ++k) s -= L[i * 16 + k] * Li[k * 16 + c];
+            Li[i * 16 + c] = s / L[i * 16 + i];
+        }
+    }
+}
+struct SkinnyHost {
+    double* buf = nullptr;  // pinned: G (256) | W (256) | R (256) | L2inv (256) | L1 (256) | L2 (256)
+};
+int skinny_lq(const double* Xsrc, double* Y, int64_t m, int64_t c, double* Rm, double* L2inv_dev, void* sub, size_t rest,
+              cudaStream_t stream, bool* handled) {
+    *handled = false;
+    static SkinnyHost sh;
+    if (!sh.buf) {
+        void* p = nullptr;
+        TTB_CHECK_CUDA(cudaHostAlloc(&p, 6 * 256 * sizeof(double), cudaHostAllocDefault));
+        sh.buf = static_cast<double*>(p);
+    }
+    double *hG = sh.buf, *hW = sh.buf + 256, *hR = sh.buf + 512, *hL2i = sh.buf + 768, *hL1 = sh.buf + 1024, *hL2 = sh.buf + 1280;
+    Workspace W(sub, rest);
+    double* Gd = W.take<double>(256);
+    double* Wd = W.take<double>(256);
+    if (!Gd || !Wd) return kOk;
+    void* gws = W.base + W.off;
+    const size_t gws_bytes = rest - W.off;
+    if (gws_bytes < skinny_apply_gram_workspace_bytes()) return kOk;
+    const int mi = int(m);
+    // pass 1: G1 = X X^T
+    {
+        GemmArgs g;
+        g.M = m; g.N = m; g.K = c;
+        g.A = Xsrc; g.sAm = c; g.sAk = 1;
+        g.B = Xsrc; g.sBk = 1; g.sBn = c;
+        g.C = Gd; g.ldc = 16;
+        TTB_CHECK_CUDA(cudaMemsetAsync(Gd, 0, 256 * sizeof(double), stream));
+        ProfScope ps_("svd.skinny_gram", stream);
+        TTB_PROPAGATE(gemm(g, gws, gws_bytes, stream));
+    }
+    TTB_CHECK_CUDA(cudaMemcpyAsync(hG, Gd, 256 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
+    // cond(X)^2 <= ~1e12: the first pass then leaves cond(Y) - 1 <~ 1e-4 and the second one finishes the job
+    if (!host_cholesky(hG, mi, hL1, 1e-12)) return kOk;
+    host_lower_inverse(hL1, mi, hW);
+    TTB_CHECK_CUDA(cudaMemcpyAsync(Wd, hW, 256 * sizeof(double), cudaMemcpyHostToDevice, stream));
+    // pass 2: Y = L1^{-1} X, G2 = Y Y^T
+    {
+        ProfScope ps_("svd.skinny_apply_gram", stream);
+        const int st = skinny_apply_gram(Wd, Xsrc, c, Y, c, mi, c, Gd, gws, gws_bytes, stream);
+        if (st == kUnsupported) return kOk;
+        TTB_PROPAGATE(st);
+    }
+    TTB_CHECK_CUDA(cudaMemcpyAsync(hG, Gd, 256 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
+    if (!host_cholesky(hG, mi, hL2, 0.25)) {
+        set_last_error("trunc_svd: skinny LQ second Cholesky failed (matrix too ill-conditioned)");
+        return kNotConverged;
+    }
+    host_lower_inverse(hL2, mi, hL2i);
+    // R (p x m, p = m) with M = R^T Q:  R^T = L1 L2  =>  R[i][j] = sum_k L1[j][k] L2[k][i]
+    for (int i = 0; i < mi; ++i)
+        for (int j = 0; j < mi; ++j) {
+            double s = 0.0;
+            for (int k = i; k <= j; ++k) s += hL1[j * 16 + k] * hL2[k * 16 + i];
+            hR[i * mi + j] = s;
+        }
+    TTB_CHECK_CUDA(cudaMemcpyAsync(Rm, hR, size_t(mi) * mi * sizeof(double), cudaMemcpyHostToDevice, stream));
+    TTB_CHECK_CUDA(cudaMemcpyAsync(L2inv_dev, hL2i, 256 * sizeof(double), cudaMemcpyHostToDevice, stream));
+    TTB_CHECK_CUDA(cudaStreamSynchronize(stream));  // the pinned scratch is reused by the next call
+    *handled = true;
+    return kOk;
 }
 }  // namespace
 
@@ -135,7 +251,7 @@ void trunc_svd_reset_heuristics() { g_cert_skip = g_cert_backoff = 0; }
 int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizing, int max_rank,
               double jacobi_abs_tol, bool inplace, double* U_out, double* SVt_out, double* sigma_out,
               TruncSvdInfo* res, void* ws, size_t ws_bytes, cudaStream_t stream, double deflate_tol,
-              double jacobi_stop_rel) {
+              double jacobi_stop_rel, const double* M_src) {
     TTB_REQUIRE(M && U_out && SVt_out && res, "trunc_svd: null pointer");
     TTB_REQUIRE(m >= 1 && c >= 1, "trunc_svd: empty matrix");
     TTB_REQUIRE(std::min(m, c) <= 8192, "trunc_svd: min(m, n) > 8192 unsupported");
@@ -164,23 +280,30 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
     unsigned long long* conv = W.take<unsigned long long>(64);
     const size_t jlog_bytes = jacobi_log_bytes(int(std::min(m, c)), kJacobiMaxSweeps);
     char* jlog = jlog_bytes ? W.take<char>(jlog_bytes) : nullptr;
+    double* L2inv_dev = (path == kPathWideLQ && m <= 16) ? W.take<double>(256) : nullptr;  // skinny LQ (below)
     TTB_REQUIRE(big && Rm && J && Jsel && Lm && perm && sigma && nrm2 && info && conv, "trunc_svd: carve failed");
     const size_t rest = ws_bytes - W.off;
     void* sub = W.base + W.off;
 
     PhaseTimer pt(stream);
     double* X;  // rows to rotate (p x q)
+    bool skinny = false;            // the skinny LQ path was taken: big holds Y with Q = L2^{-1} Y
     if (path == kPathTall) {
         // M^T (c x m): rows orthonormalised in place, R (p x c) holds M^T = R^T Q  =>  M = Q_col R
-        { ProfScope ps_("svd.transpose", stream); TTB_PROPAGATE(transpose(M, m, c, c, big, m, stream)); }
+        { ProfScope ps_("svd.transpose", stream); TTB_PROPAGATE(transpose(M_src ? M_src : M, m, c, c, big, m, stream)); }
         int64_t rk = p;
         TTB_PROPAGATE(orth_rows(big, c, m, m, Rm, c, sub, rest, stream, deflate_tol, &rk));
         p = int(rk);
         X = Rm;
     } else {
-        if (big != M)
-            TTB_CHECK_CUDA(cudaMemcpyAsync(big, M, size_t(m) * c * 8, cudaMemcpyDeviceToDevice, stream));
-        if (path == kPathWideLQ) {
+        const double* src = M_src ? M_src : M;  // where the matrix is
+        if (path == kPathWideLQ && L2inv_dev != nullptr && skinny_lq_applicable(m, c, src, big))
+            TTB_PROPAGATE(skinny_lq(src, big, m, c, Rm, L2inv_dev, sub, rest, stream, &skinny));
+        if (!skinny && big != src)
+            TTB_CHECK_CUDA(cudaMemcpyAsync(big, src, size_t(m) * c * 8, cudaMemcpyDeviceToDevice, stream));
+        if (skinny) {
+            X = Rm;  // p = m rows; big holds Y = L2 Q
+        } else if (path == kPathWideLQ) {
             // rows of M orthonormalised in place: M = R^T Q with Q (p x c) orthonormal rows, R (p x m).
             // The rows of R are rotated: R = J^T Xrot with Xrot = diag(s) W^T  =>  M = W diag(s) (J Q).
             int64_t rk = p;
@@ -311,9 +434,20 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
         // U (m x rho) = normalised selected rows of Xrot, transposed;  carry (rho x c) = (diag(s) J[sel]) . Q
         TTB_PROPAGATE(gather_rows(X, q, perm, rho, q, U_out, rho, true, stream, sigma, 2));
         TTB_PROPAGATE(gather_rows(J, p, perm, rho, p, Jsel, p, false, stream, sigma, 1));
+        const double* coef = Jsel;
+        if (skinny) {  // Q = L2^{-1} Y is never formed: fold L2^{-1} into the coefficients
+            GemmArgs g2;
+            g2.M = rho; g2.N = p; g2.K = p;
+            g2.A = Jsel; g2.sAm = p; g2.sAk = 1;
+            g2.B = L2inv_dev; g2.sBk = 16; g2.sBn = 1;
+            g2.C = Lm; g2.ldc = p;
+            g2.force_splits = 1;
+            TTB_PROPAGATE(gemm(g2, nullptr, 0, stream));
+            coef = Lm;
+        }
         GemmArgs g;
         g.M = rho; g.N = c; g.K = p;
-        g.A = Jsel; g.sAm = p; g.sAk = 1;
+        g.A = coef; g.sAm = p; g.sAk = 1;
         g.B = big; g.sBk = c; g.sBn = 1;
         g.C = SVt_out; g.ldc = c;
         { ProfScope ps_("svd.gemm_carry_wide", stream); TTB_PROPAGATE(gemm(g, sub, rest, stream)); }

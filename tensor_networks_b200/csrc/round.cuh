@@ -58,7 +58,9 @@ void trunc_svd_reset_heuristics();
 int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizing, int max_rank,
               double jacobi_abs_tol, bool inplace, double* U_out, double* SVt_out, double* sigma_out,
               TruncSvdInfo* res, void* ws, size_t ws_bytes, cudaStream_t stream, double deflate_tol = 0.0,
-              double jacobi_stop_rel = 0.0);
+              double jacobi_stop_rel = 0.0, const double* M_src = nullptr);
+// M_src != nullptr: the matrix is read from M_src (left untouched) and M is scratch of the same size (inplace
+// semantics for M) -- the first TT-SVD step reads the caller's tensor directly instead of a copy of it.
 // Stopping level of the Jacobi iteration inside a truncation SWEEP (rounding, TT-SVD): the sweep after which
 // the largest relative off-diagonal was <= 3e-5 leaves ~1e-9, i.e. the discarded energy is within 1e-18
 // (relative) of the optimal one and the ranks cannot change; U = Q J^T is orthonormal regardless.  Saves the

@@ -23,36 +23,6 @@ namespace ttb {
 
 namespace {
 
-constexpr int NRM_NT = 256;
-__global__ void __launch_bounds__(NRM_NT) sumsq_partial_kernel(const double* __restrict__ x, int64_t n,
-                                                               double* __restrict__ partial) {
-    double s = 0.0;
-    for (int64_t i = int64_t(blockIdx.x) * NRM_NT + threadIdx.x; i < n; i += int64_t(gridDim.x) * NRM_NT)
-        s = fma(x[i], x[i], s);
-    __shared__ double red[NRM_NT / 32];
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        double v = (threadIdx.x < NRM_NT / 32) ? red[threadIdx.x] : 0.0;
-        v = warp_sum(v);
-        if (threadIdx.x == 0) partial[blockIdx.x] = v;
-    }
-}
-__global__ void sumsq_final_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
-    __shared__ double red[32];
-    double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        double v = (threadIdx.x < blockDim.x / 32) ? red[threadIdx.x] : 0.0;
-        v = warp_sum(v);
-        if (threadIdx.x == 0) out[0] = v;
-    }
-}
-
 constexpr int kNormBlocks = 1184;  // 8 x 148
 
 }  // namespace
@@ -95,25 +65,17 @@ int ttsvd(const double* dense, int d, const int64_t* shape, double eps, int max_
     Workspace W(ws, ws_bytes);
     double* bufA = W.take<double>(N);
     double* bufB = W.take<double>(N);
-    double* partial = W.take<double>(kNormBlocks + 8);
-    if (!bufA || !bufB || !partial) {
+    if (!bufA || !bufB) {
         set_last_error("ttsvd: workspace too small, need " + std::to_string(ttsvd_workspace_bytes(d, shape)) + " bytes");
         return kWorkspaceTooSmall;
     }
     const size_t rest = ws_bytes - W.off;
     void* sub = W.base + W.off;
 
-    // ||X||_F (deterministic two-stage reduction) -> delta
-    sumsq_partial_kernel<<<kNormBlocks, NRM_NT, 0, stream>>>(dense, int64_t(N), partial);
-    sumsq_final_kernel<<<1, 1024, 0, stream>>>(partial, kNormBlocks, partial + kNormBlocks);
-    TTB_CHECK_CUDA(cudaGetLastError());
-    double fro2 = 0.0;
-    TTB_CHECK_CUDA(cudaMemcpyAsync(&fro2, partial + kNormBlocks, 8, cudaMemcpyDeviceToHost, stream));
-    TTB_CHECK_CUDA(cudaMemcpyAsync(bufA, dense, N * 8, cudaMemcpyDeviceToDevice, stream));
-    TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
-    const double fro = std::sqrt(fro2);
-    const double delta = eps / std::sqrt(double(d - 1)) * fro;
-    if (delta_out) *delta_out = delta;
+    // delta = eps / sqrt(d-1) * ||X||_F: the first step truncates relative to the norm it measures itself
+    // (sum of the squared singular values of the first unfolding), so the tensor is neither copied nor read
+    // for a norm of its own; the first unfolding is read in place (M_src) and bufA only receives scratch.
+    double fro = 0.0, delta = 0.0;
 
     int64_t r = 1;
     int64_t c = int64_t(N);
@@ -133,8 +95,15 @@ int ttsvd(const double* dense, int d, const int64_t* shape, double eps, int max_
         // rows of an unfolding that are dependent at working precision are dropped before the SVD
         // (same safe deflation as the RQ pass of the rounding sweep, see round.cu)
         const double deflate_tol = deflation_tolerance(eps, std::max(m, c));
-        TTB_PROPAGATE(trunc_svd(bufA, m, c, delta, false, max_rank, 1e-14 * fro, /*inplace=*/true, arena + off,
-                                bufB, nullptr, &info, sub, rest, stream, deflate_tol, kSweepJacobiStop));
+        const bool first = (k == 0);
+        TTB_PROPAGATE(trunc_svd(bufA, m, c, first ? eps / std::sqrt(double(d - 1)) : delta, first, max_rank,
+                                first ? 0.0 : 1e-14 * fro, /*inplace=*/true, arena + off, bufB, nullptr, &info, sub, rest,
+                                stream, deflate_tol, kSweepJacobiStop, first ? dense : nullptr));
+        if (first) {
+            delta = info.delta_abs;
+            fro = std::sqrt(info.fro2);
+            if (delta_out) *delta_out = delta;
+        }
         const int64_t rho = info.rank;
         if (getenv("TTB_DEBUG"))
             fprintf(stderr, "[ttsvd] step %d: m=%lld c=%lld rank=%lld sweeps=%d converged=%d fro2=%.6e delta=%.3e\n", k,
