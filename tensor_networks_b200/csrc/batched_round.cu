@@ -39,6 +39,7 @@ struct RoundBatchParams {
     int r[kMaxDR + 1];      // storage (input) bond ranks
     double* core[kMaxDR];   // (batch, r[k], n[k], r[k+1])
     double eps;
+    double deflate_tol;  // deflation_tolerance(eps, row length): the same rule as the single-train sweep (round.cuh)
     int max_rank;
     int64_t* ranks_out;     // (batch, d+1)
     int* status_out;        // (batch): Jacobi sweeps that hit the cap
@@ -608,7 +609,7 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
         __syncthreads();
 
         // =========================== RQ pass ===========================
-        const double deflate_tol = (p.eps > 0.0) ? fmin(1e-13, 1e-3 * p.eps) : 0.0;
+        const double deflate_tol = p.deflate_tol;
         const double deflate_tol2 = deflate_tol * deflate_tol;
         for (int k = d - 1; k >= 1; --k) {
             const int c = p.r[k], nn = p.n[k], ro = p.r[k + 1], rn = rq[k + 1];
@@ -1067,6 +1068,7 @@ int round_batched(const TTBatchDesc& t, double eps, int max_rank, int64_t* ranks
         }
         for (int k = 0; k <= t.d; ++k) p.r[k] = int(t.r[k]);
         p.eps = eps;
+        p.deflate_tol = deflation_tolerance(eps, 256);  // rows of at most 256 entries
         p.max_rank = max_rank;
         p.ranks_out = ranks_out_dev;
         p.status_out = status_out_dev;

@@ -102,6 +102,7 @@ int host_words(HostWords* hw) {
 namespace {
 constexpr size_t kGemmWsCap = size_t(64) << 20;  // recommended split-K scratch, never required
 constexpr int kJacobiMaxSweeps = 40;
+constexpr int64_t kJacobiMaxWidth = 3328;
 
 enum SvdPath { kPathTall, kPathWideLQ, kPathWideDirect };
 SvdPath svd_path(int64_t m, int64_t c) {
@@ -254,7 +255,18 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
               double jacobi_stop_rel, const double* M_src) {
     TTB_REQUIRE(M && U_out && SVt_out && res, "trunc_svd: null pointer");
     TTB_REQUIRE(m >= 1 && c >= 1, "trunc_svd: empty matrix");
-    TTB_REQUIRE(std::min(m, c) <= 8192, "trunc_svd: min(m, n) > 8192 unsupported");
+    {
+        // The small factor handed to the Jacobi kernels is p x q with rows [X | J] of p + q columns, eight of which must
+        // fit the shared memory of one SM (svd.cu, pick_block): p + q <= kJacobiMaxWidth.  Tall and very wide inputs
+        // reach it as p x p (p = min(m, n) <= 1664), moderately wide ones (n < 2 m) as m x n.
+        const int64_t pmin = std::min(m, c);
+        const int64_t width = (svd_path(m, c) == kPathWideDirect) ? m + round_up<int64_t>(c, 8) : 2 * round_up<int64_t>(pmin, 8);
+        if (width > kJacobiMaxWidth) {
+            set_last_error("trunc_svd: factor of " + std::to_string(pmin) + " singular values is wider than the on-chip Jacobi "
+                           "SVD supports (rank <= 1664 for tall / very wide matrices, m + n <= 3328 otherwise)");
+            return kUnsupported;
+        }
+    }
     const size_t need = trunc_svd_required(m, c, inplace);
     if (ws == nullptr || ws_bytes < need) {
         set_last_error("trunc_svd: workspace too small, need " + std::to_string(need) + " bytes");
@@ -353,7 +365,7 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
         g_cert_backoff = std::min(64, std::max(1, 2 * g_cert_backoff));
         g_cert_skip = g_cert_backoff;
     }
-    int sweeps = 0;
+    int sweeps = kJacobiDeferStatus;  // ask jacobi_rows not to synchronise for its status (decoded after the rank read-back)
     // An earlier version left pairs of rows that are BOTH below 1e-3 delta unrotated (they are truncated
     // whatever happens to them).  Rows that straddle that floor are then rotated against a set of
     // noise rows that is not orthogonal in itself, and the iteration degrades to linear convergence
@@ -408,6 +420,7 @@ int trunc_svd(double* M, int64_t m, int64_t c, double delta, bool with_normalizi
                              stream));
     TTB_CHECK_CUDA(cudaMemcpyAsync(hw.info, info, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
     TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
+    if (sweeps == kJacobiDeferStatus) jst = jacobi_decode_status(hw.conv, kJacobiMaxSweeps, &sweeps);
     const int rho = int(hw.info[0]);
     res->rank = rho;
     res->delta_abs = hw.info[1];

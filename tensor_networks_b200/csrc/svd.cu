@@ -1032,11 +1032,13 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
     TTB_REQUIRE(X && J && conv_dev && conv_host_pinned, "jacobi_rows: null pointer");
     if (!(stop_rel > 0.0)) stop_rel = 3e-8;
     TTB_REQUIRE(p >= 1 && q >= 1 && ldx >= q, "jacobi_rows: bad extents");
-    if (sweeps_out) *sweeps_out = 0;
+    const bool defer = sweeps_out && *sweeps_out == kJacobiDeferStatus;
+    if (sweeps_out && !defer) *sweeps_out = 0;
     if (p == 1) {
         set_identity_kernel<<<1, 32, 0, stream>>>(J, p);
         ++g_launch_count;
         TTB_CHECK_CUDA(cudaGetLastError());
+        if (sweeps_out) *sweeps_out = 0;
         return kOk;
     }
 
@@ -1153,6 +1155,11 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
                 }
                 double* hout = reinterpret_cast<double*>(conv_host_pinned);
                 TTB_CHECK_CUDA(cudaMemcpyAsync(hout, cp.out, (jtiming ? 56 : 2) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+                if (sweeps_out && *sweeps_out == kJacobiDeferStatus && !jtiming) {
+                    // the caller synchronises the stream later anyway (rank read-back) and decodes the two status
+                    // words itself (jacobi_decode_status): no host round trip of its own for the iteration
+                    return kOk;
+                }
                 TTB_CHECK_CUDA(cudaStreamSynchronize(stream));
                 if (jtiming)
                     fprintf(stderr, "[jacobi] p=%d q=%d b=%d sweeps=%d clocks: gram %.0f rounds %.0f apply %.0f syncA %.0f xchg %.0f syncB %.0f\n",
@@ -1176,6 +1183,7 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
             (void)cudaGetLastError();  // cluster shape not schedulable here: fall through to the multi-launch path
         }
     }
+    if (sweeps_out) *sweeps_out = 0;  // multi-launch path: synchronous, no deferred status
     {
         const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(int64_t(p) * p, 256), 1024));
         set_identity_kernel<<<blocks, 256, 0, stream>>>(J, p);
@@ -1242,6 +1250,14 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
         // pushed it to the 1e-18 level and no verification sweep is needed.
         if (mx <= std::max(jp.tol, stop_rel)) return kOk;
     }
+    set_last_error("jacobi_rows: not converged after " + std::to_string(max_sweeps) + " sweeps");
+    return kNotConverged;
+}
+
+int jacobi_decode_status(const unsigned long long* conv_host_pinned, int max_sweeps, int* sweeps_out) {
+    const double* hout = reinterpret_cast<const double*>(conv_host_pinned);
+    if (sweeps_out) *sweeps_out = int(hout[0]);
+    if (hout[1] != 0.0) return kOk;
     set_last_error("jacobi_rows: not converged after " + std::to_string(max_sweeps) + " sweeps");
     return kNotConverged;
 }

@@ -19,6 +19,11 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
 // log_ws / log_bytes (jacobi_log_bytes): scratch for the rotation log of the single-launch kernel -- with it the
 // kernel rotates only the rows of X and J is rebuilt from the logged rotations by a second, fully parallel launch.
 size_t jacobi_log_bytes(int p, int max_sweeps);
+// Deferred status: set *sweeps_out = kJacobiDeferStatus before the call; if it still holds that value afterwards the
+// single-launch kernel was used, its status words are on their way to conv_host_pinned (copy enqueued on `stream`, no
+// synchronisation) and jacobi_decode_status() reads them once the caller has synchronised the stream.
+constexpr int kJacobiDeferStatus = -12345;
+int jacobi_decode_status(const unsigned long long* conv_host_pinned, int max_sweeps, int* sweeps_out);
 // stop_rel: the iteration ends after the first sweep whose largest relative off-diagonal, measured BEFORE its
 // rotation, is <= stop_rel (0 = 3e-8).  Jacobi converges quadratically, so that sweep itself leaves ~stop_rel^2.
 // J stays orthogonal to machine precision whatever the value; only the residual coupling of the rotated rows

@@ -62,6 +62,26 @@ def test_delta_svd_graded_vs_numpy(m, n, decay):
     assert np.max(np.abs(g - np.eye(k))) < 1e-12
 
 
+def test_delta_svd_width_limit():
+    """The Jacobi kernels hold eight rows of [X | J] in shared memory: the documented limit is 1664 singular
+    values for tall / very wide inputs.  The boundary case works (multi-launch path, rows of 3332 columns),
+    one block more is refused with an explanation instead of a failed launch."""
+    from tensor_networks_b200.utils import delta_svd_dev
+
+    rng = np.random.default_rng(3)
+    m, p = 1800, 1664
+    a = rng.standard_normal((m, 40)) @ rng.standard_normal((40, p)) + 1e-7 * rng.standard_normal((m, p))
+    u, s, svt, info = delta_svd_dev(torch.from_numpy(a).cuda(), 1e-4 * np.linalg.norm(a))
+    assert info["rank"] == 40
+    s_np = np.linalg.svd(a, compute_uv=False)[:40]
+    assert np.max(np.abs(s.cpu().numpy() - s_np) / s_np) < 1e-10
+    rec = (u @ svt).cpu().numpy()
+    assert np.linalg.norm(rec - a) <= 2e-4 * np.linalg.norm(a)
+    b = rng.standard_normal((1700, 1672))
+    with pytest.raises(Exception, match="wider than the on-chip Jacobi"):
+        delta_svd_dev(torch.from_numpy(b).cuda(), 0.0)
+
+
 @pytest.mark.parametrize("m,n,rank", [(200, 96, 40), (96, 200, 40), (512, 128, 17), (64, 64, 1)])
 def test_delta_svd_rank_deficient(m, n, rank):
     """Exactly rank-deficient input: the dropped part is roundoff, the kept part is exact."""
