@@ -827,6 +827,7 @@ __global__ void __launch_bounds__(TI_NT, 1) tri_inv_fro_dmma_kernel(const double
 constexpr int AW = 8;        // columns per CTA (one DMMA n tile)
 constexpr int AWP = 12;      // pitch of the slice rows (== 12 mod 16: conflict-free B fragments)
 constexpr int AW_NT = 256;
+constexpr int AW_ST = 4;     // staged phases of the log
 template <int JC_B>
 __global__ void __launch_bounds__(AW_NT) apply_wlog_kernel(const double* __restrict__ wlog, const int* __restrict__ blog,
                                                            const double* __restrict__ status, int p, int nb,
@@ -837,8 +838,8 @@ __global__ void __launch_bounds__(AW_NT) apply_wlog_kernel(const double* __restr
     const int h = nb >> 1, nphase = nb - 1;
     const int rows = nb * JC_B;
     double* Js = sm;                              // [rows][AWP]
-    double* Wst = Js + size_t(rows) * AWP;        // 2 x [h][R2][WP]
-    int* Bst = reinterpret_cast<int*>(Wst + 2 * size_t(h) * R2 * WP);  // 2 x [h][2]
+    double* Wst = Js + size_t(rows) * AWP;        // AW_ST x [h][R2][WP]
+    int* Bst = reinterpret_cast<int*>(Wst + size_t(AW_ST) * h * R2 * WP);  // AW_ST x [h][2]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frow = lane >> 2, fk = lane & 3;
     const int c0 = blockIdx.x * AW;
@@ -847,27 +848,28 @@ __global__ void __launch_bounds__(AW_NT) apply_wlog_kernel(const double* __restr
         const int r = idx / AWP, c = idx % AWP;
         Js[idx] = (c < AW && r == c0 + c) ? 1.0 : 0.0;
     }
-    auto stage = [&](int ph, int buf) {
-        const double* src = wlog + size_t(ph) * h * R2 * R2;
-        double* dst = Wst + size_t(buf) * h * R2 * WP;
-        constexpr int CPR = R2 / 2;  // 16-byte chunks per rotation row
-        for (int idx = tid; idx < h * R2 * CPR; idx += AW_NT) {
-            const int row = idx / CPR, ch = idx % CPR;
-            cp_async16(dst + size_t(row) * WP + 2 * ch, src + size_t(row) * R2 + 2 * ch, true);
+    // one cp.async group per phase (empty groups past the end keep the wait count uniform), AW_ST - 1 phases ahead:
+    // a phase is far shorter than an L2 round trip
+    auto stage = [&](int ph) {
+        if (ph < total_phases) {
+            const int buf = ph % AW_ST;
+            const double* src = wlog + size_t(ph) * h * R2 * R2;
+            double* dst = Wst + size_t(buf) * h * R2 * WP;
+            constexpr int CPR = R2 / 2;  // 16-byte chunks per rotation row
+            for (int idx = tid; idx < h * R2 * CPR; idx += AW_NT) {
+                const int row = idx / CPR, ch = idx % CPR;
+                cp_async16(dst + size_t(row) * WP + 2 * ch, src + size_t(row) * R2 + 2 * ch, true);
+            }
+            if (tid < h) cp_async8(Bst + buf * 2 * h + 2 * tid, blog + size_t(ph) * 2 * h + 2 * tid, true);
         }
-        if (tid < 2 * h) Bst[buf * 2 * h + tid] = blog[size_t(ph) * 2 * h + tid];
         cp_async_commit();
     };
-    if (total_phases > 0) stage(0, 0);
+    for (int ph = 0; ph < AW_ST - 1; ++ph) stage(ph);
     for (int ph = 0; ph < total_phases; ++ph) {
-        const int buf = ph & 1;
-        if (ph + 1 < total_phases) {
-            stage(ph + 1, buf ^ 1);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();  // the staged rotations of this phase are visible; every warp is done with the previous phase
+        const int buf = ph % AW_ST;
+        cp_async_wait<AW_ST - 2>();
+        __syncthreads();  // the rotations of this phase are visible; every warp is done with the previous phase
+        stage(ph + AW_ST - 1);  // into the buffer of phase ph - 1
         const double* Wp = Wst + size_t(buf) * h * R2 * WP;
         const int* Bp = Bst + buf * 2 * h;
         for (int e = warp; e < h; e += AW_NT / 32) {
@@ -892,8 +894,9 @@ __global__ void __launch_bounds__(AW_NT) apply_wlog_kernel(const double* __restr
                 *reinterpret_cast<double2*>(Js + dst_row * AWP + 2 * fk) = make_double2(acc[i][0], acc[i][1]);
             }
         }
-        __syncthreads();  // the next stage() overwrites the buffer just used two iterations from now; rows are final
     }
+    cp_async_wait<0>();
+    __syncthreads();
     for (int idx = tid; idx < rows * AW; idx += AW_NT) {
         const int r = idx / AW, c = idx % AW;
         if (r < p && c0 + c < p) J[size_t(r) * p + c0 + c] = Js[r * AWP + c];
@@ -1140,8 +1143,8 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
             if (le == cudaSuccess) {
                 ++g_launch_count;
                 if (log_mode) {
-                    const size_t asmem = (size_t(nbc) * jcb * AWP + 2 * size_t(nbc / 2) * (2 * jcb) * (2 * jcb + 4)) * sizeof(double) +
-                                         2 * size_t(nbc) * sizeof(int) + 64;
+                    const size_t asmem = (size_t(nbc) * jcb * AWP + size_t(AW_ST) * (nbc / 2) * (2 * jcb) * (2 * jcb + 4)) * sizeof(double) +
+                                         size_t(AW_ST) * size_t(nbc) * sizeof(int) + 64;
                     auto akern = (jcb == 8) ? apply_wlog_kernel<8> : apply_wlog_kernel<16>;
                     static size_t aconf[2] = {0, 0};
                     size_t& ac = aconf[jcb == 8 ? 0 : 1];
