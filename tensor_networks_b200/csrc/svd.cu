@@ -190,6 +190,123 @@ __device__ __forceinline__ void jacobi_rounds(double* G, double* W, int R2_arg, 
     __syncthreads();
 }
 
+// Same rounds for the single-launch cluster kernel, with the work split over three thread groups that
+// synchronise through named barriers instead of two block-wide barriers per round:
+//   group R  (NR = (R2/2)^2 threads, at least 64): the first R2/2 lanes compute the rotations of a round, then every
+//            thread of the group updates one 2 x 2 block of G.  This is the critical path; its two barriers per round
+//            involve only the NR threads.
+//   group W  (128 threads): applies the rotations to W one round behind, as soon as the parameters are published
+//            (producer / consumer barrier, parameters of ALL rounds are kept, so nothing is overwritten).
+//   the remaining warps go straight to the closing block barrier.
+// Barrier ids: 1 = group R; 2, 3 = "parameters of round rd published" (by parity); 4, 5 = "W done with round rd".
+// (the non-.aligned forms: the lanes of the first warp may not have reconverged after the parameter computation)
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("barrier.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+constexpr int JS_MAXROUNDS = 16;
+template <int R2>
+__device__ __forceinline__ void jacobi_rounds_split(double* G, double* W, int bsz, int mode, const RotTol rt, double2* pcs_all,
+                                                    int2* pij_all, double* blk_max) {
+    constexpr int np = R2 / 2;
+    constexpr int NR = np * np < 64 ? 64 : np * np;
+    constexpr int NW = 128;
+    static_assert(NR + NW <= JB_NT, "thread groups exceed the block");
+    const int tid = threadIdx.x;
+    const int nrounds = (mode == 0) ? bsz - 1 : bsz;
+    if (tid < NR) {
+        double run_max = 0.0;
+        for (int rd = 0; rd < nrounds; ++rd) {
+            if (tid < np) {
+                int i, j;
+                if (mode == 0) {
+                    const int hp = bsz >> 1, half = tid / hp;
+                    rr_pair(bsz, rd, tid % hp, i, j);
+                    i += half * bsz;
+                    j += half * bsz;
+                } else {
+                    i = tid;
+                    j = tid + rd;
+                    if (j >= bsz) j -= bsz;
+                    j += bsz;
+                }
+                const double a = G[i * JB_GP + i], b = G[j * JB_GP + j], c = G[i * JB_GP + j];
+                double cs = 1.0, sn = 0.0;
+                if (a > 0.0 && b > 0.0 && c != 0.0 && fmax(a, b) > rt.noise2) {
+                    const double sc = pow2_scale(fmax(a, b));
+                    const double as = a * sc, bs = b * sc, cs_ = c * sc;
+                    const double ab = as * bs;
+                    const double c2 = cs_ * cs_;
+                    const bool small_abs = c * c <= rt.abs_tol2 * fmax(a, b);
+                    if (ab > 1e-30) {
+                        if (!small_abs) run_max = fmax(run_max, c2 * rcp_seed64(ab));
+                        if (c2 > rt.tol2 * ab && !small_abs) {
+                            const double tau = bs - as;
+                            const double tc = 2.0 * cs_;
+                            const double h2 = fma(tau, tau, tc * tc);
+                            const double rs = fast_rsqrt3(h2);
+                            const double cs2 = fma(0.5 * fabs(tau), rs, 0.5);
+                            const double rcs = fast_rsqrt3(cs2);
+                            cs = cs2 * rcs;
+                            sn = copysign((0.5 * tc * rs) * rcs, tc * tau);
+                        }
+                    } else {
+                        const double rel2 = c2 / ab;
+                        if (!small_abs) run_max = fmax(run_max, rel2);
+                        if (rel2 > rt.tol2 && !small_abs) {
+                            const double tau = bs - as;
+                            const double tc = 2.0 * cs_;
+                            const double t = tc / (tau + copysign(sqrt(fma(tau, tau, tc * tc)), tau));
+                            cs = rsqrt(fma(t, t, 1.0));
+                            sn = cs * t;
+                        }
+                    }
+                }
+                pcs_all[rd * np + tid] = make_double2(cs, sn);
+                pij_all[rd * np + tid] = make_int2(i, j);
+            }
+            // the W group may still be busy with round rd - 2 on the same barrier id: wait for its "done" first
+            if (rd >= 2) named_sync(4 + (rd & 1), NR + NW);
+            named_arrive(2 + (rd & 1), NR + NW);  // parameters of round rd are published (release)
+            named_sync(1, NR);
+            if (tid < np * np) {
+                const int ra = tid / np, cb = tid % np;
+                const double2 ca = pcs_all[rd * np + ra], cbv = pcs_all[rd * np + cb];
+                const int2 ia = pij_all[rd * np + ra], ib = pij_all[rd * np + cb];
+                double* gi = G + ia.x * JB_GP;
+                double* gj = G + ia.y * JB_GP;
+                const double gii = gi[ib.x], gij = gi[ib.y], gji = gj[ib.x], gjj = gj[ib.y];
+                const double tii = fma(ca.x, gii, -ca.y * gji), tij = fma(ca.x, gij, -ca.y * gjj);
+                const double tji = fma(ca.y, gii, ca.x * gji), tjj = fma(ca.y, gij, ca.x * gjj);
+                gi[ib.x] = fma(cbv.x, tii, -cbv.y * tij);
+                gi[ib.y] = fma(cbv.y, tii, cbv.x * tij);
+                gj[ib.x] = fma(cbv.x, tji, -cbv.y * tjj);
+                gj[ib.y] = fma(cbv.y, tji, cbv.x * tjj);
+            }
+            named_sync(1, NR);
+        }
+        // drain the "W done" barriers of the last two rounds so that every barrier phase is complete
+        for (int rd = (nrounds >= 2 ? nrounds - 2 : 0); rd < nrounds; ++rd) named_sync(4 + (rd & 1), NR + NW);
+        if (tid < 32) {
+            run_max = warp_max(run_max);
+            if (tid == 0 && run_max > *blk_max) *blk_max = run_max;
+        }
+    } else if (tid < NR + NW) {
+        const int wt = tid - NR;
+        for (int rd = 0; rd < nrounds; ++rd) {
+            named_sync(2 + (rd & 1), NR + NW);  // parameters of round rd (acquire)
+            for (int it = wt; it < np * R2; it += NW) {
+                const int ra = it / R2, l = it % R2;
+                const double2 ca = pcs_all[rd * np + ra];
+                const int2 ia = pij_all[rd * np + ra];
+                const double wi = W[ia.x * JB_GP + l], wj = W[ia.y * JB_GP + l];
+                W[ia.x * JB_GP + l] = fma(ca.x, wi, -ca.y * wj);
+                W[ia.y * JB_GP + l] = fma(ca.y, wi, ca.x * wj);
+            }
+            named_arrive(4 + (rd & 1), NR + NW);
+        }
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(JB_NT, 1) jacobi_block_kernel(const JacobiParams p) {
     extern __shared__ __align__(16) double sm[];
     double* T = sm;  // [R2][pitch]
@@ -383,6 +500,7 @@ struct JacobiClusterParams {
     // Halves the rows' width in shared memory, in the DMMA apply and in the DSMEM exchange of every phase.
     double* wlog;
     int* blog;
+    int split_rounds;  // 1: rotation rounds with thread groups and named barriers (jacobi_rounds_split)
 };
 // Rows per block: 16 (32 staged rows per CTA) or 8 (16 staged rows: twice the CTAs and phases, but the
 // 16 x 16 Gram makes every rotation round ~40 % cheaper and the tiles to exchange half as large).
@@ -398,8 +516,8 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
     double* T = T0;         // the buffer that holds this phase's rows
     double* G = T0 + size_t(p.dbuf ? 2 : 1) * size_t(R2) * p.pitch;   // [R2][JB_GP]
     double* W = G + JB_MAXR * JB_GP;
-    __shared__ double2 pcs[JB_MAXR / 2];
-    __shared__ int2 pij[JB_MAXR / 2];
+    __shared__ double2 pcs[JS_MAXROUNDS * (JB_MAXR / 2)];  // rotation parameters of every round of a call
+    __shared__ int2 pij[JS_MAXROUNDS * (JB_MAXR / 2)];
     __shared__ double blk_max;
     __shared__ double conv_in[JC_MAXH];
     __shared__ int arr_top[JC_MAXH], arr_bot[JC_MAXH];
@@ -502,8 +620,13 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
 
             JC_TICK(0)
             // ---- rotations ----
-            if (phase == 0) jacobi_rounds<2 * JC_B>(G, W, R2, JC_B, 0, rt, true, pcs, pij, &blk_max);
-            jacobi_rounds<2 * JC_B>(G, W, R2, JC_B, 1, rt, true, pcs, pij, &blk_max);
+            if (p.split_rounds) {
+                if (phase == 0) jacobi_rounds_split<2 * JC_B>(G, W, JC_B, 0, rt, pcs, pij, &blk_max);
+                jacobi_rounds_split<2 * JC_B>(G, W, JC_B, 1, rt, pcs, pij, &blk_max);
+            } else {
+                if (phase == 0) jacobi_rounds<2 * JC_B>(G, W, R2, JC_B, 0, rt, true, pcs, pij, &blk_max);
+                jacobi_rounds<2 * JC_B>(G, W, R2, JC_B, 1, rt, true, pcs, pij, &blk_max);
+            }
             const double* Wf = W;
             if (tid == 0) sweep_max = fmax(sweep_max, blk_max);
             if (p.wlog != nullptr) {
@@ -1092,20 +1215,25 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
             cudaGetDevice(&dev0);
             cudaDeviceGetAttribute(&maxsm0, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev0);
             const size_t csmem2 = csmem + size_t(2 * jcb) * cp.pitch * sizeof(double);
-            cp.dbuf = (push_enabled && nbc > 2 && csmem2 + 4096 <= size_t(maxsm0)) ? 1 : 0;
+            cp.dbuf = (push_enabled && nbc > 2 && csmem2 + 10240 <= size_t(maxsm0)) ? 1 : 0;
             if (cp.dbuf) csmem = csmem2;
         }
         int dev = 0, maxsm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         if (cluster_enabled && nbc / 2 <= (jcb == 8 && nonportable_ok ? 16 : 8) && cp.ncol <= 32 * JB_NWARP &&
-            csmem + 4096 <= size_t(maxsm)) {
+            csmem + 10240 <= size_t(maxsm)) {
             cp.X = X; cp.ldx = ldx; cp.J = J; cp.p = p; cp.q = q; cp.nb = nbc;
             cp.tol = 1e-15 * std::sqrt(double(std::max(q, 16)));
             cp.abs_tol2 = abs_tol * abs_tol;
             cp.noise2 = noise_floor * noise_floor;
             cp.stop_rel = std::max(cp.tol, stop_rel);  // quadratic convergence: the rotations of that sweep leave ~stop_rel^2
             cp.max_sweeps = max_sweeps;
+            static const bool split_rounds = [] {
+                const char* e = getenv("TTB_JACOBI_SPLIT");
+                return e == nullptr || e[0] != '0';
+            }();
+            cp.split_rounds = split_rounds ? 1 : 0;
             cp.out = reinterpret_cast<double*>(conv_dev);
             static const bool jtiming = getenv("TTB_JACOBI_TIMING") != nullptr;
             cp.timing = jtiming ? 1 : 0;
