@@ -388,13 +388,13 @@ def run_batched(batch=8192, d=20, n=8, r=32, eps=1e-8, steps=5, rank=0, world=1,
     # ---- inner ----
     vals = torch.empty(batch, dtype=torch.float64, device="cuda")
     for _ in range(2):
-        all_gather_items(a.inner(b), batch, out=vals)
+        vals = all_gather_items(a.inner(b), batch, out=vals)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with _Clocks() as ck_in:
         e0.record()
         for _ in range(steps):
-            all_gather_items(a.inner(b), batch, out=vals)
+            vals = all_gather_items(a.inner(b), batch, out=vals)
         e1.record()
         barrier()
     ms_inner = sync_max(e0.elapsed_time(e1) / steps)

@@ -37,6 +37,9 @@ def all_gather_items(local: torch.Tensor, batch: int, group: Optional[dist.Proce
     if not dist.is_initialized():
         if local.shape[0] != batch:
             raise ValueError("single process: local must hold the whole batch")
+        if out is not None and out.data_ptr() != local.data_ptr():
+            out.copy_(local)  # same contract as the collective path: the caller's buffer holds the result
+            return out
         return local
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
