@@ -62,6 +62,34 @@ def test_delta_svd_graded_vs_numpy(m, n, decay):
     assert np.max(np.abs(g - np.eye(k))) < 1e-12
 
 
+@pytest.mark.parametrize("m,c,cond", [(16, 131072, 1e2), (12, 65536 + 16 * 7, 1e4), (16, 262144, 1e9), (5, 98304, 1.0)])
+def test_delta_svd_skinny_lq(m, c, cond):
+    """Very wide matrices with at most 16 rows take the three-pass skinny LQ (Gram, fused L1^-1 apply + second Gram,
+    carry with L2^-1 folded in); cond = 1e9 makes the host Cholesky decline, so the generic panel path is checked
+    on the same shape.  Singular values, reconstruction and orthonormality of U against numpy."""
+    from tensor_networks_b200.utils import delta_svd_dev
+
+    rng = np.random.default_rng(m + c)
+    u, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    s_true = np.logspace(0.0, -np.log10(cond), m) if cond > 1.0 else np.ones(m)
+    a = (u * s_true) @ (rng.standard_normal((m, c)) / np.sqrt(c))
+    U, s, svt, info = delta_svd_dev(torch.from_numpy(a).cuda(), 0.0)
+    U, s, svt = U.cpu().numpy(), s.cpu().numpy(), svt.cpu().numpy()
+    s_np = np.linalg.svd(a, compute_uv=False)
+    assert info["rank"] == m
+    assert np.max(np.abs(s - s_np)) < 1e-12 * s_np[0]
+    assert np.linalg.norm(U @ svt - a) <= 1e-12 * np.linalg.norm(a)
+    assert np.max(np.abs(U.T @ U - np.eye(m))) < 1e-11
+    # truncation through the same path: drop the smaller half of the spectrum
+    if cond > 1.0:
+        delta = 0.5 * (s_np[m // 2 - 1] + s_np[m // 2]) if m >= 4 else 0.0
+        tail = np.sqrt(np.sum(s_np[m // 2:] ** 2))
+        U2, s2, svt2, info2 = delta_svd_dev(torch.from_numpy(a).cuda(), float(tail * (1 + 1e-9)))
+        assert info2["rank"] == m // 2
+        err = np.linalg.norm(U2.cpu().numpy() @ svt2.cpu().numpy() - a)
+        assert abs(err - tail) <= 1e-9 * np.linalg.norm(a)
+
+
 def test_delta_svd_width_limit():
     """The Jacobi kernels hold eight rows of [X | J] in shared memory: the documented limit is 1664 singular
     values for tall / very wide inputs.  The boundary case works (multi-launch path, rows of 3332 columns),
