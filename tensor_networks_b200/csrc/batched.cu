@@ -32,7 +32,7 @@ namespace ttb {
 
 namespace {
 
-constexpr int IB_NT = 512;
+constexpr int IB_NT = 256;  // 8 warps: 2 slices x 4 row tiles; TWO CTAs per SM (the cross-warp sum / barriers of one item overlap the DMMAs of the other)
 constexpr int IB_R = 32;        // max bond rank handled on chip
 constexpr int IB_EP = IB_R + 4; // pitch of E and of the partial buffers
 
@@ -54,7 +54,7 @@ struct InnerBatchParams {
 //   operand of GEMM 2; both pitches make the 64-bit fragment loads bank-conflict free.
 // Chunks are double-buffered with cp.async across cores and items, so HBM latency is hidden
 // behind the DMMA work of the previous chunk.
-constexpr int IB_CS = 4;
+constexpr int IB_CS = 2;
 constexpr int IB_BP = 36, IB_AP = 34;
 constexpr int IB_BST = IB_CS * IB_R * IB_BP;
 constexpr int IB_AST = IB_CS * IB_R * IB_AP;
@@ -148,7 +148,7 @@ __device__ __forceinline__ void chunk_issue(const InnerBatchParams& p, const Chu
     }
 }
 
-__global__ void __launch_bounds__(IB_NT, 1) inner_batched_kernel(const __grid_constant__ InnerBatchParams p) {
+__global__ void __launch_bounds__(IB_NT, 2) inner_batched_kernel(const __grid_constant__ InnerBatchParams p) {
     extern __shared__ __align__(16) double sm[];
     double* stages = sm;                      // [2][IB_STAGE]
     double* red = sm + 2 * IB_STAGE;          // [IB_CS][IB_R][IB_EP]
@@ -368,7 +368,7 @@ int inner_batched(const TTBatchDesc& a, const TTBatchDesc& b, double* out_dev, v
                                                 int(kInnerBatchSmem)));
             configured = true;
         }
-        const int grid = int(std::min<int64_t>(a.batch, int64_t(num_sms())));
+        const int grid = int(std::min<int64_t>(a.batch, int64_t(2) * num_sms()));
         inner_batched_kernel<<<grid, IB_NT, kInnerBatchSmem, stream>>>(p);
         if (btiming) {
             long long h[4];

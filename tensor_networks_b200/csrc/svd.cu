@@ -81,6 +81,53 @@ struct RotTol {
     double abs_tol2;  // skip rotation when g_ij^2 <= abs_tol2 * max(g_ii, g_jj)
     double noise2;    // skip pairs whose rows are both below this squared norm
 };
+// Rotation that annihilates the off-diagonal of the 2 x 2 Gram block [[a, c], [c, b]] (a, b = squared row norms):
+//   row_i' = cs row_i - sn row_j,  row_j' = sn row_i + cs row_j;   (cs, sn) = (1, 0) when the pair is skipped.
+// Straight-line code with ONE rarely taken branch: the guards are predicates evaluated beside the arithmetic and
+// applied by a final select.  The branchy first version (six data-dependent branches, DSETP.MAX scaling) measured
+// 592 clk per round on the single critical warp; this form has a ~240 clk dependent chain (TTB_JACOBI_TIMING).
+//   cos(2 theta) = |tau| / h, sin(2 theta) = 2c / h with tau = b - a, h = hypot(tau, 2c):
+//   cs^2 = (1 + cos 2theta) / 2 in [1/2, 1] (no cancellation), sn = sin(2 theta) / (2 cs).
+//   Two reciprocal square roots, no division; cs^2 + sn^2 = 1 to rounding.
+// The 2 x 2 problem is scaled by a power of two taken from the exponent of a + b, so the squares cannot overflow
+// or underflow.  rel2_out: squared relative off-diagonal c^2 / (a b) (2^-20 accurate, convergence monitor only),
+// 0 for pairs that do not count (degenerate, below the absolute threshold or the noise floor).
+__device__ __forceinline__ double2 rotation_params(double a, double b, double c, const RotTol rt, double* rel2_out) {
+    const double s = a + b;
+    const bool ok = a > 0.0 && b > 0.0 && c != 0.0 && s > rt.noise2;
+    const double sc = pow2_scale(ok ? s : 1.0);
+    const double as = a * sc, bs = b * sc, cs_ = c * sc;
+    const double ab = as * bs, c2 = cs_ * cs_;
+    const bool counted = ok && !(c * c <= rt.abs_tol2 * s);
+    const double tau = bs - as;
+    const double tc = 2.0 * cs_;
+    const double h2 = fma(tau, tau, tc * tc);
+    const double rs = fast_rsqrt3(ok ? h2 : 1.0);
+    const double cs2 = fma(0.5 * fabs(tau), rs, 0.5);
+    const double rcs = fast_rsqrt3(cs2);
+    double cs = cs2 * rcs;
+    double sn = copysign((0.5 * tc * rs) * rcs, tc * tau);
+    const bool rotate = counted && c2 > rt.tol2 * ab;
+    double rel2 = counted ? c2 * rcp_seed64(ab > 1e-30 ? ab : 1.0) : 0.0;
+    if (counted && !(ab > 1e-30)) {
+        // extremely graded pair (b / a < 1e-30): exact library arithmetic
+        rel2 = c2 / ab;
+        if (rel2 > rt.tol2) {
+            const double t = tc / (tau + copysign(sqrt(fma(tau, tau, tc * tc)), tau));
+            cs = rsqrt(fma(t, t, 1.0));
+            sn = cs * t;
+        } else {
+            cs = 1.0;
+            sn = 0.0;
+        }
+    } else if (!rotate) {
+        cs = 1.0;
+        sn = 0.0;
+    }
+    *rel2_out = rel2;
+    return make_double2(cs, sn);
+}
+
 // One pass of disjoint-pair rounds on the R2 x R2 Gram matrix G (R2 = 2 bsz = 8, 16 or 32) of the
 // staged rows, accumulating the rotations in W (both updated IN PLACE).
 // mode 0: pairs INSIDE each of the two blocks (two independent tournaments of bsz players, bsz - 1
@@ -113,44 +160,10 @@ __device__ __forceinline__ void jacobi_rounds(double* G, double* W, int R2_arg, 
                 if (j >= bsz) j -= bsz;
                 j += bsz;
             }
-            const double a = G[i * JB_GP + i], b = G[j * JB_GP + j], c = G[i * JB_GP + j];
-            double cs = 1.0, sn = 0.0;
-            if (a > 0.0 && b > 0.0 && c != 0.0 && fmax(a, b) > rt.noise2) {
-                // scale the 2 x 2 problem by a power of two so that max(a, b) is in [1, 2)
-                const double sc = pow2_scale(fmax(a, b));
-                const double as = a * sc, bs = b * sc, cs_ = c * sc;
-                const double ab = as * bs;
-                const double c2 = cs_ * cs_;
-                const bool small_abs = c * c <= rt.abs_tol2 * fmax(a, b);
-                if (ab > 1e-30) {
-                    // convergence monitor only: a 2^-20 reciprocal is plenty, and it stays off the critical path
-                    if (track && !small_abs) run_max = fmax(run_max, c2 * rcp_seed64(ab));
-                    if (c2 > rt.tol2 * ab && !small_abs) {
-                        // cos(2 theta) = |tau| / h, sin(2 theta) = 2c / h with tau = b - a, h = hypot(tau, 2c):
-                        // cs^2 = (1 + cos 2theta) / 2 in [1/2, 1] (no cancellation), sn = sin(2 theta) / (2 cs).
-                        // Two reciprocal square roots, no division; cs^2 + sn^2 = 1 to rounding.
-                        const double tau = bs - as;
-                        const double tc = 2.0 * cs_;
-                        const double h2 = fma(tau, tau, tc * tc);
-                        const double rs = fast_rsqrt3(h2);
-                        const double cs2 = fma(0.5 * fabs(tau), rs, 0.5);
-                        const double rcs = fast_rsqrt3(cs2);
-                        cs = cs2 * rcs;
-                        sn = copysign((0.5 * tc * rs) * rcs, tc * tau);
-                    }
-                } else {
-                    // extremely graded pair (b / a < 1e-30): exact library arithmetic
-                    const double rel2 = c2 / ab;
-                    if (track && !small_abs) run_max = fmax(run_max, rel2);
-                    if (rel2 > rt.tol2 && !small_abs) {
-                        const double tau = bs - as;
-                        const double tc = 2.0 * cs_;
-                        const double t = tc / (tau + copysign(sqrt(fma(tau, tau, tc * tc)), tau));
-                        cs = rsqrt(fma(t, t, 1.0));
-                        sn = cs * t;
-                    }
-                }
-            }
+            double rel2;
+            const double2 rot = rotation_params(G[i * JB_GP + i], G[j * JB_GP + j], G[i * JB_GP + j], rt, &rel2);
+            if (track) run_max = fmax(run_max, rel2);
+            const double cs = rot.x, sn = rot.y;
             // row_i' = cs row_i - sn row_j,  row_j' = sn row_i + cs row_j
             pcs[tid] = make_double2(cs, sn);
             pij[tid] = make_int2(i, j);
@@ -203,9 +216,25 @@ __device__ __forceinline__ void jacobi_rounds(double* G, double* W, int R2_arg, 
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("barrier.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 constexpr int JS_MAXROUNDS = 16;
+// pair t of round rd: mode 0 = inside the two blocks (two round-robin tournaments of bsz players), mode 1 = cross pairs
+__device__ __forceinline__ int2 round_pair(int mode, int bsz, int rd, int t) {
+    int i, j;
+    if (mode == 0) {
+        const int hp = bsz >> 1, half = t / hp;
+        rr_pair(bsz, rd, t % hp, i, j);
+        i += half * bsz;
+        j += half * bsz;
+    } else {
+        i = t;
+        j = t + rd;
+        if (j >= bsz) j -= bsz;
+        j += bsz;
+    }
+    return make_int2(i, j);
+}
 template <int R2>
 __device__ __forceinline__ void jacobi_rounds_split(double* G, double* W, int bsz, int mode, const RotTol rt, double2* pcs_all,
-                                                    int2* pij_all, double* blk_max) {
+                                                    int2* pij_all, double* blk_max, long long* dbg = nullptr) {
     constexpr int np = R2 / 2;
     constexpr int NR = np * np < 64 ? 64 : np * np;
     constexpr int NW = 128;
@@ -214,66 +243,37 @@ __device__ __forceinline__ void jacobi_rounds_split(double* G, double* W, int bs
     const int nrounds = (mode == 0) ? bsz - 1 : bsz;
     if (tid < NR) {
         double run_max = 0.0;
+        long long d0 = 0, d1 = 0, d2 = 0, d3 = 0, tl = dbg ? clock64() : 0;
+        const int ra = tid / np, cb = tid % np;  // the 2 x 2 block of G this thread updates: pairs ra (rows) x cb (columns)
+        const bool upd = tid < np * np;
         for (int rd = 0; rd < nrounds; ++rd) {
-            if (tid < np) {
-                int i, j;
-                if (mode == 0) {
-                    const int hp = bsz >> 1, half = tid / hp;
-                    rr_pair(bsz, rd, tid % hp, i, j);
-                    i += half * bsz;
-                    j += half * bsz;
-                } else {
-                    i = tid;
-                    j = tid + rd;
-                    if (j >= bsz) j -= bsz;
-                    j += bsz;
-                }
-                const double a = G[i * JB_GP + i], b = G[j * JB_GP + j], c = G[i * JB_GP + j];
-                double cs = 1.0, sn = 0.0;
-                if (a > 0.0 && b > 0.0 && c != 0.0 && fmax(a, b) > rt.noise2) {
-                    const double sc = pow2_scale(fmax(a, b));
-                    const double as = a * sc, bs = b * sc, cs_ = c * sc;
-                    const double ab = as * bs;
-                    const double c2 = cs_ * cs_;
-                    const bool small_abs = c * c <= rt.abs_tol2 * fmax(a, b);
-                    if (ab > 1e-30) {
-                        if (!small_abs) run_max = fmax(run_max, c2 * rcp_seed64(ab));
-                        if (c2 > rt.tol2 * ab && !small_abs) {
-                            const double tau = bs - as;
-                            const double tc = 2.0 * cs_;
-                            const double h2 = fma(tau, tau, tc * tc);
-                            const double rs = fast_rsqrt3(h2);
-                            const double cs2 = fma(0.5 * fabs(tau), rs, 0.5);
-                            const double rcs = fast_rsqrt3(cs2);
-                            cs = cs2 * rcs;
-                            sn = copysign((0.5 * tc * rs) * rcs, tc * tau);
-                        }
-                    } else {
-                        const double rel2 = c2 / ab;
-                        if (!small_abs) run_max = fmax(run_max, rel2);
-                        if (rel2 > rt.tol2 && !small_abs) {
-                            const double tau = bs - as;
-                            const double tc = 2.0 * cs_;
-                            const double t = tc / (tau + copysign(sqrt(fma(tau, tau, tc * tc)), tau));
-                            cs = rsqrt(fma(t, t, 1.0));
-                            sn = cs * t;
-                        }
-                    }
-                }
-                pcs_all[rd * np + tid] = make_double2(cs, sn);
-                pij_all[rd * np + tid] = make_int2(i, j);
+            // nothing below depends on the rotations of this round: pair indices, addresses and the OLD values of
+            // this thread's block are fetched while the first lanes compute the parameters
+            const int2 ia = round_pair(mode, bsz, rd, ra), ib = round_pair(mode, bsz, rd, cb);
+            double* gi = G + ia.x * JB_GP;
+            double* gj = G + ia.y * JB_GP;
+            double gii = 0.0, gij = 0.0, gji = 0.0, gjj = 0.0;
+            if (upd) {
+                gii = gi[ib.x];
+                gij = gi[ib.y];
+                gji = gj[ib.x];
+                gjj = gj[ib.y];
             }
+            if (tid < np) {
+                const int2 pr = round_pair(mode, bsz, rd, tid);
+                pij_all[rd * np + tid] = pr;
+                double rel2;
+                pcs_all[rd * np + tid] = rotation_params(G[pr.x * JB_GP + pr.x], G[pr.y * JB_GP + pr.y], G[pr.x * JB_GP + pr.y], rt, &rel2);
+                run_max = fmax(run_max, rel2);
+            }
+            if (dbg && tid == 0) { const long long n_ = clock64(); d0 += n_ - tl; tl = n_; }
             // the W group may still be busy with round rd - 2 on the same barrier id: wait for its "done" first
             if (rd >= 2) named_sync(4 + (rd & 1), NR + NW);
             named_arrive(2 + (rd & 1), NR + NW);  // parameters of round rd are published (release)
             named_sync(1, NR);
-            if (tid < np * np) {
-                const int ra = tid / np, cb = tid % np;
+            if (dbg && tid == 0) { const long long n_ = clock64(); d1 += n_ - tl; tl = n_; }
+            if (upd) {
                 const double2 ca = pcs_all[rd * np + ra], cbv = pcs_all[rd * np + cb];
-                const int2 ia = pij_all[rd * np + ra], ib = pij_all[rd * np + cb];
-                double* gi = G + ia.x * JB_GP;
-                double* gj = G + ia.y * JB_GP;
-                const double gii = gi[ib.x], gij = gi[ib.y], gji = gj[ib.x], gjj = gj[ib.y];
                 const double tii = fma(ca.x, gii, -ca.y * gji), tij = fma(ca.x, gij, -ca.y * gjj);
                 const double tji = fma(ca.y, gii, ca.x * gji), tjj = fma(ca.y, gij, ca.x * gjj);
                 gi[ib.x] = fma(cbv.x, tii, -cbv.y * tij);
@@ -281,7 +281,12 @@ __device__ __forceinline__ void jacobi_rounds_split(double* G, double* W, int bs
                 gj[ib.x] = fma(cbv.x, tji, -cbv.y * tjj);
                 gj[ib.y] = fma(cbv.y, tji, cbv.x * tjj);
             }
+            if (dbg && tid == 0) { const long long n_ = clock64(); d2 += n_ - tl; tl = n_; }
             named_sync(1, NR);
+            if (dbg && tid == 0) { const long long n_ = clock64(); d3 += n_ - tl; tl = n_; }
+        }
+        if (dbg && tid == 0) {
+            dbg[0] += d0; dbg[1] += d1; dbg[2] += d2; dbg[3] += d3; dbg[4] += nrounds;
         }
         // drain the "W done" barriers of the last two rounds so that every barrier phase is complete
         for (int rd = (nrounds >= 2 ? nrounds - 2 : 0); rd < nrounds; ++rd) named_sync(4 + (rd & 1), NR + NW);
@@ -519,6 +524,7 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
     __shared__ double2 pcs[JS_MAXROUNDS * (JB_MAXR / 2)];  // rotation parameters of every round of a call
     __shared__ int2 pij[JS_MAXROUNDS * (JB_MAXR / 2)];
     __shared__ double blk_max;
+    __shared__ long long rounds_dbg[8];
     __shared__ double conv_in[JC_MAXH];
     __shared__ int arr_top[JC_MAXH], arr_bot[JC_MAXH];
 
@@ -538,6 +544,7 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
         arr_top[tid] = 2 * tid;
         arr_bot[tid] = 2 * tid + 1;
     }
+    if (tid < 8) rounds_dbg[tid] = 0;
     // ---- stage: X rows by cp.async, J rows = identity ----
     {
         const bool vec_ok = ((p.ldx & 1) == 0) && ((p.q & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0);
@@ -621,8 +628,9 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
             JC_TICK(0)
             // ---- rotations ----
             if (p.split_rounds) {
-                if (phase == 0) jacobi_rounds_split<2 * JC_B>(G, W, JC_B, 0, rt, pcs, pij, &blk_max);
-                jacobi_rounds_split<2 * JC_B>(G, W, JC_B, 1, rt, pcs, pij, &blk_max);
+                long long* rdbg = (TIMING && p.timing != 0 && rank == 0) ? rounds_dbg : nullptr;
+                if (phase == 0) jacobi_rounds_split<2 * JC_B>(G, W, JC_B, 0, rt, pcs, pij, &blk_max, rdbg);
+                jacobi_rounds_split<2 * JC_B>(G, W, JC_B, 1, rt, pcs, pij, &blk_max, rdbg);
             } else {
                 if (phase == 0) jacobi_rounds<2 * JC_B>(G, W, R2, JC_B, 0, rt, true, pcs, pij, &blk_max);
                 jacobi_rounds<2 * JC_B>(G, W, R2, JC_B, 1, rt, true, pcs, pij, &blk_max);
@@ -795,6 +803,10 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
         if (p.wlog == nullptr)
             for (int k = lane; k < p.p; k += 32) jr[k] = t[p.qx + k];
     }
+    if (TIMING && p.timing != 0 && rank == 0 && tid == 0 && p.split_rounds)
+        printf("[jacobi rounds] per round: params %.0f, publish+sync %.0f, update %.0f, sync %.0f clk (%lld rounds)\n",
+               double(rounds_dbg[0]) / rounds_dbg[4], double(rounds_dbg[1]) / rounds_dbg[4], double(rounds_dbg[2]) / rounds_dbg[4],
+               double(rounds_dbg[3]) / rounds_dbg[4], rounds_dbg[4]);
     if (rank == 0 && tid == 0) {
         p.out[0] = double(sweeps);
         p.out[1] = converged ? 1.0 : 0.0;
