@@ -8,7 +8,7 @@
 //   GEMM 2   G_t (M2 x 56) = C2[:, s, :]^T (M2 x M) . T (M x 56)         C2 = second core, slice s = c / K2
 // CTA t owns the 56-column strip [56 t, 56 t + 56) of T (147 strips for n K2 = 8192 on 148 SMs), keeps it in
 // shared memory and multiplies it at once with the matching slice of the second core (a strip that
-// straddles two slices runs GEMM 2 as two passes over compile-time column-fragment ranges).  The only grid-wide
+// straddles two slices takes the A fragments of its left / right column fragments from two ring stages per k-step).  The only grid-wide
 // dependency per core is the sum of the strip results: barrier -> deterministic reduction (fixed order over
 // the n slices) that writes the next environment in the k-major layout GEMM 1 wants -> barrier.  The
 // 3-phase kernel of inner_fused.cu needs three barriers per core, a T round trip through L2 and drains its
@@ -192,6 +192,45 @@ __device__ __forceinline__ void run_pass(double (&acc)[4][NJ][2], uint32_t& it, 
     }
 }
 
+// GEMM 2 of a strip that straddles the slices s0 | s0 + 1 of the second core at column fragment JS: the copy warp
+// stages the k rows of BOTH slices in two consecutive ring stages per k-step; fragments j < JS take their A operand
+// from the first, the others from the second, so the strip issues exactly the DMMAs of an aligned strip in one
+// pass over k (two sequential passes leave the pass with few fragments bound by the per-stage turn-around:
+// those strips were 3.5 % -- at worst 6.4 % -- behind the aligned ones at the barrier).  JS is a compile-time value.
+template <int JS>
+__device__ __forceinline__ void run_pass_dual(double (&acc)[4][NJ][2], uint32_t& it, int nk, const double* ring,
+                                              uint32_t full_bar, uint32_t empty_bar, int a_off, const double* __restrict__ Tb,
+                                              int lane) {
+    for (int kt = 0; kt < nk; ++kt, it += 2) {
+        const int s0 = it % TM_STAGES, s1 = (it + 1) % TM_STAGES;
+        mbar_wait(full_bar + 8 * s0, (it / TM_STAGES) & 1);
+        mbar_wait(full_bar + 8 * s1, ((it + 1) / TM_STAGES) & 1);
+        const double* A0 = ring + s0 * STAGE_ELEMS + a_off;
+        const double* A1 = ring + s1 * STAGE_ELEMS + a_off;
+        const double* Bs = Tb + kt * BKT * TP;
+#pragma unroll
+        for (int kk = 0; kk < BKT / 4; ++kk) {
+            double a0[4], a1[4], b[NJ];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a0[i] = A0[kk * 4 * HP + 8 * i];
+                a1[i] = A1[kk * 4 * HP + 8 * i];
+            }
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) b[j] = Bs[kk * 4 * TP + 8 * j];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dmma884(acc[i][j][0], acc[i][j][1], j < JS ? a0[i] : a1[i], b[j]);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(empty_bar + 8 * s0);
+            mbar_arrive(empty_bar + 8 * s1);
+        }
+    }
+}
+
 template <bool TIMING, bool STREAMED>
 __global__ void __launch_bounds__(TM_NT, 1) inner_tma_kernel(const TmaParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -266,8 +305,8 @@ __global__ void __launch_bounds__(TM_NT, 1) inner_tma_kernel(const TmaParams p) 
                         tma_load_2d(stg + 2 * F_HALF, &st->mapC1, c0, kt * BKT, full_bar + 8 * s);
                     }
                     const StripSlices sl = strip_slices(c0, K2, ncols);
-                    for (int ps = 0; ps < sl.passes; ++ps) {  // a straddling strip: slice s0, then slice s0 + 1
-                        for (int kt = 0; kt < nk2; ++kt, ++it) {
+                    for (int kt = 0; kt < nk2; ++kt) {
+                        for (int ps = 0; ps < sl.passes; ++ps, ++it) {  // a straddling strip: slice s0, then s0 + 1, per k-step
                             const int s = it % TM_STAGES;
                             mbar_wait(empty_bar + 8 * s, ((it / TM_STAGES) & 1) ^ 1);
                             double* stg = ring + s * STAGE_ELEMS;
@@ -314,20 +353,20 @@ __global__ void __launch_bounds__(TM_NT, 1) inner_tma_kernel(const TmaParams p) 
                 TM_TICK(0)
                 // ---- GEMM 2: strip result = C2[:, s, :]^T . T ----
                 const StripSlices sl = strip_slices(c0, K2, ncols);
-#define TM_G2(JLO, JHI) run_pass<JLO, JHI, false>(acc, it, nk2, ring, full_bar, empty_bar, a_off, b_off, Tb, lane)
                 if (sl.passes == 1) {
-                    TM_G2(0, NJ);
+                    run_pass<0, NJ, false>(acc, it, nk2, ring, full_bar, empty_bar, a_off, b_off, Tb, lane);
                 } else {
+#define TM_G2D(JS) run_pass_dual<JS>(acc, it, nk2, ring, full_bar, empty_bar, a_off, Tb, lane)
                     switch (sl.jsplit) {
-                        case 1: TM_G2(0, 1); TM_G2(1, NJ); break;
-                        case 2: TM_G2(0, 2); TM_G2(2, NJ); break;
-                        case 3: TM_G2(0, 3); TM_G2(3, NJ); break;
-                        case 4: TM_G2(0, 4); TM_G2(4, NJ); break;
-                        case 5: TM_G2(0, 5); TM_G2(5, NJ); break;
-                        default: TM_G2(0, 6); TM_G2(6, NJ); break;
+                        case 1: TM_G2D(1); break;
+                        case 2: TM_G2D(2); break;
+                        case 3: TM_G2D(3); break;
+                        case 4: TM_G2D(4); break;
+                        case 5: TM_G2D(5); break;
+                        default: TM_G2D(6); break;
                     }
+#undef TM_G2D
                 }
-#undef TM_G2
                 double* Pt = p.P + int64_t(t) * P_TILE;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
