@@ -92,47 +92,45 @@ struct RotTol {
 // The 2 x 2 problem is scaled by a power of two taken from the exponent of a + b, so the squares cannot overflow
 // or underflow.  rel2_out: squared relative off-diagonal c^2 / (a b) (2^-20 accurate, convergence monitor only),
 // 0 for pairs that do not count (degenerate, below the absolute threshold or the noise floor).
-#ifndef TTB_JACOBI_F32_ANGLE
-#define TTB_JACOBI_F32_ANGLE 0  // measured: 694 vs 564 clk per round (the fp64 <-> fp32 conversions cost more than the short fp32 chain saves)
-#endif
+// (a single-precision angle with fp64 normalisation was measured slower: 694 vs 564 clk per round, the conversions
+// cost more than the short fp32 chain saves)
 __device__ __forceinline__ double2 rotation_params(double a, double b, double c, const RotTol rt, double* rel2_out) {
+    // Every dependent fp64 operation costs ~20 clk on the single critical warp, so the chain is kept short:
+    //  * t = tan(theta) = 2c / (tau + sign(tau) hypot(tau, 2c)), tau = b - a, from the ~2^-20 accurate MUFU seeds only
+    //    (one multiply each, no refinement): the ANGLE needs no more -- a 1e-6 relative error leaves 1e-6 of the
+    //    off-diagonal, the iteration stays superlinear and stops at 3e-5 / 3e-8 all the same;
+    //  * cs = 1 / sqrt(1 + t^2) with the third-order refined reciprocal square root and sn = cs t: orthogonality
+    //    (cs^2 + sn^2 = 1 to fp64 rounding) depends on that last step alone, whatever t is;
+    //  * no rescaling on the fast path: squared row norms between 2^-400 and 2^400 cannot overflow or underflow
+    //    the squares below; anything else (and pairs graded beyond 1e-30) takes the scaled library-arithmetic path;
+    //  * the guards are predicates evaluated beside the arithmetic and applied by a final select (one rare branch).
     const double s = a + b;
     const bool ok = a > 0.0 && b > 0.0 && c != 0.0 && s > rt.noise2;
-    const double sc = pow2_scale(ok ? s : 1.0);
-    const double as = a * sc, bs = b * sc, cs_ = c * sc;
-    const double ab = as * bs, c2 = cs_ * cs_;
-    const bool counted = ok && !(c * c <= rt.abs_tol2 * s);
-    const double tau = bs - as;
-    const double tc = 2.0 * cs_;
-#if TTB_JACOBI_F32_ANGLE
-    // The ANGLE needs no more than single precision (a 1e-7 relative error leaves 1e-7 of the off-diagonal, the
-    // iteration stays superlinear and stops at 3e-5 / 3e-8); orthogonality does: t = tan(theta) is computed in fp32
-    // (4-clk operations instead of ~20-clk dependent fp64 ones on the single critical warp), cs = 1 / sqrt(1 + t^2)
-    // and sn = cs t in fp64, so cs^2 + sn^2 = 1 to fp64 rounding whatever t is.
-    const float tf = float(tau), cf = float(tc);
-    const float h2f = fmaf(tf, tf, cf * cf);
-    const float hf = h2f * rsqrtf(fmaxf(h2f, 1e-36f));
-    const float tq = cf * __frcp_rn(fabsf(tf) + hf + 1e-37f);
-    const double t_ = double(copysignf(tq, tq * tf));
-    double cs = fast_rsqrt3(fma(t_, t_, 1.0));
-    double sn = cs * t_;
-#else
+    const int ex = dbl_exponent(s);
+    const bool mid = ex > -400 && ex < 400;
+    const double ab = a * b, c2 = c * c;
+    const bool counted = ok && !(c2 <= rt.abs_tol2 * s);
+    const double tau = b - a;
+    const double tc = 2.0 * c;
     const double h2 = fma(tau, tau, tc * tc);
-    const double rs = fast_rsqrt3(ok ? h2 : 1.0);
-    const double cs2 = fma(0.5 * fabs(tau), rs, 0.5);
-    const double rcs = fast_rsqrt3(cs2);
-    double cs = cs2 * rcs;
-    double sn = copysign((0.5 * tc * rs) * rcs, tc * tau);
-#endif
+    const double h = h2 * rsqrt_seed64(h2);
+    const double t = copysign(tc * rcp_seed64(fabs(tau) + h), tc * tau);
+    double cs = fast_rsqrt3(fma(t, t, 1.0));
+    double sn = cs * t;
+    double rel2 = c2 * rcp_seed64(ab);
+    const bool fast = mid && ab > 1e-30 * s * s;  // not extremely graded: min / max of the two squared norms above ~1e-30
     const bool rotate = counted && c2 > rt.tol2 * ab;
-    double rel2 = counted ? c2 * rcp_seed64(ab > 1e-30 ? ab : 1.0) : 0.0;
-    if (counted && !(ab > 1e-30)) {
-        // extremely graded pair (b / a < 1e-30): exact library arithmetic
-        rel2 = c2 / ab;
+    if (counted && !fast) {
+        // out-of-range magnitudes or an extremely graded pair: power-of-two scaling and exact library arithmetic
+        const double sc = pow2_scale(s);
+        const double as = a * sc, bs = b * sc, cs_ = c * sc;
+        const double abs_ = as * bs, c2s = cs_ * cs_;
+        rel2 = c2s / abs_;
         if (rel2 > rt.tol2) {
-            const double t = tc / (tau + copysign(sqrt(fma(tau, tau, tc * tc)), tau));
-            cs = rsqrt(fma(t, t, 1.0));
-            sn = cs * t;
+            const double taus = bs - as, tcs = 2.0 * cs_;
+            const double tt = tcs / (taus + copysign(sqrt(fma(taus, taus, tcs * tcs)), taus));
+            cs = rsqrt(fma(tt, tt, 1.0));
+            sn = cs * tt;
         } else {
             cs = 1.0;
             sn = 0.0;
@@ -141,7 +139,7 @@ __device__ __forceinline__ double2 rotation_params(double a, double b, double c,
         cs = 1.0;
         sn = 0.0;
     }
-    *rel2_out = rel2;
+    *rel2_out = counted ? rel2 : 0.0;
     return make_double2(cs, sn);
 }
 
