@@ -15,6 +15,7 @@ struct ProfRec {
     cudaEvent_t e0, e1;
 };
 std::vector<ProfRec> g_prof;
+std::vector<size_t> g_prof_open;  // indices of the scopes that are open (scopes may nest)
 std::vector<cudaEvent_t> g_free_events;
 cudaEvent_t take_event() {
     if (!g_free_events.empty()) {
@@ -38,11 +39,14 @@ bool prof_enabled() {
 void prof_begin(const char* name, cudaStream_t stream) {
     ProfRec r{name, take_event(), take_event()};
     cudaEventRecord(r.e0, stream);
+    g_prof_open.push_back(g_prof.size());
     g_prof.push_back(r);
 }
 void prof_end(cudaStream_t stream) {
-    // scopes do not nest: the last record is the open one
-    if (!g_prof.empty()) cudaEventRecord(g_prof.back().e1, stream);
+    if (g_prof_open.empty()) return;
+    const size_t idx = g_prof_open.back();
+    g_prof_open.pop_back();
+    if (idx < g_prof.size()) cudaEventRecord(g_prof[idx].e1, stream);
 }
 void prof_report(const char* title) {
     if (!prof_enabled() || g_prof.empty()) return;
@@ -59,6 +63,7 @@ void prof_report(const char* title) {
         g_free_events.push_back(r.e1);
     }
     g_prof.clear();
+    g_prof_open.clear();
     std::vector<std::pair<std::string, std::pair<double, int>>> v(agg.begin(), agg.end());
     std::sort(v.begin(), v.end(), [](const auto& a, const auto& b) { return a.second.first > b.second.first; });
     fprintf(stderr, "[prof] %s: %.3f ms in scopes\n", title, total);

@@ -1691,7 +1691,10 @@ static int orth_rows_impl(double* M, int64_t c, int64_t m, int64_t ldm, double* 
         g.C = R + jc; g.ldc = ldr;
         TTB_PROPAGATE(gemm(g, gws, gws_bytes, stream));
     }
-    if (jq < c) {  // rows that hold no orthonormal vector are zero (the reference's padding)
+    // rows that hold no orthonormal vector are zero (the reference's padding) -- unless the caller asked for
+    // deflation: it then shrinks to rank_out rows and never reads the dropped ones (for the 256 x 10^6 unfoldings of
+    // the TT-SVD the zero fill alone was 0.4 ms of HBM writes)
+    if (jq < c && !(deflate_tol > 0.0 && rank_out != nullptr)) {
         const int64_t extra = c - jq;
         const int blocks = int(std::min<int64_t>(ceil_div<int64_t>(extra * m, 256), 2048));
         zero_rows_kernel<<<blocks, 256, 0, stream>>>(M + jq * ldm, extra, m, ldm);
