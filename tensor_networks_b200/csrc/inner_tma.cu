@@ -531,7 +531,9 @@ bool plan_tma(const TTDesc& A, const TTDesc& B, TmaPlan* plan) {
     plan->p_elems = std::max<size_t>(plan->p_elems, size_t(num_sms()) + 8);
     if (mode >= 2) return true;
     // rows of the 256-row warp layout that are padding are wasted DMMA issue slots; fewer strips than SMs idle them
-    return min_rank >= 192 && min_tiles >= (3 * num_sms()) / 4;
+    // (tools/tma_dispatch_sweep.py on B200: the strip kernel wins from rank 224 up with >= 128 strips; at rank 200
+    // or with ~110 strips or fewer the three-phase kernel is 2-30 % faster)
+    return min_rank >= 208 && min_tiles >= (3 * num_sms()) / 4;
 }
 
 size_t tma_bytes(const TmaPlan& pl, int d) {
