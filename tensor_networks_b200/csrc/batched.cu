@@ -32,7 +32,11 @@ namespace ttb {
 
 namespace {
 
-constexpr int IB_NT = 256;  // 8 warps: 2 slices x 4 row tiles; TWO CTAs per SM (the cross-warp sum / barriers of one item overlap the DMMAs of the other)
+// Two launch configurations (template parameters IB_CS = slices per chunk, IB_NT = 128 IB_CS threads):
+//   <2, 256>: 8 warps (2 slices x 4 row tiles), TWO CTAs per SM -- the cross-warp sum / barriers of one item overlap
+//             the DMMAs of the other (7.55 ms for the 8192 pairs of configs[4], 7.94 ms with one CTA per SM);
+//   <4, 512>: 16 warps, one CTA per SM: half the latency per item, so fewer items are lost to the last, partial
+//             wave when a GPU holds only a few waves' worth (1024 pairs per GPU at N = 8: 7 waves of 148 against 4 of 296).
 constexpr int IB_R = 32;        // max bond rank handled on chip
 constexpr int IB_EP = IB_R + 4; // pitch of E and of the partial buffers
 
@@ -54,12 +58,16 @@ struct InnerBatchParams {
 //   operand of GEMM 2; both pitches make the 64-bit fragment loads bank-conflict free.
 // Chunks are double-buffered with cp.async across cores and items, so HBM latency is hidden
 // behind the DMMA work of the previous chunk.
-constexpr int IB_CS = 2;
 constexpr int IB_BP = 36, IB_AP = 34;
-constexpr int IB_BST = IB_CS * IB_R * IB_BP;
-constexpr int IB_AST = IB_CS * IB_R * IB_AP;
-constexpr int IB_STAGE = IB_BST + IB_AST;
-constexpr int IB_RED = IB_CS * IB_R * IB_EP;
+template <int IB_CS>
+struct IbCfg {
+    static constexpr int NT = 128 * IB_CS;
+    static constexpr int BST = IB_CS * IB_R * IB_BP;
+    static constexpr int AST = IB_CS * IB_R * IB_AP;
+    static constexpr int STAGE = BST + AST;
+    static constexpr int RED = IB_CS * IB_R * IB_EP;
+    static constexpr size_t SMEM = size_t(2 * STAGE + RED + IB_R * IB_EP) * sizeof(double);
+};
 
 struct ChunkIter {
     int64_t item;
@@ -68,6 +76,7 @@ struct ChunkIter {
 
 __device__ __forceinline__ bool chunk_valid(const InnerBatchParams& p, const ChunkIter& it) { return it.item < p.batch; }
 
+template <int IB_CS>
 __device__ __forceinline__ void chunk_advance(const InnerBatchParams& p, ChunkIter& it, int64_t item_stride) {
     const int nch = (p.n[it.k] + IB_CS - 1) / IB_CS;
     if (++it.c < nch) return;
@@ -77,7 +86,9 @@ __device__ __forceinline__ void chunk_advance(const InnerBatchParams& p, ChunkIt
     it.item += item_stride;
 }
 
+template <int IB_CS>
 __device__ __forceinline__ void chunk_issue(const InnerBatchParams& p, const ChunkIter& it, double* stage) {
+    constexpr int IB_NT = IbCfg<IB_CS>::NT, IB_BST = IbCfg<IB_CS>::BST;
     const int tid = threadIdx.x;
     const int k = it.k;
     const int a = p.ra[k], a2 = p.ra[k + 1], b = p.rb[k], b2 = p.rb[k + 1], n = p.n[k];
@@ -148,7 +159,9 @@ __device__ __forceinline__ void chunk_issue(const InnerBatchParams& p, const Chu
     }
 }
 
-__global__ void __launch_bounds__(IB_NT, 2) inner_batched_kernel(const __grid_constant__ InnerBatchParams p) {
+template <int IB_CS>
+__global__ void __launch_bounds__(IbCfg<IB_CS>::NT, IB_CS == 2 ? 2 : 1) inner_batched_kernel(const __grid_constant__ InnerBatchParams p) {
+    constexpr int IB_NT = IbCfg<IB_CS>::NT, IB_BST = IbCfg<IB_CS>::BST, IB_STAGE = IbCfg<IB_CS>::STAGE, IB_RED = IbCfg<IB_CS>::RED;
     extern __shared__ __align__(16) double sm[];
     double* stages = sm;                      // [2][IB_STAGE]
     double* red = sm + 2 * IB_STAGE;          // [IB_CS][IB_R][IB_EP]
@@ -163,9 +176,9 @@ __global__ void __launch_bounds__(IB_NT, 2) inner_batched_kernel(const __grid_co
     ChunkIter cur{int64_t(blockIdx.x), 0, 0};
     ChunkIter nxt = cur;
     if (!chunk_valid(p, cur)) return;
-    chunk_issue(p, cur, stages);
+    chunk_issue<IB_CS>(p, cur, stages);
     cp_async_commit();
-    chunk_advance(p, nxt, gridDim.x);
+    chunk_advance<IB_CS>(p, nxt, gridDim.x);
 
     double acc[4][2];
     int t = 0;
@@ -208,7 +221,7 @@ __global__ void __launch_bounds__(IB_NT, 2) inner_batched_kernel(const __grid_co
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dmma884(c[j][0], c[j][1], af, bf[j]);
             }
-            if (chunk_valid(p, nxt)) chunk_issue(p, nxt, stages + ((t + 1) & 1) * IB_STAGE);
+            if (chunk_valid(p, nxt)) chunk_issue<IB_CS>(p, nxt, stages + ((t + 1) & 1) * IB_STAGE);
             cp_async_commit();
             issued = true;
             const double* asp = Ast + 2 * fq * IB_AP + fr;            // arow(j)[8 l] = asp[8 j * IB_AP + 8 l]
@@ -248,7 +261,7 @@ __global__ void __launch_bounds__(IB_NT, 2) inner_batched_kernel(const __grid_co
                 // scheduler reach this point one DMMA burst apart, so the address arithmetic of one warp
                 // hides behind the tensor work of the others (issued at the top of the iteration, all 16
                 // warps did it at once and the DMMA pipe sat idle meanwhile).
-                if (chunk_valid(p, nxt)) chunk_issue(p, nxt, stages + ((t + 1) & 1) * IB_STAGE);
+                if (chunk_valid(p, nxt)) chunk_issue<IB_CS>(p, nxt, stages + ((t + 1) & 1) * IB_STAGE);
                 cp_async_commit();
                 issued = true;
                 // ---- E'^T(i, l) += C(i, j) . A_s(j, l): C fragments reused as the A operand ----
@@ -266,7 +279,7 @@ __global__ void __launch_bounds__(IB_NT, 2) inner_batched_kernel(const __grid_co
             }
         }
         if (!issued) {  // warps without work in this chunk still move their share of the next one
-            if (chunk_valid(p, nxt)) chunk_issue(p, nxt, stages + ((t + 1) & 1) * IB_STAGE);
+            if (chunk_valid(p, nxt)) chunk_issue<IB_CS>(p, nxt, stages + ((t + 1) & 1) * IB_STAGE);
             cp_async_commit();
         }
         if (timing) { const long long now = clock64(); tacc1 += now - tprev; tprev = now; }
@@ -299,7 +312,7 @@ __global__ void __launch_bounds__(IB_NT, 2) inner_batched_kernel(const __grid_co
             if (k == p.d - 1 && tid == 0) p.out[cur.item] = E[0];
         }
         cur = nxt;
-        chunk_advance(p, nxt, gridDim.x);
+        chunk_advance<IB_CS>(p, nxt, gridDim.x);
         ++t;
         if (timing) { const long long now = clock64(); tacc2 += now - tprev; tprev = now; ++tchunks; }
     }
@@ -307,7 +320,6 @@ __global__ void __launch_bounds__(IB_NT, 2) inner_batched_kernel(const __grid_co
     if (timing) { p.dbg[0] = tacc0; p.dbg[1] = tacc1; p.dbg[2] = tacc2; p.dbg[3] = tchunks; }
 }
 
-constexpr size_t kInnerBatchSmem = size_t(2 * IB_STAGE + IB_RED + IB_R * IB_EP) * sizeof(double);
 
 }  // namespace
 
@@ -364,12 +376,27 @@ int inner_batched(const TTBatchDesc& a, const TTBatchDesc& b, double* out_dev, v
         p.dbg = btiming ? dbg_dev : nullptr;
         static bool configured = false;
         if (!configured) {
-            TTB_CHECK_CUDA(cudaFuncSetAttribute(inner_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                int(kInnerBatchSmem)));
+            TTB_CHECK_CUDA(cudaFuncSetAttribute(inner_batched_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                int(IbCfg<2>::SMEM)));
+            TTB_CHECK_CUDA(cudaFuncSetAttribute(inner_batched_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                int(IbCfg<4>::SMEM)));
             configured = true;
         }
-        const int grid = int(std::min<int64_t>(a.batch, int64_t(2) * num_sms()));
-        inner_batched_kernel<<<grid, IB_NT, kInnerBatchSmem, stream>>>(p);
+        // waves of resident CTAs: an item takes ~1.9 x as long with two CTAs per SM as alone on the SM
+        const int64_t sms = num_sms();
+        const double cost2 = 1.9 * double(ceil_div<int64_t>(a.batch, 2 * sms)), cost1 = double(ceil_div<int64_t>(a.batch, sms));
+        static const int forced = [] {
+            const char* e = getenv("TTB_BINNER_CTAS");
+            return e ? atoi(e) : 0;
+        }();
+        const bool two = forced ? forced == 2 : cost2 <= cost1;
+        if (two) {
+            const int grid = int(std::min<int64_t>(a.batch, 2 * sms));
+            inner_batched_kernel<2><<<grid, IbCfg<2>::NT, IbCfg<2>::SMEM, stream>>>(p);
+        } else {
+            const int grid = int(std::min<int64_t>(a.batch, sms));
+            inner_batched_kernel<4><<<grid, IbCfg<4>::NT, IbCfg<4>::SMEM, stream>>>(p);
+        }
         if (btiming) {
             long long h[4];
             cudaMemcpy(h, dbg_dev, 32, cudaMemcpyDeviceToHost);
