@@ -357,6 +357,9 @@ int inner_batched(const TTBatchDesc& a, const TTBatchDesc& b, double* out_dev, v
     TTB_REQUIRE(out_dev != nullptr, "inner_batched: null output");
 
     if (small_ranks(a) && small_ranks(b)) {
+        bool taken = false;
+        TTB_PROPAGATE(inner_batched_tma(a, b, out_dev, stream, &taken));
+        if (taken) return kOk;
         InnerBatchParams p{};
         p.d = a.d;
         p.batch = a.batch;

@@ -23,6 +23,9 @@ size_t inner_batched_workspace_bytes(const TTBatchDesc& a, const TTBatchDesc& b)
 int inner_batched(const TTBatchDesc& a, const TTBatchDesc& b, double* out_dev, void* ws, size_t ws_bytes,
                   cudaStream_t stream);
 
+// TMA-staged variant for bond ranks <= 32 (batched_tma.cu); *taken = false when its shape / alignment rules do not hold.
+int inner_batched_tma(const TTBatchDesc& a, const TTBatchDesc& b, double* out_dev, cudaStream_t stream, bool* taken);
+
 // tt_svd_round (pytens/algs.py:1841-1903) on every item, in place on the batch storage:
 // item i's core k is written compactly as (ranks[i][k], n[k], ranks[i][k+1]) at the start
 // of its slab.  ranks_out_dev: DEVICE (batch, d+1) int64; status_out_dev: DEVICE (batch)

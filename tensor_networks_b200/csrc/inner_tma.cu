@@ -28,6 +28,7 @@
 
 #include "gemm.cuh"
 #include "sweep_sync.cuh"
+#include "tma.cuh"
 #include "tt.cuh"
 
 namespace ttb {
@@ -35,6 +36,7 @@ namespace ttb {
 namespace {
 
 using namespace sweep_sync;
+using namespace tma;
 
 constexpr int TM_CONS = 256;            // 8 MMA warps (2 per scheduler)
 constexpr int TM_NT = TM_CONS + 32;     // + one copy warp (one elected lane issues the TMA copies)
@@ -88,54 +90,6 @@ struct TmaParams {
     long long* timing;  // TTB_SWEEP_TIMING: CTA 0 clock64 sums {gemm1, gemm2 + store, barrier A, reduce, barrier B}
 };
 
-// ---- mbarrier / TMA primitives (PTX) ----
-// (barriers are addressed by their 32-bit shared-memory address: no generic -> shared conversion in the hot loop)
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// A wait that can never complete (a lost TMA transaction) traps after ~2 s instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TM_CONS) : "memory"); }
 
 // Slices touched by the strip [c0, c0 + TW) of the (M x n K2) matrix T and the fragment where the second begins.
@@ -449,41 +403,6 @@ __global__ void __launch_bounds__(TM_NT, 1) inner_tma_kernel(const TmaParams p) 
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = [] {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess) {
-            (void)cudaGetLastError();
-            f = nullptr;
-        }
-        return reinterpret_cast<EncodeTiledFn>(f);
-    }();
-    return fn;
-}
-
-bool encode(CUtensorMap* map, const double* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-            const uint32_t* box) {
-    const cuuint32_t ones[3] = {1, 1, 1};
-    cuuint64_t gd[3];
-    cuuint64_t gs[2];
-    cuuint32_t bx[3];
-    for (int i = 0; i < rank; ++i) {
-        gd[i] = dims[i];
-        bx[i] = box[i];
-    }
-    for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-    const CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, cuuint32_t(rank), const_cast<double*>(base), gd,
-                                   gs, bx, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS;
-}
-
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // TTB_INNER_TMA: 0 = never, 1 (default) = when the shapes keep the strips efficient, 2 = whenever structurally possible

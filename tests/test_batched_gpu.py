@@ -25,6 +25,10 @@ def _make(batch, shape, ra, rb, seed):
         (37, [3, 5, 2, 7, 4, 6], [4, 9, 13, 7, 3], [5, 2, 32, 8, 6]),  # ragged ranks, odd n
         (300, [11, 9, 10], [17, 31], [32, 1]),  # more items than resident CTAs, n > 8 warps
         (4, [6], [], []),  # d = 1
+        (37, [3, 5, 2, 7, 4, 6], [4, 10, 14, 8, 2], [6, 2, 32, 8, 6]),  # even ragged ranks: TMA boxes with zero fill
+        (300, [11, 9, 10], [18, 30], [32, 2]),  # TMA path, more items than resident CTAs
+        (7, [5, 4], [6], [12]),  # d = 2: first core + plain last core only
+        (9, [4] * 6, [2] * 5, [2] * 5),  # rank 2 throughout
         (3, [5] * 5, [1] * 4, [1] * 4),  # rank-1
         (2, [6] * 4, [40, 33, 36], [8, 40, 8]),  # ranks > 32: large-rank fallback per item
     ],
@@ -41,6 +45,23 @@ def test_inner_batched_vs_oracle(batch, shape, ra, rb):
     nrm = ta.norm().cpu().numpy()
     ref_n = np.array([orc.norm(x) for x in a])
     assert np.all(np.abs(nrm - ref_n) <= RTOL * ref_n)
+
+
+def test_inner_batched_tma_matches_cp_async_kernel(monkeypatch):
+    """The TMA-staged kernel (batched_tma.cu) and the cp.async kernel (batched.cu) agree to roundoff on the
+    cfg5 item shape and on a ragged even-rank shape; TTB_BINNER_TMA=0 selects the latter."""
+    from tensor_networks_b200.batch import TensorTrainBatch
+
+    for shape, ra, rb in (([8] * 20, [32] * 19, [32] * 19), ([5, 8, 3, 9], [8, 24, 6], [30, 16, 32])):
+        ta = TensorTrainBatch.rand(700, shape, ra, seed=11)
+        tb = TensorTrainBatch.rand(700, shape, rb, seed=12)
+        monkeypatch.setenv("TTB_BINNER_TMA", "1")
+        v_tma = ta.inner(tb)
+        monkeypatch.setenv("TTB_BINNER_TMA", "0")
+        v_cp = ta.inner(tb)
+        monkeypatch.delenv("TTB_BINNER_TMA")
+        scale = ta.norm() * tb.norm()
+        assert torch.all((v_tma - v_cp).abs() <= 1e-13 * scale), ((v_tma - v_cp).abs() / scale).max()
 
 
 def test_inner_batched_matches_single_path_and_is_deterministic():
