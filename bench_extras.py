@@ -355,6 +355,18 @@ def _rand_shard(batch, lo, hi, shape, ranks, seed):
     return TensorTrainBatch(cores)
 
 
+def _traffic(key):
+    """ncu DRAM bytes per launch recorded in profiles/traffic.json (None when absent)."""
+    import json
+    import os
+
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
+            return json.load(f).get(key)
+    except (OSError, ValueError):
+        return None
+
+
 def run_batched(batch=8192, d=20, n=8, r=32, eps=1e-8, steps=5, rank=0, world=1, gather_cores=True):
     """configs[4]: `batch` independent TT pairs (inner, bonds r) and TTs (rounding of X (+) X with
     X bonds r/2), sharded by contiguous blocks across `world` ranks; per-item results are
@@ -444,7 +456,7 @@ def run_batched(batch=8192, d=20, n=8, r=32, eps=1e-8, steps=5, rank=0, world=1,
                                "frac": f_inner / (ms_inner * 1e-3) / 1e12 / (fp * world),
                                "hbm_achieved": by_inner / (ms_inner * 1e-3) / 1e9, "hbm_peak": peak_hbm * world,
                                "hbm_frac": by_inner / (ms_inner * 1e-3) / 1e9 / (peak_hbm * world), "hbm_peak_source": hbm_src,
-                               "traffic": None},
+                               "traffic": _traffic("inner_batched_tma_bytes_per_launch") if (world == 1 and batch == 8192) else None},
                   "clocks": ck_in.summary() if rank == 0 else None},
         "round": {"ms": ms_round, "gflops": f_round / (ms_round * 1e-3) / 1e9,
                   "algorithmic_gbs": by_round / (ms_round * 1e-3) / 1e9, "items_per_s": batch / (ms_round * 1e-3),

@@ -1,4 +1,4 @@
-// TMA-staged batched TT inner products for bond ranks <= 32: one CTA walks a list of pairs, two CTAs per SM.
+// TMA-staged batched TT inner products for bond ranks <= 32: one CTA walks a list of pairs, three CTAs per SM.
 //
 // Same arithmetic as inner_batched_kernel (batched.cu; batches of TensorNetwork.inner calls, pytens/algs.py:585-587):
 // per core k and mode slice s
@@ -11,8 +11,10 @@
 //     kernel meets at 9 barriers per core).  Once per core the warps exchange their rows through a double-buffered
 //     32 x 36 tile (one 128-thread named barrier) and reload the whole environment as 32 B-operand fragments that
 //     stay in REGISTERS for the next core (the cp.async kernel re-reads them from shared memory for every slice).
-//   * a fifth warp (one elected lane) feeds a 5-stage ring of slice boxes with cp.async.bulk.tensor (TMA) guarded by
-//     full / empty mbarriers.  The boxes come from 4-d tensor maps (column, slice, row, item) of the batch storage and
+//   * slice boxes arrive by cp.async.bulk.tensor (TMA) in a 3-slot ring guarded by full mbarriers.  There is no copy
+//     warp (registers are allocated per four warps: a fifth warp would cost a third of the budget and the third CTA
+//     per SM) and no empty barrier: a warp that is done with a slot bumps the slot's release counter (acq_rel), and
+//     the warp that arrives last issues the refill at once.  The boxes come from 4-d tensor maps (column, slice, row, item) of the batch storage and
 //     are 36 (B side) and 34 (A side) doubles wide: the columns past the bond rank are TMA zero fill, and the pitches
 //     == 4 (mod 16) and == 2 (mod 8) make the 64-bit and 128-bit fragment loads bank-conflict free without swizzling.
 //     Rows / columns outside a core (bond ranks below 32, the rank-1 first core) are zero fill as well, so any shape
@@ -38,16 +40,14 @@ constexpr int BT_R = 32;                 // largest bond rank
 constexpr int BT_BP = 36;                // B-side box width / pitch (== 4 mod 16)
 constexpr int BT_AP = 34;                // A-side box width / pitch (== 2 mod 8)
 constexpr int BT_EP = 36;                // pitch of the exchange tile
-constexpr int BT_STAGES = 5;
 constexpr int BT_MMA_WARPS = 4;
-constexpr int BT_CONS = 32 * BT_MMA_WARPS;
-constexpr int BT_NT = BT_CONS + 32;
-constexpr int BT_BBOX = BT_R * BT_BP;    // doubles per B-side box
+constexpr int BT_NT = 32 * BT_MMA_WARPS;  // no copy warp: registers are allocated per four warps, a fifth one costs 1/3
+constexpr int BT_BBOX = BT_R * BT_BP;     // doubles per B-side box
 constexpr int BT_ABOX = BT_R * BT_AP;
 constexpr int BT_STAGE = BT_BBOX + BT_ABOX;
 constexpr uint32_t kStageBytes = BT_STAGE * 8;
 constexpr int BT_EX = BT_R * BT_EP;
-constexpr size_t kBtSmem = size_t(BT_STAGES * BT_STAGE + 2 * BT_EX) * 8 + 16 * BT_STAGES + 64 + 128;
+constexpr size_t bt_smem(int stages) { return size_t(stages * BT_STAGE + 2 * BT_EX) * 8 + 16 * stages + 64 + 128; }
 constexpr int BT_MAXD = 64;
 static_assert((BT_BBOX * 8) % 128 == 0 && (BT_ABOX * 8) % 128 == 0, "TMA destinations stay 128-byte aligned");
 
@@ -64,7 +64,9 @@ struct BtParams {
     double* out;
 };
 
-// One slice of one core: 64 DMMAs per warp when all ranks are 32.
+// One slice of one core: 64 DMMAs per warp when all ranks are 32.  Four accumulator chains per product; eight (even /
+// odd K steps, separate accumulators per k half) were measured and are slower (5.08 vs 4.86 ms): with three warps per
+// scheduler the DMMA latency is hidden already and the extra additions and registers only cost.
 template <bool FULL>
 __device__ __forceinline__ void slice_mma(double (&acc)[2][4], const double (&ef)[8][4], const double* __restrict__ bsp,
                                           const double* __restrict__ asp, int kt, int nt, int lp) {
@@ -111,48 +113,58 @@ __device__ __forceinline__ void slice_mma(double (&acc)[2][4], const double (&ef
     }
 }
 
-__global__ void __launch_bounds__(BT_NT, 2) inner_batched_tma_kernel(const __grid_constant__ BtParams p) {
+// Position of a ring slot's load in the (item, core, slice) order of a CTA.
+struct BtCursor {
+    int64_t item;
+    int k, s;
+};
+__device__ __forceinline__ void bt_advance(const BtParams& p, BtCursor& c, int64_t item_stride) {
+    if (++c.s < p.n[c.k]) return;
+    c.s = 0;
+    if (++c.k < p.d - 1) return;
+    c.k = 0;
+    c.item += item_stride;
+}
+__device__ __forceinline__ void bt_issue(const BtParams& p, const BtCursor& c, double* dst, uint32_t bar) {
+    mbar_expect_tx(bar, kStageBytes);
+    tma_load_4d(dst, &p.mapB[c.k], 0, c.s, 0, int(c.item), bar);
+    tma_load_4d(dst + BT_BBOX, &p.mapA[c.k], 0, c.s, 0, int(c.item), bar);
+}
+
+// STAGES ring slots, MINB CTAs per SM.
+template <int STAGES, int MINB>
+__global__ void __launch_bounds__(BT_NT, MINB) inner_batched_tma_kernel(const __grid_constant__ BtParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    double* ring = reinterpret_cast<double*>(base);                 // [BT_STAGES][BT_STAGE]
-    double* ex = ring + BT_STAGES * BT_STAGE;                       // [2][32][BT_EP]: E'^T (row b', column a')
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ex + 2 * BT_EX);  // full[BT_STAGES], empty[BT_STAGES]
-    double* fin = reinterpret_cast<double*>(bars + 2 * BT_STAGES);  // [4] warp sums of the last core
-    const uint32_t full_bar = smem_u32(bars), empty_bar = smem_u32(bars + BT_STAGES);
+    double* ring = reinterpret_cast<double*>(base);                 // [STAGES][BT_STAGE]
+    double* ex = ring + STAGES * BT_STAGE;                          // [2][32][BT_EP]: E'^T (row b', column a')
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ex + 2 * BT_EX);  // full[STAGES]
+    unsigned* released = reinterpret_cast<unsigned*>(bars + STAGES);  // [STAGES] warps done with the slot, running count
+    double* fin = reinterpret_cast<double*>(released + STAGES + (STAGES & 1));  // [4] warp sums of the last core
+    const uint32_t full_bar = smem_u32(bars), released_u32 = smem_u32(released);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d = p.d;
+    // `ahead` is the load that refills the slot a warp has just finished with (STAGES slices further on).  There is no
+    // copy warp and no empty barrier: every warp bumps the slot's release counter (acq_rel) when it is done reading, and
+    // the warp that arrives LAST -- it knows that all four are done -- issues the refill at once.
+    BtCursor ahead{int64_t(blockIdx.x), 0, 0};
     if (tid == 0) {
-        for (int s = 0; s < BT_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar + 8 * s, 1);
-            mbar_init(empty_bar + 8 * s, BT_MMA_WARPS);
+            released[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+        BtCursor c = ahead;
+        for (int s = 0; s < STAGES && c.item < p.batch; ++s) {
+            bt_issue(p, c, ring + s * BT_STAGE, full_bar + 8 * s);
+            bt_advance(p, c, gridDim.x);
+        }
     }
+    for (int s = 0; s < STAGES && ahead.item < p.batch; ++s) bt_advance(p, ahead, gridDim.x);
     __syncthreads();
 
-    const int d = p.d;
-    if (warp == BT_MMA_WARPS) {
-        // ---- copy warp: one box pair per (item, core, slice), in the order the MMA warps consume them ----
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int64_t item = blockIdx.x; item < p.batch; item += gridDim.x) {
-                for (int k = 0; k < d - 1; ++k) {
-                    const int n = p.n[k];
-                    for (int s = 0; s < n; ++s, ++it) {
-                        const uint32_t st = it % BT_STAGES;
-                        mbar_wait(empty_bar + 8 * st, ((it / BT_STAGES) & 1) ^ 1);
-                        mbar_expect_tx(full_bar + 8 * st, kStageBytes);
-                        double* dst = ring + st * BT_STAGE;
-                        tma_load_4d(dst, &p.mapB[k], 0, s, 0, int(item), full_bar + 8 * st);
-                        tma_load_4d(dst + BT_BBOX, &p.mapA[k], 0, s, 0, int(item), full_bar + 8 * st);
-                    }
-                }
-            }
-        }
-        return;
-    }
-
-    // ---- MMA warps ----
     const int fr = lane >> 2, fq = lane & 3, wi = warp;
     uint32_t it = 0;
     for (int64_t item = blockIdx.x; item < p.batch; item += gridDim.x) {
@@ -174,8 +186,8 @@ __global__ void __launch_bounds__(BT_NT, 2) inner_batched_tma_kernel(const __gri
 #pragma unroll
                 for (int q = 0; q < 4; ++q) acc[m][q] = 0.0;
             for (int s = 0; s < n; ++s, ++it) {
-                const uint32_t st = it % BT_STAGES;
-                mbar_wait(full_bar + 8 * st, (it / BT_STAGES) & 1);
+                const uint32_t st = it % STAGES;
+                mbar_wait(full_bar + 8 * st, (it / STAGES) & 1);
                 const double* bsp = ring + st * BT_STAGE + fq * BT_BP + 8 * wi + fr;
                 const double* asp = ring + st * BT_STAGE + BT_BBOX + 2 * fq * BT_AP + 2 * fr;
                 if (full) {
@@ -184,7 +196,13 @@ __global__ void __launch_bounds__(BT_NT, 2) inner_batched_tma_kernel(const __gri
                     slice_mma<false>(acc, ef, bsp, asp, kt, nt, lp);
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(empty_bar + 8 * st);
+                if (lane == 0) {
+                    unsigned old;
+                    asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(released_u32 + 4 * st) : "memory");
+                    if ((old & (BT_MMA_WARPS - 1)) == BT_MMA_WARPS - 1 && ahead.item < p.batch)
+                        bt_issue(p, ahead, ring + st * BT_STAGE, full_bar + 8 * st);
+                }
+                if (ahead.item < p.batch) bt_advance(p, ahead, gridDim.x);
             }
             // ---- exchange: rows 8 wi .. 8 wi + 7 of E'^T, columns 16 m + 4 fq + {0, 1, 2, 3} ----
             double* exk = ex + (k & 1) * BT_EX;
@@ -197,7 +215,7 @@ __global__ void __launch_bounds__(BT_NT, 2) inner_batched_tma_kernel(const __gri
                     *reinterpret_cast<double2*>(row + 16 * m + 2) = make_double2(acc[m][1], acc[m][3]);
                 }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(BT_CONS) : "memory");
+            __syncthreads();
             if (k < d - 2) {
                 // next E[a][b] = E'^T[b][a]: fragment (kk, j) = exk[(4 kk + fq) * EP + 8 j + fr]
                 const double* ep = exk + fq * BT_EP + fr;
@@ -227,7 +245,7 @@ __global__ void __launch_bounds__(BT_NT, 2) inner_batched_tma_kernel(const __gri
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
             if (lane == 0) fin[warp] = v;
-            asm volatile("bar.sync 1, %0;" ::"n"(BT_CONS) : "memory");
+            __syncthreads();
             if (tid == 0) p.out[item] = (fin[0] + fin[1]) + (fin[2] + fin[3]);
             // fin and both exchange tiles are next written after further barriers of the next item (>= 1 in between)
         }
@@ -274,13 +292,17 @@ int inner_batched_tma(const TTBatchDesc& a, const TTBatchDesc& b, double* out_de
     p.Alast = a.core[d - 1];
     p.Blast = b.core[d - 1];
     p.out = out_dev;
+    // three CTAs of four warps per SM with 3 ring slots each (168 registers): 4.86 ms for the 8192 pairs of configs[4];
+    // two CTAs with 5 slots: 4.89 ms; with a dedicated copy warp (five warps are allocated as eight): 5.11 ms
+    constexpr int kStages = 3, kPerSm = 3;
     static bool configured = false;
     if (!configured) {
-        TTB_CHECK_CUDA(cudaFuncSetAttribute(inner_batched_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBtSmem)));
+        TTB_CHECK_CUDA(cudaFuncSetAttribute(inner_batched_tma_kernel<kStages, kPerSm>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, int(bt_smem(kStages))));
         configured = true;
     }
-    const int grid = int(std::min<int64_t>(a.batch, 2 * int64_t(num_sms())));
-    inner_batched_tma_kernel<<<grid, BT_NT, kBtSmem, stream>>>(p);
+    const int grid = int(std::min<int64_t>(a.batch, kPerSm * int64_t(num_sms())));
+    inner_batched_tma_kernel<kStages, kPerSm><<<grid, BT_NT, bt_smem(kStages), stream>>>(p);
     TTB_CHECK_CUDA(cudaGetLastError());
     ++g_launch_count;
     *taken = true;

@@ -1294,6 +1294,9 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
+            // (a single-CTA one-sided Jacobi for p <= 64 -- half-warp per row pair, no blocks, no cluster -- was measured
+            // SLOWER than this kernel: 0.47 vs 0.38 ms for a 64 x 64 factor; the ~500 clk rotation-parameter chain per
+            // round is the same and the redundant fp64 work of 512 threads saturates the FP64 pipe)
             const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, cp);
             if (le == cudaSuccess) {
                 ++g_launch_count;
