@@ -174,6 +174,17 @@ int ttb_delta_svd_f64(const double* data, int64_t m, int64_t n, double delta, in
                       int32_t max_rank, double* u_out, double* s_out, double* svt_out, double* info_out,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Batched eigendecomposition of the Gram matrices of Gram-SVD rounding: the np.linalg.eigh + |.| + sqrt + decimal
+ * rounding + masked reciprocal of gram_eig_and_svd (pytens/algs.py:1727-1749) for `count` symmetric positive
+ * semidefinite matrices g (count, p, p), p <= 256, in one launch of the on-chip Jacobi kernel (one thread-block
+ * cluster per matrix).  Outputs (DEVICE): a_out = V diag(e12), b_out = V diag(em12) as (count, p, p) row-major with
+ * the eigenvalues in descending order (the reference's ascending order is immaterial to the products they enter),
+ * eig_out (count, p) = |lambda|, status_out (count, 2) doubles or NULL = {Jacobi sweeps, converged}.  No host
+ * synchronisation. */
+size_t ttb_gram_eig_batched_workspace_bytes(int32_t count, int32_t p);
+int ttb_gram_eig_batched_f64(const double* g, int32_t count, int32_t p, double* a_out, double* b_out, double* eig_out,
+                             double* status_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* tt_svd_round (pytens/algs.py:1841-1903) on every item of a batch, in place: item
  * i's core k is rewritten compactly as (ranks[i][k], n[k], ranks[i][k+1]) at the
  * start of its slab.  ranks_out_dev: DEVICE (batch, d+1) int64 -- no host

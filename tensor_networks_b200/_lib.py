@@ -117,6 +117,13 @@ def _declare(lib):
         P(c_double), c_void_p, c_size_t, c_void_p,
     ]
 
+    lib.ttb_gram_eig_batched_workspace_bytes.restype = c_size_t
+    lib.ttb_gram_eig_batched_workspace_bytes.argtypes = [c_int32, c_int32]
+    lib.ttb_gram_eig_batched_f64.restype = c_int
+    lib.ttb_gram_eig_batched_f64.argtypes = [
+        c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p,
+    ]
+
     lib.ttb_ttsvd_workspace_bytes.restype = c_size_t
     lib.ttb_ttsvd_workspace_bytes.argtypes = [c_int32, P(c_int64)]
     lib.ttb_ttsvd_f64.restype = c_int

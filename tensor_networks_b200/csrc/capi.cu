@@ -7,6 +7,7 @@
 #include "round.cuh"
 #include "qr.cuh"
 #include "batched.cuh"
+#include "gram_eig.cuh"
 #include "ttsvd.cuh"
 #include "tensor_ops.cuh"
 #include "staging.cuh"
@@ -211,6 +212,13 @@ int ttb_delta_svd_f64(const double* data, int64_t m, int64_t n, double delta, in
         info_out[3] = info.fro2;
     }
     return rc;
+}
+
+size_t ttb_gram_eig_batched_workspace_bytes(int32_t count, int32_t p) { return ttb::gram_eig_batched_workspace_bytes(count, p); }
+
+int ttb_gram_eig_batched_f64(const double* g, int32_t count, int32_t p, double* a_out, double* b_out, double* eig_out,
+                             double* status_out, void* workspace, size_t workspace_bytes, void* stream) {
+    return ttb::gram_eig_batched(g, count, p, a_out, b_out, eig_out, status_out, workspace, workspace_bytes, as_stream(stream));
 }
 
 size_t ttb_round_batched_workspace_bytes(const ttb_tt_batch* t) {

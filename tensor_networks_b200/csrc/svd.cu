@@ -521,6 +521,11 @@ struct JacobiClusterParams {
     double* wlog;
     int* blog;
     int split_rounds;  // 1: rotation rounds with thread groups and named barriers (jacobi_rounds_split)
+    // Batched launches (jacobi_rows_batched): gridDim.y problems of identical shape, one cluster each; problem b works on
+    // X + b bs_x, J + b bs_j, out + b bs_out, wlog + b bs_wlog, blog + b bs_blog (all zero for a single problem).
+    int64_t bs_x, bs_j, bs_wlog, bs_blog;
+    int bs_out;
+    const double* abs_tol2_dev;  // per-problem squared absolute threshold (replaces abs_tol2 when non-null)
 };
 // Rows per block: 16 (32 staged rows per CTA) or 8 (16 staged rows: twice the CTAs and phases, but the
 // 16 x 16 Gram makes every rotation round ~40 % cheaper and the tiles to exchange half as large).
@@ -544,6 +549,12 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
     __shared__ int arr_top[JC_MAXH], arr_bot[JC_MAXH];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // this cluster's problem (blockIdx.y; a single problem has all batch strides zero)
+    double* const Xb = p.X + int64_t(blockIdx.y) * p.bs_x;
+    double* const Jb = p.J + int64_t(blockIdx.y) * p.bs_j;
+    double* const outb = p.out + int64_t(blockIdx.y) * p.bs_out;
+    double* const wlogb = p.wlog ? p.wlog + int64_t(blockIdx.y) * p.bs_wlog : nullptr;
+    int* const blogb = p.blog ? p.blog + int64_t(blockIdx.y) * p.bs_blog : nullptr;
     const int h = p.nb >> 1;
     const int rank = int(cluster.block_rank());
     // circle-method successor of my two blocks (position top[0] is fixed): where the rows I hold now are needed next
@@ -562,7 +573,7 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
     if (tid < 8) rounds_dbg[tid] = 0;
     // ---- stage: X rows by cp.async, J rows = identity ----
     {
-        const bool vec_ok = ((p.ldx & 1) == 0) && ((p.q & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0);
+        const bool vec_ok = ((p.ldx & 1) == 0) && ((p.q & 1) == 0) && ((reinterpret_cast<uintptr_t>(Xb) & 15) == 0);
         const int cpr = p.ncol >> 1;  // 16-byte chunks per staged row
         for (int idx = tid; idx < R2 * cpr; idx += JB_NT) {
             const int a = idx / cpr, k = (idx % cpr) * 2;
@@ -572,10 +583,10 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
             if (k < p.qx) {
                 if (vec_ok) {
                     const bool ok = live && k < p.q;
-                    cp_async16(dst, ok ? p.X + int64_t(gr) * p.ldx + k : p.X, ok);
+                    cp_async16(dst, ok ? Xb + int64_t(gr) * p.ldx + k : Xb, ok);
                 } else {
-                    dst[0] = (live && k < p.q) ? p.X[int64_t(gr) * p.ldx + k] : 0.0;
-                    dst[1] = (live && k + 1 < p.q) ? p.X[int64_t(gr) * p.ldx + k + 1] : 0.0;
+                    dst[0] = (live && k < p.q) ? Xb[int64_t(gr) * p.ldx + k] : 0.0;
+                    dst[1] = (live && k + 1 < p.q) ? Xb[int64_t(gr) * p.ldx + k + 1] : 0.0;
                 }
             } else {
                 const int kk = k - p.qx;
@@ -589,7 +600,7 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
     __syncthreads();
     cluster.sync();  // every CTA of the cluster is resident before any DSMEM traffic
 
-    const RotTol rt{p.tol * p.tol, p.abs_tol2, p.noise2};
+    const RotTol rt{p.tol * p.tol, p.abs_tol2_dev ? p.abs_tol2_dev[blockIdx.y] : p.abs_tol2, p.noise2};
     const int nphase = p.nb - 1;
     int sweeps = 0;
     bool converged = false;
@@ -652,13 +663,13 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
             }
             const double* Wf = W;
             if (tid == 0) sweep_max = fmax(sweep_max, blk_max);
-            if (p.wlog != nullptr) {
+            if (wlogb != nullptr) {
                 const size_t e = (size_t(sweep) * nphase + phase) * h + rank;
-                double* dst = p.wlog + e * (R2 * R2);
+                double* dst = wlogb + e * (R2 * R2);
                 for (int idx = tid; idx < R2 * R2; idx += JB_NT) dst[idx] = W[(idx / R2) * JB_GP + (idx % R2)];
                 if (tid == 0) {
-                    p.blog[2 * e] = arr_top[rank];
-                    p.blog[2 * e + 1] = arr_bot[rank];
+                    blogb[2 * e] = arr_top[rank];
+                    blogb[2 * e + 1] = arr_bot[rank];
                 }
             }
             JC_TICK(1)
@@ -804,7 +815,7 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
         // mx is the largest squared relative off-diagonal met BEFORE its rotation in this sweep; Jacobi
         // converges quadratically, so below stop_rel the rotations of this very sweep have finished the job
         converged = sqrt(mx) <= p.stop_rel;
-        if (TIMING && timing && sweep < 48) p.out[8 + sweep] = sqrt(mx);
+        if (TIMING && timing && sweep < 48) outb[8 + sweep] = sqrt(mx);
     }
     // ---- write back ----
     for (int a = warp; a < R2; a += JB_NWARP) {
@@ -812,10 +823,10 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
         const int gr = blk * JC_B + (a % JC_B);
         if (gr >= p.p) continue;
         const double* t = T + size_t(a) * p.pitch;
-        double* xr = p.X + int64_t(gr) * p.ldx;
-        double* jr = p.J + int64_t(gr) * p.p;
+        double* xr = Xb + int64_t(gr) * p.ldx;
+        double* jr = Jb + int64_t(gr) * p.p;
         for (int k = lane; k < p.q; k += 32) xr[k] = t[k];
-        if (p.wlog == nullptr)
+        if (wlogb == nullptr)
             for (int k = lane; k < p.p; k += 32) jr[k] = t[p.qx + k];
     }
     if (TIMING && p.timing != 0 && rank == 0 && tid == 0 && p.split_rounds)
@@ -823,10 +834,10 @@ __global__ void __launch_bounds__(JB_NT, 1) jacobi_cluster_kernel(const JacobiCl
                double(rounds_dbg[0]) / rounds_dbg[4], double(rounds_dbg[1]) / rounds_dbg[4], double(rounds_dbg[2]) / rounds_dbg[4],
                double(rounds_dbg[3]) / rounds_dbg[4], rounds_dbg[4]);
     if (rank == 0 && tid == 0) {
-        p.out[0] = double(sweeps);
-        p.out[1] = converged ? 1.0 : 0.0;
+        outb[0] = double(sweeps);
+        outb[1] = converged ? 1.0 : 0.0;
         if (TIMING && timing)
-            for (int k = 0; k < 6; ++k) p.out[2 + k] = double(tacc[k]);
+            for (int k = 0; k < 6; ++k) outb[2 + k] = double(tacc[k]);
     }
 #undef JC_TICK
 }
@@ -981,7 +992,13 @@ constexpr int AW_ST = 4;     // staged phases of the log
 template <int JC_B>
 __global__ void __launch_bounds__(AW_NT) apply_wlog_kernel(const double* __restrict__ wlog, const int* __restrict__ blog,
                                                            const double* __restrict__ status, int p, int nb,
-                                                           double* __restrict__ J) {
+                                                           double* __restrict__ J, int64_t bs_wlog = 0, int64_t bs_blog = 0,
+                                                           int bs_status = 0, int64_t bs_j = 0) {
+    // batched launches: problem blockIdx.y (all strides zero for a single problem)
+    wlog += int64_t(blockIdx.y) * bs_wlog;
+    blog += int64_t(blockIdx.y) * bs_blog;
+    status += int64_t(blockIdx.y) * bs_status;
+    J += int64_t(blockIdx.y) * bs_j;
     extern __shared__ __align__(16) double sm[];
     constexpr int R2 = 2 * JC_B;
     constexpr int WP = R2 + 4;                    // pitch of a staged rotation (conflict-free A fragments)
@@ -1181,13 +1198,15 @@ size_t jacobi_log_bytes(int p, int max_sweeps) {
 
 int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol, double noise_floor, int max_sweeps,
                 int* sweeps_out, unsigned long long* conv_dev, unsigned long long* conv_host_pinned,
-                cudaStream_t stream, double stop_rel, void* log_ws, size_t log_bytes) {
-    TTB_REQUIRE(X && J && conv_dev && conv_host_pinned, "jacobi_rows: null pointer");
+                cudaStream_t stream, double stop_rel, void* log_ws, size_t log_bytes, const JacobiBatch* batch) {
+    TTB_REQUIRE(X && J && conv_dev && (conv_host_pinned || batch), "jacobi_rows: null pointer");
+    const int nprob = batch ? batch->count : 1;
+    TTB_REQUIRE(nprob >= 1, "jacobi_rows: empty batch");
     if (!(stop_rel > 0.0)) stop_rel = 3e-8;
     TTB_REQUIRE(p >= 1 && q >= 1 && ldx >= q, "jacobi_rows: bad extents");
     const bool defer = sweeps_out && *sweeps_out == kJacobiDeferStatus;
     if (sweeps_out && !defer) *sweeps_out = 0;
-    if (p == 1) {
+    if (p == 1 && !batch) {
         set_identity_kernel<<<1, 32, 0, stream>>>(J, p);
         ++g_launch_count;
         TTB_CHECK_CUDA(cudaGetLastError());
@@ -1229,7 +1248,9 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
         }();
         const size_t log_entries = size_t(max_sweeps) * size_t(nbc - 1) * size_t(nbc / 2);
         const size_t log_w_bytes = round_up<size_t>(log_entries * size_t(2 * jcb) * size_t(2 * jcb) * sizeof(double), 256);
-        const bool log_mode = log_enabled && nbc > 2 && log_ws != nullptr && log_bytes >= log_w_bytes + log_entries * 2 * sizeof(int);
+        const size_t log_stride = round_up<size_t>(log_w_bytes + log_entries * 2 * sizeof(int), 256);  // bytes per problem
+        const bool log_mode = log_enabled && nbc > 2 && log_ws != nullptr &&
+                              log_bytes >= (nprob > 1 ? size_t(nprob) * log_stride : log_w_bytes + log_entries * 2 * sizeof(int));
         if (log_mode) {
             cp.ncol = cp.qx;
             cp.pitch = cp.ncol + 4;
@@ -1262,7 +1283,16 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
             }();
             cp.split_rounds = split_rounds ? 1 : 0;
             cp.out = reinterpret_cast<double*>(conv_dev);
-            static const bool jtiming = getenv("TTB_JACOBI_TIMING") != nullptr;
+            if (batch) {
+                cp.bs_x = batch->stride_x;
+                cp.bs_j = batch->stride_j;
+                cp.bs_out = 8;
+                cp.bs_wlog = int64_t(log_stride / sizeof(double));
+                cp.bs_blog = int64_t(log_stride / sizeof(int));
+                cp.abs_tol2_dev = batch->abs_tol2_dev;
+            }
+            static const bool jtiming_env = getenv("TTB_JACOBI_TIMING") != nullptr;
+            const bool jtiming = jtiming_env && !batch;
             cp.timing = jtiming ? 1 : 0;
             auto kern = jtiming ? ((jcb == 8) ? jacobi_cluster_kernel<8, true> : jacobi_cluster_kernel<16, true>)
                                 : ((jcb == 8) ? jacobi_cluster_kernel<8, false> : jacobi_cluster_kernel<16, false>);
@@ -1283,7 +1313,7 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
                 }
             }
             cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(unsigned(nbc / 2));
+            cfg.gridDim = dim3(unsigned(nbc / 2), unsigned(nprob));
             cfg.blockDim = dim3(JB_NT);
             cfg.dynamicSmemBytes = csmem;
             cfg.stream = stream;
@@ -1310,10 +1340,12 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
                         TTB_CHECK_CUDA(cudaFuncSetAttribute(akern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(asmem)));
                         ac = asmem;
                     }
-                    akern<<<ceil_div(p, AW), AW_NT, asmem, stream>>>(cp.wlog, cp.blog, cp.out, p, nbc, J);
+                    akern<<<dim3(ceil_div(p, AW), nprob), AW_NT, asmem, stream>>>(cp.wlog, cp.blog, cp.out, p, nbc, J, cp.bs_wlog,
+                                                                                   cp.bs_blog, cp.bs_out, cp.bs_j);
                     ++g_launch_count;
                     TTB_CHECK_CUDA(cudaGetLastError());
                 }
+                if (batch) return kOk;  // status words (sweeps, converged) stay on the device: conv_dev[8 b], [8 b + 1] as doubles
                 double* hout = reinterpret_cast<double*>(conv_host_pinned);
                 TTB_CHECK_CUDA(cudaMemcpyAsync(hout, cp.out, (jtiming ? 56 : 2) * sizeof(double), cudaMemcpyDeviceToHost, stream));
                 if (sweeps_out && *sweeps_out == kJacobiDeferStatus && !jtiming) {
@@ -1339,10 +1371,14 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
                 (void)cudaGetLastError();
                 nonportable_ok = false;
                 return jacobi_rows(X, p, q, ldx, J, abs_tol, noise_floor, max_sweeps, sweeps_out, conv_dev, conv_host_pinned,
-                                   stream, stop_rel, log_ws, log_bytes);
+                                   stream, stop_rel, log_ws, log_bytes, batch);
             }
             (void)cudaGetLastError();  // cluster shape not schedulable here: fall through to the multi-launch path
         }
+    }
+    if (batch) {
+        set_last_error("jacobi_rows: batched problems need the single-launch cluster kernel (2 <= p <= 256)");
+        return kUnsupported;
     }
     if (sweeps_out) *sweeps_out = 0;  // multi-launch path: synchronous, no deferred status
     {

@@ -13,9 +13,19 @@ namespace ttb {
 // themselves changes neither the retained subspace nor the discarded energy); 0 = off.  conv_dev / conv_host_pinned: one 8-byte
 // device word and one pinned host word used for the per-sweep convergence read.
 // Synchronises `stream` once per sweep.
+// batch != nullptr: `count` independent problems of the same shape in ONE launch (one thread-block cluster each):
+// problem b rotates X + b stride_x with J + b stride_j; conv_dev must hold 8 doubles per problem (status words
+// [8 b] = sweeps, [8 b + 1] = converged, left on the device: no host synchronisation at all), log_ws
+// count * round_up(jacobi_log_bytes, 256) bytes.  Needs the single-launch kernel (2 <= p <= 256), else kUnsupported.
+struct JacobiBatch {
+    int count;
+    int64_t stride_x, stride_j;  // in doubles
+    const double* abs_tol2_dev;  // (count) squared absolute skip thresholds per problem on the device, or null (use abs_tol)
+};
 int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol, double noise_floor, int max_sweeps,
                 int* sweeps_out, unsigned long long* conv_dev, unsigned long long* conv_host_pinned,
-                cudaStream_t stream, double stop_rel = 0.0, void* log_ws = nullptr, size_t log_bytes = 0);
+                cudaStream_t stream, double stop_rel = 0.0, void* log_ws = nullptr, size_t log_bytes = 0,
+                const JacobiBatch* batch = nullptr);
 // log_ws / log_bytes (jacobi_log_bytes): scratch for the rotation log of the single-launch kernel -- with it the
 // kernel rotates only the rows of X and J is rebuilt from the logged rotations by a second, fully parallel launch.
 size_t jacobi_log_bytes(int p, int max_sweeps);

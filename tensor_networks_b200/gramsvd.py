@@ -3,11 +3,13 @@
 Mirror of `eps_to_rank` / `gram_eig_and_svd` / `tt_gramsvd_round` of the reference
 (pytens/algs.py:1707-1717, :1720-1768, :1771-1838; exercised by tests/main_test.py:245-262).  The
 Gram sweeps and all core updates are FP64 GEMMs on the DMMA kernels of this package (`ttb_gemm_f64`);
-the symmetric eigendecompositions and the small SVD per bond run on the device Jacobi SVD
-(`ttb_delta_svd_f64`: for a symmetric positive semidefinite Gram matrix the singular values are the
-|eigenvalues| the reference takes, and the left singular vectors are its eigenvectors).  Only the
-vectors of eigenvalues (<= r doubles per bond) visit the host, where the reference's decimal rounding
-of their square roots is applied with the same numpy call.
+the symmetric eigendecompositions run on the device Jacobi kernel, batched: all right Gram matrices of a
+train are known after the first sweep and are factored by ONE launch (`ttb_gram_eig_batched_f64`, one
+thread-block cluster per matrix), which also applies the reference's decimal rounding of the square
+roots and writes the scaled eigenvector matrices A = V diag(e12), B = V diag(em12) -- no eigenvalue
+visits the host and no elementwise glue runs in eager torch.  Per bond that leaves one eigendecomposition
+(the left Gram matrix of the updated core), one truncated SVD (`ttb_delta_svd_f64`) and five GEMMs.
+Gram matrices larger than 256 x 256 take the generic path (three `ttb_delta_svd_f64` calls per bond).
 """
 
 from __future__ import annotations
@@ -69,9 +71,42 @@ def _rounded_sqrt(eig: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return torch.from_numpy(e12).to(eig.device), torch.from_numpy(em12).to(eig.device)
 
 
+GRAM_EIG_MAX = 256  # largest Gram matrix of the batched on-chip eigendecomposition
+
+
+def gram_eig_batched_dev(g: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Eigen-factors of a stack of Gram matrices g (count, p, p), p <= 256, in one launch:
+    (A, B, eig) with A = V diag(e12), B = V diag(em12) (pytens/algs.py:1727-1749), eig (count, p) descending."""
+    L = _lib.lib()
+    g = g.contiguous()
+    count, p = int(g.shape[0]), int(g.shape[1])
+    a = torch.empty_like(g)
+    b = torch.empty_like(g)
+    eig = torch.empty((count, p), dtype=torch.float64, device=g.device)
+    ws = workspace(L.ttb_gram_eig_batched_workspace_bytes(count, p), g.device, slot="gram_eig")
+    check(
+        L.ttb_gram_eig_batched_f64(
+            g.data_ptr(), count, p, a.data_ptr(), b.data_ptr(), eig.data_ptr(), None, ws.data_ptr(), ws.numel(), _stream_ptr()
+        )
+    )
+    return a, b, eig
+
+
+def bond_factors_dev(al: torch.Tensor, bl: torch.Tensor, ar: torch.Tensor, br: torch.Tensor, delta: float):
+    """(curr, next) of one bond from the eigen-factors of its left / right Gram matrices (pytens/algs.py:1751-1768):
+    tmp = A_l^T A_r, (u, s v^T) = truncated SVD, curr = B_l u, next = s v^T B_r^T."""
+    tmp = dev_mm(al, ar, ta=True)
+    u, _s, svt, _ = delta_svd_dev(tmp, float(delta))  # rank rule == eps_to_rank (tail energy <= delta)
+    return dev_mm(bl, u), dev_mm(svt, br, tb=True)
+
+
 def gram_eig_and_svd_dev(gl: torch.Tensor, gr: torch.Tensor, delta: float) -> Tuple[torch.Tensor, torch.Tensor]:
     """Device form of gram_eig_and_svd (pytens/algs.py:1720-1768): returns (curr, next) with
     curr (r x rk) to be applied to core i from the right and next (rk x r) to core i+1 from the left."""
+    if max(int(gl.shape[0]), int(gr.shape[0])) <= GRAM_EIG_MAX:
+        al, bl, _ = gram_eig_batched_dev(gl[None])
+        ar, br, _ = gram_eig_batched_dev(gr[None])
+        return bond_factors_dev(al[0], bl[0], ar[0], br[0], delta)
     vl, eigl, _, _ = delta_svd_dev(gl, 0.0)  # G = V |Lambda| V^T: columns of vl are the eigenvectors
     vr, eigr, _, _ = delta_svd_dev(gr, 0.0)
     eigl12, eiglm12 = _rounded_sqrt(eigl)
@@ -113,12 +148,26 @@ def gramsvd_round(tt: TensorTrain, eps: float) -> TensorTrain:
         gr[i] = dev_mm(tmp, c.reshape(r0, n * r1), tb=True)
     norm = float(np.sqrt(gr[0].reshape(-1)[0].item()))
     delta = eps * norm / (d - 1) ** 0.5
+    # all right Gram matrices at once, one launch per distinct size (usually one)
+    right = {}
+    by_size = {}
+    for i in range(1, d):
+        by_size.setdefault(int(gr[i].shape[0]), []).append(i)
+    for size, idxs in by_size.items():
+        if size <= GRAM_EIG_MAX:
+            a, b, _ = gram_eig_batched_dev(torch.stack([gr[i] for i in idxs]))
+            for pos, i in enumerate(idxs):
+                right[i] = (a[pos], b[pos])
     for i in range(d - 1):
         c = cores[i]
         r0, n, r1 = (int(x) for x in c.shape)
         m2 = c.reshape(r0 * n, r1)
         gl = dev_mm(m2, m2, ta=True)
-        curr, nxt = gram_eig_and_svd_dev(gl, gr[i + 1], delta)
+        if (i + 1) in right and r1 <= GRAM_EIG_MAX:
+            al, bl, _ = gram_eig_batched_dev(gl[None])
+            curr, nxt = bond_factors_dev(al[0], bl[0], right[i + 1][0], right[i + 1][1], delta)
+        else:
+            curr, nxt = gram_eig_and_svd_dev(gl, gr[i + 1], delta)
         rk = int(curr.shape[1])
         cores[i] = dev_mm(m2, curr).reshape(r0, n, rk)
         c1 = cores[i + 1]

@@ -102,3 +102,42 @@ def test_gram_eig_and_svd_host_api():
     assert c.shape == c_ref.shape and n.shape == n_ref.shape
     # the factors are unique up to an orthogonal mixing; the rounded product a c n b is not
     assert np.allclose(a @ c @ n @ b, a @ c_ref @ n_ref @ b, atol=1e-8 * np.linalg.norm(a @ b))
+
+
+@pytest.mark.parametrize("count,p,decades", [(1, 1, 0.0), (3, 2, 1.0), (5, 37, 0.5), (19, 128, 0.13), (2, 256, 0.07)])
+def test_gram_eig_batched_matches_eigh(count, p, decades):
+    """ttb_gram_eig_batched_f64 (one cluster-Jacobi launch for the whole stack) against numpy's eigh plus the
+    reference's rounding rule (pytens/algs.py:1727-1749): eigenvalues, A A^T = V diag(e12^2) V^T and B from A."""
+    import torch
+
+    from tensor_networks_b200.gramsvd import gram_eig_batched_dev
+
+    rng = np.random.default_rng(100 + p)
+    gs = []
+    for _ in range(count):
+        x = rng.standard_normal((p + 5, p)) * 10.0 ** (-decades * np.arange(p))[None, :]  # graded columns: Gram spans 2x the decades
+        q = np.linalg.qr(rng.standard_normal((p, p)))[0]
+        gs.append(q @ (x.T @ x) @ q.T)
+    g = np.stack(gs)
+    a, b, eig = (t.cpu().numpy() for t in gram_eig_batched_dev(torch.from_numpy(g).cuda()))
+    for i in range(count):
+        w, v = np.linalg.eigh(g[i])
+        w = np.abs(w)[::-1]
+        assert np.all(np.abs(eig[i] - w) <= 1e-13 * w[0]), np.max(np.abs(eig[i] - w)) / w[0]
+        e12 = orc.round_sqrt_eigs(w)
+        # the device values pass through the same rounding grid: identical up to a grid step at rounding boundaries
+        step = 10.0 ** np.ceil(np.log10(e12.max() * 1e-8 + 1e-15))
+        got12 = np.sqrt(np.sum(a[i] ** 2, axis=0))  # column norms of V diag(e12)
+        # (the square root of an eigenvalue at the roundoff level of eigh, ~1e-14 of the largest, is not determined:
+        # two backward-stable solvers differ there by several grid steps -- compared above 1e-10 of the largest only)
+        big = w > 1e-10 * w[0]
+        assert np.all(np.abs(got12 - e12)[big] <= 1.01 * step), np.max(np.abs(got12 - e12)[big]) / step
+        assert np.all(got12[~big] <= 1e-5 * e12[0])
+        # A A^T reproduces G to the rounding of the square roots
+        assert np.linalg.norm(a[i] @ a[i].T - g[i]) <= 4e-8 * np.linalg.norm(g[i]) * np.sqrt(p)
+        nz = got12 > 0
+        assert np.allclose(b[i][:, nz], a[i][:, nz] / got12[nz] ** 2, rtol=1e-12, atol=0.0)
+        assert np.all(b[i][:, ~nz] == 0.0)
+        # columns are orthogonal (eigenvectors) wherever they are not rounded away
+        vn = a[i][:, nz] / got12[nz]
+        assert np.abs(vn.T @ vn - np.eye(vn.shape[1])).max() <= 1e-10

@@ -23,18 +23,16 @@ for i in range(d - 2, -1, -1):
     tmp = tick("gram_sweep", lambda: g.dev_mm(c.reshape(r0 * nn, r1), gr[i + 1]).reshape(r0, nn * r1))
     gr[i] = tick("gram_sweep", lambda: g.dev_mm(tmp, c.reshape(r0, nn * r1), tb=True))
 norm = float(np.sqrt(gr[0].reshape(-1)[0].item())); delta = eps * norm / (d - 1) ** 0.5
+ar, br, _ = tick("eig_right_batched", lambda: g.gram_eig_batched_dev(torch.stack(gr[1:])))
 for i in range(d - 1):
     c = cores[i]; r0, nn, r1 = c.shape; m2 = c.reshape(r0 * nn, r1)
     gl = tick("gl", lambda: g.dev_mm(m2, m2, ta=True))
-    vl, el, _, _ = tick("eig_l", lambda: delta_svd_dev(gl, 0.0))
-    vr, er, _, _ = tick("eig_r", lambda: delta_svd_dev(gr[i + 1], 0.0))
-    (l12, lm12) = tick("round_sqrt", lambda: g._rounded_sqrt(el)); (r12, rm12) = tick("round_sqrt", lambda: g._rounded_sqrt(er))
-    tmp = tick("tmp", lambda: g.dev_mm(vl * l12[None, :], vr * r12[None, :], ta=True))
-    u, _s, svt, _ = tick("svd_tmp", lambda: delta_svd_dev(tmp, float(delta)))
-    curr = tick("factors", lambda: g.dev_mm(vl, lm12[:, None] * u)); nxt = tick("factors", lambda: g.dev_mm(svt * rm12[None, :], vr, tb=True))
+    al, bl, _ = tick("eig_l", lambda: g.gram_eig_batched_dev(gl[None]))
+    tmp = tick("tmp_gemm", lambda: g.dev_mm(al[0], ar[i], ta=True))
+    u, s, svt, _ = tick("svd_mid", lambda: delta_svd_dev(tmp, float(delta)))
+    curr = tick("factors", lambda: g.dev_mm(bl[0], u)); nxt = tick("factors", lambda: g.dev_mm(svt, br[i], tb=True))
     rk = curr.shape[1]
-    cores[i] = tick("update", lambda: g.dev_mm(m2, curr).reshape(r0, nn, rk))
+    cores[i] = tick("core_update", lambda: g.dev_mm(m2, curr).reshape(r0, nn, rk))
     c1 = cores[i + 1]
-    cores[i + 1] = tick("update", lambda: g.dev_mm(nxt, c1.reshape(c1.shape[0], -1)).reshape(rk, c1.shape[1], c1.shape[2]))
-    if i == 5: print("shapes", gl.shape, el.shape, er.shape, tmp.shape, rk)
-for k, v in acc.items(): print(f"{k:12s} {v:8.3f} ms total  {v/(d-1):7.3f} per bond")
+    cores[i + 1] = tick("core_update", lambda: g.dev_mm(nxt, c1.reshape(c1.shape[0], -1)).reshape(rk, c1.shape[1], c1.shape[2]))
+for k, v in acc.items(): print(f"{k:20s} {v:8.3f} ms total  {v/(d-1):7.3f} per bond")
