@@ -113,7 +113,8 @@ __device__ __forceinline__ StripSlices strip_slices(int c0, int K2, int ncols) {
 // turn-around; issuing the TMA copies from the MMA warps (one elected thread, or rotating over the warps) --
 // 4 to 15 % slower than a dedicated copy warp; run-time register selects of the A operand and reloading a
 // fragment register right behind the DMMAs that read it -- both stall on the write-after-read hazard with
-// the tensor pipe.)
+// the tensor pipe; sixteen MMA warps with 16 x 56 warp tiles (four per scheduler, 96 registers, no spills) --
+// 4.76 ms against 4.72 ms: warp-level parallelism is not what limits the GEMM phases.)
 template <int JLO, int JHI>
 __device__ __forceinline__ void mma_stage(double (&acc)[4][NJ][2], const double* __restrict__ As,
                                           const double* __restrict__ Bs) {

@@ -1249,7 +1249,11 @@ int jacobi_rows(double* X, int p, int q, int64_t ldx, double* J, double abs_tol,
         const size_t log_entries = size_t(max_sweeps) * size_t(nbc - 1) * size_t(nbc / 2);
         const size_t log_w_bytes = round_up<size_t>(log_entries * size_t(2 * jcb) * size_t(2 * jcb) * sizeof(double), 256);
         const size_t log_stride = round_up<size_t>(log_w_bytes + log_entries * 2 * sizeof(int), 256);  // bytes per problem
-        const bool log_mode = log_enabled && nbc > 2 && log_ws != nullptr &&
+        // (the replay kernel stages all rows of a column slice plus AW_ST phases of rotations: with 16-row blocks that
+        // exceeds one SM's shared memory from p = 256 on -- no log then)
+        const size_t replay_smem = (size_t(nbc) * jcb * AWP + size_t(AW_ST) * (nbc / 2) * (2 * jcb) * (2 * jcb + 4)) * sizeof(double) +
+                                   size_t(AW_ST) * size_t(nbc) * sizeof(int) + 64;
+        const bool log_mode = log_enabled && nbc > 2 && log_ws != nullptr && replay_smem <= size_t(220) * 1024 &&
                               log_bytes >= (nprob > 1 ? size_t(nprob) * log_stride : log_w_bytes + log_entries * 2 * sizeof(int));
         if (log_mode) {
             cp.ncol = cp.qx;
