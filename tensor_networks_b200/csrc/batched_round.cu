@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = p.d;
-    long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+    long long tacc[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;  // 12 / 13: the staging copies inside load_tile (RQ / forward)
     const bool timing = TIMING && p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
 #define RB_TICK(slot)                     \
     if (TIMING && timing) {               \
@@ -626,6 +626,7 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
                         // barrier are they written back -- the output of slice s overlaps the input of later ones
                         const int wid = nn * ro;
                         stage_rows(As, core, c, wid);
+                        RB_TICK(12)
                         const int fr = lane >> 2, fq = lane & 3;
                         const int njobs = ((c + 7) >> 3) * nn, ntl = (rn + 7) >> 3;
                         double acc[4][4][2];
@@ -789,6 +790,7 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
                         // tensor-pipe version: stage the raw core (ck x nn c) in the tile, out = carry . core as
                         // (rho x nn c) DMMA tiles held in registers, barrier, then scatter to As[j][q nn + s]
                         stage_rows(As, core, ck, wid);
+                        RB_TICK(13)
                         const int fr = lane >> 2, fq = lane & 3;
                         const int mtl = (rho + 7) >> 3, etl = (wid + 7) >> 3, njobs = mtl * etl;
                         const int kst = (ck + 3) >> 2;
@@ -1026,7 +1028,11 @@ __global__ void __launch_bounds__(RB_NT, 2) round_batched_kernel(const __grid_co
         __syncthreads();
     }
     if (TIMING && timing)
+    {
         for (int i = 0; i < 12; ++i) p.dbg[i] = tacc[i];
+        p.dbg[20] = tacc[12];
+        p.dbg[21] = tacc[13];
+    }
 #undef RB_TICK
 }
 
@@ -1097,6 +1103,8 @@ int round_batched(const TTBatchDesc& t, double eps, int max_rank, int64_t* ranks
             round_batched_kernel<true><<<grid, RB_NT, kRoundBatchSmem, stream>>>(p);
             long long h[24];
             cudaMemcpy(h, dbg_dev, 192, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[bround] staging copies inside load+push / load+carry (CTA 0, cumulative kcycles): RQ %lld, FWD %lld\n",
+                    h[20] / 1000, h[21] / 1000);
             fprintf(stderr, "[bround] RQ cholqr_tile kcycles (CTA 0, cumulative): gram1 %lld chol %lld dinv %lld solve %lld gram2 %lld W2 %lld apply2 %lld resid %lld rest(in tick 8) \n",
                     h[12] / 1000, h[13] / 1000, h[14] / 1000, h[15] / 1000, h[16] / 1000, h[17] / 1000, h[18] / 1000, h[19] / 1000);
             fprintf(stderr, "[bround] Cholesky-QR fast path: RQ %lld ok / %lld fallback, FWD %lld ok / %lld fallback\n", h[8], h[9],
