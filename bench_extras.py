@@ -398,18 +398,49 @@ def run_batched(batch=8192, d=20, n=8, r=32, eps=1e-8, steps=5, rank=0, world=1,
 
     peak_hbm, hbm_src = hbm_peak()
     # ---- inner ----
+    # (a) local kernel + NCCL all-gather of the scalars; (b) fused: the kernel stores its results into every rank's
+    # array over NVLink (symmetric memory) and the ranks meet at a signal barrier -- no collective behind the kernel
+    from tensor_networks_b200.sharding import PeerGather, inner_sharded
+
     vals = torch.empty(batch, dtype=torch.float64, device="cuda")
-    for _ in range(2):
+    # (an inner step is short -- 0.7 ms per GPU at N = 8 -- so it gets its own, larger step count: with 3 steps and 2
+    # warm-up calls the first collectives' lazy set-up was still inside the timed region: 1.07 ms instead of 0.69)
+    isteps = max(steps, 20)
+    for _ in range(5):
         vals = all_gather_items(a.inner(b), batch, out=vals)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with _Clocks() as ck_in:
         e0.record()
-        for _ in range(steps):
+        for _ in range(isteps):
             vals = all_gather_items(a.inner(b), batch, out=vals)
         e1.record()
         barrier()
-    ms_inner = sync_max(e0.elapsed_time(e1) / steps)
+    ms_inner_nccl = sync_max(e0.elapsed_time(e1) / isteps)
+    ms_inner = ms_inner_nccl
+    inner_path = "local kernel + NCCL all_gather of fp64 scalars" if world > 1 else "local kernel (single GPU)"
+    fused_note = None
+    if world > 1:
+        pg = PeerGather(batch)
+        fused_ok = torch.tensor([1 if (pg.fused and pg.handle is not None) else 0], device="cuda")
+        dist.all_reduce(fused_ok, op=dist.ReduceOp.MIN)  # every rank takes the same path
+        if int(fused_ok.item()) == 1:
+            for _ in range(5):
+                vf = inner_sharded(a, b, batch, gather=pg)
+            barrier()
+            same = bool(torch.equal(vf, vals))
+            e0.record()
+            for _ in range(isteps):
+                vf = inner_sharded(a, b, batch, gather=pg)
+            e1.record()
+            barrier()
+            ms_inner = sync_max(e0.elapsed_time(e1) / isteps)
+            vals = vf
+            inner_path = ("fused: the kernel's epilogue stores every result into all ranks' arrays over NVLink (symmetric memory) "
+                          "+ one signal-pad barrier per step; no collective")
+            fused_note = {"ms_nccl_variant": ms_inner_nccl, "bitwise_equal_to_nccl_variant": same}
+        else:
+            fused_note = {"unavailable": pg.why_not or "symmetric memory rendezvous failed on some rank"}
     f_inner = orc.inner_flops([n] * d, [r] * (d - 1), [r] * (d - 1)) * batch
     by_inner = 2 * orc.tt_bytes([n] * d, [r] * (d - 1)) * batch
 
@@ -457,6 +488,7 @@ def run_batched(batch=8192, d=20, n=8, r=32, eps=1e-8, steps=5, rank=0, world=1,
                                "hbm_achieved": by_inner / (ms_inner * 1e-3) / 1e9, "hbm_peak": peak_hbm * world,
                                "hbm_frac": by_inner / (ms_inner * 1e-3) / 1e9 / (peak_hbm * world), "hbm_peak_source": hbm_src,
                                "traffic": _traffic("inner_batched_tma_bytes_per_launch") if (world == 1 and batch == 8192) else None},
+                  "gather": inner_path, "fused_gather": fused_note,
                   "clocks": ck_in.summary() if rank == 0 else None},
         "round": {"ms": ms_round, "gflops": f_round / (ms_round * 1e-3) / 1e9,
                   "algorithmic_gbs": by_round / (ms_round * 1e-3) / 1e9, "items_per_s": batch / (ms_round * 1e-3),
@@ -467,7 +499,7 @@ def run_batched(batch=8192, d=20, n=8, r=32, eps=1e-8, steps=5, rank=0, world=1,
                                "traffic": None},
                   "clocks": ck_rd.summary() if rank == 0 else None},
         "gather_cores": gather,
-        "collective": "all_gather of fp64 scalars (inner) and the int64 rank table (rounding); optional all_gather of the rounded cores",
+        "collective": "inner: see inner.gather; rounding: NCCL all_gather of the int64 rank table; optional all_gather of the rounded cores",
         "checksum_inner": float(vals.abs().sum().item()),
         "checksum_note": "sum |<A_i, B_i>| over the gathered batch; the batch is generated identically for every N",
     }

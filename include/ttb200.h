@@ -119,6 +119,15 @@ size_t ttb_inner_batched_workspace_bytes(const ttb_tt_batch* a, const ttb_tt_bat
 int ttb_inner_batched_f64(const ttb_tt_batch* a, const ttb_tt_batch* b, double* out_dev, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* Sharded form of ttb_inner_batched_f64 (north_star item 4: batches shard across the GPUs, scalar results are
+ * gathered over NVLink): result i of this rank's shard is stored at out_peers[r][item_offset + i] for every r <
+ * n_peers (<= 8), where out_peers[r] is rank r's full-batch result array mapped into this process (symmetric memory /
+ * CUDA IPC).  The stores are the kernel's epilogue, so no collective follows -- the ranks only meet at a barrier
+ * before they read.  Replaces the per-item TensorNetwork.inner loop of the reference's callers plus the gather. */
+size_t ttb_inner_batched_scatter_workspace_bytes(const ttb_tt_batch* a, const ttb_tt_batch* b);
+int ttb_inner_batched_scatter_f64(const ttb_tt_batch* a, const ttb_tt_batch* b, double* const* out_peers, int32_t n_peers,
+                                  int64_t item_offset, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- dense contraction of a chain --------------------------------------
  * out_dev (n_1 x ... x n_d, C-order) = the tensor the TT represents; what
  * TensorNetwork.contract() returns for a chain (pytens/algs.py:469-485). */

@@ -137,6 +137,13 @@ def _declare(lib):
     lib.ttb_inner_batched_f64.restype = c_int
     lib.ttb_inner_batched_f64.argtypes = [P(ttb_tt_batch), P(ttb_tt_batch), c_void_p, c_void_p, c_size_t, c_void_p]
 
+    lib.ttb_inner_batched_scatter_workspace_bytes.restype = c_size_t
+    lib.ttb_inner_batched_scatter_workspace_bytes.argtypes = [P(ttb_tt_batch), P(ttb_tt_batch)]
+    lib.ttb_inner_batched_scatter_f64.restype = c_int
+    lib.ttb_inner_batched_scatter_f64.argtypes = [
+        P(ttb_tt_batch), P(ttb_tt_batch), P(c_void_p), c_int32, c_int64, c_void_p, c_size_t, c_void_p,
+    ]
+
     lib.ttb_round_batched_workspace_bytes.restype = c_size_t
     lib.ttb_round_batched_workspace_bytes.argtypes = [P(ttb_tt_batch)]
     lib.ttb_round_batched_f64.restype = c_int

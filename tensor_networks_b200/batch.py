@@ -158,6 +158,23 @@ class TensorTrainBatch:
         check(L.ttb_inner_batched_f64(da.ref(), db.ref(), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr()))
         return out
 
+    def inner_scatter(self, other: "TensorTrainBatch", peer_ptrs: Sequence[int], offset: int) -> None:
+        """<self_i, other_i> of this shard stored at peer_ptrs[r] + 8 (offset + i) for EVERY r: the peers' full-batch
+        result arrays are mapped into this process (`sharding.PeerGather`), so the kernel's epilogue is the all-gather
+        (`ttb_inner_batched_scatter_f64`).  The caller synchronises the ranks (PeerGather.barrier) before reading."""
+        if self.item_ranks is not None or other.item_ranks is not None:
+            raise RuntimeError("inner on a rounded batch: call .item(i) (ranks differ per item)")
+        if self.shape() != other.shape() or self.batch != other.batch:
+            raise AssertionError("inner: batches differ in size or free indices")
+        import ctypes
+
+        L = _lib.lib()
+        da, db = self.descriptor(), other.descriptor()
+        ws = workspace(L.ttb_inner_batched_scatter_workspace_bytes(da.ref(), db.ref()), self.device)
+        ptrs = (ctypes.c_void_p * len(peer_ptrs))(*[int(x) for x in peer_ptrs])
+        check(L.ttb_inner_batched_scatter_f64(da.ref(), db.ref(), ptrs, len(peer_ptrs), int(offset), ws.data_ptr(), ws.numel(),
+                                              _stream_ptr()))
+
     def norm(self) -> torch.Tensor:
         """(B,) CUDA tensor of sqrt(|<X_i, X_i>|) -- TensorNetwork.norm, pytens/algs.py:589-594."""
         return self.inner(self).abs().sqrt()

@@ -347,6 +347,44 @@ size_t inner_batched_workspace_bytes(const TTBatchDesc& a, const TTBatchDesc& b)
     return inner_workspace_bytes(da, db);
 }
 
+namespace {
+__global__ void scatter_results_kernel(const double* __restrict__ src, int64_t n, PeerScatter sc) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const double v = src[i];
+        for (int r = 0; r < sc.count; ++r) sc.peers[r][sc.offset + i] = v;
+    }
+}
+}  // namespace
+
+size_t inner_batched_scatter_workspace_bytes(const TTBatchDesc& a, const TTBatchDesc& b) {
+    return inner_batched_workspace_bytes(a, b) + round_up<size_t>(size_t(std::max<int64_t>(a.batch, 1)) * 8, 256) + 256;
+}
+
+int inner_batched_scatter(const TTBatchDesc& a, const TTBatchDesc& b, const PeerScatter& sc, void* ws, size_t ws_bytes,
+                          cudaStream_t stream) {
+    TTB_PROPAGATE(validate_batch(a, "inner_batched_scatter: A"));
+    TTB_PROPAGATE(validate_batch(b, "inner_batched_scatter: B"));
+    TTB_REQUIRE(a.d == b.d && a.batch == b.batch, "inner_batched_scatter: operands differ in d or batch");
+    for (int k = 0; k < a.d; ++k) TTB_REQUIRE(a.n[k] == b.n[k], "inner_batched_scatter: mode sizes differ");
+    TTB_REQUIRE(sc.count >= 1 && sc.count <= kMaxPeers && sc.offset >= 0, "inner_batched_scatter: bad peer list");
+    for (int r = 0; r < sc.count; ++r) TTB_REQUIRE(sc.peers[r] != nullptr, "inner_batched_scatter: null peer buffer");
+    if (a.batch == 0) return kOk;
+    if (small_ranks(a) && small_ranks(b)) {
+        bool taken = false;
+        TTB_PROPAGATE(inner_batched_tma(a, b, nullptr, stream, &taken, &sc));  // epilogue stores to the peers
+        if (taken) return kOk;
+    }
+    // other shapes: local results first, then one scatter launch
+    const size_t tmp_bytes = round_up<size_t>(size_t(a.batch) * 8, 256);
+    TTB_REQUIRE(ws != nullptr && ws_bytes >= tmp_bytes + 256, "inner_batched_scatter: workspace too small");
+    double* tmp = static_cast<double*>(ws);
+    TTB_PROPAGATE(inner_batched(a, b, tmp, static_cast<char*>(ws) + tmp_bytes, ws_bytes - tmp_bytes, stream));
+    scatter_results_kernel<<<int(std::min<int64_t>(ceil_div<int64_t>(a.batch, 256), 1184)), 256, 0, stream>>>(tmp, a.batch, sc);
+    ++g_launch_count;
+    TTB_CHECK_CUDA(cudaGetLastError());
+    return kOk;
+}
+
 int inner_batched(const TTBatchDesc& a, const TTBatchDesc& b, double* out_dev, void* ws, size_t ws_bytes,
                   cudaStream_t stream) {
     TTB_PROPAGATE(validate_batch(a, "inner_batched: A"));

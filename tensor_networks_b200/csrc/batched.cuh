@@ -15,6 +15,16 @@ struct TTBatchDesc {
     double* const* core;
 };
 
+// Where the per-item results of a sharded batch go: result i of this rank is stored at peers[r][offset + i] for every
+// r < count -- the peers' buffers are mapped over NVLink (symmetric memory), so the kernel's epilogue IS the all-gather
+// and no collective follows (the ranks only meet at a signal barrier).  count <= kMaxPeers.
+constexpr int kMaxPeers = 8;
+struct PeerScatter {
+    double* peers[kMaxPeers];
+    int count;
+    int64_t offset;
+};
+
 int validate_batch(const TTBatchDesc& t, const char* what);
 
 // out_dev[i] = <A_i, B_i>.  Bond ranks <= 32 run in one fused kernel (one CTA per
@@ -22,9 +32,14 @@ int validate_batch(const TTBatchDesc& t, const char* what);
 size_t inner_batched_workspace_bytes(const TTBatchDesc& a, const TTBatchDesc& b);
 int inner_batched(const TTBatchDesc& a, const TTBatchDesc& b, double* out_dev, void* ws, size_t ws_bytes,
                   cudaStream_t stream);
+// Same, with the results stored straight into every peer's gathered array (out_dev is not used).
+size_t inner_batched_scatter_workspace_bytes(const TTBatchDesc& a, const TTBatchDesc& b);
+int inner_batched_scatter(const TTBatchDesc& a, const TTBatchDesc& b, const PeerScatter& sc, void* ws, size_t ws_bytes,
+                          cudaStream_t stream);
 
 // TMA-staged variant for bond ranks <= 32 (batched_tma.cu); *taken = false when its shape / alignment rules do not hold.
-int inner_batched_tma(const TTBatchDesc& a, const TTBatchDesc& b, double* out_dev, cudaStream_t stream, bool* taken);
+int inner_batched_tma(const TTBatchDesc& a, const TTBatchDesc& b, double* out_dev, cudaStream_t stream, bool* taken,
+                      const PeerScatter* sc = nullptr);
 
 // tt_svd_round (pytens/algs.py:1841-1903) on every item, in place on the batch storage:
 // item i's core k is written compactly as (ranks[i][k], n[k], ranks[i][k+1]) at the start

@@ -61,7 +61,10 @@ struct BtParams {
     const double* Alast;  // (batch, ra[d-1], n[d-1])
     const double* Blast;
     int64_t batch;
-    double* out;
+    double* out;          // local results (n_out == 0) ...
+    double* out_peers[kMaxPeers];  // ... or every rank's gathered array, item i at out_peers[r][out_offset + i]
+    int n_out;
+    int64_t out_offset;
 };
 
 // One slice of one core: 64 DMMAs per warp when all ranks are 32.  Four accumulator chains per product; eight (even /
@@ -246,7 +249,15 @@ __global__ void __launch_bounds__(BT_NT, MINB) inner_batched_tma_kernel(const __
             for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
             if (lane == 0) fin[warp] = v;
             __syncthreads();
-            if (tid == 0) p.out[item] = (fin[0] + fin[1]) + (fin[2] + fin[3]);
+            if (tid == 0) {
+                const double v = (fin[0] + fin[1]) + (fin[2] + fin[3]);
+                if (p.n_out == 0) {
+                    p.out[item] = v;
+                } else {
+                    // fused all-gather: the result goes straight into every rank's array over NVLink
+                    for (int r = 0; r < p.n_out; ++r) p.out_peers[r][p.out_offset + item] = v;
+                }
+            }
             // fin and both exchange tiles are next written after further barriers of the next item (>= 1 in between)
         }
     }
@@ -256,7 +267,8 @@ __global__ void __launch_bounds__(BT_NT, MINB) inner_batched_tma_kernel(const __
 
 // Returns kOk with *taken = false when the shape / alignment rules of the TMA path do not hold (the caller then
 // runs the cp.async kernel).  TTB_BINNER_TMA=0 disables the path.
-int inner_batched_tma(const TTBatchDesc& a, const TTBatchDesc& b, double* out_dev, cudaStream_t stream, bool* taken) {
+int inner_batched_tma(const TTBatchDesc& a, const TTBatchDesc& b, double* out_dev, cudaStream_t stream, bool* taken,
+                      const PeerScatter* sc) {
     *taken = false;
     const char* env = getenv("TTB_BINNER_TMA");  // read on every call, so a test can switch inside one process
     const bool enabled = !(env && atoi(env) == 0);
@@ -292,6 +304,9 @@ int inner_batched_tma(const TTBatchDesc& a, const TTBatchDesc& b, double* out_de
     p.Alast = a.core[d - 1];
     p.Blast = b.core[d - 1];
     p.out = out_dev;
+    p.n_out = sc ? sc->count : 0;
+    p.out_offset = sc ? sc->offset : 0;
+    for (int r = 0; r < kMaxPeers; ++r) p.out_peers[r] = (sc && r < sc->count) ? sc->peers[r] : nullptr;
     // three CTAs of four warps per SM with 3 ring slots each (168 registers): 4.86 ms for the 8192 pairs of configs[4];
     // two CTAs with 5 slots: 4.89 ms; with a dedicated copy warp (five warps are allocated as eight): 5.11 ms
     constexpr int kStages = 3, kPerSm = 3;

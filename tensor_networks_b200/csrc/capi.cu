@@ -121,6 +121,28 @@ int ttb_inner_batched_f64(const ttb_tt_batch* a, const ttb_tt_batch* b, double* 
     return ttb::inner_batched(to_bdesc(a), to_bdesc(b), out_dev, workspace, workspace_bytes, as_stream(stream));
 }
 
+size_t ttb_inner_batched_scatter_workspace_bytes(const ttb_tt_batch* a, const ttb_tt_batch* b) {
+    if (!a || !b) return 0;
+    return ttb::inner_batched_scatter_workspace_bytes(to_bdesc(a), to_bdesc(b));
+}
+
+int ttb_inner_batched_scatter_f64(const ttb_tt_batch* a, const ttb_tt_batch* b, double* const* out_peers, int32_t n_peers,
+                                  int64_t item_offset, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!a || !b || !out_peers) {
+        ttb::set_last_error("ttb_inner_batched_scatter_f64: null argument");
+        return TTB_INVALID_ARGUMENT;
+    }
+    if (n_peers < 1 || n_peers > ttb::kMaxPeers) {
+        ttb::set_last_error("ttb_inner_batched_scatter_f64: n_peers must be in [1, 8]");
+        return TTB_INVALID_ARGUMENT;
+    }
+    ttb::PeerScatter sc{};
+    sc.count = n_peers;
+    sc.offset = item_offset;
+    for (int r = 0; r < n_peers; ++r) sc.peers[r] = out_peers[r];
+    return ttb::inner_batched_scatter(to_bdesc(a), to_bdesc(b), sc, workspace, workspace_bytes, as_stream(stream));
+}
+
 size_t ttb_tt_to_dense_workspace_bytes(const ttb_tt* a) {
     if (!a) return 0;
     return ttb::tt_to_dense_workspace_bytes(to_desc(a));

@@ -64,6 +64,31 @@ def test_inner_batched_tma_matches_cp_async_kernel(monkeypatch):
         assert torch.all((v_tma - v_cp).abs() <= 1e-13 * scale), ((v_tma - v_cp).abs() / scale).max()
 
 
+def test_inner_batched_scatter_single_rank():
+    """The fused compute + gather entry point (ttb_inner_batched_scatter_f64) with this process as its only peer:
+    same values as the plain call, at the right offset, for the TMA kernel and for the fallback shapes."""
+    from tensor_networks_b200.batch import TensorTrainBatch
+    from tensor_networks_b200.sharding import PeerGather, inner_sharded
+
+    for shape, ra, rb in (([8] * 20, [32] * 19, [32] * 19), ([5, 8, 3, 9], [7, 24, 5], [30, 15, 32]), ([6] * 4, [40, 33, 36], [8, 40, 8])):
+        nb = 50 if max(ra) <= 32 else 3
+        ta = TensorTrainBatch.rand(nb, shape, ra, seed=21)
+        tb = TensorTrainBatch.rand(nb, shape, rb, seed=22)
+        ref = ta.inner(tb)
+        pg = PeerGather(nb)
+        assert pg.fused and pg.ptrs == [pg.tensor.data_ptr()]
+        got = inner_sharded(ta, tb, nb, gather=pg)
+        assert got.data_ptr() == pg.tensor.data_ptr()
+        assert torch.equal(got, ref)
+        # two "peers" (two local arrays) and a non-zero offset
+        big1 = torch.full((nb + 7,), -1.0, dtype=torch.float64, device="cuda")
+        big2 = torch.full((nb + 7,), -1.0, dtype=torch.float64, device="cuda")
+        ta.inner_scatter(tb, [big1.data_ptr(), big2.data_ptr()], 4)
+        for big in (big1, big2):
+            assert torch.equal(big[4 : 4 + nb], ref)
+            assert torch.all(big[:4] == -1.0) and torch.all(big[4 + nb :] == -1.0)
+
+
 def test_inner_batched_matches_single_path_and_is_deterministic():
     from tensor_networks_b200.batch import TensorTrainBatch
 

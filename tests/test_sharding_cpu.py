@@ -57,7 +57,23 @@ def _worker(rank, world, port, batch, q):
     full_cores = [torch.randn((batch, rcap[k], 4, rcap[k + 1]), dtype=torch.float64, generator=gen) for k in range(3)]
     got = all_gather_padded_cores([c[lo:hi].clone() for c in full_cores], batch)
     ok_cores = all(torch.equal(g, f) for g, f in zip(got, full_cores))
-    q.put((rank, ok_scalar and ok_ranks and ok_cap and ok_cores))
+    # PeerGather without peer-mappable memory (CPU / gloo): not fused, and inner_sharded takes the collective path
+    # into the gather's own buffer
+    from tensor_networks_b200.sharding import PeerGather, inner_sharded
+
+    class _Local:  # stands in for a TensorTrainBatch shard: the oracle is the local compute
+        batch = hi - lo
+
+        def inner(self, other):
+            return local
+
+    pg = PeerGather(batch, device="cpu")
+    ok_pg = (not pg.fused) and pg.why_not is not None
+    got_pg = inner_sharded(_Local(), _Local(), batch, gather=pg)
+    ok_pg = ok_pg and bool(torch.equal(got_pg, ref))
+    if batch % world == 0:  # even shards: the collective writes straight into the gather's buffer
+        ok_pg = ok_pg and got_pg.data_ptr() == pg.tensor.data_ptr()
+    q.put((rank, ok_scalar and ok_ranks and ok_cap and ok_cores and ok_pg))
     dist.barrier()
     dist.destroy_process_group()
 
