@@ -555,8 +555,49 @@ def cpu_batched_sample(d=20, n=8, r=32, eps=1e-8, items=8):
             "inner_pairs_per_s": items / t_in, "round_items_per_s": items / t_rd}
 
 
+def run_cfg1_sweep(cpu_budget_s=12.0):
+    """configs[0]: the points of examples/inner_product_scaling.py (the reference's own CPU-runnable sweep: rank scaling
+    at n = 20, d = 20; mode-size scaling at r = 20, d = 20; dimension scaling at r = 5, n = 5), cores scaled so that
+    d = 640 stays finite.  Per point: device-resident time of TensorTrain.inner (CUDA events, best of 5 after warm-up)
+    and one pass of the numpy oracle sweep on the host cores (skipped once the CPU budget is spent)."""
+    points = [(20, 20, r) for r in (10, 20, 40, 80, 160, 320, 640)]
+    points += [(20, n, 20) for n in (5, 10, 20, 40, 80, 160, 320, 640, 1280, 2560)]
+    points += [(d, 5, 5) for d in (5, 10, 20, 40, 80, 160, 320, 640)]
+    rows, cpu_spent = [], 0.0
+    for d, n, r in points:
+        rng = np.random.default_rng(4)
+        a = orc.rand_tt([n] * d, [r] * (d - 1), rng)
+        b = orc.rand_tt([n] * d, [r] * (d - 1), rng)
+        ta, tb = TensorTrain.from_cores(a), TensorTrain.from_cores(b)
+        for _ in range(3):
+            v = ta.inner_dev(tb)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            v = ta.inner_dev(tb)
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        flops = orc.inner_flops([n] * d, [r] * (d - 1), [r] * (d - 1))
+        row = {"d": d, "n": n, "r": r, "gpu_ms": best, "gpu_gflops": flops / (best * 1e-3) / 1e9}
+        if cpu_spent < cpu_budget_s:
+            t0 = time.perf_counter()
+            ref = float(orc.inner(a, b))
+            dt = time.perf_counter() - t0
+            cpu_spent += dt
+            got = float(v.item())
+            row.update({"cpu_ms": 1e3 * dt, "cpu_gflops": flops / dt / 1e9, "rel_diff": abs(got - ref) / abs(ref)})
+        rows.append(row)
+        del ta, tb
+    return {"workload": "examples/inner_product_scaling.py sweep points (BASELINE configs[0]), scaled cores, seed 4",
+            "cpu": "numpy oracle sweep (port), one pass per point, all BLAS threads", "points": rows}
+
+
 def run_all():
     out = {}
+    out["cfg1_scaling_sweep"] = run_cfg1_sweep()
     out["round_cfg3"] = run_round()
     out["round_cfg3_generic"] = run_round_cfg3_generic()
     out["round_generic"] = run_round_generic()
@@ -576,6 +617,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     table = {
         "small": lambda: run_round(d=10, n=32, r=64, cpu_sample_d=0),
+        "cfg1": run_cfg1_sweep,
         "round": run_round,
         "cfg3generic": run_round_cfg3_generic,
         "generic": run_round_generic,

@@ -40,7 +40,7 @@ namespace {
 constexpr int IB_R = 32;        // max bond rank handled on chip
 constexpr int IB_EP = IB_R + 4; // pitch of E and of the partial buffers
 
-constexpr int kMaxD = 128;
+constexpr int kMaxD = kBatchedMaxD;  // 28 KB of kernel parameters at 1024 (limit 32 764 bytes)
 struct InnerBatchParams {
     int d;
     int64_t batch;

@@ -18,6 +18,9 @@ struct TTBatchDesc {
 // Where the per-item results of a sharded batch go: result i of this rank is stored at peers[r][offset + i] for every
 // r < count -- the peers' buffers are mapped over NVLink (symmetric memory), so the kernel's epilogue IS the all-gather
 // and no collective follows (the ranks only meet at a signal barrier).  count <= kMaxPeers.
+constexpr int kBatchedMaxD = 1024;      // longest chain the fused small-rank inner kernel takes (kernel parameter arrays)
+constexpr int kSmallSlicesPerCore = 12; // single small trains go through it up to this many mode slices per core on average
+                                        // (a lone CTA needs ~0.8 us per slice: 20 slices per core are on a par with the GEMM path)
 constexpr int kMaxPeers = 8;
 struct PeerScatter {
     double* peers[kMaxPeers];

@@ -308,16 +308,24 @@ int inner_batched_tma(const TTBatchDesc& a, const TTBatchDesc& b, double* out_de
     p.out_offset = sc ? sc->offset : 0;
     for (int r = 0; r < kMaxPeers; ++r) p.out_peers[r] = (sc && r < sc->count) ? sc->peers[r] : nullptr;
     // three CTAs of four warps per SM with 3 ring slots each (168 registers): 4.86 ms for the 8192 pairs of configs[4];
-    // two CTAs with 5 slots: 4.89 ms; with a dedicated copy warp (five warps are allocated as eight): 5.11 ms
-    constexpr int kStages = 3, kPerSm = 3;
+    // two CTAs with 5 slots: 4.89 ms; with a dedicated copy warp (five warps are allocated as eight): 5.11 ms.
+    // Batches that leave SMs idle anyway (a single small train routed here by inner()) get one CTA per SM with an
+    // 11-slot ring: a lone CTA is bound by the latency of the box copies, so the depth of the ring is its throughput.
+    constexpr int kStages = 3, kPerSm = 3, kDeepStages = 11;
     static bool configured = false;
     if (!configured) {
         TTB_CHECK_CUDA(cudaFuncSetAttribute(inner_batched_tma_kernel<kStages, kPerSm>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(bt_smem(kStages))));
+        TTB_CHECK_CUDA(cudaFuncSetAttribute(inner_batched_tma_kernel<kDeepStages, 1>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, int(bt_smem(kDeepStages))));
         configured = true;
     }
-    const int grid = int(std::min<int64_t>(a.batch, kPerSm * int64_t(num_sms())));
-    inner_batched_tma_kernel<kStages, kPerSm><<<grid, BT_NT, bt_smem(kStages), stream>>>(p);
+    if (a.batch <= int64_t(num_sms())) {
+        inner_batched_tma_kernel<kDeepStages, 1><<<int(a.batch), BT_NT, bt_smem(kDeepStages), stream>>>(p);
+    } else {
+        const int grid = int(std::min<int64_t>(a.batch, kPerSm * int64_t(num_sms())));
+        inner_batched_tma_kernel<kStages, kPerSm><<<grid, BT_NT, bt_smem(kStages), stream>>>(p);
+    }
     TTB_CHECK_CUDA(cudaGetLastError());
     ++g_launch_count;
     *taken = true;

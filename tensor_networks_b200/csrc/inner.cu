@@ -15,6 +15,7 @@
 #include "gemm.cuh"
 #include "tt.cuh"
 #include "staging.cuh"
+#include "batched.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -165,6 +166,26 @@ int inner(const TTDesc& A, const TTDesc& B, double* out_dev, void* ws, size_t ws
         TTB_REQUIRE(A.n[k] == B.n[k], "inner: mode sizes differ (free indices must match)");
     TTB_REQUIRE(out_dev != nullptr, "inner: null output");
 
+    // Small trains (every bond rank <= 32, few mode slices per core): the whole sweep as ONE launch of the batched
+    // small-rank kernel on a batch of one -- a CTA walks the cores with the environment on chip (~0.8 us per mode
+    // slice) instead of two GEMM launches and a reduction per core (12-19 us per core: on the reference's own scaling
+    // sweep, examples/inner_product_scaling.py, d = 640 / r = 5 / n = 5 took 7.6 ms -- 3.0 ms this way; numpy on the
+    // host: 1.4 ms).  TTB_INNER_SMALL=0 disables; the slice budget keeps longer cores on the per-core GEMM path, where
+    // all SMs share a core.
+    static const bool small_enabled = [] {
+        const char* e = getenv("TTB_INNER_SMALL");
+        return e == nullptr || e[0] != '0';
+    }();
+    if (small_enabled && A.d >= 2 && A.d <= kBatchedMaxD) {
+        bool small = true;
+        int64_t slices = 0;
+        for (int k = 0; k <= A.d && small; ++k) small = A.r[k] <= 32 && B.r[k] <= 32;
+        for (int k = 0; k < A.d; ++k) slices += A.n[k];
+        if (small && slices <= int64_t(kSmallSlicesPerCore) * A.d) {
+            const TTBatchDesc ba{A.d, 1, A.n, A.r, A.core}, bb{B.d, 1, B.n, B.r, B.core};
+            return inner_batched(ba, bb, out_dev, ws, ws_bytes, stream);
+        }
+    }
     if (fused_enabled()) {
         // one persistent cooperative kernel for the whole sweep when every step is large: the TMA-staged
         // strip kernel for bond ranks <= 256, else the three-phase kernel

@@ -112,3 +112,25 @@ def test_errors():
     b = TensorTrain.rand([4, 5, 7], [2, 3], seed=2)
     with pytest.raises(AssertionError):
         a.inner(b)
+
+
+@pytest.mark.parametrize(
+    "d,n,r",
+    [
+        # BASELINE configs[0] = examples/inner_product_scaling.py (the reference's own CPU sweep): rank scaling at
+        # n = 20, d = 20 (the two largest ranks on fewer cores so that the numpy oracle finishes in seconds) ...
+        (20, 20, 10), (20, 20, 20), (20, 20, 40), (20, 20, 80), (20, 20, 160), (8, 20, 320), (4, 20, 640),
+        # ... mode-size scaling at r = 20, d = 20 ...
+        (20, 5, 20), (20, 160, 20), (20, 2560, 20),
+        # ... and dimension scaling at r = 5, n = 5 (cores scaled: the unscaled d = 640 product overflows fp64)
+        (5, 5, 5), (80, 5, 5), (640, 5, 5),
+    ],
+)
+def test_inner_reference_scaling_sweep(d, n, r):
+    rng = np.random.default_rng(4)  # the example seeds numpy with 4
+    a = orc.rand_tt([n] * d, [r] * (d - 1), rng)
+    b = orc.rand_tt([n] * d, [r] * (d - 1), rng)
+    ref = float(orc.inner(a, b))
+    got = float(_tt(a).inner(_tt(b)))
+    assert np.isfinite(ref) and ref != 0.0
+    assert abs(got - ref) <= RTOL * abs(ref), (got, ref)
