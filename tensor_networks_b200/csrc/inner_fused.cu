@@ -256,11 +256,12 @@ struct FusedPlan {
     double flops = 0.0;
 };
 
-bool plan_fused(const TTDesc& A, const TTDesc& B, FusedPlan* plan) {
+bool plan_fused(const TTDesc& A, const TTDesc& B, FusedPlan* plan, bool resident = false) {
     const int d = A.d;
     if (d < 2 || d != B.d) return false;
     const int sms = num_sms();
-    double min_step_flops = 1e300;
+    double min_step_flops = 1e300, min_tile_eff = 1.0;
+    int64_t max_rank = 0;
     plan->steps.resize(d);
     for (int k = 0; k < d; ++k) {
         if (A.n[k] != B.n[k]) return false;
@@ -277,7 +278,18 @@ bool plan_fused(const TTDesc& A, const TTDesc& B, FusedPlan* plan) {
         s.eb_order = c_eb <= c_ea;
         const double fl = 2.0 * std::min(c_eb, c_ea);
         plan->flops += (k == 0) ? 2.0 * n * a2 * b2 : fl;
-        if (k > 0 && k < d - 1) min_step_flops = std::min(min_step_flops, fl);
+        if (k > 0 && k < d - 1) {
+            min_step_flops = std::min(min_step_flops, fl);
+            max_rank = std::max(max_rank, std::max(std::max(a, a2), std::max(b, b2)));
+            // tile quantisation: both phases work on 128-row tiles (phase 2: 128 x 64) whatever the ranks are; the
+            // per-GEMM path picks its tile shapes per product.  Measured at n = 20, d = 20: r = 160 fused 0.82 ms /
+            // per GEMM 0.64 ms, r = 320 2.83 / 2.15 ms, r = 256 1.26 / 1.32 ms.
+            const double m1 = s.eb_order ? double(a) : double(b);
+            const double e1 = m1 / double(round_up<int64_t>(int64_t(m1), CfgT::BM));
+            const double e2 = double(a2) * double(b2) /
+                              (double(round_up<int64_t>(a2, CfgE::BM)) * double(round_up<int64_t>(b2, CfgE::BN)));
+            min_tile_eff = std::min(min_tile_eff, std::min(e1, e2));
+        }
         if (k < d - 1) {
             const int64_t K2 = (k == 0) ? n : (s.eb_order ? a * n : b * n);
             const int64_t tiles = ceil_div<int64_t>(a2, CfgE::BM) * ceil_div<int64_t>(b2, CfgE::BN);
@@ -296,6 +308,13 @@ bool plan_fused(const TTDesc& A, const TTDesc& B, FusedPlan* plan) {
     }
     plan->p_elems = std::max<size_t>(plan->p_elems, size_t(sms) + 8);
     // only worth a persistent grid when every interior step keeps 148 SMs busy for a while
+    // With the operands resident in HBM the three-phase kernel only pays around bond rank 256 (configs[1]: 5.10 ms
+    // against 5.30 ms for one GEMM launch per product); for larger ranks the per-GEMM path, whose tile engine was
+    // tuned further in round 2, is 5 - 22 % faster (d = 8, n = 64, r = 640: 12.9 against 16.6 ms = 31 TFLOP/s;
+    // tools/prof_inner_ranks.py).  The streamed mode keeps it for every rank: overlapping the host-to-device copies
+    // needs a persistent kernel that polls the per-core ready flags.
+    // (and there only from ~20 mode slices per core on: d = 20, r = 256: n = 16 1.19 against 0.99 ms, n = 20 1.26 against 1.32 ms)
+    if (resident && (max_rank > 256 || min_tile_eff < 0.9 || min_step_flops < 1.3e9)) return false;
     return d >= 3 && min_step_flops >= 2.0e8;
 }
 
@@ -316,7 +335,7 @@ size_t inner_fused_workspace_bytes(const TTDesc& a, const TTDesc& b) {
 int inner_fused(const TTDesc& A, const TTDesc& B, double* out_dev, void* ws, size_t ws_bytes, cudaStream_t stream,
                 const int* ready_dev, int* fail_dev) {
     FusedPlan pl;
-    if (!plan_fused(A, B, &pl)) return kUnsupported;
+    if (!plan_fused(A, B, &pl, /*resident=*/ready_dev == nullptr)) return kUnsupported;
     if (ws == nullptr || ws_bytes < fused_bytes(pl, A.d)) return kUnsupported;
     // which instantiation runs: plain, in-kernel timing (TTB_SWEEP_TIMING), or streamed (per-core ready flags)
     static const bool sweep_timing = getenv("TTB_SWEEP_TIMING") != nullptr;
