@@ -283,7 +283,7 @@ int inner_batched_tma(const TTBatchDesc& a, const TTBatchDesc& b, double* out_de
         if ((reinterpret_cast<uintptr_t>(a.core[k]) & 15) || (reinterpret_cast<uintptr_t>(b.core[k]) & 15)) return kOk;
         if (a.n[k] > (1 << 20)) return kOk;
     }
-    static BtParams p;  // 16 KB of kernel parameters: built in place (one host thread per process, see DESIGN limits)
+    static thread_local BtParams p;  // 17 KB of kernel parameters, built in place (per host thread)
     p.d = d;
     p.batch = a.batch;
     for (int k = 0; k < d; ++k) p.n[k] = int(a.n[k]);

@@ -40,7 +40,7 @@ extern "C" {
 
 const char* ttb_version(void) { return "ttb200 0.1.0 (sm_100a, fp64 DMMA)"; }
 const char* ttb_last_error(void) { return ttb::last_error_cstr(); }
-uint64_t ttb_launch_count(void) { return ttb::g_launch_count; }
+uint64_t ttb_launch_count(void) { return ttb::g_launch_count.load(); }
 // debug aid for tools/ (not declared in the public header)
 double ttb_debug_chol_bench_us(int w, int reps) { return ttb::debug_chol_bench_us(w, reps); }
 

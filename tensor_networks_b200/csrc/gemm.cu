@@ -17,7 +17,7 @@
 
 namespace ttb {
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 // ---- optional per-launch timing of the dgemm kernels (bench.py roofline) ----
 namespace {

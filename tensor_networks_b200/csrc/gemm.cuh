@@ -8,6 +8,8 @@
 // the tall-skinny QR, and the TT-SVD projections.
 #pragma once
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace ttb {
@@ -62,6 +64,6 @@ int profile_begin(cudaStream_t stream);
 void profile_end(int slot, double flops, cudaStream_t stream);
 
 // number of kernels launched by gemm() so far (bench.py's gpu_launches)
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;  // kernels launched by the library (any host thread)
 
 }  // namespace ttb

@@ -18,6 +18,7 @@
 #include "batched.cuh"
 
 #include <algorithm>
+#include <mutex>
 #include <cstdlib>
 #include <vector>
 
@@ -106,6 +107,9 @@ size_t inner_streamed_workspace_bytes(const TTDesc& a, const TTDesc& b) {
 
 int inner_streamed(const TTDesc& A, const TTDesc& B, const double* const* a_host, const double* const* b_host,
                    double* out_dev, void* ws, size_t ws_bytes, cudaStream_t stream, cudaStream_t copy_stream) {
+    // the host staging ring and its worker threads are shared: streamed calls are serialised
+    static std::mutex streamed_mutex;
+    std::lock_guard<std::mutex> streamed_lock(streamed_mutex);
     TTB_PROPAGATE(validate(A, "inner_streamed: A"));
     TTB_PROPAGATE(validate(B, "inner_streamed: B"));
     TTB_REQUIRE(A.d == B.d && a_host && b_host && out_dev, "inner_streamed: bad arguments");
@@ -117,7 +121,7 @@ int inner_streamed(const TTDesc& A, const TTDesc& B, const double* const* a_host
     char* rest = static_cast<char*>(ws) + flag_bytes;
     const size_t rest_bytes = ws_bytes - flag_bytes;
 
-    static cudaEvent_t ev_reset = nullptr, ev_copied = nullptr;
+    static thread_local cudaEvent_t ev_reset = nullptr, ev_copied = nullptr;
     if (!ev_reset) {
         TTB_CHECK_CUDA(cudaEventCreateWithFlags(&ev_reset, cudaEventDisableTiming));
         TTB_CHECK_CUDA(cudaEventCreateWithFlags(&ev_copied, cudaEventDisableTiming));

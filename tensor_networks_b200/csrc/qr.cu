@@ -1165,7 +1165,7 @@ struct OrthHost {
     double* status = nullptr;            // pinned, 4 doubles
 };
 int orth_host(OrthHost* h) {
-    static OrthHost g;
+    static thread_local OrthHost g;  // pinned scratch per host thread
     if (!g.flag) {
         void* p = nullptr;
         TTB_CHECK_CUDA(cudaHostAlloc(&p, 64, cudaHostAllocDefault));
@@ -1723,7 +1723,7 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
         return e == nullptr || e[0] != '0';
     }();
     static const bool debug = getenv("TTB_DEBUG") != nullptr;
-    static std::map<std::tuple<int64_t, int64_t, bool>, OrthPlan> plans;
+    static thread_local std::map<std::tuple<int64_t, int64_t, bool>, OrthPlan> plans;  // recorded plans: per host thread
     OrthPlan& plan = plans[std::make_tuple(c, m, deflate_tol > 0.0)];
     const OrthLayout L = orth_layout(c, m);
     if (debug)
@@ -1750,8 +1750,8 @@ int orth_rows(double* M, int64_t c, int64_t m, int64_t ldm, double* R, int64_t l
             return e == nullptr || e[0] != '0';
         }();
         if (graph_enabled && !debug && !prof_enabled() && !gemm_profile_active()) {
-            static std::map<std::tuple<int64_t, int64_t, bool>, OrthGraph> graphs;
-            static cudaStream_t cap_stream = nullptr;
+            static thread_local std::map<std::tuple<int64_t, int64_t, bool>, OrthGraph> graphs;
+            static thread_local cudaStream_t cap_stream = nullptr;
             if (graphs.size() > 64 && graphs.find(std::make_tuple(c, m, deflate_tol > 0.0)) == graphs.end()) {
                 // many distinct shapes (e.g. a long solver run): start over rather than grow without bound
                 for (auto& kv : graphs)

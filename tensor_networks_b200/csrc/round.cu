@@ -50,8 +50,9 @@ struct PhaseTimer {
         return ms;
     }
 };
-double g_t_qr = 0, g_t_jac = 0, g_t_rest = 0, g_t_rq = 0, g_t_push = 0;
-int g_cert_skip = 0, g_cert_backoff = 0;  // certificate back-off (see trunc_svd)
+// (per host thread: concurrent sweeps from several threads, each on its own stream and workspace, do not share state)
+thread_local double g_t_qr = 0, g_t_jac = 0, g_t_rest = 0, g_t_rq = 0, g_t_push = 0;
+thread_local int g_cert_skip = 0, g_cert_backoff = 0;  // certificate back-off (see trunc_svd)
 
 __global__ void transpose_kernel(const double* __restrict__ in, int64_t rows, int64_t cols, int64_t ldi,
                                  double* __restrict__ out, int64_t ldo) {
@@ -83,7 +84,7 @@ struct HostWords {
     double* info = nullptr;              // pinned, 4 doubles
 };
 int host_words(HostWords* hw) {
-    static HostWords g;
+    static thread_local HostWords g;  // pinned scratch per host thread
     if (!g.conv) {
         void* p = nullptr;
         TTB_CHECK_CUDA(cudaHostAlloc(&p, 1024, cudaHostAllocDefault));
@@ -182,7 +183,7 @@ struct SkinnyHost {
 int skinny_lq(const double* Xsrc, double* Y, int64_t m, int64_t c, double* Rm, double* L2inv_dev, void* sub, size_t rest,
               cudaStream_t stream, bool* handled) {
     *handled = false;
-    static SkinnyHost sh;
+    static thread_local SkinnyHost sh;
     if (!sh.buf) {
         void* p = nullptr;
         TTB_CHECK_CUDA(cudaHostAlloc(&p, 6 * 256 * sizeof(double), cudaHostAllocDefault));

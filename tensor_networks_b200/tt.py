@@ -18,6 +18,7 @@ libttb200.so.
 from __future__ import annotations
 
 import math
+import threading
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -30,8 +31,10 @@ _WORKSPACES: dict = {}
 
 
 def workspace(nbytes: int, device: torch.device, slot: str = "main") -> torch.Tensor:
-    """A cached, grow-only uint8 scratch buffer per (device, slot)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
+    """A cached, grow-only uint8 scratch buffer per (device, slot, host thread, current stream): calls from several
+    threads or on several streams never share scratch memory."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), slot, threading.get_ident(),
+           torch.cuda.current_stream().cuda_stream)
     buf = _WORKSPACES.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = None
