@@ -410,7 +410,7 @@ __device__ bool cholqr_tile(double* __restrict__ As, int ww, int hlen, double de
                 sc.dsv[j] = flagged ? 1.0 : d;
             }
             if (!flagged) {
-                const double invd = 1.0 / d;
+                const double invd = fast_rcp3(d);  // d > 0, finite and normal here; 2^-58 accurate, a third of the latency of the division
                 double ci[2], ck[2];
 #pragma unroll
                 for (int ii = 0; ii < 2; ++ii) ci[ii] = cb[ty + 16 * ii] * invd;
