@@ -99,17 +99,28 @@ class PeerGather:
             self.tensor = torch.empty(self.batch, dtype=dtype, device=device)
             self.why_not = "symmetric memory needs CUDA devices of one node (at most 8 ranks)"
             return
+        # Two steps, with agreement in between: the allocation is local and may fail on one rank only (then NO rank
+        # may enter the rendezvous, which is a collective over the group's store and would wait for the missing rank).
+        buf, err = None, None
         try:
             import torch.distributed._symmetric_memory as symm_mem
 
-            self.tensor = symm_mem.empty(self.batch, dtype=dtype, device=device)
-            self.handle = symm_mem.rendezvous(self.tensor, group if group is not None else dist.group.WORLD)
-            self.ptrs = [int(x) for x in self.handle.buffer_ptrs]
-        except Exception as exc:  # no peer mapping on this box: fall back to the collective
+            buf = symm_mem.empty(self.batch, dtype=dtype, device=device)
+        except Exception as exc:
+            err = f"{type(exc).__name__}: {exc}"
+        ok = torch.tensor([1 if buf is not None else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 1:
+            try:
+                self.handle = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+                self.ptrs = [int(x) for x in self.handle.buffer_ptrs]
+                self.tensor = buf
+            except Exception as exc:  # no peer mapping on this box (the same on every rank): the collective path
+                err = f"{type(exc).__name__}: {exc}"
+                self.handle, self.ptrs = None, None
+        if self.ptrs is None:
             self.tensor = torch.empty(self.batch, dtype=dtype, device=device)
-            self.handle = None
-            self.ptrs = None
-            self.why_not = f"{type(exc).__name__}: {exc}"
+            self.why_not = err or "symmetric memory allocation failed on another rank"
 
     @property
     def fused(self) -> bool:
