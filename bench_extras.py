@@ -463,6 +463,8 @@ def run_batched(batch=8192, d=20, n=8, r=32, eps=1e-8, steps=5, rank=0, world=1,
     # ---- optional: all-gather of the rounded cores (north_star item 4) ----
     gather = None
     if gather_cores:
+        from tensor_networks_b200.sharding import gathered_cores_numel
+
         zc = clones[-1]
         full = all_gather_cores(zc, batch, ranks)  # warm-up
         barrier()
@@ -473,7 +475,30 @@ def run_batched(batch=8192, d=20, n=8, r=32, eps=1e-8, steps=5, rank=0, world=1,
         ms_g = sync_max(e0.elapsed_time(e1))
         gbytes = sum(c.numel() * 8 for c in full.cores)
         gather = {"ms": ms_g, "bytes_gathered_per_rank": int(gbytes), "gbs": gbytes / (ms_g * 1e-3) / 1e9,
-                  "layout": "uniform zero-padded (batch, r_cap, n, r_cap) per core: pack kernel + one NCCL all-gather per core"}
+                  "path": "pack kernel + one NCCL all-gather per core" if world > 1 else "pack kernel (single GPU)",
+                  "layout": "uniform zero-padded (batch, r_cap, n, r_cap) per core"}
+        if world > 1:
+            # fused: the pack kernel stores every core straight into all ranks' arenas over NVLink (symmetric memory)
+            arena = PeerGather(gathered_cores_numel(zc, batch, ranks))
+            ok_t = torch.tensor([1 if (arena.fused and arena.handle is not None) else 0], device="cuda")
+            dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+            if int(ok_t.item()) == 1:
+                ff = all_gather_cores(zc, batch, ranks, arena=arena)  # warm-up
+                barrier()
+                same = all(bool(torch.equal(x, y_)) for x, y_ in zip(ff.cores, full.cores))
+                e0.record()
+                ff = all_gather_cores(zc, batch, ranks, arena=arena)
+                e1.record()
+                barrier()
+                ms_f = sync_max(e0.elapsed_time(e1))
+                gather.update({"ms_nccl_variant": ms_g, "ms": ms_f, "gbs": gbytes / (ms_f * 1e-3) / 1e9,
+                               "equal_to_nccl_variant": same,
+                               "path": "fused: the pack kernel of each core stores into every rank's arena over NVLink "
+                                       "(symmetric memory), one signal barrier at the end; no collective"})
+                del ff
+            else:
+                gather["fused_unavailable"] = arena.why_not or "symmetric memory unavailable on some rank"
+            del arena
         del full
     fp = fp64_peak() if world == 1 else FP64_NOMINAL_TFLOPS
     res = {

@@ -262,6 +262,12 @@ int ttb_diag_f64(const double* s, int64_t n, double* out, void* stream);
  * scalar and core results"). */
 int ttb_pack_rounded_cores_f64(const double* core, int64_t batch, int64_t slab, int64_t n, const int64_t* ranks_dev,
                                int32_t d, int32_t k, int64_t RL, int64_t RR, double* out, void* stream);
+/* Sharded form: the packed core of this shard is stored straight into EVERY rank's gathered array
+ * out_peers[r] (total_batch, RL, n, RR), item i at row item_offset + i -- pack and all-gather of the rounded cores
+ * are one kernel over NVLink peer memory (n_peers <= 8); the ranks meet at a barrier before reading. */
+int ttb_pack_rounded_cores_scatter_f64(const double* core, int64_t batch, int64_t slab, int64_t n, const int64_t* ranks_dev,
+                                       int32_t d, int32_t k, int64_t RL, int64_t RR, double* const* out_peers, int32_t n_peers,
+                                       int64_t item_offset, void* stream);
 /* y = alpha * x + beta * y over count elements (x may be NULL: y *= beta): TensorNetwork.scale
  * (pytens/algs.py:578-583) and the one-node case of TensorNetwork.__add__ */
 int ttb_axpby_f64(int64_t count, double alpha, const double* x, double beta, double* y, void* stream);

@@ -174,6 +174,11 @@ def _declare(lib):
     lib.ttb_pack_rounded_cores_f64.argtypes = [
         c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p,
     ]
+    lib.ttb_pack_rounded_cores_scatter_f64.restype = c_int
+    lib.ttb_pack_rounded_cores_scatter_f64.argtypes = [
+        c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int32, c_int32, c_int64, c_int64, P(c_void_p), c_int32, c_int64,
+        c_void_p,
+    ]
     lib.ttb_axpby_f64.restype = c_int
     lib.ttb_axpby_f64.argtypes = [c_int64, c_double, c_void_p, c_double, c_void_p, c_void_p]
 

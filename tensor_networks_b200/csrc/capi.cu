@@ -302,6 +302,16 @@ int ttb_pack_rounded_cores_f64(const double* core, int64_t batch, int64_t slab, 
                                int32_t d, int32_t k, int64_t RL, int64_t RR, double* out, void* stream) {
     return ttb::pack_rounded_cores(core, batch, slab, n, ranks_dev, d, k, RL, RR, out, as_stream(stream));
 }
+int ttb_pack_rounded_cores_scatter_f64(const double* core, int64_t batch, int64_t slab, int64_t n, const int64_t* ranks_dev,
+                                       int32_t d, int32_t k, int64_t RL, int64_t RR, double* const* out_peers, int32_t n_peers,
+                                       int64_t item_offset, void* stream) {
+    if (!out_peers) {
+        ttb::set_last_error("ttb_pack_rounded_cores_scatter_f64: null peer list");
+        return TTB_INVALID_ARGUMENT;
+    }
+    return ttb::pack_rounded_cores_scatter(core, batch, slab, n, ranks_dev, d, k, RL, RR, out_peers, n_peers, item_offset,
+                                           as_stream(stream));
+}
 int ttb_axpby_f64(int64_t count, double alpha, const double* x, double beta, double* y, void* stream) {
     return ttb::axpby(count, alpha, x, beta, y, as_stream(stream));
 }

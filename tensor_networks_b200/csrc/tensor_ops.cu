@@ -139,16 +139,28 @@ __global__ void __launch_bounds__(256) axpby_kernel(int64_t count, double alpha,
 // rl_i = ranks[i * (d + 1) + k], rr_i = ranks[i * (d + 1) + k + 1] (what ttb_round_batched_f64 leaves);
 // out is (batch, RL, n, RR) with zeros beyond the item's own ranks -- a valid core of bond ranks
 // (RL, RR) for every item, so that the cores of a whole batch can be all-gathered as one array.
+// One item per blockIdx.y step, 32-bit index arithmetic inside an item (the first version decomposed a flat 64-bit
+// index with five divisions per element: 100 GB/s).  With peers the packed core goes straight into EVERY rank's
+// gathered array over NVLink (item i at row item_offset + i): pack and all-gather are one kernel.
+struct PackPeers {
+    double* out[8];
+    int count;
+    int64_t item_offset;
+};
 __global__ void __launch_bounds__(256) pack_rounded_kernel(const double* __restrict__ core, int64_t batch, int64_t slab,
-                                                           int64_t n, const int64_t* __restrict__ ranks, int d, int k,
-                                                           int64_t RL, int64_t RR, double* __restrict__ out) {
-    const int64_t per = RL * n * RR, total = batch * per;
-    for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-         idx += int64_t(gridDim.x) * blockDim.x) {
-        const int64_t i = idx / per, rem = idx % per;
-        const int64_t a = rem / (n * RR), jn = (rem / RR) % n, b = rem % RR;
-        const int64_t rl = ranks[i * (d + 1) + k], rr = ranks[i * (d + 1) + k + 1];
-        out[idx] = (a < rl && b < rr) ? core[i * slab + (a * n + jn) * rr + b] : 0.0;
+                                                           int n, const int64_t* __restrict__ ranks, int d, int k,
+                                                           int RL, int RR, PackPeers pp) {
+    const int per = RL * n * RR, row = n * RR;
+    for (int64_t i = blockIdx.y; i < batch; i += gridDim.y) {
+        const int rl = int(ranks[i * (d + 1) + k]), rr = int(ranks[i * (d + 1) + k + 1]);
+        const double* __restrict__ src = core + i * slab;
+        const int64_t obase = (pp.item_offset + i) * per;
+        for (int rem = blockIdx.x * blockDim.x + threadIdx.x; rem < per; rem += gridDim.x * blockDim.x) {
+            const int a = rem / row, r2 = rem - a * row;
+            const int jn = r2 / RR, b = r2 - jn * RR;
+            const double v = (a < rl && b < rr) ? src[(a * n + jn) * rr + b] : 0.0;
+            for (int r = 0; r < pp.count; ++r) pp.out[r][obase + rem] = v;
+        }
     }
 }
 
@@ -260,15 +272,35 @@ int diag_embed(const double* s, int64_t n, double* out, cudaStream_t stream) {
     return kOk;
 }
 
-int pack_rounded_cores(const double* core, int64_t batch, int64_t slab, int64_t n, const int64_t* ranks_dev, int d,
-                       int k, int64_t RL, int64_t RR, double* out, cudaStream_t stream) {
+int pack_rounded_cores_scatter(const double* core, int64_t batch, int64_t slab, int64_t n, const int64_t* ranks_dev, int d,
+                               int k, int64_t RL, int64_t RR, double* const* peers, int n_peers, int64_t item_offset,
+                               cudaStream_t stream) {
     if (batch <= 0) return kOk;
-    TTB_REQUIRE(core && ranks_dev && out, "pack_rounded_cores: null pointer");
+    TTB_REQUIRE(core && ranks_dev && peers, "pack_rounded_cores: null pointer");
     TTB_REQUIRE(k >= 0 && k < d && n >= 1 && RL >= 1 && RR >= 1 && slab >= 1, "pack_rounded_cores: bad extents");
-    pack_rounded_kernel<<<grid_for(batch * RL * n * RR), 256, 0, stream>>>(core, batch, slab, n, ranks_dev, d, k, RL, RR, out);
+    TTB_REQUIRE(n_peers >= 1 && n_peers <= 8 && item_offset >= 0, "pack_rounded_cores: bad peer list");
+    TTB_REQUIRE(RL * n * RR < (int64_t(1) << 30), "pack_rounded_cores: item too large");
+    PackPeers pp{};
+    pp.count = n_peers;
+    pp.item_offset = item_offset;
+    for (int r = 0; r < n_peers; ++r) {
+        TTB_REQUIRE(peers[r] != nullptr, "pack_rounded_cores: null peer buffer");
+        pp.out[r] = peers[r];
+    }
+    const int per = int(RL * n * RR);
+    const int gx = std::max(1, std::min(ceil_div(per, 256), 8));
+    const int gy = int(std::min<int64_t>(batch, std::max<int64_t>(1, int64_t(num_sms()) * 16 / gx)));
+    pack_rounded_kernel<<<dim3(gx, gy), 256, 0, stream>>>(core, batch, slab, int(n), ranks_dev, d, k, int(RL), int(RR), pp);
     ++g_launch_count;
     TTB_CHECK_CUDA(cudaGetLastError());
     return kOk;
+}
+
+int pack_rounded_cores(const double* core, int64_t batch, int64_t slab, int64_t n, const int64_t* ranks_dev, int d,
+                       int k, int64_t RL, int64_t RR, double* out, cudaStream_t stream) {
+    TTB_REQUIRE(out != nullptr || batch <= 0, "pack_rounded_cores: null pointer");
+    double* one[1] = {out};
+    return pack_rounded_cores_scatter(core, batch, slab, n, ranks_dev, d, k, RL, RR, one, 1, 0, stream);
 }
 
 int axpby(int64_t count, double alpha, const double* x, double beta, double* y, cudaStream_t stream) {

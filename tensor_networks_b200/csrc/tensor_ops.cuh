@@ -18,6 +18,10 @@ int scale_rows(double* mat, int64_t rows, int64_t cols, int64_t ld, const double
 // out (n x n, row-major) = diag(s)
 int diag_embed(const double* s, int64_t n, double* out, cudaStream_t stream);
 // compact per-item rounded cores of a batch -> uniform zero-padded (batch, RL, n, RR) array (see tensor_ops.cu)
+// (peers: every rank's gathered array (total_batch, RL, n, RR); item i of this shard lands at row item_offset + i of each)
+int pack_rounded_cores_scatter(const double* core, int64_t batch, int64_t slab, int64_t n, const int64_t* ranks_dev, int d,
+                               int k, int64_t RL, int64_t RR, double* const* peers, int n_peers, int64_t item_offset,
+                               cudaStream_t stream);
 int pack_rounded_cores(const double* core, int64_t batch, int64_t slab, int64_t n, const int64_t* ranks_dev, int d,
                        int k, int64_t RL, int64_t RR, double* out, cudaStream_t stream);
 // y = alpha x + beta y (x may be null: y *= beta)

@@ -197,12 +197,55 @@ def all_gather_padded_cores(cores_local: Sequence[torch.Tensor], batch: int,
     return [all_gather_items(c, batch, group) for c in cores_local]
 
 
-def all_gather_cores(y_local, batch: int, table: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
+def gathered_cores_numel(y_local, batch: int, table: torch.Tensor) -> int:
+    """Elements of the uniform padded layout of the whole batch (the size of the `arena` of all_gather_cores)."""
+    rcap = padded_ranks(table)
+    return sum(int(batch) * rcap[k] * int(c.shape[2]) * rcap[k + 1] for k, c in enumerate(y_local.cores))
+
+
+def all_gather_cores(y_local, batch: int, table: torch.Tensor, group: Optional[dist.ProcessGroup] = None,
+                     arena: Optional[PeerGather] = None):
     """The rounded cores of every shard on every rank, as a `TensorTrainBatch` whose bond ranks are the
-    batch-wide maxima (items with smaller ranks are zero-padded): pack kernel + one NCCL all-gather per
-    core (cfg5: 8192 items, ranks 16 -> about 0.31 GB gathered instead of the 9.7 GB of raw slabs)."""
+    batch-wide maxima (items with smaller ranks are zero-padded; cfg5: 8192 items, ranks 16 -> 2.3 GB instead of
+    the 9.7 GB of raw slabs).
+
+    With an `arena` (a `PeerGather` of at least gathered_cores_numel() doubles whose buffers are peer-mapped) the pack
+    kernel of every core stores its output straight into EVERY rank's arena over NVLink
+    (`ttb_pack_rounded_cores_scatter_f64`): pack and all-gather are one kernel per core and the ranks meet at one
+    signal barrier at the end; the returned cores are views of the arena (valid until it is written again).
+    Otherwise: pack kernel + one NCCL all-gather per core."""
     from .batch import TensorTrainBatch
 
     rcap = padded_ranks(table)
+    if arena is not None and arena.fused:
+        import ctypes
+
+        from . import _lib
+        from ._lib import check
+        from .tt import _stream_ptr
+
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        lo, hi = shard_range(batch, rank, world)
+        if y_local.batch != hi - lo:
+            raise ValueError(f"rank {rank}: expected {hi - lo} local items, got {y_local.batch}")
+        if y_local.item_ranks is None:
+            raise RuntimeError("all_gather_cores: the batch has not been rounded")
+        if arena.tensor.numel() < gathered_cores_numel(y_local, batch, table) or arena.tensor.dtype != torch.float64:
+            raise ValueError("all_gather_cores: arena too small (see gathered_cores_numel) or not float64")
+        L = _lib.lib()
+        d, nloc = y_local.d, y_local.batch
+        full, off = [], 0
+        for k, c in enumerate(y_local.cores):
+            n = int(c.shape[2])
+            slab = int(c.shape[1]) * n * int(c.shape[3])
+            cnt = int(batch) * rcap[k] * n * rcap[k + 1]
+            ptrs = (ctypes.c_void_p * len(arena.ptrs))(*[int(p) + 8 * off for p in arena.ptrs])
+            check(L.ttb_pack_rounded_cores_scatter_f64(c.data_ptr(), nloc, slab, n, y_local.item_ranks.data_ptr(), d, k,
+                                                       rcap[k], rcap[k + 1], ptrs, len(arena.ptrs), lo, _stream_ptr()))
+            full.append(arena.tensor[off : off + cnt].view(int(batch), rcap[k], n, rcap[k + 1]))
+            off += cnt
+        arena.barrier()
+        return TensorTrainBatch(full)
     full = all_gather_padded_cores(pack_rounded(y_local, rcap), batch, group)
     return TensorTrainBatch(full)

@@ -216,3 +216,10 @@ def test_pack_rounded_cores_uniform_layout():
         assert np.linalg.norm(got - want) <= 1e-9 * np.linalg.norm(want)
     same = all_gather_cores(y, 6, table)
     assert all(torch.equal(a, b) for a, b in zip(same.cores, full.cores))
+    # the fused path (pack kernel stores into every rank's arena) with this process as its only peer
+    from tensor_networks_b200.sharding import PeerGather, gathered_cores_numel
+
+    arena = PeerGather(gathered_cores_numel(y, 6, table) + 3)
+    fused = all_gather_cores(y, 6, table, arena=arena)
+    assert all(torch.equal(a, b) for a, b in zip(fused.cores, full.cores))
+    assert fused.cores[0].data_ptr() == arena.tensor.data_ptr()
