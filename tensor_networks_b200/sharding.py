@@ -151,17 +151,18 @@ def inner_sharded(a_local, b_local, batch: int, group: Optional[dist.ProcessGrou
 
 
 def round_sharded(y_local, eps: float, batch: int, max_rank: Optional[int] = None,
-                  group: Optional[dist.ProcessGroup] = None, gather_cores: bool = False):
+                  group: Optional[dist.ProcessGroup] = None, gather_cores: bool = False, arena=None):
     """Round every local item in place and all-gather the (batch, d+1) rank table.
 
     By default the rounded cores stay sharded (they are what the next local step consumes).  With
     `gather_cores` the cores are all-gathered as well and a full `TensorTrainBatch` is returned next to
-    the table (north_star item 4: "all-gather of scalar and core results")."""
+    the table (north_star item 4: "all-gather of scalar and core results"); with an `arena` (see all_gather_cores) the
+    pack kernel gathers them over NVLink peer memory itself."""
     y_local.round(eps, max_rank=max_rank)
     table = all_gather_items(y_local.item_ranks, batch, group)
     if not gather_cores:
         return table
-    return table, all_gather_cores(y_local, batch, table, group)
+    return table, all_gather_cores(y_local, batch, table, group, arena=arena)
 
 
 def padded_ranks(table: torch.Tensor) -> List[int]:
