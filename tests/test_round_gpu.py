@@ -179,3 +179,29 @@ def test_round_medium_rank_vs_oracle():
     z2 = z.clone().round(1e-8)
     assert z2.ranks() == z.ranks()
     assert abs(float(z2.inner(z)) / (z2.norm() * nz) - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("scale", [1e-6, 1e-9, 1e-11])
+def test_round_under_cancellation_matches_reference(scale):
+    """A formal sum with heavy cancellation, x + (-x) + scale * z (the shape of a GMRES residual b - A x): the rows that
+    deflation drops are exact dependencies, so ranks and accuracy stay those of the reference's LAPACK path -- also
+    where the reference itself degrades (scale = 1e-11: both keep noise ranks and lose five digits)."""
+    from tensor_networks_b200 import TensorTrain
+
+    rng = np.random.default_rng(7)
+    shape = [8] * 6
+    x = orc.rand_tt(shape, [6] * 5, rng)
+    z = orc.rand_tt(shape, [4] * 5, rng)
+    xm = [c.copy() for c in x]
+    xm[0] = -xm[0]
+    zs = [c.copy() for c in z]
+    zs[0] = zs[0] * scale
+    y = orc.tt_add(orc.tt_add(x, xm), zs)
+    want = orc.to_dense(zs)
+    ref_cores, _ = orc.svd_round([c.copy() for c in y], 1e-6)
+    ref_err = np.linalg.norm(orc.to_dense(ref_cores) - want) / np.linalg.norm(want)
+    t = TensorTrain.from_cores(y)
+    t.round(1e-6)
+    err = np.linalg.norm(t.dense() - want) / np.linalg.norm(want)
+    assert t.ranks() == orc.ranks_of(ref_cores)
+    assert err <= 2.0 * ref_err + 1e-10
