@@ -308,13 +308,18 @@ bool plan_fused(const TTDesc& A, const TTDesc& B, FusedPlan* plan, bool resident
     }
     plan->p_elems = std::max<size_t>(plan->p_elems, size_t(sms) + 8);
     // only worth a persistent grid when every interior step keeps 148 SMs busy for a while
-    // With the operands resident in HBM the three-phase kernel only pays around bond rank 256 (configs[1]: 5.10 ms
-    // against 5.30 ms for one GEMM launch per product); for larger ranks the per-GEMM path, whose tile engine was
-    // tuned further in round 2, is 5 - 22 % faster (d = 8, n = 64, r = 640: 12.9 against 16.6 ms = 31 TFLOP/s;
-    // tools/prof_inner_ranks.py).  The streamed mode keeps it for every rank: overlapping the host-to-device copies
-    // needs a persistent kernel that polls the per-core ready flags.
-    // (and there only from ~20 mode slices per core on: d = 20, r = 256: n = 16 1.19 against 0.99 ms, n = 20 1.26 against 1.32 ms)
-    if (resident && (max_rank > 256 || min_tile_eff < 0.9 || min_step_flops < 1.3e9)) return false;
+    // With the operands resident in HBM the per-GEMM path, whose tile engine was tuned further in round 2, is as fast or
+    // faster on every shape measured (tools/prof_inner_ranks.py): bond ranks above 256 by 5 - 22 % (d = 8, n = 64, r = 640:
+    // 12.9 against 16.6 ms = 31 TFLOP/s), ranks off the 128-row tile grid by 20 - 30 %, r = 256 between -5 % (n = 20) and
+    // +8 % (n = 48) -- and the TMA strip kernel takes the shapes where a persistent sweep pays (configs[1]: 4.75 ms against
+    // 5.10 ms here and 5.30 ms per GEMM).  The three-phase kernel therefore only serves the streamed mode, where
+    // overlapping the host-to-device copies needs a persistent kernel that polls the per-core ready flags
+    // (TTB_INNER_FUSED3=1 re-enables it for resident operands).
+    const char* f3 = getenv("TTB_INNER_FUSED3");  // read on every call, so a test can switch inside one process
+    const bool resident_enabled = f3 != nullptr && f3[0] == '1';
+    (void)max_rank;
+    (void)min_tile_eff;
+    if (resident && !resident_enabled) return false;
     return d >= 3 && min_step_flops >= 2.0e8;
 }
 

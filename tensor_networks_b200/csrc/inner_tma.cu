@@ -426,6 +426,7 @@ bool plan_tma(const TTDesc& A, const TTDesc& B, TmaPlan* plan) {
     if (d < 3 || d != B.d) return false;
     plan->eb.assign(d, 1);
     int64_t min_tiles = 1 << 30, min_rank = 1 << 30;
+    double min_wave_eff = 1.0;
     for (int k = 0; k < d; ++k) {
         if (A.n[k] != B.n[k]) return false;
         if (!aligned16(A.core[k]) || !aligned16(B.core[k])) return false;
@@ -445,6 +446,8 @@ bool plan_tma(const TTDesc& A, const TTDesc& B, TmaPlan* plan) {
             const int64_t K2 = plan->eb[k] ? b2 : a2;
             const int64_t tiles = ceil_div<int64_t>(n * K2, TW);
             min_tiles = std::min(min_tiles, tiles);
+            const int64_t sms = num_sms();
+            min_wave_eff = std::min(min_wave_eff, double(tiles) / double(ceil_div<int64_t>(tiles, sms) * sms));
             plan->p_elems = std::max<size_t>(plan->p_elems, size_t(tiles) * P_TILE);
         }
     }
@@ -453,7 +456,10 @@ bool plan_tma(const TTDesc& A, const TTDesc& B, TmaPlan* plan) {
     // rows of the 256-row warp layout that are padding are wasted DMMA issue slots; fewer strips than SMs idle them
     // (tools/tma_dispatch_sweep.py on B200: the strip kernel wins from rank 224 up with >= 128 strips; at rank 200
     // or with ~110 strips or fewer the three-phase kernel is 2-30 % faster)
-    return min_rank >= 208 && min_tiles >= (3 * num_sms()) / 4;
+    // Strips are dealt out in waves of one per SM: 220 strips (n = 48, r = 256) take as long as 293 (n = 64) -- with less
+    // than 85 % of the last wave used the per-GEMM path is faster (n = 48: 1.29 against 1.47 ms at d = 12, r = 256;
+    // tools/prof_inner_ranks.py).
+    return min_rank >= 208 && min_tiles >= (3 * num_sms()) / 4 && min_wave_eff >= 0.85;
 }
 
 size_t tma_bytes(const TmaPlan& pl, int d) {

@@ -126,3 +126,22 @@ def test_tma_sweep_streamed(monkeypatch):
     # pageable numpy cores through the drop-in entry point
     got = float(TensorTrain.inner_host(a, b))
     assert abs(got - ref) <= RTOL * abs(ref), (got, ref)
+
+
+def test_three_phase_kernel_resident_parity(monkeypatch):
+    """The three-phase persistent kernel (inner_fused.cu) serves the streamed mode by default; TTB_INNER_FUSED3=1 runs
+    it on resident operands: one launch, same value as the oracle and as the default (per-GEMM) dispatch."""
+    rng = np.random.default_rng(21)
+    shape, r = [24] * 6, [320] * 5
+    a, b = _scaled(shape, r, rng), _scaled(shape, r, rng)
+    ref = float(orc.inner(a, b))
+    ta, tb = _tt(a), _tt(b)
+    monkeypatch.delenv("TTB_INNER_FUSED3", raising=False)
+    l0 = _launches()
+    base = float(ta.inner(tb))
+    assert _launches() - l0 > 1  # one launch per GEMM
+    monkeypatch.setenv("TTB_INNER_FUSED3", "1")
+    l0 = _launches()
+    got = float(ta.inner(tb))
+    assert _launches() - l0 == 1
+    assert abs(got - ref) <= RTOL * abs(ref) and abs(base - ref) <= RTOL * abs(ref)
