@@ -13,6 +13,7 @@
 #include "gemm_tile.cuh"
 
 #include <algorithm>
+#include <unordered_map>
 #include <vector>
 
 namespace ttb {
@@ -620,8 +621,35 @@ int gemm(const GemmArgs& g, void* ws, size_t ws_bytes, cudaStream_t stream) {
     aligned = aligned && ((a_kc ? g.K : g.M) % 2 == 0) && ((b_kc ? g.K : g.N) % 2 == 0);
 
     // ---- tile / split-K heuristic: minimise modelled time over candidates ----
+    // (memoised per shape and host thread: the candidate loop is up to ~10^3 iterations per call; small sweeps issue
+    // 60+ GEMMs per inner product and are bound by launch costs on both sides -- 2.2 us per launch on the host,
+    // ~4.8 us per dependent small kernel on the device, tools/prof_inner_host.py)
     const int sms = num_sms();
     int best_tile = kTile64x64, best_splits = 1;
+    struct HeurKey {
+        int64_t M, N, K, batch;
+        int aligned, force_tile, force_splits;
+        bool operator==(const HeurKey& o) const {
+            return M == o.M && N == o.N && K == o.K && batch == o.batch && aligned == o.aligned && force_tile == o.force_tile &&
+                   force_splits == o.force_splits;
+        }
+    };
+    struct HeurHash {
+        size_t operator()(const HeurKey& k) const {
+            uint64_t h = 1469598103934665603ull;
+            for (uint64_t v : {uint64_t(k.M), uint64_t(k.N), uint64_t(k.K), uint64_t(k.batch),
+                               uint64_t(k.aligned * 64 + (k.force_tile + 1) * 8), uint64_t(k.force_splits)})
+                h = (h ^ v) * 1099511628211ull;
+            return size_t(h);
+        }
+    };
+    static thread_local std::unordered_map<HeurKey, std::pair<int, int>, HeurHash> heur_cache;
+    const HeurKey hkey{g.M, g.N, g.K, g.batch, aligned ? 1 : 0, g.force_tile, g.force_splits};
+    const auto hit = heur_cache.find(hkey);
+    if (hit != heur_cache.end()) {
+        best_tile = hit->second.first;
+        best_splits = hit->second.second;
+    } else {
     {
         double best_cost = 1e300;
         const int smax_ws = max_splits_for(g.M, g.N, g.batch);
@@ -652,6 +680,9 @@ int gemm(const GemmArgs& g, void* ws, size_t ws_bytes, cudaStream_t stream) {
                 }
             }
         }
+    }
+        if (heur_cache.size() > 4096) heur_cache.clear();
+        heur_cache.emplace(hkey, std::make_pair(best_tile, best_splits));
     }
     int splits = best_splits;
     if (splits > 1) {
