@@ -613,6 +613,19 @@ def run_cfg1_sweep(cpu_budget_s=12.0):
             best = min(best, e0.elapsed_time(e1))
         flops = orc.inner_flops([n] * d, [r] * (d - 1), [r] * (d - 1))
         row = {"d": d, "n": n, "r": r, "gpu_ms": best, "gpu_gflops": flops / (best * 1e-3) / 1e9}
+        # the same point through the drop-in call on numpy cores (upload + sweep + scalar read-back), best of 3
+        if sum(c.nbytes for c in a) <= (1 << 30):
+            from tensor_networks_b200 import algs
+
+            na = algs.TensorNetwork.from_tensor_train(ta)  # numpy cores in the reference's shapes
+            nb_ = algs.TensorNetwork.from_tensor_train(tb)
+            float(na.inner(nb_))
+            t_best = 1e30
+            for _ in range(3):
+                t0 = time.perf_counter()
+                float(na.inner(nb_))
+                t_best = min(t_best, time.perf_counter() - t0)
+            row["dropin_ms"] = 1e3 * t_best
         if cpu_spent < cpu_budget_s:
             t0 = time.perf_counter()
             ref = float(orc.inner(a, b))

@@ -102,3 +102,31 @@ def test_tt_svd_and_errors():
     t = tn.contract()
     have = [i.name for i in t.indices]
     assert np.allclose(np.transpose(t.value, [have.index(n) for n in free]), before, atol=1e-7)
+
+
+def test_dropin_inner_small_host_trains_packed_path():
+    """algs.TensorNetwork.inner on small numpy trains (the points of examples/inner_product_scaling.py) goes through the
+    packed upload (all cores in one pinned buffer, one copy): values as the oracle's, odd core sizes and rank-1 ends
+    included, operands untouched."""
+    from oracle import tt_oracle as orc
+    from tensor_networks_b200 import algs
+    from tensor_networks_b200.types import Index
+
+    np.random.seed(4)
+    for d, n, r in ((20, 20, 10), (12, 5, 5), (6, 7, 3), (2, 9, 4)):
+        idx = [Index(f"x{i}", n) for i in range(d)]
+        a = algs.TensorNetwork.rand_tt(idx, [r] * (d - 1))
+        b = algs.TensorNetwork.rand_tt(idx, [r + 1] * (d - 1))
+        ca = [a.network.nodes[k]["tensor"].value.copy() for k in range(d)]
+        cb = [b.network.nodes[k]["tensor"].value.copy() for k in range(d)]
+        ref = float(orc.inner(orc.as_cores3(ca), orc.as_cores3(cb)))
+        got = a.inner(b)
+        assert isinstance(got, np.ndarray) and got.shape == () and got.dtype == np.float64
+        assert abs(float(got) - ref) <= 1e-12 * abs(ref)
+        assert abs(float(b.inner(a)) - ref) <= 1e-12 * abs(ref)
+        assert all(np.array_equal(a.network.nodes[k]["tensor"].value, ca[k]) for k in range(d))
+    # a network whose free indices differ is not TT-compatible: the reference's attach() + contract() route
+    idx2 = [Index(f"x{i}", 5) for i in range(3)]
+    idx3 = [Index("x0", 5), Index("x1", 5), Index("y", 5)]
+    p, q = algs.TensorNetwork.rand_tt(idx2, [2, 2]), algs.TensorNetwork.rand_tt(idx3, [2, 2])
+    assert not p._tt_compatible(q) and p._tt_compatible(p)
