@@ -9,19 +9,22 @@
 //   * FOUR MMA warps per CTA, warp w owns rows 8w .. 8w+7 of E'^T and runs ALL slices of a core itself, so the sum over
 //     slices stays in its accumulator registers: no cross-warp reduction, no CTA-wide barrier per chunk (the cp.async
 //     kernel meets at 9 barriers per core).  Once per core the warps exchange their rows through a double-buffered
-//     32 x 36 tile (one 128-thread named barrier) and reload the whole environment as 32 B-operand fragments that
+//     32 x 36 tile (one block barrier of the 128 threads) and reload the whole environment as 32 B-operand fragments that
 //     stay in REGISTERS for the next core (the cp.async kernel re-reads them from shared memory for every slice).
 //   * slice boxes arrive by cp.async.bulk.tensor (TMA) in a 3-slot ring guarded by full mbarriers.  There is no copy
 //     warp (registers are allocated per four warps: a fifth warp would cost a third of the budget and the third CTA
 //     per SM) and no empty barrier: a warp that is done with a slot bumps the slot's release counter (acq_rel), and
-//     the warp that arrives last issues the refill at once.  The boxes come from 4-d tensor maps (column, slice, row, item) of the batch storage and
-//     are 36 (B side) and 34 (A side) doubles wide: the columns past the bond rank are TMA zero fill, and the pitches
+//     the warp that arrives last issues the refill at once.  The boxes come from 4-d tensor maps (column, slice, row,
+//     item) of the batch storage and are 36 (B side) and 34 (A side) doubles wide: the columns past the bond rank are TMA zero fill, and the pitches
 //     == 4 (mod 16) and == 2 (mod 8) make the 64-bit and 128-bit fragment loads bank-conflict free without swizzling.
 //     Rows / columns outside a core (bond ranks below 32, the rank-1 first core) are zero fill as well, so any shape
 //     with ranks <= 32 runs the same code; trip counts are trimmed to the real ranks where that saves DMMAs.
 //   * second product: the column-to-fragment map is permuted (a DMMA pair covers columns 16m + 2c and 16m + 2c + 1),
 //     so one 128-bit load fetches the B fragments of two DMMAs and a lane's four results are four adjacent columns.
 // The last core (trailing rank 1) is a 32 x 32 x n weighted sum done with plain FMAs in a fixed order.
+// Sharded batches: the epilogue can store every result straight into all ranks' arrays (peer memory over NVLink), which
+// makes the all-gather of the scalars part of this kernel (PeerScatter, sharding.PeerGather).  Small batches (a single
+// train routed here by inner()) run one CTA per SM with an 11-slot ring.
 #include "batched.cuh"
 
 #include <algorithm>
