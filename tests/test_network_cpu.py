@@ -93,3 +93,42 @@ def test_constructors_host():
     np.random.seed(0)
     t = TensorNetwork.rand_tucker(idx, 2)
     assert sorted(map(str, t.network.nodes)) == ["G0", "G1", "G2", "root"]
+
+
+def test_tt_compatibility_check_host_logic():
+    """Which pairs of networks take the fused TT sweep in TensorNetwork.inner (pytens/algs.py:585-587 semantics are
+    kept for everything else): same free indices node by node, TT core shapes, chain of bonds."""
+    from tensor_networks_b200.algs import Index, Tensor, TensorNetwork, _tt_signature
+
+    idx = [Index(f"x{i}", 4) for i in range(5)]
+    a = TensorNetwork.rand_tt(idx, [2, 3, 3, 2])
+    b = TensorNetwork.rand_tt(idx, [3, 1, 2, 4])
+    assert _tt_signature(a) == idx and a._tt_compatible(b) and b._tt_compatible(a) and a._tt_compatible(a)
+    # a different free index at one node, a different number of nodes, a renamed copy
+    other = list(idx)
+    other[2] = Index("y", 4)
+    assert not a._tt_compatible(TensorNetwork.rand_tt(other, [2, 2, 2, 2]))
+    assert not a._tt_compatible(TensorNetwork.rand_tt(idx[:4], [2, 2, 2]))
+    # same free indices in a different node order: not the same train
+    perm = [idx[1], idx[0]] + idx[2:]
+    assert not a._tt_compatible(TensorNetwork.rand_tt(perm, [2, 2, 2, 2]))
+    # not a chain in the reference's layout: string node names, a star, a 3-d first core
+    named = TensorNetwork()
+    named.add_node("a", Tensor(np.zeros((4, 2)), [idx[0], Index("r1", 2)]))
+    named.add_node("b", Tensor(np.zeros((2, 4)), [Index("r1", 2), idx[1]]))
+    named.add_edge("a", "b")
+    assert _tt_signature(named) is None
+    odd = TensorNetwork()
+    odd.add_node(0, Tensor(np.zeros((1, 4, 2)), [Index("r0", 1), idx[0], Index("r1", 2)]))
+    odd.add_node(1, Tensor(np.zeros((2, 4)), [Index("r1", 2), idx[1]]))
+    odd.add_edge(0, 1)
+    assert _tt_signature(odd) is None
+    # a bond that does not link neighbours
+    broken = TensorNetwork()
+    broken.add_node(0, Tensor(np.zeros((4, 2)), [idx[0], Index("r1", 2)]))
+    broken.add_node(1, Tensor(np.zeros((2, 4, 2)), [Index("q", 2), idx[1], Index("r2", 2)]))
+    broken.add_node(2, Tensor(np.zeros((2, 4)), [Index("r2", 2), idx[2]]))
+    assert _tt_signature(broken) is None
+    # a repeated free index is not a TT over d distinct modes
+    rep = TensorNetwork.rand_tt([idx[0], idx[0], idx[1]], [2, 2])
+    assert not rep._tt_compatible(rep)
