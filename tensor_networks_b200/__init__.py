@@ -11,4 +11,4 @@ from .tt import TensorTrain  # noqa: F401
 from . import _lib  # noqa: F401
 
 __all__ = ["Index", "SVDConfig", "TensorTrain"]
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -38,7 +38,7 @@ inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
 extern "C" {
 
-const char* ttb_version(void) { return "ttb200 0.1.0 (sm_100a, fp64 DMMA)"; }
+const char* ttb_version(void) { return "ttb200 0.2.0 (sm_100a, fp64 DMMA, TMA)"; }
 const char* ttb_last_error(void) { return ttb::last_error_cstr(); }
 uint64_t ttb_launch_count(void) { return ttb::g_launch_count.load(); }
 // debug aid for tools/ (not declared in the public header)
